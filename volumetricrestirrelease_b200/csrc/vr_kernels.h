@@ -1,0 +1,16 @@
+// vr_kernels.h — host-callable launchers of the kernels in vr_kernels.cu.
+#pragma once
+#include "vr_types.h"
+
+namespace vrd {
+cudaError_t uploadScene(const DScene& s, cudaStream_t st);
+cudaError_t launchFeatures(const FrameParams& fp, cudaStream_t st);
+cudaError_t launchInitial(const FrameParams& fp, cudaStream_t st);
+cudaError_t launchTemporal(const FrameParams& fp, cudaStream_t st);
+cudaError_t launchSpatial(const FrameParams& fp, cudaStream_t st);
+cudaError_t launchFinal(const FrameParams& fp, cudaStream_t st);
+cudaError_t launchImportance(float* importance, int dim, int sx, int sy, cudaStream_t st);
+cudaError_t launchImportanceMip(const float* src, float* dst, int d, cudaStream_t st);
+cudaError_t launchResToAos(ResBuf b, vrestir_reservoir* out, int n, cudaStream_t st);
+cudaError_t launchResFromAos(ResBuf b, const vrestir_reservoir* in, int n, cudaStream_t st);
+}

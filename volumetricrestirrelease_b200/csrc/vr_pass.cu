@@ -1,0 +1,814 @@
+// vr_pass.cu — host side of the pass behind the C ABI (include/vrestir.h): option surface, device residency of the
+// scene, reservoir buffers, the per-frame dispatch sequence of VR/VolumetricReSTIR.cpp:303-772, buffer access.
+//
+// B200-first choices made here (details in DESIGN.md):
+//   * reservoir / feature history is kept by rotating three device buffers instead of K4's copy and the two
+//     copyResource calls (VR/VolumetricReSTIR.cpp:629-638,699-718): zero bytes moved per frame;
+//   * the whole scene descriptor lives in __constant__ memory (one 8 KB upload when something changed);
+//   * the atlas of the reuse mip is pinned in L2 with an access-policy window on the pass's stream.
+// There is no CPU fallback anywhere: every entry point that needs the GPU fails with VRESTIR_ERR_CUDA without one.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "vr_host.h"
+#include "vr_kernels.h"
+
+using namespace vrd;
+
+namespace vr {
+static thread_local std::string g_lastError;
+int setError(int code, const std::string& msg) { g_lastError = msg; return code; }
+}  // namespace vr
+using vr::setError;
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e__ = (call);                                                                                  \
+        if (e__ != cudaSuccess) return setError(VRESTIR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+namespace {
+
+struct DevSlot { void* nodes[3] = {nullptr, nullptr, nullptr}; void* child[3] = {nullptr, nullptr, nullptr}; void* atlas = nullptr; size_t atlasBytes = 0; };
+
+struct KeyDesc { const char* name; size_t off; int type; };
+#define K_I(f) {#f, offsetof(vrestir_params, f), 0}
+#define K_U(f) {#f, offsetof(vrestir_params, f), 1}
+#define K_F(f) {#f, offsetof(vrestir_params, f), 2}
+const KeyDesc kKeys[] = {
+    K_I(mMaxBounces), K_I(mEnableTemporalReuse), K_I(mEnableSpatialReuse), K_I(mVertexReuse), K_I(mVertexReuseStartBounce), K_I(mUseReference),
+    K_I(mUseEnvironmentLights), K_I(mUseAnalyticLights), K_I(mUseEmissiveLights), K_I(mBaselineSamplePerPixel), K_I(mVisualizeTotalTransmittance),
+    K_I(mUseSurfaceScene), K_I(mUsePrevVolumeForReproj), K_I(mInitialBaseMipLevel), K_I(mInitialM), K_I(mInitialLightSamples), K_I(mInitialLightingMipLevel),
+    K_I(mInitialVisibilityUseLinearSampler), K_I(mInitialLightingUseLinearSampler), K_U(mInitialLightingTrackingMethod), K_F(mInitialVisibilityTStepScale),
+    K_F(mInitialLightingTStepScale), K_I(mInitialUseRussianRoulette), K_I(mInitialUseCoarserGridForIndirectBounce), K_F(mTemporalReuseMThreshold),
+    K_U(mTemporalReprojectionMode), K_U(mTemporalMISMethod), K_I(mTemporalReprojectionMipLevel), K_I(mSpatialReuseRounds), K_I(mSpatialVisibilityMipLevel),
+    K_I(mSpatialLightingMipLevel), K_I(mSpatialVisibilityUseLinearSampler), K_I(mSpatialLightingUseLinearSampler), K_F(mSpatialVisibilityTStepScale),
+    K_F(mSpatialLightingTStepScale), K_U(mSpatialVisibilityTrackingMethod), K_U(mSpatialLightingTrackingMethod), K_U(mRandomSamplerType), K_F(mSampleRadius),
+    K_I(mSpatialSampleCount), K_I(mEnableVisibilitySimilarityRejection), K_U(mSpatialMISMethod), K_I(mFinalLightSamples), K_I(mFinalVisibilitySamples),
+    K_U(mFinalVisibilityTrackingMethod), K_U(mFinalLightTrackingMethod), K_U(mFinalRandomSamplerType), K_F(mFinalTStepScale)};
+
+}  // namespace
+
+struct vrestir_pass {
+    int device = 0;
+    vrestir_params P{};
+    bool mOutputMotionVec = false, mFreezeFrame = false, mRandomizeFrameSeed = false;
+    float densityExtra = -1.f, albedoExtra = -1.f, anisotropyExtra = -1.f;
+    int envSamplerType = VRESTIR_ENV_SAMPLER_HIERARCHICAL;
+    unsigned randState = 1;
+
+    DScene scene{};
+    vrestir_volume_desc volBase{};
+    bool sceneDirty = true, haveVolume = false, haveCamera = false;
+    DevSlot dslots[VRESTIR_MAX_SLOTS];
+    void* d_lut = nullptr; void* d_lutPrev = nullptr;
+    vrestir_camera cam{};
+    // env
+    void* d_env = nullptr; float* d_importance = nullptr; size_t importanceCount = 0;
+    float* d_envAliasThr = nullptr; uint32_t* d_envAliasRedirect = nullptr;
+    std::vector<float> envAliasThr; std::vector<uint32_t> envAliasRedirect;
+    // lights
+    void* d_lights = nullptr; void* d_tris = nullptr; void* d_alias = nullptr; void* d_aliasWeights = nullptr;
+    std::vector<uint32_t> aliasItems; std::vector<float> aliasWeights; float aliasWeightSum = 0.f;
+
+    int W = 0, H = 0, rowBegin = 0, rowEnd = 0;
+    int allocW = 0, allocH = 0, allocB = 0;
+    float4* res[3] = {nullptr, nullptr, nullptr};
+    float3* ext[3] = {nullptr, nullptr, nullptr};
+    int2* feat[2] = {nullptr, nullptr};
+    float4* refColor = nullptr;
+    int ia = 0, ib = 1, it = 2;        // physical indices of ping-pong buffers 0/1 and the temporal history
+    int finalPhys = 0;                 // physical buffer holding the final reservoirs of the frame in flight
+    int featCur = 0, featPrev = 1;
+    int mFrameCount = 0, mTemporalSampleAccumulated = 0; bool mOptionsChanged = true;
+    cudaEvent_t ev[8] = {};
+    bool evValid[8] = {};
+    cudaStream_t hostStream = nullptr;
+    float4* d_hostColor = nullptr; float2* d_hostMvec = nullptr; size_t hostColorPixels = 0;
+    uint64_t launches = 0;
+    vrestir_timings timings{};
+    void* persistBase = nullptr; size_t persistBytes = 0;
+};
+
+namespace {
+
+size_t N(const vrestir_pass* p) { return (size_t)p->W * p->H; }
+ResBuf resView(const vrestir_pass* p, int phys) { ResBuf b; b.p0 = p->res[phys]; b.p1 = p->res[phys] + N(p); return b; }
+
+int ensureBuffers(vrestir_pass* p) {
+    const int B = p->P.mMaxBounces;
+    if (p->allocW == p->W && p->allocH == p->H && p->allocB == B && p->res[0]) return VRESTIR_OK;
+    const size_t n = N(p);
+    for (int i = 0; i < 3; i++) { if (p->res[i]) cudaFree(p->res[i]); if (p->ext[i]) cudaFree(p->ext[i]); p->res[i] = nullptr; p->ext[i] = nullptr; }
+    for (int i = 0; i < 2; i++) { if (p->feat[i]) cudaFree(p->feat[i]); p->feat[i] = nullptr; }
+    if (p->refColor) { cudaFree(p->refColor); p->refColor = nullptr; }
+    for (int i = 0; i < 3; i++) {
+        CK(cudaMalloc(&p->res[i], n * 32)); CK(cudaMemset(p->res[i], 0, n * 32));
+        if (B > 1) { CK(cudaMalloc(&p->ext[i], n * (size_t)(B - 1) * 12)); CK(cudaMemset(p->ext[i], 0, n * (size_t)(B - 1) * 12)); }
+    }
+    for (int i = 0; i < 2; i++) { CK(cudaMalloc(&p->feat[i], n * 8)); CK(cudaMemset(p->feat[i], 0, n * 8)); }
+    CK(cudaMalloc(&p->refColor, n * 16)); CK(cudaMemset(p->refColor, 0, n * 16));
+    p->allocW = p->W; p->allocH = p->H; p->allocB = B;
+    p->ia = 0; p->ib = 1; p->it = 2; p->finalPhys = 0; p->featCur = 0; p->featPrev = 1;
+    return VRESTIR_OK;
+}
+
+void freeSlot(DevSlot& d) {
+    for (int l = 0; l < 3; l++) { if (d.nodes[l]) cudaFree(d.nodes[l]); if (d.child[l]) cudaFree(d.child[l]); d.nodes[l] = d.child[l] = nullptr; }
+    if (d.atlas) cudaFree(d.atlas);
+    d.atlas = nullptr; d.atlasBytes = 0;
+}
+
+int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
+    DevSlot& d = p->dslots[slot];
+    freeSlot(d);
+    DSlot& s = p->scene.slots[slot];
+    memset(&s, 0, sizeof(s));
+    if (!g.valid) return VRESTIR_OK;
+    if (g.top_lev < 1 || g.top_lev > 2) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "top_lev must be 1 or 2");
+    s.valid = 1; s.top_lev = g.top_lev;
+    for (int l = 0; l < 3; l++) {
+        s.dim[l] = g.dim[l]; s.res[l] = g.res[l]; s.vdel[l] = g.vdel[l];
+        if (g.node_count[l] && g.nodes[l]) {
+            CK(cudaMalloc(&d.nodes[l], (size_t)g.node_count[l] * sizeof(vrestir_node)));
+            CK(cudaMemcpy(d.nodes[l], g.nodes[l], (size_t)g.node_count[l] * sizeof(vrestir_node), cudaMemcpyHostToDevice));
+        }
+        if (g.childlist_count[l] && g.childlist[l]) {
+            CK(cudaMalloc(&d.child[l], (size_t)g.childlist_count[l] * 4));
+            CK(cudaMemcpy(d.child[l], g.childlist[l], (size_t)g.childlist_count[l] * 4, cudaMemcpyHostToDevice));
+        }
+        s.nodes[l] = (const vrestir_node*)d.nodes[l]; s.child[l] = (const uint32_t*)d.child[l]; s.childCount[l] = g.childlist_count[l];
+    }
+    for (int i = 0; i < 3; i++) { s.bmin[i] = g.bmin[i]; s.bmax[i] = g.bmax[i]; }
+    memcpy(s.w2m, g.world_to_medium, 64);
+    s.max_value = g.max_value; s.compress_scale = g.compress_scale; s.format = g.atlas_format; s.channels = g.atlas_channels;
+    const size_t bytes = (size_t)g.brick_count * g.atlas_channels * VRESTIR_BRICK_VOXELS * (g.atlas_format == VRESTIR_ATLAS_UNORM8 ? 1 : 4);
+    if (bytes) {
+        CK(cudaMalloc(&d.atlas, bytes + 16));
+        CK(cudaMemcpy(d.atlas, g.atlas, bytes, cudaMemcpyHostToDevice));
+        d.atlasBytes = bytes;
+    }
+    s.atlas = d.atlas;
+    return VRESTIR_OK;
+}
+
+void applyOverrides(vrestir_pass* p) {   // VR/VolumetricReSTIR.cpp:211-235
+    vrestir_volume_desc v = p->volBase;
+    if (p->densityExtra > 0) v.densityScaleFactor = p->densityExtra;
+    if (p->anisotropyExtra > 0) v.PhaseFunctionConstantG = p->anisotropyExtra;
+    if (p->albedoExtra > 0) for (int i = 0; i < 3; i++) { v.sigma_s[i] = v.sigma_t * p->albedoExtra; v.sigma_a[i] = v.sigma_t - v.sigma_s[i]; }
+    v.usePrevGridForReproj = p->P.mUsePrevVolumeForReproj;
+    if (memcmp(&v, &p->scene.vol, sizeof(v)) != 0) { p->scene.vol = v; p->sceneDirty = true; }
+}
+
+SamplingOptions mkOpt(uint32_t vt, uint32_t lt, int ls, int lm, int vs, int vm, int vl, int ll, float vts, float lts, const vrestir_params& m) {
+    SamplingOptions o;
+    o.visibilityTrackingMethod = vt; o.lightingTrackingMethod = lt; o.lightSamples = ls; o.lightingMipLevel = lm; o.visibilitySamples = vs; o.visibilityMipLevel = vm;
+    o.visibilityUseLinearSampler = vl; o.lightingUseLinearSampler = ll; o.visibilityTStepScale = vts; o.lightingTStepScale = lts;
+    o.useEnvironmentLights = m.mUseEnvironmentLights; o.useAnalyticLights = m.mUseAnalyticLights; o.useEmissiveLights = m.mUseEmissiveLights;
+    o.vertexReuseStartBounce = m.mVertexReuseStartBounce;
+    return o;
+}
+
+// F/Utils/Math/MathHelpers.slang:178-197,356-361; VR/SpatialReuse.cs.slang:64-81 — offsets depend only on (sampleId, frame seed): host-side, fp64 stays off the GPU
+float radicalInverse(uint32_t i) {
+    i = (i & 0x55555555u) << 1 | (i & 0xAAAAAAAAu) >> 1; i = (i & 0x33333333u) << 2 | (i & 0xCCCCCCCCu) >> 2;
+    i = (i & 0x0F0F0F0Fu) << 4 | (i & 0xF0F0F0F0u) >> 4; i = (i & 0x00FF00FFu) << 8 | (i & 0xFF00FF00u) >> 8;
+    i = (i << 16) | (i >> 16);
+    return (float)i * 2.3283064365386963e-10f;
+}
+int f2iHost(float v) { if (std::isnan(v)) return 0; if (v >= 2147483648.f) return INT32_MAX; if (v <= -2147483648.f) return INT32_MIN; return (int)v; }
+int2 neighborOffset(const vrestir_params& m, int sampleId, int frameId) {
+    float ux, uy;
+    if (m.mRandomSamplerType == VRESTIR_SAMPLER_HAMMERSLEY) { ux = (float)sampleId / (float)m.mSpatialSampleCount; uy = radicalInverse((uint32_t)sampleId); }
+    else if (sampleId == 0) { ux = 0; uy = 0; }
+    else {
+        double mult = (double)(frameId * m.mSpatialSampleCount + sampleId);
+        double a = 0.754877669 * mult, b = 0.569840296 * mult;
+        ux = (float)(a - std::floor(a)); uy = (float)(b - std::floor(b));
+    }
+    // sample_disk: the two libm calls below run on the host for every caller (oracle and product do the same)
+    float r = sqrtf(ux), phi = 6.28318530717958647693f * uy;
+    return make_int2(f2iHost(m.mSampleRadius * (r * cosf(phi))), f2iHost(m.mSampleRadius * (r * sinf(phi))));
+}
+
+void buildFrameParams(vrestir_pass* p, FrameParams& fp, float* out_color, float* out_mvec) {
+    const vrestir_params& m = p->P;
+    memset(&fp, 0, sizeof(fp));
+    fp.W = p->W; fp.H = p->H; fp.rowBegin = p->rowBegin; fp.rowEnd = p->rowEnd;
+    fp.frameCount = p->mFrameCount;
+    fp.numTotalRounds = (m.mEnableSpatialReuse ? m.mSpatialReuseRounds : 0) + (m.mEnableTemporalReuse ? 1 : 0) + 1 + 1;   // VR/VolumetricReSTIR.cpp:452-453
+    fp.maxBounces = m.mMaxBounces;
+    fp.useReference = m.mUseReference; fp.baselineSpp = m.mBaselineSamplePerPixel; fp.initialM = m.mInitialM;
+    fp.useRussianRoulette = m.mInitialUseRussianRoulette; fp.noReuse = !m.mEnableSpatialReuse && !m.mEnableTemporalReuse;
+    fp.useCoarserGrid = m.mInitialUseCoarserGridForIndirectBounce;
+    fp.visualizeTransmittance = m.mVisualizeTotalTransmittance; fp.outputMotionVec = p->mOutputMotionVec;
+    fp.temporalMThreshold = m.mTemporalReuseMThreshold; fp.temporalMIS = m.mTemporalMISMethod; fp.reprojectionMode = m.mTemporalReprojectionMode;
+    fp.reprojectionMip = m.mTemporalReprojectionMipLevel;
+    fp.spatialRounds = m.mSpatialReuseRounds; fp.roundOffset = (m.mEnableTemporalReuse ? 1 : 0) + 1; fp.spatialMIS = m.mSpatialMISMethod; fp.sampleCount = m.mSpatialSampleCount;
+    // VR/VolumetricReSTIR.cpp:457-496
+    fp.initial = mkOpt(VRESTIR_ANALYTIC_TRACKING, m.mInitialLightingTrackingMethod, m.mInitialLightSamples, m.mInitialLightingMipLevel, 1,
+                       m.mInitialVisibilityUseLinearSampler ? m.mInitialBaseMipLevel : m.mInitialBaseMipLevel + VRESTIR_NUM_MAX_MIPS, m.mInitialVisibilityUseLinearSampler,
+                       m.mInitialLightingUseLinearSampler, m.mInitialVisibilityTStepScale, m.mInitialLightingTStepScale, m);
+    fp.spatial = mkOpt(m.mSpatialVisibilityTrackingMethod, m.mSpatialLightingTrackingMethod, 1, m.mSpatialLightingMipLevel, 1, m.mSpatialVisibilityMipLevel,
+                       m.mSpatialVisibilityUseLinearSampler, m.mSpatialLightingUseLinearSampler, m.mSpatialVisibilityTStepScale, m.mSpatialLightingTStepScale, m);
+    const bool lightDet = m.mFinalLightTrackingMethod == VRESTIR_ANALYTIC_TRACKING || m.mFinalLightTrackingMethod == VRESTIR_RAY_MARCHING;
+    const bool visDet = m.mFinalVisibilityTrackingMethod == VRESTIR_ANALYTIC_TRACKING || m.mFinalVisibilityTrackingMethod == VRESTIR_RAY_MARCHING;
+    fp.fin = mkOpt(m.mFinalVisibilityTrackingMethod, m.mFinalLightTrackingMethod, lightDet ? 1 : m.mFinalLightSamples, 0, visDet ? 1 : m.mFinalVisibilitySamples, 0, 1, 1,
+                   m.mFinalTStepScale, m.mFinalTStepScale, m);
+    fp.features = p->feat[p->featCur]; fp.featuresTemporal = p->feat[p->featPrev];
+    fp.refColor = p->refColor;
+    fp.outColor = (float4*)out_color; fp.outMvec = (float2*)out_mvec;
+}
+
+int syncScene(vrestir_pass* p, cudaStream_t st) {
+    applyOverrides(p);
+    // camera
+    DScene& s = p->scene;
+    auto f3of = [](const float* a) { return make_float3(a[0], a[1], a[2]); };
+    s.camPos = f3of(p->cam.posW); s.camU = f3of(p->cam.cameraU); s.camV = f3of(p->cam.cameraV); s.camW = f3of(p->cam.cameraW);
+    s.envSamplerType = p->envSamplerType;
+    // the constant bank is shared by every pass of this process on this device: upload whenever anything may differ
+    static thread_local const vrestir_pass* lastOwner = nullptr;
+    static thread_local DScene lastScene;
+    if (lastOwner != p || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0) {
+        CK(uploadScene(s, st));
+        // the async copy reads `s` at enqueue time only when the source is pageable (staged); keep a private copy alive
+        lastScene = s; lastOwner = p; p->sceneDirty = false;
+    }
+    return VRESTIR_OK;
+}
+
+void recordEv(vrestir_pass* p, int i, cudaStream_t st) { if (!p->ev[i]) cudaEventCreate(&p->ev[i]); cudaEventRecord(p->ev[i], st); p->evValid[i] = true; }
+
+int setPersistingWindow(vrestir_pass* p, cudaStream_t st) {
+    // "a coarse mip pinned in B200's L2": the atlas of the reuse mip (mSpatialVisibilityMipLevel) gets a persisting
+    // access-policy window on the stream that runs K2/K3.
+    int slot = p->P.mSpatialVisibilityMipLevel;
+    if (slot < 0 || slot >= VRESTIR_MAX_SLOTS || !p->dslots[slot].atlas) return VRESTIR_OK;
+    void* base = p->dslots[slot].atlas; size_t bytes = p->dslots[slot].atlasBytes;
+    if (base == p->persistBase && bytes == p->persistBytes) return VRESTIR_OK;
+    int maxWin = 0, maxPersist = 0;
+    cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, p->device);
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
+    if (maxWin <= 0 || maxPersist <= 0) return VRESTIR_OK;
+    size_t want = std::min(bytes, (size_t)maxPersist);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = base;
+    attr.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)maxWin);
+    attr.accessPolicyWindow.hitRatio = bytes <= want ? 1.0f : (float)((double)want / (double)bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+    p->persistBase = base; p->persistBytes = bytes;
+    return VRESTIR_OK;
+}
+
+int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, cudaStream_t st) {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    if (!p->haveVolume || !p->haveCamera || p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "volume/camera/frame not set");
+    const vrestir_params& m = p->P;
+    if (m.mUseSurfaceScene) return setError(VRESTIR_ERR_UNSUPPORTED, "mUseSurfaceScene: surface scenes are outside the hot-path scope (SURVEY.md 8f rank 4)");
+    if (m.mVertexReuse) return setError(VRESTIR_ERR_UNSUPPORTED, "mVertexReuse is not implemented");
+    if (m.mMaxBounces < 1 || m.mMaxBounces > VRESTIR_MAX_BOUNCES) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mMaxBounces must be 1..4");
+    if (m.mSpatialSampleCount < 1 || m.mSpatialSampleCount > 32) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mSpatialSampleCount must be 1..32");
+    if (m.mInitialM < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mInitialM must be >= 1");
+    if (m.mUseEnvironmentLights && !p->scene.haveEnv) return setError(VRESTIR_ERR_NOT_READY, "mUseEnvironmentLights without an env map");
+    if (m.mUseAnalyticLights && p->scene.lightCount == 0) return setError(VRESTIR_ERR_NOT_READY, "mUseAnalyticLights without lights");
+    {   // every mip the options name must be bound
+        auto ok = [&](int slot) { return slot >= 0 && slot < VRESTIR_MAX_SLOTS && p->scene.slots[slot].valid; };
+        const int initVis = m.mInitialVisibilityUseLinearSampler ? m.mInitialBaseMipLevel : m.mInitialBaseMipLevel + VRESTIR_NUM_MAX_MIPS;
+        const bool reuse = m.mEnableSpatialReuse || m.mEnableTemporalReuse;
+        bool good = ok(0) && ok(m.mInitialLightingMipLevel) && (reuse ? ok(initVis) : true) && ok(m.mSpatialVisibilityMipLevel) && ok(m.mSpatialLightingMipLevel) &&
+                    (m.mEnableTemporalReuse && m.mTemporalReprojectionMode != VRESTIR_REPROJECTION_NONE ? ok(VRESTIR_NUM_MAX_MIPS + m.mTemporalReprojectionMipLevel) : true);
+        if (!good) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "an option names a mip level that the volume does not have");
+    }
+    CK(cudaSetDevice(p->device));
+    int rc = ensureBuffers(p); if (rc) return rc;
+    if (stage == 0 && p->mOptionsChanged) {   // VR/VolumetricReSTIR.cpp:349-359
+        if (p->mRandomizeFrameSeed) p->mFrameCount = rand_r(&p->randState) % 65536; else p->mFrameCount = 0;
+        p->mTemporalSampleAccumulated = 0; p->mOptionsChanged = false;
+    }
+    rc = syncScene(p, st); if (rc) return rc;
+    FrameParams fp; buildFrameParams(p, fp, out_color, out_mvec);
+    const bool active = !p->mFreezeFrame;
+    switch (stage) {
+        case 0:
+            recordEv(p, 0, st);
+            setPersistingWindow(p, st);
+            if (active && !m.mUseReference) { CK(launchFeatures(fp, st)); p->launches++; }
+            recordEv(p, 1, st);
+            break;
+        case 1:
+            if (active) {
+                fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
+                CK(launchInitial(fp, st)); p->launches++;
+                p->finalPhys = p->ia;
+            }
+            recordEv(p, 2, st);
+            break;
+        case 2:
+            if (active && !m.mUseReference && m.mEnableTemporalReuse) {
+                if (p->mTemporalSampleAccumulated != 0) {   // gIsFirstFrame skips the kernel (VR/TemporalReuse.cs.slang:93)
+                    fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
+                    fp.temporal = resView(p, p->it); fp.extTemporal = p->ext[p->it];
+                    CK(launchTemporal(fp, st)); p->launches++;
+                }
+                p->finalPhys = p->ia;
+            }
+            recordEv(p, 3, st);
+            break;
+        case 3:
+            if (active && !m.mUseReference && m.mEnableSpatialReuse) {
+                const int in = (arg % 2 == 0) ? p->ia : p->ib, out = (arg % 2 == 0) ? p->ib : p->ia;
+                fp.cur = resView(p, in); fp.out = resView(p, out); fp.extCur = p->ext[in]; fp.extOut = p->ext[out];
+                fp.roundId = arg;
+                const int r2TimeSeed = ((m.mSpatialReuseRounds + 1) * p->mFrameCount + arg) % 16;   // VR/SpatialReuse.cs.slang:109
+                for (int s = 0; s < m.mSpatialSampleCount; s++) fp.offsets[s] = neighborOffset(m, s, r2TimeSeed);
+                CK(launchSpatial(fp, st)); p->launches++;
+                p->finalPhys = out;
+            }
+            if (!(m.mEnableSpatialReuse && arg + 1 < m.mSpatialReuseRounds)) recordEv(p, 4, st);
+            break;
+        case 4:
+            // K4 CopyReservoirs / copyResource(temporal <- cur): the final buffer *becomes* the history, the old history
+            // takes over its ping-pong role.  No bytes move.
+            if (active && !m.mUseReference && m.mEnableTemporalReuse) {
+                const int f = p->finalPhys, oldT = p->it;
+                if (f == p->ia) p->ia = oldT; else if (f == p->ib) p->ib = oldT;
+                p->it = f;
+            }
+            recordEv(p, 5, st);
+            break;
+        case 5:
+            fp.cur = resView(p, p->finalPhys); fp.extCur = p->ext[p->finalPhys];
+            if (p->mFreezeFrame) fp.frameCount = p->mFrameCount - 1;
+            if (!out_color) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "out_color is null");
+            CK(launchFinal(fp, st)); p->launches++;
+            recordEv(p, 6, st);
+            break;
+        case 6: {   // VR/VolumetricReSTIR.cpp:765-772 (+ :636 feature history, as a swap)
+            if (active && !m.mUseReference && m.mEnableTemporalReuse) std::swap(p->featCur, p->featPrev);
+            p->mTemporalSampleAccumulated = 1;
+            memcpy(p->scene.prevView, p->cam.viewMat, 64); memcpy(p->scene.prevProj, p->cam.projMat, 64);
+            p->scene.prevU = p->scene.camU; p->scene.prevV = p->scene.camV; p->scene.prevW = p->scene.camW; p->scene.prevPos = p->scene.camPos;
+            p->sceneDirty = true;
+            if (!p->mFreezeFrame) p->mFrameCount++;
+            break;
+        }
+        default: return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad stage");
+    }
+    return VRESTIR_OK;
+}
+
+// F/Utils/Sampling/AliasTable.cpp:46-126 (std::mt19937 seeded with 123 as in EmissivePowerSampler.cpp:76)
+void buildAliasTable(std::vector<float> weights, std::vector<uint32_t>& itemsOut, float& weightSumOut) {
+    const uint32_t count = (uint32_t)weights.size();
+    std::mt19937 rng(123);
+    double weightSum = 0.0;
+    for (float f : weights) weightSum += f;
+    double factor = count / weightSum;
+    for (float& f : weights) f = (float)(f * factor);
+    std::vector<uint32_t> permutation(count);
+    for (uint32_t i = 0; i < count; ++i) permutation[i] = i;
+    std::sort(permutation.begin(), permutation.end(), [&](uint32_t a, uint32_t b) { return weights[a] < weights[b]; });
+    std::vector<float> thresholds(count);
+    std::vector<uint32_t> redirect(count);
+    uint32_t head = 0, tail = count - 1;
+    if (count == 1) { thresholds[0] = 1.f; redirect[0] = 0; }
+    while (head != tail) {
+        int i = permutation[head], j = permutation[tail];
+        thresholds[i] = weights[i];
+        redirect[i] = j;
+        weights[j] -= 1.f - weights[i];
+        if (head == tail - 1) { thresholds[j] = 1.f; redirect[j] = j; break; }
+        else if (weights[j] < 1.f) { std::swap(permutation[head], permutation[tail]); tail--; }
+        else head++;
+    }
+    for (uint32_t i = 0; i < count; ++i) permutation[i] = i;
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t dst = i + ((uint32_t)rng() % (count - i));
+        std::swap(thresholds[i], thresholds[dst]); std::swap(redirect[i], redirect[dst]); std::swap(permutation[i], permutation[dst]);
+    }
+    itemsOut.resize((size_t)count * 4);
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t tb; memcpy(&tb, &thresholds[i], 4);
+        itemsOut[i * 4 + 0] = tb; itemsOut[i * 4 + 1] = redirect[i]; itemsOut[i * 4 + 2] = permutation[i]; itemsOut[i * 4 + 3] = 0;
+    }
+    weightSumOut = (float)weightSum;
+}
+
+// Vose alias table over the finest importance mip (env-map alias sampling, north star); threshold = P(keep own texel)
+void buildEnvAlias(const float* w, uint32_t count, std::vector<float>& thr, std::vector<uint32_t>& redirect) {
+    thr.assign(count, 1.f); redirect.resize(count);
+    double sum = 0; for (uint32_t i = 0; i < count; i++) sum += w[i];
+    std::vector<double> q(count);
+    std::vector<uint32_t> small, large;
+    for (uint32_t i = 0; i < count; i++) { q[i] = sum > 0 ? (double)w[i] * count / sum : 1.0; redirect[i] = i; (q[i] < 1.0 ? small : large).push_back(i); }
+    while (!small.empty() && !large.empty()) {
+        uint32_t s = small.back(); small.pop_back();
+        uint32_t l = large.back();
+        thr[s] = (float)q[s]; redirect[s] = l;
+        q[l] -= 1.0 - q[s];
+        if (q[l] < 1.0) { large.pop_back(); small.push_back(l); }
+    }
+    for (uint32_t i : small) thr[i] = 1.f;
+    for (uint32_t i : large) thr[i] = 1.f;
+}
+
+}  // namespace
+
+// ================================================================================================ C API
+extern "C" {
+
+const char* vrestir_last_error(void) { return vr::g_lastError.c_str(); }
+const char* vrestir_version(void) { return "vrestir-b200 0.1 (sm_100a)"; }
+
+void vrestir_default_params(vrestir_params* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->mMaxBounces = 1; o->mEnableTemporalReuse = 1; o->mEnableSpatialReuse = 1; o->mVertexReuse = 0; o->mVertexReuseStartBounce = 1; o->mUseReference = 0;
+    o->mUseEnvironmentLights = 1; o->mUseAnalyticLights = 0; o->mUseEmissiveLights = 0; o->mBaselineSamplePerPixel = 1; o->mVisualizeTotalTransmittance = 0;
+    o->mUseSurfaceScene = 0; o->mUsePrevVolumeForReproj = 1;
+    o->mInitialBaseMipLevel = 1; o->mInitialM = 4; o->mInitialLightSamples = 1; o->mInitialLightingMipLevel = 2; o->mInitialVisibilityUseLinearSampler = 0;
+    o->mInitialLightingUseLinearSampler = 1; o->mInitialLightingTrackingMethod = VRESTIR_RAY_MARCHING; o->mInitialVisibilityTStepScale = 1.f;
+    o->mInitialLightingTStepScale = 2.f; o->mInitialUseRussianRoulette = 1; o->mInitialUseCoarserGridForIndirectBounce = 1;
+    o->mTemporalReuseMThreshold = 4.f; o->mTemporalReprojectionMode = VRESTIR_REPROJECTION_LINEAR; o->mTemporalMISMethod = VRESTIR_MIS_TALBOT; o->mTemporalReprojectionMipLevel = 1;
+    o->mSpatialReuseRounds = 1; o->mSpatialVisibilityMipLevel = 1; o->mSpatialLightingMipLevel = 1; o->mSpatialVisibilityUseLinearSampler = 1; o->mSpatialLightingUseLinearSampler = 1;
+    o->mSpatialVisibilityTStepScale = 1.f; o->mSpatialLightingTStepScale = 1.f; o->mSpatialVisibilityTrackingMethod = VRESTIR_RAY_MARCHING;
+    o->mSpatialLightingTrackingMethod = VRESTIR_RAY_MARCHING; o->mRandomSamplerType = VRESTIR_SAMPLER_R2; o->mSampleRadius = 10.f; o->mSpatialSampleCount = 4;
+    o->mEnableVisibilitySimilarityRejection = 0; o->mSpatialMISMethod = VRESTIR_MIS_TALBOT;
+    o->mFinalLightSamples = 1; o->mFinalVisibilitySamples = 1; o->mFinalVisibilityTrackingMethod = VRESTIR_ANALYTIC_TRACKING; o->mFinalLightTrackingMethod = VRESTIR_ANALYTIC_TRACKING;
+    o->mFinalRandomSamplerType = VRESTIR_SAMPLER_R2; o->mFinalTStepScale = 0.2f;
+}
+
+int vrestir_create(const vrestir_params* params, int device, vrestir_pass** out) {
+    if (!out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null out");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return setError(VRESTIR_ERR_CUDA, std::string("no CUDA device: the VolumetricReSTIR pass has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= count) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad device index");
+    CK(cudaSetDevice(device));
+    auto* p = new vrestir_pass();
+    p->device = device;
+    if (params) p->P = *params; else vrestir_default_params(&p->P);
+    memset(&p->scene, 0, sizeof(p->scene));
+    *out = p;
+    return VRESTIR_OK;
+}
+
+int vrestir_destroy(vrestir_pass* p) {
+    if (!p) return VRESTIR_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (auto& d : p->dslots) freeSlot(d);
+    for (int i = 0; i < 3; i++) { if (p->res[i]) cudaFree(p->res[i]); if (p->ext[i]) cudaFree(p->ext[i]); }
+    for (int i = 0; i < 2; i++) if (p->feat[i]) cudaFree(p->feat[i]);
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->hostStream) cudaStreamDestroy(p->hostStream);
+    delete p;
+    return VRESTIR_OK;
+}
+
+int vrestir_set_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
+    if (!p || !g) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    if (!g->slots[0].valid) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "slot 0 (density mip 0) must be valid");
+    for (int s = 0; s < VRESTIR_MAX_SLOTS; s++) { int rc = uploadSlot(p, s, g->slots[s]); if (rc) return rc; }
+    p->volBase = g->volume;
+    if (p->d_lut) { cudaFree(p->d_lut); p->d_lut = nullptr; }
+    if (g->blackbody_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, g->blackbody_lut, 2048, cudaMemcpyHostToDevice)); }
+    p->scene.lut = (const float4*)p->d_lut;
+    p->haveVolume = true; p->sceneDirty = true; p->mOptionsChanged = true; p->persistBase = nullptr;
+    applyOverrides(p);
+    return VRESTIR_OK;
+}
+
+int vrestir_advance_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
+    if (!p || !g || !p->haveVolume) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "advance_volume before set_volume");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    auto moveSlot = [&](int from, int to) {
+        freeSlot(p->dslots[to]);
+        p->dslots[to] = p->dslots[from]; p->dslots[from] = DevSlot{};
+        p->scene.slots[to] = p->scene.slots[from]; memset(&p->scene.slots[from], 0, sizeof(DSlot));
+    };
+    for (int i = 0; i < VRESTIR_NUM_MAX_MIPS; i++) if (VRESTIR_PREV_DENSITY_GRID_OFFSET + i < VRESTIR_MAX_SLOTS) moveSlot(i, VRESTIR_PREV_DENSITY_GRID_OFFSET + i);
+    moveSlot(VRESTIR_TEMPERATURE_GRID_ID, VRESTIR_TEMPERATURE_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
+    moveSlot(VRESTIR_VELOCITY_GRID_ID, VRESTIR_VELOCITY_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
+    const int lastHasEmission = p->volBase.hasEmission;
+    for (int s = 0; s < VRESTIR_PREV_DENSITY_GRID_OFFSET - 1; s++) { int rc = uploadSlot(p, s, g->slots[s]); if (rc) return rc; }
+    p->volBase = g->volume; p->volBase.lastFrameHasEmission = lastHasEmission; p->volBase.hasAnimation = 1;
+    if (g->blackbody_lut && !p->d_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, g->blackbody_lut, 2048, cudaMemcpyHostToDevice)); p->scene.lut = (const float4*)p->d_lut; }
+    p->sceneDirty = true; p->persistBase = nullptr;
+    applyOverrides(p);
+    return VRESTIR_OK;
+}
+
+int vrestir_set_camera(vrestir_pass* p, const vrestir_camera* cam) {
+    if (!p || !cam) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    p->cam = *cam; p->haveCamera = true; p->sceneDirty = true;
+    return VRESTIR_OK;
+}
+
+int vrestir_set_envmap(vrestir_pass* p, const vrestir_envmap_desc* env) {
+    if (!p || !env || !env->texels || env->width < 1 || env->height < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad env map");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    if (p->d_env) cudaFree(p->d_env);
+    const size_t bytes = (size_t)env->width * env->height * 16;
+    CK(cudaMalloc(&p->d_env, bytes));
+    CK(cudaMemcpy(p->d_env, env->texels, bytes, cudaMemcpyHostToDevice));
+    DScene& s = p->scene;
+    s.haveEnv = 1; s.envW = env->width; s.envH = env->height; s.envTexels = (const float4*)p->d_env;
+    s.envIntensity = env->intensity; s.envTint = make_float3(env->tint[0], env->tint[1], env->tint[2]);
+    memcpy(s.envT, env->transform, 36); memcpy(s.envInvT, env->invTransform, 36); memcpy(s.envPrevT, env->prevTransform, 36); memcpy(s.envPrevInvT, env->prevInvTransform, 36);
+    // K6: importance map 512^2, 64 spp/texel, + mip chain (EnvMapSampler.cpp:83-116)
+    const int dim = 512, spp = 64;
+    int mips = 0; for (int d = dim; d >= 1; d >>= 1) mips++;
+    size_t total = 0; for (int i = 0; i < mips; i++) { s.impOffset[i] = (unsigned)total; total += (size_t)(dim >> i) * (dim >> i); }
+    s.impDim = dim; s.impBaseMip = mips - 1;
+    if (p->d_importance) cudaFree(p->d_importance);
+    CK(cudaMalloc(&p->d_importance, total * 4));
+    p->importanceCount = total;
+    s.importance = p->d_importance;
+    CK(uploadScene(s, 0)); CK(cudaDeviceSynchronize());
+    const int sx = std::max(1, (int)std::sqrt((double)spp)), sy = spp / sx;
+    CK(launchImportance(p->d_importance, dim, sx, sy, 0)); p->launches++;
+    for (int mip = 1; mip < mips; mip++) { CK(launchImportanceMip(p->d_importance + s.impOffset[mip - 1], p->d_importance + s.impOffset[mip], dim >> mip, 0)); p->launches++; }
+    CK(cudaDeviceSynchronize());
+    // alias table over the finest mip (used when mEnvSamplerType == VRESTIR_ENV_SAMPLER_ALIAS)
+    std::vector<float> base((size_t)dim * dim);
+    CK(cudaMemcpy(base.data(), p->d_importance, base.size() * 4, cudaMemcpyDeviceToHost));
+    buildEnvAlias(base.data(), (uint32_t)base.size(), p->envAliasThr, p->envAliasRedirect);
+    if (p->d_envAliasThr) cudaFree(p->d_envAliasThr);
+    if (p->d_envAliasRedirect) cudaFree(p->d_envAliasRedirect);
+    CK(cudaMalloc(&p->d_envAliasThr, base.size() * 4)); CK(cudaMalloc(&p->d_envAliasRedirect, base.size() * 4));
+    CK(cudaMemcpy(p->d_envAliasThr, p->envAliasThr.data(), base.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_envAliasRedirect, p->envAliasRedirect.data(), base.size() * 4, cudaMemcpyHostToDevice));
+    s.envAliasThr = p->d_envAliasThr; s.envAliasRedirect = p->d_envAliasRedirect; s.envAliasCount = (unsigned)base.size();
+    p->sceneDirty = true; p->mOptionsChanged = true;
+    return VRESTIR_OK;
+}
+
+int vrestir_set_analytic_lights(vrestir_pass* p, const vrestir_light* lights, int count) {
+    if (!p || count < 0 || (count > 0 && !lights)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad lights");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < count; i++) if (lights[i].type > VRESTIR_LIGHT_DIRECTIONAL) return setError(VRESTIR_ERR_UNSUPPORTED, "only point and directional analytic lights are supported");
+    if (p->d_lights) { cudaFree(p->d_lights); p->d_lights = nullptr; }
+    if (count) { CK(cudaMalloc(&p->d_lights, (size_t)count * sizeof(vrestir_light))); CK(cudaMemcpy(p->d_lights, lights, (size_t)count * sizeof(vrestir_light), cudaMemcpyHostToDevice)); }
+    p->scene.lights = (const vrestir_light*)p->d_lights; p->scene.lightCount = count;
+    p->sceneDirty = true; p->mOptionsChanged = true;
+    return VRESTIR_OK;
+}
+
+int vrestir_set_emissive_triangles(vrestir_pass* p, const vrestir_emissive_triangle* tris, int count, float mul) {
+    if (!p || count < 0 || (count > 0 && !tris)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad triangles");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    void** ptrs[] = {&p->d_tris, &p->d_alias, &p->d_aliasWeights};
+    for (void** q : ptrs) if (*q) { cudaFree(*q); *q = nullptr; }
+    p->aliasItems.clear(); p->aliasWeights.clear(); p->aliasWeightSum = 0.f;
+    if (count) {
+        p->aliasWeights.resize(count);
+        for (int i = 0; i < count; i++) {   // flux = luminance(Le) * area * pi (F/Experimental/Scene/Lights/FinalizeIntegration.cs.slang:73)
+            float lum = 0.2126f * tris[i].Le[0] + 0.7152f * tris[i].Le[1] + 0.0722f * tris[i].Le[2];
+            p->aliasWeights[i] = lum * tris[i].area * 3.14159265358979323846f;
+        }
+        buildAliasTable(p->aliasWeights, p->aliasItems, p->aliasWeightSum);
+        CK(cudaMalloc(&p->d_tris, (size_t)count * sizeof(vrestir_emissive_triangle)));
+        CK(cudaMemcpy(p->d_tris, tris, (size_t)count * sizeof(vrestir_emissive_triangle), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&p->d_alias, (size_t)count * 16)); CK(cudaMemcpy(p->d_alias, p->aliasItems.data(), (size_t)count * 16, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&p->d_aliasWeights, (size_t)count * 4)); CK(cudaMemcpy(p->d_aliasWeights, p->aliasWeights.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
+    }
+    DScene& s = p->scene;
+    s.tris = (const vrestir_emissive_triangle*)p->d_tris; s.triCount = count; s.alias = (const uint4*)p->d_alias; s.aliasWeights = (const float*)p->d_aliasWeights;
+    s.aliasWeightSum = p->aliasWeightSum; s.emissiveMul = mul;
+    p->sceneDirty = true; p->mOptionsChanged = true;
+    return VRESTIR_OK;
+}
+
+int vrestir_get_emissive_alias(const vrestir_pass* p, uint32_t* items, float* weights, float* weight_sum) {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    if (items && !p->aliasItems.empty()) memcpy(items, p->aliasItems.data(), p->aliasItems.size() * 4);
+    if (weights && !p->aliasWeights.empty()) memcpy(weights, p->aliasWeights.data(), p->aliasWeights.size() * 4);
+    if (weight_sum) *weight_sum = p->aliasWeightSum;
+    return VRESTIR_OK;
+}
+int vrestir_get_env_alias(const vrestir_pass* p, float* thresholds, uint32_t* redirect, int* count) {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    if (count) *count = (int)p->envAliasThr.size();
+    if (thresholds && !p->envAliasThr.empty()) memcpy(thresholds, p->envAliasThr.data(), p->envAliasThr.size() * 4);
+    if (redirect && !p->envAliasRedirect.empty()) memcpy(redirect, p->envAliasRedirect.data(), p->envAliasRedirect.size() * 4);
+    return VRESTIR_OK;
+}
+
+int vrestir_set_frame(vrestir_pass* p, int w, int h, int row_begin, int row_end) {
+    if (!p || w <= 0 || h <= 0 || row_begin < 0 || row_end > h || row_begin >= row_end) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad frame / row band");
+    if ((long long)w * h > (1ll << 30)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "frame too large");
+    if (p->W != w || p->H != h) p->mOptionsChanged = true;
+    p->W = w; p->H = h; p->rowBegin = row_begin; p->rowEnd = row_end;
+    return VRESTIR_OK;
+}
+
+int vrestir_update(vrestir_pass* p, const char* key, double value) {
+    if (!p || !key) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    std::string k(key);
+    if (k.rfind("mParams.", 0) == 0) k = k.substr(8);
+    bool found = false;
+    for (const auto& kd : kKeys)
+        if (k == kd.name) {
+            char* base = (char*)&p->P + kd.off;
+            if (kd.type == 0) *(int32_t*)base = (int32_t)value; else if (kd.type == 1) *(uint32_t*)base = (uint32_t)value; else *(float*)base = (float)value;
+            found = true; break;
+        }
+    if (!found) {
+        found = true;
+        if (k == "mOutputMotionVec") p->mOutputMotionVec = value != 0;
+        else if (k == "mFreezeFrame") p->mFreezeFrame = value != 0;
+        else if (k == "volumeDensityScaleExtraControl") p->densityExtra = (float)value;
+        else if (k == "volumeAlbedoExtraControl") p->albedoExtra = (float)value;
+        else if (k == "volumeAnisotropyExtraControl") p->anisotropyExtra = (float)value;
+        else if (k == "mEnvSamplerType") p->envSamplerType = (int)value;
+        else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
+        else found = false;
+    }
+    p->mOptionsChanged = true;   // VR/VolumetricReSTIR.cpp:1339
+    p->sceneDirty = true;
+    if (!found) return setError(VRESTIR_WARN_UNKNOWN_KEY, std::string("Unknown field '") + key + "' in a VolumetricReSTIR dictionary");
+    return VRESTIR_OK;
+}
+
+int vrestir_set_params(vrestir_pass* p, const vrestir_params* params) {
+    if (!p || !params) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    p->P = *params; p->mOptionsChanged = true; p->sceneDirty = true;
+    return VRESTIR_OK;
+}
+int vrestir_get_params(const vrestir_pass* p, vrestir_params* out) {
+    if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = p->P; return VRESTIR_OK;
+}
+int vrestir_set_frame_count(vrestir_pass* p, int fc, int acc) {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    p->mFrameCount = fc; p->mTemporalSampleAccumulated = acc; p->mOptionsChanged = false; return VRESTIR_OK;
+}
+int vrestir_get_frame_count(const vrestir_pass* p, int* fc) {
+    if (!p || !fc) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    *fc = p->mFrameCount; return VRESTIR_OK;
+}
+/* previous-frame camera for staged parity tests of K2 (normally saved by stage 6) */
+int vrestir_set_prev_camera(vrestir_pass* p, const vrestir_camera* cam) {
+    if (!p || !cam) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    DScene& s = p->scene;
+    memcpy(s.prevView, cam->viewMat, 64); memcpy(s.prevProj, cam->projMat, 64);
+    s.prevU = make_float3(cam->cameraU[0], cam->cameraU[1], cam->cameraU[2]); s.prevV = make_float3(cam->cameraV[0], cam->cameraV[1], cam->cameraV[2]);
+    s.prevW = make_float3(cam->cameraW[0], cam->cameraW[1], cam->cameraW[2]); s.prevPos = make_float3(cam->posW[0], cam->posW[1], cam->posW[2]);
+    p->sceneDirty = true;
+    return VRESTIR_OK;
+}
+
+int vrestir_execute_stage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, void* stream) {
+    return runStage(p, stage, arg, out_color, out_mvec, (cudaStream_t)stream);
+}
+
+int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = runStage(p, 0, 0, out_color, out_mvec, st))) return rc;
+    if ((rc = runStage(p, 1, 0, out_color, out_mvec, st))) return rc;
+    if ((rc = runStage(p, 2, 0, out_color, out_mvec, st))) return rc;
+    if (p->P.mEnableSpatialReuse) { for (int r = 0; r < p->P.mSpatialReuseRounds; r++) if ((rc = runStage(p, 3, r, out_color, out_mvec, st))) return rc; }
+    else recordEv(p, 4, st);
+    if ((rc = runStage(p, 4, 0, out_color, out_mvec, st))) return rc;
+    if ((rc = runStage(p, 5, 0, out_color, out_mvec, st))) return rc;
+    if ((rc = runStage(p, 6, 0, out_color, out_mvec, st))) return rc;
+    return VRESTIR_OK;
+}
+
+int vrestir_execute_host(vrestir_pass* p, float* out_color_host, float* out_mvec_host) {
+    if (!p || !out_color_host) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set");
+    CK(cudaSetDevice(p->device));
+    if (!p->hostStream) CK(cudaStreamCreateWithFlags(&p->hostStream, cudaStreamNonBlocking));
+    const size_t n = N(p);
+    if (p->hostColorPixels != n) {
+        if (p->d_hostColor) cudaFree(p->d_hostColor);
+        if (p->d_hostMvec) cudaFree(p->d_hostMvec);
+        CK(cudaMalloc(&p->d_hostColor, n * 16)); CK(cudaMalloc(&p->d_hostMvec, n * 8));
+        CK(cudaMemsetAsync(p->d_hostColor, 0, n * 16, p->hostStream)); CK(cudaMemsetAsync(p->d_hostMvec, 0, n * 8, p->hostStream));
+        p->hostColorPixels = n;
+    }
+    int rc = vrestir_execute(p, (float*)p->d_hostColor, out_mvec_host ? (float*)p->d_hostMvec : nullptr, p->hostStream);
+    if (rc) return rc;
+    const size_t off = (size_t)p->rowBegin * p->W, cnt = (size_t)(p->rowEnd - p->rowBegin) * p->W;
+    CK(cudaMemcpyAsync(out_color_host + off * 4, p->d_hostColor + off, cnt * 16, cudaMemcpyDeviceToHost, p->hostStream));
+    if (out_mvec_host) CK(cudaMemcpyAsync(out_mvec_host + off * 2, p->d_hostMvec + off, cnt * 8, cudaMemcpyDeviceToHost, p->hostStream));
+    CK(cudaStreamSynchronize(p->hostStream));
+    return VRESTIR_OK;
+}
+
+int vrestir_get_timings(vrestir_pass* p, vrestir_timings* out) {
+    if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    for (int i = 0; i <= 6; i++) if (!p->evValid[i]) return setError(VRESTIR_ERR_NOT_READY, "no completed frame");
+    CK(cudaEventSynchronize(p->ev[6]));
+    float* dst[6] = {&out->features_ms, &out->initial_ms, &out->temporal_ms, &out->spatial_ms, &out->copy_ms, &out->final_ms};
+    for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(dst[i], p->ev[i], p->ev[i + 1]));
+    CK(cudaEventElapsedTime(&out->total_ms, p->ev[0], p->ev[6]));
+    return VRESTIR_OK;
+}
+int vrestir_get_launch_count(const vrestir_pass* p, uint64_t* out) {
+    if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = p->launches; return VRESTIR_OK;
+}
+
+static int physOf(const vrestir_pass* p, int buffer) {
+    switch (buffer) {
+        case VRESTIR_BUF_RESERVOIR_0: case VRESTIR_BUF_EXTRA_0: return p->ia;
+        case VRESTIR_BUF_RESERVOIR_1: case VRESTIR_BUF_EXTRA_1: return p->ib;
+        default: return p->it;
+    }
+}
+int vrestir_buffer_bytes(const vrestir_pass* p, int buffer, size_t* bytes) {
+    if (!p || !bytes) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    const size_t n = N(p); const int B = p->P.mMaxBounces;
+    switch (buffer) {
+        case VRESTIR_BUF_RESERVOIR_0: case VRESTIR_BUF_RESERVOIR_1: case VRESTIR_BUF_RESERVOIR_TEMPORAL: *bytes = n * sizeof(vrestir_reservoir); break;
+        case VRESTIR_BUF_EXTRA_0: case VRESTIR_BUF_EXTRA_1: case VRESTIR_BUF_EXTRA_TEMPORAL: *bytes = n * (size_t)std::max(0, B - 1) * 12; break;
+        case VRESTIR_BUF_FEATURES: case VRESTIR_BUF_FEATURES_TEMPORAL: *bytes = n * 8; break;
+        case VRESTIR_BUF_ENV_IMPORTANCE: *bytes = p->importanceCount * 4; break;
+        default: return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad buffer id");
+    }
+    return VRESTIR_OK;
+}
+int vrestir_get_buffer(vrestir_pass* p, int buffer, void* dst, size_t bytes) {
+    if (!p || (!dst && bytes)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(p->device));
+    size_t need; int rc = vrestir_buffer_bytes(p, buffer, &need); if (rc) return rc;
+    if (need != bytes) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "size mismatch");
+    if (buffer != VRESTIR_BUF_ENV_IMPORTANCE) { if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set"); rc = ensureBuffers(p); if (rc) return rc; }
+    CK(cudaDeviceSynchronize());
+    if (!bytes) return VRESTIR_OK;
+    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
+        vrestir_reservoir* tmp; CK(cudaMalloc(&tmp, bytes));
+        cudaError_t e = launchResToAos(resView(p, physOf(p, buffer)), tmp, (int)N(p), 0); p->launches++;
+        if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, bytes, cudaMemcpyDeviceToHost);
+        cudaFree(tmp); CK(e);
+    } else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) CK(cudaMemcpy(dst, p->ext[physOf(p, buffer)], bytes, cudaMemcpyDeviceToHost));
+    else if (buffer == VRESTIR_BUF_FEATURES) CK(cudaMemcpy(dst, p->feat[p->featCur], bytes, cudaMemcpyDeviceToHost));
+    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) CK(cudaMemcpy(dst, p->feat[p->featPrev], bytes, cudaMemcpyDeviceToHost));
+    else CK(cudaMemcpy(dst, p->d_importance, bytes, cudaMemcpyDeviceToHost));
+    return VRESTIR_OK;
+}
+int vrestir_set_buffer(vrestir_pass* p, int buffer, const void* src, size_t bytes) {
+    if (!p || (!src && bytes)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(p->device));
+    size_t need; int rc = vrestir_buffer_bytes(p, buffer, &need); if (rc) return rc;
+    if (need != bytes) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "size mismatch");
+    if (buffer != VRESTIR_BUF_ENV_IMPORTANCE) { if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set"); rc = ensureBuffers(p); if (rc) return rc; }
+    CK(cudaDeviceSynchronize());
+    if (!bytes) return VRESTIR_OK;
+    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
+        vrestir_reservoir* tmp; CK(cudaMalloc(&tmp, bytes));
+        cudaError_t e = cudaMemcpy(tmp, src, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { e = launchResFromAos(resView(p, physOf(p, buffer)), tmp, (int)N(p), 0); p->launches++; }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(tmp); CK(e);
+    } else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) CK(cudaMemcpy(p->ext[physOf(p, buffer)], src, bytes, cudaMemcpyHostToDevice));
+    else if (buffer == VRESTIR_BUF_FEATURES) CK(cudaMemcpy(p->feat[p->featCur], src, bytes, cudaMemcpyHostToDevice));
+    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) CK(cudaMemcpy(p->feat[p->featPrev], src, bytes, cudaMemcpyHostToDevice));
+    else CK(cudaMemcpy(p->d_importance, src, bytes, cudaMemcpyHostToDevice));
+    return VRESTIR_OK;
+}
+int vrestir_device_buffer(vrestir_pass* p, int buffer, void** base, size_t* plane_stride_bytes, int* planes) {
+    if (!p || !base) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set");
+    int rc = ensureBuffers(p); if (rc) return rc;
+    const size_t n = N(p);
+    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) { *base = p->res[physOf(p, buffer)]; if (plane_stride_bytes) *plane_stride_bytes = n * 16; if (planes) *planes = 2; }
+    else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) { *base = p->ext[physOf(p, buffer)]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
+    else if (buffer == VRESTIR_BUF_FEATURES) { *base = p->feat[p->featCur]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
+    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) { *base = p->feat[p->featPrev]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
+    else return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad buffer id");
+    return VRESTIR_OK;
+}
+int vrestir_spatial_input_buffer(const vrestir_pass* p, int round, int* buffer) {
+    if (!p || !buffer) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    *buffer = (round % 2 == 0) ? VRESTIR_BUF_RESERVOIR_0 : VRESTIR_BUF_RESERVOIR_1;
+    return VRESTIR_OK;
+}
+
+int vrestir_scene_load_vbx(const char*, int, const vrestir_scene_params*, vrestir_scene**) {
+    return setError(VRESTIR_ERR_UNSUPPORTED, ".vbx loading is not implemented yet (SURVEY.md 8f rank 1)");
+}
+
+}  // extern "C"

@@ -1,0 +1,593 @@
+// vr_scene.cpp — host-side scene data for the VolumetricReSTIR hot path: procedural sparse density grids, the
+// mip / conservative-mip chain, the GVDB-style 5-4-3 tree + brick pool, VolumeDesc, camera / env-map / light helpers.
+//
+// This is the data contract of the reference's scene loader and offline converter, rebuilt for synthetic inputs:
+//   tree + atlas + VolumeDesc      F/Scene/Scene.cpp:2898-3298 (addGVDBVolume), F/Scene/GVDB/gvdbNodes.slang:38-95
+//   brick (min,max,avg) bounds      F/Scene/Scene.cpp:2981-3012 (10^3 apron-inclusive block, avg / 512)
+//   8-bit coarse / conservative     F/Scene/Scene.cpp:3161-3174 (ATLAS_COMPRESSION == 1 variant), 1e-9 clamp :3154-3156
+//   mip + conservative rule         gvdb-voxel-src/source/gvdb_library/src/gvdb_volume_gvdb.cpp:2703-2885
+//   camera U,V,W + view/proj        F/Scene/Camera/Camera.cpp:150-189
+// (F/ = Source/Falcor/).  Layout differences from the reference (brick pool instead of a 3-D atlas texture, explicit
+// node.pos / node.link instead of 16-bit packed pos/value) are described in include/vrestir.h and DESIGN.md.
+#include "../../include/vrestir.h"
+#include "vr_host.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace vr {
+
+// ------------------------------------------------------------------------------------------------ helpers
+template <class F> static void parallelFor(int n, F f) {
+    int nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    if (n < 4) nt = 1;
+    std::atomic<int> next{0};
+    auto body = [&]() { for (;;) { int i = next.fetch_add(1); if (i >= n) break; f(i); } };
+    if (nt == 1) { body(); return; }
+    std::vector<std::thread> th;
+    for (int i = 0; i < nt; i++) th.emplace_back(body);
+    for (auto& t : th) t.join();
+}
+
+static inline uint32_t hash3(int x, int y, int z, uint32_t seed) {
+    uint32_t h = seed * 0x9E3779B1u + 0x7F4A7C15u;
+    h ^= (uint32_t)x * 0x85EBCA6Bu; h = (h << 13) | (h >> 19); h *= 0xC2B2AE35u;
+    h ^= (uint32_t)y * 0x27D4EB2Fu; h = (h << 15) | (h >> 17); h *= 0x165667B1u;
+    h ^= (uint32_t)z * 0x9E3779B1u; h = (h << 11) | (h >> 21); h *= 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+static inline float lattice(int x, int y, int z, uint32_t seed) { return (float)(hash3(x, y, z, seed) >> 8) * (1.0f / 16777216.0f); }
+static inline float smooth(float t) { return t * t * (3.f - 2.f * t); }
+static float valueNoise(float x, float y, float z, uint32_t seed) {
+    float fx = std::floor(x), fy = std::floor(y), fz = std::floor(z);
+    int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    float tx = smooth(x - fx), ty = smooth(y - fy), tz = smooth(z - fz);
+    float c[8];
+    for (int i = 0; i < 8; i++) c[i] = lattice(ix + (i & 1), iy + ((i >> 1) & 1), iz + (i >> 2), seed);
+    float x00 = c[0] + tx * (c[1] - c[0]), x10 = c[2] + tx * (c[3] - c[2]), x01 = c[4] + tx * (c[5] - c[4]), x11 = c[6] + tx * (c[7] - c[6]);
+    float y0 = x00 + ty * (x10 - x00), y1 = x01 + ty * (x11 - x01);
+    return y0 + tz * (y1 - y0);
+}
+static float fbm(float x, float y, float z, uint32_t seed, int octaves = 5) {
+    float sum = 0.f, amp = 0.5f, norm = 0.f;
+    for (int o = 0; o < octaves; o++) {
+        sum += amp * valueNoise(x, y, z, seed + 101u * (uint32_t)o);
+        norm += amp; amp *= 0.5f; x *= 2.f; y *= 2.f; z *= 2.f;
+    }
+    return sum / norm;
+}
+
+struct Dense {
+    int nx = 0, ny = 0, nz = 0, ch = 1;
+    std::vector<float> v;   // [ch][z][y][x]
+    size_t n() const { return (size_t)nx * ny * nz; }
+    float at(int x, int y, int z, int c = 0) const {
+        if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) return 0.f;
+        return v[(size_t)c * n() + ((size_t)z * ny + y) * nx + x];
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ procedural fields
+static float ellipsoid(float x, float y, float z, float cx, float cy, float cz, float rx, float ry, float rz) {
+    float dx = (x - cx) / rx, dy = (y - cy) / ry, dz = (z - cz) / rz;
+    return 1.f - std::sqrt(dx * dx + dy * dy + dz * dz);   // > 0 inside
+}
+static float shapeDensity(const vrestir_scene_params& sp, float u, float v, float w, float* temperature, float vel[3]) {
+    // (u,v,w) in [0,1]^3 over the grid; returns density in [0,1]
+    const uint32_t seed = sp.seed;
+    const float f = 6.f;
+    switch (sp.kind) {
+        case 0: {   // sphere (radius 0.375 of the box) x fBm, SURVEY.md 8(d) config 1
+            float dx = u - 0.5f, dy = v - 0.5f, dz = w - 0.5f;
+            float r = std::sqrt(dx * dx + dy * dy + dz * dz);
+            if (r > 0.375f) return 0.f;
+            float n = fbm(u * f, v * f, w * f, seed);
+            float edge = std::min(1.f, (0.375f - r) * 16.f);
+            return std::max(0.f, n - 0.35f) / 0.65f * edge;
+        }
+        case 1: {   // bunny-cloud-like blob: body + head + two ears, eroded by fBm
+            float s = -1.f;
+            s = std::max(s, ellipsoid(u, v, w, 0.50f, 0.36f, 0.52f, 0.36f, 0.30f, 0.34f));
+            s = std::max(s, ellipsoid(u, v, w, 0.30f, 0.62f, 0.50f, 0.20f, 0.19f, 0.21f));
+            s = std::max(s, ellipsoid(u, v, w, 0.27f, 0.85f, 0.40f, 0.065f, 0.16f, 0.08f));
+            s = std::max(s, ellipsoid(u, v, w, 0.30f, 0.85f, 0.61f, 0.065f, 0.16f, 0.08f));
+            s = std::max(s, ellipsoid(u, v, w, 0.82f, 0.30f, 0.52f, 0.10f, 0.10f, 0.10f));
+            if (s < -0.25f) return 0.f;
+            float n = fbm(u * 7.f, v * 7.f, w * 7.f, seed);
+            float d = s * 2.2f + (n - 0.5f) * 1.1f;
+            return std::min(1.f, std::max(0.f, d) * 2.5f);
+        }
+        case 2: {   // plume: rising turbulent column, advected upward with frame_time
+            float t = sp.frame_time;
+            float cx = 0.5f + 0.06f * std::sin(6.f * v + 0.7f * t), cz = 0.5f + 0.06f * std::cos(5.f * v + 0.9f * t);
+            float rad = 0.07f + 0.22f * v;
+            float dx = u - cx, dz = w - cz;
+            float r = std::sqrt(dx * dx + dz * dz) / rad;
+            float rise = std::min(1.f, 0.25f + 0.05f * t);
+            float body = (r < 1.f && v < rise) ? (1.f - r) : 0.f;
+            float n = fbm(u * 8.f, (v - 0.04f * t) * 8.f, w * 8.f, seed);
+            float d = body * std::max(0.f, n - 0.3f) * 2.4f * std::min(1.f, (rise - v) * 12.f);
+            d = std::min(1.f, std::max(0.f, d));
+            if (temperature) *temperature = d > 0.f ? 2000.f * std::max(0.f, 1.f - v / std::max(rise, 1e-3f)) * std::min(1.f, d * 3.f) : 0.f;
+            if (vel) {   // curl-like swirl + rise, |v| <= 2 voxels / frame (index units of mip 0)
+                float sw = 1.2f * (n - 0.5f);
+                vel[0] = d > 0.f ? -dz / std::max(rad, 1e-3f) * sw : 0.f;
+                vel[1] = d > 0.f ? 1.5f * (1.f - 0.5f * r) : 0.f;
+                vel[2] = d > 0.f ? dx / std::max(rad, 1e-3f) * sw : 0.f;
+            }
+            return d;
+        }
+        case 3: {   // dense cloud filling most of the box
+            float n = fbm(u * 5.f, v * 5.f, w * 5.f, seed);
+            float bx = std::min(std::min(u, 1.f - u), std::min(std::min(v, 1.f - v), std::min(w, 1.f - w)));
+            float edge = std::min(1.f, bx * 12.f);
+            return std::min(1.f, std::max(0.f, n - 0.38f) * 3.0f) * edge;
+        }
+        default: {  // thin fBm shells
+            float n = fbm(u * 10.f, v * 10.f, w * 10.f, seed, 4);
+            float sh = 1.f - std::fabs(n - 0.5f) * 60.f;
+            return std::max(0.f, sh);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ mip chain
+// conservative mip 0: zero voxels take the mean of their positive 27-neighbourhood (GV/.../gvdb_volume_gvdb.cpp:2753-2801)
+static Dense makeConservative0(const Dense& src) {
+    Dense d = src;
+    parallelFor(src.nz, [&](int z) {
+        for (int y = 0; y < src.ny; y++)
+            for (int x = 0; x < src.nx; x++) {
+                float org = src.at(x, y, z);
+                if (org != 0.f) continue;
+                float avg = 0.f;
+                for (int ii = -1; ii <= 1; ii++)
+                    for (int jj = -1; jj <= 1; jj++)
+                        for (int kk = -1; kk <= 1; kk++) { float t = src.at(x + ii, y + jj, z + kk); avg += t > 0.f ? t : 0.f; }
+                avg /= 27.f;
+                if (avg > 0.f) d.v[((size_t)z * src.ny + y) * src.nx + x] = avg;
+            }
+    });
+    return d;
+}
+// mip k from mip k-1 of the same type: 2x box, 3-tap polyphase on odd axes (GV/.../gvdb_volume_gvdb.cpp:2803-2862)
+static Dense downsample(const Dense& prev) {
+    Dense d; d.nx = std::max(1, prev.nx / 2); d.ny = std::max(1, prev.ny / 2); d.nz = std::max(1, prev.nz / 2); d.ch = 1;
+    d.v.assign(d.n(), 0.f);
+    const int ni = prev.nx % 2 == 0 ? 2 : 3, nj = prev.ny % 2 == 0 ? 2 : 3, nk = prev.nz % 2 == 0 ? 2 : 3;
+    auto weights = [](int n, int cur, int i, float w[3]) {
+        if (n == 2) { w[0] = w[1] = w[2] = 0.5f; return; }
+        float den = (float)(2 * cur + 1);
+        w[0] = (float)(cur - i) / den; w[1] = (float)cur / den; w[2] = (float)(1 + i) / den;
+    };
+    parallelFor(d.nz, [&](int k) {
+        float wi[3], wj[3], wk[3];
+        weights(nk, d.nz, k, wk);
+        for (int j = 0; j < d.ny; j++) {
+            weights(nj, d.ny, j, wj);
+            for (int i = 0; i < d.nx; i++) {
+                weights(ni, d.nx, i, wi);
+                float res = 0.f;
+                for (int ii = 0; ii < ni; ii++)
+                    for (int jj = 0; jj < nj; jj++)
+                        for (int kk = 0; kk < nk; kk++) res += wi[ii] * wj[jj] * wk[kk] * prev.at(2 * i + ii, 2 * j + jj, 2 * k + kk);
+                if (res > 0.f) d.v[((size_t)k * d.ny + j) * d.nx + i] = res;
+            }
+        }
+    });
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------ tree + brick pool
+struct BuiltSlot {
+    std::vector<vrestir_node> nodes[3];
+    std::vector<uint32_t> child[3];
+    std::vector<uint8_t> atlas;
+    bool used = false;
+};
+
+static void buildSlot(const Dense& src, int format, bool conservative, BuiltSlot& out, vrestir_grid_slot& g) {
+    const int BX = (src.nx + 7) / 8, BY = (src.ny + 7) / 8, BZ = (src.nz + 7) / 8;
+    const int ch = src.ch;
+    float maxv = 0.f;
+    for (size_t i = 0; i < src.n(); i++) maxv = std::max(maxv, std::fabs(src.v[i]));   // channel 0 (density / temperature / vx)
+    if (ch > 1) for (size_t i = src.n(); i < src.v.size(); i++) maxv = std::max(maxv, std::fabs(src.v[i]));
+    if (maxv <= 0.f) maxv = 1.f;
+    // active bricks: any non-zero in the 10^3 apron-inclusive block (so every trilinear footprint lies in a brick)
+    std::vector<uint8_t> active((size_t)BX * BY * BZ, 0);
+    parallelFor(BZ, [&](int bz) {
+        for (int by = 0; by < BY; by++)
+            for (int bx = 0; bx < BX; bx++) {
+                bool any = false;
+                for (int c = 0; c < ch && !any; c++)
+                    for (int z = bz * 8 - 1; z <= bz * 8 + 8 && !any; z++)
+                        for (int y = by * 8 - 1; y <= by * 8 + 8 && !any; y++)
+                            for (int x = bx * 8 - 1; x <= bx * 8 + 8; x++) if (src.at(x, y, z, c) != 0.f) { any = true; break; }
+                active[((size_t)bz * BY + by) * BX + bx] = any;
+            }
+    });
+    // ensure at least one brick so the tree is well formed
+    bool anyActive = false; for (auto a : active) anyActive |= a != 0;
+    if (!anyActive) active[0] = 1;
+
+    const int N1X = (src.nx + 127) / 128, N1Y = (src.ny + 127) / 128, N1Z = (src.nz + 127) / 128;
+    const bool three = (N1X * N1Y * N1Z) > 1;
+    g = vrestir_grid_slot{};
+    g.valid = 1; g.top_lev = three ? 2 : 1;
+    g.dim[0] = 3; g.dim[1] = 4; g.dim[2] = 5; g.res[0] = 8; g.res[1] = 16; g.res[2] = 32;
+    g.vdel[0] = 1.f; g.vdel[1] = 8.f; g.vdel[2] = 128.f; g.noderange[0] = 8; g.noderange[1] = 128; g.noderange[2] = 4096;
+
+    // level-1 nodes: one per 128^3 cell that has an active brick (z-major order), level-0 nodes in (node1, z, y, x) order
+    std::vector<int32_t> n1id((size_t)N1X * N1Y * N1Z, -1);
+    for (int bz = 0; bz < BZ; bz++) for (int by = 0; by < BY; by++) for (int bx = 0; bx < BX; bx++)
+        if (active[((size_t)bz * BY + by) * BX + bx]) n1id[((size_t)(bz / 16) * N1Y + by / 16) * N1X + bx / 16] = 0;
+    uint32_t n1count = 0;
+    for (auto& v : n1id) if (v == 0) v = (int32_t)n1count++;
+    out.nodes[1].resize(n1count);
+    out.child[1].assign((size_t)n1count * 4096, 0xFFFFFFFFu);
+    uint32_t brickCount = 0;
+    for (int z1 = 0; z1 < N1Z; z1++) for (int y1 = 0; y1 < N1Y; y1++) for (int x1 = 0; x1 < N1X; x1++) {
+        int32_t id = n1id[((size_t)z1 * N1Y + y1) * N1X + x1];
+        if (id < 0) continue;
+        vrestir_node& n = out.nodes[1][id];
+        n.pos[0] = x1 * 128; n.pos[1] = y1 * 128; n.pos[2] = z1 * 128; n.link = (uint32_t)id;
+        n.bounds[0] = n.bounds[1] = n.bounds[2] = n.bounds[3] = 0.f;
+        for (int cz = 0; cz < 16; cz++) for (int cy = 0; cy < 16; cy++) for (int cx = 0; cx < 16; cx++) {
+            int bx = x1 * 16 + cx, by = y1 * 16 + cy, bz = z1 * 16 + cz;
+            if (bx >= BX || by >= BY || bz >= BZ || !active[((size_t)bz * BY + by) * BX + bx]) continue;
+            out.child[1][(size_t)id * 4096 + (((cz << 4) + cy) << 4) + cx] = brickCount++;
+        }
+    }
+    out.nodes[0].resize(brickCount);
+    const size_t bpv = format == VRESTIR_ATLAS_UNORM8 ? 1 : 4;
+    out.atlas.assign((size_t)brickCount * ch * VRESTIR_BRICK_VOXELS * bpv, 0);
+    // fill bricks
+    std::vector<std::array<int, 3>> brickPos(brickCount);
+    for (uint32_t id = 0; id < n1count; id++)
+        for (int b = 0; b < 4096; b++) {
+            uint32_t c = out.child[1][(size_t)id * 4096 + b];
+            if (c == 0xFFFFFFFFu) continue;
+            const vrestir_node& n1 = out.nodes[1][id];
+            brickPos[c] = {n1.pos[0] + (b & 15) * 8, n1.pos[1] + ((b >> 4) & 15) * 8, n1.pos[2] + (b >> 8) * 8};
+        }
+    parallelFor((int)brickCount, [&](int bi) {
+        vrestir_node& n = out.nodes[0][bi];
+        n.pos[0] = brickPos[bi][0]; n.pos[1] = brickPos[bi][1]; n.pos[2] = brickPos[bi][2]; n.link = (uint32_t)bi;
+        for (int c = 0; c < ch; c++) {
+            size_t base = ((size_t)bi * ch + c) * VRESTIR_BRICK_VOXELS;
+            for (int z = -1; z <= 8; z++) for (int y = -1; y <= 8; y++) for (int x = -1; x <= 8; x++) {
+                float v = src.at(n.pos[0] + x, n.pos[1] + y, n.pos[2] + z, c);
+                if (v / maxv < 1e-9f && v >= 0.f) v = 0.f;                            // F/Scene/Scene.cpp:3154-3156
+                size_t idx = base + (size_t)((z + 1) * 10 + (y + 1)) * 10 + (x + 1);
+                if (format == VRESTIR_ATLAS_UNORM8) {
+                    int q = (int)std::lround(255.0 * (double)(v / maxv));
+                    q = std::max(0, std::min(255, q));
+                    if (q == 0 && v > 0.f && conservative) q = 1;                     // F/Scene/Scene.cpp:3171
+                    out.atlas[idx] = (uint8_t)q;
+                } else {
+                    memcpy(&out.atlas[idx * 4], &v, 4);
+                }
+            }
+        }
+        // (min, max, avg) over the stored 10^3 block, x outermost like F/Scene/Scene.cpp:2989-3010; avg = sum / 512
+        float mn = 3.402823466e+38f, mx = 0.f, sum = 0.f;
+        size_t base = (size_t)bi * ch * VRESTIR_BRICK_VOXELS;
+        for (int i = -1; i <= 8; i++) for (int j = -1; j <= 8; j++) for (int k = -1; k <= 8; k++) {
+            size_t idx = base + (size_t)((k + 1) * 10 + (j + 1)) * 10 + (i + 1);
+            float d;
+            if (format == VRESTIR_ATLAS_UNORM8) d = (float)out.atlas[idx] * 0.003921568859368563f * maxv;
+            else memcpy(&d, &out.atlas[idx * 4], 4);
+            mn = std::min(mn, d); mx = std::max(mx, d); sum += d;
+        }
+        n.bounds[0] = mn; n.bounds[1] = mx; n.bounds[2] = sum / 512.f; n.bounds[3] = 0.f;
+    });
+    if (three) {
+        out.nodes[2].resize(1);
+        vrestir_node& r = out.nodes[2][0];
+        r.pos[0] = r.pos[1] = r.pos[2] = 0; r.link = 0; r.bounds[0] = r.bounds[1] = r.bounds[2] = r.bounds[3] = 0.f;
+        out.child[2].assign(32768, 0xFFFFFFFFu);
+        for (int z1 = 0; z1 < N1Z; z1++) for (int y1 = 0; y1 < N1Y; y1++) for (int x1 = 0; x1 < N1X; x1++) {
+            int32_t id = n1id[((size_t)z1 * N1Y + y1) * N1X + x1];
+            if (id >= 0) out.child[2][(((z1 << 5) + y1) << 5) + x1] = (uint32_t)id;
+        }
+    } else if (n1count == 0) {
+        out.nodes[1].resize(1);
+    }
+    for (int l = 0; l < 3; l++) {
+        g.node_count[l] = (uint32_t)out.nodes[l].size(); g.nodes[l] = out.nodes[l].empty() ? nullptr : out.nodes[l].data();
+        g.childlist[l] = out.child[l].empty() ? nullptr : out.child[l].data(); g.childlist_count[l] = out.child[l].size();
+    }
+    g.bmin[0] = g.bmin[1] = g.bmin[2] = 0.f;
+    g.bmax[0] = (float)src.nx; g.bmax[1] = (float)src.ny; g.bmax[2] = (float)src.nz;
+    g.max_value = maxv;
+    g.compress_scale = format == VRESTIR_ATLAS_UNORM8 ? maxv : 1.f;
+    g.atlas_format = format; g.atlas_channels = ch; g.brick_count = brickCount; g.atlas = out.atlas.data();
+    out.used = true;
+}
+
+static void mat4Identity(double* m) { for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+static void mat4Mul(const double* a, const double* b, double* o) {   // o = a * b (row-vector convention: apply a, then b)
+    double t[16];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { double s = 0; for (int k = 0; k < 4; k++) s += a[i * 4 + k] * b[k * 4 + j]; t[i * 4 + j] = s; }
+    memcpy(o, t, sizeof(t));
+}
+static void toF(const double* m, float* o) { for (int i = 0; i < 16; i++) o[i] = (float)m[i]; }
+
+}  // namespace vr
+
+using namespace vr;
+
+struct vrestir_scene {
+    vrestir_grid_desc desc{};
+    BuiltSlot slots[VRESTIR_MAX_SLOTS];
+    std::vector<float> lut;
+    vrestir_scene_params params{};
+};
+
+static void setTransforms(vrestir_scene& s, int slot, const int dim0[3], const int dimk[3]) {
+    const vrestir_scene_params& p = s.params;
+    double X[16], Xi[16], E[16], Ei[16], M[16];
+    mat4Identity(X); mat4Identity(Xi); mat4Identity(E); mat4Identity(Ei);
+    for (int a = 0; a < 3; a++) {
+        double sc = (double)p.voxel_size * (double)dim0[a] / (double)dimk[a];   // per-axis prescale, gvdb_volume_gvdb.cpp:2731
+        double org = -0.5 * (double)dim0[a] * (double)p.voxel_size;            // volume centred on the model origin
+        X[a * 5] = sc; X[12 + a] = org;
+        Xi[a * 5] = 1.0 / sc; Xi[12 + a] = -org / sc;
+        E[a * 5] = p.world_scaling; E[12 + a] = p.world_translation[a];
+        Ei[a * 5] = 1.0 / p.world_scaling; Ei[12 + a] = -p.world_translation[a] / p.world_scaling;
+    }
+    vrestir_grid_slot& g = s.desc.slots[slot];
+    toF(X, g.xform); toF(Xi, g.invxform);
+    mat4Mul(X, E, M); toF(M, g.medium_to_world);
+    mat4Mul(Ei, Xi, M); toF(M, g.world_to_medium);
+    if (slot == 0) {
+        toF(E, s.desc.volume.externalModelToWorld); toF(Ei, s.desc.volume.externalWorldToModel);
+    }
+}
+
+static int buildScene(const vrestir_scene_params* p, Dense&& density, Dense* temperature, Dense* velocity, vrestir_scene** out) {
+    auto* s = new vrestir_scene();
+    s->params = *p;
+    const int dim0[3] = {density.nx, density.ny, density.nz};
+    const int numMips = std::max(1, std::min(VRESTIR_NUM_MAX_MIPS, p->num_mips));
+    // normal chain
+    {
+        Dense cur = std::move(density);
+        Dense cons = makeConservative0(cur);
+        for (int m = 0; m < numMips; m++) {
+            const int dk[3] = {cur.nx, cur.ny, cur.nz};
+            buildSlot(cur, m == 0 ? VRESTIR_ATLAS_F32 : VRESTIR_ATLAS_UNORM8, false, s->slots[m], s->desc.slots[m]);
+            setTransforms(*s, m, dim0, dk);
+            buildSlot(cons, VRESTIR_ATLAS_UNORM8, true, s->slots[VRESTIR_NUM_MAX_MIPS + m], s->desc.slots[VRESTIR_NUM_MAX_MIPS + m]);
+            setTransforms(*s, VRESTIR_NUM_MAX_MIPS + m, dim0, dk);
+            if (m + 1 < numMips) {
+                if (cur.nx < 2 || cur.ny < 2 || cur.nz < 2) { s->params.num_mips = m + 1; break; }
+                cur = downsample(cur); cons = downsample(cons);
+            }
+        }
+    }
+    int builtMips = 0; for (int m = 0; m < VRESTIR_NUM_MAX_MIPS; m++) if (s->desc.slots[m].valid) builtMips = m + 1;
+    if (temperature) {
+        buildSlot(*temperature, VRESTIR_ATLAS_F32, false, s->slots[VRESTIR_TEMPERATURE_GRID_ID], s->desc.slots[VRESTIR_TEMPERATURE_GRID_ID]);
+        setTransforms(*s, VRESTIR_TEMPERATURE_GRID_ID, dim0, dim0);
+    }
+    if (velocity) {
+        buildSlot(*velocity, VRESTIR_ATLAS_F32, false, s->slots[VRESTIR_VELOCITY_GRID_ID], s->desc.slots[VRESTIR_VELOCITY_GRID_ID]);
+        setTransforms(*s, VRESTIR_VELOCITY_GRID_ID, dim0, dim0);
+    }
+    // VolumeDesc (F/Scene/Scene.cpp:3246-3298)
+    vrestir_volume_desc& v = s->desc.volume;
+    for (int i = 0; i < 3; i++) { v.sigma_a[i] = p->sigma_a[i]; v.sigma_s[i] = p->sigma_s[i]; }
+    v.sigma_t = p->sigma_s[0] + p->sigma_a[0];
+    v.PhaseFunctionConstantG = p->g;
+    v.densityScaleFactor = p->density_scale;
+    v.densityScaleFactorByScaling = p->density_scale / p->world_scaling;
+    const float* X = s->desc.slots[0].xform;
+    auto len3 = [](const float* r) { return std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); };
+    v.tStep = (len3(X) + len3(X + 4) + len3(X + 8)) / 3.f;
+    v.hasEmission = temperature ? 1 : 0; v.hasVelocity = velocity ? 1 : 0; v.hasAnimation = 0; v.lastFrameHasEmission = 0;
+    v.LeScale = p->LeScale; v.temperatureCutOff = p->temperatureCutOff; v.temperatureScale = p->temperatureScale;
+    v.velocityScale = 1.f; v.numMips = builtMips; v.usePrevGridForReproj = 0;
+    v.volumeWorldScaling = p->world_scaling;
+    v.superVoxelWorldSpaceDiagonalLength = 8.f * std::sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2] + X[4] * X[4] + X[5] * X[5] + X[6] * X[6] + X[8] * X[8] + X[9] * X[9] + X[10] * X[10]);
+    if (temperature) { s->lut.resize(512); vrestir_make_blackbody_lut(s->lut.data()); s->desc.blackbody_lut = s->lut.data(); }
+    *out = s;
+    return VRESTIR_OK;
+}
+
+extern "C" {
+
+int vrestir_scene_create(const vrestir_scene_params* p, vrestir_scene** out) {
+    if (!p || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (p->dim[0] < 8 || p->dim[1] < 8 || p->dim[2] < 8 || p->dim[0] > 4096 || p->dim[1] > 4096 || p->dim[2] > 4096)
+        return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "grid dimensions must be in [8, 4096]");
+    if ((double)p->dim[0] * p->dim[1] * p->dim[2] > 1.2e9) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "dense procedural build limited to 1.2e9 voxels");
+    Dense d; d.nx = p->dim[0]; d.ny = p->dim[1]; d.nz = p->dim[2]; d.v.assign(d.n(), 0.f);
+    Dense T, V;
+    const bool wt = p->with_temperature && p->kind == 2, wv = p->with_velocity && p->kind == 2;
+    if (wt) { T = d; }
+    if (wv) { V.nx = d.nx; V.ny = d.ny; V.nz = d.nz; V.ch = 3; V.v.assign(d.n() * 3, 0.f); }
+    parallelFor(d.nz, [&](int z) {
+        for (int y = 0; y < d.ny; y++)
+            for (int x = 0; x < d.nx; x++) {
+                float u = ((float)x + 0.5f) / (float)d.nx, v = ((float)y + 0.5f) / (float)d.ny, w = ((float)z + 0.5f) / (float)d.nz;
+                float temp = 0.f, vel[3] = {0, 0, 0};
+                float dens = shapeDensity(*p, u, v, w, wt ? &temp : nullptr, wv ? vel : nullptr);
+                size_t i = ((size_t)z * d.ny + y) * d.nx + x;
+                d.v[i] = dens;
+                if (wt) T.v[i] = temp;
+                if (wv) { V.v[i] = vel[0]; V.v[d.n() + i] = vel[1]; V.v[2 * d.n() + i] = vel[2]; }
+            }
+    });
+    return buildScene(p, std::move(d), wt ? &T : nullptr, wv ? &V : nullptr, out);
+}
+
+int vrestir_scene_create_from_dense(const vrestir_scene_params* p, const float* density, const float* temperature, const float* velocity_xyz, vrestir_scene** out) {
+    if (!p || !density || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (p->dim[0] < 1 || p->dim[1] < 1 || p->dim[2] < 1 || p->dim[0] > 4096 || p->dim[1] > 4096 || p->dim[2] > 4096)
+        return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "grid dimensions must be in [1, 4096]");
+    Dense d; d.nx = p->dim[0]; d.ny = p->dim[1]; d.nz = p->dim[2]; d.v.assign(density, density + d.n());
+    Dense T, V;
+    if (temperature) { T.nx = d.nx; T.ny = d.ny; T.nz = d.nz; T.v.assign(temperature, temperature + d.n()); }
+    if (velocity_xyz) {
+        V.nx = d.nx; V.ny = d.ny; V.nz = d.nz; V.ch = 3; V.v.resize(d.n() * 3);
+        for (size_t i = 0; i < d.n(); i++) for (int c = 0; c < 3; c++) V.v[(size_t)c * d.n() + i] = velocity_xyz[i * 3 + c];
+    }
+    return buildScene(p, std::move(d), temperature ? &T : nullptr, velocity_xyz ? &V : nullptr, out);
+}
+
+int vrestir_scene_destroy(vrestir_scene* s) { delete s; return VRESTIR_OK; }
+const vrestir_grid_desc* vrestir_scene_grid(const vrestir_scene* s) { return s ? &s->desc : nullptr; }
+
+int vrestir_scene_dense_mip(const vrestir_scene* s, int mip, int conservative, float* out, int32_t out_dim[3]) {
+    if (!s || mip < 0 || mip >= VRESTIR_NUM_MAX_MIPS) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad mip");
+    const int slot = mip + (conservative ? VRESTIR_NUM_MAX_MIPS : 0);
+    const vrestir_grid_slot& g = s->desc.slots[slot];
+    if (!g.valid) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "slot not built");
+    const int nx = (int)g.bmax[0], ny = (int)g.bmax[1], nz = (int)g.bmax[2];
+    if (out_dim) { out_dim[0] = nx; out_dim[1] = ny; out_dim[2] = nz; }
+    if (!out) return VRESTIR_OK;
+    memset(out, 0, (size_t)nx * ny * nz * 4);
+    for (uint32_t b = 0; b < g.brick_count; b++) {
+        const vrestir_node& n = g.nodes[0][b];
+        for (int z = 0; z < 8; z++) for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            int gx = n.pos[0] + x, gy = n.pos[1] + y, gz = n.pos[2] + z;
+            if (gx >= nx || gy >= ny || gz >= nz) continue;
+            size_t idx = (size_t)b * g.atlas_channels * VRESTIR_BRICK_VOXELS + (size_t)((z + 1) * 10 + (y + 1)) * 10 + (x + 1);
+            float v;
+            if (g.atlas_format == VRESTIR_ATLAS_UNORM8) v = (float)((const uint8_t*)g.atlas)[idx] * 0.003921568859368563f * g.compress_scale;
+            else v = ((const float*)g.atlas)[idx];
+            out[((size_t)gz * ny + gy) * nx + gx] = v;
+        }
+    }
+    return VRESTIR_OK;
+}
+
+int vrestir_scene_stats(const vrestir_scene* s, int slot, uint32_t* bricks, uint64_t* atlas_bytes) {
+    if (!s || slot < 0 || slot >= VRESTIR_MAX_SLOTS) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad slot");
+    const vrestir_grid_slot& g = s->desc.slots[slot];
+    if (bricks) *bricks = g.valid ? g.brick_count : 0;
+    if (atlas_bytes) *atlas_bytes = g.valid ? (uint64_t)s->slots[slot].atlas.size() : 0;
+    return VRESTIR_OK;
+}
+
+// F/Scene/Camera/Camera.cpp:150-189 (focalDistance = 10000 as in CameraData.slang:60; view = lookAt RH, proj = perspective RH)
+int vrestir_camera_look_at(const float pos[3], const float target[3], const float up[3], float fovY, float aspect, float nearZ, float farZ, vrestir_camera* out) {
+    if (!pos || !target || !up || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    auto sub = [](const float* a, const float* b, float* o) { for (int i = 0; i < 3; i++) o[i] = a[i] - b[i]; };
+    auto nrm = [](float* a) { float l = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); for (int i = 0; i < 3; i++) a[i] /= l; };
+    auto crs = [](const float* a, const float* b, float* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; };
+    auto dt = [](const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    const float focalDistance = 10000.f;
+    float f[3], s[3], u[3];
+    sub(target, pos, f); nrm(f);
+    crs(f, up, s); nrm(s);
+    crs(s, f, u);
+    const float ulen = focalDistance * std::tan(fovY * 0.5f) * aspect, vlen = focalDistance * std::tan(fovY * 0.5f);
+    float vv[3]; crs(s, f, vv); nrm(vv);   // cameraV = normalize(cross(U, W))
+    for (int i = 0; i < 3; i++) { out->posW[i] = pos[i]; out->cameraW[i] = f[i] * focalDistance; out->cameraU[i] = s[i] * ulen; out->cameraV[i] = vv[i] * vlen; }
+    // view (row-vector convention): columns are s, u, -f
+    float* V = out->viewMat;
+    V[0] = s[0]; V[1] = u[0]; V[2] = -f[0]; V[3] = 0; V[4] = s[1]; V[5] = u[1]; V[6] = -f[1]; V[7] = 0; V[8] = s[2]; V[9] = u[2]; V[10] = -f[2]; V[11] = 0;
+    V[12] = -dt(s, pos); V[13] = -dt(u, pos); V[14] = dt(f, pos); V[15] = 1;
+    float* P = out->projMat; memset(P, 0, 64);
+    const float th = std::tan(fovY * 0.5f);
+    P[0] = 1.f / (aspect * th); P[5] = 1.f / th; P[10] = farZ / (nearZ - farZ); P[11] = -1.f; P[14] = -(farZ * nearZ) / (farZ - nearZ);
+    out->nearZ = nearZ; out->farZ = farZ;
+    return VRESTIR_OK;
+}
+
+int vrestir_make_sky_envmap(int width, int height, uint32_t seed, float* out) {
+    if (width < 2 || height < 2 || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad env map size");
+    const float sunDir[3] = {0.45f, 0.62f, -0.64f};
+    parallelFor(height, [&](int y) {
+        for (int x = 0; x < width; x++) {
+            float u = ((float)x + 0.5f) / (float)width, v = ((float)y + 0.5f) / (float)height;
+            float phi = (u - 0.5f) * 6.28318530718f, th = v * 3.14159265359f;
+            float d[3] = {std::sin(phi) * std::sin(th), std::cos(th), -std::cos(phi) * std::sin(th)};
+            float up = d[1];
+            float horizon = std::exp(-std::fabs(up) * 4.f);
+            float sky[3] = {0.25f + 0.55f * horizon, 0.42f + 0.45f * horizon, 0.85f + 0.1f * horizon};
+            float gnd[3] = {0.18f, 0.16f, 0.13f};
+            float t = std::min(1.f, std::max(0.f, up * 8.f + 0.5f));
+            float cs = d[0] * sunDir[0] + d[1] * sunDir[1] + d[2] * sunDir[2];
+            float sun = cs > 0.9995f ? 900.f : 0.f;
+            float glow = std::pow(std::max(0.f, cs), 64.f) * 6.f + std::pow(std::max(0.f, cs), 8.f) * 0.6f;
+            float cl = 0.85f + 0.3f * fbm(u * 12.f, v * 6.f, 0.5f, seed, 4);
+            float* o = &out[((size_t)y * width + x) * 4];
+            for (int c = 0; c < 3; c++) o[c] = (gnd[c] * (1.f - t) + sky[c] * t) * cl + (c == 2 ? 0.8f : 1.f) * (sun + glow);
+            o[3] = 1.f;
+        }
+    });
+    return VRESTIR_OK;
+}
+
+int vrestir_make_emissive_shell(int count, uint32_t seed, const float center[3], float radius, vrestir_emissive_triangle* out) {
+    if (count < 0 || !out || !center) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad arguments");
+    for (int i = 0; i < count; i++) {
+        auto rnd = [&](int k) { return lattice(i, k, 17, seed); };
+        float z = 1.f - 2.f * rnd(0), ph = 6.28318530718f * rnd(1), r = std::sqrt(std::max(0.f, 1.f - z * z));
+        float n[3] = {r * std::cos(ph), z, r * std::sin(ph)};
+        float c[3] = {center[0] + n[0] * radius, center[1] + n[1] * radius, center[2] + n[2] * radius};
+        // tangent frame
+        float a[3] = {std::fabs(n[0]) > 0.9f ? 0.f : 1.f, std::fabs(n[0]) > 0.9f ? 1.f : 0.f, 0.f};
+        float t1[3] = {n[1] * a[2] - n[2] * a[1], n[2] * a[0] - n[0] * a[2], n[0] * a[1] - n[1] * a[0]};
+        float l = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]); for (auto& v : t1) v /= l;
+        float t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+        float size = radius * 0.02f * std::exp(0.6f * (rnd(2) + rnd(3) + rnd(4) - 1.5f) * 2.f);   // ~log-normal
+        float rot = 6.28318530718f * rnd(5);
+        vrestir_emissive_triangle& T = out[i];
+        for (int v = 0; v < 3; v++) {
+            float ang = rot + 2.09439510239f * (float)v;
+            for (int k = 0; k < 3; k++) T.posW[v][k] = c[k] + size * (std::cos(ang) * t1[k] + std::sin(ang) * t2[k]);
+        }
+        // inward-facing normal (lights shine on the volume)
+        float e1[3], e2[3];
+        for (int k = 0; k < 3; k++) { e1[k] = T.posW[1][k] - T.posW[0][k]; e2[k] = T.posW[2][k] - T.posW[0][k]; }
+        float cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        float cl = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+        T.area = 0.5f * cl;
+        float sgn = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) > 0.f ? -1.f : 1.f;
+        if (sgn < 0.f) { for (int k = 0; k < 3; k++) std::swap(T.posW[1][k], T.posW[2][k]); }
+        for (int k = 0; k < 3; k++) T.normal[k] = -n[k];
+        float power = 40.f * std::exp(0.8f * (rnd(6) + rnd(7) + rnd(8) - 1.5f) * 2.f);
+        float hue = rnd(9);
+        T.Le[0] = power * (0.6f + 0.4f * hue); T.Le[1] = power * (0.6f + 0.4f * (1.f - std::fabs(2.f * hue - 1.f))); T.Le[2] = power * (1.f - 0.4f * hue);
+    }
+    return VRESTIR_OK;
+}
+
+// Planck-law spectrum -> linear sRGB via Gaussian fits of the CIE 1931 colour-matching functions (Wyman et al. 2013),
+// normalised so that the hottest entry has max component 1; 128 entries for T = 50 K .. 6400 K (50 K steps).
+int vrestir_make_blackbody_lut(float* out) {
+    if (!out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    auto g = [](double x, double mu, double s1, double s2) { double t = (x - mu) / (x < mu ? s1 : s2); return std::exp(-0.5 * t * t); };
+    double rgb[128][3]; double mx = 0;
+    for (int i = 0; i < 128; i++) {
+        double T = 50.0 * (i + 1);
+        double X = 0, Y = 0, Z = 0;
+        for (double lam = 380; lam <= 780; lam += 5) {
+            double l = lam * 1e-9;
+            double B = 3.741771852e-16 / (std::pow(l, 5) * (std::exp(1.438776877e-2 / (l * T)) - 1.0));
+            double xb = 1.056 * g(lam, 599.8, 37.9, 31.0) + 0.362 * g(lam, 442.0, 16.0, 26.7) - 0.065 * g(lam, 501.1, 20.4, 26.2);
+            double yb = 0.821 * g(lam, 568.8, 46.9, 40.5) + 0.286 * g(lam, 530.9, 16.3, 31.1);
+            double zb = 1.217 * g(lam, 437.0, 11.8, 36.0) + 0.681 * g(lam, 459.0, 26.0, 13.8);
+            X += B * xb; Y += B * yb; Z += B * zb;
+        }
+        rgb[i][0] = std::max(0.0, 3.2406 * X - 1.5372 * Y - 0.4986 * Z);
+        rgb[i][1] = std::max(0.0, -0.9689 * X + 1.8758 * Y + 0.0415 * Z);
+        rgb[i][2] = std::max(0.0, 0.0557 * X - 0.2040 * Y + 1.0570 * Z);
+        for (int c = 0; c < 3; c++) mx = std::max(mx, rgb[i][c]);
+    }
+    for (int i = 0; i < 128; i++) { for (int c = 0; c < 3; c++) out[i * 4 + c] = (float)(rgb[i][c] / mx); out[i * 4 + 3] = 0.f; }
+    return VRESTIR_OK;
+}
+
+}  // extern "C"

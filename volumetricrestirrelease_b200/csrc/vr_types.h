@@ -1,0 +1,74 @@
+// vr_types.h — plain structs shared by the kernels (vr_kernels.cu) and the host pass (vr_pass.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vrestir.h"
+
+namespace vrd {
+
+// ------------------------------------------------------------------------------------------------ device scene
+struct DSlot {
+    int valid, top_lev;
+    int dim[3], res[3];
+    float vdel[3];
+    const vrestir_node* nodes[3];
+    const uint32_t* child[3];
+    unsigned long long childCount[3];
+    float bmin[3], bmax[3];
+    float w2m[16];
+    float max_value, compress_scale;
+    int format, channels;
+    const void* atlas;
+};
+
+struct DScene {
+    DSlot slots[VRESTIR_MAX_SLOTS];
+    vrestir_volume_desc vol;
+    const float4* lut;
+    float3 camPos, camU, camV, camW;
+    float prevView[16], prevProj[16];
+    float3 prevU, prevV, prevW, prevPos;
+    int haveEnv, envW, envH;
+    const float4* envTexels;
+    float envIntensity; float3 envTint;
+    float envT[9], envInvT[9], envPrevT[9], envPrevInvT[9];
+    const float* importance; int impDim, impBaseMip; unsigned impOffset[12];
+    int envSamplerType; const float* envAliasThr; const uint32_t* envAliasRedirect; unsigned envAliasCount;
+    int lightCount; const vrestir_light* lights;
+    int triCount; const vrestir_emissive_triangle* tris; const uint4* alias; const float* aliasWeights;
+    float aliasWeightSum, emissiveMul;
+};
+
+struct SamplingOptions {   // VR/HostDeviceSharedDefinitions.h:82-138
+    uint32_t visibilityTrackingMethod, lightingTrackingMethod;
+    int lightSamples, lightingMipLevel, visibilitySamples, visibilityMipLevel;
+    int visibilityUseLinearSampler, lightingUseLinearSampler;
+    float visibilityTStepScale, lightingTStepScale;
+    int useEnvironmentLights, useAnalyticLights, useEmissiveLights;
+    int vertexReuseStartBounce;
+};
+
+// SoA reservoir storage: plane 0 = (runningSum, M, depth, p_y), plane 1 = (lightUV.x, lightUV.y, lightID, sampledPixel);
+// extraBounceStartId is implied by the pixel the record is read from (pixel * (B-1)).
+struct ResBuf { float4* p0; float4* p1; };
+
+struct FrameParams {
+    int W, H, rowBegin, rowEnd;
+    int frameCount, numTotalRounds, maxBounces;
+    int useReference, baselineSpp, initialM, useRussianRoulette, noReuse, useCoarserGrid;
+    int visualizeTransmittance, outputMotionVec;
+    // temporal
+    float temporalMThreshold; uint32_t temporalMIS, reprojectionMode; int reprojectionMip;
+    // spatial
+    int spatialRounds, roundId, roundOffset; uint32_t spatialMIS; int sampleCount;
+    int2 offsets[32];
+    SamplingOptions initial, spatial, fin;
+    ResBuf cur, out, temporal;
+    float3* extCur; float3* extOut; float3* extTemporal;   // packed 12-byte records
+    int2* features; const int2* featuresTemporal;          // (noReflectiveSurface, transmittance bits)
+    float4* refColor;
+    float4* outColor; float2* outMvec;
+};
+
+
+}  // namespace vrd
