@@ -1,0 +1,127 @@
+"""Row-sharded multi-GPU execution of the pass: one process per GPU, contiguous row bands, reservoir-halo exchange.
+
+The path shards by image rows: K0/K1/K5 are per-pixel independent; K3 reads neighbour reservoirs
+within ``mSampleRadius`` rows of the round's *input* buffer and K2 reads the previous frame's reservoir/features at the
+reprojected pixel.  So the only data that crosses GPUs is a halo of reservoir rows (and feature rows for K2), exchanged
+between neighbouring ranks with NCCL send/recv directly on the pass's device buffers (zero-copy tensor views).
+The volume, env map and lights are replicated.  RNG is keyed by absolute pixel + frame, so a sharded frame is
+bit-identical to the single-GPU frame as long as the halo covers the taps (tests/test_multi_gpu.py).
+
+The same code runs on CPU tensors with the gloo backend (host-logic tests, world_size 2).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi as capi
+
+
+def row_bands(height, world_size, align=8):
+    """Contiguous bands, `align`-row aligned (CTA tile height), as even as possible.  Returns [(r0, r1)] per rank."""
+    units = math.ceil(height / align)
+    base, rem = divmod(units, world_size)
+    bands, u = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < rem else 0)
+        bands.append((min(height, u * align), min(height, (u + n) * align)))
+        u += n
+    return bands
+
+
+class _DevPtr:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def device_view(ptr, nbytes, device):
+    """Zero-copy uint8 tensor over a raw CUDA allocation owned by the pass."""
+    return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
+
+
+def exchange_row_halo(planes, band, halo, rank, world_size, bands=None, group=None):
+    """Exchange `halo` rows above/below `band` between neighbouring ranks.
+
+    planes: list of 2-D (rows, row_bytes) uint8 tensors covering the FULL frame height (each rank holds valid data in
+    its own band); after the call rows [r0-halo, r0) and [r1, r1+halo) hold the neighbours' data.
+    """
+    r0, r1 = band
+    ops = []
+    H = planes[0].shape[0]
+    for t in planes:
+        if rank > 0:
+            lo = max(0, r0 - halo)
+            ops.append(dist.P2POp(dist.isend, t[r0:min(r1, r0 + halo)], rank - 1, group))
+            ops.append(dist.P2POp(dist.irecv, t[lo:r0], rank - 1, group))
+        if rank < world_size - 1:
+            hi = min(H, r1 + halo)
+            ops.append(dist.P2POp(dist.isend, t[max(r0, r1 - halo):r1], rank + 1, group))
+            ops.append(dist.P2POp(dist.irecv, t[r1:hi], rank + 1, group))
+    if not ops:
+        return
+    # a neighbour's band can be shorter than the halo: both sides must agree on sizes, so clamp consistently
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+class ShardedPass:
+    """Drives one ``VolumetricReSTIR`` pass per rank over its row band with halo exchanges between the stages."""
+
+    def __init__(self, pass_, width, height, rank, world_size, device, temporal_halo=16):
+        self.p = pass_
+        self.W, self.H = width, height
+        self.rank, self.world = rank, world_size
+        self.device = device
+        self.bands = row_bands(height, world_size)
+        self.band = self.bands[rank]
+        self.temporal_halo = temporal_halo
+        min_band = min(b[1] - b[0] for b in self.bands)
+        self.max_halo = min_band
+
+    def _planes(self, buffer):
+        base, stride, planes = self.p.device_buffer(buffer)
+        n = self.W * self.H
+        out = []
+        if buffer in (capi.BUF_RESERVOIR_0, capi.BUF_RESERVOIR_1, capi.BUF_RESERVOIR_TEMPORAL):
+            for k in range(planes):
+                out.append(device_view(base + k * stride, n * 16, self.device).view(self.H, self.W * 16))
+        elif buffer in (capi.BUF_FEATURES, capi.BUF_FEATURES_TEMPORAL):
+            out.append(device_view(base, n * 8, self.device).view(self.H, self.W * 8))
+        else:
+            B = self.p.params.mMaxBounces
+            if B > 1 and base:
+                out.append(device_view(base, n * (B - 1) * 12, self.device).view(self.H, self.W * (B - 1) * 12))
+        return out
+
+    def _exchange(self, buffers, halo):
+        if self.world == 1:
+            return
+        halo = min(int(halo), self.max_halo)
+        planes = []
+        for b in buffers:
+            planes += self._planes(b)
+        torch.cuda.current_stream().synchronize() if self.device != "cpu" else None
+        exchange_row_halo(planes, self.band, halo, self.rank, self.world)
+
+    def execute(self, out_color_ptr, out_mvec_ptr=None, stream=None):
+        p = self.p
+        prm = p.params
+        B = prm.mMaxBounces
+        radius = int(math.ceil(prm.mSampleRadius))
+        p.execute_stage(0, 0, out_color_ptr, out_mvec_ptr, stream)
+        p.execute_stage(1, 0, out_color_ptr, out_mvec_ptr, stream)
+        p.execute_stage(2, 0, out_color_ptr, out_mvec_ptr, stream)
+        if prm.mEnableSpatialReuse and not prm.mUseReference:
+            for r in range(prm.mSpatialReuseRounds):
+                inb = p.spatial_input_buffer(r)
+                bufs = [inb, capi.BUF_FEATURES] + ([capi.BUF_EXTRA_0 if inb == capi.BUF_RESERVOIR_0 else capi.BUF_EXTRA_1] if B > 1 else [])
+                self._exchange(bufs[:1] + bufs[2:], radius)
+                p.execute_stage(3, r, out_color_ptr, out_mvec_ptr, stream)
+        p.execute_stage(4, 0, out_color_ptr, out_mvec_ptr, stream)
+        p.execute_stage(5, 0, out_color_ptr, out_mvec_ptr, stream)
+        p.execute_stage(6, 0, out_color_ptr, out_mvec_ptr, stream)
+        if prm.mEnableTemporalReuse and not prm.mUseReference:
+            # history for the next frame's K2: reprojected taps land within `temporal_halo` rows of the band
+            bufs = [capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL] + ([capi.BUF_EXTRA_TEMPORAL] if B > 1 else [])
+            self._exchange(bufs, self.temporal_halo)
