@@ -325,6 +325,10 @@ int vrestir_get_timings(vrestir_pass* pass, vrestir_timings* out);
 /* number of kernels this library launched since create (claim for bench.py's gpu_launches) */
 int vrestir_get_launch_count(const vrestir_pass* pass, uint64_t* out);
 
+/* Diagnostics: world-space rays whose hierarchical DDA ran >= 1024 outer iterations since the last call
+ * (8 floats each: origin, dir, mip (+100 when vertex-centred), iterations; first 64) and their total count. */
+int vrestir_debug_long_rays(vrestir_pass* pass, float* out64x8, uint32_t* count);
+
 /* Buffer access.  Host copies use the AoS views documented at the enum; `bytes` must match vrestir_buffer_bytes. */
 int vrestir_buffer_bytes(const vrestir_pass* pass, int buffer, size_t* bytes);
 int vrestir_get_buffer(vrestir_pass* pass, int buffer, void* host_dst, size_t bytes);

@@ -486,7 +486,10 @@ struct HDDAState {
     }
     void Step() {
         t.x = t.y;
-        tSide = tSide + toF(mask) * tDel;
+        // Deliberate deviation from gvdbDda.slang:153 (`tSide += float3(mask) * tDel`): for a ray with an exactly-zero direction
+        // component tDel is +inf and 0*inf poisons tSide with NaN, after which every mask is 0 and the traversal spins until
+        // the 4096-iteration cap.  The select form is identical for finite tDel and traverses axis-parallel rays correctly.
+        tSide = f3(mask.x ? tSide.x + tDel.x : tSide.x, mask.y ? tSide.y + tDel.y : tSide.y, mask.z ? tSide.z + tDel.z : tSide.z);
         p = {p.x + mask.x * pStep.x, p.y + mask.y * pStep.y, p.z + mask.z * pStep.z};
     }
 };
@@ -1992,7 +1995,10 @@ void stageFinal(Pass& p, const FrameSetup& fs, int buf, float* out_color) {
             if (cur.runningSum > 0.f) {
                 Ray ray = {pos, normalize(camRayDirNN(U, V, Wv, x, y, p.W, p.H)), 0, cur.depth};
                 ExtraProvider prov{p.ext[buf].data()};
+                uint64_t taps0 = tl_cnt.taps;
                 float3 col = evaluate_F(c, cur, prov, ray, sg, fs.fin, noReuse);
+                if (getenv("VRO_DEBUG_HEAVY") && tl_cnt.taps - taps0 > 20000)
+                    fprintf(stderr, "heavy pixel %d %d taps %llu depth %g lightID %d uv %.9g %.9g\n", x, y, (unsigned long long)(tl_cnt.taps - taps0), cur.depth, cur.lightID, cur.lightUV.x, cur.lightUV.y);
                 float Wt = cur.p_y == 0.0f ? 1.f : cur.runningSum / (cur.p_y * cur.M);
                 col *= Wt;
                 outputColor += col;

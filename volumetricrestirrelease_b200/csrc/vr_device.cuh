@@ -25,6 +25,9 @@ namespace vrd {
 #define VRD_NOINLINE __device__ __noinline__
 
 __constant__ DScene c_scene;   // this header is included by exactly one translation unit (vr_kernels.cu)
+// diagnostics: rays whose hierarchical DDA ran >= 1024 outer iterations (origin, dir, mip, iterations), first 64
+__device__ float g_dbgRays[64 * 8];
+__device__ unsigned g_dbgCount;
 
 
 // ------------------------------------------------------------------------------------------------ math
@@ -341,7 +344,9 @@ struct HDDAState {
     }
     VRD void Step() {
         tx = ty;
-        tSide = tSide + make_float3((float)mask.x, (float)mask.y, (float)mask.z) * tDel;
+        // select instead of gvdbDda.slang:153's mask*tDel: identical for finite tDel, and an exactly-zero direction component
+        // (tDel = +inf) no longer turns tSide into NaN (0*inf), which made the traversal spin to the 4096-iteration cap
+        tSide = make_float3(mask.x ? tSide.x + tDel.x : tSide.x, mask.y ? tSide.y + tDel.y : tSide.y, mask.z ? tSide.z + tDel.z : tSide.z);
         p = make_int3(p.x + mask.x * pStep.x, p.y + mask.y * pStep.y, p.z + mask.z * pStep.z);
     }
 };
@@ -413,6 +418,14 @@ __device__ void VolumeTrackingGVDB(const Ray& rWorld, int mipLevel, SampleGenera
         while (lev <= topLev && dda.tx > tMax[lev]) {
             lev++;
             if (lev <= topLev) dda.Prepare(vminL[lev], g.vdel[lev]);
+        }
+    }
+    if (iter >= 1024) {
+        unsigned k = atomicAdd(&g_dbgCount, 1u);
+        if (k < 64) {
+            float* o = &g_dbgRays[k * 8];
+            o[0] = rWorld.origin.x; o[1] = rWorld.origin.y; o[2] = rWorld.origin.z; o[3] = rWorld.dir.x; o[4] = rWorld.dir.y; o[5] = rWorld.dir.z;
+            o[6] = (float)(mipLevel + (vertexCenter ? 100 : 0)); o[7] = (float)iter;
         }
     }
     adapter.ExecuteEndStep();

@@ -518,6 +518,13 @@ __global__ void k_res_from_aos(ResBuf b, const vrestir_reservoir* in, int n) {
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 gridFor(const FrameParams& fp) { return dim3((fp.W + 15) / 16, (fp.rowEnd - fp.rowBegin + 7) / 8); }
 
+cudaError_t readDebugRays(float* out64x8, unsigned* count) {
+    cudaError_t e = cudaMemcpyFromSymbol(count, g_dbgCount, 4);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out64x8, g_dbgRays, sizeof(float) * 64 * 8);
+    unsigned zero = 0;
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_dbgCount, &zero, 4);
+    return e;
+}
 cudaError_t uploadScene(const DScene& s, cudaStream_t st) { return cudaMemcpyToSymbolAsync(c_scene, &s, sizeof(DScene), 0, cudaMemcpyHostToDevice, st); }
 
 #define VR_DISPATCH_B(kern, fp, st)                                                              \

@@ -3,6 +3,7 @@
 #include "vr_types.h"
 
 namespace vrd {
+cudaError_t readDebugRays(float* out64x8, unsigned* count);
 cudaError_t uploadScene(const DScene& s, cudaStream_t st);
 cudaError_t launchFeatures(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchInitial(const FrameParams& fp, cudaStream_t st);

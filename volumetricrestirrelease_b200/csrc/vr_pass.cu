@@ -807,6 +807,16 @@ int vrestir_spatial_input_buffer(const vrestir_pass* p, int round, int* buffer) 
     return VRESTIR_OK;
 }
 
+int vrestir_debug_long_rays(vrestir_pass* p, float* out64x8, uint32_t* count) {
+    if (!p || !out64x8 || !count) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    unsigned c = 0;
+    CK(readDebugRays(out64x8, &c));
+    *count = c;
+    return VRESTIR_OK;
+}
+
 int vrestir_scene_load_vbx(const char*, int, const vrestir_scene_params*, vrestir_scene**) {
     return setError(VRESTIR_ERR_UNSUPPORTED, ".vbx loading is not implemented yet (SURVEY.md 8f rank 1)");
 }

@@ -167,6 +167,12 @@ class VolumetricReSTIR:
         capi.check(self._lib.vrestir_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in capi.Timings._fields_}
 
+    def debug_long_rays(self):
+        out = np.zeros((64, 8), dtype=np.float32)
+        n = C.c_uint32()
+        capi.check(self._lib.vrestir_debug_long_rays(self._h, out.ctypes.data, C.byref(n)))
+        return out[:min(64, n.value)], int(n.value)
+
     def launch_count(self):
         n = C.c_uint64()
         capi.check(self._lib.vrestir_get_launch_count(self._h, C.byref(n)))
