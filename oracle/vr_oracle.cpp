@@ -9,10 +9,10 @@
  * expression below is evaluated exactly as written, left to right.
  *
  * Hardware behaviours that are not in the reference source and are pinned here:
- *   - trilinear SampleLevel on the brick atlas: exact fp32 lerp x, then y, then z, lerp(a,b,t) = a + t*(b-a),
+ *   - trilinear SampleLevel on the brick atlas: fp32 lerp x, then y, then z with lerp(a,b,t) = fma(t, b-a, a),
  *     texel centres at +0.5, fetched from the brick's own 10^3 apron-inclusive block (never crosses bricks);
  *   - coarse/conservative mips are 8-bit UNORM (the reference's ATLAS_COMPRESSION==1 variant, F/Scene/Scene.cpp:3164-3174,
- *     instead of BC4): texel = u8 * fl(1/255);
+ *     instead of BC4): point fetch = u8 * fl(1/255); trilinear = filter the codes, then * fl(1/255);
  *   - lat-long env lookup: bilinear, wrap U, clamp V, texel centres at +0.5;
  *   - importance-map mip chain: 2x2 box, ((a+b)+(c+d))*0.25;
  *   - structured-buffer reads out of range return 0; float->int conversions saturate, NaN -> 0;
@@ -289,16 +289,20 @@ inline const vrestir_node* getNodeAtPoint(const vrestir_grid_slot& g, float3 pos
 }
 
 // ---- brick-pool voxel fetch (replaces the 3-D atlas texture; layout in include/vrestir.h) ----
-inline float atlasVoxel(const vrestir_grid_slot& g, uint32_t brick, int ix, int iy, int iz, int ch = 0) {
-    // ix,iy,iz in [-1, 8]; outside the block = border colour 0 (VR/VolumetricReSTIR.cpp:78-85)
+inline float atlasVoxelRaw(const vrestir_grid_slot& g, uint32_t brick, int ix, int iy, int iz, int ch = 0) {
+    // stored code (UNORM8 code as float, or the fp32 value); ix,iy,iz in [-1, 8]; outside the block = border colour 0
     if (ix < -1 || iy < -1 || iz < -1 || ix > 8 || iy > 8 || iz > 8) return 0.f;
     size_t idx = ((size_t)brick * g.atlas_channels + ch) * VRESTIR_BRICK_VOXELS + (size_t)((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1);
     tl_cnt.voxels++;
-    if (g.atlas_format == VRESTIR_ATLAS_UNORM8) { tl_cnt.vbytes += 1; return (float)((const uint8_t*)g.atlas)[idx] * 0.003921568859368563f; }
+    if (g.atlas_format == VRESTIR_ATLAS_UNORM8) { tl_cnt.vbytes += 1; return (float)((const uint8_t*)g.atlas)[idx]; }
     tl_cnt.vbytes += 4;
     return ((const float*)g.atlas)[idx];
 }
-inline float lerpf(float a, float b, float t) { return a + t * (b - a); }
+inline float atlasVoxel(const vrestir_grid_slot& g, uint32_t brick, int ix, int iy, int iz, int ch = 0) {
+    float r = atlasVoxelRaw(g, brick, ix, iy, iz, ch);
+    return g.atlas_format == VRESTIR_ATLAS_UNORM8 ? r * 0.003921568859368563f : r;
+}
+inline float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }   // pinned: one fused multiply-add
 // SampleLevel with the linear border sampler at brick-local position p (voxel units, brick interior = [0,8)^3)
 inline float sampleBrickLinear(const vrestir_grid_slot& g, uint32_t brick, float3 p, int ch = 0) {
     tl_cnt.taps++;
@@ -306,13 +310,15 @@ inline float sampleBrickLinear(const vrestir_grid_slot& g, uint32_t brick, float
     float fx0 = floorf(qx), fy0 = floorf(qy), fz0 = floorf(qz);
     int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
     float fx = qx - fx0, fy = qy - fy0, fz = qz - fz0;
-    float v000 = atlasVoxel(g, brick, ix, iy, iz, ch), v100 = atlasVoxel(g, brick, ix + 1, iy, iz, ch);
-    float v010 = atlasVoxel(g, brick, ix, iy + 1, iz, ch), v110 = atlasVoxel(g, brick, ix + 1, iy + 1, iz, ch);
-    float v001 = atlasVoxel(g, brick, ix, iy, iz + 1, ch), v101 = atlasVoxel(g, brick, ix + 1, iy, iz + 1, ch);
-    float v011 = atlasVoxel(g, brick, ix, iy + 1, iz + 1, ch), v111 = atlasVoxel(g, brick, ix + 1, iy + 1, iz + 1, ch);
+    float v000 = atlasVoxelRaw(g, brick, ix, iy, iz, ch), v100 = atlasVoxelRaw(g, brick, ix + 1, iy, iz, ch);
+    float v010 = atlasVoxelRaw(g, brick, ix, iy + 1, iz, ch), v110 = atlasVoxelRaw(g, brick, ix + 1, iy + 1, iz, ch);
+    float v001 = atlasVoxelRaw(g, brick, ix, iy, iz + 1, ch), v101 = atlasVoxelRaw(g, brick, ix + 1, iy, iz + 1, ch);
+    float v011 = atlasVoxelRaw(g, brick, ix, iy + 1, iz + 1, ch), v111 = atlasVoxelRaw(g, brick, ix + 1, iy + 1, iz + 1, ch);
+    // pinned filter: fp32 fma-lerp x, y, z on the stored codes; UNORM8 codes are scaled by fl(1/255) once, after filtering
     float c00 = lerpf(v000, v100, fx), c10 = lerpf(v010, v110, fx), c01 = lerpf(v001, v101, fx), c11 = lerpf(v011, v111, fx);
     float c0 = lerpf(c00, c10, fy), c1 = lerpf(c01, c11, fy);
-    return lerpf(c0, c1, fz);
+    float r = lerpf(c0, c1, fz);
+    return g.atlas_format == VRESTIR_ATLAS_UNORM8 ? r * 0.003921568859368563f : r;
 }
 inline float sampleBrickPoint(const vrestir_grid_slot& g, uint32_t brick, float3 p, int ch = 0) {
     tl_cnt.taps++;

@@ -58,7 +58,7 @@ VRD float fsign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 VRD int f2i(float v) { return __float2int_rz(v); }            // saturating, NaN -> 0 (D3D ftoi)
 VRD uint32_t f2u(float v) { return __float2uint_rz(v); }
 VRD float luminance(float3 c) { return dot(c, f3(0.2126f, 0.7152f, 0.0722f)); }
-VRD float lerpf(float a, float b, float t) { return a + t * (b - a); }
+VRD float lerpf(float a, float b, float t) { return __fmaf_rn(t, b - a, a); }   // pinned: one fused multiply-add (oracle: fmaf)
 VRD float3 v3(const float* a) { return make_float3(a[0], a[1], a[2]); }
 VRD float3 mulPoint(float3 p, const float* M) {
     return make_float3(p.x * M[0] + p.y * M[4] + p.z * M[8] + M[12], p.x * M[1] + p.y * M[5] + p.z * M[9] + M[13],
@@ -161,11 +161,16 @@ VRD uint32_t getBrickAtPoint(const DSlot& g, float3 pos, float3& vminOut) {
 
 // ---- brick-pool fetch ----
 template <bool CHECKED>
-VRD float atlasVoxel(const DSlot& g, uint32_t brick, int ix, int iy, int iz, int ch = 0) {
+VRD float atlasVoxelRaw(const DSlot& g, uint32_t brick, int ix, int iy, int iz, int ch = 0) {   // stored code, no UNORM scale
     if (CHECKED) { if ((unsigned)(ix + 1) > 9u || (unsigned)(iy + 1) > 9u || (unsigned)(iz + 1) > 9u) return 0.f; }
-    size_t idx = ((size_t)brick * g.channels + ch) * VRESTIR_BRICK_VOXELS + (size_t)(((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1));
-    if (g.format == VRESTIR_ATLAS_UNORM8) return (float)__ldg(&((const uint8_t*)g.atlas)[idx]) * kUnorm8;
+    const unsigned idx = (brick * (unsigned)g.channels + (unsigned)ch) * VRESTIR_BRICK_VOXELS + (unsigned)(((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1));
+    if (g.format == VRESTIR_ATLAS_UNORM8) return (float)__ldg(&((const uint8_t*)g.atlas)[idx]);
     return __ldg(&((const float*)g.atlas)[idx]);
+}
+template <bool CHECKED>
+VRD float atlasVoxel(const DSlot& g, uint32_t brick, int ix, int iy, int iz, int ch = 0) {
+    const float r = atlasVoxelRaw<CHECKED>(g, brick, ix, iy, iz, ch);
+    return g.format == VRESTIR_ATLAS_UNORM8 ? r * kUnorm8 : r;
 }
 template <bool CHECKED>
 VRD float sampleBrickLinear(const DSlot& g, uint32_t brick, float3 p, int ch = 0) {
@@ -174,26 +179,37 @@ VRD float sampleBrickLinear(const DSlot& g, uint32_t brick, float3 p, int ch = 0
     int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
     float fx = qx - fx0, fy = qy - fy0, fz = qz - fz0;
     float v000, v100, v010, v110, v001, v101, v011, v111;
+    const bool u8 = g.format == VRESTIR_ATLAS_UNORM8;
     if (!CHECKED) {
-        size_t base = ((size_t)brick * g.channels + ch) * VRESTIR_BRICK_VOXELS + (size_t)(((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1));
-        if (g.format == VRESTIR_ATLAS_UNORM8) {
-            const uint8_t* a = (const uint8_t*)g.atlas + base;
-            v000 = (float)__ldg(a) * kUnorm8; v100 = (float)__ldg(a + 1) * kUnorm8; v010 = (float)__ldg(a + 10) * kUnorm8; v110 = (float)__ldg(a + 11) * kUnorm8;
-            v001 = (float)__ldg(a + 100) * kUnorm8; v101 = (float)__ldg(a + 101) * kUnorm8; v011 = (float)__ldg(a + 110) * kUnorm8; v111 = (float)__ldg(a + 111) * kUnorm8;
+        if (u8 && g.quads) {
+            // 2 x LDG.32: each word holds the 2x2 xy-neighbourhood of one z plane (raw UNORM8 codes)
+            const uint32_t* q = g.quads + (brick * 810u + (unsigned)(((iz + 1) * 9 + (iy + 1)) * 9 + (ix + 1)));
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 81);
+            v000 = (float)(w0 & 0xffu); v100 = (float)((w0 >> 8) & 0xffu); v010 = (float)((w0 >> 16) & 0xffu); v110 = (float)(w0 >> 24);
+            v001 = (float)(w1 & 0xffu); v101 = (float)((w1 >> 8) & 0xffu); v011 = (float)((w1 >> 16) & 0xffu); v111 = (float)(w1 >> 24);
         } else {
-            const float* a = (const float*)g.atlas + base;
-            v000 = __ldg(a); v100 = __ldg(a + 1); v010 = __ldg(a + 10); v110 = __ldg(a + 11);
-            v001 = __ldg(a + 100); v101 = __ldg(a + 101); v011 = __ldg(a + 110); v111 = __ldg(a + 111);
+            const unsigned base = (brick * (unsigned)g.channels + (unsigned)ch) * VRESTIR_BRICK_VOXELS + (unsigned)(((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1));
+            if (u8) {
+                const uint8_t* a = (const uint8_t*)g.atlas + base;
+                v000 = (float)__ldg(a); v100 = (float)__ldg(a + 1); v010 = (float)__ldg(a + 10); v110 = (float)__ldg(a + 11);
+                v001 = (float)__ldg(a + 100); v101 = (float)__ldg(a + 101); v011 = (float)__ldg(a + 110); v111 = (float)__ldg(a + 111);
+            } else {
+                const float* a = (const float*)g.atlas + base;
+                v000 = __ldg(a); v100 = __ldg(a + 1); v010 = __ldg(a + 10); v110 = __ldg(a + 11);
+                v001 = __ldg(a + 100); v101 = __ldg(a + 101); v011 = __ldg(a + 110); v111 = __ldg(a + 111);
+            }
         }
     } else {
-        v000 = atlasVoxel<true>(g, brick, ix, iy, iz, ch); v100 = atlasVoxel<true>(g, brick, ix + 1, iy, iz, ch);
-        v010 = atlasVoxel<true>(g, brick, ix, iy + 1, iz, ch); v110 = atlasVoxel<true>(g, brick, ix + 1, iy + 1, iz, ch);
-        v001 = atlasVoxel<true>(g, brick, ix, iy, iz + 1, ch); v101 = atlasVoxel<true>(g, brick, ix + 1, iy, iz + 1, ch);
-        v011 = atlasVoxel<true>(g, brick, ix, iy + 1, iz + 1, ch); v111 = atlasVoxel<true>(g, brick, ix + 1, iy + 1, iz + 1, ch);
+        v000 = atlasVoxelRaw<true>(g, brick, ix, iy, iz, ch); v100 = atlasVoxelRaw<true>(g, brick, ix + 1, iy, iz, ch);
+        v010 = atlasVoxelRaw<true>(g, brick, ix, iy + 1, iz, ch); v110 = atlasVoxelRaw<true>(g, brick, ix + 1, iy + 1, iz, ch);
+        v001 = atlasVoxelRaw<true>(g, brick, ix, iy, iz + 1, ch); v101 = atlasVoxelRaw<true>(g, brick, ix + 1, iy, iz + 1, ch);
+        v011 = atlasVoxelRaw<true>(g, brick, ix, iy + 1, iz + 1, ch); v111 = atlasVoxelRaw<true>(g, brick, ix + 1, iy + 1, iz + 1, ch);
     }
+    // pinned filter: fp32 fma-lerp x, y, z on the stored codes; UNORM8 codes are scaled by fl(1/255) once, after filtering
     float c00 = lerpf(v000, v100, fx), c10 = lerpf(v010, v110, fx), c01 = lerpf(v001, v101, fx), c11 = lerpf(v011, v111, fx);
     float c0 = lerpf(c00, c10, fy), c1 = lerpf(c01, c11, fy);
-    return lerpf(c0, c1, fz);
+    float r = lerpf(c0, c1, fz);
+    return u8 ? r * kUnorm8 : r;
 }
 template <bool CHECKED>
 VRD float sampleBrickPoint(const DSlot& g, uint32_t brick, float3 p, int ch = 0) {
@@ -205,7 +221,7 @@ VRD float getValueAtPoint(const DSlot& g, float3 pos, bool linear, int ch = 0) {
     uint32_t brick = getBrickAtPoint(g, pos, vmin);
     if (brick == ID_UNDEFL) return 0.f;
     float3 p_rel = pos - vmin;
-    return linear ? sampleBrickLinear<true>(g, brick, p_rel, ch) : sampleBrickPoint<true>(g, brick, p_rel, ch);
+    return linear ? sampleBrickLinear<false>(g, brick, p_rel, ch) : sampleBrickPoint<false>(g, brick, p_rel, ch);   // p_rel in [0,8)^3 by construction
 }
 
 // ------------------------------------------------------------------------------------------------ VolumeBase
@@ -316,24 +332,28 @@ VRD Ray makeRay(float3 o, float3 d, float tmin, float tmax) { Ray r; r.origin = 
 
 // ------------------------------------------------------------------------------------------------ HDDA
 struct HDDAState {
-    float3 pos, dir; int3 pStep; float3 tDel; float tx, ty; int3 p; float3 tSide; int3 mask;
+    // invDir = 1/dir once per ray.  Node spans are powers of two (8 / 128 voxels per child, 1 inside a brick), so
+    // |vdel * invDir| and (x - vmin) * (1/vdel) are bit-identical to the reference's |vdel / dir| and (x - vmin) / vdel
+    // (F/Scene/GVDB/gvdbDda.slang:121-135) while saving six IEEE divisions per level change.
+    float3 pos, dir, invDir; float3 tDel; float tx, ty; int3 p; float3 tSide; int3 mask;
     VRD void SetFromRay(float3 startPos, float3 startDir, float t0) {
         pos = startPos; dir = startDir;
-        pStep = make_int3(dir.x >= 0 ? 1 : -1, dir.y >= 0 ? 1 : -1, dir.z >= 0 ? 1 : -1);
+        invDir = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
         tx = t0; ty = 0.f;
     }
-    VRD void Prepare(float3 vmin, float vdel) {
-        tDel = make_float3(fabsf(vdel / dir.x), fabsf(vdel / dir.y), fabsf(vdel / dir.z));
-        float3 pFlt = (pos + tx * dir - vmin) / f3(vdel);
+    VRD float3 stepSign() const { return make_float3(dir.x >= 0 ? 1.f : -1.f, dir.y >= 0 ? 1.f : -1.f, dir.z >= 0 ? 1.f : -1.f); }
+    VRD void Prepare(float3 vmin, float vdel, float invVdel) {
+        tDel = make_float3(fabsf(vdel * invDir.x), fabsf(vdel * invDir.y), fabsf(vdel * invDir.z));
+        float3 pFlt = (pos + tx * dir - vmin) * invVdel;
         float3 fl = make_float3(floorf(pFlt.x), floorf(pFlt.y), floorf(pFlt.z));
-        tSide = ((fl - pFlt + f3(0.5f)) * make_float3((float)pStep.x, (float)pStep.y, (float)pStep.z) + f3(0.5f)) * tDel + f3(tx);
+        tSide = ((fl - pFlt + f3(0.5f)) * stepSign() + f3(0.5f)) * tDel + f3(tx);
         p = make_int3((int)fl.x, (int)fl.y, (int)fl.z);
     }
     VRD void PrepareLeaf(float3 vmin) {
-        tDel = make_float3(fabsf(1.0f / dir.x), fabsf(1.0f / dir.y), fabsf(1.0f / dir.z));
+        tDel = make_float3(fabsf(invDir.x), fabsf(invDir.y), fabsf(invDir.z));
         float3 pFlt = pos + tx * dir - vmin;
         float3 fl = make_float3(floorf(pFlt.x), floorf(pFlt.y), floorf(pFlt.z));
-        tSide = ((fl - pFlt + f3(0.5f)) * make_float3((float)pStep.x, (float)pStep.y, (float)pStep.z) + f3(0.5f)) * tDel + f3(tx);
+        tSide = ((fl - pFlt + f3(0.5f)) * stepSign() + f3(0.5f)) * tDel + f3(tx);
         p = make_int3((int)fl.x, (int)fl.y, (int)fl.z);
     }
     VRD void Next() {
@@ -347,52 +367,59 @@ struct HDDAState {
         // select instead of gvdbDda.slang:153's mask*tDel: identical for finite tDel, and an exactly-zero direction component
         // (tDel = +inf) no longer turns tSide into NaN (0*inf), which made the traversal spin to the 4096-iteration cap
         tSide = make_float3(mask.x ? tSide.x + tDel.x : tSide.x, mask.y ? tSide.y + tDel.y : tSide.y, mask.z ? tSide.z + tDel.z : tSide.z);
-        p = make_int3(p.x + mask.x * pStep.x, p.y + mask.y * pStep.y, p.z + mask.z * pStep.z);
+        p = make_int3(p.x + (mask.x ? (dir.x >= 0 ? 1 : -1) : 0), p.y + (mask.y ? (dir.y >= 0 ? 1 : -1) : 0), p.z + (mask.z ? (dir.z >= 0 ? 1 : -1) : 0));
     }
 };
 VRD bool inRange(int3 p, int hiExclusive) { return (unsigned)p.x < (unsigned)hiExclusive && (unsigned)p.y < (unsigned)hiExclusive && (unsigned)p.z < (unsigned)hiExclusive; }
 
-// VR/VolumeUtils.slang:171-282.  The adapter sees (dda, brick min corner, brick id, scaled brick bounds).
+// VR/VolumeUtils.slang:171-282.  The adapter sees (dda, brick min corner, brick id, leaf node id).
+// Per-level state (only levels 1 and 2 exist) lives in scalar registers, not in dynamically indexed local arrays.
 template <class Adapter>
 __device__ void VolumeTrackingGVDB(const Ray& rWorld, int mipLevel, SampleGenerator& sg, Adapter& adapter, bool vertexCenter) {
     const DSlot& g = c_scene.slots[mipLevel];
-    uint32_t nodeid[3]; float tMax[3]; uint32_t link[3]; float3 vminL[3];
     const float epsilon = 0.01f;
     int lev = g.top_lev;
     const int topLev = lev;
-    nodeid[lev] = 0;
     Ray ray = WorldToMedium(rWorld, mipLevel);
     if (vertexCenter) ray.origin = ray.origin - f3(0.5f);
     float tNear, tFar;
     if (!IntersectVolumeBound(ray, tNear, tFar, mipLevel, vertexCenter)) { adapter.ExecuteEndStep(); return; }
     adapter.SetRayInfo(tNear, tFar, ray);
     adapter.ExecuteStartStep();
+    const int res1 = g.res[1], res2 = g.res[2], dim1 = g.dim[1], dim2 = g.dim[2];
+    const float vdel1 = g.vdel[1], vdel2 = g.vdel[2], ivdel1 = 1.0f / vdel1, ivdel2 = 1.0f / vdel2;
+    const unsigned cnt1 = g.childCount32[1], cnt2 = g.childCount32[2];
+    uint32_t link1 = ID_UNDEFL, link2 = ID_UNDEFL; float3 vmin1 = f3(0.f), vmin2 = f3(0.f); float tMax1 = 0.f, tMax2 = 0.f;
     {
         NodeHead h = loadNodeHead(g, lev, 0);
-        link[lev] = (uint32_t)h.a.w; vminL[lev] = nodePos(h.a);
+        if (lev == 2) { link2 = (uint32_t)h.a.w; vmin2 = nodePos(h.a); tMax2 = tFar; }
+        else { link1 = (uint32_t)h.a.w; vmin1 = nodePos(h.a); tMax1 = tFar; }
     }
-    tMax[lev] = tFar;
     int iter = 0;
     HDDAState dda;
     dda.SetFromRay(ray.origin, ray.dir, tNear + epsilon);
-    dda.Prepare(vminL[lev], g.vdel[lev]);
+    if (lev == 2) dda.Prepare(vmin2, vdel2, ivdel2); else dda.Prepare(vmin1, vdel1, ivdel1);
     if (vertexCenter) {
+        const int r = lev == 2 ? res2 : res1;
         int it = 0;
-        while (it++ < 3 && (dda.p.x < 0 || dda.p.y < 0 || dda.p.z < 0 || dda.p.x > g.res[lev] || dda.p.y > g.res[lev] || dda.p.z > g.res[lev])) {
+        while (it++ < 3 && (dda.p.x < 0 || dda.p.y < 0 || dda.p.z < 0 || dda.p.x > r || dda.p.y > r || dda.p.z > r)) {
             dda.Next(); dda.Step(); dda.tx += epsilon;
         }
     }
-    for (; iter < 4096 && lev > 0 && lev <= topLev && inRange(dda.p, g.res[lev] + 1); iter++) {
+    for (; iter < 4096 && lev > 0 && lev <= topLev && inRange(dda.p, (lev == 2 ? res2 : res1) + 1); iter++) {
         dda.Next();
-        const int b = (((dda.p.z << g.dim[lev]) + dda.p.y) << g.dim[lev]) + dda.p.x;
+        const int dm = lev == 2 ? dim2 : dim1;
+        const int b = (((dda.p.z << dm) + dda.p.y) << dm) + dda.p.x;
         uint32_t childNodeId;
         {
-            const uint32_t listid = link[lev];
+            const uint32_t listid = lev == 2 ? link2 : link1;
             if (listid == ID_UNDEFL) childNodeId = ID_UNDEFL;
             else {
-                const long long r3 = (long long)(g.res[lev] * g.res[lev] * g.res[lev]);
-                const long long idx = (long long)listid * r3 + (long long)b;
-                childNodeId = (idx < 0 || (unsigned long long)idx >= g.childCount[lev]) ? 0u : __ldg(&g.child[lev][idx]);
+                // p == res passes the inclusive bound (VR/VolumeUtils.slang:231) and aliases into the list like the shader's
+                // ByteAddressBuffer load; outside the whole list D3D returns 0
+                const int r = lev == 2 ? res2 : res1;
+                const long long idx = (long long)listid * (long long)(r * r * r) + (long long)b;
+                childNodeId = (idx < 0 || idx >= (long long)(lev == 2 ? cnt2 : cnt1)) ? 0u : __ldg(&g.child[lev][idx]);
             }
         }
         if (childNodeId != ID_UNDEFL) {
@@ -404,20 +431,19 @@ __device__ void VolumeTrackingGVDB(const Ray& rWorld, int mipLevel, SampleGenera
                 dda.Step();
                 dda.tx += epsilon;
             } else {
-                lev--;
-                nodeid[lev] = childNodeId;
-                NodeHead h = loadNodeHead(g, lev, childNodeId);
-                link[lev] = (uint32_t)h.a.w; vminL[lev] = nodePos(h.a);
-                tMax[lev] = dda.ty;
-                dda.Prepare(vminL[lev], g.vdel[lev]);
+                lev = 1;
+                NodeHead h = loadNodeHead(g, 1, childNodeId);
+                link1 = (uint32_t)h.a.w; vmin1 = nodePos(h.a);
+                tMax1 = dda.ty;
+                dda.Prepare(vmin1, vdel1, ivdel1);
             }
         } else {
             dda.Step();
             dda.tx += epsilon;
         }
-        while (lev <= topLev && dda.tx > tMax[lev]) {
+        while (lev <= topLev && dda.tx > (lev == 2 ? tMax2 : tMax1)) {
             lev++;
-            if (lev <= topLev) dda.Prepare(vminL[lev], g.vdel[lev]);
+            if (lev <= topLev) dda.Prepare(vmin2, vdel2, ivdel2);
         }
     }
     if (iter >= 1024) {

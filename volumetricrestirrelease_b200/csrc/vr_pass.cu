@@ -33,7 +33,7 @@ using vr::setError;
 
 namespace {
 
-struct DevSlot { void* nodes[3] = {nullptr, nullptr, nullptr}; void* child[3] = {nullptr, nullptr, nullptr}; void* atlas = nullptr; size_t atlasBytes = 0; };
+struct DevSlot { void* nodes[3] = {nullptr, nullptr, nullptr}; void* child[3] = {nullptr, nullptr, nullptr}; void* atlas = nullptr; size_t atlasBytes = 0; void* quads = nullptr; size_t quadBytes = 0; };
 
 struct KeyDesc { const char* name; size_t off; int type; };
 #define K_I(f) {#f, offsetof(vrestir_params, f), 0}
@@ -120,7 +120,8 @@ int ensureBuffers(vrestir_pass* p) {
 void freeSlot(DevSlot& d) {
     for (int l = 0; l < 3; l++) { if (d.nodes[l]) cudaFree(d.nodes[l]); if (d.child[l]) cudaFree(d.child[l]); d.nodes[l] = d.child[l] = nullptr; }
     if (d.atlas) cudaFree(d.atlas);
-    d.atlas = nullptr; d.atlasBytes = 0;
+    if (d.quads) cudaFree(d.quads);
+    d.atlas = nullptr; d.atlasBytes = 0; d.quads = nullptr; d.quadBytes = 0;
 }
 
 int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
@@ -141,8 +142,11 @@ int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
             CK(cudaMalloc(&d.child[l], (size_t)g.childlist_count[l] * 4));
             CK(cudaMemcpy(d.child[l], g.childlist[l], (size_t)g.childlist_count[l] * 4, cudaMemcpyHostToDevice));
         }
+        if (g.childlist_count[l] >= (1ull << 31)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "child list too large");
         s.nodes[l] = (const vrestir_node*)d.nodes[l]; s.child[l] = (const uint32_t*)d.child[l]; s.childCount[l] = g.childlist_count[l];
+        s.childCount32[l] = (unsigned)g.childlist_count[l];
     }
+    if ((unsigned long long)g.brick_count * g.atlas_channels * VRESTIR_BRICK_VOXELS >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "brick pool too large for 32-bit voxel indices");
     for (int i = 0; i < 3; i++) { s.bmin[i] = g.bmin[i]; s.bmax[i] = g.bmax[i]; }
     memcpy(s.w2m, g.world_to_medium, 64);
     s.max_value = g.max_value; s.compress_scale = g.compress_scale; s.format = g.atlas_format; s.channels = g.atlas_channels;
@@ -153,6 +157,24 @@ int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
         d.atlasBytes = bytes;
     }
     s.atlas = d.atlas;
+    s.quads = nullptr;
+    if (bytes && g.atlas_format == VRESTIR_ATLAS_UNORM8 && g.atlas_channels == 1) {
+        // device-only repack for trilinear fetches: per brick [10][9][9] words, word(z,y,x) = codes (x,y) (x+1,y) (x,y+1) (x+1,y+1) of plane z
+        std::vector<uint32_t> q((size_t)g.brick_count * 810);
+        const uint8_t* a = (const uint8_t*)g.atlas;
+        for (uint32_t b = 0; b < g.brick_count; b++) {
+            const uint8_t* blk = a + (size_t)b * VRESTIR_BRICK_VOXELS;
+            uint32_t* o = q.data() + (size_t)b * 810;
+            for (int z = 0; z < 10; z++) for (int y = 0; y < 9; y++) for (int x = 0; x < 9; x++) {
+                const uint8_t* c = blk + (z * 10 + y) * 10 + x;
+                o[(z * 9 + y) * 9 + x] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[10] << 16) | ((uint32_t)c[11] << 24);
+            }
+        }
+        d.quadBytes = q.size() * 4;
+        CK(cudaMalloc(&d.quads, d.quadBytes));
+        CK(cudaMemcpy(d.quads, q.data(), d.quadBytes, cudaMemcpyHostToDevice));
+        s.quads = (const uint32_t*)d.quads;
+    }
     return VRESTIR_OK;
 }
 
@@ -250,7 +272,8 @@ int setPersistingWindow(vrestir_pass* p, cudaStream_t st) {
     // access-policy window on the stream that runs K2/K3.
     int slot = p->P.mSpatialVisibilityMipLevel;
     if (slot < 0 || slot >= VRESTIR_MAX_SLOTS || !p->dslots[slot].atlas) return VRESTIR_OK;
-    void* base = p->dslots[slot].atlas; size_t bytes = p->dslots[slot].atlasBytes;
+    void* base = p->dslots[slot].quads ? p->dslots[slot].quads : p->dslots[slot].atlas;
+    size_t bytes = p->dslots[slot].quads ? p->dslots[slot].quadBytes : p->dslots[slot].atlasBytes;
     if (base == p->persistBase && bytes == p->persistBytes) return VRESTIR_OK;
     int maxWin = 0, maxPersist = 0;
     cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, p->device);

@@ -19,6 +19,8 @@ struct DSlot {
     float max_value, compress_scale;
     int format, channels;
     const void* atlas;
+    const uint32_t* quads;   // UNORM8 single-channel slots: [brick][10][9][9] words of 2x2 xy-neighbours (trilinear = 2 loads)
+    unsigned childCount32[3];
 };
 
 struct DScene {
