@@ -538,6 +538,49 @@ struct MediumTrRayMarchingAdapter : AdapterBase {
     VRD void ExecuteEndStep() { if (hasInitialized) Tr = expf(Tr); else Tr = 1.f; }
 };
 
+// Shared camera march: one traversal of a ray yields the ray-marched transmittance to up to 3 depths.
+// Bit-identical to running MediumTrRayMarchingAdapter once per depth (same global sample phase, same partial sums in the
+// same order; a depth's value is the running sum at the first sample with t >= min(boxFar, depth), or at the end of the
+// ray).  Used by the task-parallel reuse kernels, where several stored samples are evaluated along the same pixel ray
+// (VR/SpatialReuse.cs.slang:183-239 evaluates each tap at every other tap's ray).
+struct MultiDepthRayMarchingAdapter : AdapterBase {
+    float Tr; bool useLinearSampler; float tStep; bool hasInitialized;
+    float thr[3], out[3]; int n; unsigned pending;
+    VRD void Init(bool linear, float step, const float* depths, int count) {
+        Tr = 0.f; useLinearSampler = linear; tStep = step; hasInitialized = false; n = count; pending = (1u << count) - 1u;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { thr[k] = k < count ? depths[k] : 0.f; out[k] = 0.f; }
+    }
+    VRD void ExecuteStartStep() { hasInitialized = true; }
+    VRD bool ExecuteMainStep(const DSlot& g, const HDDAState& dda, float3 vmin_leaf, uint32_t brick, uint32_t, float& t, SampleGenerator&) {
+        t = tNear + (floorf((t - tNear) / tStep) + 0.5f) * tStep;
+        if (t < dda.tx) t += tStep;
+        float3 wp = ray.origin + t * ray.dir;
+        float3 p = wp - vmin_leaf;
+        const float3 wpt = 1.f * tStep * ray.dir;
+        const float res = (float)g.res[0];
+        const float sig = c_scene.vol.sigma_t;
+        for (int iter = 0; iter < MAX_BRICK_STEPS && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < res && p.y < res && p.z < res; iter++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if ((pending >> k) & 1u) { if (t >= fminf(tFar, thr[k])) { out[k] = Tr; pending &= ~(1u << k); } }
+            if (!pending) return true;
+            float density = DensityInAtlas<false>(g, brick, p, useLinearSampler);
+            float sigma_t = density * sig;
+            Tr += -sigma_t * 1.f * tStep;
+            p = p + wpt;
+            t += 1.f * tStep;
+        }
+        return false;
+    }
+    VRD void ExecuteEndStep() {
+#pragma unroll
+        for (int k = 0; k < 3; k++) if ((pending >> k) & 1u) out[k] = Tr;
+        pending = 0;
+    }
+    VRD float result(int k) const { return hasInitialized ? expf(out[k]) : 1.f; }
+};
+
 // VR/VolumeTrackingAdapterGVDB.slang:212-436
 struct SampleMediumAnalyticAdapter : AdapterBase {
     float hitDistances[4], outTr[4], pdf[4]; int numSamples; float opticalThickness; bool hasInitialized, useLinearSampler;
@@ -779,6 +822,16 @@ VRD_NOINLINE float MediumTrRayMarchingGeneric(const Ray& r, int mip, bool linear
     SampleGenerator dummy; dummy.s0 = dummy.s1 = dummy.s2 = dummy.s3 = 0;
     VolumeTrackingGVDB(r, mip, dummy, a, false);
     return a.Tr;
+}
+// ray.tMax must be the largest of `depths`
+VRD_NOINLINE void MediumTrRayMarchingMulti(const Ray& r, int mip, bool linear, float tStepScale, const float* depths, int count, float* outTr) {
+    int eff = mip >= VRESTIR_PREV_DENSITY_GRID_OFFSET ? mip - VRESTIR_PREV_DENSITY_GRID_OFFSET : mip;
+    eff = eff >= VRESTIR_NUM_MAX_MIPS ? eff - VRESTIR_NUM_MAX_MIPS : eff;
+    MultiDepthRayMarchingAdapter a;
+    a.Init(linear, c_scene.vol.tStep * c_scene.vol.volumeWorldScaling * tStepScale * (eff + 1), depths, count);
+    SampleGenerator dummy; dummy.s0 = dummy.s1 = dummy.s2 = dummy.s3 = 0;
+    VolumeTrackingGVDB(r, mip, dummy, a, false);
+    for (int k = 0; k < count; k++) outTr[k] = a.result(k);
 }
 VRD_NOINLINE void SampleMediumAnalyticGeneric(const Ray& r, SampleGenerator& sg, bool linear, float hit[4], int mip, float pdf[4], float outTr[4], int numSamples) {
     SampleMediumAnalyticAdapter a; a.Init(numSamples, linear);
@@ -1179,7 +1232,8 @@ VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2
 
 // VR/ReSTIRHelper.slang:91-423 (no SURFACE_SCENE / VERTEX_REUSE)
 template <int B, class Extra>
-__device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool noReuse, bool isFinalShading) {
+__device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool noReuse, bool isFinalShading,
+                              float externalVis = -1.f) {   // externalVis: IExternalVisibilityProvider of VR/ArrayDataProvider.slang:48-63 (bounce 0)
     const vrestir_volume_desc& vd = c_scene.vol;
     const bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
     const int mipLevelOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
@@ -1196,8 +1250,10 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
     {
         float density = (isBackgroundSample || noReuse) ? 1.f : DensityWorldSpace(p_World, mipLevelOffset);
         if (density == 0.f) return f3(0.f);
-        if (!noReuse)
-            visibility = computeVisibility(ray, sg, o.visibilitySamples, o.visibilityMipLevel + mipLevelOffset, o.visibilityUseLinearSampler, o.visibilityTrackingMethod, o.visibilityTStepScale);
+        if (!noReuse) {
+            if (externalVis != -1.f) visibility = externalVis;
+            else visibility = computeVisibility(ray, sg, o.visibilitySamples, o.visibilityMipLevel + mipLevelOffset, o.visibilityUseLinearSampler, o.visibilityTrackingMethod, o.visibilityTStepScale);
+        }
         float3 sigma_s = isBackgroundSample ? f3(1.f) : (isSelfEmission ? sigA : sigS);
         if (noReuse && !isBackgroundSample) sigma_s = sigma_s / vd.sigma_t;
         F = F * (visibility * density * sigma_s);

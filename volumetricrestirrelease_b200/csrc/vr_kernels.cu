@@ -13,6 +13,10 @@
 #include "vr_device.cuh"
 #include "vr_kernels.h"
 
+#ifndef VR_MINB
+#define VR_MINB 4
+#endif
+
 namespace vrd {
 
 VRD bool pixelOf(const FrameParams& fp, int& x, int& y) {
@@ -26,7 +30,7 @@ VRD Ray primaryRay(const FrameParams& fp, int x, int y) {
 }
 
 // ------------------------------------------------------------------------------------------------ K0
-__global__ void __launch_bounds__(128) k_features(FrameParams fp) {
+__global__ void __launch_bounds__(128, VR_MINB) k_features(FrameParams fp) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     Ray ray = primaryRay(fp, x, y);
@@ -201,7 +205,7 @@ __device__ float3 IntegrateByVolumePathTracing(Ray ray, SampleGenerator& sg, con
 }
 
 template <int B>
-__global__ void __launch_bounds__(128) k_initial(FrameParams fp) {
+__global__ void __launch_bounds__(128, VR_MINB) k_initial(FrameParams fp) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     SampleGenerator sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(128) k_initial(FrameParams fp) {
 
 // ------------------------------------------------------------------------------------------------ K2
 template <int B>
-__global__ void __launch_bounds__(128) k_temporal(FrameParams fp) {
+__global__ void __launch_bounds__(128, VR_MINB) k_temporal(FrameParams fp) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     const int W = fp.W, H = fp.H;
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(128) k_temporal(FrameParams fp) {
 
 // ------------------------------------------------------------------------------------------------ K3
 template <int B>
-__global__ void __launch_bounds__(128) k_spatial(FrameParams fp) {
+__global__ void __launch_bounds__(128, VR_MINB) k_spatial(FrameParams fp) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     const int W = fp.W, H = fp.H;
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(128) k_spatial(FrameParams fp) {
 
 // ------------------------------------------------------------------------------------------------ K5
 template <int B>
-__global__ void __launch_bounds__(128) k_final(FrameParams fp) {
+__global__ void __launch_bounds__(128, VR_MINB) k_final(FrameParams fp) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     const int pixelId = y * fp.W + x;
