@@ -22,12 +22,12 @@
 namespace vrd {
 
 #define VRD __device__ __forceinline__
-#define VRD_NOINLINE __device__ __noinline__
+#define VRD_NOINLINE static __device__ __noinline__
 
-__constant__ DScene c_scene;   // this header is included by exactly one translation unit (vr_kernels.cu)
+static __constant__ DScene c_scene;   // one private copy per translation unit (vr_kernels.cu, vr_wavefront.cu); uploadScene* fills each
 // diagnostics: rays whose hierarchical DDA ran >= 1024 outer iterations (origin, dir, mip, iterations), first 64
-__device__ float g_dbgRays[64 * 8];
-__device__ unsigned g_dbgCount;
+static __device__ float g_dbgRays[64 * 8];
+static __device__ unsigned g_dbgCount;
 
 
 // ------------------------------------------------------------------------------------------------ math
@@ -1200,12 +1200,10 @@ struct ExtraProviderRW {   // buffer written by the same kernel (K2's gCurExtraB
     VRD float3 get(int i) const { return global[i]; }
 };
 
-// VR/ReSTIRHelper.slang:435-496
-template <class = void>
-VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2 lightUV, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool cullNonOpaqueGeometry) {
-    Ray shadowRay = makeRay(mi.p, f3(0.f, 0.f, 1.f), 0, 0); float3 Ld = f3(0.f); bool isValidSample = true;
-    const bool useLastFrameGrid = c_scene.vol.usePrevGridForReproj && isLastFrame && c_scene.vol.hasAnimation;
-    const int densityGridOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
+// VR/ReSTIRHelper.slang:435-496, first half: the shadow ray of a stored light sample and its unshadowed radiance * phase.
+// Returns isValidSample.  Shared by the per-pixel kernels and the wavefront gather / combine kernels.
+VRD bool lightRayAndLd(const MediumInteraction& mi, int lightID, float2 lightUV, bool isLastFrame, Ray& shadowRay, float3& Ld) {
+    shadowRay = makeRay(mi.p, f3(0.f, 0.f, 1.f), 0, 0); Ld = f3(0.f); bool isValidSample = true;
     if (lightID < 0) {
         float3 wiWorld = envDecodeLightUV(lightUV, lightID, isLastFrame);
         shadowRay = makeRay(mi.p, wiWorld, 0, kRayTMax);
@@ -1223,6 +1221,14 @@ VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2
             Ld = ls.Le * c_scene.emissiveMul * mi.phaseFunction(mi.wo, ls.dir) * ls.cosTheta / (ls.distance * ls.distance);
         }
     }
+    return isValidSample;
+}
+template <class = void>
+VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2 lightUV, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool cullNonOpaqueGeometry) {
+    Ray shadowRay; float3 Ld;
+    const bool isValidSample = lightRayAndLd(mi, lightID, lightUV, isLastFrame, shadowRay, Ld);
+    const bool useLastFrameGrid = c_scene.vol.usePrevGridForReproj && isLastFrame && c_scene.vol.hasAnimation;
+    const int densityGridOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
     float Tr = 1.f;
     if (isValidSample)
         Tr = computeVisibility(shadowRay, sg, o.lightSamples, cullNonOpaqueGeometry ? o.lightingMipLevel + densityGridOffset : 0, o.lightingUseLinearSampler,
@@ -1331,6 +1337,18 @@ VRD void resampleNeighbor(Reservoir& tap, const Ray& ray, SampleGenerator& sg, c
     if (isinf(weight) || isnan(weight)) weight = 0.f;
     tap.runningSum *= weight;
     tap.p_y = p_y_hat;
+}
+
+// ------------------------------------------------------------------------------------------------ pixel mapping
+// one thread per pixel; a warp covers an 8x4 pixel tile, a CTA of 4 warps 16x8 pixels
+VRD bool pixelOf(const FrameParams& fp, int& x, int& y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    y = fp.rowBegin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    return x < fp.W && y < fp.rowEnd;
+}
+VRD Ray primaryRay(const FrameParams& fp, int x, int y) {
+    return makeRay(c_scene.camPos, normalize(camRayDirNN(c_scene.camU, c_scene.camV, c_scene.camW, x, y, fp.W, fp.H)), 0.f, kRayTMax);
 }
 
 }  // namespace vrd

@@ -19,16 +19,6 @@
 
 namespace vrd {
 
-VRD bool pixelOf(const FrameParams& fp, int& x, int& y) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    y = fp.rowBegin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    return x < fp.W && y < fp.rowEnd;
-}
-VRD Ray primaryRay(const FrameParams& fp, int x, int y) {
-    return makeRay(c_scene.camPos, normalize(camRayDirNN(c_scene.camU, c_scene.camV, c_scene.camW, x, y, fp.W, fp.H)), 0.f, kRayTMax);
-}
-
 // ------------------------------------------------------------------------------------------------ K0
 __global__ void __launch_bounds__(128, VR_MINB) k_features(FrameParams fp) {
     int x, y;

@@ -12,6 +12,12 @@ cudaError_t launchSpatial(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchFinal(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchImportance(float* importance, int dim, int sx, int sy, cudaStream_t st);
 cudaError_t launchImportanceMip(const float* src, float* dst, int d, cudaStream_t st);
+// wavefront path (vr_wavefront.cu)
+cudaError_t uploadSceneWavefront(const DScene& s, cudaStream_t st);
+int marchBlocksPerSM(int nt);
+cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, int nt, int blocks, cudaStream_t st);
+cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
+cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchResToAos(ResBuf b, vrestir_reservoir* out, int n, cudaStream_t st);
 cudaError_t launchResFromAos(ResBuf b, const vrestir_reservoir* in, int n, cudaStream_t st);
 }

@@ -92,6 +92,11 @@ struct vrestir_pass {
     uint64_t launches = 0;
     vrestir_timings timings{};
     void* persistBase = nullptr; size_t persistBytes = 0;
+    // wavefront (task-stream) path: march-task streams, result blocks, counters {cam.count, cam.cursor, light.count, light.cursor}
+    bool mUseWavefront = true;
+    uint4* wfCamTasks = nullptr; uint4* wfLightTasks = nullptr; float* wfResults = nullptr; unsigned* wfCounters = nullptr;
+    size_t wfPixels = 0;
+    int marchBlocks1 = 0, marchBlocks3 = 0;
 };
 
 namespace {
@@ -115,6 +120,40 @@ int ensureBuffers(vrestir_pass* p) {
     p->allocW = p->W; p->allocH = p->H; p->allocB = B;
     p->ia = 0; p->ib = 1; p->it = 2; p->finalPhys = 0; p->featCur = 0; p->featPrev = 1;
     return VRESTIR_OK;
+}
+
+// camera tasks: <= 4 per pixel, light tasks: <= 12 per pixel (S <= 4 taps), result block: WF_BLOCK floats per pixel of the band
+int ensureWavefront(vrestir_pass* p) {
+    const size_t n = (size_t)(p->rowEnd - p->rowBegin) * p->W;
+    if (p->wfPixels == n && p->wfResults) return VRESTIR_OK;
+    if (p->wfCamTasks) cudaFree(p->wfCamTasks);
+    if (p->wfLightTasks) cudaFree(p->wfLightTasks);
+    if (p->wfResults) cudaFree(p->wfResults);
+    p->wfCamTasks = p->wfLightTasks = nullptr; p->wfResults = nullptr; p->wfPixels = 0;
+    if (n * 12 >= (1ull << 32) || n * WF_BLOCK >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit task indices; shard the frame");
+    CK(cudaMalloc(&p->wfCamTasks, n * 4 * 32));
+    CK(cudaMalloc(&p->wfLightTasks, n * 12 * 32));
+    CK(cudaMalloc(&p->wfResults, n * WF_BLOCK * sizeof(float)));
+    if (!p->wfCounters) CK(cudaMalloc(&p->wfCounters, 64));
+    p->wfPixels = n;
+    if (!p->marchBlocks1) {
+        int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+        p->marchBlocks1 = sms * marchBlocksPerSM(1); p->marchBlocks3 = sms * marchBlocksPerSM(3);
+    }
+    return VRESTIR_OK;
+}
+WfBufs wfView(const vrestir_pass* p) {
+    WfBufs w;
+    w.cam.tasks = p->wfCamTasks; w.cam.count = p->wfCounters; w.cam.cursor = p->wfCounters + 1; w.cam.capacity = (unsigned)(p->wfPixels * 4);
+    w.light.tasks = p->wfLightTasks; w.light.count = p->wfCounters + 2; w.light.cursor = p->wfCounters + 3; w.light.capacity = (unsigned)(p->wfPixels * 12);
+    w.results = p->wfResults;
+    return w;
+}
+// the wavefront form of K3 covers the default option family; everything else runs the per-pixel kernel
+bool wavefrontSpatialOk(const vrestir_pass* p) {
+    const vrestir_params& m = p->P;
+    return p->mUseWavefront && m.mMaxBounces == 1 && m.mSpatialSampleCount <= 4 && m.mSpatialVisibilityTrackingMethod == VRESTIR_RAY_MARCHING &&
+           m.mSpatialLightingTrackingMethod == VRESTIR_RAY_MARCHING;
 }
 
 void freeSlot(DevSlot& d) {
@@ -259,6 +298,7 @@ int syncScene(vrestir_pass* p, cudaStream_t st) {
     static thread_local DScene lastScene;
     if (lastOwner != p || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0) {
         CK(uploadScene(s, st));
+        CK(uploadSceneWavefront(s, st));
         // the async copy reads `s` at enqueue time only when the source is pageable (staged); keep a private copy alive
         lastScene = s; lastOwner = p; p->sceneDirty = false;
     }
@@ -354,7 +394,18 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                 fp.roundId = arg;
                 const int r2TimeSeed = ((m.mSpatialReuseRounds + 1) * p->mFrameCount + arg) % 16;   // VR/SpatialReuse.cs.slang:109
                 for (int s = 0; s < m.mSpatialSampleCount; s++) fp.offsets[s] = neighborOffset(m, s, r2TimeSeed);
-                CK(launchSpatial(fp, st)); p->launches++;
+                if (wavefrontSpatialOk(p)) {
+                    rc = ensureWavefront(p); if (rc) return rc;
+                    const WfBufs wf = wfView(p);
+                    CK(cudaMemsetAsync(p->wfCounters, 0, 16, st));
+                    CK(launchSpatialGather(fp, wf, st));
+                    const MarchKind kc = {m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 1};
+                    const MarchKind kl = {m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0};
+                    CK(launchMarch(wf.cam, wf.results, kc, 3, p->marchBlocks3, st));
+                    CK(launchMarch(wf.light, wf.results, kl, 1, p->marchBlocks1, st));
+                    CK(launchSpatialCombine(fp, wf, st));
+                    p->launches += 4;
+                } else { CK(launchSpatial(fp, st)); p->launches++; }
                 p->finalPhys = out;
             }
             if (!(m.mEnableSpatialReuse && arg + 1 < m.mSpatialReuseRounds)) recordEv(p, 4, st);
@@ -493,7 +544,7 @@ int vrestir_destroy(vrestir_pass* p) {
     for (auto& d : p->dslots) freeSlot(d);
     for (int i = 0; i < 3; i++) { if (p->res[i]) cudaFree(p->res[i]); if (p->ext[i]) cudaFree(p->ext[i]); }
     for (int i = 0; i < 2; i++) if (p->feat[i]) cudaFree(p->feat[i]);
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec};
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
@@ -663,6 +714,7 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
         else if (k == "volumeAlbedoExtraControl") p->albedoExtra = (float)value;
         else if (k == "volumeAnisotropyExtraControl") p->anisotropyExtra = (float)value;
         else if (k == "mEnvSamplerType") p->envSamplerType = (int)value;
+        else if (k == "mUseWavefront") p->mUseWavefront = value != 0;   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
     }

@@ -72,5 +72,14 @@ struct FrameParams {
     float4* outColor; float2* outMvec;
 };
 
+// ------------------------------------------------------------------------------------------------ wavefront streams
+// A march task is 2 x uint4: light tasks (originMode 0) = (origin.xyz, tMax | dir.xyz, result index); camera tasks
+// (originMode 1/2: origin = current / previous camera position) = (thr0, thr1, thr2, threshold mask | dir.xyz, result index).
+struct MarchKind { int mip, linear; float tStepScale; int originMode; };
+struct WfStream { uint4* tasks; unsigned* count; unsigned* cursor; unsigned capacity; };
+// per-pixel result block (floats): D[i*4+j] density of tap i's sample seen from ray j, C[j*3+k] camera transmittance along
+// ray j to the depth of tap i (k = i - (i > j)), L[i*4+j] light transmittance from that point
+enum { WF_BLOCK = 48, WF_D = 0, WF_C = 16, WF_L = 28 };
+struct WfBufs { WfStream cam, light; float* results; };
 
 }  // namespace vrd
