@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvrestir.so")
+LIB_PATH = os.environ.get("VRESTIR_LIB") or os.path.join(_HERE, "libvrestir.so")   # VRESTIR_LIB: developer override (tuning variants)
 
 MAX_SLOTS = 30
 NUM_MAX_MIPS = 8

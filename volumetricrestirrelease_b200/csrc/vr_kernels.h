@@ -15,7 +15,7 @@ cudaError_t launchImportanceMip(const float* src, float* dst, int d, cudaStream_
 // wavefront path (vr_wavefront.cu)
 cudaError_t uploadSceneWavefront(const DScene& s, cudaStream_t st);
 int marchBlocksPerSM(int nt);
-cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, int nt, int blocks, cudaStream_t st);
+cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st);
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchResToAos(ResBuf b, vrestir_reservoir* out, int n, cudaStream_t st);

@@ -3,59 +3,109 @@
 // One task = one ray through one density mip with up to NT depth thresholds; the result for threshold k is
 // exp(-sum sigma_t * step) over the ray-march samples with t < min(boxFar, thr[k]) — bit-identical to running
 // VolumeTrackingGVDB<MediumTrRayMarchingAdapter> (VR/VolumeUtils.slang:171-282,350-362 +
-// VR/VolumeTrackingAdapterGVDB.slang:140-208) once per threshold: same hierarchical-DDA arithmetic, same global sample
-// phase, same partial sums in the same order (see MultiDepthRayMarchingAdapter in vr_device.cuh).
+// VR/VolumeTrackingAdapterGVDB.slang:140-208) once per threshold: same hierarchical-DDA arithmetic (F/Scene/GVDB/
+// gvdbDda.slang:86-157), same global sample phase, same partial sums in the same order.
 //
-// What is different from the per-pixel kernels is only the scheduling:
+// What is different from the per-pixel kernels is only the scheduling and the instruction diet:
 //   * tasks come from a compacted global stream (background pixels and dead taps never occupy a lane);
-//   * a warp is a pool of 32 persistent lanes: a lane that finishes its ray pulls the next task from the stream
-//     (refill when >= VR_REFILL_MIN lanes are idle), so short and long rays do not wait for each other;
-//   * inside the pool the two inner loops of the reference traversal (empty-space DDA stepping and in-brick sampling)
-//     are run as two alternating phases chosen by majority vote over the lanes, so each issued instruction serves at
-//     least half of the busy lanes instead of the ~7/32 measured for the nested loops (profiles/r01_ncu_full_*).
+//   * a warp is a pool of 32 persistent lanes: a lane that finishes its ray parks its result and pulls the next task from
+//     the stream when >= VR_REFILL_MIN lanes are parked (result write-out, task fetch and ray setup then run on >= 8 lanes);
+//   * the two inner loops of the reference traversal (empty-space DDA stepping and in-brick sampling) are two alternating
+//     phases chosen by majority vote over the busy lanes: every issued step serves at least half of them, instead of the
+//     ~7/32 lanes ncu measured for the nested loops (profiles/r01_ncu_full_k_spatial_k_initial_baseline.txt);
+//   * the grid descriptor travels as a kernel parameter (constant bank 0 operands instead of indexed c[3] loads), the
+//     level-2 state lives in constants (the root node), float->int / floor / UNORM8->float conversions use exact
+//     full-rate FADD/LOP forms instead of the quarter-rate F2I / FRND / I2F units.
 #pragma once
 #include "vr_device.cuh"
 
 namespace vrd {
 
 #ifndef VR_REFILL_MIN
-#define VR_REFILL_MIN 8
+#define VR_REFILL_MIN 12
+#endif
+#ifndef VR_STEPS_PER_VOTE
+#define VR_STEPS_PER_VOTE 2
 #endif
 
-enum { MARCH_IDLE = 0, MARCH_TRAV = 1, MARCH_BRICK = 2 };
+// phase encoding: bit 0 set = busy
+enum { MARCH_IDLE = 0, MARCH_TRAV = 1, MARCH_DONE = 2, MARCH_BRICK = 3 };
 
-template <int NT>
+// exact floor for |x| < 2^22: round-down add of 1.5 * 2^23 leaves floor(x) in the low mantissa bits
+VRD float fastFloor(float x, int& i) {
+    const float m = __fadd_rd(x, 12582912.f);
+    i = __float_as_int(m) - 0x4B400000;
+    return m - 12582912.f;
+}
+// exact UNORM8 code -> float: 2^23 + b, minus 2^23
+VRD float byteToFloat(uint32_t w, int sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + sel) ) - 8388608.f; }
+
+// FAST: the slot is a single-channel UNORM8 pool with the quad repack and the sampler is trilinear (every reuse mip)
+template <int NT, bool FAST>
 struct Marcher {
-    // ray (index space of the mip) and adapter state
-    HDDAState dda;                 // dda.pos / dda.dir are the medium-space ray
+    // medium-space ray
+    float3 pos, dir, invDir;
+    int3 stepI;                    // +1 / -1 per axis (dir >= 0 ? 1 : -1)
+    // DDA state at the current level
+    float3 tDel, tSide; int3 p; float tx, ty; int mask;   // mask bits 0..2 = x, y, z
+    // adapter
     float tNear, tFar, tStep;
-    float thr[NT], out[NT];
+    float thrEff[NT], out[NT];     // thrEff = min(tFar, thr)
     float Tr;
-    unsigned pending, todo;        // thresholds not yet resolved / thresholds this task asked for
-    unsigned outIdx;
-    // traversal (VR/VolumeUtils.slang:198-279); only levels 1 and 2 exist
+    unsigned pending, todo, outIdx;
+    bool initialized;
+    // traversal: level 1 node in registers, level 2 is the root (constants of the launch)
     int lev, iter;
-    uint32_t link1, link2;
-    float3 vmin1, vmin2;
-    float tMax1, tMax2;
-    // in-brick sampling (VR/VolumeTrackingAdapterGVDB.slang:165-201)
+    uint32_t link1; float3 vmin1; float tMax1;
+    // in-brick sampling
     float3 pb; float t; uint32_t brick; int biter;
     int phase;
 
-    VRD void finish(float* results, bool initialized) {
+    VRD void writeOut(float* results) {
 #pragma unroll
         for (int k = 0; k < NT; k++)
             if ((todo >> k) & 1u) results[outIdx + k] = initialized ? expf(((pending >> k) & 1u) ? Tr : out[k]) : 1.f;
         phase = MARCH_IDLE;
     }
 
-    // originMode: 0 = explicit origin + one threshold (a = origin.xyz, tMax), 1 / 2 = camera / previous camera origin with
-    // up to 3 thresholds (a = thr0, thr1, thr2, mask)
-    VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, float* results) {
+    VRD void prepare(float3 vmin, float vdel, float ivdel) {   // HDDAState::Prepare
+        tDel = make_float3(fabsf(vdel * invDir.x), fabsf(vdel * invDir.y), fabsf(vdel * invDir.z));
+        float3 pFlt = (pos + tx * dir - vmin) * ivdel;
+        float3 fl = make_float3(floorf(pFlt.x), floorf(pFlt.y), floorf(pFlt.z));
+        const float3 sgn = make_float3(dir.x >= 0 ? 1.f : -1.f, dir.y >= 0 ? 1.f : -1.f, dir.z >= 0 ? 1.f : -1.f);
+        tSide = ((fl - pFlt + f3(0.5f)) * sgn + f3(0.5f)) * tDel + f3(tx);
+        p = make_int3((int)fl.x, (int)fl.y, (int)fl.z);
+    }
+    VRD void next() {   // HDDAState::Next
+        const bool mx = (tSide.x < tSide.y) & (tSide.x <= tSide.z);
+        const bool my = (tSide.y < tSide.z) & (tSide.y <= tSide.x);
+        const bool mz = (tSide.z < tSide.x) & (tSide.z <= tSide.y);
+        mask = (mx ? 1 : 0) | (my ? 2 : 0) | (mz ? 4 : 0);
+        ty = mx ? tSide.x : (my ? tSide.y : tSide.z);
+    }
+    VRD void step() {   // HDDAState::Step (select form) followed by the traversal's `t.x += epsilon`
+        if (mask & 1) { tSide.x += tDel.x; p.x += stepI.x; }
+        if (mask & 2) { tSide.y += tDel.y; p.y += stepI.y; }
+        if (mask & 4) { tSide.z += tDel.z; p.z += stepI.z; }
+        tx = ty + 0.01f;
+    }
+    // `while (lev <= topLev && t.x > tMax[lev]) { lev++; if (lev <= topLev) Prepare(root) }`, lev == 3 means finished
+    VRD void ascend(const DSlot& g) {
+        if (lev == 1) {
+            if (!(tx > tMax1)) return;
+            if (g.top_lev == 1) { phase = MARCH_DONE; return; }
+            lev = 2;
+            prepare(make_float3((float)g.rootPos[0], (float)g.rootPos[1], (float)g.rootPos[2]), g.vdel[2], 1.0f / g.vdel[2]);
+        }
+        if (tx > tFar) phase = MARCH_DONE;   // tMax[2] = tFar
+    }
+
+    VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, const DSlot& g) {
         Ray rW;
         rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
         outIdx = b.w;
         rW.tMin = 0.f;
+        float thr[NT];
         if (kind.originMode == 0) {
             rW.origin = make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
             thr[0] = __uint_as_float(a.w);
@@ -77,133 +127,150 @@ struct Marcher {
         for (int k = 0; k < NT; k++) out[k] = 0.f;
         Tr = 0.f;
         const int mip = kind.mip;
-        const DSlot& g = c_scene.slots[mip];
         int eff = mip >= VRESTIR_PREV_DENSITY_GRID_OFFSET ? mip - VRESTIR_PREV_DENSITY_GRID_OFFSET : mip;
         eff = eff >= VRESTIR_NUM_MAX_MIPS ? eff - VRESTIR_NUM_MAX_MIPS : eff;
         tStep = c_scene.vol.tStep * c_scene.vol.volumeWorldScaling * kind.tStepScale * (eff + 1);
-        Ray ray = WorldToMedium(rW, mip);
-        if (!IntersectVolumeBound(ray, tNear, tFar, mip, false)) { finish(results, false); return; }
+        // WorldToMedium + IntersectVolumeBound (VR/VolumeBase.slang:103-175)
+        Ray ray; ray.origin = mulPoint(rW.origin, g.w2m); ray.dir = mulVec(rW.dir, g.w2m); ray.tMin = rW.tMin; ray.tMax = rW.tMax;
+        initialized = IntersectP(v3(g.bmin), v3(g.bmax), ray, tNear, tFar);
+        if (!initialized) { phase = MARCH_DONE; return; }
+#pragma unroll
+        for (int k = 0; k < NT; k++) thrEff[k] = fminf(tFar, thr[k]);
+        pos = ray.origin; dir = ray.dir;
+        invDir = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+        stepI = make_int3(dir.x >= 0 ? 1 : -1, dir.y >= 0 ? 1 : -1, dir.z >= 0 ? 1 : -1);
+        tx = tNear + 0.01f; ty = 0.f; mask = 0;
         lev = g.top_lev;
-        link1 = link2 = ID_UNDEFL; vmin1 = vmin2 = f3(0.f); tMax1 = tMax2 = 0.f;
-        {
-            NodeHead h = loadNodeHead(g, lev, 0);
-            if (lev == 2) { link2 = (uint32_t)h.a.w; vmin2 = nodePos(h.a); tMax2 = tFar; }
-            else { link1 = (uint32_t)h.a.w; vmin1 = nodePos(h.a); tMax1 = tFar; }
-        }
         iter = 0;
-        dda.SetFromRay(ray.origin, ray.dir, tNear + 0.01f);
-        if (lev == 2) dda.Prepare(vmin2, g.vdel[2], 1.0f / g.vdel[2]); else dda.Prepare(vmin1, g.vdel[1], 1.0f / g.vdel[1]);
+        const float3 rootPos = make_float3((float)g.rootPos[0], (float)g.rootPos[1], (float)g.rootPos[2]);
+        if (lev == 2) { link1 = ID_UNDEFL; vmin1 = f3(0.f); tMax1 = 0.f; prepare(rootPos, g.vdel[2], 1.0f / g.vdel[2]); }
+        else { link1 = g.rootLink; vmin1 = rootPos; tMax1 = tFar; prepare(rootPos, g.vdel[1], 1.0f / g.vdel[1]); }
         phase = MARCH_TRAV;
     }
 
-    VRD void ascend(const DSlot& g, int topLev) {
-        while (lev <= topLev && dda.tx > (lev == 2 ? tMax2 : tMax1)) {
-            lev++;
-            if (lev <= topLev) dda.Prepare(vmin2, g.vdel[2], 1.0f / g.vdel[2]);
+    // one iteration of the outer loop of VolumeTrackingGVDB, up to (not including) the adapter's sampling loop
+    VRD void travStep(const DSlot& g) {
+        const bool l2 = lev == 2;
+        const int r = l2 ? g.res[2] : g.res[1];
+        if (!(iter < 4096 && inRange(p, r + 1))) { phase = MARCH_DONE; return; }
+        iter++;
+        next();
+        const int dm = l2 ? g.dim[2] : g.dim[1];
+        const unsigned b = (unsigned)((((p.z << dm) + p.y) << dm) + p.x);
+        const uint32_t listid = l2 ? g.rootLink : link1;
+        uint32_t child = ID_UNDEFL;
+        if (listid != ID_UNDEFL) {
+            // p == res passes the inclusive bound (VR/VolumeUtils.slang:231) and aliases into the list like the shader's
+            // ByteAddressBuffer load; outside the whole list D3D returns 0.  listid < node count and the list holds < 2^31
+            // entries (checked at upload), so 32-bit arithmetic cannot wrap.
+            const unsigned idx = listid * (unsigned)(r * r * r) + b;
+            child = idx >= (l2 ? g.childCount32[2] : g.childCount32[1]) ? 0u : __ldg((l2 ? g.child[2] : g.child[1]) + idx);
         }
+        if (child == ID_UNDEFL) { step(); ascend(g); return; }
+        if (!l2) {
+            // brick entry: prologue of MediumTrRayMarchingAdapter::ExecuteMainStep
+            const int4 leaf = __ldg((const int4*)&g.nodes[0][child]);
+            brick = (uint32_t)leaf.w;
+            float tt = tx - 0.01f;
+            tt = tNear + (floorf((tt - tNear) / tStep) + 0.5f) * tStep;
+            if (tt < tx) tt += tStep;
+            t = tt;
+            const float3 wp = pos + tt * dir;
+            pb = wp - nodePos(leaf);
+            biter = 0;
+            phase = MARCH_BRICK;
+            return;
+        }
+        lev = 1;
+        const int4 h = __ldg((const int4*)&g.nodes[1][child]);
+        link1 = (uint32_t)h.w; vmin1 = nodePos(h);
+        tMax1 = ty;
+        prepare(vmin1, g.vdel[1], 1.0f / g.vdel[1]);
+        ascend(g);
     }
 
-    // one iteration of the outer loop of VolumeTrackingGVDB, up to (not including) the adapter call
-    VRD void travStep(const DSlot& g, float* results) {
-        const int topLev = g.top_lev;
-        const int r = lev == 2 ? g.res[2] : g.res[1];
-        if (!(iter < 4096 && lev > 0 && lev <= topLev && inRange(dda.p, r + 1))) { finish(results, true); return; }
-        iter++;
-        dda.Next();
-        const int dm = lev == 2 ? g.dim[2] : g.dim[1];
-        const int b = (((dda.p.z << dm) + dda.p.y) << dm) + dda.p.x;
-        uint32_t childNodeId;
-        {
-            const uint32_t listid = lev == 2 ? link2 : link1;
-            if (listid == ID_UNDEFL) childNodeId = ID_UNDEFL;
-            else {
-                const long long idx = (long long)listid * (long long)(r * r * r) + (long long)b;
-                childNodeId = (idx < 0 || idx >= (long long)(lev == 2 ? g.childCount32[2] : g.childCount32[1])) ? 0u : __ldg(&g.child[lev][idx]);
-            }
-        }
-        if (childNodeId != ID_UNDEFL) {
-            if (lev == 1) {
-                // brick entry: MultiDepthRayMarchingAdapter::ExecuteMainStep prologue
-                float tt = dda.tx - 0.01f;
-                NodeHead leaf = loadNodeHead(g, 0, childNodeId);
-                brick = (uint32_t)leaf.a.w;
-                tt = tNear + (floorf((tt - tNear) / tStep) + 0.5f) * tStep;
-                if (tt < dda.tx) tt += tStep;
-                t = tt;
-                float3 wp = dda.pos + tt * dda.dir;
-                pb = wp - nodePos(leaf.a);
-                biter = 0;
-                phase = MARCH_BRICK;
-                return;
-            }
-            lev = 1;
-            NodeHead h = loadNodeHead(g, 1, childNodeId);
-            link1 = (uint32_t)h.a.w; vmin1 = nodePos(h.a);
-            tMax1 = dda.ty;
-            dda.Prepare(vmin1, g.vdel[1], 1.0f / g.vdel[1]);
-        } else {
-            dda.Step();
-            dda.tx += 0.01f;
-        }
-        ascend(g, topLev);
+    VRD float sampleFast(const DSlot& g) {   // sampleBrickLinear<false> on the quad repack, same filter arithmetic
+        int ix, iy, iz;
+        const float qx = pb.x - 0.5f, qy = pb.y - 0.5f, qz = pb.z - 0.5f;
+        const float fx0 = fastFloor(qx, ix), fy0 = fastFloor(qy, iy), fz0 = fastFloor(qz, iz);
+        const float fx = qx - fx0, fy = qy - fy0, fz = qz - fz0;
+        const uint32_t* q = g.quads + (brick * 810u + (unsigned)(((iz + 1) * 9 + (iy + 1)) * 9 + (ix + 1)));
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 81);
+        const float v000 = byteToFloat(w0, 0), v100 = byteToFloat(w0, 1), v010 = byteToFloat(w0, 2), v110 = byteToFloat(w0, 3);
+        const float v001 = byteToFloat(w1, 0), v101 = byteToFloat(w1, 1), v011 = byteToFloat(w1, 2), v111 = byteToFloat(w1, 3);
+        const float c00 = lerpf(v000, v100, fx), c10 = lerpf(v010, v110, fx), c01 = lerpf(v001, v101, fx), c11 = lerpf(v011, v111, fx);
+        const float c0 = lerpf(c00, c10, fy), c1 = lerpf(c01, c11, fy);
+        return lerpf(c0, c1, fz) * kUnorm8;
     }
 
     // one iteration of the in-brick sampling loop; on leaving the brick performs the tail of the outer iteration
-    VRD void sampleStep(const DSlot& g, bool linear, float* results) {
-        const float res = (float)g.res[0];
+    VRD void sampleStep(const DSlot& g, bool linear) {
+        const float res = 8.f;   // bricks are 8^3 (VRESTIR_BRICK_VOXELS = 10^3 with apron)
         if (!(biter < MAX_BRICK_STEPS && pb.x >= 0 && pb.y >= 0 && pb.z >= 0 && pb.x < res && pb.y < res && pb.z < res)) {
-            dda.Step();
-            dda.tx += 0.01f;
+            step();
             phase = MARCH_TRAV;
-            ascend(g, g.top_lev);
+            ascend(g);
             return;
         }
 #pragma unroll
         for (int k = 0; k < NT; k++)
-            if ((pending >> k) & 1u) { if (t >= fminf(tFar, thr[k])) { out[k] = Tr; pending &= ~(1u << k); } }
-        if (!pending) { finish(results, true); return; }
-        float density = DensityInAtlas<false>(g, brick, pb, linear);
-        float sigma_t = density * c_scene.vol.sigma_t;
+            if ((pending >> k) & 1u) { if (t >= thrEff[k]) { out[k] = Tr; pending &= ~(1u << k); } }
+        if (!pending) { phase = MARCH_DONE; return; }
+        float density;
+        if (FAST) density = sampleFast(g) * g.compress_scale * c_scene.vol.densityScaleFactorByScaling;
+        else density = DensityInAtlas<false>(g, brick, pb, linear);
+        const float sigma_t = density * c_scene.vol.sigma_t;
         Tr += -sigma_t * 1.f * tStep;
-        const float3 wpt = 1.f * tStep * dda.dir;
+        const float3 wpt = 1.f * tStep * dir;
         pb = pb + wpt;
         t += 1.f * tStep;
         biter++;
     }
 };
 
-// Persistent-lane pool over one task stream.  tasks: 2 x uint4 per task; count: tasks in the stream; cursor: next unclaimed.
-template <int NT>
-__device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind kind) {
+// Persistent-lane pool over one task stream.  tasks: 2 x uint4 per task; total: tasks in the stream; cursor: next unclaimed.
+template <int NT, bool FAST>
+__device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
-    const DSlot& g = c_scene.slots[kind.mip];
     const bool linear = kind.linear != 0;
-    Marcher<NT> m;
+    Marcher<NT, FAST> m;
     m.phase = MARCH_IDLE;
     bool drained = false;
     for (;;) {
-        unsigned idle = __ballot_sync(FULL, m.phase == MARCH_IDLE);
-        if (!drained && __popc(idle) >= VR_REFILL_MIN) {
-            const unsigned n = __popc(idle);
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(cursor, n);
-            base = __shfl_sync(FULL, base, 0);
-            if (m.phase == MARCH_IDLE) {
-                const unsigned idx = base + __popc(idle & ltMask);
-                if (idx < total) {
-                    const uint4 a = __ldcs(&tasks[2 * (size_t)idx]), b = __ldcs(&tasks[2 * (size_t)idx + 1]);
-                    m.setup(a, b, kind, results);
+        unsigned parked = __ballot_sync(FULL, !(m.phase & 1));
+        if (__popc(parked) >= VR_REFILL_MIN) {
+            if (m.phase == MARCH_DONE) m.writeOut(results);
+            if (!drained) {
+                const unsigned n = __popc(parked);
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(cursor, n);
+                base = __shfl_sync(FULL, base, 0);
+                if (!(m.phase & 1)) {
+                    const unsigned idx = base + __popc(parked & ltMask);
+                    if (idx < total) {
+                        const uint4 a = __ldcs(&tasks[2 * (size_t)idx]), b = __ldcs(&tasks[2 * (size_t)idx + 1]);
+                        m.setup(a, b, kind, g);
+                    }
                 }
+                if (base + n >= total) drained = true;
             }
-            if (base + n >= total) drained = true;
-            idle = __ballot_sync(FULL, m.phase == MARCH_IDLE);
+            parked = __ballot_sync(FULL, !(m.phase & 1));
+            if (parked == FULL) {
+                if (__ballot_sync(FULL, m.phase == MARCH_DONE)) continue;   // box misses of this refill: write them out first
+                if (drained) break;
+                continue;
+            }
         }
-        if (idle == FULL) { if (drained) break; continue; }
         const unsigned tm = __ballot_sync(FULL, m.phase == MARCH_TRAV);
-        if (2 * __popc(tm) >= 32 - __popc(idle)) { if (m.phase == MARCH_TRAV) m.travStep(g, results); }
-        else { if (m.phase == MARCH_BRICK) m.sampleStep(g, linear, results); }
+        if (2 * __popc(tm) >= 32 - __popc(parked)) {
+#pragma unroll 1
+            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.phase == MARCH_TRAV) m.travStep(g);
+        } else {
+#pragma unroll 1
+            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.phase == MARCH_BRICK) m.sampleStep(g, linear);
+        }
     }
 }
 

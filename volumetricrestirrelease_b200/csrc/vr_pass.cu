@@ -185,6 +185,9 @@ int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
         s.nodes[l] = (const vrestir_node*)d.nodes[l]; s.child[l] = (const uint32_t*)d.child[l]; s.childCount[l] = g.childlist_count[l];
         s.childCount32[l] = (unsigned)g.childlist_count[l];
     }
+    if (!g.nodes[g.top_lev] || !g.node_count[g.top_lev]) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "slot has no root node");
+    for (int i = 0; i < 3; i++) s.rootPos[i] = g.nodes[g.top_lev][0].pos[i];
+    s.rootLink = g.nodes[g.top_lev][0].link;
     if ((unsigned long long)g.brick_count * g.atlas_channels * VRESTIR_BRICK_VOXELS >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "brick pool too large for 32-bit voxel indices");
     for (int i = 0; i < 3; i++) { s.bmin[i] = g.bmin[i]; s.bmax[i] = g.bmax[i]; }
     memcpy(s.w2m, g.world_to_medium, 64);
@@ -401,8 +404,8 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                     CK(launchSpatialGather(fp, wf, st));
                     const MarchKind kc = {m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 1};
                     const MarchKind kl = {m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0};
-                    CK(launchMarch(wf.cam, wf.results, kc, 3, p->marchBlocks3, st));
-                    CK(launchMarch(wf.light, wf.results, kl, 1, p->marchBlocks1, st));
+                    CK(launchMarch(wf.cam, wf.results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st));
+                    CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
                     CK(launchSpatialCombine(fp, wf, st));
                     p->launches += 4;
                 } else { CK(launchSpatial(fp, st)); p->launches++; }

@@ -17,15 +17,15 @@
 #include "vr_kernels.h"
 
 #ifndef VR_MARCH_MINB
-#define VR_MARCH_MINB 4
+#define VR_MARCH_MINB 8
 #endif
 
 namespace vrd {
 
 // ------------------------------------------------------------------------------------------------ march kernels
-template <int NT>
-__global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march(WfStream s, float* results, MarchKind kind) {
-    marchPool<NT>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind);
+template <int NT, bool FAST>
+__global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
+    marchPool<NT, FAST>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 gather
@@ -241,13 +241,15 @@ cudaError_t uploadSceneWavefront(const DScene& s, cudaStream_t st) { return cuda
 
 int marchBlocksPerSM(int nt) {
     int n = 0;
-    if (nt == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march<1>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march<3>, 128, 0);
+    if (nt == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march<1, true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march<3, true>, 128, 0);
     return n > 0 ? n : 1;
 }
-cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, int nt, int blocks, cudaStream_t st) {
-    if (nt == 1) k_march<1><<<blocks, 128, 0, st>>>(s, results, kind);
-    else k_march<3><<<blocks, 128, 0, st>>>(s, results, kind);
+cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st) {
+    // FAST: trilinear sampler on a single-channel UNORM8 pool with the quad repack (every coarse / conservative mip)
+    const bool fast = kind.linear && grid.format == VRESTIR_ATLAS_UNORM8 && grid.quads != nullptr;
+    if (nt == 1) { if (fast) k_march<1, true><<<blocks, 128, 0, st>>>(s, results, kind, grid); else k_march<1, false><<<blocks, 128, 0, st>>>(s, results, kind, grid); }
+    else { if (fast) k_march<3, true><<<blocks, 128, 0, st>>>(s, results, kind, grid); else k_march<3, false><<<blocks, 128, 0, st>>>(s, results, kind, grid); }
     return cudaGetLastError();
 }
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
