@@ -24,12 +24,18 @@ namespace vrd {
 #ifndef VR_REFILL_MIN
 #define VR_REFILL_MIN 12
 #endif
+#ifndef VR_SLOW_WEIGHT
+#define VR_SLOW_WEIGHT 2
+#endif
 #ifndef VR_STEPS_PER_VOTE
-#define VR_STEPS_PER_VOTE 2
+#define VR_STEPS_PER_VOTE 3
 #endif
 
-// phase encoding: bit 0 set = busy
-enum { MARCH_IDLE = 0, MARCH_TRAV = 1, MARCH_DONE = 2, MARCH_BRICK = 3 };
+// Lane states; state >> 1 is the group the majority vote counts: 0 parked, 1 level-1 stepping, 2 in-brick sampling, 3 slow
+// events.  The events of a ray (brick entry / exit, leaving or entering a level-1 node, steps at the root level) are not
+// executed where they are detected (1-5 lanes, ncu) but deferred to the head of the phase they lead to, where the lanes
+// that hit the same event since the last switch are processed together.
+enum { MARCH_IDLE = 0, MARCH_DONE = 1, MARCH_TRAV = 2, MARCH_EXIT = 3, MARCH_BRICK = 4, MARCH_ENTER = 5, MARCH_ASCEND = 6, MARCH_ROOT = 7 };
 
 // exact floor for |x| < 2^22: round-down add of 1.5 * 2^23 leaves floor(x) in the low mantissa bits
 VRD float fastFloor(float x, int& i) {
@@ -38,6 +44,7 @@ VRD float fastFloor(float x, int& i) {
     return m - 12582912.f;
 }
 // exact UNORM8 code -> float: 2^23 + b, minus 2^23
+VRD float launder(float x) { asm volatile("" : "+f"(x)); return x; }
 VRD float byteToFloat(uint32_t w, int sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + sel) ) - 8388608.f; }
 
 // FAST: the slot is a single-channel UNORM8 pool with the quad repack and the sampler is trilinear (every reuse mip)
@@ -55,7 +62,7 @@ struct Marcher {
     unsigned pending, todo, outIdx;
     bool initialized;
     // traversal: level 1 node in registers, level 2 is the root (constants of the launch)
-    int lev, iter;
+    int iter;
     uint32_t link1; float3 vmin1; float tMax1;
     // in-brick sampling
     float3 pb; float t; uint32_t brick; int biter;
@@ -89,17 +96,6 @@ struct Marcher {
         if (mask & 4) { tSide.z += tDel.z; p.z += stepI.z; }
         tx = ty + 0.01f;
     }
-    // `while (lev <= topLev && t.x > tMax[lev]) { lev++; if (lev <= topLev) Prepare(root) }`, lev == 3 means finished
-    VRD void ascend(const DSlot& g) {
-        if (lev == 1) {
-            if (!(tx > tMax1)) return;
-            if (g.top_lev == 1) { phase = MARCH_DONE; return; }
-            lev = 2;
-            prepare(make_float3((float)g.rootPos[0], (float)g.rootPos[1], (float)g.rootPos[2]), g.vdel[2], 1.0f / g.vdel[2]);
-        }
-        if (tx > tFar) phase = MARCH_DONE;   // tMax[2] = tFar
-    }
-
     VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, const DSlot& g) {
         Ray rW;
         rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
@@ -140,53 +136,78 @@ struct Marcher {
         invDir = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
         stepI = make_int3(dir.x >= 0 ? 1 : -1, dir.y >= 0 ? 1 : -1, dir.z >= 0 ? 1 : -1);
         tx = tNear + 0.01f; ty = 0.f; mask = 0;
-        lev = g.top_lev;
         iter = 0;
         const float3 rootPos = make_float3((float)g.rootPos[0], (float)g.rootPos[1], (float)g.rootPos[2]);
-        if (lev == 2) { link1 = ID_UNDEFL; vmin1 = f3(0.f); tMax1 = 0.f; prepare(rootPos, g.vdel[2], 1.0f / g.vdel[2]); }
-        else { link1 = g.rootLink; vmin1 = rootPos; tMax1 = tFar; prepare(rootPos, g.vdel[1], 1.0f / g.vdel[1]); }
-        phase = MARCH_TRAV;
+        if (g.top_lev == 2) { link1 = ID_UNDEFL; vmin1 = f3(0.f); tMax1 = 0.f; prepare(rootPos, g.vdel[2], g.ivdel[2]); phase = MARCH_ROOT; }
+        else { link1 = g.rootLink; vmin1 = rootPos; tMax1 = tFar; prepare(rootPos, g.vdel[1], g.ivdel[1]); phase = MARCH_TRAV; }
     }
 
-    // one iteration of the outer loop of VolumeTrackingGVDB, up to (not including) the adapter's sampling loop
-    VRD void travStep(const DSlot& g) {
-        const bool l2 = lev == 2;
-        const int r = l2 ? g.res[2] : g.res[1];
-        if (!(iter < 4096 && inRange(p, r + 1))) { phase = MARCH_DONE; return; }
+    // ---- slow events (group 3) -------------------------------------------------------------------------------------
+    // MARCH_ASCEND: `while (lev <= topLev && t.x > tMax[lev]) { lev++; if (lev <= topLev) Prepare(root) }` on leaving a level-1
+    // node; MARCH_ROOT: one iteration of the outer loop of VolumeTrackingGVDB at the root level, including the descent.
+    VRD void slowStep(const DSlot& g) {
+        tx = launder(tx);
+        if (phase == MARCH_ASCEND) {
+            if (g.top_lev == 1) { phase = MARCH_DONE; return; }
+            prepare(make_float3((float)g.rootPos[0], (float)g.rootPos[1], (float)g.rootPos[2]), g.vdel[2], g.ivdel[2]);
+            if (tx > tFar) { phase = MARCH_DONE; return; }   // tMax[2] = tFar
+            phase = MARCH_ROOT;
+        }
+        if (!(iter < 4096 && inRange(p, g.res[2] + 1))) { phase = MARCH_DONE; return; }
         iter++;
         next();
-        const int dm = l2 ? g.dim[2] : g.dim[1];
-        const unsigned b = (unsigned)((((p.z << dm) + p.y) << dm) + p.x);
-        const uint32_t listid = l2 ? g.rootLink : link1;
+        const unsigned b = (unsigned)((((p.z << g.dim[2]) + p.y) << g.dim[2]) + p.x);
         uint32_t child = ID_UNDEFL;
-        if (listid != ID_UNDEFL) {
-            // p == res passes the inclusive bound (VR/VolumeUtils.slang:231) and aliases into the list like the shader's
-            // ByteAddressBuffer load; outside the whole list D3D returns 0.  listid < node count and the list holds < 2^31
-            // entries (checked at upload), so 32-bit arithmetic cannot wrap.
-            const unsigned idx = listid * (unsigned)(r * r * r) + b;
-            child = idx >= (l2 ? g.childCount32[2] : g.childCount32[1]) ? 0u : __ldg((l2 ? g.child[2] : g.child[1]) + idx);
+        if (g.rootLink != ID_UNDEFL) {
+            const unsigned idx = g.rootLink * g.res3[2] + b;
+            child = idx >= g.childCount32[2] ? 0u : __ldg(g.child[2] + idx);
         }
-        if (child == ID_UNDEFL) { step(); ascend(g); return; }
-        if (!l2) {
-            // brick entry: prologue of MediumTrRayMarchingAdapter::ExecuteMainStep
-            const int4 leaf = __ldg((const int4*)&g.nodes[0][child]);
-            brick = (uint32_t)leaf.w;
-            float tt = tx - 0.01f;
-            tt = tNear + (floorf((tt - tNear) / tStep) + 0.5f) * tStep;
-            if (tt < tx) tt += tStep;
-            t = tt;
-            const float3 wp = pos + tt * dir;
-            pb = wp - nodePos(leaf);
-            biter = 0;
-            phase = MARCH_BRICK;
-            return;
-        }
-        lev = 1;
+        if (child == ID_UNDEFL) { step(); if (tx > tFar) phase = MARCH_DONE; return; }
         const int4 h = __ldg((const int4*)&g.nodes[1][child]);
         link1 = (uint32_t)h.w; vmin1 = nodePos(h);
         tMax1 = ty;
-        prepare(vmin1, g.vdel[1], 1.0f / g.vdel[1]);
-        ascend(g);
+        prepare(vmin1, g.vdel[1], g.ivdel[1]);
+        phase = tx > tMax1 ? MARCH_ASCEND : MARCH_TRAV;
+    }
+
+    // ---- level-1 stepping (group 1) ---------------------------------------------------------------------------------
+    // MARCH_EXIT: tail of the outer iteration after the adapter returned (`dda.Step(); t.x += epsilon;` + level check)
+    VRD void exitBrick() {
+        step();
+        phase = tx > tMax1 ? MARCH_ASCEND : MARCH_TRAV;
+    }
+    // one iteration of the outer loop of VolumeTrackingGVDB inside a level-1 node, up to (not including) the adapter call
+    VRD void travStep(const DSlot& g) {
+        if (!(iter < 4096 && inRange(p, g.res[1] + 1))) { phase = MARCH_DONE; return; }
+        iter++;
+        next();
+        const unsigned b = (unsigned)((((p.z << g.dim[1]) + p.y) << g.dim[1]) + p.x);
+        uint32_t child = ID_UNDEFL;
+        if (link1 != ID_UNDEFL) {
+            // p == res passes the inclusive bound (VR/VolumeUtils.slang:231) and aliases into the list like the shader's
+            // ByteAddressBuffer load; outside the whole list D3D returns 0.  link1 < node count and the list holds < 2^31
+            // entries (checked at upload), so 32-bit arithmetic cannot wrap.
+            const unsigned idx = link1 * g.res3[1] + b;
+            child = idx >= g.childCount32[1] ? 0u : __ldg(g.child[1] + idx);
+        }
+        if (child == ID_UNDEFL) { step(); if (tx > tMax1) phase = MARCH_ASCEND; return; }
+        brick = child;   // leaf node id until enterBrick() replaces it with the brick id
+        phase = MARCH_ENTER;
+    }
+
+    // ---- in-brick sampling (group 2) --------------------------------------------------------------------------------
+    // MARCH_ENTER: prologue of MediumTrRayMarchingAdapter::ExecuteMainStep
+    VRD void enterBrick(const DSlot& g) {
+        const int4 leaf = __ldg((const int4*)&g.nodes[0][brick]);
+        brick = (uint32_t)leaf.w;
+        float tt = tx - 0.01f;
+        tt = tNear + (floorf((tt - tNear) / tStep) + 0.5f) * tStep;
+        if (tt < tx) tt += tStep;
+        t = tt;
+        const float3 wp = pos + tt * dir;
+        pb = wp - nodePos(leaf);
+        biter = 0;
+        phase = MARCH_BRICK;
     }
 
     VRD float sampleFast(const DSlot& g) {   // sampleBrickLinear<false> on the quad repack, same filter arithmetic
@@ -207,15 +228,14 @@ struct Marcher {
     VRD void sampleStep(const DSlot& g, bool linear) {
         const float res = 8.f;   // bricks are 8^3 (VRESTIR_BRICK_VOXELS = 10^3 with apron)
         if (!(biter < MAX_BRICK_STEPS && pb.x >= 0 && pb.y >= 0 && pb.z >= 0 && pb.x < res && pb.y < res && pb.z < res)) {
-            step();
-            phase = MARCH_TRAV;
-            ascend(g);
+            phase = MARCH_EXIT;
             return;
         }
 #pragma unroll
         for (int k = 0; k < NT; k++)
             if ((pending >> k) & 1u) { if (t >= thrEff[k]) { out[k] = Tr; pending &= ~(1u << k); } }
-        if (!pending) { phase = MARCH_DONE; return; }
+        // every further sample can only lower Tr and expf(x) == 0 for x <= -110: the remaining thresholds are exactly 0
+        if (!pending || Tr < -110.f) { phase = MARCH_DONE; return; }
         float density;
         if (FAST) density = sampleFast(g) * g.compress_scale * c_scene.vol.densityScaleFactorByScaling;
         else density = DensityInAtlas<false>(g, brick, pb, linear);
@@ -239,7 +259,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
     m.phase = MARCH_IDLE;
     bool drained = false;
     for (;;) {
-        unsigned parked = __ballot_sync(FULL, !(m.phase & 1));
+        unsigned parked = __ballot_sync(FULL, m.phase < 2);
         if (__popc(parked) >= VR_REFILL_MIN) {
             if (m.phase == MARCH_DONE) m.writeOut(results);
             if (!drained) {
@@ -247,7 +267,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(cursor, n);
                 base = __shfl_sync(FULL, base, 0);
-                if (!(m.phase & 1)) {
+                if (m.phase < 2) {
                     const unsigned idx = base + __popc(parked & ltMask);
                     if (idx < total) {
                         const uint4 a = __ldcs(&tasks[2 * (size_t)idx]), b = __ldcs(&tasks[2 * (size_t)idx + 1]);
@@ -256,18 +276,24 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
                 }
                 if (base + n >= total) drained = true;
             }
-            parked = __ballot_sync(FULL, !(m.phase & 1));
+            parked = __ballot_sync(FULL, m.phase < 2);
             if (parked == FULL) {
                 if (__ballot_sync(FULL, m.phase == MARCH_DONE)) continue;   // box misses of this refill: write them out first
                 if (drained) break;
                 continue;
             }
         }
-        const unsigned tm = __ballot_sync(FULL, m.phase == MARCH_TRAV);
-        if (2 * __popc(tm) >= 32 - __popc(parked)) {
+        const int grp = m.phase >> 1;
+        const int nT = __popc(__ballot_sync(FULL, grp == 1)), nS = __popc(__ballot_sync(FULL, grp == 2));
+        const int nSlow = 32 - __popc(parked) - nT - nS;
+        if (VR_SLOW_WEIGHT * nSlow >= max(nT, nS)) {
+            if (grp == 3) m.slowStep(g);
+        } else if (nT >= nS) {
+            if (m.phase == MARCH_EXIT) m.exitBrick();
 #pragma unroll 1
             for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.phase == MARCH_TRAV) m.travStep(g);
         } else {
+            if (m.phase == MARCH_ENTER) m.enterBrick(g);
 #pragma unroll 1
             for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.phase == MARCH_BRICK) m.sampleStep(g, linear);
         }

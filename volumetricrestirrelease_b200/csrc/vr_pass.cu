@@ -184,6 +184,7 @@ int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
         if (g.childlist_count[l] >= (1ull << 31)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "child list too large");
         s.nodes[l] = (const vrestir_node*)d.nodes[l]; s.child[l] = (const uint32_t*)d.child[l]; s.childCount[l] = g.childlist_count[l];
         s.childCount32[l] = (unsigned)g.childlist_count[l];
+        s.ivdel[l] = 1.0f / g.vdel[l]; s.res3[l] = (unsigned)(g.res[l] * g.res[l] * g.res[l]);
     }
     if (!g.nodes[g.top_lev] || !g.node_count[g.top_lev]) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "slot has no root node");
     for (int i = 0; i < 3; i++) s.rootPos[i] = g.nodes[g.top_lev][0].pos[i];

@@ -21,6 +21,7 @@ struct DSlot {
     const void* atlas;
     const uint32_t* quads;   // UNORM8 single-channel slots: [brick][10][9][9] words of 2x2 xy-neighbours (trilinear = 2 loads)
     unsigned childCount32[3];
+    float ivdel[3]; unsigned res3[3];   // 1 / vdel (IEEE, computed on the host) and res^3
     int rootPos[3]; uint32_t rootLink;   // nodes[top_lev][0]: the root never changes during a launch, the march engine reads it from constants
 };
 
