@@ -223,7 +223,7 @@ def test_three_level_tree_full_reuse():
 def _frames_buffers(params, scene, w, h, wavefront, frames=3):
     """Run `frames` frames through the public execute() and return (image, final reservoirs) of the last one."""
     import torch
-    gp = VolumetricReSTIR.create({"mParams": params, "mUseWavefront": int(wavefront)})
+    gp = VolumetricReSTIR.create({"mParams": params, "mUseWavefront": int(wavefront), "mWavefrontInitial": int(wavefront)})
     gp.setScene(scene, w, h)
     color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     for _ in range(frames):

@@ -1339,6 +1339,27 @@ VRD void resampleNeighbor(Reservoir& tap, const Ray& ray, SampleGenerator& sg, c
     tap.p_y = p_y_hat;
 }
 
+// ------------------------------------------------------------------------------------------------ march-task streams
+// Append one task per lane with `has` to a stream; every lane of the warp must call (one atomic per warp).
+VRD void wfEmit(const WfStream& s, bool has, uint4 a, uint4 b) {
+    const unsigned bal = __ballot_sync(0xffffffffu, has);
+    if (!bal) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(s.count, (unsigned)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (has) {
+        const unsigned pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (pos < s.capacity) { s.tasks[2 * (size_t)pos] = a; s.tasks[2 * (size_t)pos + 1] = b; }
+    }
+}
+VRD uint4 wfLightTask(const Ray& sh, unsigned out) {
+    return make_uint4(__float_as_uint(sh.dir.x), __float_as_uint(sh.dir.y), __float_as_uint(sh.dir.z), out);
+}
+VRD uint4 wfLightTaskOrigin(const Ray& sh) {
+    return make_uint4(__float_as_uint(sh.origin.x), __float_as_uint(sh.origin.y), __float_as_uint(sh.origin.z), __float_as_uint(sh.tMax));
+}
+
 // ------------------------------------------------------------------------------------------------ pixel mapping
 // one thread per pixel; a warp covers an 8x4 pixel tile, a CTA of 4 warps 16x8 pixels
 VRD bool pixelOf(const FrameParams& fp, int& x, int& y) {

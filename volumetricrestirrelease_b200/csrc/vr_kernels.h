@@ -6,7 +6,7 @@ namespace vrd {
 cudaError_t readDebugRays(float* out64x8, unsigned* count);
 cudaError_t uploadScene(const DScene& s, cudaStream_t st);
 cudaError_t launchFeatures(const FrameParams& fp, cudaStream_t st);
-cudaError_t launchInitial(const FrameParams& fp, cudaStream_t st);
+cudaError_t launchInitial(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchTemporal(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchSpatial(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchFinal(const FrameParams& fp, cudaStream_t st);
@@ -17,6 +17,7 @@ cudaError_t uploadSceneWavefront(const DScene& s, cudaStream_t st);
 int marchBlocksPerSM(int nt);
 cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st);
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
+cudaError_t launchInitialFinish(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchResToAos(ResBuf b, vrestir_reservoir* out, int n, cudaStream_t st);
 cudaError_t launchResFromAos(ResBuf b, const vrestir_reservoir* in, int n, cudaStream_t st);

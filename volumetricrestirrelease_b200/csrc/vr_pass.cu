@@ -94,6 +94,7 @@ struct vrestir_pass {
     void* persistBase = nullptr; size_t persistBytes = 0;
     // wavefront (task-stream) path: march-task streams, result blocks, counters {cam.count, cam.cursor, light.count, light.cursor}
     bool mUseWavefront = true;
+    bool mWavefrontInitial = false;   // K1's p-hat re-evaluation through the march engine: measured slower (short single-threshold rays), off by default
     uint4* wfCamTasks = nullptr; uint4* wfLightTasks = nullptr; float* wfResults = nullptr; unsigned* wfCounters = nullptr;
     size_t wfPixels = 0;
     int marchBlocks1 = 0, marchBlocks3 = 0;
@@ -149,11 +150,18 @@ WfBufs wfView(const vrestir_pass* p) {
     w.results = p->wfResults;
     return w;
 }
-// the wavefront form of K3 covers the default option family; everything else runs the per-pixel kernel
-bool wavefrontSpatialOk(const vrestir_pass* p) {
+// the wavefront forms cover the default option family (single bounce, ray-marched p-hat under the spatial options);
+// everything else runs the per-pixel kernels
+bool wavefrontEvalOk(const vrestir_pass* p) {
     const vrestir_params& m = p->P;
-    return p->mUseWavefront && m.mMaxBounces == 1 && m.mSpatialSampleCount <= 4 && m.mSpatialVisibilityTrackingMethod == VRESTIR_RAY_MARCHING &&
+    return p->mUseWavefront && m.mMaxBounces == 1 && m.mSpatialVisibilityTrackingMethod == VRESTIR_RAY_MARCHING &&
            m.mSpatialLightingTrackingMethod == VRESTIR_RAY_MARCHING;
+}
+bool wavefrontSpatialOk(const vrestir_pass* p) { return wavefrontEvalOk(p) && p->P.mSpatialSampleCount <= 4; }
+void wavefrontKinds(const vrestir_pass* p, MarchKind& cam, MarchKind& light) {
+    const vrestir_params& m = p->P;
+    cam = MarchKind{m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 1};
+    light = MarchKind{m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0};
 }
 
 void freeSlot(DevSlot& d) {
@@ -375,7 +383,23 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
         case 1:
             if (active) {
                 fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
-                CK(launchInitial(fp, st)); p->launches++;
+                const bool defer = p->mWavefrontInitial && wavefrontEvalOk(p) && !m.mUseReference;
+                WfBufs wf{};
+                MarchKind kc{}, kl{};
+                if (defer) {
+                    rc = ensureWavefront(p); if (rc) return rc;
+                    wf = wfView(p);
+                    CK(cudaMemsetAsync(p->wfCounters, 0, 16, st));
+                    fp.deferPHat = 1;
+                    wavefrontKinds(p, kc, kl);
+                }
+                CK(launchInitial(fp, wf, st)); p->launches++;
+                if (defer) {
+                    CK(launchMarch(wf.cam, wf.results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st));
+                    CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
+                    CK(launchInitialFinish(fp, wf, st));
+                    p->launches += 3;
+                }
                 p->finalPhys = p->ia;
             }
             recordEv(p, 2, st);
@@ -403,8 +427,8 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                     const WfBufs wf = wfView(p);
                     CK(cudaMemsetAsync(p->wfCounters, 0, 16, st));
                     CK(launchSpatialGather(fp, wf, st));
-                    const MarchKind kc = {m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 1};
-                    const MarchKind kl = {m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0};
+                    MarchKind kc, kl;
+                    wavefrontKinds(p, kc, kl);
                     CK(launchMarch(wf.cam, wf.results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st));
                     CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
                     CK(launchSpatialCombine(fp, wf, st));
@@ -718,7 +742,8 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
         else if (k == "volumeAlbedoExtraControl") p->albedoExtra = (float)value;
         else if (k == "volumeAnisotropyExtraControl") p->anisotropyExtra = (float)value;
         else if (k == "mEnvSamplerType") p->envSamplerType = (int)value;
-        else if (k == "mUseWavefront") p->mUseWavefront = value != 0;   // 0 forces the per-pixel kernels (A/B tests)
+        else if (k == "mUseWavefront") p->mUseWavefront = value != 0;
+        else if (k == "mWavefrontInitial") p->mWavefrontInitial = value != 0;   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
     }

@@ -61,6 +61,7 @@ struct FrameParams {
     int frameCount, numTotalRounds, maxBounces;
     int useReference, baselineSpp, initialM, useRussianRoulette, noReuse, useCoarserGrid;
     int visualizeTransmittance, outputMotionVec;
+    int deferPHat;   // K1: leave the final p-hat re-evaluation to the march engine (k_initial_finish applies it)
     // temporal
     float temporalMThreshold; uint32_t temporalMIS, reprojectionMode; int reprojectionMip;
     // spatial

@@ -234,6 +234,22 @@ __global__ void __launch_bounds__(128) k_spatial_combine(FrameParams fp, WfBufs 
     storeReservoir(fp.out, pixelId, output);
 }
 
+// ------------------------------------------------------------------------------------------------ K1 finish
+// VR/TraceRays.cs.slang:176-183: p-hat of the pixel's own reservoir on its own ray under the spatial options
+__global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfBufs wf) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    const int pixelId = y * fp.W + x;
+    const float4 a = fp.cur.p0[pixelId];   // (runningSum, M, depth, p_y)
+    if (!(a.x > 0.f)) return;
+    Reservoir r = loadReservoirRW(fp.cur, pixelId, 1);
+    const float* blk = wf.results + (size_t)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
+    const float p_hat = wfPHat(r, c_scene.camPos, tapRayDir(fp, x, y), blk, 0, 0);
+    r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
+    r.p_y = p_hat;
+    fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 gridForWf(const FrameParams& fp) { return dim3((fp.W + 15) / 16, (fp.rowEnd - fp.rowBegin + 7) / 8); }
 
@@ -253,6 +269,7 @@ cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind
     return cudaGetLastError();
 }
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
+cudaError_t launchInitialFinish(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_initial_finish<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 
 }  // namespace vrd
