@@ -194,11 +194,11 @@ __device__ float3 IntegrateByVolumePathTracing(Ray ray, SampleGenerator& sg, con
     return L;
 }
 
-template <int B>
+template <int B, bool DEFER>
 __global__ void __launch_bounds__(128, VR_MINB) k_initial(FrameParams fp, WfBufs wf) {
     int x, y;
     const bool inFrame = pixelOf(fp, x, y);
-    const bool defer = B == 1 && fp.deferPHat;   // warp-uniform: every lane has to reach the task emission below
+    constexpr bool defer = B == 1 && DEFER;   // every lane has to reach the task emission below
     if (!defer && !inFrame) return;
     bool hasCam = false, hasLight = false;
     uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, la = ca, lb = ca;
@@ -564,10 +564,10 @@ cudaError_t uploadScene(const DScene& s, cudaStream_t st) { return cudaMemcpyToS
 cudaError_t launchFeatures(const FrameParams& fp, cudaStream_t st) { k_features<<<gridFor(fp), 128, 0, st>>>(fp); return cudaGetLastError(); }
 cudaError_t launchInitial(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) {
     switch (fp.maxBounces) {
-        case 1: k_initial<1><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
-        case 2: k_initial<2><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
-        case 3: k_initial<3><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
-        default: k_initial<4><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
+        case 1: if (fp.deferPHat) k_initial<1, true><<<gridFor(fp), 128, 0, st>>>(fp, wf); else k_initial<1, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
+        case 2: k_initial<2, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
+        case 3: k_initial<3, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
+        default: k_initial<4, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
     }
     return cudaGetLastError();
 }

@@ -409,7 +409,40 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                 if (p->mTemporalSampleAccumulated != 0) {   // gIsFirstFrame skips the kernel (VR/TemporalReuse.cs.slang:93)
                     fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
                     fp.temporal = resView(p, p->it); fp.extTemporal = p->ext[p->it];
-                    CK(launchTemporal(fp, st)); p->launches++;
+                    if (wavefrontEvalOk(p)) {
+                        rc = ensureWavefront(p); if (rc) return rc;
+                        // four explicit-origin streams {camera, light} x {current, previous frame}; identical march configurations share one stream
+                        const bool prevGrid = p->scene.vol.usePrevGridForReproj && p->scene.vol.hasAnimation;
+                        const int off = prevGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
+                        MarchKind kinds[4] = {{m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 0},
+                                              {m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0},
+                                              {m.mSpatialVisibilityMipLevel + off, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 0},
+                                              {m.mSpatialLightingMipLevel + off, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0}};
+                        for (int k = 0; k < 4; k++)
+                            if (kinds[k].mip < 0 || kinds[k].mip >= VRESTIR_MAX_SLOTS || !p->scene.slots[kinds[k].mip].valid) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "temporal reuse names a grid slot that is not bound");
+                        WfBufs4 wf{};
+                        wf.results = p->wfResults;
+                        const size_t n = p->wfPixels;
+                        // one buffer (16 n tasks) is plenty: <= 4 tasks per pixel in this stage
+                        uint4* bufs[4] = {p->wfLightTasks, p->wfLightTasks + 2 * (2 * n), p->wfLightTasks + 2 * (4 * n), p->wfLightTasks + 2 * (6 * n)};
+                        bool unique[4];
+                        for (int k = 0; k < 4; k++) {
+                            int alias = -1;
+                            for (int j = 0; j < k && alias < 0; j++) if (memcmp(&kinds[j], &kinds[k], sizeof(MarchKind)) == 0) alias = j;
+                            unique[k] = alias < 0;
+                            if (alias >= 0) wf.s[k] = wf.s[alias];
+                            else { wf.s[k].tasks = bufs[k]; wf.s[k].count = p->wfCounters + 2 * k; wf.s[k].cursor = p->wfCounters + 2 * k + 1; wf.s[k].capacity = (unsigned)(2 * n); }
+                        }
+                        // aliased streams can receive up to 4 tasks per pixel: they own the whole remaining buffer
+                        if (!unique[1] && !unique[2] && !unique[3]) wf.s[0].capacity = wf.s[1].capacity = wf.s[2].capacity = wf.s[3].capacity = (unsigned)(12 * n);
+                        else if (!unique[2] && !unique[3]) { wf.s[0].capacity = wf.s[2].capacity = (unsigned)(2 * n); wf.s[1].capacity = wf.s[3].capacity = (unsigned)(2 * n); }
+                        CK(cudaMemsetAsync(p->wfCounters, 0, 32, st));
+                        CK(launchTemporalGather(fp, wf, st));
+                        for (int k = 0; k < 4; k++)
+                            if (unique[k]) { CK(launchMarch(wf.s[k], wf.results, kinds[k], p->scene.slots[kinds[k].mip], 1, p->marchBlocks1, st)); p->launches++; }
+                        CK(launchTemporalCombine(fp, wf, st));
+                        p->launches += 2;
+                    } else { CK(launchTemporal(fp, st)); p->launches++; }
                 }
                 p->finalPhys = p->ia;
             }

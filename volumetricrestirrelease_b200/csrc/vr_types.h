@@ -84,5 +84,8 @@ struct WfStream { uint4* tasks; unsigned* count; unsigned* cursor; unsigned capa
 // ray j to the depth of tap i (k = i - (i > j)), L[i*4+j] light transmittance from that point
 enum { WF_BLOCK = 48, WF_D = 0, WF_C = 16, WF_L = 28 };
 struct WfBufs { WfStream cam, light; float* results; };
+// K2: four explicit-origin streams {current camera, current light, previous-frame camera, previous-frame light};
+// streams whose march configuration is identical alias the same buffer
+struct WfBufs4 { WfStream s[4]; float* results; };
 
 }  // namespace vrd

@@ -153,10 +153,11 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
 }
 
 // ------------------------------------------------------------------------------------------------ K3 combine
-// evaluate_F_ / evaluate_P_hat (VR/ReSTIRHelper.slang:91-423, B == 1, current frame) with the density and the two
-// transmittances taken from the pixel's result block
-VRD float wfPHat(const Reservoir& tap, float3 origin, float3 dir, const float* blk, int i, int j) {
+// evaluate_F_ / evaluate_P_hat (VR/ReSTIRHelper.slang:91-423, B == 1) with the density at the sample point and the two
+// transmittances supplied by the caller (gather kernel / march engine)
+VRD float wfPHatV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, float density, float visibility, float lightTr) {
     const vrestir_volume_desc& vd = c_scene.vol;
+    const bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
     Ray ray = makeRay(origin, dir, 0.f, tap.depth);
     const bool isBackgroundSample = tap.depth == kRayTMax;
     const bool isSelfEmission = tap.lightID == VRESTIR_SELF_EMISSION_LIGHT_ID;
@@ -164,22 +165,49 @@ VRD float wfPHat(const Reservoir& tap, float3 origin, float3 dir, const float* b
     const float3 p_World = ray.at(ray.tMax);
     const MediumInteraction mi = makeMI(p_World, -ray.dir, true);
     const float3 sigA = v3(vd.sigma_a), sigS = v3(vd.sigma_s);
-    const float density = blk[WF_D + i * 4 + j];
     if (density == 0.f) return luminance(f3(0.f));
-    const float visibility = blk[WF_C + j * 3 + (i - (i > j ? 1 : 0))];
     const float3 sigma_s = isBackgroundSample ? f3(1.f) : (isSelfEmission ? sigA : sigS);
     F = F * (visibility * density * sigma_s);
     if (any_gt0(F)) {
-        if (isBackgroundSample) F = F * envEval(ray.dir, false);
-        else if (isSelfEmission) F = F * EmissionWorldSpace(p_World, false);
+        if (isBackgroundSample) F = F * envEval(ray.dir, isLastFrame);
+        else if (isSelfEmission) F = F * EmissionWorldSpace(p_World, useLastFrameGrid);
         else {
             Ray sh; float3 Ld;
-            const bool valid = lightRayAndLd(mi, tap.lightID, tap.lightUV, false, sh, Ld);
-            const float Tr = valid ? blk[WF_L + i * 4 + j] : 1.f;
+            const bool valid = lightRayAndLd(mi, tap.lightID, tap.lightUV, isLastFrame, sh, Ld);
+            const float Tr = valid ? lightTr : 1.f;
             F = F * (Tr * Ld);
         }
     }
     return luminance(F);
+}
+VRD float wfPHat(const Reservoir& tap, float3 origin, float3 dir, const float* blk, int i, int j) {
+    return wfPHatV(tap, origin, dir, false, blk[WF_D + i * 4 + j], blk[WF_C + j * 3 + (i - (i > j ? 1 : 0))], blk[WF_L + i * 4 + j]);
+}
+// Gather side of one p-hat evaluation: density point query, then (when the sample can contribute) one camera march task
+// (explicit origin, threshold = tap.depth) and one light march task.  Result slots: out+0 density, out+1 camera Tr, out+2 light Tr.
+// Every lane of the warp must call; `want` masks the lanes that have an evaluation.
+VRD void wfEmitEval(bool want, const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, float* results, unsigned out,
+                    const WfStream& camStream, const WfStream& lightStream) {
+    bool hasCam = false, hasLight = false;
+    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, la = ca, lb = ca;
+    if (want) {
+        const vrestir_volume_desc& vd = c_scene.vol;
+        const bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
+        const bool bg = tap.depth == kRayTMax;
+        const Ray r = makeRay(origin, dir, 0.f, tap.depth);
+        const float3 pW = r.at(r.tMax);
+        const float density = bg ? 1.f : DensityWorldSpace(pW, useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0);
+        results[out] = density;
+        if (density != 0.f) {
+            hasCam = true; ca = wfLightTaskOrigin(r); cb = wfLightTask(r, out + 1);
+            if (!bg && tap.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
+                Ray sh; float3 Ld;
+                if (lightRayAndLd(makeMI(pW, -dir, true), tap.lightID, tap.lightUV, isLastFrame, sh, Ld)) { hasLight = true; la = wfLightTaskOrigin(sh); lb = wfLightTask(sh, out + 2); }
+            }
+        }
+    }
+    wfEmit(camStream, hasCam, ca, cb);
+    wfEmit(lightStream, hasLight, la, lb);
 }
 
 __global__ void __launch_bounds__(128) k_spatial_combine(FrameParams fp, WfBufs wf) {
@@ -234,6 +262,168 @@ __global__ void __launch_bounds__(128) k_spatial_combine(FrameParams fp, WfBufs 
     storeReservoir(fp.out, pixelId, output);
 }
 
+// ------------------------------------------------------------------------------------------------ K2 wavefront
+// VR/TemporalReuse.cs.slang:80-377 for B == 1 and ray-marched p-hat: the kernel is cut at its two p-hat evaluations
+// (E1: the history sample on the current ray = resampleNeighbor; E0: the current sample on the previous-frame ray = the
+// Talbot MIS term).  Block slots: E0 = {0,1,2}, E1 = {3,4,5} (density, camera Tr, light Tr), 6 = state flag,
+// 7/8 = reprojected pixel, 9..12 = RNG state after the reprojection-depth sampling.
+enum { T2_E0 = 0, T2_E1 = 3, T2_FLAG = 6, T2_POS = 7, T2_SG = 9 };
+
+VRD float3 prevRayDir(const FrameParams& fp, int px, int py) {
+    return normalize(camRayDirNN(c_scene.prevU, c_scene.prevV, c_scene.prevW, px, py, fp.W, fp.H));
+}
+
+__global__ void __launch_bounds__(128) k_temporal_gather(FrameParams fp, WfBufs4 wf) {
+    int x, y;
+    const bool inFrame = pixelOf(fp, x, y);
+    const int W = fp.W, H = fp.H;
+    const int pixelId = inFrame ? y * W + x : fp.rowBegin * W;
+    const unsigned blkBase = (unsigned)(pixelId - fp.rowBegin * W) * WF_BLOCK;
+    float* blk = wf.results + blkBase;
+    bool wantE0 = false, wantE1 = false;
+    Reservoir t0 = createNewReservoir(), t1 = createNewReservoir();
+    float3 dirCur = f3(0.f), dirPrev = f3(0.f);
+    if (inFrame) {
+        SampleGenerator sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount + 1));
+        t0 = loadReservoir(fp.cur, pixelId, 1);
+        const Ray ray = primaryRay(fp, x, y);
+        dirCur = ray.dir;
+        int2 reprojScreenPos = make_int2(0, 0);
+        const int2 cf = fp.features[pixelId];
+        const bool isBackgroundReservoir = __int_as_float(cf.y) == 1.f && cf.x;
+        bool useFallbackReservoir = true, haveTap = false, skip = false;
+        if (fp.reprojectionMode != VRESTIR_REPROJECTION_NONE) {
+            float reprojDepth = t0.depth;
+            if (reprojDepth == kRayTMax && fp.reprojectionMode != VRESTIR_REPROJECTION_NO_BACKGROUND && !isBackgroundReservoir)
+                reprojDepth = RejectionSampleRandomPointByDensity(ray, sg, VRESTIR_NUM_MAX_MIPS + fp.reprojectionMip);
+            float3 pw = ray.origin + ray.dir * reprojDepth;
+            if (c_scene.vol.hasVelocity && c_scene.vol.hasAnimation) {
+                float3 v = VelocityWorld(pw) * c_scene.vol.velocityScale;
+                pw = pw - v;
+            }
+            const float* Vm = c_scene.prevView; const float* Pm = c_scene.prevProj;
+            float vp[4], cp[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) vp[j] = pw.x * Vm[0 + j] + pw.y * Vm[4 + j] + pw.z * Vm[8 + j] + 1.f * Vm[12 + j];
+#pragma unroll
+            for (int j = 0; j < 4; j++) cp[j] = vp[0] * Pm[0 + j] + vp[1] * Pm[4 + j] + vp[2] * Pm[8 + j] + vp[3] * Pm[12 + j];
+            float2 scrPos = make_float2(cp[0] / cp[3], cp[1] / cp[3]);
+            int2 scrPosI;
+            if (reprojDepth == kRayTMax) { scrPos = make_float2((float)x + 0.5f, (float)y + 0.5f); scrPosI = make_int2(x, y); }
+            else {
+                scrPos.x = 0.5f * scrPos.x + 0.5f; scrPos.y = -0.5f * scrPos.y + 0.5f;
+                scrPos.x *= (float)W; scrPos.y *= (float)H;
+                scrPosI = make_int2(f2i(scrPos.x), f2i(scrPos.y));
+            }
+            {
+                const int id = (int)((uint32_t)scrPosI.y * (uint32_t)W + (uint32_t)scrPosI.x);
+                int2 tf = make_int2(0, 0);
+                if (id >= 0 && id < W * H) tf = __ldg(&fp.featuresTemporal[id]);
+                const bool isTapBackgroundReservoir = __int_as_float(tf.y) == 1.f && tf.x;
+                if (isBackgroundReservoir && !isTapBackgroundReservoir) skip = true;   // keeps K1's reservoir (VR/TemporalReuse.cs.slang:190-197)
+            }
+            if (!skip) {
+                scrPosI = make_int2(f2i(scrPos.x), f2i(scrPos.y));
+                reprojScreenPos = scrPosI;
+                if (scrPosI.x >= 0 && scrPosI.x < W && scrPosI.y >= 0 && scrPosI.y < H) haveTap = true;
+                if (haveTap) useFallbackReservoir = false;
+            }
+        }
+        if (!skip && useFallbackReservoir) reprojScreenPos = make_int2(x, y);
+        if (fp.outputMotionVec && fp.outMvec) fp.outMvec[pixelId] = make_float2((float)(reprojScreenPos.x - x) / (float)W, (float)(reprojScreenPos.y - y) / (float)H);
+        blk[T2_FLAG] = skip ? 0.f : 1.f;
+        if (!skip) {
+            blk[T2_POS] = __int_as_float(reprojScreenPos.x); blk[T2_POS + 1] = __int_as_float(reprojScreenPos.y);
+            blk[T2_SG] = __uint_as_float(sg.s0); blk[T2_SG + 1] = __uint_as_float(sg.s1); blk[T2_SG + 2] = __uint_as_float(sg.s2); blk[T2_SG + 3] = __uint_as_float(sg.s3);
+            t1 = loadReservoir(fp.temporal, reprojScreenPos.y * W + reprojScreenPos.x, 1);
+            dirPrev = prevRayDir(fp, reprojScreenPos.x, reprojScreenPos.y);
+            if (t1.depth != kRayTMax) {
+                float3 worldPos = c_scene.prevPos + t1.depth * dirPrev;
+                t1.depth = length(worldPos - ray.origin);
+            }
+            float centerPrevFrameDepth = t0.depth;
+            if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_scene.prevPos); }
+            // E1: resampleNeighbor(taps[1]) on the current ray
+            if (t1.p_y > 0.f) {
+                if (isnan(t1.runningSum) || isinf(t1.runningSum)) t1.runningSum = 0.f;
+                wantE1 = t1.runningSum != 0.f;
+            }
+            // E0: Talbot term of taps[0] seen from the previous frame's ray
+            if (fp.temporalMIS == VRESTIR_MIS_TALBOT && t0.p_y > 0.f) {
+                if (isnan(t0.runningSum) || isinf(t0.runningSum)) t0.runningSum = 0.f;
+                wantE0 = t0.runningSum > 0.f;
+            }
+            t0.depth = centerPrevFrameDepth;   // usedDepth of the (i = 0, j = 1) term
+        }
+    }
+    wfEmitEval(wantE1, t1, c_scene.camPos, dirCur, false, wf.results, blkBase + T2_E1, wf.s[0], wf.s[1]);
+    wfEmitEval(wantE0, t0, c_scene.prevPos, dirPrev, true, wf.results, blkBase + T2_E0, wf.s[2], wf.s[3]);
+}
+
+__global__ void __launch_bounds__(128) k_temporal_combine(FrameParams fp, WfBufs4 wf) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    const int W = fp.W;
+    const int pixelId = y * W + x;
+    const float* blk = wf.results + (size_t)(pixelId - fp.rowBegin * W) * WF_BLOCK;
+    if (blk[T2_FLAG] == 0.f) return;
+    SampleGenerator sg;
+    sg.s0 = __float_as_uint(blk[T2_SG]); sg.s1 = __float_as_uint(blk[T2_SG + 1]); sg.s2 = __float_as_uint(blk[T2_SG + 2]); sg.s3 = __float_as_uint(blk[T2_SG + 3]);
+    const int2 reprojScreenPos = make_int2(__float_as_int(blk[T2_POS]), __float_as_int(blk[T2_POS + 1]));
+    Reservoir taps[2];
+    taps[0] = loadReservoirRW(fp.cur, pixelId, 1);
+    taps[1] = loadReservoir(fp.temporal, reprojScreenPos.y * W + reprojScreenPos.x, 1);
+    const Ray ray = primaryRay(fp, x, y);
+    const uint32_t mis = fp.temporalMIS;
+    Reservoir output = mis == VRESTIR_MIS_TALBOT ? createNewReservoir() : taps[0];
+    const int numUsedReservoirs = 2;
+    const float curM = taps[0].M;
+    const float MaxPrevM = fp.temporalMThreshold * curM;
+    const float3 dirPrev = prevRayDir(fp, reprojScreenPos.x, reprojScreenPos.y);
+    if (taps[1].depth != kRayTMax) {
+        float3 worldPos = c_scene.prevPos + taps[1].depth * dirPrev;
+        taps[1].depth = length(worldPos - ray.origin);
+    }
+    float centerPrevFrameDepth = taps[0].depth;
+    if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_scene.prevPos); }
+    const int startSampleId = mis == VRESTIR_MIS_TALBOT ? 0 : 1;
+    for (int i = startSampleId; i < numUsedReservoirs; i++) {
+        float talbotMISWeight = 1.f;
+        float neighbor_py = 0.f;
+        if (taps[i].p_y > 0.f) {
+            neighbor_py = taps[i].p_y;
+            if (isnan(taps[i].runningSum) || isinf(taps[i].runningSum)) taps[i].runningSum = 0.f;
+            if (i > 0 && taps[i].runningSum != 0.f) {   // resampleNeighbor
+                const float p_y_hat = wfPHatV(taps[i], ray.origin, ray.dir, false, blk[T2_E1], blk[T2_E1 + 1], blk[T2_E1 + 2]);
+                float weight = p_y_hat / taps[i].p_y;
+                if (isinf(weight) || isnan(weight)) weight = 0.f;
+                taps[i].runningSum *= weight;
+                taps[i].p_y = p_y_hat;
+            }
+        } else { taps[i].p_y = 0.f; taps[i].runningSum = 0.f; }
+        if (mis == VRESTIR_MIS_TALBOT && taps[i].runningSum > 0.f) {
+            float p_sum = 0, p_qi = 0, k = 0;
+            for (int j = 0; j < numUsedReservoirs; j++) {
+                const float correctedM = fminf(MaxPrevM, taps[j].M);
+                k += correctedM;
+                if (j == 0) { p_qi = taps[i].p_y; p_sum += taps[i].p_y * correctedM; }
+                else if (i == j) { p_qi = neighbor_py; p_sum += neighbor_py * correctedM; }
+                else {
+                    // i == 0, j == 1: taps[0] at depth centerPrevFrameDepth on the previous frame's ray
+                    Reservoir tp = taps[i]; tp.depth = centerPrevFrameDepth;
+                    float p_y = wfPHatV(tp, c_scene.prevPos, dirPrev, true, blk[T2_E0], blk[T2_E0 + 1], blk[T2_E0 + 2]);
+                    if (isinf(p_y) || isnan(p_y)) p_y = 0.f;
+                    p_sum += p_y * correctedM;
+                }
+            }
+            if (p_sum > 0) talbotMISWeight = p_qi * k / p_sum;
+        }
+        taps[i].runningSum *= talbotMISWeight;
+        simpleResampleStepWithMaxM<1>(taps[i], MaxPrevM, output, sg);
+    }
+    storeReservoir(fp.cur, pixelId, output);
+}
+
 // ------------------------------------------------------------------------------------------------ K1 finish
 // VR/TraceRays.cs.slang:176-183: p-hat of the pixel's own reservoir on its own ray under the spatial options
 __global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfBufs wf) {
@@ -269,6 +459,8 @@ cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind
     return cudaGetLastError();
 }
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
+cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
+cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchInitialFinish(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_initial_finish<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 
