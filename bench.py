@@ -246,6 +246,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = gp.launch_count() - launches0
+    wfc = gp.wavefront_counters()
+    if rank == 0:
+        print(f"[bench] wavefront: last-stage task streams (count, cursor) {wfc[:8]}", file=sys.stderr)
     # per-stage timings (pass-internal CUDA events on the launching stream), averaged over `steps` more frames
     stage_acc = {}
     for _ in range(args.steps):

@@ -328,6 +328,9 @@ int vrestir_get_launch_count(const vrestir_pass* pass, uint64_t* out);
 /* Diagnostics: world-space rays whose hierarchical DDA ran >= 1024 outer iterations since the last call
  * (8 floats each: origin, dir, mip (+100 when vertex-centred), iterations; first 64) and their total count. */
 int vrestir_debug_long_rays(vrestir_pass* pass, float* out64x8, uint32_t* count);
+/* Diagnostics of the wavefront path: out[0..7] = task-stream counters {count, cursor} x 4 of the last stage run,
+ * out[8..15] reserved. */
+int vrestir_debug_wavefront_counters(vrestir_pass* pass, uint32_t out[16]);
 
 /* Buffer access.  Host copies use the AoS views documented at the enum; `bytes` must match vrestir_buffer_bytes. */
 int vrestir_buffer_bytes(const vrestir_pass* pass, int buffer, size_t* bytes);

@@ -223,7 +223,7 @@ def test_three_level_tree_full_reuse():
 def _frames_buffers(params, scene, w, h, wavefront, frames=3):
     """Run `frames` frames through the public execute() and return (image, final reservoirs) of the last one."""
     import torch
-    gp = VolumetricReSTIR.create({"mParams": params, "mUseWavefront": int(wavefront), "mWavefrontInitial": int(wavefront)})
+    gp = VolumetricReSTIR.create({"mParams": params, "mUseWavefront": int(wavefront), **({} if wavefront is True else {"mInitialMode": int(wavefront)})})
     gp.setScene(scene, w, h)
     color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     for _ in range(frames):
@@ -250,8 +250,9 @@ def test_wavefront_equals_per_pixel(variant):
         kw = dict(mUseAnalyticLights=1)
     sc = sc or env_scene()
     p = VolumetricReSTIRParams(**kw)
-    img_w, res_w = _frames_buffers(p, sc, w, h, True)
     img_s, res_s = _frames_buffers(p, sc, w, h, False)
-    assert np.array_equal(res_w.view(np.uint32), res_s.view(np.uint32)), "wavefront reservoirs differ from the per-pixel kernels"
-    assert np.array_equal(img_w.view(np.uint32), img_s.view(np.uint32))
+    for mode in (True, 2):   # True: default wavefront pipeline (speculative K1); 2: K1 per-pixel + p-hat through the engine
+        img_w, res_w = _frames_buffers(p, sc, w, h, mode)
+        assert np.array_equal(res_w.view(np.uint32), res_s.view(np.uint32)), f"wavefront reservoirs (mode {mode}) differ from the per-pixel kernels"
+        assert np.array_equal(img_w.view(np.uint32), img_s.view(np.uint32))
     assert (img_w[..., :3].sum(-1) > 0).mean() > 0.05

@@ -132,7 +132,7 @@ SYMBOLS = [
     "vrestir_set_analytic_lights", "vrestir_set_emissive_triangles", "vrestir_get_emissive_alias",
     "vrestir_get_env_alias", "vrestir_set_frame", "vrestir_update", "vrestir_set_params", "vrestir_get_params",
     "vrestir_set_frame_count", "vrestir_set_prev_camera", "vrestir_get_frame_count", "vrestir_execute",
-    "vrestir_execute_host", "vrestir_execute_stage", "vrestir_get_timings", "vrestir_debug_long_rays", "vrestir_get_launch_count",
+    "vrestir_execute_host", "vrestir_execute_stage", "vrestir_get_timings", "vrestir_debug_long_rays", "vrestir_debug_wavefront_counters", "vrestir_get_launch_count",
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
     "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
     "vrestir_scene_grid", "vrestir_scene_dense_mip", "vrestir_scene_stats", "vrestir_camera_look_at",
@@ -178,6 +178,7 @@ def lib():
     L.vrestir_execute_stage.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.vrestir_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.vrestir_debug_long_rays.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
+    L.vrestir_debug_wavefront_counters.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.vrestir_get_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.vrestir_buffer_bytes.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
     L.vrestir_get_buffer.argtypes = [vp, C.c_int, vp, C.c_size_t]

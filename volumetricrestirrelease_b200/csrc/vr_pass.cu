@@ -94,10 +94,11 @@ struct vrestir_pass {
     void* persistBase = nullptr; size_t persistBytes = 0;
     // wavefront (task-stream) path: march-task streams, result blocks, counters {cam.count, cam.cursor, light.count, light.cursor}
     bool mUseWavefront = true;
-    bool mWavefrontInitial = false;   // K1's p-hat re-evaluation through the march engine: measured slower (short single-threshold rays), off by default
+    int mInitialMode = 1;   // K1: 0 per-pixel kernel, 1 lock-step wavefront (default), 2 per-pixel + p-hat re-evaluation through the march engine (measured slower)
     uint4* wfCamTasks = nullptr; uint4* wfLightTasks = nullptr; float* wfResults = nullptr; unsigned* wfCounters = nullptr;
     size_t wfPixels = 0;
     int marchBlocks1 = 0, marchBlocks3 = 0;
+    float* wfInitialState = nullptr; size_t wfInitialPixels = 0;   // lock-step wavefront K1
 };
 
 namespace {
@@ -383,7 +384,34 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
         case 1:
             if (active) {
                 fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
-                const bool defer = p->mWavefrontInitial && wavefrontEvalOk(p) && !m.mUseReference;
+                // lock-step wavefront K1 (vr_wavefront.cu): single bounce, reuse on, <= 4 candidates, ray-marched light visibility
+                const bool wfInitial = wavefrontEvalOk(p) && !m.mUseReference && !fp.noReuse && m.mInitialM <= 4 &&
+                                       m.mInitialLightingTrackingMethod == VRESTIR_RAY_MARCHING && m.mInitialLightSamples <= 1 && p->mInitialMode == 1;
+                if (wfInitial) {
+                    rc = ensureWavefront(p); if (rc) return rc;
+                    const size_t n = p->wfPixels;
+                    if (p->wfInitialPixels != n) {
+                        if (p->wfInitialState) cudaFree(p->wfInitialState);
+                        p->wfInitialState = nullptr; p->wfInitialPixels = 0;
+                        if (n * K1_STRIDE >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit record indices; shard the frame");
+                        CK(cudaMalloc(&p->wfInitialState, n * K1_STRIDE * sizeof(float)));
+                        p->wfInitialPixels = n;
+                    }
+                    WfInitial wi;
+                    wi.light.tasks = p->wfLightTasks; wi.light.count = p->wfCounters; wi.light.cursor = p->wfCounters + 1; wi.light.capacity = (unsigned)n;
+                    wi.state = p->wfInitialState;
+                    fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
+                    const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0};
+                    for (int s = 0; s <= m.mInitialM; s++) {
+                        if (s < m.mInitialM) CK(cudaMemsetAsync(p->wfCounters, 0, 8, st));
+                        CK(launchInitialStep(fp, wi, s, st)); p->launches++;
+                        if (s < m.mInitialM) { CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st)); p->launches++; }
+                    }
+                    p->finalPhys = p->ia;
+                    recordEv(p, 2, st);
+                    break;
+                }
+                const bool defer = p->mInitialMode == 2 && wavefrontEvalOk(p) && !m.mUseReference;
                 WfBufs wf{};
                 MarchKind kc{}, kl{};
                 if (defer) {
@@ -605,7 +633,7 @@ int vrestir_destroy(vrestir_pass* p) {
     for (auto& d : p->dslots) freeSlot(d);
     for (int i = 0; i < 3; i++) { if (p->res[i]) cudaFree(p->res[i]); if (p->ext[i]) cudaFree(p->ext[i]); }
     for (int i = 0; i < 2; i++) if (p->feat[i]) cudaFree(p->feat[i]);
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters};
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
@@ -776,7 +804,7 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
         else if (k == "volumeAnisotropyExtraControl") p->anisotropyExtra = (float)value;
         else if (k == "mEnvSamplerType") p->envSamplerType = (int)value;
         else if (k == "mUseWavefront") p->mUseWavefront = value != 0;
-        else if (k == "mWavefrontInitial") p->mWavefrontInitial = value != 0;   // 0 forces the per-pixel kernels (A/B tests)
+        else if (k == "mInitialMode") p->mInitialMode = (int)value;   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
     }
@@ -944,6 +972,15 @@ int vrestir_spatial_input_buffer(const vrestir_pass* p, int round, int* buffer) 
     return VRESTIR_OK;
 }
 
+int vrestir_debug_wavefront_counters(vrestir_pass* p, uint32_t out[16]) {
+    if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    memset(out, 0, 64);
+    if (!p->wfCounters) return VRESTIR_OK;
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, p->wfCounters, 64, cudaMemcpyDeviceToHost));
+    return VRESTIR_OK;
+}
 int vrestir_debug_long_rays(vrestir_pass* p, float* out64x8, uint32_t* count) {
     if (!p || !out64x8 || !count) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     CK(cudaSetDevice(p->device));

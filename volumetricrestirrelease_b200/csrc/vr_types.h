@@ -84,6 +84,9 @@ struct WfStream { uint4* tasks; unsigned* count; unsigned* cursor; unsigned capa
 // ray j to the depth of tap i (k = i - (i > j)), L[i*4+j] light transmittance from that point
 enum { WF_BLOCK = 48, WF_D = 0, WF_C = 16, WF_L = 28 };
 struct WfBufs { WfStream cam, light; float* results; };
+// K1 lock-step candidate state: K1_STRIDE floats per pixel (vr_wavefront.cu)
+enum { K1_WORDS = 20, K1_STRIDE = 80 };
+struct WfInitial { WfStream light; float* state; };
 // K2: four explicit-origin streams {current camera, current light, previous-frame camera, previous-frame light};
 // streams whose march configuration is identical alias the same buffer
 struct WfBufs4 { WfStream s[4]; float* results; };

@@ -262,6 +262,183 @@ __global__ void __launch_bounds__(128) k_spatial_combine(FrameParams fp, WfBufs 
     storeReservoir(fp.out, pixelId, output);
 }
 
+// ------------------------------------------------------------------------------------------------ K1 wavefront
+// VR/TraceRays.cs.slang:64-201 + VR/ComputeInitialSample.slang for B == 1 with reuse enabled and ray-marched light
+// visibility.  The candidate loop is cut at the shadow march of SampleDirectLighting (VR/VolumeUtils.slang:454-492) and run
+// as M + 1 lock-step kernels with one march launch between two of them:
+//   k_initial_step(0)      traversal (<= 4 distance candidates) + light sample of candidate 0 -> one light-march task
+//   k_march                the shadow marches of candidate s of all pixels
+//   k_initial_step(s)      finishes candidate s-1 with its visibility, streams it through the reservoir (the WRS draw),
+//                          then samples the light of candidate s;  the last step re-evaluates p-hat and stores.
+// The random-number stream of candidate s+1 starts after the draws of candidate s, and whether candidate s draws its WRS
+// number depends on its weight and hence on its march (VR/Reservoir.slang:29-32; a visibility that underflows to exactly 0
+// is common in dense clouds: 40 % of the pixels of the bench frame have one), so the candidates of ONE pixel cannot be
+// marched together; the candidates s of ALL pixels can.
+struct K1Cand {
+    unsigned flags;        // bit0 valid hit, bit1 hitEmpty, bit2 light sample valid, bit3 shadow march, bit4 speculated weight > 0
+    float hd, pd, ot, density;
+    float3 Li; float ph, outLightPdf;
+    float3 Le; int lightID; float2 lightUV;
+    float uEm, uWrs;   // uWrs unused (kept for the record layout)
+};
+VRD Reservoir k1Finish(const K1Cand& c, float vis, const FrameParams& fp) {
+    const vrestir_volume_desc& vd = c_scene.vol;
+    const float3 sigA = v3(vd.sigma_a), sigS = v3(vd.sigma_s);
+    Reservoir out = createNewReservoir();
+    out.M = 1;
+    const bool valid = c.flags & 1u;
+    const float pathPdf = 1.f * c.pd;
+    out.depth = valid ? c.hd : kRayTMax;
+    out.p_y = pathPdf;
+    if (c.flags & 2u) { out.p_y = 0.f; out.runningSum = 0.f; return out; }
+    if (valid) {
+        const float3 albedo = sigS / vd.sigma_t;
+        out.lightID = c.lightID; out.lightUV = c.lightUV;
+        float3 Ld = f3(0.f);
+        if (c.flags & 4u) {
+            float3 Li = c.Li;
+            if (c.flags & 8u) Li = Li * vis;
+            Ld = Ld + c.ph * Li / 1.f;
+        }
+        const float3 one_minus_albedo = f3(1.f) - albedo;
+        float p_src = out.p_y;
+        {
+            float lumE = luminance(one_minus_albedo * c.Le);
+            float emissionRatio = lumE / (lumE + luminance(albedo * Ld));
+            if (isnan(emissionRatio)) emissionRatio = 0.f;
+            if (c.uEm < emissionRatio) { p_src *= emissionRatio; out.lightID = VRESTIR_SELF_EMISSION_LIGHT_ID; }
+            else p_src *= c.outLightPdf * (1 - emissionRatio);
+        }
+        out.runningSum = p_src == 0.f ? 0.f : 1.f;
+        out.p_y = p_src;
+        float pathPHat = 1.f;
+        pathPHat *= c.ot;
+        pathPHat *= c.density;
+        float p_y;
+        if (out.lightID == VRESTIR_SELF_EMISSION_LIGHT_ID) p_y = pathPHat * luminance(sigA * c.Le);
+        else p_y = pathPHat * luminance(sigS * Ld * c.outLightPdf);
+        if (out.runningSum > 0.f) {
+            out.runningSum = out.p_y == 0.f ? 0.f : p_y / out.p_y;
+            out.p_y = p_y;
+        }
+    } else {
+        float pathPHat = 1.f;
+        pathPHat *= c.ot;
+        const float p_y = pathPHat * luminance(c.Le);   // Le = envEval(ray.dir) for a candidate that left the volume
+        out.runningSum = out.p_y == 0.f ? 0.f : p_y / out.p_y;
+        out.p_y = p_y;
+    }
+    return out;
+}
+VRD void k1Store(float* r, const K1Cand& c) {
+    float4* q = (float4*)r;
+    q[0] = make_float4(__uint_as_float(c.flags), c.hd, c.pd, c.ot);
+    q[1] = make_float4(c.density, c.Li.x, c.Li.y, c.Li.z);
+    q[2] = make_float4(c.ph, c.outLightPdf, c.Le.x, c.Le.y);
+    q[3] = make_float4(c.Le.z, __int_as_float(c.lightID), c.lightUV.x, c.lightUV.y);
+    r[16] = c.uEm; r[17] = c.uWrs;
+}
+VRD K1Cand k1Load(const float* r) {
+    const float4* q = (const float4*)r;
+    const float4 a = q[0], b = q[1], c4 = q[2], d = q[3];
+    K1Cand c;
+    c.flags = __float_as_uint(a.x); c.hd = a.y; c.pd = a.z; c.ot = a.w;
+    c.density = b.x; c.Li = f3(b.y, b.z, b.w);
+    c.ph = c4.x; c.outLightPdf = c4.y; c.Le = f3(c4.z, c4.w, d.x);
+    c.lightID = __float_as_int(d.y); c.lightUV = make_float2(d.z, d.w);
+    c.uEm = r[16]; c.uWrs = r[17];
+    return c;
+}
+
+// per-pixel state words (K1_STRIDE floats): [0,20) candidate record (+18 = its visibility, written by the march),
+// [20,24) RNG state, [24,36) hd/pd/ot of the 4 distance candidates, [36,44) the reservoir being streamed
+enum { K1_SG = 20, K1_HD = 24, K1_RES = 36 };
+
+// MODE 0: s == 0 (traversal + first candidate), 1: 0 < s < M, 2: s == M (last candidate's finish + p-hat); separate
+// instantiations so that the light-weight middle steps do not carry the registers of the traversal / the p-hat marches
+template <int MODE>
+__global__ void __launch_bounds__(128, MODE == 1 ? 8 : 4) k_initial_step(FrameParams fp, WfInitial wi, int s) {
+    int x, y;
+    const bool inFrame = pixelOf(fp, x, y);
+    const int pixelId = inFrame ? y * fp.W + x : fp.rowBegin * fp.W;
+    const unsigned recBase = (unsigned)(pixelId - fp.rowBegin * fp.W) * K1_STRIDE;
+    float* st = wi.state + recBase;
+    const SamplingOptions& o = fp.initial;
+    const int M = fp.initialM;
+    bool hasTask = false;
+    uint4 ta = make_uint4(0, 0, 0, 0), tb = ta;
+    if (inFrame) {
+        SampleGenerator sg;
+        const Ray ray = primaryRay(fp, x, y);
+        Reservoir finalReservoir = createNewReservoir();
+        float hd = 0.f, pd = 0.f, ot = 0.f;
+        if (MODE == 0) {
+            sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
+            float hds[4] = {0, 0, 0, 0}, pds[4] = {0, 0, 0, 0}, ots[4] = {0, 0, 0, 0};
+            SampleMediumAnalyticGeneric(ray, sg, o.visibilityUseLinearSampler, hds, o.visibilityMipLevel, pds, ots, M);
+            ((float4*)(st + K1_HD))[0] = make_float4(hds[0], hds[1], hds[2], hds[3]);
+            ((float4*)(st + K1_HD))[1] = make_float4(pds[0], pds[1], pds[2], pds[3]);
+            ((float4*)(st + K1_HD))[2] = make_float4(ots[0], ots[1], ots[2], ots[3]);
+            hd = hds[0]; pd = pds[0]; ot = ots[0];
+        } else {
+            const float4 g4 = ((const float4*)(st + K1_SG))[0];
+            sg.s0 = __float_as_uint(g4.x); sg.s1 = __float_as_uint(g4.y); sg.s2 = __float_as_uint(g4.z); sg.s3 = __float_as_uint(g4.w);
+            const float4 r0 = ((const float4*)(st + K1_RES))[0], r1 = ((const float4*)(st + K1_RES))[1];
+            finalReservoir.runningSum = r0.x; finalReservoir.M = r0.y; finalReservoir.depth = r0.z; finalReservoir.p_y = r0.w;
+            finalReservoir.lightUV = make_float2(r1.x, r1.y); finalReservoir.lightID = __float_as_int(r1.z); finalReservoir.sampledPixel = __float_as_int(r1.w);
+            // finish candidate s-1 and stream it through the reservoir
+            const K1Cand c = k1Load(st);
+            const float vis = (c.flags & 8u) ? st[18] : 1.f;
+            const Reservoir outReservoir = k1Finish(c, vis, fp);
+            simpleResampleStep<1>(outReservoir, finalReservoir, sg);
+            if (MODE != 2) { hd = st[K1_HD + s]; pd = st[K1_HD + 4 + s]; ot = st[K1_HD + 8 + s]; }
+        }
+        if (MODE != 2) {
+            // candidate s up to its shadow march (VR/ComputeInitialSample.slang:60-284, bounce 0)
+            K1Cand c;
+            c.flags = 0; c.hd = hd; c.pd = pd; c.ot = ot; c.density = 0.f;
+            c.Li = f3(0.f); c.ph = 0.f; c.outLightPdf = 0.f; c.Le = f3(0.f); c.lightID = 0; c.lightUV = make_float2(0, 0); c.uEm = 0.f; c.uWrs = 0.f;
+            const bool valid = c.hd != kRayTMax;
+            const MediumInteraction mi = makeMI(ray.at(c.hd), -ray.dir, valid);
+            if (valid) { c.flags |= 1u; c.density = DensityWorldSpace(mi.p, 0); }
+            const bool hitEmpty = valid && c.density == 0.f;
+            if (hitEmpty) c.flags |= 2u;
+            else if (valid) {
+                c.lightID = -1;
+                if (c_scene.vol.hasEmission && c.density > 0.f) c.Le = EmissionWorldSpace(mi.p);
+                SceneLightSample ls;
+                const bool lvalid = sampleSceneLights(mi.p, o.useEnvironmentLights, o.useAnalyticLights, o.useEmissiveLights, sg, ls, c.lightID, c.lightUV);
+                c.outLightPdf = lvalid ? ls.pdfArea : 0.f;
+                if (lvalid) {
+                    c.flags |= 4u;
+                    c.Li = ls.Li;
+                    c.ph = mi.phaseFunction(mi.wo, ls.dir);
+                    if (o.lightSamples != 0) {
+                        c.flags |= 8u; hasTask = true;
+                        const Ray sh = makeRay(mi.p, ls.rayDir, 0, ls.rayDistance);
+                        ta = wfLightTaskOrigin(sh); tb = wfLightTask(sh, recBase + 18);
+                    }
+                }
+                c.uEm = sampleNext1D(sg);
+            } else c.Le = envEval(ray.dir);
+            k1Store(st, c);
+            ((float4*)(st + K1_SG))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
+            ((float4*)(st + K1_RES))[0] = make_float4(finalReservoir.runningSum, finalReservoir.M, finalReservoir.depth, finalReservoir.p_y);
+            ((float4*)(st + K1_RES))[1] = make_float4(finalReservoir.lightUV.x, finalReservoir.lightUV.y, __int_as_float(finalReservoir.lightID), __int_as_float(finalReservoir.sampledPixel));
+        } else {
+            // VR/TraceRays.cs.slang:176-183: p-hat of the streamed reservoir under the spatial options (ray-marched: no draws)
+            ExtraProvider prov; prov.global = nullptr; prov.local = nullptr;
+            const float p_hat = evaluate_P_hat<1>(ray, sg, prov, fp.spatial, finalReservoir, false);
+            if (finalReservoir.runningSum > 0.f) {
+                finalReservoir.runningSum *= finalReservoir.p_y == 0.f ? 0.f : p_hat / finalReservoir.p_y;
+                finalReservoir.p_y = p_hat;
+            }
+            storeReservoir(fp.cur, pixelId, finalReservoir);
+        }
+    }
+    if (MODE != 2) wfEmit(wi.light, hasTask, ta, tb);
+}
+
 // ------------------------------------------------------------------------------------------------ K2 wavefront
 // VR/TemporalReuse.cs.slang:80-377 for B == 1 and ray-marched p-hat: the kernel is cut at its two p-hat evaluations
 // (E1: the history sample on the current ray = resampleNeighbor; E0: the current sample on the previous-frame ray = the
@@ -459,6 +636,12 @@ cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind
     return cudaGetLastError();
 }
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
+cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st) {
+    if (s == 0) k_initial_step<0><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
+    else if (s < fp.initialM) k_initial_step<1><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
+    else k_initial_step<2><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
+    return cudaGetLastError();
+}
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchInitialFinish(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_initial_finish<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }

@@ -16,7 +16,7 @@ from . import _capi as capi
 kOutputChannels = {"accumulated_color": "RGBA32Float", "mvec": "RG32Float"}   # VR/VolumetricReSTIR.cpp:39-43
 
 TOP_LEVEL_KEYS = ("mOutputMotionVec", "mFreezeFrame", "volumeDensityScaleExtraControl", "volumeAlbedoExtraControl",
-                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mWavefrontInitial")
+                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mInitialMode")
 # accepted for script compatibility, camera / env-light animation and UI live outside the hot path
 IGNORED_KEYS = ("mCameraMoveScale", "mCameraForwardScale", "mCameraFrameInterval", "mCameraPauseInterval",
                 "mCameraShakeTotalRounds", "mCameraShakeRoundsBeforePause", "mCameraAnimationMode", "mAnimateEnvLight",
@@ -73,6 +73,11 @@ class VolumetricReSTIR:
         self._frame = None
         self._keep = []
         self._apply_dict(dict_)
+
+    def wavefront_counters(self):
+        out = (C.c_uint32 * 16)()
+        capi.check(self._lib.vrestir_debug_wavefront_counters(self._h, out))
+        return list(out)
 
     # RenderPassLibrary registers `create(RenderContext*, const Dictionary&)` (VR/VolumetricReSTIR.cpp:61-70)
     @classmethod
