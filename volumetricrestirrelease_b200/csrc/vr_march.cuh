@@ -47,33 +47,20 @@ VRD float fastFloor(float x, int& i) {
 VRD float launder(float x) { asm volatile("" : "+f"(x)); return x; }
 VRD float byteToFloat(uint32_t w, int sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + sel) ) - 8388608.f; }
 
-// FAST: the slot is a single-channel UNORM8 pool with the quad repack and the sampler is trilinear (every reuse mip)
-template <int NT, bool FAST>
-struct Marcher {
+// ---- traversal shared by all marchers: the hierarchical DDA of VolumeTrackingGVDB (VR/VolumeUtils.slang:171-282) as a
+// per-lane state machine.  The adapter-specific parts (in-brick work, results) live in the derived marchers.
+struct MarchTrav {
     // medium-space ray
     float3 pos, dir, invDir;
     int3 stepI;                    // +1 / -1 per axis (dir >= 0 ? 1 : -1)
     // DDA state at the current level
     float3 tDel, tSide; int3 p; float tx, ty; int mask;   // mask bits 0..2 = x, y, z
-    // adapter
-    float tNear, tFar, tStep;
-    float thrEff[NT], out[NT];     // thrEff = min(tFar, thr)
-    float Tr;
-    unsigned pending, todo, outIdx;
-    bool initialized;
-    // traversal: level 1 node in registers, level 2 is the root (constants of the launch)
+    float tNear, tFar;
+    // level 1 node in registers, level 2 is the root (constants of the launch)
     int iter;
     uint32_t link1; float3 vmin1; float tMax1;
-    // in-brick sampling
-    float3 pb; float t; uint32_t brick; int biter;
+    uint32_t brick;                // leaf node id while MARCH_ENTER is pending, brick id afterwards
     int phase;
-
-    VRD void writeOut(float* results) {
-#pragma unroll
-        for (int k = 0; k < NT; k++)
-            if ((todo >> k) & 1u) results[outIdx + k] = initialized ? expf(((pending >> k) & 1u) ? Tr : out[k]) : 1.f;
-        phase = MARCH_IDLE;
-    }
 
     VRD void prepare(float3 vmin, float vdel, float ivdel) {   // HDDAState::Prepare
         tDel = make_float3(fabsf(vdel * invDir.x), fabsf(vdel * invDir.y), fabsf(vdel * invDir.z));
@@ -96,50 +83,28 @@ struct Marcher {
         if (mask & 4) { tSide.z += tDel.z; p.z += stepI.z; }
         tx = ty + 0.01f;
     }
-    VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, const DSlot& g) {
-        Ray rW;
-        rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
-        outIdx = b.w;
-        rW.tMin = 0.f;
-        float thr[NT];
-        if (kind.originMode == 0) {
-            rW.origin = make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
-            thr[0] = __uint_as_float(a.w);
-#pragma unroll
-            for (int k = 1; k < NT; k++) thr[k] = 0.f;
-            todo = 1u;
-            rW.tMax = thr[0];
-        } else {
-            rW.origin = kind.originMode == 1 ? c_scene.camPos : c_scene.prevPos;
-            const float v[3] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)};
-            todo = a.w & ((1u << NT) - 1u);
-            float mx = 0.f;
-#pragma unroll
-            for (int k = 0; k < NT; k++) { thr[k] = k < 3 ? v[k] : 0.f; if ((todo >> k) & 1u) mx = fmaxf(mx, thr[k]); }
-            rW.tMax = mx;
-        }
-        pending = todo;
-#pragma unroll
-        for (int k = 0; k < NT; k++) out[k] = 0.f;
-        Tr = 0.f;
-        const int mip = kind.mip;
-        int eff = mip >= VRESTIR_PREV_DENSITY_GRID_OFFSET ? mip - VRESTIR_PREV_DENSITY_GRID_OFFSET : mip;
-        eff = eff >= VRESTIR_NUM_MAX_MIPS ? eff - VRESTIR_NUM_MAX_MIPS : eff;
-        tStep = c_scene.vol.tStep * c_scene.vol.volumeWorldScaling * kind.tStepScale * (eff + 1);
-        // WorldToMedium + IntersectVolumeBound (VR/VolumeBase.slang:103-175)
+    // WorldToMedium + IntersectVolumeBound + the prologue of VolumeTrackingGVDB (VR/VolumeBase.slang:103-175,
+    // VR/VolumeUtils.slang:183-225).  Returns false when the ray misses the box.
+    VRD bool beginTraversal(const Ray& rW, const DSlot& g, bool vertexCenter) {
         Ray ray; ray.origin = mulPoint(rW.origin, g.w2m); ray.dir = mulVec(rW.dir, g.w2m); ray.tMin = rW.tMin; ray.tMax = rW.tMax;
-        initialized = IntersectP(v3(g.bmin), v3(g.bmax), ray, tNear, tFar);
-        if (!initialized) { phase = MARCH_DONE; return; }
-#pragma unroll
-        for (int k = 0; k < NT; k++) thrEff[k] = fminf(tFar, thr[k]);
+        float3 mn = v3(g.bmin), mx = v3(g.bmax);
+        if (vertexCenter) { ray.origin = ray.origin - f3(0.5f); mn = mn - f3(0.5f); mx = mx - f3(0.5f); }
+        if (!IntersectP(mn, mx, ray, tNear, tFar)) return false;
         pos = ray.origin; dir = ray.dir;
         invDir = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
         stepI = make_int3(dir.x >= 0 ? 1 : -1, dir.y >= 0 ? 1 : -1, dir.z >= 0 ? 1 : -1);
         tx = tNear + 0.01f; ty = 0.f; mask = 0;
         iter = 0;
         const float3 rootPos = make_float3((float)g.rootPos[0], (float)g.rootPos[1], (float)g.rootPos[2]);
-        if (g.top_lev == 2) { link1 = ID_UNDEFL; vmin1 = f3(0.f); tMax1 = 0.f; prepare(rootPos, g.vdel[2], g.ivdel[2]); phase = MARCH_ROOT; }
+        const bool top2 = g.top_lev == 2;
+        if (top2) { link1 = ID_UNDEFL; vmin1 = f3(0.f); tMax1 = 0.f; prepare(rootPos, g.vdel[2], g.ivdel[2]); phase = MARCH_ROOT; }
         else { link1 = g.rootLink; vmin1 = rootPos; tMax1 = tFar; prepare(rootPos, g.vdel[1], g.ivdel[1]); phase = MARCH_TRAV; }
+        if (vertexCenter) {   // VR/VolumeUtils.slang:216-225: step until the start cell is inside the node
+            const int r = top2 ? g.res[2] : g.res[1];
+            int it = 0;
+            while (it++ < 3 && (p.x < 0 || p.y < 0 || p.z < 0 || p.x > r || p.y > r || p.z > r)) { next(); step(); }
+        }
+        return true;
     }
 
     // ---- slow events (group 3) -------------------------------------------------------------------------------------
@@ -193,6 +158,61 @@ struct Marcher {
         if (child == ID_UNDEFL) { step(); if (tx > tMax1) phase = MARCH_ASCEND; return; }
         brick = child;   // leaf node id until enterBrick() replaces it with the brick id
         phase = MARCH_ENTER;
+    }
+};
+
+// ---- ray-marched transmittance (MediumTrRayMarchingAdapter) with up to NT depth thresholds.
+// FAST: the slot is a single-channel UNORM8 pool with the quad repack and the sampler is trilinear (every reuse mip)
+template <int NT, bool FAST>
+struct RayMarcher : MarchTrav {
+    float tStep;
+    float thrEff[NT], out[NT];     // thrEff = min(tFar, thr)
+    float Tr;
+    unsigned pending, todo, outIdx;
+    bool initialized;
+    float3 pb; float t; int biter;   // in-brick sampling
+
+    VRD void writeOut(float* results) {
+#pragma unroll
+        for (int k = 0; k < NT; k++)
+            if ((todo >> k) & 1u) results[outIdx + k] = initialized ? expf(((pending >> k) & 1u) ? Tr : out[k]) : 1.f;
+        phase = MARCH_IDLE;
+    }
+
+    VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, const DSlot& g) {
+        Ray rW;
+        rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
+        outIdx = b.w;
+        rW.tMin = 0.f;
+        float thr[NT];
+        if (kind.originMode == 0) {
+            rW.origin = make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+            thr[0] = __uint_as_float(a.w);
+#pragma unroll
+            for (int k = 1; k < NT; k++) thr[k] = 0.f;
+            todo = 1u;
+            rW.tMax = thr[0];
+        } else {
+            rW.origin = kind.originMode == 1 ? c_scene.camPos : c_scene.prevPos;
+            const float v[3] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)};
+            todo = a.w & ((1u << NT) - 1u);
+            float mx = 0.f;
+#pragma unroll
+            for (int k = 0; k < NT; k++) { thr[k] = k < 3 ? v[k] : 0.f; if ((todo >> k) & 1u) mx = fmaxf(mx, thr[k]); }
+            rW.tMax = mx;
+        }
+        pending = todo;
+#pragma unroll
+        for (int k = 0; k < NT; k++) out[k] = 0.f;
+        Tr = 0.f;
+        const int mip = kind.mip;
+        int eff = mip >= VRESTIR_PREV_DENSITY_GRID_OFFSET ? mip - VRESTIR_PREV_DENSITY_GRID_OFFSET : mip;
+        eff = eff >= VRESTIR_NUM_MAX_MIPS ? eff - VRESTIR_NUM_MAX_MIPS : eff;
+        tStep = c_scene.vol.tStep * c_scene.vol.volumeWorldScaling * kind.tStepScale * (eff + 1);
+        initialized = beginTraversal(rW, g, false);
+        if (!initialized) { phase = MARCH_DONE; return; }
+#pragma unroll
+        for (int k = 0; k < NT; k++) thrEff[k] = fminf(tFar, thr[k]);
     }
 
     // ---- in-brick sampling (group 2) --------------------------------------------------------------------------------
@@ -248,14 +268,87 @@ struct Marcher {
     }
 };
 
+// ---- exact transmittance of the trilinear interpolant (MediumTrAnalyticAdapter with the linear sampler,
+// VR/VolumeTrackingAdapterGVDB.slang:20-136; vertex-centred traversal): the in-brick phase walks the 8^3 voxel cells of the
+// brick with a leaf DDA and integrates the cubic sigma(t) of every cell in closed form.  One explicit-origin task, one result.
+struct AnalyticMarcher : MarchTrav {
+    float Tr; unsigned outIdx;
+    float3 lSide; int3 lp; float ltx, lty;   // leaf DDA (HDDAState leaf = dda; leaf.PrepareLeaf(vmin_leaf))
+    float3 vminLeaf;
+    float t; int biter;
+
+    VRD void writeOut(float* results) { results[outIdx] = expf(Tr); phase = MARCH_IDLE; }
+
+    VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, const DSlot& g) {
+        Ray rW;
+        rW.origin = make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+        rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
+        rW.tMin = 0.f; rW.tMax = __uint_as_float(a.w);
+        outIdx = b.w;
+        Tr = 0.f;
+        if (!beginTraversal(rW, g, true)) phase = MARCH_DONE;
+    }
+
+    VRD void enterBrick(const DSlot& g) {
+        const int4 leaf = __ldg((const int4*)&g.nodes[0][brick]);
+        brick = (uint32_t)leaf.w;
+        vminLeaf = nodePos(leaf);
+        t = tx - 0.01f;
+        // HDDAState::PrepareLeaf on a copy of the level-1 state
+        const float3 tDelL = make_float3(fabsf(invDir.x), fabsf(invDir.y), fabsf(invDir.z));
+        const float3 pFlt = pos + tx * dir - vminLeaf;
+        const float3 fl = make_float3(floorf(pFlt.x), floorf(pFlt.y), floorf(pFlt.z));
+        const float3 sgn = make_float3(dir.x >= 0 ? 1.f : -1.f, dir.y >= 0 ? 1.f : -1.f, dir.z >= 0 ? 1.f : -1.f);
+        lSide = ((fl - pFlt + f3(0.5f)) * sgn + f3(0.5f)) * tDelL + f3(tx);
+        lp = make_int3((int)fl.x, (int)fl.y, (int)fl.z);
+        ltx = tx; lty = ty;
+        biter = 0;
+        phase = MARCH_BRICK;
+    }
+
+    // one voxel cell of the brick
+    VRD void sampleStep(const DSlot& g, bool) {
+        if (!(biter < MAX_BRICK_STEPS && inRange(lp, 8))) { phase = MARCH_EXIT; return; }
+        // leaf.Next()
+        const bool mx = (lSide.x < lSide.y) & (lSide.x <= lSide.z);
+        const bool my = (lSide.y < lSide.z) & (lSide.y <= lSide.x);
+        const bool mz = (lSide.z < lSide.x) & (lSide.z <= lSide.y);
+        lty = mx ? lSide.x : (my ? lSide.y : lSide.z);
+        const float maxDeltaT = lty - t;
+        float v[8];
+        if (g.format == VRESTIR_ATLAS_F32 && g.channels == 1) {
+            // corners lp + {0,1}^3 lie inside the 10^3 apron block for every cell of the brick: unchecked loads
+            const float* a = (const float*)g.atlas + (brick * (unsigned)VRESTIR_BRICK_VOXELS + (unsigned)(((lp.z + 1) * 10 + (lp.y + 1)) * 10 + (lp.x + 1)));
+            const float s1 = g.compress_scale, s2 = c_scene.vol.densityScaleFactorByScaling;
+            v[0] = __ldg(a) * s1 * s2; v[1] = __ldg(a + 1) * s1 * s2; v[2] = __ldg(a + 10) * s1 * s2; v[3] = __ldg(a + 11) * s1 * s2;
+            v[4] = __ldg(a + 100) * s1 * s2; v[5] = __ldg(a + 101) * s1 * s2; v[6] = __ldg(a + 110) * s1 * s2; v[7] = __ldg(a + 111) * s1 * s2;
+        } else FetchEightVoxels(g, brick, lp, v);
+        const float3 p0 = pos + ltx * dir - (make_float3((float)lp.x, (float)lp.y, (float)lp.z) + vminLeaf);
+        float c3, c2, c1, c0;
+        trilinearCubic(v, c_scene.vol.sigma_t, dir, p0, c3, c2, c1, c0);
+        const float t_dist = fminf(tFar - t, maxDeltaT);
+        const float t2 = t_dist * t_dist, t3 = t2 * t_dist, t4 = t2 * t2;
+        Tr += -(c3 * t4 / 4 + c2 * t3 / 3 + c1 * t2 / 2 + c0 * t_dist);
+        // past tFar, or expf(Tr) already underflows to exactly 0 and can only stay there
+        if (t + maxDeltaT >= tFar || Tr < -110.f) { phase = MARCH_DONE; return; }
+        t += maxDeltaT;
+        // leaf.Step()
+        ltx = lty;
+        if (mx) { lSide.x += fabsf(invDir.x); lp.x += stepI.x; }
+        if (my) { lSide.y += fabsf(invDir.y); lp.y += stepI.y; }
+        if (mz) { lSide.z += fabsf(invDir.z); lp.z += stepI.z; }
+        biter++;
+    }
+};
+
 // Persistent-lane pool over one task stream.  tasks: 2 x uint4 per task; total: tasks in the stream; cursor: next unclaimed.
-template <int NT, bool FAST>
+template <class M>
 __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
     const bool linear = kind.linear != 0;
-    Marcher<NT, FAST> m;
+    M m;
     m.phase = MARCH_IDLE;
     bool drained = false;
     for (;;) {

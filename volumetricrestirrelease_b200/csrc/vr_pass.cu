@@ -97,7 +97,7 @@ struct vrestir_pass {
     int mInitialMode = 1;   // K1: 0 per-pixel kernel, 1 lock-step wavefront (default), 2 per-pixel + p-hat re-evaluation through the march engine (measured slower)
     uint4* wfCamTasks = nullptr; uint4* wfLightTasks = nullptr; float* wfResults = nullptr; unsigned* wfCounters = nullptr;
     size_t wfPixels = 0;
-    int marchBlocks1 = 0, marchBlocks3 = 0;
+    int marchBlocks1 = 0, marchBlocks3 = 0, analyticBlocks = 0;
     float* wfInitialState = nullptr; size_t wfInitialPixels = 0;   // lock-step wavefront K1
 };
 
@@ -513,7 +513,18 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
             fp.cur = resView(p, p->finalPhys); fp.extCur = p->ext[p->finalPhys];
             if (p->mFreezeFrame) fp.frameCount = p->mFrameCount - 1;
             if (!out_color) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "out_color is null");
-            CK(launchFinal(fp, st)); p->launches++;
+            if (p->mUseWavefront && m.mMaxBounces == 1 && !m.mUseReference && !m.mVisualizeTotalTransmittance &&
+                m.mFinalVisibilityTrackingMethod == VRESTIR_ANALYTIC_TRACKING && m.mFinalLightTrackingMethod == VRESTIR_ANALYTIC_TRACKING) {
+                rc = ensureWavefront(p); if (rc) return rc;
+                if (!p->analyticBlocks) { int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device); p->analyticBlocks = sms * analyticBlocksPerSM(); }
+                WfStream s; s.tasks = p->wfLightTasks; s.count = p->wfCounters; s.cursor = p->wfCounters + 1; s.capacity = (unsigned)(2 * p->wfPixels);
+                CK(cudaMemsetAsync(p->wfCounters, 0, 8, st));
+                CK(launchFinalGather(fp, s, p->wfResults, st));
+                const MarchKind k = {0, 1, m.mFinalTStepScale, 0};
+                CK(launchMarchAnalytic(s, p->wfResults, k, p->scene.slots[0], p->analyticBlocks, st));
+                CK(launchFinalCombine(fp, p->wfResults, st));
+                p->launches += 3;
+            } else { CK(launchFinal(fp, st)); p->launches++; }
             recordEv(p, 6, st);
             break;
         case 6: {   // VR/VolumetricReSTIR.cpp:765-772 (+ :636 feature history, as a swap)

@@ -25,7 +25,13 @@ namespace vrd {
 // ------------------------------------------------------------------------------------------------ march kernels
 template <int NT, bool FAST>
 __global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
-    marchPool<NT, FAST>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
+    marchPool<RayMarcher<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
+}
+#ifndef VR_ANALYTIC_MINB
+#define VR_ANALYTIC_MINB 6
+#endif
+__global__ void __launch_bounds__(128, VR_ANALYTIC_MINB) k_march_analytic(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
+    marchPool<AnalyticMarcher>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 gather
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
 // ------------------------------------------------------------------------------------------------ K3 combine
 // evaluate_F_ / evaluate_P_hat (VR/ReSTIRHelper.slang:91-423, B == 1) with the density at the sample point and the two
 // transmittances supplied by the caller (gather kernel / march engine)
-VRD float wfPHatV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, float density, float visibility, float lightTr) {
+VRD float3 wfFV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, bool noReuse, float density, float visibility, float lightTr) {
     const vrestir_volume_desc& vd = c_scene.vol;
     const bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
     Ray ray = makeRay(origin, dir, 0.f, tap.depth);
@@ -165,8 +171,9 @@ VRD float wfPHatV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFr
     const float3 p_World = ray.at(ray.tMax);
     const MediumInteraction mi = makeMI(p_World, -ray.dir, true);
     const float3 sigA = v3(vd.sigma_a), sigS = v3(vd.sigma_s);
-    if (density == 0.f) return luminance(f3(0.f));
-    const float3 sigma_s = isBackgroundSample ? f3(1.f) : (isSelfEmission ? sigA : sigS);
+    if (density == 0.f) return f3(0.f);
+    float3 sigma_s = isBackgroundSample ? f3(1.f) : (isSelfEmission ? sigA : sigS);
+    if (noReuse && !isBackgroundSample) sigma_s = sigma_s / vd.sigma_t;
     F = F * (visibility * density * sigma_s);
     if (any_gt0(F)) {
         if (isBackgroundSample) F = F * envEval(ray.dir, isLastFrame);
@@ -178,7 +185,10 @@ VRD float wfPHatV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFr
             F = F * (Tr * Ld);
         }
     }
-    return luminance(F);
+    return F;
+}
+VRD float wfPHatV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, float density, float visibility, float lightTr) {
+    return luminance(wfFV(tap, origin, dir, isLastFrame, false, density, visibility, lightTr));
 }
 VRD float wfPHat(const Reservoir& tap, float3 origin, float3 dir, const float* blk, int i, int j) {
     return wfPHatV(tap, origin, dir, false, blk[WF_D + i * 4 + j], blk[WF_C + j * 3 + (i - (i > j ? 1 : 0))], blk[WF_L + i * 4 + j]);
@@ -601,6 +611,58 @@ __global__ void __launch_bounds__(128) k_temporal_combine(FrameParams fp, WfBufs
     storeReservoir(fp.cur, pixelId, output);
 }
 
+// ------------------------------------------------------------------------------------------------ K5 wavefront
+// VR/FinalShading.cs.slang:71-141 with analytic tracking for both transmittances (the default): the pixel's reservoir is
+// shaded with the exact transmittance of the trilinear mip-0 interpolant along the camera ray and the light ray.
+// Block slots: 0 density, 1 camera Tr, 2 light Tr.
+__global__ void __launch_bounds__(128) k_final_gather(FrameParams fp, WfStream stream, float* results) {
+    int x, y;
+    const bool inFrame = pixelOf(fp, x, y);
+    const int pixelId = inFrame ? y * fp.W + x : fp.rowBegin * fp.W;
+    const unsigned out = (unsigned)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
+    bool hasCam = false, hasLight = false;
+    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, la = ca, lb = ca;
+    if (inFrame) {
+        const Reservoir cur = loadReservoir(fp.cur, pixelId, 1);
+        if (cur.runningSum > 0.f) {
+            const bool noReuse = fp.noReuse != 0;
+            const bool bg = cur.depth == kRayTMax;
+            const Ray r = makeRay(c_scene.camPos, tapRayDir(fp, x, y), 0.f, cur.depth);
+            const float3 pW = r.at(r.tMax);
+            const float density = (bg || noReuse) ? 1.f : DensityWorldSpace(pW, 0);
+            results[out] = density;
+            if (density != 0.f) {
+                if (!noReuse) { hasCam = true; ca = wfLightTaskOrigin(r); cb = wfLightTask(r, out + 1); }
+                if (!bg && cur.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
+                    Ray sh; float3 Ld;
+                    if (lightRayAndLd(makeMI(pW, -r.dir, true), cur.lightID, cur.lightUV, false, sh, Ld)) { hasLight = true; la = wfLightTaskOrigin(sh); lb = wfLightTask(sh, out + 2); }
+                }
+            }
+        }
+    }
+    wfEmit(stream, hasCam, ca, cb);
+    wfEmit(stream, hasLight, la, lb);
+}
+
+__global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    const int pixelId = y * fp.W + x;
+    const float* blk = results + (size_t)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
+    float3 outputColor = f3(0.f);
+    const Reservoir cur = loadReservoir(fp.cur, pixelId, 1);
+    if (cur.runningSum > 0.f) {
+        const bool noReuse = fp.noReuse != 0;
+        float3 col = wfFV(cur, c_scene.camPos, tapRayDir(fp, x, y), false, noReuse, blk[0], noReuse ? 1.f : blk[1], blk[2]);
+        const float Wt = cur.p_y == 0.0f ? 1.f : cur.runningSum / (cur.p_y * cur.M);
+        col = col * Wt;
+        outputColor = outputColor + col;
+    }
+    float4 o = make_float4(outputColor.x, outputColor.y, outputColor.z, 1.f);
+    if (isnan(o.x) || isinf(o.x) || isnan(o.y) || isinf(o.y) || isnan(o.z) || isinf(o.z)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+    fp.outColor[pixelId] = o;
+}
+
 // ------------------------------------------------------------------------------------------------ K1 finish
 // VR/TraceRays.cs.slang:176-183: p-hat of the pixel's own reservoir on its own ray under the spatial options
 __global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfBufs wf) {
@@ -636,6 +698,10 @@ cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind
     return cudaGetLastError();
 }
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
+int analyticBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march_analytic, 128, 0); return n > 0 ? n : 1; }
+cudaError_t launchMarchAnalytic(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int blocks, cudaStream_t st) { k_march_analytic<<<blocks, 128, 0, st>>>(s, results, kind, grid); return cudaGetLastError(); }
+cudaError_t launchFinalGather(const FrameParams& fp, const WfStream& s, float* results, cudaStream_t st) { k_final_gather<<<gridForWf(fp), 128, 0, st>>>(fp, s, results); return cudaGetLastError(); }
+cudaError_t launchFinalCombine(const FrameParams& fp, const float* results, cudaStream_t st) { k_final_combine<<<gridForWf(fp), 128, 0, st>>>(fp, results); return cudaGetLastError(); }
 cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st) {
     if (s == 0) k_initial_step<0><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
     else if (s < fp.initialM) k_initial_step<1><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
