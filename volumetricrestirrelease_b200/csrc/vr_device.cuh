@@ -1340,8 +1340,24 @@ VRD void resampleNeighbor(Reservoir& tap, const Ray& ray, SampleGenerator& sg, c
 }
 
 // ------------------------------------------------------------------------------------------------ march-task streams
-// Append one task per lane with `has` to a stream; every lane of the warp must call (one atomic per warp).
-VRD void wfEmit(const WfStream& s, bool has, uint4 a, uint4 b) {
+// Explicit-origin tasks are PREPARED by the emitting kernel (where all 32 lanes are busy): the ray is already in the index
+// space of the mip it will be marched through and clipped against the volume box (WorldToMedium + IntersectVolumeBound,
+// VR/VolumeBase.slang:103-175); rays that miss the box get their result (transmittance 1) written at once and never
+// become a task.  Layout, 3 x uint4: (pos.xyz, tNear) (dir.xyz, tFar) (result index, 0, 0, 0).
+struct PreparedRay { float3 pos, dir; float tNear, tFar; };
+VRD bool wfPrepare(const Ray& rW, int mip, bool vertexCenter, PreparedRay& o) {
+    const DSlot& g = c_scene.slots[mip];
+    Ray ray; ray.origin = mulPoint(rW.origin, g.w2m); ray.dir = mulVec(rW.dir, g.w2m); ray.tMin = rW.tMin; ray.tMax = rW.tMax;
+    float3 mn = v3(g.bmin), mx = v3(g.bmax);
+    if (vertexCenter) { ray.origin = ray.origin - f3(0.5f); mn = mn - f3(0.5f); mx = mx - f3(0.5f); }
+    o.pos = ray.origin; o.dir = ray.dir;
+    return IntersectP(mn, mx, ray, o.tNear, o.tFar);
+}
+// Append one prepared task per lane with `want` to a stream; every lane of the warp must call (one atomic per warp).
+VRD void wfEmitRay(const WfStream& s, bool want, const Ray& rW, int mip, bool vertexCenter, float* results, unsigned out) {
+    PreparedRay pr;
+    bool has = false;
+    if (want) { has = wfPrepare(rW, mip, vertexCenter, pr); if (!has) results[out] = 1.f; }
     const unsigned bal = __ballot_sync(0xffffffffu, has);
     if (!bal) return;
     const int lane = threadIdx.x & 31;
@@ -1350,14 +1366,13 @@ VRD void wfEmit(const WfStream& s, bool has, uint4 a, uint4 b) {
     base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
     if (has) {
         const unsigned pos = base + __popc(bal & ((1u << lane) - 1u));
-        if (pos < s.capacity) { s.tasks[2 * (size_t)pos] = a; s.tasks[2 * (size_t)pos + 1] = b; }
+        if (pos < s.capacity) {
+            uint4* q = s.tasks + 3 * (size_t)pos;
+            q[0] = make_uint4(__float_as_uint(pr.pos.x), __float_as_uint(pr.pos.y), __float_as_uint(pr.pos.z), __float_as_uint(pr.tNear));
+            q[1] = make_uint4(__float_as_uint(pr.dir.x), __float_as_uint(pr.dir.y), __float_as_uint(pr.dir.z), __float_as_uint(pr.tFar));
+            q[2] = make_uint4(out, 0u, 0u, 0u);
+        }
     }
-}
-VRD uint4 wfLightTask(const Ray& sh, unsigned out) {
-    return make_uint4(__float_as_uint(sh.dir.x), __float_as_uint(sh.dir.y), __float_as_uint(sh.dir.z), out);
-}
-VRD uint4 wfLightTaskOrigin(const Ray& sh) {
-    return make_uint4(__float_as_uint(sh.origin.x), __float_as_uint(sh.origin.y), __float_as_uint(sh.origin.z), __float_as_uint(sh.tMax));
 }
 
 // ------------------------------------------------------------------------------------------------ pixel mapping

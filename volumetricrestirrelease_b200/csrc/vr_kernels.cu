@@ -194,83 +194,51 @@ __device__ float3 IntegrateByVolumePathTracing(Ray ray, SampleGenerator& sg, con
     return L;
 }
 
-template <int B, bool DEFER>
-__global__ void __launch_bounds__(128, VR_MINB) k_initial(FrameParams fp, WfBufs wf) {
+template <int B>
+__global__ void __launch_bounds__(128, VR_MINB) k_initial(FrameParams fp) {
     int x, y;
-    const bool inFrame = pixelOf(fp, x, y);
-    constexpr bool defer = B == 1 && DEFER;   // every lane has to reach the task emission below
-    if (!defer && !inFrame) return;
-    bool hasCam = false, hasLight = false;
-    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, la = ca, lb = ca;
-    if (inFrame) {
-        SampleGenerator sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
-        const int reservoirId = y * fp.W + x;
-        Ray ray = primaryRay(fp, x, y);
-        if (fp.useReference) {
-            float3 avgL = f3(0.f);
-            for (int r = 0; r < fp.baselineSpp; r++) avgL = avgL + IntegrateByVolumePathTracing(ray, sg, fp);
-            float3 o = avgL / (float)fp.baselineSpp;
-            fp.refColor[reservoirId] = make_float4(o.x, o.y, o.z, 1.f);
-            return;
-        }
-        float3 finalExtra[B > 1 ? B - 1 : 1];
-        float3 extra[B > 1 ? B - 1 : 1];
+    if (!pixelOf(fp, x, y)) return;
+    SampleGenerator sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
+    const int reservoirId = y * fp.W + x;
+    Ray ray = primaryRay(fp, x, y);
+    if (fp.useReference) {
+        float3 avgL = f3(0.f);
+        for (int r = 0; r < fp.baselineSpp; r++) avgL = avgL + IntegrateByVolumePathTracing(ray, sg, fp);
+        float3 o = avgL / (float)fp.baselineSpp;
+        fp.refColor[reservoirId] = make_float4(o.x, o.y, o.z, 1.f);
+        return;
+    }
+    float3 finalExtra[B > 1 ? B - 1 : 1];
+    float3 extra[B > 1 ? B - 1 : 1];
 #pragma unroll
-        for (int i = 0; i < (B > 1 ? B - 1 : 1); i++) { finalExtra[i] = f3(0.f); extra[i] = f3(0.f); }
-        Reservoir finalReservoir = createNewReservoir();
-        const int rounds = (fp.initialM + 3) / 4;
-        for (int roundId = 0; roundId < rounds; roundId++) {
-            float hd[4] = {0, 0, 0, 0}, pd[4] = {0, 0, 0, 0}, ot[4] = {0, 0, 0, 0};
-            const int roundSamples = roundId == rounds - 1 ? (fp.initialM - 4 * (rounds - 1)) : 4;
-            if (!fp.noReuse) SampleMediumAnalyticGeneric(ray, sg, fp.initial.visibilityUseLinearSampler, hd, fp.initial.visibilityMipLevel, pd, ot, roundSamples);
-            for (int s = 0; s < roundSamples; s++) {
-                Reservoir outReservoir = ComputeInitialSample<B>(ray, hd[s], pd[s], ot[s], sg, fp, extra);
-                bool isSelected = simpleResampleStep<B>(outReservoir, finalReservoir, sg);
-                if (B > 1 && isSelected) {
-                    const int mib = decodeMaxIndirectBounces<B>(finalReservoir.sampledPixel);
-                    for (int b = 0; b < mib && b < B - 1; b++) finalExtra[b] = extra[b];
-                }
-            }
-        }
-        if (defer) {
-            // VR/TraceRays.cs.slang:176-183 split off: the reservoir is stored as is, the p-hat of its sample on this pixel's
-            // own ray (spatial options) becomes march tasks and k_initial_finish applies `runningSum *= p_hat / p_y`.
-            storeReservoir(fp.cur, reservoirId, finalReservoir);
-            if (finalReservoir.runningSum > 0.f) {
-                const unsigned blkBase = (unsigned)(reservoirId - fp.rowBegin * fp.W) * WF_BLOCK;
-                const bool bg = finalReservoir.depth == kRayTMax;
-                const Ray r = makeRay(ray.origin, ray.dir, 0.f, finalReservoir.depth);
-                const float3 pW = r.at(r.tMax);
-                const float density = bg ? 1.f : DensityWorldSpace(pW, 0);
-                wf.results[blkBase + WF_D] = density;
-                if (density != 0.f) {
-                    hasCam = true;
-                    ca = make_uint4(__float_as_uint(finalReservoir.depth), 0u, 0u, 1u);
-                    cb = wfLightTask(r, blkBase + WF_C);
-                    if (!bg && finalReservoir.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
-                        Ray sh; float3 Ld;
-                        if (lightRayAndLd(makeMI(pW, -r.dir, true), finalReservoir.lightID, finalReservoir.lightUV, false, sh, Ld)) {
-                            hasLight = true; la = wfLightTaskOrigin(sh); lb = wfLightTask(sh, blkBase + WF_L);
-                        }
-                    }
-                }
-            }
-        } else {
-            ExtraProvider prov; prov.global = nullptr; prov.local = finalExtra;
-            Reservoir tapForEval = finalReservoir; tapForEval.extraBounceStartId = 0;
-            float p_hat = evaluate_P_hat<B>(ray, sg, prov, fp.spatial, tapForEval, false);
-            if (finalReservoir.runningSum > 0.f) {
-                finalReservoir.runningSum *= finalReservoir.p_y == 0.f ? 0.f : p_hat / finalReservoir.p_y;
-                finalReservoir.p_y = p_hat;
-            }
-            storeReservoir(fp.cur, reservoirId, finalReservoir);
-            if (B > 1) {
+    for (int i = 0; i < (B > 1 ? B - 1 : 1); i++) { finalExtra[i] = f3(0.f); extra[i] = f3(0.f); }
+    Reservoir finalReservoir = createNewReservoir();
+    const int rounds = (fp.initialM + 3) / 4;
+    for (int roundId = 0; roundId < rounds; roundId++) {
+        float hd[4] = {0, 0, 0, 0}, pd[4] = {0, 0, 0, 0}, ot[4] = {0, 0, 0, 0};
+        const int roundSamples = roundId == rounds - 1 ? (fp.initialM - 4 * (rounds - 1)) : 4;
+        if (!fp.noReuse) SampleMediumAnalyticGeneric(ray, sg, fp.initial.visibilityUseLinearSampler, hd, fp.initial.visibilityMipLevel, pd, ot, roundSamples);
+        for (int s = 0; s < roundSamples; s++) {
+            Reservoir outReservoir = ComputeInitialSample<B>(ray, hd[s], pd[s], ot[s], sg, fp, extra);
+            bool isSelected = simpleResampleStep<B>(outReservoir, finalReservoir, sg);
+            if (B > 1 && isSelected) {
                 const int mib = decodeMaxIndirectBounces<B>(finalReservoir.sampledPixel);
-                for (int b = 0; b < mib && b < B - 1; b++) fp.extCur[(size_t)reservoirId * (B - 1) + b] = finalExtra[b];
+                for (int b = 0; b < mib && b < B - 1; b++) finalExtra[b] = extra[b];
             }
         }
     }
-    if (defer) { wfEmit(wf.cam, hasCam, ca, cb); wfEmit(wf.light, hasLight, la, lb); }
+    ExtraProvider prov; prov.global = nullptr; prov.local = finalExtra;
+    Reservoir tapForEval = finalReservoir; tapForEval.extraBounceStartId = 0;
+    float p_hat = evaluate_P_hat<B>(ray, sg, prov, fp.spatial, tapForEval, false);
+    if (finalReservoir.runningSum > 0.f) {
+        finalReservoir.runningSum *= finalReservoir.p_y == 0.f ? 0.f : p_hat / finalReservoir.p_y;
+        finalReservoir.p_y = p_hat;
+    }
+    storeReservoir(fp.cur, reservoirId, finalReservoir);
+    if (B > 1) {
+        const int mib = decodeMaxIndirectBounces<B>(finalReservoir.sampledPixel);
+        for (int b = 0; b < mib && b < B - 1; b++) fp.extCur[(size_t)reservoirId * (B - 1) + b] = finalExtra[b];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -562,15 +530,7 @@ cudaError_t uploadScene(const DScene& s, cudaStream_t st) { return cudaMemcpyToS
     }
 
 cudaError_t launchFeatures(const FrameParams& fp, cudaStream_t st) { k_features<<<gridFor(fp), 128, 0, st>>>(fp); return cudaGetLastError(); }
-cudaError_t launchInitial(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) {
-    switch (fp.maxBounces) {
-        case 1: if (fp.deferPHat) k_initial<1, true><<<gridFor(fp), 128, 0, st>>>(fp, wf); else k_initial<1, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
-        case 2: k_initial<2, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
-        case 3: k_initial<3, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
-        default: k_initial<4, false><<<gridFor(fp), 128, 0, st>>>(fp, wf); break;
-    }
-    return cudaGetLastError();
-}
+cudaError_t launchInitial(const FrameParams& fp, cudaStream_t st) { VR_DISPATCH_B(k_initial, fp, st); return cudaGetLastError(); }
 cudaError_t launchTemporal(const FrameParams& fp, cudaStream_t st) { VR_DISPATCH_B(k_temporal, fp, st); return cudaGetLastError(); }
 cudaError_t launchSpatial(const FrameParams& fp, cudaStream_t st) { VR_DISPATCH_B(k_spatial, fp, st); return cudaGetLastError(); }
 cudaError_t launchFinal(const FrameParams& fp, cudaStream_t st) { VR_DISPATCH_B(k_final, fp, st); return cudaGetLastError(); }

@@ -6,7 +6,7 @@ namespace vrd {
 cudaError_t readDebugRays(float* out64x8, unsigned* count);
 cudaError_t uploadScene(const DScene& s, cudaStream_t st);
 cudaError_t launchFeatures(const FrameParams& fp, cudaStream_t st);
-cudaError_t launchInitial(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
+cudaError_t launchInitial(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchTemporal(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchSpatial(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchFinal(const FrameParams& fp, cudaStream_t st);
@@ -24,7 +24,6 @@ cudaError_t launchFinalCombine(const FrameParams& fp, const float* results, cuda
 cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st);
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st);
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st);
-cudaError_t launchInitialFinish(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchResToAos(ResBuf b, vrestir_reservoir* out, int n, cudaStream_t st);
 cudaError_t launchResFromAos(ResBuf b, const vrestir_reservoir* in, int n, cudaStream_t st);

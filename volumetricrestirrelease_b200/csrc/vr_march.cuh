@@ -90,7 +90,12 @@ struct MarchTrav {
         float3 mn = v3(g.bmin), mx = v3(g.bmax);
         if (vertexCenter) { ray.origin = ray.origin - f3(0.5f); mn = mn - f3(0.5f); mx = mx - f3(0.5f); }
         if (!IntersectP(mn, mx, ray, tNear, tFar)) return false;
-        pos = ray.origin; dir = ray.dir;
+        beginPrepared(ray.origin, ray.dir, g, vertexCenter);
+        return true;
+    }
+    // the part after the box test, for rays prepared by the emitting kernel (tNear / tFar already set)
+    VRD void beginPrepared(float3 rayOrigin, float3 rayDir, const DSlot& g, bool vertexCenter) {
+        pos = rayOrigin; dir = rayDir;
         invDir = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
         stepI = make_int3(dir.x >= 0 ? 1 : -1, dir.y >= 0 ? 1 : -1, dir.z >= 0 ? 1 : -1);
         tx = tNear + 0.01f; ty = 0.f; mask = 0;
@@ -104,7 +109,6 @@ struct MarchTrav {
             int it = 0;
             while (it++ < 3 && (p.x < 0 || p.y < 0 || p.z < 0 || p.x > r || p.y > r || p.z > r)) { next(); step(); }
         }
-        return true;
     }
 
     // ---- slow events (group 3) -------------------------------------------------------------------------------------
@@ -179,36 +183,42 @@ struct RayMarcher : MarchTrav {
         phase = MARCH_IDLE;
     }
 
-    VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, const DSlot& g) {
-        Ray rW;
-        rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
-        outIdx = b.w;
-        rW.tMin = 0.f;
-        float thr[NT];
-        if (kind.originMode == 0) {
-            rW.origin = make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
-            thr[0] = __uint_as_float(a.w);
-#pragma unroll
-            for (int k = 1; k < NT; k++) thr[k] = 0.f;
-            todo = 1u;
-            rW.tMax = thr[0];
-        } else {
-            rW.origin = kind.originMode == 1 ? c_scene.camPos : c_scene.prevPos;
-            const float v[3] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)};
-            todo = a.w & ((1u << NT) - 1u);
-            float mx = 0.f;
-#pragma unroll
-            for (int k = 0; k < NT; k++) { thr[k] = k < 3 ? v[k] : 0.f; if ((todo >> k) & 1u) mx = fmaxf(mx, thr[k]); }
-            rW.tMax = mx;
-        }
-        pending = todo;
-#pragma unroll
-        for (int k = 0; k < NT; k++) out[k] = 0.f;
-        Tr = 0.f;
+    VRD void setup(const uint4* q, const MarchKind& kind, const DSlot& g) {
         const int mip = kind.mip;
         int eff = mip >= VRESTIR_PREV_DENSITY_GRID_OFFSET ? mip - VRESTIR_PREV_DENSITY_GRID_OFFSET : mip;
         eff = eff >= VRESTIR_NUM_MAX_MIPS ? eff - VRESTIR_NUM_MAX_MIPS : eff;
         tStep = c_scene.vol.tStep * c_scene.vol.volumeWorldScaling * kind.tStepScale * (eff + 1);
+        Tr = 0.f;
+#pragma unroll
+        for (int k = 0; k < NT; k++) out[k] = 0.f;
+        if (kind.originMode == 0) {
+            // prepared task: the ray hits the box; its single threshold is ray.tMax, and min(tFar, tMax) == tFar
+            const uint4 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2);
+            outIdx = c.x;
+            todo = pending = 1u;
+            initialized = true;
+            tNear = __uint_as_float(a.w); tFar = __uint_as_float(b.w);
+            thrEff[0] = tFar;
+#pragma unroll
+            for (int k = 1; k < NT; k++) thrEff[k] = 0.f;
+            beginPrepared(make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)),
+                          make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), g, false);
+            return;
+        }
+        const uint4 a = __ldcs(q), b = __ldcs(q + 1);
+        Ray rW;
+        rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
+        outIdx = b.w;
+        rW.tMin = 0.f;
+        rW.origin = kind.originMode == 1 ? c_scene.camPos : c_scene.prevPos;
+        const float v[3] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)};
+        float thr[NT];
+        todo = a.w & ((1u << NT) - 1u);
+        float mx = 0.f;
+#pragma unroll
+        for (int k = 0; k < NT; k++) { thr[k] = k < 3 ? v[k] : 0.f; if ((todo >> k) & 1u) mx = fmaxf(mx, thr[k]); }
+        rW.tMax = mx;
+        pending = todo;
         initialized = beginTraversal(rW, g, false);
         if (!initialized) { phase = MARCH_DONE; return; }
 #pragma unroll
@@ -279,14 +289,13 @@ struct AnalyticMarcher : MarchTrav {
 
     VRD void writeOut(float* results) { results[outIdx] = expf(Tr); phase = MARCH_IDLE; }
 
-    VRD void setup(const uint4 a, const uint4 b, const MarchKind& kind, const DSlot& g) {
-        Ray rW;
-        rW.origin = make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
-        rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
-        rW.tMin = 0.f; rW.tMax = __uint_as_float(a.w);
-        outIdx = b.w;
+    VRD void setup(const uint4* q, const MarchKind& kind, const DSlot& g) {
+        const uint4 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2);   // prepared task (vertex-centred box)
+        outIdx = c.x;
         Tr = 0.f;
-        if (!beginTraversal(rW, g, true)) phase = MARCH_DONE;
+        tNear = __uint_as_float(a.w); tFar = __uint_as_float(b.w);
+        beginPrepared(make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)),
+                      make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), g, true);
     }
 
     VRD void enterBrick(const DSlot& g) {
@@ -341,7 +350,8 @@ struct AnalyticMarcher : MarchTrav {
     }
 };
 
-// Persistent-lane pool over one task stream.  tasks: 2 x uint4 per task; total: tasks in the stream; cursor: next unclaimed.
+// Persistent-lane pool over one task stream.  tasks: 3 (explicit, prepared) or 2 (camera) x uint4 per task; total: tasks in
+// the stream; cursor: next unclaimed.
 template <class M>
 __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g) {
     const unsigned FULL = 0xffffffffu;
@@ -362,10 +372,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
                 base = __shfl_sync(FULL, base, 0);
                 if (m.phase < 2) {
                     const unsigned idx = base + __popc(parked & ltMask);
-                    if (idx < total) {
-                        const uint4 a = __ldcs(&tasks[2 * (size_t)idx]), b = __ldcs(&tasks[2 * (size_t)idx + 1]);
-                        m.setup(a, b, kind, g);
-                    }
+                    if (idx < total) m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * idx, kind, g);
                 }
                 if (base + n >= total) drained = true;
             }

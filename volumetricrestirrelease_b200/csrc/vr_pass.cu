@@ -94,7 +94,7 @@ struct vrestir_pass {
     void* persistBase = nullptr; size_t persistBytes = 0;
     // wavefront (task-stream) path: march-task streams, result blocks, counters {cam.count, cam.cursor, light.count, light.cursor}
     bool mUseWavefront = true;
-    int mInitialMode = 1;   // K1: 0 per-pixel kernel, 1 lock-step wavefront (default), 2 per-pixel + p-hat re-evaluation through the march engine (measured slower)
+    int mInitialMode = 1;   // K1: 0 per-pixel kernel, 1 lock-step wavefront (default)
     uint4* wfCamTasks = nullptr; uint4* wfLightTasks = nullptr; float* wfResults = nullptr; unsigned* wfCounters = nullptr;
     size_t wfPixels = 0;
     int marchBlocks1 = 0, marchBlocks3 = 0, analyticBlocks = 0;
@@ -134,7 +134,7 @@ int ensureWavefront(vrestir_pass* p) {
     p->wfCamTasks = p->wfLightTasks = nullptr; p->wfResults = nullptr; p->wfPixels = 0;
     if (n * 12 >= (1ull << 32) || n * WF_BLOCK >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit task indices; shard the frame");
     CK(cudaMalloc(&p->wfCamTasks, n * 4 * 32));
-    CK(cudaMalloc(&p->wfLightTasks, n * 12 * 32));
+    CK(cudaMalloc(&p->wfLightTasks, n * 12 * 48));   // explicit (prepared) tasks are 48 B
     CK(cudaMalloc(&p->wfResults, n * WF_BLOCK * sizeof(float)));
     if (!p->wfCounters) CK(cudaMalloc(&p->wfCounters, 64));
     p->wfPixels = n;
@@ -411,23 +411,7 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                     recordEv(p, 2, st);
                     break;
                 }
-                const bool defer = p->mInitialMode == 2 && wavefrontEvalOk(p) && !m.mUseReference;
-                WfBufs wf{};
-                MarchKind kc{}, kl{};
-                if (defer) {
-                    rc = ensureWavefront(p); if (rc) return rc;
-                    wf = wfView(p);
-                    CK(cudaMemsetAsync(p->wfCounters, 0, 16, st));
-                    fp.deferPHat = 1;
-                    wavefrontKinds(p, kc, kl);
-                }
-                CK(launchInitial(fp, wf, st)); p->launches++;
-                if (defer) {
-                    CK(launchMarch(wf.cam, wf.results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st));
-                    CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
-                    CK(launchInitialFinish(fp, wf, st));
-                    p->launches += 3;
-                }
+                CK(launchInitial(fp, st)); p->launches++;
                 p->finalPhys = p->ia;
             }
             recordEv(p, 2, st);
@@ -452,12 +436,13 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                         wf.results = p->wfResults;
                         const size_t n = p->wfPixels;
                         // one buffer (16 n tasks) is plenty: <= 4 tasks per pixel in this stage
-                        uint4* bufs[4] = {p->wfLightTasks, p->wfLightTasks + 2 * (2 * n), p->wfLightTasks + 2 * (4 * n), p->wfLightTasks + 2 * (6 * n)};
+                        uint4* bufs[4] = {p->wfLightTasks, p->wfLightTasks + 3 * (2 * n), p->wfLightTasks + 3 * (4 * n), p->wfLightTasks + 3 * (6 * n)};
                         bool unique[4];
                         for (int k = 0; k < 4; k++) {
                             int alias = -1;
                             for (int j = 0; j < k && alias < 0; j++) if (memcmp(&kinds[j], &kinds[k], sizeof(MarchKind)) == 0) alias = j;
                             unique[k] = alias < 0;
+                            wf.mip[k] = kinds[k].mip;
                             if (alias >= 0) wf.s[k] = wf.s[alias];
                             else { wf.s[k].tasks = bufs[k]; wf.s[k].count = p->wfCounters + 2 * k; wf.s[k].cursor = p->wfCounters + 2 * k + 1; wf.s[k].capacity = (unsigned)(2 * n); }
                         }

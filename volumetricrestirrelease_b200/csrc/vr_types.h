@@ -61,7 +61,6 @@ struct FrameParams {
     int frameCount, numTotalRounds, maxBounces;
     int useReference, baselineSpp, initialM, useRussianRoulette, noReuse, useCoarserGrid;
     int visualizeTransmittance, outputMotionVec;
-    int deferPHat;   // K1: leave the final p-hat re-evaluation to the march engine (k_initial_finish applies it)
     // temporal
     float temporalMThreshold; uint32_t temporalMIS, reprojectionMode; int reprojectionMip;
     // spatial
@@ -76,8 +75,9 @@ struct FrameParams {
 };
 
 // ------------------------------------------------------------------------------------------------ wavefront streams
-// A march task is 2 x uint4: light tasks (originMode 0) = (origin.xyz, tMax | dir.xyz, result index); camera tasks
-// (originMode 1/2: origin = current / previous camera position) = (thr0, thr1, thr2, threshold mask | dir.xyz, result index).
+// Explicit tasks (originMode 0) are 3 x uint4, prepared by the emitter: (pos.xyz, tNear | dir.xyz, tFar | result index) with
+// the ray in the index space of the march mip and clipped to the volume box.  Camera tasks (originMode 1/2: origin = current /
+// previous camera position) are 2 x uint4: (thr0, thr1, thr2, threshold mask | world dir.xyz, result index).
 struct MarchKind { int mip, linear; float tStepScale; int originMode; };
 struct WfStream { uint4* tasks; unsigned* count; unsigned* cursor; unsigned capacity; };
 // per-pixel result block (floats): D[i*4+j] density of tap i's sample seen from ray j, C[j*3+k] camera transmittance along
@@ -89,6 +89,6 @@ enum { K1_WORDS = 20, K1_STRIDE = 80 };
 struct WfInitial { WfStream light; float* state; };
 // K2: four explicit-origin streams {current camera, current light, previous-frame camera, previous-frame light};
 // streams whose march configuration is identical alias the same buffer
-struct WfBufs4 { WfStream s[4]; float* results; };
+struct WfBufs4 { WfStream s[4]; int mip[4]; float* results; };
 
 }  // namespace vrd

@@ -94,7 +94,11 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
                     camBits |= 1u << (j * 3 + (i - (i > j ? 1 : 0)));
                     if (!bg && tap.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
                         Ray sh; float3 Ld;
-                        if (lightRayAndLd(makeMI(pW, -dir, true), tap.lightID, tap.lightUV, false, sh, Ld)) lightBits |= 1u << (i * 4 + j);
+                        if (lightRayAndLd(makeMI(pW, -dir, true), tap.lightID, tap.lightUV, false, sh, Ld)) {
+                            PreparedRay pr;   // rays that miss the volume box are resolved here (transmittance 1)
+                            if (wfPrepare(sh, fp.spatial.lightingMipLevel, false, pr)) lightBits |= 1u << (i * 4 + j);
+                            else blk[WF_L + i * 4 + j] = 1.f;
+                        }
                     }
                 } else if (j == 0) alive = false;   // p-hat on the centre ray is 0: the tap is dropped, no MIS terms
             }
@@ -148,9 +152,13 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
                 const float3 pW = r.at(r.tMax);
                 Ray sh; float3 Ld;
                 lightRayAndLd(makeMI(pW, -dir, true), tap.lightID, tap.lightUV, false, sh, Ld);
+                PreparedRay pr;
+                wfPrepare(sh, fp.spatial.lightingMipLevel, false, pr);
                 if (pos < wf.light.capacity) {
-                    wf.light.tasks[2 * (size_t)pos] = make_uint4(__float_as_uint(sh.origin.x), __float_as_uint(sh.origin.y), __float_as_uint(sh.origin.z), __float_as_uint(sh.tMax));
-                    wf.light.tasks[2 * (size_t)pos + 1] = make_uint4(__float_as_uint(sh.dir.x), __float_as_uint(sh.dir.y), __float_as_uint(sh.dir.z), blkBase + WF_L + i * 4 + j);
+                    uint4* q = wf.light.tasks + 3 * (size_t)pos;
+                    q[0] = make_uint4(__float_as_uint(pr.pos.x), __float_as_uint(pr.pos.y), __float_as_uint(pr.pos.z), __float_as_uint(pr.tNear));
+                    q[1] = make_uint4(__float_as_uint(pr.dir.x), __float_as_uint(pr.dir.y), __float_as_uint(pr.dir.z), __float_as_uint(pr.tFar));
+                    q[2] = make_uint4(blkBase + WF_L + i * 4 + j, 0u, 0u, 0u);
                 }
             }
             lightBase += __popc(bal);
@@ -197,27 +205,26 @@ VRD float wfPHat(const Reservoir& tap, float3 origin, float3 dir, const float* b
 // (explicit origin, threshold = tap.depth) and one light march task.  Result slots: out+0 density, out+1 camera Tr, out+2 light Tr.
 // Every lane of the warp must call; `want` masks the lanes that have an evaluation.
 VRD void wfEmitEval(bool want, const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, float* results, unsigned out,
-                    const WfStream& camStream, const WfStream& lightStream) {
+                    const WfStream& camStream, int camMip, const WfStream& lightStream, int lightMip) {
     bool hasCam = false, hasLight = false;
-    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, la = ca, lb = ca;
+    Ray r = makeRay(origin, dir, 0.f, tap.depth), sh = r;
     if (want) {
         const vrestir_volume_desc& vd = c_scene.vol;
         const bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
         const bool bg = tap.depth == kRayTMax;
-        const Ray r = makeRay(origin, dir, 0.f, tap.depth);
         const float3 pW = r.at(r.tMax);
         const float density = bg ? 1.f : DensityWorldSpace(pW, useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0);
         results[out] = density;
         if (density != 0.f) {
-            hasCam = true; ca = wfLightTaskOrigin(r); cb = wfLightTask(r, out + 1);
+            hasCam = true;
             if (!bg && tap.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
-                Ray sh; float3 Ld;
-                if (lightRayAndLd(makeMI(pW, -dir, true), tap.lightID, tap.lightUV, isLastFrame, sh, Ld)) { hasLight = true; la = wfLightTaskOrigin(sh); lb = wfLightTask(sh, out + 2); }
+                float3 Ld;
+                hasLight = lightRayAndLd(makeMI(pW, -dir, true), tap.lightID, tap.lightUV, isLastFrame, sh, Ld);
             }
         }
     }
-    wfEmit(camStream, hasCam, ca, cb);
-    wfEmit(lightStream, hasLight, la, lb);
+    wfEmitRay(camStream, hasCam, r, camMip, false, results, out + 1);
+    wfEmitRay(lightStream, hasLight, sh, lightMip, false, results, out + 2);
 }
 
 __global__ void __launch_bounds__(128) k_spatial_combine(FrameParams fp, WfBufs wf) {
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : 4) k_initial_step(FramePa
     const SamplingOptions& o = fp.initial;
     const int M = fp.initialM;
     bool hasTask = false;
-    uint4 ta = make_uint4(0, 0, 0, 0), tb = ta;
+    Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
     if (inFrame) {
         SampleGenerator sg;
         const Ray ray = primaryRay(fp, x, y);
@@ -425,8 +432,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : 4) k_initial_step(FramePa
                     c.ph = mi.phaseFunction(mi.wo, ls.dir);
                     if (o.lightSamples != 0) {
                         c.flags |= 8u; hasTask = true;
-                        const Ray sh = makeRay(mi.p, ls.rayDir, 0, ls.rayDistance);
-                        ta = wfLightTaskOrigin(sh); tb = wfLightTask(sh, recBase + 18);
+                        shadow = makeRay(mi.p, ls.rayDir, 0, ls.rayDistance);
                     }
                 }
                 c.uEm = sampleNext1D(sg);
@@ -446,7 +452,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : 4) k_initial_step(FramePa
             storeReservoir(fp.cur, pixelId, finalReservoir);
         }
     }
-    if (MODE != 2) wfEmit(wi.light, hasTask, ta, tb);
+    if (MODE != 2) wfEmitRay(wi.light, hasTask, shadow, o.lightingMipLevel, false, wi.state, recBase + 18);
 }
 
 // ------------------------------------------------------------------------------------------------ K2 wavefront
@@ -543,8 +549,8 @@ __global__ void __launch_bounds__(128) k_temporal_gather(FrameParams fp, WfBufs4
             t0.depth = centerPrevFrameDepth;   // usedDepth of the (i = 0, j = 1) term
         }
     }
-    wfEmitEval(wantE1, t1, c_scene.camPos, dirCur, false, wf.results, blkBase + T2_E1, wf.s[0], wf.s[1]);
-    wfEmitEval(wantE0, t0, c_scene.prevPos, dirPrev, true, wf.results, blkBase + T2_E0, wf.s[2], wf.s[3]);
+    wfEmitEval(wantE1, t1, c_scene.camPos, dirCur, false, wf.results, blkBase + T2_E1, wf.s[0], wf.mip[0], wf.s[1], wf.mip[1]);
+    wfEmitEval(wantE0, t0, c_scene.prevPos, dirPrev, true, wf.results, blkBase + T2_E0, wf.s[2], wf.mip[2], wf.s[3], wf.mip[3]);
 }
 
 __global__ void __launch_bounds__(128) k_temporal_combine(FrameParams fp, WfBufs4 wf) {
@@ -621,27 +627,28 @@ __global__ void __launch_bounds__(128) k_final_gather(FrameParams fp, WfStream s
     const int pixelId = inFrame ? y * fp.W + x : fp.rowBegin * fp.W;
     const unsigned out = (unsigned)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
     bool hasCam = false, hasLight = false;
-    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, la = ca, lb = ca;
+    Ray r = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f), sh = r;
     if (inFrame) {
         const Reservoir cur = loadReservoir(fp.cur, pixelId, 1);
         if (cur.runningSum > 0.f) {
             const bool noReuse = fp.noReuse != 0;
             const bool bg = cur.depth == kRayTMax;
-            const Ray r = makeRay(c_scene.camPos, tapRayDir(fp, x, y), 0.f, cur.depth);
+            r = makeRay(c_scene.camPos, tapRayDir(fp, x, y), 0.f, cur.depth);
             const float3 pW = r.at(r.tMax);
             const float density = (bg || noReuse) ? 1.f : DensityWorldSpace(pW, 0);
             results[out] = density;
             if (density != 0.f) {
-                if (!noReuse) { hasCam = true; ca = wfLightTaskOrigin(r); cb = wfLightTask(r, out + 1); }
+                hasCam = !noReuse;
                 if (!bg && cur.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
-                    Ray sh; float3 Ld;
-                    if (lightRayAndLd(makeMI(pW, -r.dir, true), cur.lightID, cur.lightUV, false, sh, Ld)) { hasLight = true; la = wfLightTaskOrigin(sh); lb = wfLightTask(sh, out + 2); }
+                    float3 Ld;
+                    hasLight = lightRayAndLd(makeMI(pW, -r.dir, true), cur.lightID, cur.lightUV, false, sh, Ld);
                 }
             }
         }
     }
-    wfEmit(stream, hasCam, ca, cb);
-    wfEmit(stream, hasLight, la, lb);
+    // analytic tracking with the linear sampler traverses vertex-centred (VR/VolumeUtils.slang:284-292)
+    wfEmitRay(stream, hasCam, r, 0, true, results, out + 1);
+    wfEmitRay(stream, hasLight, sh, 0, true, results, out + 2);
 }
 
 __global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const float* results) {
@@ -661,22 +668,6 @@ __global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const flo
     float4 o = make_float4(outputColor.x, outputColor.y, outputColor.z, 1.f);
     if (isnan(o.x) || isinf(o.x) || isnan(o.y) || isinf(o.y) || isnan(o.z) || isinf(o.z)) o = make_float4(0.f, 0.f, 0.f, 0.f);
     fp.outColor[pixelId] = o;
-}
-
-// ------------------------------------------------------------------------------------------------ K1 finish
-// VR/TraceRays.cs.slang:176-183: p-hat of the pixel's own reservoir on its own ray under the spatial options
-__global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfBufs wf) {
-    int x, y;
-    if (!pixelOf(fp, x, y)) return;
-    const int pixelId = y * fp.W + x;
-    const float4 a = fp.cur.p0[pixelId];   // (runningSum, M, depth, p_y)
-    if (!(a.x > 0.f)) return;
-    Reservoir r = loadReservoirRW(fp.cur, pixelId, 1);
-    const float* blk = wf.results + (size_t)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
-    const float p_hat = wfPHat(r, c_scene.camPos, tapRayDir(fp, x, y), blk, 0, 0);
-    r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
-    r.p_y = p_hat;
-    fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -710,7 +701,6 @@ cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s,
 }
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
-cudaError_t launchInitialFinish(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_initial_finish<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 
 }  // namespace vrd
