@@ -87,6 +87,9 @@ struct vrestir_pass {
     int mFrameCount = 0, mTemporalSampleAccumulated = 0; bool mOptionsChanged = true;
     cudaEvent_t ev[8] = {};
     bool evValid[8] = {};
+    // K0 (features) has no consumer before K2: vrestir_execute runs it on an auxiliary stream next to K1
+    bool mOverlapFeatures = true, framesOverlapped = false;
+    cudaStream_t auxStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaStream_t hostStream = nullptr;
     float4* d_hostColor = nullptr; float2* d_hostMvec = nullptr; size_t hostColorPixels = 0;
     uint64_t launches = 0;
@@ -367,7 +370,7 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
     }
     CK(cudaSetDevice(p->device));
     int rc = ensureBuffers(p); if (rc) return rc;
-    if (stage == 0 && p->mOptionsChanged) {   // VR/VolumetricReSTIR.cpp:349-359
+    if ((stage == 0 || stage == -1) && p->mOptionsChanged) {   // VR/VolumetricReSTIR.cpp:349-359
         if (p->mRandomizeFrameSeed) p->mFrameCount = rand_r(&p->randState) % 65536; else p->mFrameCount = 0;
         p->mTemporalSampleAccumulated = 0; p->mOptionsChanged = false;
     }
@@ -375,6 +378,10 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
     FrameParams fp; buildFrameParams(p, fp, out_color, out_mvec);
     const bool active = !p->mFreezeFrame;
     switch (stage) {
+        case -1:   // frame begin on the main stream when K0 runs concurrently on the auxiliary stream (vrestir_execute)
+            recordEv(p, 7, st);
+            setPersistingWindow(p, st);
+            break;
         case 0:
             recordEv(p, 0, st);
             setPersistingWindow(p, st);
@@ -633,6 +640,9 @@ int vrestir_destroy(vrestir_pass* p) {
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
+    if (p->auxStream) cudaStreamDestroy(p->auxStream);
+    if (p->evFork) cudaEventDestroy(p->evFork);
+    if (p->evJoin) cudaEventDestroy(p->evJoin);
     delete p;
     return VRESTIR_OK;
 }
@@ -800,7 +810,8 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
         else if (k == "volumeAnisotropyExtraControl") p->anisotropyExtra = (float)value;
         else if (k == "mEnvSamplerType") p->envSamplerType = (int)value;
         else if (k == "mUseWavefront") p->mUseWavefront = value != 0;
-        else if (k == "mInitialMode") p->mInitialMode = (int)value;   // 0 forces the per-pixel kernels (A/B tests)
+        else if (k == "mInitialMode") p->mInitialMode = (int)value;
+        else if (k == "mOverlapFeatures") p->mOverlapFeatures = value != 0;   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
     }
@@ -845,8 +856,23 @@ int vrestir_execute_stage(vrestir_pass* p, int stage, int arg, float* out_color,
 int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = runStage(p, 0, 0, out_color, out_mvec, st))) return rc;
-    if ((rc = runStage(p, 1, 0, out_color, out_mvec, st))) return rc;
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    const bool overlap = p->mOverlapFeatures && !p->P.mUseReference && !p->mFreezeFrame;
+    p->framesOverlapped = overlap;
+    if (overlap) {
+        CK(cudaSetDevice(p->device));
+        if (!p->auxStream) { CK(cudaStreamCreateWithFlags(&p->auxStream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&p->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming)); }
+        if ((rc = runStage(p, -1, 0, out_color, out_mvec, st))) return rc;   // options / frame counter / scene constants, on the main stream
+        CK(cudaEventRecord(p->evFork, st));
+        CK(cudaStreamWaitEvent(p->auxStream, p->evFork, 0));
+        if ((rc = runStage(p, 0, 0, out_color, out_mvec, p->auxStream))) return rc;
+        CK(cudaEventRecord(p->evJoin, p->auxStream));
+        if ((rc = runStage(p, 1, 0, out_color, out_mvec, st))) return rc;
+        CK(cudaStreamWaitEvent(st, p->evJoin, 0));
+    } else {
+        if ((rc = runStage(p, 0, 0, out_color, out_mvec, st))) return rc;
+        if ((rc = runStage(p, 1, 0, out_color, out_mvec, st))) return rc;
+    }
     if ((rc = runStage(p, 2, 0, out_color, out_mvec, st))) return rc;
     if (p->P.mEnableSpatialReuse) { for (int r = 0; r < p->P.mSpatialReuseRounds; r++) if ((rc = runStage(p, 3, r, out_color, out_mvec, st))) return rc; }
     else recordEv(p, 4, st);
@@ -885,6 +911,10 @@ int vrestir_get_timings(vrestir_pass* p, vrestir_timings* out) {
     float* dst[6] = {&out->features_ms, &out->initial_ms, &out->temporal_ms, &out->spatial_ms, &out->copy_ms, &out->final_ms};
     for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(dst[i], p->ev[i], p->ev[i + 1]));
     CK(cudaEventElapsedTime(&out->total_ms, p->ev[0], p->ev[6]));
+    if (p->framesOverlapped && p->evValid[7]) {   // K0 ran next to K1: initial / total are measured from the frame start on the main stream
+        CK(cudaEventElapsedTime(&out->initial_ms, p->ev[7], p->ev[2]));
+        CK(cudaEventElapsedTime(&out->total_ms, p->ev[7], p->ev[6]));
+    }
     return VRESTIR_OK;
 }
 int vrestir_get_launch_count(const vrestir_pass* p, uint64_t* out) {

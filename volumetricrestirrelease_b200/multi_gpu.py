@@ -109,6 +109,9 @@ class ShardedPass:
         prm = p.params
         B = prm.mMaxBounces
         radius = int(math.ceil(prm.mSampleRadius))
+        if self.world == 1:   # nothing to exchange: the whole-frame call (K0 overlapped with K1 on an auxiliary stream)
+            p.execute(out_color_ptr, out_mvec_ptr, stream)
+            return
         p.execute_stage(0, 0, out_color_ptr, out_mvec_ptr, stream)
         p.execute_stage(1, 0, out_color_ptr, out_mvec_ptr, stream)
         p.execute_stage(2, 0, out_color_ptr, out_mvec_ptr, stream)
