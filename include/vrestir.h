@@ -322,6 +322,16 @@ int vrestir_execute_host(vrestir_pass* pass, float* out_color_host, float* out_m
 int vrestir_execute_stage(vrestir_pass* pass, int stage, int arg, float* out_color, float* out_mvec, void* stream);
 
 int vrestir_get_timings(vrestir_pass* pass, vrestir_timings* out);
+/* The two march launches of the last spatial-reuse round (the dominant kernels of a frame): CUDA-event times on the launching
+ * stream and the number of tasks each stream held.  Feeds bench.py's roofline object. */
+typedef struct vrestir_march_timings {
+    float spatial_cam_ms, spatial_light_ms;
+    uint32_t spatial_cam_tasks, spatial_light_tasks;
+} vrestir_march_timings;
+int vrestir_get_march_timings(vrestir_pass* pass, vrestir_march_timings* out);
+/* Read-bandwidth microbenchmark: `bytes` are read `iters` times by every SM with 16-byte loads (CUDA events); a buffer that
+ * fits L2 (e.g. 32 MiB) gives the L2 -> SM peak the volume-fetch kernels are compared with, a large one the HBM read peak. */
+int vrestir_debug_read_bandwidth(int device, size_t bytes, int iters, float* gb_per_s);
 /* number of kernels this library launched since create (claim for bench.py's gpu_launches) */
 int vrestir_get_launch_count(const vrestir_pass* pass, uint64_t* out);
 

@@ -509,6 +509,23 @@ __global__ void k_res_from_aos(ResBuf b, const vrestir_reservoir* in, int n) {
     b.p1[i] = make_float4(r.lightUV[0], r.lightUV[1], __int_as_float(r.lightID), __int_as_float(r.sampledPixel));
 }
 
+// ------------------------------------------------------------------------------------------------ bandwidth probe
+// every thread streams the buffer with 16-byte loads (grid-stride), `iters` times; the xor keeps the loads alive
+__global__ void __launch_bounds__(256) k_read_bandwidth(const uint4* __restrict__ buf, size_t n16, int iters, unsigned* sink) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; it++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) *sink = acc.x;
+}
+cudaError_t launchReadBandwidth(const void* buf, size_t bytes, int iters, int blocks, unsigned* sink, cudaStream_t st) {
+    k_read_bandwidth<<<blocks, 256, 0, st>>>((const uint4*)buf, bytes / 16, iters, sink);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 gridFor(const FrameParams& fp) { return dim3((fp.W + 15) / 16, (fp.rowEnd - fp.rowBegin + 7) / 8); }
 

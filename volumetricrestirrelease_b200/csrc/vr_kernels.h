@@ -25,6 +25,7 @@ cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s,
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st);
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st);
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
+cudaError_t launchReadBandwidth(const void* buf, size_t bytes, int iters, int blocks, unsigned* sink, cudaStream_t st);
 cudaError_t launchResToAos(ResBuf b, vrestir_reservoir* out, int n, cudaStream_t st);
 cudaError_t launchResFromAos(ResBuf b, const vrestir_reservoir* in, int n, cudaStream_t st);
 }

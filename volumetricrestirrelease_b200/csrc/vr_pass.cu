@@ -90,6 +90,7 @@ struct vrestir_pass {
     // K0 (features) has no consumer before K2: vrestir_execute runs it on an auxiliary stream next to K1
     bool mOverlapFeatures = true, framesOverlapped = false;
     cudaStream_t auxStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evMarch[3] = {}; bool evMarchValid = false;   // around the two march launches of the last spatial round
     cudaStream_t hostStream = nullptr;
     float4* d_hostColor = nullptr; float2* d_hostMvec = nullptr; size_t hostColorPixels = 0;
     uint64_t launches = 0;
@@ -482,8 +483,15 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                     CK(launchSpatialGather(fp, wf, st));
                     MarchKind kc, kl;
                     wavefrontKinds(p, kc, kl);
+                    for (auto& e : p->evMarch) if (!e) CK(cudaEventCreate(&e));
+                    CK(cudaEventRecord(p->evMarch[0], st));
                     CK(launchMarch(wf.cam, wf.results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st));
+                    CK(cudaEventRecord(p->evMarch[1], st));
                     CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
+                    CK(cudaEventRecord(p->evMarch[2], st));
+                    p->evMarchValid = true;
+                    CK(cudaMemcpyAsync(p->wfCounters + 8, p->wfCounters, 4, cudaMemcpyDeviceToDevice, st));       // task counts of this round (diagnostics)
+                    CK(cudaMemcpyAsync(p->wfCounters + 9, p->wfCounters + 2, 4, cudaMemcpyDeviceToDevice, st));
                     CK(launchSpatialCombine(fp, wf, st));
                     p->launches += 4;
                 } else { CK(launchSpatial(fp, st)); p->launches++; }
@@ -643,6 +651,7 @@ int vrestir_destroy(vrestir_pass* p) {
     if (p->auxStream) cudaStreamDestroy(p->auxStream);
     if (p->evFork) cudaEventDestroy(p->evFork);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
+    for (auto& e : p->evMarch) if (e) cudaEventDestroy(e);
     delete p;
     return VRESTIR_OK;
 }
@@ -915,6 +924,37 @@ int vrestir_get_timings(vrestir_pass* p, vrestir_timings* out) {
         CK(cudaEventElapsedTime(&out->initial_ms, p->ev[7], p->ev[2]));
         CK(cudaEventElapsedTime(&out->total_ms, p->ev[7], p->ev[6]));
     }
+    return VRESTIR_OK;
+}
+int vrestir_get_march_timings(vrestir_pass* p, vrestir_march_timings* out) {
+    if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!p->evMarchValid) return setError(VRESTIR_ERR_NOT_READY, "no wavefront spatial round has run");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventSynchronize(p->evMarch[2]));
+    CK(cudaEventElapsedTime(&out->spatial_cam_ms, p->evMarch[0], p->evMarch[1]));
+    CK(cudaEventElapsedTime(&out->spatial_light_ms, p->evMarch[1], p->evMarch[2]));
+    uint32_t c[2] = {0, 0};
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(c, p->wfCounters + 8, 8, cudaMemcpyDeviceToHost));
+    out->spatial_cam_tasks = c[0]; out->spatial_light_tasks = c[1];
+    return VRESTIR_OK;
+}
+int vrestir_debug_read_bandwidth(int device, size_t bytes, int iters, float* gbs) {
+    if (!gbs || bytes < 4096 || iters < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
+    CK(cudaSetDevice(device));
+    void* buf = nullptr; unsigned* sink = nullptr;
+    CK(cudaMalloc(&buf, bytes)); CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(buf, 1, bytes));
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(launchReadBandwidth(buf, bytes, 2, sms * 8, sink, nullptr));   // warm-up: brings the buffer into L2 when it fits
+    CK(cudaEventRecord(e0, nullptr));
+    CK(launchReadBandwidth(buf, bytes, iters, sms * 8, sink, nullptr));
+    CK(cudaEventRecord(e1, nullptr));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
+    *gbs = (float)((double)(bytes / 16 * 16) * iters / (ms * 1e-3) / 1e9);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
     return VRESTIR_OK;
 }
 int vrestir_get_launch_count(const vrestir_pass* p, uint64_t* out) {

@@ -172,6 +172,11 @@ class VolumetricReSTIR:
         capi.check(self._lib.vrestir_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in capi.Timings._fields_}
 
+    def march_timings(self):
+        t = capi.MarchTimings()
+        capi.check(self._lib.vrestir_get_march_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in capi.MarchTimings._fields_}
+
     def debug_long_rays(self):
         out = np.zeros((64, 8), dtype=np.float32)
         n = C.c_uint32()
