@@ -215,8 +215,9 @@ def main():
     params = make_params(args)
     gp = VolumetricReSTIR.create({"mParams": params}, device=local)
     sp = ShardedPass(gp, W, H, rank, world, torch.device("cuda", local))
-    r0, r1 = sp.band
-    gp.setScene(scene, W, H, r0, r1)
+    gp.setScene(scene, W, H)
+    r0, r1 = sp.balance()      # world > 1: cost-balanced row bands from one full-frame K0 (sky rows are cheap)
+    gp.setRowBand(r0, r1)
     if rank == 0:
         print(f"[bench] scene + upload {time.time() - t0:.1f}s; bricks mip0={scene.volume.stats(0)} mip1={scene.volume.stats(1)} "
               f"cons1={scene.volume.stats(9)} mip2={scene.volume.stats(2)}", file=sys.stderr)
@@ -320,7 +321,7 @@ def main():
                             "(SIMT divergence between DDA stepping and in-brick sampling), see profiles/"}
     line = {"metric": "ms/frame", "value": ms, "unit": "ms/frame", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(d=args.dim, m=args.mips, w=W, h=H, b=args.bounces), "parallelism": f"rows/{world}",
+            "config": {"workload": WORKLOAD.format(d=args.dim, m=args.mips, w=W, h=H, b=args.bounces), "parallelism": f"rows/{world}" + (f" (cost-balanced bands {sp.bands})" if world > 1 else ""),
                        "l2": "inputs larger than L2 (fp32 mip-0 brick pool + ~0.9 GB/frame of reservoir traffic stream through every frame; the reuse mip is pinned in L2 by design)",
                        "camera": "static", "stage_ms": {k: round(v, 3) for k, v in stage_acc.items()}},
             "clocks": clocks,

@@ -47,3 +47,25 @@ def test_row_bands_cover_frame_and_are_tile_aligned():
             assert all(r0 % 8 == 0 for r0, _ in b)
             sizes = [r1 - r0 for r0, r1 in b]
             assert max(sizes) - min(sizes) <= 8 + (h % 8)
+
+
+def test_balanced_row_bands_partition_and_balance():
+    """Cost-balanced bands: contiguous, aligned, cover the frame, respect the minimum band height, and are better balanced
+    than the even split for a frame whose cost sits in the middle rows (cloud in front of sky)."""
+    import numpy as np
+    from volumetricrestirrelease_b200.multi_gpu import balanced_row_bands, row_bands
+    H = 1080
+    y = np.arange(H)
+    cost = 0.05 * 1920 + 1920 * np.exp(-((y - 520) / 180.0) ** 2)
+    for n in (2, 3, 4, 8):
+        bands = balanced_row_bands(cost, n)
+        assert bands[0][0] == 0 and bands[-1][1] == H
+        assert all(b[1] == bands[i + 1][0] for i, b in enumerate(bands[:-1]))
+        assert all(b[0] % 8 == 0 for b in bands) and all(b[1] - b[0] >= 16 for b in bands)
+        even = row_bands(H, n)
+        worst = lambda bs: max(cost[a:b].sum() for a, b in bs)
+        assert worst(bands) <= worst(even) + 1e-9
+        if n >= 4:
+            assert worst(bands) < 0.75 * worst(even)
+    # degenerate: fewer aligned units than ranks x minimum -> even split
+    assert balanced_row_bands(np.ones(40), 4) == row_bands(40, 4)

@@ -30,6 +30,40 @@ def row_bands(height, world_size, align=8):
     return bands
 
 
+def balanced_row_bands(row_cost, world_size, align=8, min_rows=16):
+    """Contiguous, `align`-row aligned bands with (nearly) equal summed cost.  `row_cost`: per-row cost estimate (len H).
+    Every band keeps at least `min_rows` rows (the halo a neighbour reads from it must lie inside one band).
+    Deterministic: every rank computes the same partition from the same costs."""
+    row_cost = np.asarray(row_cost, dtype=np.float64)
+    height = len(row_cost)
+    units = math.ceil(height / align)
+    mu = max(1, math.ceil(min_rows / align))
+    if units < world_size * mu:
+        return row_bands(height, world_size, align)
+    unit_cost = np.add.reduceat(row_cost, np.arange(0, height, align))
+    csum = np.concatenate([[0.0], np.cumsum(unit_cost)])
+    total = csum[-1]
+    cuts = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        u = int(np.searchsorted(csum, target))
+        # the cut closest to the target, leaving room for the remaining ranks
+        if u > 0 and abs(csum[u - 1] - target) <= abs(csum[min(u, units)] - target):
+            u -= 1
+        u = max(cuts[-1] + mu, min(u, units - (world_size - r) * mu))
+        cuts.append(u)
+    cuts.append(units)
+    return [(min(height, cuts[r] * align), min(height, cuts[r + 1] * align)) for r in range(world_size)]
+
+
+def row_cost_from_features(features, background_weight=0.05):
+    """Cost model for the row partition: a pixel whose camera ray meets the medium (total transmittance < 1 in the K0
+    feature buffer) costs 1, a background pixel `background_weight` (it still runs K0/K1's traversal and the pass-through)."""
+    tr = features["transmittance"]
+    active = (tr != 1.0).sum(axis=1).astype(np.float64)
+    return active + background_weight * tr.shape[1]
+
+
 class _DevPtr:
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
@@ -79,6 +113,23 @@ class ShardedPass:
         min_band = min(b[1] - b[0] for b in self.bands)
         self.max_halo = min_band
 
+    def balance(self, background_weight=0.05):
+        """Re-partition the rows by estimated cost (the scaling limiter of row sharding is load imbalance,
+        sky rows are cheap).  Call after ``pass.setScene(scene, W, H)`` (full frame) and before the first frame: every rank
+        runs K0 over the whole frame once, derives the same per-row cost from the feature buffer and takes its band.
+        Returns the band of this rank."""
+        FEAT_DTYPE = np.dtype([("noReflectiveSurface", np.int32), ("transmittance", np.float32)])
+        if self.world > 1:
+            self.p.setRowBand(0, self.H)
+            self.p.execute_stage(0)
+            feat = self.p.get_buffer(capi.BUF_FEATURES).view(FEAT_DTYPE).reshape(self.H, self.W)
+            self.bands = balanced_row_bands(row_cost_from_features(feat, background_weight), self.world, min_rows=max(16, self.temporal_halo))
+            self.band = self.bands[self.rank]
+            self.max_halo = min(b[1] - b[0] for b in self.bands)
+            self.p.setRowBand(*self.band)
+            self.p.updateDict({})          # a fresh option-change epoch: frame counter and history restart
+        return self.band
+
     def _planes(self, buffer):
         base, stride, planes = self.p.device_buffer(buffer)
         n = self.W * self.H
@@ -101,7 +152,8 @@ class ShardedPass:
         planes = []
         for b in buffers:
             planes += self._planes(b)
-        torch.cuda.current_stream().synchronize() if self.device != "cpu" else None
+        # NCCL send/recv are ordered after the pass's kernels through torch's current stream (the pass launches on the same,
+        # default, stream) and work.wait() only makes that stream wait: no host synchronisation
         exchange_row_halo(planes, self.band, halo, self.rank, self.world)
 
     def execute(self, out_color_ptr, out_mvec_ptr=None, stream=None):

@@ -133,6 +133,11 @@ class VolumetricReSTIR:
             capi.check(L.vrestir_set_emissive_triangles(self._h, scene.emissiveTriangles, len(scene.emissiveTriangles),
                                                         float(scene.emissiveIntensityMultiplier)))
 
+    def setRowBand(self, row_begin, row_end):
+        """Restrict the pass to rows [row_begin, row_end) of the frame (multi-GPU row sharding)."""
+        w, h = self._frame
+        capi.check(self._lib.vrestir_set_frame(self._h, w, h, int(row_begin), int(row_end)))
+
     def updateCamera(self):
         cam = self._scene.camera.data(*self._frame)
         capi.check(self._lib.vrestir_set_camera(self._h, C.byref(cam)))
