@@ -216,12 +216,14 @@ def main():
     gp = VolumetricReSTIR.create({"mParams": params}, device=local)
     sp = ShardedPass(gp, W, H, rank, world, torch.device("cuda", local))
     gp.setScene(scene, W, H)
-    r0, r1 = sp.balance()      # world > 1: cost-balanced row bands from one full-frame K0 (sky rows are cheap)
+    color = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    # world > 1: cost-balanced row bands from a full-frame K0 cost model (the measured-time refinement is off: with the fixed
+    # per-launch latency of a short band it over-corrects, 7.06 vs 6.49 ms at 4K on 8 GPUs)
+    r0, r1 = sp.balance(refine=0)
     gp.setRowBand(r0, r1)
     if rank == 0:
         print(f"[bench] scene + upload {time.time() - t0:.1f}s; bricks mip0={scene.volume.stats(0)} mip1={scene.volume.stats(1)} "
               f"cons1={scene.volume.stats(9)} mip2={scene.volume.stats(2)}", file=sys.stderr)
-    color = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     host_color = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
 
     def barrier():

@@ -74,11 +74,13 @@ def device_view(ptr, nbytes, device):
     return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
 
 
-def exchange_row_halo(planes, band, halo, rank, world_size, bands=None, group=None):
+def exchange_row_halo(planes, band, halo, rank, world_size, bands=None, group=None, wait=True):
     """Exchange `halo` rows above/below `band` between neighbouring ranks.
 
     planes: list of 2-D (rows, row_bytes) uint8 tensors covering the FULL frame height (each rank holds valid data in
     its own band); after the call rows [r0-halo, r0) and [r1, r1+halo) hold the neighbours' data.
+    wait=False returns the pending works instead of making the current stream wait for them (the caller overlaps the
+    transfer with stages that do not read the halo).
     """
     r0, r1 = band
     ops = []
@@ -93,10 +95,14 @@ def exchange_row_halo(planes, band, halo, rank, world_size, bands=None, group=No
             ops.append(dist.P2POp(dist.isend, t[max(r0, r1 - halo):r1], rank + 1, group))
             ops.append(dist.P2POp(dist.irecv, t[r1:hi], rank + 1, group))
     if not ops:
-        return
+        return []
     # a neighbour's band can be shorter than the halo: both sides must agree on sizes, so clamp consistently
-    for w in dist.batch_isend_irecv(ops):
-        w.wait()
+    works = dist.batch_isend_irecv(ops)
+    if wait:
+        for w in works:
+            w.wait()
+        return []
+    return works
 
 
 class ShardedPass:
@@ -113,21 +119,52 @@ class ShardedPass:
         min_band = min(b[1] - b[0] for b in self.bands)
         self.max_halo = min_band
 
-    def balance(self, background_weight=0.05):
+    def balance(self, background_weight=0.05, refine=0, out_color_ptr=None):
         """Re-partition the rows by estimated cost (the scaling limiter of row sharding is load imbalance,
-        sky rows are cheap).  Call after ``pass.setScene(scene, W, H)`` (full frame) and before the first frame: every rank
-        runs K0 over the whole frame once, derives the same per-row cost from the feature buffer and takes its band.
-        Returns the band of this rank."""
+        sky rows are cheap).  Call after ``pass.setScene(scene, W, H)`` (full frame) and before the first frame.
+
+        1. Every rank runs K0 over the whole frame once and derives the same per-row cost from the feature buffer
+           (1 per pixel whose ray meets the medium, `background_weight` per background pixel) -> equal-cost bands.
+        2. `refine` times (off by default: the fixed launch latency of short bands makes it over-correct): two frames are rendered on the current bands, the ranks all-gather their device time per frame,
+           the model cost of every band is rescaled by its measured time and the rows are cut again (needs
+           `out_color_ptr`, a full-frame float4 device buffer).
+        The temporal history restarts afterwards.  Returns the band of this rank."""
         FEAT_DTYPE = np.dtype([("noReflectiveSurface", np.int32), ("transmittance", np.float32)])
-        if self.world > 1:
-            self.p.setRowBand(0, self.H)
-            self.p.execute_stage(0)
-            feat = self.p.get_buffer(capi.BUF_FEATURES).view(FEAT_DTYPE).reshape(self.H, self.W)
-            self.bands = balanced_row_bands(row_cost_from_features(feat, background_weight), self.world, min_rows=max(16, self.temporal_halo))
-            self.band = self.bands[self.rank]
-            self.max_halo = min(b[1] - b[0] for b in self.bands)
+        if self.world == 1:
+            return self.band
+        min_rows = max(16, self.temporal_halo)
+        self.p.setRowBand(0, self.H)
+        self.p.execute_stage(0)
+        feat = self.p.get_buffer(capi.BUF_FEATURES).view(FEAT_DTYPE).reshape(self.H, self.W)
+        cost = row_cost_from_features(feat, background_weight)
+
+        def apply(bands):
+            self.bands = bands
+            self.band = bands[self.rank]
+            self.max_halo = min(b[1] - b[0] for b in bands)
             self.p.setRowBand(*self.band)
             self.p.updateDict({})          # a fresh option-change epoch: frame counter and history restart
+
+        apply(balanced_row_bands(cost, self.world, min_rows=min_rows))
+        for _ in range(refine if out_color_ptr else 0):
+            for _f in range(2):
+                self.execute(out_color_ptr)
+            # compute time of this rank's band; the spatial stage's own event pair would include the wait for the neighbours' halo
+            tm = self.p.timings()
+            busy = tm["features_ms"] + tm["initial_ms"] + tm["temporal_ms"] + tm["final_ms"]
+            try:
+                mt = self.p.march_timings()
+                busy += mt["spatial_cam_ms"] + mt["spatial_light_ms"]
+            except capi.VRestirError:
+                busy += tm["spatial_ms"]
+            ms = torch.tensor([busy], dtype=torch.float64, device=self.device)
+            every = [torch.zeros_like(ms) for _ in range(self.world)]
+            dist.all_gather(every, ms)
+            for r, (a, b) in enumerate(self.bands):
+                s = cost[a:b].sum()
+                if s > 0:
+                    cost[a:b] *= float(every[r].item()) / s
+            apply(balanced_row_bands(cost, self.world, min_rows=min_rows))
         return self.band
 
     def _planes(self, buffer):
@@ -145,16 +182,16 @@ class ShardedPass:
                 out.append(device_view(base, n * (B - 1) * 12, self.device).view(self.H, self.W * (B - 1) * 12))
         return out
 
-    def _exchange(self, buffers, halo):
+    def _exchange(self, buffers, halo, wait=True):
         if self.world == 1:
-            return
+            return []
         halo = min(int(halo), self.max_halo)
         planes = []
         for b in buffers:
             planes += self._planes(b)
         # NCCL send/recv are ordered after the pass's kernels through torch's current stream (the pass launches on the same,
         # default, stream) and work.wait() only makes that stream wait: no host synchronisation
-        exchange_row_halo(planes, self.band, halo, self.rank, self.world)
+        return exchange_row_halo(planes, self.band, halo, self.rank, self.world, wait=wait)
 
     def execute(self, out_color_ptr, out_mvec_ptr=None, stream=None):
         p = self.p
@@ -166,6 +203,9 @@ class ShardedPass:
             return
         p.execute_stage(0, 0, out_color_ptr, out_mvec_ptr, stream)
         p.execute_stage(1, 0, out_color_ptr, out_mvec_ptr, stream)
+        for w in getattr(self, "_pending_history", []):   # the history halo of the previous frame travelled during K0/K1
+            w.wait()
+        self._pending_history = []
         p.execute_stage(2, 0, out_color_ptr, out_mvec_ptr, stream)
         if prm.mEnableSpatialReuse and not prm.mUseReference:
             for r in range(prm.mSpatialReuseRounds):
@@ -179,4 +219,4 @@ class ShardedPass:
         if prm.mEnableTemporalReuse and not prm.mUseReference:
             # history for the next frame's K2: reprojected taps land within `temporal_halo` rows of the band
             bufs = [capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL] + ([capi.BUF_EXTRA_TEMPORAL] if B > 1 else [])
-            self._exchange(bufs, self.temporal_halo)
+            self._pending_history = self._exchange(bufs, self.temporal_halo, wait=False)
