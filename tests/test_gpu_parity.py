@@ -223,7 +223,10 @@ def test_three_level_tree_full_reuse():
 def _frames_buffers(params, scene, w, h, wavefront, frames=3):
     """Run `frames` frames through the public execute() and return (image, final reservoirs) of the last one."""
     import torch
-    gp = VolumetricReSTIR.create({"mParams": params, "mUseWavefront": int(wavefront is not False), **({} if wavefront is True else {"mInitialMode": 0})})
+    d = {"mParams": params, "mUseWavefront": int(wavefront is not False), "mMarchPairEngine": int(wavefront == "pair")}
+    if wavefront == 0:
+        d["mInitialMode"] = 0
+    gp = VolumetricReSTIR.create(d)
     gp.setScene(scene, w, h)
     color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     for _ in range(frames):
@@ -251,7 +254,8 @@ def test_wavefront_equals_per_pixel(variant):
     sc = sc or env_scene()
     p = VolumetricReSTIRParams(**kw)
     img_s, res_s = _frames_buffers(p, sc, w, h, False)
-    for mode in (True, 0):   # True: default wavefront pipeline (lock-step K1); 0: wavefront K2/K3/K5 with the per-pixel K1
+    modes = (True, 0) + (("pair",) if variant == "three_level" else ())
+    for mode in modes:   # True: default wavefront pipeline (lock-step K1); 0: wavefront K2/K3/K5 with the per-pixel K1; "pair": phase-specialised march engine
         img_w, res_w = _frames_buffers(p, sc, w, h, mode)
         assert np.array_equal(res_w.view(np.uint32), res_s.view(np.uint32)), f"wavefront reservoirs (mode {mode}) differ from the per-pixel kernels"
         assert np.array_equal(img_w.view(np.uint32), img_s.view(np.uint32))
