@@ -394,6 +394,8 @@ int vrestir_make_blackbody_lut(float* out_128x4);
 
 /* GVDB .vbx reader (GV/src/gvdb_volume_gvdb.cpp:532-739): loads <dir>/<name>_mip<k>[c].vbx etc. into a scene */
 int vrestir_scene_load_vbx(const char* dir_and_prefix, int num_mips, const vrestir_scene_params* p, vrestir_scene** out);
+/* GVDB .vbx writer (GV/src/gvdb_volume_gvdb.cpp:1682-1831, version 1.12): one file per grid of the scene, same naming */
+int vrestir_scene_save_vbx(const vrestir_scene* scene, const char* dir_and_prefix);
 
 #ifdef __cplusplus
 }

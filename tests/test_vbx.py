@@ -1,0 +1,90 @@
+"""GVDB .vbx writer / reader: a scene saved as version-1.12 .vbx files and loaded back must give
+byte-identical grids (tree nodes, child lists, brick pools after the load-time UNORM8 quantisation, transforms, VolumeDesc).
+No reference test pins .vbx parsing and no .vbx asset is available offline (the 7.87 GB scene pack), so the pin is the
+round trip plus the structural checks of the file against GVDB_FILESPEC / VolumeGVDB::LoadVBX."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from volumetricrestirrelease_b200 import Scene, capi
+
+
+def _slot_bytes(g):
+    out = {}
+    for l in range(3):
+        n = g.node_count[l]
+        out[f"nodes{l}"] = bytes(C.string_at(g.nodes[l], n * 32)) if n and g.nodes[l] else b""
+        c = g.childlist_count[l]
+        out[f"child{l}"] = bytes(C.string_at(g.childlist[l], c * 4)) if c and g.childlist[l] else b""
+    bpv = 1 if g.atlas_format == 1 else 4
+    out["atlas"] = bytes(C.string_at(g.atlas, g.brick_count * g.atlas_channels * 1000 * bpv)) if g.brick_count else b""
+    return out
+
+
+SCALARS = ("valid", "top_lev", "max_value", "compress_scale", "atlas_format", "atlas_channels", "brick_count")
+ARRAYS = ("dim", "res", "vdel", "noderange", "bmin", "bmax", "xform", "invxform", "world_to_medium", "medium_to_world")
+
+
+@pytest.mark.parametrize("kind,dim,extra", [("bunny", (72, 64, 56), {}), ("bunny", (200, 150, 140), {}),
+                                            ("plume", (48, 64, 48), dict(hasVelocity=True, hasEmission=True))])
+def test_vbx_round_trip(tmp_path, kind, dim, extra):
+    sc = Scene()
+    kw = dict(sigma_a=(1, 2, 3), sigma_s=(9, 8, 7), g=0.3, numMips=3, densityScale=0.4, worldTranslation=(1.0, -2.0, 0.5), worldScaling=1.5)
+    sc.addGVDBVolume(dataFile=kind, dim=dim, seed=5, voxelSize=0.25, **kw, **extra)
+    prefix = os.path.join(str(tmp_path), "vol", "vol")
+    os.makedirs(os.path.dirname(prefix))
+    sc.volume.save_vbx(prefix)
+    files = sorted(os.listdir(os.path.dirname(prefix)))
+    assert "vol_mip0.vbx" in files and "vol_mip0c.vbx" in files and "vol_mip2c.vbx" in files
+    if extra:
+        assert {"vol_temperature.vbx", "vol_velocity_x.vbx", "vol_velocity_y.vbx", "vol_velocity_z.vbx"} <= set(files)
+    # header of the reference's custom version: 1.12, then 12 floats of transform, 32 floats xform / inverse, bounds, range, 1 grid
+    raw = open(prefix + "_mip0.vbx", "rb").read(2 + 48 + 128 + 24 + 8 + 4)
+    assert raw[0] == 1 and raw[1] == 12
+    assert struct.unpack_from("<i", raw, 2 + 48 + 128 + 24 + 8)[0] == 1
+    vmax = struct.unpack_from("<3i", raw, 2 + 48 + 128 + 12)
+    assert tuple(vmax) == tuple(dim)
+
+    sc2 = Scene()
+    sc2.loadGVDBVolume(prefix, **kw)
+    a, b = sc.volume.grid.contents, sc2.volume.grid.contents
+    for name, _ in capi.VolumeDesc._fields_:
+        va, vb = getattr(a.volume, name), getattr(b.volume, name)
+        va = list(va) if hasattr(va, "__len__") else va
+        vb = list(vb) if hasattr(vb, "__len__") else vb
+        assert va == vb, name
+    for slot in range(capi.MAX_SLOTS):
+        ga, gb = a.slots[slot], b.slots[slot]
+        assert ga.valid == gb.valid, slot
+        if not ga.valid:
+            continue
+        for f in SCALARS:
+            assert getattr(ga, f) == getattr(gb, f), (slot, f)
+        for f in ARRAYS:
+            top = ga.top_lev + 1
+            la, lb = list(getattr(ga, f)), list(getattr(gb, f))
+            if f in ("dim", "res", "vdel", "noderange"):
+                la, lb = la[:top], lb[:top]
+            if f in ("world_to_medium", "medium_to_world"):
+                # derived from the fp32 xform stored in the file (the builder multiplies in double before rounding): 1 ulp
+                np.testing.assert_allclose(la, lb, rtol=3e-7, atol=1e-7, err_msg=str((slot, f)))
+            else:
+                assert la == lb, (slot, f)
+        for l in range(3):
+            assert ga.node_count[l] == gb.node_count[l] and ga.childlist_count[l] == gb.childlist_count[l], (slot, l)
+        sa, sb = _slot_bytes(ga), _slot_bytes(gb)
+        for k in sa:
+            assert sa[k] == sb[k], (slot, k)
+
+
+def test_vbx_errors(tmp_path):
+    sc = Scene()
+    with pytest.raises(capi.VRestirError):
+        sc.loadGVDBVolume(os.path.join(str(tmp_path), "missing"))
+    bad = os.path.join(str(tmp_path), "bad_mip0.vbx")
+    open(bad, "wb").write(b"\x01\x0b" + b"\0" * 100)      # version 1.11: no xform block
+    with pytest.raises(capi.VRestirError):
+        sc.loadGVDBVolume(os.path.join(str(tmp_path), "bad"))

@@ -140,7 +140,7 @@ SYMBOLS = [
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
     "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
     "vrestir_scene_grid", "vrestir_scene_dense_mip", "vrestir_scene_stats", "vrestir_camera_look_at",
-    "vrestir_make_sky_envmap", "vrestir_make_emissive_shell", "vrestir_make_blackbody_lut", "vrestir_scene_load_vbx",
+    "vrestir_make_sky_envmap", "vrestir_make_emissive_shell", "vrestir_make_blackbody_lut", "vrestir_scene_load_vbx", "vrestir_scene_save_vbx",
 ]
 
 _lib = None
@@ -204,6 +204,7 @@ def lib():
                                               C.POINTER(EmissiveTriangle)]
     L.vrestir_make_blackbody_lut.argtypes = [vp]
     L.vrestir_scene_load_vbx.argtypes = [C.c_char_p, C.c_int, C.POINTER(SceneParams), C.POINTER(vp)]
+    L.vrestir_scene_save_vbx.argtypes = [vp, C.c_char_p]
     _lib = L
     return L
 

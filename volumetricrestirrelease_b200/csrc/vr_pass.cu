@@ -1066,8 +1066,4 @@ int vrestir_debug_long_rays(vrestir_pass* p, float* out64x8, uint32_t* count) {
     return VRESTIR_OK;
 }
 
-int vrestir_scene_load_vbx(const char*, int, const vrestir_scene_params*, vrestir_scene**) {
-    return setError(VRESTIR_ERR_UNSUPPORTED, ".vbx loading is not implemented yet (SURVEY.md 8f rank 1)");
-}
-
 }  // extern "C"

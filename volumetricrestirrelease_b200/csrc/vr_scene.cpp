@@ -15,8 +15,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <string>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -587,6 +590,376 @@ int vrestir_make_blackbody_lut(float* out) {
         for (int c = 0; c < 3; c++) mx = std::max(mx, rgb[i][c]);
     }
     for (int i = 0; i < 128; i++) { for (int c = 0; c < 3; c++) out[i * 4 + c] = (float)(rgb[i][c] / mx); out[i * 4 + 3] = 0.f; }
+    return VRESTIR_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ .vbx files
+// GVDB .vbx reader / writer.  File layout: gvdb-voxel-src/GVDB_FILESPEC.txt as actually read by
+// VolumeGVDB::LoadVBX (GV/src/gvdb_volume_gvdb.cpp:532-739) and written by SaveVBX (:1682-1831): version 1.12 (the
+// reference's custom minor version carrying xform, inverse, effective voxel bounds and value range, :596-605), one grid,
+// dtype 'f', 1 component, no compression, topology type 2, atlas layout, 64-byte nvdb::Node rows (GV/src/gvdb_node.h),
+// 8-byte child ids grp | lev << 8 | ndx << 16 (GV/src/gvdb_allocator.h:73-76), one float atlas with a 1-voxel apron.
+// File naming: <dir>/<name>_mip<k>[c].vbx, <name>_temperature.vbx, <name>_velocity_{x,y,z}.vbx (F/Scene/Scene.cpp:2806-2815).
+// Loading repacks exactly like F/Scene/Scene.cpp:2932-3056 (32-byte nodes, 4-byte child ids) into the brick-pool layout;
+// coarse / conservative mips are quantised to UNORM8 at load like F/Scene/Scene.cpp:3139-3240 (ATLAS_COMPRESSION == 1).
+namespace {
+
+#pragma pack(push, 1)
+struct VbxNode {   // nvdb::Node, 64 bytes
+    uint8_t lev, flags, priority, pad;
+    int32_t pos[3];
+    int32_t value[3];
+    float vrange[3];
+    uint64_t parent, childList, mask;
+};
+#pragma pack(pop)
+static_assert(sizeof(VbxNode) == 64, "nvdb::Node is 64 bytes");
+
+inline uint64_t vbxElem(unsigned grp, unsigned lev, uint64_t ndx) { return (uint64_t)grp | ((uint64_t)lev << 8) | (ndx << 16); }
+const uint64_t kVbxUndef = 0xFFFFFFFFFFFFFFFFull;
+
+struct File {
+    FILE* f = nullptr;
+    ~File() { if (f) fclose(f); }
+    template <class T> bool rd(T* v, size_t n = 1) { return fread(v, sizeof(T), n, f) == n; }
+    template <class T> bool wr(const T* v, size_t n = 1) { return fwrite(v, sizeof(T), n, f) == n; }
+};
+
+float slotVoxel(const vrestir_grid_slot& g, uint32_t brick, int ch, int x, int y, int z) {   // x,y,z in [-1, 8]
+    const size_t idx = ((size_t)brick * g.atlas_channels + ch) * VRESTIR_BRICK_VOXELS + (size_t)((z + 1) * 10 + (y + 1)) * 10 + (x + 1);
+    if (g.atlas_format == VRESTIR_ATLAS_UNORM8) return (float)((const uint8_t*)g.atlas)[idx] * 0.003921568859368563f * g.compress_scale;
+    return ((const float*)g.atlas)[idx];
+}
+
+int saveSlotVbx(const vrestir_grid_slot& g, int channel, const std::string& path) {
+    File fp; fp.f = fopen(path.c_str(), "wb");
+    if (!fp.f) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "cannot open " + path + " for writing");
+    const uint8_t major = 1, minor = 12;
+    const float zero3[3] = {0, 0, 0}, one3[3] = {1, 1, 1};
+    fp.wr(&major); fp.wr(&minor);
+    fp.wr(zero3, 3); fp.wr(zero3, 3); fp.wr(one3, 3); fp.wr(zero3, 3);      // pretranslation, Euler angles, scale, translation
+    fp.wr(g.xform, 16); fp.wr(g.invxform, 16);
+    int32_t vmin[3], vmax[3];
+    for (int i = 0; i < 3; i++) { vmin[i] = (int32_t)g.bmin[i]; vmax[i] = (int32_t)g.bmax[i]; }
+    fp.wr(vmin, 3); fp.wr(vmax, 3);
+    const float valMin = 0.f, valMax = g.max_value;
+    fp.wr(&valMin); fp.wr(&valMax);
+    const int32_t numGrids = 1; fp.wr(&numGrids);
+    const long gridTable = ftell(fp.f);
+    uint64_t gridOff = 0; fp.wr(&gridOff);
+    gridOff = (uint64_t)ftell(fp.f);
+    char name[256]; memset(name, 0, sizeof(name)); snprintf(name, sizeof(name), "density");
+    fp.wr(name, 256);
+    const uint8_t dtype = 'f', comps = 1, compress = 0, topo = 2, layout = 0;
+    fp.wr(&dtype); fp.wr(&comps); fp.wr(&compress);
+    fp.wr(one3, 3);
+    const int32_t leafcnt = (int32_t)g.brick_count, leafdim[3] = {8, 8, 8}, apron = 1, numChan = 1;
+    int32_t ac = 1; while ((int64_t)ac * ac * ac < leafcnt) ac++;
+    const int32_t axiscnt[3] = {ac, ac, ac}, axisres[3] = {ac * 10, ac * 10, ac * 10};
+    const uint64_t atlasSz = (uint64_t)axisres[0] * axisres[1] * axisres[2] * 4;
+    const int32_t reuse = 0;
+    fp.wr(&leafcnt); fp.wr(leafdim, 3); fp.wr(&apron); fp.wr(&numChan); fp.wr(&atlasSz); fp.wr(&topo); fp.wr(&reuse); fp.wr(&layout);
+    fp.wr(axiscnt, 3); fp.wr(axisres, 3);
+    const int32_t levels = g.top_lev + 1;
+    const uint64_t root = vbxElem(0, (unsigned)g.top_lev, 0);
+    fp.wr(&levels); fp.wr(&root);
+    for (int n = 0; n < levels; n++) {
+        const int32_t ld = g.dim[n], res = g.res[n], range[3] = {g.noderange[n], g.noderange[n], g.noderange[n]};
+        const int32_t cnt0 = (int32_t)g.node_count[n], w0 = 64, cnt1 = n == 0 ? 0 : (int32_t)g.node_count[n], w1 = n == 0 ? 0 : res * res * res * 8;
+        fp.wr(&ld); fp.wr(&res); fp.wr(range, 3); fp.wr(&cnt0); fp.wr(&w0); fp.wr(&cnt1); fp.wr(&w1);
+    }
+    // parents: one pass over the child lists
+    std::vector<uint64_t> parent[3];
+    for (int n = 0; n < levels; n++) parent[n].assign(g.node_count[n], kVbxUndef);
+    for (int n = 1; n < levels; n++) {
+        const size_t r3 = (size_t)g.res[n] * g.res[n] * g.res[n];
+        for (uint32_t i = 0; i < g.node_count[n]; i++)
+            for (size_t b = 0; b < r3; b++) {
+                const uint32_t c = g.childlist[n][(size_t)g.nodes[n][i].link * r3 + b];
+                if (c != 0xFFFFFFFFu && c < g.node_count[n - 1]) parent[n - 1][c] = vbxElem(0, (unsigned)n, i);
+            }
+    }
+    for (int n = 0; n < levels; n++)
+        for (uint32_t i = 0; i < g.node_count[n]; i++) {
+            const vrestir_node& s = g.nodes[n][i];
+            VbxNode o; memset(&o, 0, sizeof(o));
+            o.lev = (uint8_t)n; o.flags = 1;
+            for (int k = 0; k < 3; k++) { o.pos[k] = s.pos[k]; o.value[k] = -1; o.vrange[k] = s.bounds[k]; }
+            if (n == 0) {
+                const int32_t b = (int32_t)s.link;
+                o.value[0] = (b % ac) * 10 + 1; o.value[1] = ((b / ac) % ac) * 10 + 1; o.value[2] = (b / (ac * ac)) * 10 + 1;
+                o.childList = kVbxUndef;
+            } else o.childList = vbxElem(1, (unsigned)n, s.link);
+            o.parent = parent[n][i];
+            fp.wr(&o);
+        }
+    for (int n = 1; n < levels; n++) {
+        const size_t r3 = (size_t)g.res[n] * g.res[n] * g.res[n];
+        std::vector<uint64_t> row(r3);
+        // rows are indexed by the list id (= node.link); the builder uses link == node index
+        for (uint32_t i = 0; i < g.node_count[n]; i++) {
+            for (size_t b = 0; b < r3; b++) {
+                const uint32_t c = g.childlist[n][(size_t)i * r3 + b];
+                row[b] = c == 0xFFFFFFFFu ? kVbxUndef : vbxElem(0, (unsigned)(n - 1), c);
+            }
+            fp.wr(row.data(), r3);
+        }
+    }
+    const int32_t chanType = 3 /* T_FLOAT */, chanStride = 4;
+    fp.wr(&chanType); fp.wr(&chanStride);
+    std::vector<float> slice((size_t)axisres[0] * axisres[1]);
+    for (int z = 0; z < axisres[2]; z++) {
+        std::fill(slice.begin(), slice.end(), 0.f);
+        const int cz = z / 10, lz = z % 10 - 1;
+        for (int cy = 0; cy < ac; cy++) for (int cx = 0; cx < ac; cx++) {
+            const int64_t b = ((int64_t)cz * ac + cy) * ac + cx;
+            if (b >= leafcnt) continue;
+            for (int ly = -1; ly <= 8; ly++) for (int lx = -1; lx <= 8; lx++)
+                slice[(size_t)(cy * 10 + ly + 1) * axisres[0] + (cx * 10 + lx + 1)] = slotVoxel(g, (uint32_t)b, channel, lx, ly, lz);
+        }
+        if (!fp.wr(slice.data(), slice.size())) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "short write to " + path);
+    }
+    fseek(fp.f, gridTable, SEEK_SET);
+    fp.wr(&gridOff);
+    return VRESTIR_OK;
+}
+
+struct LoadedVbx {
+    BuiltSlot built; vrestir_grid_slot g{};
+    std::vector<float> voxels;   // [brick][10*10*10] floats
+};
+
+int loadSlotVbx(const std::string& path, LoadedVbx& L) {
+    File fp; fp.f = fopen(path.c_str(), "rb");
+    if (!fp.f) return VRESTIR_ERR_NOT_READY;   // caller decides whether the file is optional
+    auto bad = [&](const char* why) { return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, path + ": " + why); };
+    uint8_t major = 0, minor = 0;
+    if (!fp.rd(&major) || !fp.rd(&minor)) return bad("truncated header");
+    float xf[16], ixf[16]; int32_t vmin[3] = {0, 0, 0}, vmax[3] = {0, 0, 0}; float valMin = 0.f, valMax = 1.f;
+    bool haveX = false;
+    if ((major == 1 && minor >= 11) || major > 1) { float skip[12]; if (!fp.rd(skip, 12)) return bad("truncated transform"); }
+    if (minor == 12) { if (!fp.rd(xf, 16) || !fp.rd(ixf, 16) || !fp.rd(vmin, 3) || !fp.rd(vmax, 3) || !fp.rd(&valMin) || !fp.rd(&valMax)) return bad("truncated 1.12 block"); haveX = true; }
+    if (!haveX) return bad("only the reference's version 1.12 files (with xform / effective bounds) are supported");
+    int32_t numGrids = 0; if (!fp.rd(&numGrids) || numGrids < 1) return bad("no grids");
+    if (major >= 2) { uint8_t masks; fp.rd(&masks); if (masks) return bad("bitmask topologies are not supported"); }
+    std::vector<uint64_t> offs(numGrids); if (!fp.rd(offs.data(), offs.size())) return bad("truncated grid table");
+    if (fseek(fp.f, (long)offs[0], SEEK_SET) != 0) return bad("bad grid offset");
+    char name[256]; uint8_t dtype, comps, compress, topo, layout; float vs[3];
+    int32_t leafcnt, leafdim[3], apron, numChan, reuse, axiscnt[3], axisres[3]; uint64_t atlasSz;
+    if (!fp.rd(name, 256) || !fp.rd(&dtype) || !fp.rd(&comps) || !fp.rd(&compress) || !fp.rd(vs, 3) || !fp.rd(&leafcnt) || !fp.rd(leafdim, 3) || !fp.rd(&apron) ||
+        !fp.rd(&numChan) || !fp.rd(&atlasSz) || !fp.rd(&topo) || !fp.rd(&reuse) || !fp.rd(&layout) || !fp.rd(axiscnt, 3) || !fp.rd(axisres, 3)) return bad("truncated grid header");
+    if (dtype != 'f' || comps != 1 || compress != 0 || topo != 2 || layout != 0) return bad("only float / 1 component / uncompressed / GVDB topology / atlas layout is supported");
+    if (leafdim[0] != 8 || leafdim[1] != 8 || leafdim[2] != 8 || apron != 1) return bad("only 8^3 bricks with a 1-voxel apron are supported");
+    int32_t levels = 0; uint64_t root = 0;
+    if (!fp.rd(&levels) || !fp.rd(&root) || levels < 2 || levels > 3) return bad("only 2- or 3-level trees (5-4-3 configuration) are supported");
+    int32_t ld[3], res[3], range[3][3], cnt0[3], w0[3], cnt1[3], w1[3];
+    for (int n = 0; n < levels; n++)
+        if (!fp.rd(&ld[n]) || !fp.rd(&res[n]) || !fp.rd(range[n], 3) || !fp.rd(&cnt0[n]) || !fp.rd(&w0[n]) || !fp.rd(&cnt1[n]) || !fp.rd(&w1[n])) return bad("truncated level table");
+    static const int wantLd[3] = {3, 4, 5};
+    for (int n = 0; n < levels; n++) if (ld[n] != wantLd[n] || res[n] != (1 << ld[n]) || w0[n] != 64) return bad("tree configuration is not <3,4,5> with 64-byte nodes");
+    if (cnt0[0] != leafcnt) return bad("atlas does not hold every brick");
+    vrestir_grid_slot& g = L.g; g = vrestir_grid_slot{};
+    BuiltSlot& B = L.built;
+    std::vector<VbxNode> raw[3];
+    for (int n = 0; n < levels; n++) { raw[n].resize(cnt0[n]); if (cnt0[n] && !fp.rd(raw[n].data(), raw[n].size())) return bad("truncated node pool"); }
+    for (int n = 0; n < levels; n++) {
+        const size_t r3 = (size_t)res[n] * res[n] * res[n];
+        if (n == 0) { if (cnt1[0] * (int64_t)w1[0] != 0) fseek(fp.f, (long)((int64_t)cnt1[0] * w1[0]), SEEK_CUR); continue; }
+        if ((size_t)w1[n] != r3 * 8) return bad("child-list width does not match res^3");
+        std::vector<uint64_t> rows((size_t)cnt1[n] * r3);
+        if (!rows.empty() && !fp.rd(rows.data(), rows.size())) return bad("truncated child lists");
+        B.child[n].resize(rows.size());
+        for (size_t i = 0; i < rows.size(); i++) B.child[n][i] = (uint32_t)(((rows[i] >> 32) & 0xFFFFull) << 16) | (uint32_t)((rows[i] >> 16) & 0xFFFFull);   // F/Scene/Scene.cpp:3037
+    }
+    int32_t chanType, chanStride;
+    if (!fp.rd(&chanType) || !fp.rd(&chanStride) || chanStride != 4) return bad("atlas channel is not 4-byte float");
+    std::vector<float> atlas((size_t)axisres[0] * axisres[1] * axisres[2]);
+    if (!atlas.empty() && !fp.rd(atlas.data(), atlas.size())) return bad("truncated atlas");
+    // repack (F/Scene/Scene.cpp:2932-3056)
+    g.valid = 1; g.top_lev = 1;
+    for (int n = 0; n < levels; n++) {
+        g.dim[n] = ld[n]; g.res[n] = res[n]; g.noderange[n] = range[n][0]; g.vdel[n] = (float)range[n][0] / (float)res[n];
+        if (cnt0[n] == 1) g.top_lev = n;
+        B.nodes[n].resize(cnt0[n]);
+        for (int i = 0; i < cnt0[n]; i++) {
+            vrestir_node& o = B.nodes[n][i]; const VbxNode& s = raw[n][i];
+            for (int k = 0; k < 3; k++) o.pos[k] = s.pos[k];
+            o.bounds[0] = o.bounds[1] = o.bounds[2] = o.bounds[3] = 0.f;
+            if (n == 0) o.link = (uint32_t)i;   // brick pool order = leaf order
+            else o.link = (uint32_t)(((s.childList >> 32) & 0xFFFFull) << 16) | (uint32_t)((s.childList >> 16) & 0xFFFFull);
+        }
+    }
+    if (levels == 2) { g.dim[2] = 5; g.res[2] = 32; g.vdel[2] = 128.f; g.noderange[2] = 4096; }
+    L.voxels.assign((size_t)leafcnt * VRESTIR_BRICK_VOXELS, 0.f);
+    for (int b = 0; b < leafcnt; b++) {
+        const VbxNode& s = raw[0][b];
+        for (int z = -1; z <= 8; z++) for (int y = -1; y <= 8; y++) for (int x = -1; x <= 8; x++) {
+            const int ax = s.value[0] + x, ay = s.value[1] + y, az = s.value[2] + z;
+            if (ax < 0 || ay < 0 || az < 0 || ax >= axisres[0] || ay >= axisres[1] || az >= axisres[2]) return bad("brick lies outside the atlas");
+            L.voxels[(size_t)b * VRESTIR_BRICK_VOXELS + (size_t)((z + 1) * 10 + (y + 1)) * 10 + (x + 1)] = atlas[((size_t)az * axisres[1] + ay) * axisres[0] + ax];
+        }
+    }
+    for (int i = 0; i < 3; i++) { g.bmin[i] = (float)vmin[i]; g.bmax[i] = (float)vmax[i]; }
+    memcpy(g.xform, xf, 64); memcpy(g.invxform, ixf, 64);
+    g.max_value = valMax; g.brick_count = (uint32_t)leafcnt;
+    return VRESTIR_OK;
+}
+
+// quantise / store the voxels of a loaded grid, brick bounds as in F/Scene/Scene.cpp:2981-3012
+void finishLoadedSlot(LoadedVbx& L, int format, bool conservative, int channels, const std::vector<float>* extra1, const std::vector<float>* extra2) {
+    vrestir_grid_slot& g = L.g; BuiltSlot& B = L.built;
+    const float maxv = g.max_value > 0.f ? g.max_value : 1.f;
+    const size_t bpv = format == VRESTIR_ATLAS_UNORM8 ? 1 : 4;
+    B.atlas.assign((size_t)g.brick_count * channels * VRESTIR_BRICK_VOXELS * bpv, 0);
+    const std::vector<float>* src[3] = {&L.voxels, extra1, extra2};
+    for (uint32_t b = 0; b < g.brick_count; b++) {
+        for (int c = 0; c < channels; c++)
+            for (int i = 0; i < VRESTIR_BRICK_VOXELS; i++) {
+                float v = (*src[c])[(size_t)b * VRESTIR_BRICK_VOXELS + i];
+                if (v / maxv < 1e-9f && v >= 0.f) v = 0.f;
+                const size_t idx = ((size_t)b * channels + c) * VRESTIR_BRICK_VOXELS + i;
+                if (format == VRESTIR_ATLAS_UNORM8) {
+                    int q = (int)std::lround(255.0 * (double)(v / maxv));
+                    q = std::max(0, std::min(255, q));
+                    if (q == 0 && v > 0.f && conservative) q = 1;
+                    B.atlas[idx] = (uint8_t)q;
+                } else memcpy(&B.atlas[idx * 4], &v, 4);
+            }
+        float mn = 3.402823466e+38f, mx = 0.f, sum = 0.f;
+        const size_t base = (size_t)b * channels * VRESTIR_BRICK_VOXELS;
+        for (int i = -1; i <= 8; i++) for (int j = -1; j <= 8; j++) for (int k = -1; k <= 8; k++) {
+            const size_t idx = base + (size_t)((k + 1) * 10 + (j + 1)) * 10 + (i + 1);
+            float d;
+            if (format == VRESTIR_ATLAS_UNORM8) d = (float)B.atlas[idx] * 0.003921568859368563f * maxv; else memcpy(&d, &B.atlas[idx * 4], 4);
+            mn = std::min(mn, d); mx = std::max(mx, d); sum += d;
+        }
+        vrestir_node& n = B.nodes[0][b];
+        n.bounds[0] = mn; n.bounds[1] = mx; n.bounds[2] = sum / 512.f; n.bounds[3] = 0.f;
+    }
+    for (int l = 0; l < 3; l++) {
+        g.node_count[l] = (uint32_t)B.nodes[l].size(); g.nodes[l] = B.nodes[l].empty() ? nullptr : B.nodes[l].data();
+        g.childlist[l] = B.child[l].empty() ? nullptr : B.child[l].data(); g.childlist_count[l] = B.child[l].size();
+    }
+    g.compress_scale = format == VRESTIR_ATLAS_UNORM8 ? maxv : 1.f;
+    g.atlas_format = format; g.atlas_channels = channels; g.atlas = B.atlas.data();
+    B.used = true;
+}
+
+void externalTransforms(vrestir_scene& s, int slot) {   // VR/VolumeBase.slang:103-130 with the script's world translation / scaling
+    const vrestir_scene_params& p = s.params;
+    double X[16], Xi[16], E[16], Ei[16], M[16];
+    vrestir_grid_slot& g = s.desc.slots[slot];
+    for (int i = 0; i < 16; i++) { X[i] = g.xform[i]; Xi[i] = g.invxform[i]; }
+    mat4Identity(E); mat4Identity(Ei);
+    for (int a = 0; a < 3; a++) { E[a * 5] = p.world_scaling; E[12 + a] = p.world_translation[a]; Ei[a * 5] = 1.0 / p.world_scaling; Ei[12 + a] = -p.world_translation[a] / p.world_scaling; }
+    mat4Mul(X, E, M); toF(M, g.medium_to_world);
+    mat4Mul(Ei, Xi, M); toF(M, g.world_to_medium);
+    if (slot == 0) { toF(E, s.desc.volume.externalModelToWorld); toF(Ei, s.desc.volume.externalWorldToModel); }
+}
+
+}  // namespace
+
+extern "C" {
+
+int vrestir_scene_save_vbx(const vrestir_scene* s, const char* dir_and_prefix) {
+    if (!s || !dir_and_prefix) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    const std::string base(dir_and_prefix);
+    for (int m = 0; m < VRESTIR_NUM_MAX_MIPS; m++)
+        for (int c = 0; c < 2; c++) {
+            const vrestir_grid_slot& g = s->desc.slots[m + c * VRESTIR_NUM_MAX_MIPS];
+            if (!g.valid) continue;
+            int rc = saveSlotVbx(g, 0, base + "_mip" + std::to_string(m) + (c ? "c" : "") + ".vbx");
+            if (rc) return rc;
+        }
+    const vrestir_grid_slot& T = s->desc.slots[VRESTIR_TEMPERATURE_GRID_ID];
+    if (T.valid) { int rc = saveSlotVbx(T, 0, base + "_temperature.vbx"); if (rc) return rc; }
+    const vrestir_grid_slot& V = s->desc.slots[VRESTIR_VELOCITY_GRID_ID];
+    if (V.valid) for (int c = 0; c < 3; c++) { int rc = saveSlotVbx(V, c, base + "_velocity_" + "xyz"[c] + ".vbx"); if (rc) return rc; }
+    return VRESTIR_OK;
+}
+
+int vrestir_scene_load_vbx(const char* dir_and_prefix, int num_mips, const vrestir_scene_params* p, vrestir_scene** out) {
+    if (!dir_and_prefix || !p || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    const std::string base(dir_and_prefix);
+    std::unique_ptr<vrestir_scene> s(new vrestir_scene());
+    s->params = *p;
+    const int numMips = std::max(1, std::min(VRESTIR_NUM_MAX_MIPS, num_mips));
+    int built = 0;
+    for (int m = 0; m < numMips; m++)
+        for (int c = 0; c < 2; c++) {
+            LoadedVbx L;
+            const std::string path = base + "_mip" + std::to_string(m) + (c ? "c" : "") + ".vbx";
+            int rc = loadSlotVbx(path, L);
+            if (rc == VRESTIR_ERR_NOT_READY) {
+                if (m == 0 && c == 0) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "cannot open " + path);
+                continue;
+            }
+            if (rc) return rc;
+            const int slot = m + c * VRESTIR_NUM_MAX_MIPS;
+            finishLoadedSlot(L, (m == 0 && c == 0) ? VRESTIR_ATLAS_F32 : VRESTIR_ATLAS_UNORM8, c == 1, 1, nullptr, nullptr);
+            s->slots[slot] = std::move(L.built);
+            s->desc.slots[slot] = L.g;
+            // pointers into the moved vectors
+            vrestir_grid_slot& g = s->desc.slots[slot]; BuiltSlot& B = s->slots[slot];
+            for (int l = 0; l < 3; l++) { g.nodes[l] = B.nodes[l].empty() ? nullptr : B.nodes[l].data(); g.childlist[l] = B.child[l].empty() ? nullptr : B.child[l].data(); }
+            g.atlas = B.atlas.data();
+            externalTransforms(*s, slot);
+            if (c == 0) built = m + 1;
+        }
+    bool haveT = false, haveV = false;
+    {
+        LoadedVbx L;
+        int rc = loadSlotVbx(base + "_temperature.vbx", L);
+        if (rc == VRESTIR_OK) {
+            finishLoadedSlot(L, VRESTIR_ATLAS_F32, false, 1, nullptr, nullptr);
+            const int slot = VRESTIR_TEMPERATURE_GRID_ID;
+            s->slots[slot] = std::move(L.built); s->desc.slots[slot] = L.g;
+            vrestir_grid_slot& g = s->desc.slots[slot]; BuiltSlot& B = s->slots[slot];
+            for (int l = 0; l < 3; l++) { g.nodes[l] = B.nodes[l].empty() ? nullptr : B.nodes[l].data(); g.childlist[l] = B.child[l].empty() ? nullptr : B.child[l].data(); }
+            g.atlas = B.atlas.data();
+            externalTransforms(*s, slot);
+            haveT = true;
+        } else if (rc != VRESTIR_ERR_NOT_READY) return rc;
+    }
+    {
+        LoadedVbx Lx, Ly, Lz;
+        int rx = loadSlotVbx(base + "_velocity_x.vbx", Lx);
+        if (rx == VRESTIR_OK) {
+            int ry = loadSlotVbx(base + "_velocity_y.vbx", Ly), rz = loadSlotVbx(base + "_velocity_z.vbx", Lz);
+            if (ry || rz) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "velocity needs _velocity_x/_y/_z.vbx with one shared topology");
+            if (Ly.g.brick_count != Lx.g.brick_count || Lz.g.brick_count != Lx.g.brick_count) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "velocity components have different topologies");
+            Lx.g.max_value = std::max(Lx.g.max_value, std::max(Ly.g.max_value, Lz.g.max_value));
+            finishLoadedSlot(Lx, VRESTIR_ATLAS_F32, false, 3, &Ly.voxels, &Lz.voxels);   // zipped to RGB like F/Scene/Scene.cpp:3180-3240
+            const int slot = VRESTIR_VELOCITY_GRID_ID;
+            s->slots[slot] = std::move(Lx.built); s->desc.slots[slot] = Lx.g;
+            vrestir_grid_slot& g = s->desc.slots[slot]; BuiltSlot& B = s->slots[slot];
+            for (int l = 0; l < 3; l++) { g.nodes[l] = B.nodes[l].empty() ? nullptr : B.nodes[l].data(); g.childlist[l] = B.child[l].empty() ? nullptr : B.child[l].data(); }
+            g.atlas = B.atlas.data();
+            externalTransforms(*s, slot);
+            haveV = true;
+        } else if (rx != VRESTIR_ERR_NOT_READY) return rx;
+    }
+    // VolumeDesc (F/Scene/Scene.cpp:3246-3298)
+    vrestir_volume_desc& v = s->desc.volume;
+    for (int i = 0; i < 3; i++) { v.sigma_a[i] = p->sigma_a[i]; v.sigma_s[i] = p->sigma_s[i]; }
+    v.sigma_t = p->sigma_s[0] + p->sigma_a[0];
+    v.PhaseFunctionConstantG = p->g;
+    v.densityScaleFactor = p->density_scale;
+    v.densityScaleFactorByScaling = p->density_scale / p->world_scaling;
+    const float* X = s->desc.slots[0].xform;
+    auto len3 = [](const float* r) { return std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); };
+    v.tStep = (len3(X) + len3(X + 4) + len3(X + 8)) / 3.f;
+    v.hasEmission = haveT ? 1 : 0; v.hasVelocity = haveV ? 1 : 0; v.hasAnimation = 0; v.lastFrameHasEmission = 0;
+    v.LeScale = p->LeScale; v.temperatureCutOff = p->temperatureCutOff; v.temperatureScale = p->temperatureScale;
+    v.velocityScale = 1.f; v.numMips = built; v.usePrevGridForReproj = 0;
+    v.volumeWorldScaling = p->world_scaling;
+    v.superVoxelWorldSpaceDiagonalLength = 8.f * std::sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2] + X[4] * X[4] + X[5] * X[5] + X[6] * X[6] + X[8] * X[8] + X[9] * X[9] + X[10] * X[10]);
+    if (haveT) { s->lut.resize(512); vrestir_make_blackbody_lut(s->lut.data()); s->desc.blackbody_lut = s->lut.data(); }
+    for (int i = 0; i < 3; i++) s->params.dim[i] = (int)s->desc.slots[0].bmax[i];
+    s->params.num_mips = built;
+    *out = s.release();
     return VRESTIR_OK;
 }
 

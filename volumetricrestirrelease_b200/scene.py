@@ -60,6 +60,10 @@ class Volume:
         capi.check(capi.lib().vrestir_scene_dense_mip(self._h, mip, int(conservative), out.ctypes.data, C.byref(dim)))
         return out
 
+    def save_vbx(self, dir_and_prefix):
+        """Write every grid of the volume as GVDB .vbx files (<prefix>_mip<k>[c].vbx, _temperature.vbx, _velocity_{x,y,z}.vbx)."""
+        capi.check(capi.lib().vrestir_scene_save_vbx(self._h, str(dir_and_prefix).encode()))
+
     def close(self):
         if self._h:
             capi.lib().vrestir_scene_destroy(self._h)
@@ -135,6 +139,18 @@ class Scene:
                                worldTranslation, worldScaling, hasVelocity, hasEmission, LeScale, temperatureCutoff,
                                temperatureScale, frameTime)
             capi.check(capi.lib().vrestir_scene_create(C.byref(sp), C.byref(h)))
+        self.volume = Volume(h)
+        return self.volume
+
+    def loadGVDBVolume(self, dir_and_prefix, sigma_a=(1, 1, 1), sigma_s=(9, 9, 9), g=0.0, numMips=4, densityScale=1.0,
+                       LeScale=0.005, temperatureCutoff=1.0, temperatureScale=100.0, worldTranslation=(0, 0, 0),
+                       worldScaling=1.0):
+        """``m.addGVDBVolume(..., dataFile=<folder>/<name>, ...)`` for real assets: reads <prefix>_mip<k>[c].vbx (+ _temperature,
+        _velocity_{x,y,z}) like F/Scene/Scene.cpp:2806-2815 / GV/src/gvdb_volume_gvdb.cpp:532-739."""
+        sp = _scene_params(0, (8, 8, 8), numMips, 0, sigma_a, sigma_s, g, densityScale, 1.0, worldTranslation, worldScaling,
+                           False, False, LeScale, temperatureCutoff, temperatureScale, 0.0)
+        h = C.c_void_p()
+        capi.check(capi.lib().vrestir_scene_load_vbx(str(dir_and_prefix).encode(), int(numMips), C.byref(sp), C.byref(h)))
         self.volume = Volume(h)
         return self.volume
 
