@@ -231,7 +231,10 @@ VRD void wfEmitEval(bool want, const Reservoir& tap, float3 origin, float3 dir, 
     wfEmitRay(lightStream, hasLight, sh, lightMip, false, results, out + 2);
 }
 
-__global__ void __launch_bounds__(128) k_spatial_combine(FrameParams fp, WfBufs wf) {
+#ifndef VR_SCOMB_MINB
+#define VR_SCOMB_MINB 8
+#endif
+__global__ void __launch_bounds__(128, VR_SCOMB_MINB) k_spatial_combine(FrameParams fp, WfBufs wf) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     const int W = fp.W, S = fp.sampleCount;
@@ -378,7 +381,13 @@ enum { K1_SG = 20, K1_HD = 24, K1_RES = 36 };
 // MODE 0: s == 0 (traversal + first candidate), 1: 0 < s < M, 2: s == M (last candidate's finish + p-hat); separate
 // instantiations so that the light-weight middle steps do not carry the registers of the traversal / the p-hat marches
 template <int MODE>
-__global__ void __launch_bounds__(128, MODE == 1 ? 8 : 4) k_initial_step(FrameParams fp, WfInitial wi, int s) {
+#ifndef VR_STEP0_MINB
+#define VR_STEP0_MINB 5
+#endif
+#ifndef VR_STEP2_MINB
+#define VR_STEP2_MINB 8
+#endif
+__global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MINB : VR_STEP2_MINB)) k_initial_step(FrameParams fp, WfInitial wi, int s) {
     int x, y;
     const bool inFrame = pixelOf(fp, x, y);
     const int pixelId = inFrame ? y * fp.W + x : fp.rowBegin * fp.W;
@@ -470,7 +479,13 @@ VRD float3 prevRayDir(const FrameParams& fp, int px, int py) {
     return normalize(camRayDirNN(c_scene.prevU, c_scene.prevV, c_scene.prevW, px, py, fp.W, fp.H));
 }
 
-__global__ void __launch_bounds__(128) k_temporal_gather(FrameParams fp, WfBufs4 wf) {
+#ifndef VR_TGATHER_MINB
+#define VR_TGATHER_MINB 1
+#endif
+#ifndef VR_TCOMB_MINB
+#define VR_TCOMB_MINB 6
+#endif
+__global__ void __launch_bounds__(128, VR_TGATHER_MINB) k_temporal_gather(FrameParams fp, WfBufs4 wf) {
     int x, y;
     const bool inFrame = pixelOf(fp, x, y);
     const int W = fp.W, H = fp.H;
@@ -557,7 +572,7 @@ __global__ void __launch_bounds__(128) k_temporal_gather(FrameParams fp, WfBufs4
     wfEmitEval(wantE0, t0, c_scene.prevPos, dirPrev, true, wf.results, blkBase + T2_E0, wf.s[2], wf.mip[2], wf.s[3], wf.mip[3]);
 }
 
-__global__ void __launch_bounds__(128) k_temporal_combine(FrameParams fp, WfBufs4 wf) {
+__global__ void __launch_bounds__(128, VR_TCOMB_MINB) k_temporal_combine(FrameParams fp, WfBufs4 wf) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     const int W = fp.W;
