@@ -639,6 +639,8 @@ struct SampleMediumAnalyticAdapter : AdapterBase {
                 for (int s = 0; s < 4; s++) {
                     if (s >= numSamples) break;
                     if (hitDistances[s] == -1) {
+                        // an empty cell (sigma_t == 0) can never be hit: -log(1-u)/0 is +inf or NaN -> kRayTMax; only the draw counts
+                        if (sigma_t == 0.f) { (void)sg.next(); continue; }
                         float dT = -logf(1 - sampleNext1D(sg)) / sigma_t;
                         float curT = t + dT;
                         if (isnan(curT) || isinf(curT)) curT = kRayTMax;
@@ -918,8 +920,26 @@ VRD float impLoad(uint32_t x, uint32_t y, int mip) {
     if ((int)x >= dim || (int)y >= dim) return 0.f;
     return __ldg(&c_scene.importance[c_scene.impOffset[mip] + (size_t)y * dim + x]);
 }
+// Top of the importance mip chain (mips with dim <= 32: 32^2 + 16^2 + ... + 1 = 1365 floats) staged in shared memory by
+// kernels whose critical path is the 36-load dependent chain of the hierarchical warp (K1 step kernels).
+constexpr int IMP_TOP_DIM = 32, IMP_TOP_FLOATS = 1365;
+VRD void stageImportanceTop(float* smem) {   // every thread of the CTA calls; caller syncs
+    if (c_scene.impDim < IMP_TOP_DIM) return;
+    int first = 0; while ((c_scene.impDim >> first) > IMP_TOP_DIM) first++;
+    const unsigned base = c_scene.impOffset[first];
+    for (int i = threadIdx.x; i < IMP_TOP_FLOATS; i += blockDim.x) smem[i] = __ldg(&c_scene.importance[base + i]);
+}
+VRD float impLoadT(uint32_t x, uint32_t y, int mip, const float* impTop) {
+    const int dim = c_scene.impDim >> mip;
+    if ((int)x >= dim || (int)y >= dim) return 0.f;
+    if (impTop && dim <= IMP_TOP_DIM) {
+        int first = 0; while ((c_scene.impDim >> first) > IMP_TOP_DIM) first++;
+        return impTop[c_scene.impOffset[mip] - c_scene.impOffset[first] + (size_t)y * dim + x];
+    }
+    return __ldg(&c_scene.importance[c_scene.impOffset[mip] + (size_t)y * dim + x]);
+}
 struct EnvMapSample { float3 dir; float pdf; float3 Le; };
-VRD_NOINLINE void envSample(float2 rnd, EnvMapSample& result) {
+VRD_NOINLINE void envSample(float2 rnd, EnvMapSample& result, const float* impTop = nullptr) {
     float2 pp = rnd; uint32_t posx = 0, posy = 0;
     if (c_scene.envSamplerType == VRESTIR_ENV_SAMPLER_ALIAS && c_scene.envAliasCount) {
         const uint32_t count = c_scene.envAliasCount;
@@ -933,7 +953,7 @@ VRD_NOINLINE void envSample(float2 rnd, EnvMapSample& result) {
     } else {
         for (int mip = c_scene.impBaseMip - 1; mip >= 0; mip--) {
             posx *= 2; posy *= 2;
-            float w0 = impLoad(posx, posy, mip), w1 = impLoad(posx + 1, posy, mip), w2 = impLoad(posx, posy + 1, mip), w3 = impLoad(posx + 1, posy + 1, mip);
+            float w0 = impLoadT(posx, posy, mip, impTop), w1 = impLoadT(posx + 1, posy, mip, impTop), w2 = impLoadT(posx, posy + 1, mip, impTop), w3 = impLoadT(posx + 1, posy + 1, mip, impTop);
             float q0 = w0 + w2, q1 = w1 + w3;
             uint32_t offx, offy;
             float d = q0 / (q0 + q1);
@@ -946,7 +966,7 @@ VRD_NOINLINE void envSample(float2 rnd, EnvMapSample& result) {
     float invDim = 1.f / (float)c_scene.impDim;
     float2 uv = make_float2(((float)posx + pp.x) * invDim, ((float)posy + pp.y) * invDim);
     float3 dir = oct_to_ndir_equal_area_unorm(uv);
-    float avg_w = impLoad(0, 0, c_scene.impBaseMip);
+    float avg_w = impLoadT(0, 0, c_scene.impBaseMip, impTop);
     float pdf = impLoad(posx, posy, 0) / avg_w;
     result.dir = envToWorld(dir);
     result.pdf = pdf * k1_4Pi;
@@ -1033,7 +1053,8 @@ VRD bool emissiveSampleLight(float3 posW, SampleGenerator& sg, TriangleLightSamp
 }
 
 // VR/VolumeUtils.slang:12-149
-VRD_NOINLINE bool sampleSceneLights(float3 rayOrigin, bool kEnv, bool kAnalytic, bool kEmissive, SampleGenerator& sg, SceneLightSample& ls, int& outLightIndex, float2& outLightUV) {
+VRD_NOINLINE bool sampleSceneLights(float3 rayOrigin, bool kEnv, bool kAnalytic, bool kEmissive, SampleGenerator& sg, SceneLightSample& ls, int& outLightIndex, float2& outLightUV,
+                                    const float* impTop = nullptr) {
     ls.dir = f3(0.f); ls.distance = 0.f; ls.Li = f3(0.f); ls.pdf = 0.f; ls.pdfArea = 0.f; ls.rayDir = f3(0.f); ls.rayDistance = 0.f;
     if (!kEnv && !kAnalytic && !kEmissive) return false;
     float p0 = kEnv ? 1.f : 0.f, p1 = kAnalytic ? 1.f : 0.f, p2 = kEmissive ? 1.f : 0.f;
@@ -1045,7 +1066,7 @@ VRD_NOINLINE bool sampleSceneLights(float3 rayOrigin, bool kEnv, bool kAnalytic,
     if (kEnv) {
         if (u < p0) {
             EnvMapSample lightSample;
-            envSample(sampleNext2D(sg), lightSample);
+            envSample(sampleNext2D(sg), lightSample, impTop);
             float pdf = p0 * lightSample.pdf;
             ls.rayDir = ls.dir = lightSample.dir;
             ls.rayDistance = ls.distance = kRayTMax;

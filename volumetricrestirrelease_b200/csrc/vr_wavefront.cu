@@ -397,6 +397,9 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
     const int M = fp.initialM;
     bool hasTask = false;
     Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
+    __shared__ float impTop[IMP_TOP_FLOATS];
+    const bool stageImp = MODE != 2 && o.useEnvironmentLights && c_scene.haveEnv && c_scene.envSamplerType != VRESTIR_ENV_SAMPLER_ALIAS && c_scene.impDim >= IMP_TOP_DIM;
+    if (stageImp) { stageImportanceTop(impTop); __syncthreads(); }
     if (inFrame) {
         SampleGenerator sg;
         const Ray ray = primaryRay(fp, x, y);
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
                 c.lightID = -1;
                 if (c_scene.vol.hasEmission && c.density > 0.f) c.Le = EmissionWorldSpace(mi.p);
                 SceneLightSample ls;
-                const bool lvalid = sampleSceneLights(mi.p, o.useEnvironmentLights, o.useAnalyticLights, o.useEmissiveLights, sg, ls, c.lightID, c.lightUV);
+                const bool lvalid = sampleSceneLights(mi.p, o.useEnvironmentLights, o.useAnalyticLights, o.useEmissiveLights, sg, ls, c.lightID, c.lightUV, stageImp ? impTop : nullptr);
                 c.outLightPdf = lvalid ? ls.pdfArea : 0.f;
                 if (lvalid) {
                     c.flags |= 4u;
