@@ -402,12 +402,12 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                         if (p->wfInitialState) cudaFree(p->wfInitialState);
                         p->wfInitialState = nullptr; p->wfInitialPixels = 0;
                         if (n * K1_STRIDE >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit record indices; shard the frame");
-                        CK(cudaMalloc(&p->wfInitialState, n * K1_STRIDE * sizeof(float)));
+                        CK(cudaMalloc(&p->wfInitialState, n * K1_STRIDE * sizeof(float) + n));   // + one done flag per pixel
                         p->wfInitialPixels = n;
                     }
                     WfInitial wi;
                     wi.light.tasks = p->wfLightTasks; wi.light.count = p->wfCounters; wi.light.cursor = p->wfCounters + 1; wi.light.capacity = (unsigned)n;
-                    wi.state = p->wfInitialState;
+                    wi.state = p->wfInitialState; wi.done = (uint8_t*)(p->wfInitialState + n * K1_STRIDE);
                     fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
                     const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0};
                     for (int s = 0; s <= m.mInitialM; s++) {

@@ -400,19 +400,42 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
     __shared__ float impTop[IMP_TOP_FLOATS];
     const bool stageImp = MODE != 2 && o.useEnvironmentLights && c_scene.haveEnv && c_scene.envSamplerType != VRESTIR_ENV_SAMPLER_ALIAS && c_scene.impDim >= IMP_TOP_DIM;
     if (stageImp) { stageImportanceTop(impTop); __syncthreads(); }
-    if (inFrame) {
+    uint8_t* doneFlag = wi.done + (size_t)(pixelId - fp.rowBegin * fp.W);
+    // pixels whose four distance candidates all left the volume were finished by step 0 (no light sample, no march)
+    if (inFrame && (MODE == 0 || !*doneFlag)) {
         SampleGenerator sg;
         const Ray ray = primaryRay(fp, x, y);
         Reservoir finalReservoir = createNewReservoir();
         float hd = 0.f, pd = 0.f, ot = 0.f;
+        bool finishNow = false;
         if (MODE == 0) {
             sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
             float hds[4] = {0, 0, 0, 0}, pds[4] = {0, 0, 0, 0}, ots[4] = {0, 0, 0, 0};
             SampleMediumAnalyticGeneric(ray, sg, o.visibilityUseLinearSampler, hds, o.visibilityMipLevel, pds, ots, M);
-            ((float4*)(st + K1_HD))[0] = make_float4(hds[0], hds[1], hds[2], hds[3]);
-            ((float4*)(st + K1_HD))[1] = make_float4(pds[0], pds[1], pds[2], pds[3]);
-            ((float4*)(st + K1_HD))[2] = make_float4(ots[0], ots[1], ots[2], ots[3]);
             hd = hds[0]; pd = pds[0]; ot = ots[0];
+            bool allOut = true;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (k < M && hds[k] != kRayTMax) allOut = false;
+            if (allOut) {
+                // every candidate is a background candidate: its weight needs no march, so the whole candidate loop
+                // (VR/TraceRays.cs.slang:111-175) runs here and the pixel skips the lock-step kernels
+                const float3 LeBg = envEval(ray.dir);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k >= M) break;
+                    K1Cand c;
+                    c.flags = 0; c.hd = hds[k]; c.pd = pds[k]; c.ot = ots[k]; c.density = 0.f;
+                    c.Li = f3(0.f); c.ph = 0.f; c.outLightPdf = 0.f; c.Le = LeBg; c.lightID = 0; c.lightUV = make_float2(0, 0); c.uEm = 0.f; c.uWrs = 0.f;
+                    const Reservoir outReservoir = k1Finish(c, 1.f, fp);
+                    simpleResampleStep<1>(outReservoir, finalReservoir, sg);
+                }
+                finishNow = true;
+            } else {
+                ((float4*)(st + K1_HD))[0] = make_float4(hds[0], hds[1], hds[2], hds[3]);
+                ((float4*)(st + K1_HD))[1] = make_float4(pds[0], pds[1], pds[2], pds[3]);
+                ((float4*)(st + K1_HD))[2] = make_float4(ots[0], ots[1], ots[2], ots[3]);
+            }
+            *doneFlag = allOut ? 1 : 0;
         } else {
             const float4 g4 = ((const float4*)(st + K1_SG))[0];
             sg.s0 = __float_as_uint(g4.x); sg.s1 = __float_as_uint(g4.y); sg.s2 = __float_as_uint(g4.z); sg.s3 = __float_as_uint(g4.w);
@@ -426,7 +449,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
             simpleResampleStep<1>(outReservoir, finalReservoir, sg);
             if (MODE != 2) { hd = st[K1_HD + s]; pd = st[K1_HD + 4 + s]; ot = st[K1_HD + 8 + s]; }
         }
-        if (MODE != 2) {
+        if (MODE != 2 && !finishNow) {
             // candidate s up to its shadow march (VR/ComputeInitialSample.slang:60-284, bounce 0)
             K1Cand c;
             c.flags = 0; c.hd = hd; c.pd = pd; c.ot = ot; c.density = 0.f;
@@ -457,7 +480,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
             ((float4*)(st + K1_SG))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
             ((float4*)(st + K1_RES))[0] = make_float4(finalReservoir.runningSum, finalReservoir.M, finalReservoir.depth, finalReservoir.p_y);
             ((float4*)(st + K1_RES))[1] = make_float4(finalReservoir.lightUV.x, finalReservoir.lightUV.y, __int_as_float(finalReservoir.lightID), __int_as_float(finalReservoir.sampledPixel));
-        } else {
+        } else if (MODE == 2 || finishNow) {
             // VR/TraceRays.cs.slang:176-183: p-hat of the streamed reservoir under the spatial options (ray-marched: no draws)
             ExtraProvider prov; prov.global = nullptr; prov.local = nullptr;
             const float p_hat = evaluate_P_hat<1>(ray, sg, prov, fp.spatial, finalReservoir, false);
