@@ -23,6 +23,7 @@ int analyticBlocksPerSM();
 cudaError_t launchMarchAnalytic(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int blocks, cudaStream_t st);
 cudaError_t launchFinalGather(const FrameParams& fp, const WfStream& s, float* results, cudaStream_t st);
 cudaError_t launchFinalCombine(const FrameParams& fp, const float* results, cudaStream_t st);
+cudaError_t launchInitialFinish(const FrameParams& fp, const WfInitial& wi, cudaStream_t st);
 cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st);
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st);
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st);

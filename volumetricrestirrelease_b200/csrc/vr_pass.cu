@@ -408,13 +408,25 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                     WfInitial wi;
                     wi.light.tasks = p->wfLightTasks; wi.light.count = p->wfCounters; wi.light.cursor = p->wfCounters + 1; wi.light.capacity = (unsigned)n;
                     wi.state = p->wfInitialState; wi.done = (uint8_t*)(p->wfInitialState + n * K1_STRIDE);
+                    // the final p-hat evaluation (spatial options) of every pixel: explicit camera + light tasks in the camera-task
+                    // buffer (<= n of each, 48 B); one stream when both march configurations are equal
+                    MarchKind kc, klp; wavefrontKinds(p, kc, klp); kc.originMode = 0;
+                    const bool oneEval = memcmp(&kc, &klp, sizeof(MarchKind)) == 0;
+                    wi.results = p->wfResults;
+                    wi.evalCam.tasks = p->wfCamTasks; wi.evalCam.count = p->wfCounters + 4; wi.evalCam.cursor = p->wfCounters + 5; wi.evalCam.capacity = (unsigned)(oneEval ? 2 * n : n);
+                    if (oneEval) wi.evalLight = wi.evalCam;
+                    else { wi.evalLight.tasks = p->wfCamTasks + 3 * n; wi.evalLight.count = p->wfCounters + 6; wi.evalLight.cursor = p->wfCounters + 7; wi.evalLight.capacity = (unsigned)n; }
+                    CK(cudaMemsetAsync(p->wfCounters + 4, 0, 16, st));
                     fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
                     const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0};
                     for (int s = 0; s <= m.mInitialM; s++) {
                         if (s < m.mInitialM) CK(cudaMemsetAsync(p->wfCounters, 0, 8, st));
-                        CK(launchInitialStep(fp, wi, s, st)); p->launches++;
+                        CK(launchInitialStep(fp, wi, s, st)); p->launches += s == 0 ? 2 : 1;
                         if (s < m.mInitialM) { CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st)); p->launches++; }
                     }
+                    CK(launchMarch(wi.evalCam, wi.results, kc, p->scene.slots[kc.mip], 1, p->marchBlocks1, st)); p->launches++;
+                    if (!oneEval) { CK(launchMarch(wi.evalLight, wi.results, klp, p->scene.slots[klp.mip], 1, p->marchBlocks1, st)); p->launches++; }
+                    CK(launchInitialFinish(fp, wi, st)); p->launches++;
                     p->finalPhys = p->ia;
                     recordEv(p, 2, st);
                     break;

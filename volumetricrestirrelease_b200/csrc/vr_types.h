@@ -86,7 +86,7 @@ enum { WF_BLOCK = 48, WF_D = 0, WF_C = 16, WF_L = 28 };
 struct WfBufs { WfStream cam, light; float* results; };
 // K1 lock-step candidate state: K1_STRIDE floats per pixel (vr_wavefront.cu)
 enum { K1_WORDS = 20, K1_STRIDE = 80 };
-struct WfInitial { WfStream light; float* state; uint8_t* done; };
+struct WfInitial { WfStream light; float* state; uint8_t* done; WfStream evalCam, evalLight; float* results; };
 // K2: four explicit-origin streams {current camera, current light, previous-frame camera, previous-frame light};
 // streams whose march configuration is identical alias the same buffer
 struct WfBufs4 { WfStream s[4]; int mip[4]; float* results; };

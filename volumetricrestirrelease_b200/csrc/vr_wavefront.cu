@@ -378,7 +378,25 @@ VRD K1Cand k1Load(const float* r) {
 // [20,24) RNG state, [24,36) hd/pd/ot of the 4 distance candidates, [36,44) the reservoir being streamed
 enum { K1_SG = 20, K1_HD = 24, K1_RES = 36 };
 
-// MODE 0: s == 0 (traversal + first candidate), 1: 0 < s < M, 2: s == M (last candidate's finish + p-hat); separate
+// The candidate traversal of K1 (SampleMediumAnalyticGeneric: <= 4 free-flight distances along the camera ray on the
+// conservative mip, one random draw per voxel cell per pending sample) in a kernel of its own: with the candidate / p-hat
+// code in the same kernel the hot loop missed the instruction cache (ncu: stall_no_instruction 2.9 per issue).
+__global__ void __launch_bounds__(128, 6) k_initial_traverse(FrameParams fp, WfInitial wi) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    const int pixelId = y * fp.W + x;
+    float* st = wi.state + (size_t)(pixelId - fp.rowBegin * fp.W) * K1_STRIDE;
+    SampleGenerator sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
+    const Ray ray = primaryRay(fp, x, y);
+    float hds[4] = {0, 0, 0, 0}, pds[4] = {0, 0, 0, 0}, ots[4] = {0, 0, 0, 0};
+    SampleMediumAnalyticGeneric(ray, sg, fp.initial.visibilityUseLinearSampler, hds, fp.initial.visibilityMipLevel, pds, ots, fp.initialM);
+    ((float4*)(st + 24))[0] = make_float4(hds[0], hds[1], hds[2], hds[3]);
+    ((float4*)(st + 24))[1] = make_float4(pds[0], pds[1], pds[2], pds[3]);
+    ((float4*)(st + 24))[2] = make_float4(ots[0], ots[1], ots[2], ots[3]);
+    ((float4*)(st + 20))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
+}
+
+// MODE 0: s == 0 (first candidate, after k_initial_traverse), 1: 0 < s < M, 2: s == M (last candidate's finish + p-hat); separate
 // instantiations so that the light-weight middle steps do not carry the registers of the traversal / the p-hat marches
 template <int MODE>
 #ifndef VR_STEP0_MINB
@@ -395,8 +413,10 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
     float* st = wi.state + recBase;
     const SamplingOptions& o = fp.initial;
     const int M = fp.initialM;
-    bool hasTask = false;
+    bool hasTask = false, wantEval = false;
     Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
+    Reservoir evalTap = createNewReservoir();
+    float3 evalDir = f3(0.f, 0.f, 1.f);
     __shared__ float impTop[IMP_TOP_FLOATS];
     const bool stageImp = MODE != 2 && o.useEnvironmentLights && c_scene.haveEnv && c_scene.envSamplerType != VRESTIR_ENV_SAMPLER_ALIAS && c_scene.impDim >= IMP_TOP_DIM;
     if (stageImp) { stageImportanceTop(impTop); __syncthreads(); }
@@ -409,9 +429,10 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
         float hd = 0.f, pd = 0.f, ot = 0.f;
         bool finishNow = false;
         if (MODE == 0) {
-            sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
-            float hds[4] = {0, 0, 0, 0}, pds[4] = {0, 0, 0, 0}, ots[4] = {0, 0, 0, 0};
-            SampleMediumAnalyticGeneric(ray, sg, o.visibilityUseLinearSampler, hds, o.visibilityMipLevel, pds, ots, M);
+            const float4 g4 = ((const float4*)(st + K1_SG))[0];
+            sg.s0 = __float_as_uint(g4.x); sg.s1 = __float_as_uint(g4.y); sg.s2 = __float_as_uint(g4.z); sg.s3 = __float_as_uint(g4.w);
+            const float4 h4 = ((const float4*)(st + K1_HD))[0], p4 = ((const float4*)(st + K1_HD))[1], o4 = ((const float4*)(st + K1_HD))[2];
+            const float hds[4] = {h4.x, h4.y, h4.z, h4.w}, pds[4] = {p4.x, p4.y, p4.z, p4.w}, ots[4] = {o4.x, o4.y, o4.z, o4.w};
             hd = hds[0]; pd = pds[0]; ot = ots[0];
             bool allOut = true;
 #pragma unroll
@@ -430,10 +451,6 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
                     simpleResampleStep<1>(outReservoir, finalReservoir, sg);
                 }
                 finishNow = true;
-            } else {
-                ((float4*)(st + K1_HD))[0] = make_float4(hds[0], hds[1], hds[2], hds[3]);
-                ((float4*)(st + K1_HD))[1] = make_float4(pds[0], pds[1], pds[2], pds[3]);
-                ((float4*)(st + K1_HD))[2] = make_float4(ots[0], ots[1], ots[2], ots[3]);
             }
             *doneFlag = allOut ? 1 : 0;
         } else {
@@ -481,17 +498,31 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
             ((float4*)(st + K1_RES))[0] = make_float4(finalReservoir.runningSum, finalReservoir.M, finalReservoir.depth, finalReservoir.p_y);
             ((float4*)(st + K1_RES))[1] = make_float4(finalReservoir.lightUV.x, finalReservoir.lightUV.y, __int_as_float(finalReservoir.lightID), __int_as_float(finalReservoir.sampledPixel));
         } else if (MODE == 2 || finishNow) {
-            // VR/TraceRays.cs.slang:176-183: p-hat of the streamed reservoir under the spatial options (ray-marched: no draws)
-            ExtraProvider prov; prov.global = nullptr; prov.local = nullptr;
-            const float p_hat = evaluate_P_hat<1>(ray, sg, prov, fp.spatial, finalReservoir, false);
-            if (finalReservoir.runningSum > 0.f) {
-                finalReservoir.runningSum *= finalReservoir.p_y == 0.f ? 0.f : p_hat / finalReservoir.p_y;
-                finalReservoir.p_y = p_hat;
-            }
+            // VR/TraceRays.cs.slang:176-183: the p-hat of the streamed reservoir under the spatial options (ray-marched: no
+            // draws) becomes march tasks; k_initial_finish applies `runningSum *= p_hat / p_y`
             storeReservoir(fp.cur, pixelId, finalReservoir);
+            wantEval = finalReservoir.runningSum > 0.f;
+            evalTap = finalReservoir;
+            evalDir = ray.dir;
         }
     }
     if (MODE != 2) wfEmitRay(wi.light, hasTask, shadow, o.lightingMipLevel, false, wi.state, recBase + 18);
+    if (MODE != 1) wfEmitEval(wantEval, evalTap, c_scene.camPos, evalDir, false, wi.results, (unsigned)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK,
+                              wi.evalCam, fp.spatial.visibilityMipLevel, wi.evalLight, fp.spatial.lightingMipLevel);
+}
+
+__global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfInitial wi) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    const int pixelId = y * fp.W + x;
+    const float4 a = fp.cur.p0[pixelId];   // (runningSum, M, depth, p_y)
+    if (!(a.x > 0.f)) return;
+    Reservoir r = loadReservoirRW(fp.cur, pixelId, 1);
+    const float* blk = wi.results + (size_t)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
+    const float p_hat = wfPHatV(r, c_scene.camPos, tapRayDir(fp, x, y), false, blk[0], blk[1], blk[2]);
+    r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
+    r.p_y = p_hat;
+    fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
 }
 
 // ------------------------------------------------------------------------------------------------ K2 wavefront
@@ -753,11 +784,12 @@ cudaError_t launchMarchAnalytic(const WfStream& s, float* results, const MarchKi
 cudaError_t launchFinalGather(const FrameParams& fp, const WfStream& s, float* results, cudaStream_t st) { k_final_gather<<<gridForWf(fp), 128, 0, st>>>(fp, s, results); return cudaGetLastError(); }
 cudaError_t launchFinalCombine(const FrameParams& fp, const float* results, cudaStream_t st) { k_final_combine<<<gridForWf(fp), 128, 0, st>>>(fp, results); return cudaGetLastError(); }
 cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st) {
-    if (s == 0) k_initial_step<0><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
+    if (s == 0) { k_initial_traverse<<<gridForWf(fp), 128, 0, st>>>(fp, wi); k_initial_step<0><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s); }
     else if (s < fp.initialM) k_initial_step<1><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
     else k_initial_step<2><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
     return cudaGetLastError();
 }
+cudaError_t launchInitialFinish(const FrameParams& fp, const WfInitial& wi, cudaStream_t st) { k_initial_finish<<<gridForWf(fp), 128, 0, st>>>(fp, wi); return cudaGetLastError(); }
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
