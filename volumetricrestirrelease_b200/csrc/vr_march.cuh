@@ -45,6 +45,7 @@ VRD float fastFloor(float x, int& i) {
 }
 // exact UNORM8 code -> float: 2^23 + b, minus 2^23
 VRD float launder(float x) { asm volatile("" : "+f"(x)); return x; }
+VRD float byteToMagic(uint32_t w, int sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + sel)); }   // 2^23 + byte
 VRD float byteToFloat(uint32_t w, int sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + sel) ) - 8388608.f; }
 
 // ---- traversal shared by all marchers: the hierarchical DDA of VolumeTrackingGVDB (VR/VolumeUtils.slang:171-282) as a
@@ -247,9 +248,12 @@ struct RayMarcher : MarchTrav {
         const float fx = qx - fx0, fy = qy - fy0, fz = qz - fz0;
         const uint32_t* q = g.quads + (brick * 810u + (unsigned)(((iz + 1) * 9 + (iy + 1)) * 9 + (ix + 1)));
         const uint32_t w0 = __ldg(q), w1 = __ldg(q + 81);
-        const float v000 = byteToFloat(w0, 0), v100 = byteToFloat(w0, 1), v010 = byteToFloat(w0, 2), v110 = byteToFloat(w0, 3);
-        const float v001 = byteToFloat(w1, 0), v101 = byteToFloat(w1, 1), v011 = byteToFloat(w1, 2), v111 = byteToFloat(w1, 3);
-        const float c00 = lerpf(v000, v100, fx), c10 = lerpf(v010, v110, fx), c01 = lerpf(v001, v101, fx), c11 = lerpf(v011, v111, fx);
+        // x-lerps: the codes arrive as 2^23 + b; (2^23 + b1) - (2^23 + b0) == b1 - b0 exactly, so only the base corner of each
+        // pair is converted (lerpf(a, b, t) = fma(t, b - a, a))
+        const float m000 = byteToMagic(w0, 0), m100 = byteToMagic(w0, 1), m010 = byteToMagic(w0, 2), m110 = byteToMagic(w0, 3);
+        const float m001 = byteToMagic(w1, 0), m101 = byteToMagic(w1, 1), m011 = byteToMagic(w1, 2), m111 = byteToMagic(w1, 3);
+        const float c00 = __fmaf_rn(fx, m100 - m000, m000 - 8388608.f), c10 = __fmaf_rn(fx, m110 - m010, m010 - 8388608.f);
+        const float c01 = __fmaf_rn(fx, m101 - m001, m001 - 8388608.f), c11 = __fmaf_rn(fx, m111 - m011, m011 - 8388608.f);
         const float c0 = lerpf(c00, c10, fy), c1 = lerpf(c01, c11, fy);
         return lerpf(c0, c1, fz) * kUnorm8;
     }
