@@ -223,7 +223,8 @@ def test_three_level_tree_full_reuse():
 def _frames_buffers(params, scene, w, h, wavefront, frames=3):
     """Run `frames` frames through the public execute() and return (image, final reservoirs) of the last one."""
     import torch
-    d = {"mParams": params, "mUseWavefront": int(wavefront is not False), "mMarchPairEngine": int(wavefront == "pair")}
+    d = {"mParams": params, "mUseWavefront": int(wavefront is not False), "mMarchPairEngine": int(wavefront == "pair"),
+         "mInitialChains": 2 if wavefront == "pair" else 1}   # the "pair" variant also runs K1 as two row-half chains
     if wavefront == 0:
         d["mInitialMode"] = 0
     gp = VolumetricReSTIR.create(d)

@@ -90,7 +90,8 @@ struct vrestir_pass {
     // K0 (features) has no consumer before K2: vrestir_execute runs it on an auxiliary stream next to K1
     bool mOverlapFeatures = true, framesOverlapped = false;
     cudaStream_t auxStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
-    cudaEvent_t evMarch[3] = {}; bool evMarchValid = false;   // around the two march launches of the last spatial round
+    cudaEvent_t evMarch[3] = {}; bool evMarchValid = false;
+    int mInitialChains = 1; cudaStream_t auxStream2 = nullptr; cudaEvent_t evFork2 = nullptr, evJoin2 = nullptr;   // K1 row halves on two streams (option; measured neutral: 8.65 vs 8.56 ms)   // around the two march launches of the last spatial round
     cudaStream_t hostStream = nullptr;
     float4* d_hostColor = nullptr; float2* d_hostMvec = nullptr; size_t hostColorPixels = 0;
     uint64_t launches = 0;
@@ -140,7 +141,7 @@ int ensureWavefront(vrestir_pass* p) {
     CK(cudaMalloc(&p->wfCamTasks, n * 4 * 32));
     CK(cudaMalloc(&p->wfLightTasks, n * 12 * 48));   // explicit (prepared) tasks are 48 B
     CK(cudaMalloc(&p->wfResults, n * WF_BLOCK * sizeof(float)));
-    if (!p->wfCounters) CK(cudaMalloc(&p->wfCounters, 64));
+    if (!p->wfCounters) CK(cudaMalloc(&p->wfCounters, 128));   // 32 counters: two chains x {stream count / cursor pairs}
     p->wfPixels = n;
     if (!p->marchBlocks1) {
         int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
@@ -405,28 +406,46 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
                         CK(cudaMalloc(&p->wfInitialState, n * K1_STRIDE * sizeof(float) + n));   // + one done flag per pixel
                         p->wfInitialPixels = n;
                     }
-                    WfInitial wi;
-                    wi.light.tasks = p->wfLightTasks; wi.light.count = p->wfCounters; wi.light.cursor = p->wfCounters + 1; wi.light.capacity = (unsigned)n;
-                    wi.state = p->wfInitialState; wi.done = (uint8_t*)(p->wfInitialState + n * K1_STRIDE);
-                    // the final p-hat evaluation (spatial options) of every pixel: explicit camera + light tasks in the camera-task
-                    // buffer (<= n of each, 48 B); one stream when both march configurations are equal
+                    // Two chains: the band is cut into two row halves that run the lock-step sequence on two streams, so the tail of
+                    // one half's march kernel (few long rays left) is filled by the other half's kernels.
                     MarchKind kc, klp; wavefrontKinds(p, kc, klp); kc.originMode = 0;
                     const bool oneEval = memcmp(&kc, &klp, sizeof(MarchKind)) == 0;
-                    wi.results = p->wfResults;
-                    wi.evalCam.tasks = p->wfCamTasks; wi.evalCam.count = p->wfCounters + 4; wi.evalCam.cursor = p->wfCounters + 5; wi.evalCam.capacity = (unsigned)(oneEval ? 2 * n : n);
-                    if (oneEval) wi.evalLight = wi.evalCam;
-                    else { wi.evalLight.tasks = p->wfCamTasks + 3 * n; wi.evalLight.count = p->wfCounters + 6; wi.evalLight.cursor = p->wfCounters + 7; wi.evalLight.capacity = (unsigned)n; }
-                    CK(cudaMemsetAsync(p->wfCounters + 4, 0, 16, st));
-                    fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
                     const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0};
-                    for (int s = 0; s <= m.mInitialM; s++) {
-                        if (s < m.mInitialM) CK(cudaMemsetAsync(p->wfCounters, 0, 8, st));
-                        CK(launchInitialStep(fp, wi, s, st)); p->launches += s == 0 ? 2 : 1;
-                        if (s < m.mInitialM) { CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st)); p->launches++; }
+                    const int rows = p->rowEnd - p->rowBegin;
+                    const int chains = (p->mInitialChains > 1 && rows >= 32) ? 2 : 1;
+                    const int mid = chains == 2 ? p->rowBegin + ((rows / 2 + 7) / 8) * 8 : p->rowEnd;
+                    if (chains == 2) {
+                        if (!p->auxStream2) { CK(cudaStreamCreateWithFlags(&p->auxStream2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&p->evFork2, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->evJoin2, cudaEventDisableTiming)); }
                     }
-                    CK(launchMarch(wi.evalCam, wi.results, kc, p->scene.slots[kc.mip], 1, p->marchBlocks1, st)); p->launches++;
-                    if (!oneEval) { CK(launchMarch(wi.evalLight, wi.results, klp, p->scene.slots[klp.mip], 1, p->marchBlocks1, st)); p->launches++; }
-                    CK(launchInitialFinish(fp, wi, st)); p->launches++;
+                    CK(cudaMemsetAsync(p->wfCounters, 0, 128, st));
+                    if (chains == 2) { CK(cudaEventRecord(p->evFork2, st)); CK(cudaStreamWaitEvent(p->auxStream2, p->evFork2, 0)); }
+                    fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
+                    for (int c = 0; c < chains; c++) {
+                        cudaStream_t sc = c == 0 ? st : p->auxStream2;
+                        FrameParams fh = fp;
+                        fh.rowBegin = c == 0 ? p->rowBegin : mid; fh.rowEnd = c == 0 ? mid : p->rowEnd;
+                        const size_t off = (size_t)(fh.rowBegin - p->rowBegin) * p->W, nh = (size_t)(fh.rowEnd - fh.rowBegin) * p->W;
+                        unsigned* cnt = p->wfCounters + 16 * c;
+                        WfInitial wi;
+                        wi.light.tasks = p->wfLightTasks + 3 * off; wi.light.count = cnt; wi.light.cursor = cnt + 1; wi.light.capacity = (unsigned)nh;
+                        wi.state = p->wfInitialState + off * K1_STRIDE; wi.done = (uint8_t*)(p->wfInitialState + n * K1_STRIDE) + off;
+                        // the final p-hat evaluation (spatial options): explicit camera + light tasks in the camera-task buffer
+                        // (<= one of each per pixel, 48 B); one stream when both march configurations are equal
+                        wi.results = p->wfResults + off * WF_BLOCK;
+                        uint4* evalBase = p->wfCamTasks + 3 * (2 * off);
+                        wi.evalCam.tasks = evalBase; wi.evalCam.count = cnt + 4; wi.evalCam.cursor = cnt + 5; wi.evalCam.capacity = (unsigned)(oneEval ? 2 * nh : nh);
+                        if (oneEval) wi.evalLight = wi.evalCam;
+                        else { wi.evalLight.tasks = evalBase + 3 * nh; wi.evalLight.count = cnt + 6; wi.evalLight.cursor = cnt + 7; wi.evalLight.capacity = (unsigned)nh; }
+                        for (int s = 0; s <= m.mInitialM; s++) {
+                            if (s > 0 && s < m.mInitialM) CK(cudaMemsetAsync(cnt, 0, 8, sc));
+                            CK(launchInitialStep(fh, wi, s, sc)); p->launches += s == 0 ? 2 : 1;
+                            if (s < m.mInitialM) { CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, sc)); p->launches++; }
+                        }
+                        CK(launchMarch(wi.evalCam, wi.results, kc, p->scene.slots[kc.mip], 1, p->marchBlocks1, sc)); p->launches++;
+                        if (!oneEval) { CK(launchMarch(wi.evalLight, wi.results, klp, p->scene.slots[klp.mip], 1, p->marchBlocks1, sc)); p->launches++; }
+                        CK(launchInitialFinish(fh, wi, sc)); p->launches++;
+                    }
+                    if (chains == 2) { CK(cudaEventRecord(p->evJoin2, p->auxStream2)); CK(cudaStreamWaitEvent(st, p->evJoin2, 0)); }
                     p->finalPhys = p->ia;
                     recordEv(p, 2, st);
                     break;
@@ -664,6 +683,9 @@ int vrestir_destroy(vrestir_pass* p) {
     if (p->evFork) cudaEventDestroy(p->evFork);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
     for (auto& e : p->evMarch) if (e) cudaEventDestroy(e);
+    if (p->auxStream2) cudaStreamDestroy(p->auxStream2);
+    if (p->evFork2) cudaEventDestroy(p->evFork2);
+    if (p->evJoin2) cudaEventDestroy(p->evJoin2);
     delete p;
     return VRESTIR_OK;
 }
@@ -833,6 +855,7 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
         else if (k == "mUseWavefront") p->mUseWavefront = value != 0;
         else if (k == "mInitialMode") p->mInitialMode = (int)value;
         else if (k == "mOverlapFeatures") p->mOverlapFeatures = value != 0;
+        else if (k == "mInitialChains") p->mInitialChains = (int)value;
         else if (k == "mMarchPairEngine") setPairEngine(value != 0);   // process-wide A/B switch of the march engine   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
