@@ -329,3 +329,28 @@ def test_plume_animated_sequence_staged(wavefront):
     assert self_emission > 0, "the emissive path was not exercised"
     for k, v in worst.items():
         assert v <= 5e-3, (k, v)   # libm-ulp differences in the black-body / velocity lookups flip a few more selections
+
+
+def test_accumulated_full_reuse_relmse():
+    """North-star convergence check: frames accumulated with full temporal + spatial reuse on the GPU (default wavefront path,
+    whole-frame execute) against the oracle's accumulation over the same frames, relMSE = mean((a-b)^2 / (b^2 + eps)) with
+    eps = 1e-2 * mean(b)^2.  Both run the same RNG streams, so the accumulations differ only by the (counted)
+    selection flips; the bound is the north star's 1e-3."""
+    import torch
+    from common import rel_mse
+    w, h, frames = 96, 64, 48
+    sc = env_scene()
+    gp, op = make_pair(sc, VolumetricReSTIRParams(), w, h)
+    color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    acc_g = np.zeros((h, w, 4), np.float64)
+    acc_c = np.zeros((h, w, 4), np.float64)
+    for _ in range(frames):
+        gp.execute(color.data_ptr())
+        torch.cuda.synchronize()
+        acc_g += color.cpu().numpy()
+        acc_c += op.execute()
+    acc_g /= frames; acc_c /= frames
+    r = rel_mse(acc_g, acc_c)
+    print(f"[accumulated {frames} frames] relMSE gpu vs oracle {r:.3e}, mean gpu {acc_g[..., :3].mean():.6f} cpu {acc_c[..., :3].mean():.6f}")
+    assert r <= 1e-3
+    assert abs(acc_g[..., :3].mean() / acc_c[..., :3].mean() - 1) < 2e-3
