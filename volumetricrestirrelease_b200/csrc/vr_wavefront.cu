@@ -47,11 +47,15 @@ VRD float3 tapRayDir(const FrameParams& fp, int tx, int ty) {
     return normalize(camRayDirNN(c_scene.camU, c_scene.camV, c_scene.camW, tx, ty, fp.W, fp.H));
 }
 
+// The tap loops are ROLLED (the four ray directions / tap depths live in shared memory): fully unrolled, the 12 inlined
+// evaluations made the kernel instruction-fetch bound (ncu: stall_no_instruction 10.8 per issue).
 __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs wf) {
+    __shared__ float s_dir[4][3][128];
+    __shared__ float s_depth[4][128];
     int x, y;
     bool active = pixelOf(fp, x, y);
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
     const int W = fp.W, S = fp.sampleCount;
     const bool talbot = fp.spatialMIS == VRESTIR_MIS_TALBOT;
@@ -68,28 +72,37 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
     const float3 origin = c_scene.camPos;
     unsigned camBits = 0;     // bit j*3+k: camera ray j needs the transmittance to the depth of tap i, k = i - (i > j)
     unsigned lightBits = 0;   // bit i*4+j: light march from ray_j.at(depth_i)
-    float depth[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned inImage = 0;     // bit s: tap s lies in the image
+    // ---- pass 0: the four rays of the pixel (own ray + the primary rays of the tap pixels) and the tap depths
+    if (active) {
+#pragma unroll 1
+        for (int s = 0; s < S; s++) {
+            int tx, ty;
+            if (!tapInImage(fp, x, y, s, tx, ty)) continue;
+            inImage |= 1u << s;
+            const float3 d = tapRayDir(fp, tx, ty);
+            s_dir[s][0][tid] = d.x; s_dir[s][1][tid] = d.y; s_dir[s][2][tid] = d.z;
+            s_depth[s][tid] = __ldg(&fp.cur.p0[ty * W + tx]).z;
+        }
+    }
     // ---- pass 1: which evaluations exist, density point queries
     if (active) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i >= S || (i == 0 && !talbot)) continue;
-            int txi, tyi;
-            if (!tapInImage(fp, x, y, i, txi, tyi)) continue;
+#pragma unroll 1
+        for (int i = talbot ? 0 : 1; i < S; i++) {
+            if (!((inImage >> i) & 1u)) continue;
+            int txi, tyi; tapInImage(fp, x, y, i, txi, tyi);
             const Reservoir tap = loadReservoir(fp.cur, tyi * W + txi, 1);
-            depth[i] = tap.depth;
             const bool wantResample = i > 0 && tap.runningSum != 0.f;                                    // resampleNeighbor
             const bool wantMIS = talbot && (i == 0 ? tap.runningSum > 0.f : tap.runningSum != 0.f);     // superset of "runningSum > 0 after resampling"
             if (!wantResample && !wantMIS) continue;
             const bool bg = tap.depth == kRayTMax;
             bool alive = true;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j >= S || j == i) continue;
-                int txj = x, tyj = y;
+#pragma unroll 1
+            for (int j = 0; j < S; j++) {
+                if (j == i) continue;
                 if (j == 0) { if (!wantResample) continue; }
-                else { if (!wantMIS || !alive) continue; if (!tapInImage(fp, x, y, j, txj, tyj)) continue; }
-                const float3 dir = tapRayDir(fp, txj, tyj);
+                else { if (!wantMIS || !alive) continue; if (!((inImage >> j) & 1u)) continue; }
+                const float3 dir = f3(s_dir[j][0][tid], s_dir[j][1][tid], s_dir[j][2][tid]);
                 const Ray r = makeRay(origin, dir, 0.f, tap.depth);
                 const float3 pW = r.at(r.tMax);
                 const float density = bg ? 1.f : DensityWorldSpace(pW, 0);
@@ -117,41 +130,36 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
     unsigned camBase = 0, lightBase = 0;
     if (lane == 0) { camBase = atomicAdd(wf.cam.count, camTot); if (lightTot) lightBase = atomicAdd(wf.light.count, lightTot); }
     camBase = __shfl_sync(FULL, camBase, 0); lightBase = __shfl_sync(FULL, lightBase, 0);
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 4; j++) {
         const unsigned m = (camBits >> (3 * j)) & 7u;
         const unsigned bal = __ballot_sync(FULL, m != 0);
         if (m) {
             const unsigned pos = camBase + __popc(bal & lt);
-            int txj = x, tyj = y;
-            if (j > 0) tapInImage(fp, x, y, j, txj, tyj);
-            const float3 dir = tapRayDir(fp, txj, tyj);
-            // threshold k of ray j is the depth of tap i = k + (k >= j)
-            const float t0 = depth[j <= 0 ? 1 : 0], t1 = depth[j <= 1 ? 2 : 1], t2 = depth[j <= 2 ? 3 : 2];
+            // threshold k of ray j is the depth of tap i = k + (k >= j); unused thresholds are masked out by m
+            const float t0 = s_depth[j <= 0 ? 1 : 0][tid], t1 = s_depth[j <= 1 ? 2 : 1][tid], t2 = s_depth[j <= 2 ? 3 : 2][tid];
             if (pos < wf.cam.capacity) {
                 wf.cam.tasks[2 * (size_t)pos] = make_uint4(__float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), m);
-                wf.cam.tasks[2 * (size_t)pos + 1] = make_uint4(__float_as_uint(dir.x), __float_as_uint(dir.y), __float_as_uint(dir.z), blkBase + WF_C + j * 3);
+                wf.cam.tasks[2 * (size_t)pos + 1] = make_uint4(__float_as_uint(s_dir[j][0][tid]), __float_as_uint(s_dir[j][1][tid]), __float_as_uint(s_dir[j][2][tid]), blkBase + WF_C + j * 3);
             }
         }
         camBase += __popc(bal);
     }
     if (lightTot == 0) return;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         const unsigned mi_ = (lightBits >> (4 * i)) & 15u;
         if (!__any_sync(FULL, mi_ != 0)) continue;
         Reservoir tap = createNewReservoir();
         if (mi_) { int txi, tyi; tapInImage(fp, x, y, i, txi, tyi); tap = loadReservoir(fp.cur, tyi * W + txi, 1); }
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 4; j++) {
             if (j == i) continue;
             const bool has = (mi_ >> j) & 1u;
             const unsigned bal = __ballot_sync(FULL, has);
             if (has) {
                 const unsigned pos = lightBase + __popc(bal & lt);
-                int txj = x, tyj = y;
-                if (j > 0) tapInImage(fp, x, y, j, txj, tyj);
-                const float3 dir = tapRayDir(fp, txj, tyj);
+                const float3 dir = f3(s_dir[j][0][tid], s_dir[j][1][tid], s_dir[j][2][tid]);
                 const Ray r = makeRay(origin, dir, 0.f, tap.depth);
                 const float3 pW = r.at(r.tMax);
                 Ray sh; float3 Ld;
