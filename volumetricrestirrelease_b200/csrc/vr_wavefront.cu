@@ -389,7 +389,10 @@ enum { K1_SG = 20, K1_HD = 24, K1_RES = 36 };
 // The candidate traversal of K1 (SampleMediumAnalyticGeneric: <= 4 free-flight distances along the camera ray on the
 // conservative mip, one random draw per voxel cell per pending sample) in a kernel of its own: with the candidate / p-hat
 // code in the same kernel the hot loop missed the instruction cache (ncu: stall_no_instruction 2.9 per issue).
-__global__ void __launch_bounds__(128, 6) k_initial_traverse(FrameParams fp, WfInitial wi) {
+#ifndef VR_TRAV_MINB
+#define VR_TRAV_MINB 6
+#endif
+__global__ void __launch_bounds__(128, VR_TRAV_MINB) k_initial_traverse(FrameParams fp, WfInitial wi) {
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     const int pixelId = y * fp.W + x;
