@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march_pair(const WfStrea
     marchPairs(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
 }
 #ifndef VR_ANALYTIC_MINB
-#define VR_ANALYTIC_MINB 6
+#define VR_ANALYTIC_MINB 8
 #endif
 __global__ void __launch_bounds__(128, VR_ANALYTIC_MINB) k_march_analytic(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
     marchPool<AnalyticMarcher>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
