@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tiles", type=int, default=15)
     ap.add_argument("--stage-breakdown", action="store_true", help="also print per-stage ms to stderr")
+    ap.add_argument("--no-pipeline", action="store_true", help="do not overlap K0/K1 of frame f+1 with K2..K5 of frame f")
     return ap.parse_args()
 
 
@@ -213,7 +214,10 @@ def main():
     t0 = time.time()
     scene = build_scene(args)
     params = make_params(args)
-    gp = VolumetricReSTIR.create({"mParams": params}, device=local)
+    # frame pipelining: the camera of the bench is static, i.e. known one frame ahead; every frame still runs its own K0/K1
+    # (keyed by its frame counter), just next to the previous frame's K2..K5 instead of after them
+    pipelined = not args.no_pipeline
+    gp = VolumetricReSTIR.create({"mParams": params, "mPipelineFrames": int(pipelined)}, device=local)
     sp = ShardedPass(gp, W, H, rank, world, torch.device("cuda", local))
     gp.setScene(scene, W, H)
     color = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
@@ -257,6 +261,32 @@ def main():
         for k, v in gp.timings().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / args.steps
 
+    pstats = gp.pipeline_stats()
+    serial_ms = None
+    mt_alone = None
+    if pipelined:   # the same frames without pipelining, for the record (option change: history restarts, so warm up again)
+        gp.updateDict({"mPipelineFrames": 0})
+        for _ in range(max(3, args.warmup)):
+            sp.execute(color.data_ptr())
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            sp.execute(color.data_ptr())
+        ev1.record()
+        barrier()
+        serial_ms = ev0.elapsed_time(ev1) / args.steps
+        serial_stage = {}
+        for _ in range(args.steps):
+            sp.execute(color.data_ptr())
+            torch.cuda.synchronize()
+            for k, v in gp.timings().items():
+                serial_stage[k] = serial_stage.get(k, 0.0) + v / args.steps
+        mt_alone = gp.march_timings()   # the march launches timed alone on the GPU (no second chain next to them): roofline input
+        gp.updateDict({"mPipelineFrames": 1})
+        for _ in range(max(3, args.warmup)):
+            sp.execute(color.data_ptr())
+        barrier()
+
     # ---- end to end with HOST buffers: every step uploads its inputs (camera + scene constants, from host memory) through
     # the public call, renders, and reads its frame back into pinned host memory.  The read-back of frame i runs on a copy
     # stream while frame i+1 renders (two device frames, two host frames): a renderer that streams frames out, not a
@@ -290,9 +320,10 @@ def main():
     barrier()                                                # includes the copy stream: torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t_e2e0) * 1e3 / args.steps
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, serial_ms or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
+        serial_ms = float(t[2]) if pipelined else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,7 +338,7 @@ def main():
 
     cpu = None
     roof = None
-    mt = gp.march_timings()
+    mt = mt_alone or gp.march_timings()
     # L2 -> SM read peak (32 MiB resident buffer) next to the HBM copy peak: the reuse mips are L2 resident by design
     l2 = capi.C.c_float(0.0)
     capi.check(capi.lib().vrestir_debug_read_bandwidth(local, 32 << 20, 50, capi.C.byref(l2)))
@@ -344,7 +375,12 @@ def main():
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(d=args.dim, m=args.mips, w=W, h=H, b=args.bounces), "parallelism": f"rows/{world}" + (f" (cost-balanced bands {sp.bands})" if world > 1 else ""),
                        "l2": "inputs larger than L2 (fp32 mip-0 brick pool + ~0.9 GB/frame of reservoir traffic stream through every frame; the reuse mip is pinned in L2 by design)",
-                       "camera": "static", "stage_ms": {k: round(v, 3) for k, v in stage_acc.items()}},
+                       "camera": "static", "stage_ms": {k: round(v, 3) for k, v in stage_acc.items()},
+                       "pipelining": ({"on": True, "what": "K0+K1 of frame f+1 run on a second stream next to K2..K5 of frame f (every frame's K0/K1 runs once, inside the timed region); "
+                                                            "stage_ms above are the main stream's (features/initial = wait for the prefetched chain)",
+                                       "prefetch_chain_ms": round(pstats["prefetch_ms"], 3), "adopted": int(pstats["adopted"]), "discarded": int(pstats["discarded"]),
+                                       "unpipelined_ms_per_frame": round(serial_ms, 3), "unpipelined_stage_ms": {k: round(v, 3) for k, v in serial_stage.items()}}
+                                      if pipelined else {"on": False})},
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms/frame", "h2d_bytes_per_step": int(capi.C.sizeof(capi.Camera) + 8192),
                     "d2h_bytes_per_step": int((r1 - r0) * W * 16)},

@@ -318,8 +318,22 @@ int vrestir_execute_host(vrestir_pass* pass, float* out_color_host, float* out_m
 
 /* Individual stages (for staged parity tests and multi-GPU drivers that interleave halo exchanges).
  * stage: 0 features, 1 initial, 2 temporal, 3 spatial round `arg`, 4 copy-to-history, 5 final shading,
- * 6 end-of-frame bookkeeping (saves prev camera, frameCount++). */
+ * 6 end-of-frame bookkeeping (saves prev camera, frameCount++),
+ * 7 prefetch (frame pipelining, see below): call between stage 1 and stage 2; no-op unless "mPipelineFrames" is on. */
 int vrestir_execute_stage(vrestir_pass* pass, int stage, int arg, float* out_color, float* out_mvec, void* stream);
+
+/* Frame pipelining (updateDict key "mPipelineFrames", off by default).  K0 (VR/GenerateFeatures.cs.slang) and K1
+ * (VR/TraceRays.cs.slang) read no history, so with the option on vrestir_execute(f) also starts K0 + K1 of frame f+1 on an
+ * internal stream, next to K2..K5 of frame f; vrestir_execute(f+1) adopts them when the camera, frame counter, row band,
+ * options and scene of frame f+1 are what the prefetch assumed, and otherwise discards them and runs K0/K1 itself (same
+ * results either way, bit for bit).  The prefetch assumes the camera stays where it is unless the application announces the
+ * next frame's camera here before vrestir_execute(f) (NULL clears it). */
+int vrestir_set_next_camera(vrestir_pass* pass, const vrestir_camera* camera);
+typedef struct vrestir_pipeline_stats {
+    uint64_t adopted, discarded;   /* prefetched frames used / thrown away since create */
+    float prefetch_ms;             /* device time of the last prefetch chain (K0 + K1 of the next frame) on its stream */
+} vrestir_pipeline_stats;
+int vrestir_get_pipeline_stats(vrestir_pass* pass, vrestir_pipeline_stats* out);
 
 int vrestir_get_timings(vrestir_pass* pass, vrestir_timings* out);
 /* The two march launches of the last spatial-reuse round (the dominant kernels of a frame): CUDA-event times on the launching

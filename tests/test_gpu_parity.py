@@ -223,8 +223,7 @@ def test_three_level_tree_full_reuse():
 def _frames_buffers(params, scene, w, h, wavefront, frames=3):
     """Run `frames` frames through the public execute() and return (image, final reservoirs) of the last one."""
     import torch
-    d = {"mParams": params, "mUseWavefront": int(wavefront is not False), "mMarchPairEngine": int(wavefront == "pair"),
-         "mInitialChains": 2 if wavefront == "pair" else 1}   # the "pair" variant also runs K1 as two row-half chains
+    d = {"mParams": params, "mUseWavefront": int(wavefront is not False), "mMarchPairEngine": int(wavefront == "pair")}
     if wavefront == 0:
         d["mInitialMode"] = 0
     gp = VolumetricReSTIR.create(d)
@@ -399,3 +398,47 @@ def test_full_size_properties_1080p():
     bad = (e > RADIANCE_RTOL).mean()
     print(f"[1080p crop vs oracle] frac > 1e-4: {bad:.2e}, max {e.max():.3g}")
     assert bad <= 5e-3
+
+
+@pytest.mark.parametrize("motion", ["static", "announced", "unannounced"])
+def test_pipelined_frames_equal_serial(motion):
+    """Frame pipelining ("mPipelineFrames": K0/K1 of frame f+1 run ahead on their own stream, next to K2..K5 of frame f) must not
+    change a single bit of any frame — whether the prefetch is adopted (static camera, or a moving camera announced one frame
+    ahead with setNextCamera) or discarded (camera moved without notice)."""
+    import copy
+    import torch
+    w, h, frames = 192, 112, 5
+    sc = env_scene()
+    pos0 = np.array(sc.camera.position)
+    path = [tuple(pos0 + np.array([0.6, -0.4, 0.3]) * 2.0 * f) if motion != "static" else tuple(pos0) for f in range(frames + 1)]
+
+    def run(pipelined):
+        gp = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams(), "mPipelineFrames": int(pipelined)})
+        sc.camera.position = path[0]
+        gp.setScene(sc, w, h)
+        color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        imgs = []
+        for f in range(frames):
+            sc.camera.position = path[f]
+            gp.updateCamera()
+            if pipelined and motion == "announced":
+                nxt = copy.copy(sc.camera)
+                nxt.position = path[f + 1]
+                gp.setNextCamera(nxt)
+            gp.execute(color.data_ptr())
+            torch.cuda.synchronize()
+            imgs.append(color.cpu().numpy().copy())
+        return imgs, gp.get_buffer(capi.BUF_RESERVOIR_TEMPORAL).copy(), gp.pipeline_stats()
+
+    ref_imgs, ref_res, st0 = run(False)
+    imgs, res, st = run(True)
+    sc.camera.position = tuple(pos0)
+    assert st0["adopted"] == 0 and st0["discarded"] == 0
+    if motion == "unannounced":
+        assert st["discarded"] == frames - 1 and st["adopted"] == 0
+    else:
+        assert st["adopted"] == frames - 1 and st["discarded"] == 0
+    for f in range(frames):
+        assert np.array_equal(imgs[f].view(np.uint32), ref_imgs[f].view(np.uint32)), f"frame {f} differs with pipelining ({motion})"
+    assert np.array_equal(res.view(np.uint32), ref_res.view(np.uint32))
+    assert (imgs[-1][..., :3].sum(-1) > 0).mean() > 0.05

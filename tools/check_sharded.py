@@ -1,0 +1,60 @@
+"""Multi-GPU bit-equality check (run under torchrun, one rank per GPU): every rank renders its row band of `frames` frames
+through ShardedPass (balanced bands, halo exchanges, frame pipelining as in bench.py) and, on the same GPU, the whole frame
+through a plain un-sharded, un-pipelined pass; the band must match the full frame bit for bit on every frame.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from volumetricrestirrelease_b200 import VolumetricReSTIR  # noqa: E402
+from volumetricrestirrelease_b200.multi_gpu import ShardedPass  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=360)
+    ap.add_argument("--frames", type=int, default=4)
+    ap.add_argument("--no-pipeline", action="store_true")
+    a = ap.parse_args()
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    args = argparse.Namespace(width=a.width, height=a.height, dim=[289, 286, 219], kind="bunny", mips=4, bounces=1)
+    W, H = a.width, a.height
+    scene = bench.build_scene(args)
+    params = bench.make_params(args)
+    gp = VolumetricReSTIR.create({"mParams": params, "mPipelineFrames": int(not a.no_pipeline)}, device=local)
+    sp = ShardedPass(gp, W, H, rank, world, torch.device("cuda", local))
+    gp.setScene(scene, W, H)
+    r0, r1 = sp.balance(refine=0)
+    full = VolumetricReSTIR.create({"mParams": params}, device=local)
+    full.setScene(scene, W, H)
+    c_band = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    c_full = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    bad = 0
+    for f in range(a.frames):
+        sp.execute(c_band.data_ptr())
+        full.execute(c_full.data_ptr())
+        torch.cuda.synchronize()
+        x = c_band[r0:r1].cpu().numpy().view(np.uint32)
+        y = c_full[r0:r1].cpu().numpy().view(np.uint32)
+        bad += int((x != y).any(axis=-1).sum())
+    lit = float((c_full[..., :3].sum(-1) > 0).float().mean())
+    t = torch.tensor([bad], device="cuda", dtype=torch.int64)
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"[check_sharded] world {world} bands {sp.bands} frames {a.frames} pipelined {not a.no_pipeline}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
+              f"pipeline {gp.pipeline_stats()}")
+    dist.destroy_process_group()
+    sys.exit(1 if int(t[0]) else 0)
+
+
+if __name__ == "__main__":
+    main()

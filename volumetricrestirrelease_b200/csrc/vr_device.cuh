@@ -24,6 +24,7 @@ namespace vrd {
 #define VRD __device__ __forceinline__
 #define VRD_NOINLINE static __device__ __noinline__
 
+static __constant__ DPrevCam c_prev;   // same scheme as c_scene below
 static __constant__ DScene c_scene;   // one private copy per translation unit (vr_kernels.cu, vr_wavefront.cu); uploadScene* fills each
 // diagnostics: rays whose hierarchical DDA ran >= 1024 outer iterations (origin, dir, mip, iterations), first 64
 static __device__ float g_dbgRays[64 * 8];
@@ -1398,14 +1399,21 @@ VRD void wfEmitRay(const WfStream& s, bool want, const Ray& rW, int mip, bool ve
 
 // ------------------------------------------------------------------------------------------------ pixel mapping
 // one thread per pixel; a warp covers an 8x4 pixel tile, a CTA of 4 warps 16x8 pixels
+// A warp always covers an 8x4 pixel tile.  128-thread CTAs cover 16x8 pixels (2x2 tiles); kernels whose per-pixel run time
+// varies a lot are launched with one warp per CTA (a CTA's registers are only released when its slowest warp retires).
 VRD bool pixelOf(const FrameParams& fp, int& x, int& y) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    y = fp.rowBegin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (blockDim.x == 32) {
+        x = blockIdx.x * 8 + (lane & 7);
+        y = fp.rowBegin + blockIdx.y * 4 + (lane >> 3);
+    } else {
+        x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+        y = fp.rowBegin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    }
     return x < fp.W && y < fp.rowEnd;
 }
 VRD Ray primaryRay(const FrameParams& fp, int x, int y) {
-    return makeRay(c_scene.camPos, normalize(camRayDirNN(c_scene.camU, c_scene.camV, c_scene.camW, x, y, fp.W, fp.H)), 0.f, kRayTMax);
+    return makeRay(fp.camPos, normalize(camRayDirNN(fp.camU, fp.camV, fp.camW, x, y, fp.W, fp.H)), 0.f, kRayTMax);
 }
 
 }  // namespace vrd

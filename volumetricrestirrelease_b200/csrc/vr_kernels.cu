@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(128, VR_MINB) k_temporal(FrameParams fp) {
             float3 v = VelocityWorld(pw) * c_scene.vol.velocityScale;
             pw = pw - v;
         }
-        const float* Vm = c_scene.prevView; const float* Pm = c_scene.prevProj;
+        const float* Vm = c_prev.prevView; const float* Pm = c_prev.prevProj;
         float vp[4], cp[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) vp[j] = pw.x * Vm[0 + j] + pw.y * Vm[4 + j] + pw.z * Vm[8 + j] + 1.f * Vm[12 + j];
@@ -310,13 +310,13 @@ __global__ void __launch_bounds__(128, VR_MINB) k_temporal(FrameParams fp) {
     if (numUsedReservoirs == 2) {
         temporalOriginalDepth = taps[1].depth;
         if (taps[1].depth != kRayTMax) {
-            float3 dir = normalize(camRayDirNN(c_scene.prevU, c_scene.prevV, c_scene.prevW, reprojScreenPos.x, reprojScreenPos.y, W, H));
-            float3 worldPos = c_scene.prevPos + taps[1].depth * dir;
+            float3 dir = normalize(camRayDirNN(c_prev.prevU, c_prev.prevV, c_prev.prevW, reprojScreenPos.x, reprojScreenPos.y, W, H));
+            float3 worldPos = c_prev.prevPos + taps[1].depth * dir;
             taps[1].depth = length(worldPos - ray.origin);
         }
     }
     float centerPrevFrameDepth = taps[0].depth;
-    if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_scene.prevPos); }
+    if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_prev.prevPos); }
     bool hasSelection = output.runningSum > 0.f;
     const int startSampleId = mis == VRESTIR_MIS_TALBOT ? 0 : 1;
     if (startSampleId == 1) selectedId = 0;
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(128, VR_MINB) k_temporal(FrameParams fp) {
                 else if (i == j) { p_qi = neighbor_py; p_sum += neighbor_py * correctedM; }
                 else {
                     float3 nOrigin, nDir;
-                    if (j == 0) { nOrigin = c_scene.camPos; nDir = normalize(camRayDirNN(c_scene.camU, c_scene.camV, c_scene.camW, tapPos2.x, tapPos2.y, W, H)); }
-                    else { nOrigin = c_scene.prevPos; nDir = normalize(camRayDirNN(c_scene.prevU, c_scene.prevV, c_scene.prevW, tapPos2.x, tapPos2.y, W, H)); }
+                    if (j == 0) { nOrigin = fp.camPos; nDir = normalize(camRayDirNN(fp.camU, fp.camV, fp.camW, tapPos2.x, tapPos2.y, W, H)); }
+                    else { nOrigin = c_prev.prevPos; nDir = normalize(camRayDirNN(c_prev.prevU, c_prev.prevV, c_prev.prevW, tapPos2.x, tapPos2.y, W, H)); }
                     const float usedDepth = j == 0 ? taps[i].depth : (i == 0 ? centerPrevFrameDepth : temporalOriginalDepth);
                     Ray neighborRay = makeRay(nOrigin, nDir, 0, usedDepth);
                     const float backupDepth = taps[i].depth;
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(128, VR_MINB) k_spatial(FrameParams fp) {
                 if (j == 0) { p_qi = tap.p_y; p_sum += tap.p_y * t2.y; }
                 else if (sampleId == j) { p_qi = t2.w; p_sum += t2.w * t2.y; }
                 else {
-                    float3 neighborRayDir = normalize(camRayDirNN(c_scene.camU, c_scene.camV, c_scene.camW, tx2, ty2, W, H));
+                    float3 neighborRayDir = normalize(camRayDirNN(fp.camU, fp.camV, fp.camW, tx2, ty2, W, H));
                     Ray neighborRay = makeRay(ray.origin, neighborRayDir, 0, tap.depth);
                     float p_y = evaluate_P_hat<B>(neighborRay, sg, prov, fp.spatial, tap, false);
                     if (isinf(p_y) || isnan(p_y)) p_y = 0.f;
@@ -537,6 +537,7 @@ cudaError_t readDebugRays(float* out64x8, unsigned* count) {
     return e;
 }
 cudaError_t uploadScene(const DScene& s, cudaStream_t st) { return cudaMemcpyToSymbolAsync(c_scene, &s, sizeof(DScene), 0, cudaMemcpyHostToDevice, st); }
+cudaError_t uploadPrevCam(const DPrevCam& s, cudaStream_t st) { return cudaMemcpyToSymbolAsync(c_prev, &s, sizeof(DPrevCam), 0, cudaMemcpyHostToDevice, st); }
 
 #define VR_DISPATCH_B(kern, fp, st)                                                              \
     switch ((fp).maxBounces) {                                                                   \

@@ -5,6 +5,7 @@
 namespace vrd {
 cudaError_t readDebugRays(float* out64x8, unsigned* count);
 cudaError_t uploadScene(const DScene& s, cudaStream_t st);
+cudaError_t uploadPrevCam(const DPrevCam& s, cudaStream_t st);
 cudaError_t launchFeatures(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchInitial(const FrameParams& fp, cudaStream_t st);
 cudaError_t launchTemporal(const FrameParams& fp, cudaStream_t st);
@@ -14,6 +15,7 @@ cudaError_t launchImportance(float* importance, int dim, int sx, int sy, cudaStr
 cudaError_t launchImportanceMip(const float* src, float* dst, int d, cudaStream_t st);
 // wavefront path (vr_wavefront.cu)
 cudaError_t uploadSceneWavefront(const DScene& s, cudaStream_t st);
+cudaError_t uploadPrevCamWavefront(const DPrevCam& s, cudaStream_t st);
 int marchBlocksPerSM(int nt);
 cudaError_t readPairWatchdog(unsigned* out64x16, unsigned* count);
 void setPairEngine(int on);   // 1: explicit single-threshold FAST streams run on the phase-specialised engine (default 0)

@@ -211,7 +211,7 @@ struct RayMarcher : MarchTrav {
         rW.dir = make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
         outIdx = b.w;
         rW.tMin = 0.f;
-        rW.origin = kind.originMode == 1 ? c_scene.camPos : c_scene.prevPos;
+        rW.origin = make_float3(kind.origin[0], kind.origin[1], kind.origin[2]);
         const float v[3] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)};
         float thr[NT];
         todo = a.w & ((1u << NT) - 1u);

@@ -77,13 +77,24 @@ struct vrestir_pass {
 
     int W = 0, H = 0, rowBegin = 0, rowEnd = 0;
     int allocW = 0, allocH = 0, allocB = 0;
-    float4* res[3] = {nullptr, nullptr, nullptr};
+    float4* res[4] = {nullptr, nullptr, nullptr, nullptr};
     float3* ext[3] = {nullptr, nullptr, nullptr};
-    int2* feat[2] = {nullptr, nullptr};
+    int2* feat[3] = {nullptr, nullptr, nullptr};
     float4* refColor = nullptr;
-    int ia = 0, ib = 1, it = 2;        // physical indices of ping-pong buffers 0/1 and the temporal history
+    int ia = 0, ib = 1, it = 2, in = 3;   // physical indices of ping-pong buffers 0/1, the temporal history and the prefetch target
     int finalPhys = 0;                 // physical buffer holding the final reservoirs of the frame in flight
-    int featCur = 0, featPrev = 1;
+    int featCur = 0, featPrev = 1, featNext = 2;
+    DPrevCam prevCam{};
+    // Frame pipelining (option mPipelineFrames): K0 + K1 of frame f+1 read no history, so they run on a stream of their own while
+    // K2..K5 of frame f run on the caller's stream (the tail of every launch of one chain is filled by the other chain).
+    // The prefetched frame is adopted by the next execute when its key (camera, frame counter, band, options) still matches.
+    bool mPipelineFrames = false, pfValid = false, haveNextCam = false;
+    vrestir_camera nextCam{};
+    struct PrefetchKey { float cam[12]; int frameCount, W, H, rowBegin, rowEnd; vrestir_params P; } pfKey{};
+    cudaStream_t pfStream = nullptr; cudaEvent_t evPfGo = nullptr, evPfDone = nullptr, evPf0 = nullptr, evPf1 = nullptr;
+    bool pfTimed = false; uint64_t pfAdopted = 0, pfDiscarded = 0;
+    // K1's own scratch (its kernels may run next to the other stages')
+    uint4* k1LightTasks = nullptr; uint4* k1EvalTasks = nullptr; float* k1Results = nullptr; unsigned* k1Counters = nullptr;
     int mFrameCount = 0, mTemporalSampleAccumulated = 0; bool mOptionsChanged = true;
     cudaEvent_t ev[8] = {};
     bool evValid[8] = {};
@@ -91,12 +102,12 @@ struct vrestir_pass {
     bool mOverlapFeatures = true, framesOverlapped = false;
     cudaStream_t auxStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaEvent_t evMarch[3] = {}; bool evMarchValid = false;
-    int mInitialChains = 1; cudaStream_t auxStream2 = nullptr; cudaEvent_t evFork2 = nullptr, evJoin2 = nullptr;   // K1 row halves on two streams (option; measured neutral: 8.65 vs 8.56 ms)   // around the two march launches of the last spatial round
+                                                                      // evMarch: around the two march launches of the last spatial round
     cudaStream_t hostStream = nullptr;
     float4* d_hostColor = nullptr; float2* d_hostMvec = nullptr; size_t hostColorPixels = 0;
     uint64_t launches = 0;
     vrestir_timings timings{};
-    void* persistBase = nullptr; size_t persistBytes = 0;
+    void* persistBase = nullptr; size_t persistBytes = 0; void* persistBasePf = nullptr; size_t persistBytesPf = 0;
     // wavefront (task-stream) path: march-task streams, result blocks, counters {cam.count, cam.cursor, light.count, light.cursor}
     bool mUseWavefront = true;
     int mInitialMode = 1;   // K1: 0 per-pixel kernel, 1 lock-step wavefront (default)
@@ -115,17 +126,20 @@ int ensureBuffers(vrestir_pass* p) {
     const int B = p->P.mMaxBounces;
     if (p->allocW == p->W && p->allocH == p->H && p->allocB == B && p->res[0]) return VRESTIR_OK;
     const size_t n = N(p);
-    for (int i = 0; i < 3; i++) { if (p->res[i]) cudaFree(p->res[i]); if (p->ext[i]) cudaFree(p->ext[i]); p->res[i] = nullptr; p->ext[i] = nullptr; }
-    for (int i = 0; i < 2; i++) { if (p->feat[i]) cudaFree(p->feat[i]); p->feat[i] = nullptr; }
+    if (p->pfStream) CK(cudaStreamSynchronize(p->pfStream));
+    p->pfValid = false;
+    for (int i = 0; i < 4; i++) { if (p->res[i]) cudaFree(p->res[i]); p->res[i] = nullptr; }
+    for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); p->ext[i] = nullptr; }
+    for (int i = 0; i < 3; i++) { if (p->feat[i]) cudaFree(p->feat[i]); p->feat[i] = nullptr; }
     if (p->refColor) { cudaFree(p->refColor); p->refColor = nullptr; }
+    for (int i = 0; i < 4; i++) { CK(cudaMalloc(&p->res[i], n * 32)); CK(cudaMemset(p->res[i], 0, n * 32)); }
     for (int i = 0; i < 3; i++) {
-        CK(cudaMalloc(&p->res[i], n * 32)); CK(cudaMemset(p->res[i], 0, n * 32));
         if (B > 1) { CK(cudaMalloc(&p->ext[i], n * (size_t)(B - 1) * 12)); CK(cudaMemset(p->ext[i], 0, n * (size_t)(B - 1) * 12)); }
     }
-    for (int i = 0; i < 2; i++) { CK(cudaMalloc(&p->feat[i], n * 8)); CK(cudaMemset(p->feat[i], 0, n * 8)); }
+    for (int i = 0; i < 3; i++) { CK(cudaMalloc(&p->feat[i], n * 8)); CK(cudaMemset(p->feat[i], 0, n * 8)); }
     CK(cudaMalloc(&p->refColor, n * 16)); CK(cudaMemset(p->refColor, 0, n * 16));
     p->allocW = p->W; p->allocH = p->H; p->allocB = B;
-    p->ia = 0; p->ib = 1; p->it = 2; p->finalPhys = 0; p->featCur = 0; p->featPrev = 1;
+    p->ia = 0; p->ib = 1; p->it = 2; p->in = 3; p->finalPhys = 0; p->featCur = 0; p->featPrev = 1; p->featNext = 2;
     return VRESTIR_OK;
 }
 
@@ -166,8 +180,8 @@ bool wavefrontEvalOk(const vrestir_pass* p) {
 bool wavefrontSpatialOk(const vrestir_pass* p) { return wavefrontEvalOk(p) && p->P.mSpatialSampleCount <= 4; }
 void wavefrontKinds(const vrestir_pass* p, MarchKind& cam, MarchKind& light) {
     const vrestir_params& m = p->P;
-    cam = MarchKind{m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 1};
-    light = MarchKind{m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0};
+    cam = MarchKind{m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 1, {p->cam.posW[0], p->cam.posW[1], p->cam.posW[2]}};
+    light = MarchKind{m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0, {0.f, 0.f, 0.f}};
 }
 
 void freeSlot(DevSlot& d) {
@@ -279,6 +293,8 @@ void buildFrameParams(vrestir_pass* p, FrameParams& fp, float* out_color, float*
     const vrestir_params& m = p->P;
     memset(&fp, 0, sizeof(fp));
     fp.W = p->W; fp.H = p->H; fp.rowBegin = p->rowBegin; fp.rowEnd = p->rowEnd;
+    auto f3of = [](const float* a) { return make_float3(a[0], a[1], a[2]); };
+    fp.camPos = f3of(p->cam.posW); fp.camU = f3of(p->cam.cameraU); fp.camV = f3of(p->cam.cameraV); fp.camW = f3of(p->cam.cameraW);
     fp.frameCount = p->mFrameCount;
     fp.numTotalRounds = (m.mEnableSpatialReuse ? m.mSpatialReuseRounds : 0) + (m.mEnableTemporalReuse ? 1 : 0) + 1 + 1;   // VR/VolumetricReSTIR.cpp:452-453
     fp.maxBounces = m.mMaxBounces;
@@ -306,33 +322,44 @@ void buildFrameParams(vrestir_pass* p, FrameParams& fp, float* out_color, float*
 
 int syncScene(vrestir_pass* p, cudaStream_t st) {
     applyOverrides(p);
-    // camera
     DScene& s = p->scene;
-    auto f3of = [](const float* a) { return make_float3(a[0], a[1], a[2]); };
-    s.camPos = f3of(p->cam.posW); s.camU = f3of(p->cam.cameraU); s.camV = f3of(p->cam.cameraV); s.camW = f3of(p->cam.cameraW);
     s.envSamplerType = p->envSamplerType;
-    // the constant bank is shared by every pass of this process on this device: upload whenever anything may differ
-    static thread_local const vrestir_pass* lastOwner = nullptr;
+    // the constant banks are shared by every pass of this process on this device: upload whenever anything may differ
     static thread_local DScene lastScene;
-    if (lastOwner != p || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0) {
+    static thread_local DPrevCam lastPrev;
+    static thread_local bool haveLast = false;
+    if (!haveLast || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0) {
+        // a prefetched K0/K1 was computed with the old constants and may still be reading them
+        if (p->pfValid) { CK(cudaStreamWaitEvent(st, p->evPfDone, 0)); p->pfValid = false; p->pfDiscarded++; }
         CK(uploadScene(s, st));
         CK(uploadSceneWavefront(s, st));
         // the async copy reads `s` at enqueue time only when the source is pageable (staged); keep a private copy alive
-        lastScene = s; lastOwner = p; p->sceneDirty = false;
+        lastScene = s; p->sceneDirty = false;
+        if (p->pfStream) {   // later work on the prefetch stream must see the new constants
+            CK(cudaEventRecord(p->evPfGo, st)); CK(cudaStreamWaitEvent(p->pfStream, p->evPfGo, 0));
+        }
     }
+    if (!haveLast || memcmp(&lastPrev, &p->prevCam, sizeof(DPrevCam)) != 0) {   // read by K2 only, which runs on `st`
+        CK(uploadPrevCam(p->prevCam, st));
+        CK(uploadPrevCamWavefront(p->prevCam, st));
+        lastPrev = p->prevCam;
+    }
+    haveLast = true;
     return VRESTIR_OK;
 }
 
 void recordEv(vrestir_pass* p, int i, cudaStream_t st) { if (!p->ev[i]) cudaEventCreate(&p->ev[i]); cudaEventRecord(p->ev[i], st); p->evValid[i] = true; }
 
-int setPersistingWindow(vrestir_pass* p, cudaStream_t st) {
+int setPersistingWindow(vrestir_pass* p, cudaStream_t st, bool prefetchStream = false) {
     // "a coarse mip pinned in B200's L2": the atlas of the reuse mip (mSpatialVisibilityMipLevel) gets a persisting
     // access-policy window on the stream that runs K2/K3.
     int slot = p->P.mSpatialVisibilityMipLevel;
     if (slot < 0 || slot >= VRESTIR_MAX_SLOTS || !p->dslots[slot].atlas) return VRESTIR_OK;
     void* base = p->dslots[slot].quads ? p->dslots[slot].quads : p->dslots[slot].atlas;
     size_t bytes = p->dslots[slot].quads ? p->dslots[slot].quadBytes : p->dslots[slot].atlasBytes;
-    if (base == p->persistBase && bytes == p->persistBytes) return VRESTIR_OK;
+    void*& cachedBase = prefetchStream ? p->persistBasePf : p->persistBase;
+    size_t& cachedBytes = prefetchStream ? p->persistBytesPf : p->persistBytes;
+    if (base == cachedBase && bytes == cachedBytes) return VRESTIR_OK;
     int maxWin = 0, maxPersist = 0;
     cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, p->device);
     cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
@@ -347,7 +374,81 @@ int setPersistingWindow(vrestir_pass* p, cudaStream_t st) {
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
     cudaGetLastError();
-    p->persistBase = base; p->persistBytes = bytes;
+    cachedBase = base; cachedBytes = bytes;
+    return VRESTIR_OK;
+}
+
+// lock-step wavefront K1 (vr_wavefront.cu): single bounce, reuse on, <= 4 candidates, ray-marched light visibility
+bool initialWavefrontOk(const vrestir_pass* p) {
+    const vrestir_params& m = p->P;
+    const bool noReuse = !m.mEnableSpatialReuse && !m.mEnableTemporalReuse;
+    return wavefrontEvalOk(p) && !m.mUseReference && !noReuse && m.mInitialM <= 4 && m.mInitialLightingTrackingMethod == VRESTIR_RAY_MARCHING &&
+           m.mInitialLightSamples <= 1 && p->mInitialMode == 1;
+}
+
+void makePrefetchKey(const vrestir_pass* p, const vrestir_camera& c, int frameCount, vrestir_pass::PrefetchKey& k) {
+    memset(&k, 0, sizeof(k));
+    memcpy(k.cam, c.posW, 12); memcpy(k.cam + 3, c.cameraU, 12); memcpy(k.cam + 6, c.cameraV, 12); memcpy(k.cam + 9, c.cameraW, 12);
+    k.frameCount = frameCount; k.W = p->W; k.H = p->H; k.rowBegin = p->rowBegin; k.rowEnd = p->rowEnd;
+    k.P = p->P;
+}
+// does the prefetched K0/K1 belong to the frame that is starting now?
+bool prefetchMatches(const vrestir_pass* p) {
+    if (!p->pfValid || p->mFreezeFrame) return false;
+    vrestir_pass::PrefetchKey k;
+    makePrefetchKey(p, p->cam, p->mFrameCount, k);
+    return memcmp(&k, &p->pfKey, sizeof(k)) == 0;
+}
+
+int ensureInitialScratch(vrestir_pass* p) {
+    const size_t n = (size_t)(p->rowEnd - p->rowBegin) * p->W;
+    if (p->wfInitialPixels == n && p->wfInitialState) return VRESTIR_OK;
+    if (p->pfStream) CK(cudaStreamSynchronize(p->pfStream));
+    p->pfValid = false;
+    void* old[] = {p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results};
+    for (void* q : old) if (q) cudaFree(q);
+    p->wfInitialState = nullptr; p->k1LightTasks = p->k1EvalTasks = nullptr; p->k1Results = nullptr; p->wfInitialPixels = 0;
+    if (n * K1_STRIDE >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit record indices; shard the frame");
+    CK(cudaMalloc(&p->wfInitialState, n * K1_STRIDE * sizeof(float) + n));   // + one done flag per pixel
+    CK(cudaMalloc(&p->k1LightTasks, n * 48));                                // one light task per pixel and candidate wave
+    CK(cudaMalloc(&p->k1EvalTasks, 2 * n * 48));                             // final p-hat: <= one camera + one light task per pixel
+    CK(cudaMalloc(&p->k1Results, n * K1_EVAL_BLOCK * sizeof(float)));
+    if (!p->k1Counters) CK(cudaMalloc(&p->k1Counters, 64));
+    p->wfInitialPixels = n;
+    if (!p->marchBlocks1) {
+        int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+        p->marchBlocks1 = sms * marchBlocksPerSM(1); p->marchBlocks3 = sms * marchBlocksPerSM(3);
+    }
+    return VRESTIR_OK;
+}
+
+// K1 as M + 1 lock-step waves over the band: traverse, then per candidate s {finish candidate s-1 / emit the light march of
+// candidate s, march}, the p-hat evaluation of the surviving sample under the spatial options, finish.  Works entirely in
+// its own scratch, on `st` (the caller's stream or the prefetch stream).  fp.cur is the output reservoir buffer.
+int runInitialWavefront(vrestir_pass* p, const FrameParams& fp, cudaStream_t st) {
+    const vrestir_params& m = p->P;
+    int rc = ensureInitialScratch(p); if (rc) return rc;
+    const size_t n = p->wfInitialPixels;
+    MarchKind kc, klp; wavefrontKinds(p, kc, klp); kc.originMode = 0; kc.origin[0] = kc.origin[1] = kc.origin[2] = 0.f;   // explicit-origin tasks
+    const bool oneEval = memcmp(&kc, &klp, sizeof(MarchKind)) == 0;
+    const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0, {0.f, 0.f, 0.f}};
+    unsigned* cnt = p->k1Counters;
+    CK(cudaMemsetAsync(cnt, 0, 64, st));
+    WfInitial wi;
+    wi.light.tasks = p->k1LightTasks; wi.light.count = cnt; wi.light.cursor = cnt + 1; wi.light.capacity = (unsigned)n;
+    wi.state = p->wfInitialState; wi.done = (uint8_t*)(p->wfInitialState + n * K1_STRIDE);
+    wi.results = p->k1Results;
+    wi.evalCam.tasks = p->k1EvalTasks; wi.evalCam.count = cnt + 4; wi.evalCam.cursor = cnt + 5; wi.evalCam.capacity = (unsigned)(oneEval ? 2 * n : n);
+    if (oneEval) wi.evalLight = wi.evalCam;
+    else { wi.evalLight.tasks = p->k1EvalTasks + 3 * n; wi.evalLight.count = cnt + 6; wi.evalLight.cursor = cnt + 7; wi.evalLight.capacity = (unsigned)n; }
+    for (int s = 0; s <= m.mInitialM; s++) {
+        if (s > 0 && s < m.mInitialM) CK(cudaMemsetAsync(cnt, 0, 8, st));
+        CK(launchInitialStep(fp, wi, s, st)); p->launches += s == 0 ? 2 : 1;
+        if (s < m.mInitialM) { CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st)); p->launches++; }
+    }
+    CK(launchMarch(wi.evalCam, wi.results, kc, p->scene.slots[kc.mip], 1, p->marchBlocks1, st)); p->launches++;
+    if (!oneEval) { CK(launchMarch(wi.evalLight, wi.results, klp, p->scene.slots[klp.mip], 1, p->marchBlocks1, st)); p->launches++; }
+    CK(launchInitialFinish(fp, wi, st)); p->launches++;
     return VRESTIR_OK;
 }
 
@@ -387,65 +488,29 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
         case 0:
             recordEv(p, 0, st);
             setPersistingWindow(p, st);
-            if (active && !m.mUseReference) { CK(launchFeatures(fp, st)); p->launches++; }
+            if (prefetchMatches(p)) {
+                // K0 of this frame ran ahead on the prefetch stream into feat[featNext]: adopt it (stage 1 waits for the chain)
+                std::swap(p->featCur, p->featNext);
+            } else if (active && !m.mUseReference) { CK(launchFeatures(fp, st)); p->launches++; }
             recordEv(p, 1, st);
             break;
         case 1:
             if (active) {
+                if (prefetchMatches(p)) {
+                    // K1 of this frame ran ahead into res[in]: it becomes ping-pong buffer 0, the old one the next prefetch target
+                    CK(cudaStreamWaitEvent(st, p->evPfDone, 0));
+                    std::swap(p->ia, p->in);
+                    p->pfValid = false; p->pfAdopted++;
+                    p->finalPhys = p->ia;
+                    recordEv(p, 2, st);
+                    break;
+                }
+                if (p->pfValid) {   // stale prefetch (camera / options moved on): its scratch must be idle before K1 reuses it
+                    CK(cudaStreamWaitEvent(st, p->evPfDone, 0)); p->pfValid = false; p->pfDiscarded++;
+                }
                 fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
-                // lock-step wavefront K1 (vr_wavefront.cu): single bounce, reuse on, <= 4 candidates, ray-marched light visibility
-                const bool wfInitial = wavefrontEvalOk(p) && !m.mUseReference && !fp.noReuse && m.mInitialM <= 4 &&
-                                       m.mInitialLightingTrackingMethod == VRESTIR_RAY_MARCHING && m.mInitialLightSamples <= 1 && p->mInitialMode == 1;
-                if (wfInitial) {
-                    rc = ensureWavefront(p); if (rc) return rc;
-                    const size_t n = p->wfPixels;
-                    if (p->wfInitialPixels != n) {
-                        if (p->wfInitialState) cudaFree(p->wfInitialState);
-                        p->wfInitialState = nullptr; p->wfInitialPixels = 0;
-                        if (n * K1_STRIDE >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit record indices; shard the frame");
-                        CK(cudaMalloc(&p->wfInitialState, n * K1_STRIDE * sizeof(float) + n));   // + one done flag per pixel
-                        p->wfInitialPixels = n;
-                    }
-                    // Two chains: the band is cut into two row halves that run the lock-step sequence on two streams, so the tail of
-                    // one half's march kernel (few long rays left) is filled by the other half's kernels.
-                    MarchKind kc, klp; wavefrontKinds(p, kc, klp); kc.originMode = 0;
-                    const bool oneEval = memcmp(&kc, &klp, sizeof(MarchKind)) == 0;
-                    const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0};
-                    const int rows = p->rowEnd - p->rowBegin;
-                    const int chains = (p->mInitialChains > 1 && rows >= 32) ? 2 : 1;
-                    const int mid = chains == 2 ? p->rowBegin + ((rows / 2 + 7) / 8) * 8 : p->rowEnd;
-                    if (chains == 2) {
-                        if (!p->auxStream2) { CK(cudaStreamCreateWithFlags(&p->auxStream2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&p->evFork2, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->evJoin2, cudaEventDisableTiming)); }
-                    }
-                    CK(cudaMemsetAsync(p->wfCounters, 0, 128, st));
-                    if (chains == 2) { CK(cudaEventRecord(p->evFork2, st)); CK(cudaStreamWaitEvent(p->auxStream2, p->evFork2, 0)); }
-                    fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
-                    for (int c = 0; c < chains; c++) {
-                        cudaStream_t sc = c == 0 ? st : p->auxStream2;
-                        FrameParams fh = fp;
-                        fh.rowBegin = c == 0 ? p->rowBegin : mid; fh.rowEnd = c == 0 ? mid : p->rowEnd;
-                        const size_t off = (size_t)(fh.rowBegin - p->rowBegin) * p->W, nh = (size_t)(fh.rowEnd - fh.rowBegin) * p->W;
-                        unsigned* cnt = p->wfCounters + 16 * c;
-                        WfInitial wi;
-                        wi.light.tasks = p->wfLightTasks + 3 * off; wi.light.count = cnt; wi.light.cursor = cnt + 1; wi.light.capacity = (unsigned)nh;
-                        wi.state = p->wfInitialState + off * K1_STRIDE; wi.done = (uint8_t*)(p->wfInitialState + n * K1_STRIDE) + off;
-                        // the final p-hat evaluation (spatial options): explicit camera + light tasks in the camera-task buffer
-                        // (<= one of each per pixel, 48 B); one stream when both march configurations are equal
-                        wi.results = p->wfResults + off * WF_BLOCK;
-                        uint4* evalBase = p->wfCamTasks + 3 * (2 * off);
-                        wi.evalCam.tasks = evalBase; wi.evalCam.count = cnt + 4; wi.evalCam.cursor = cnt + 5; wi.evalCam.capacity = (unsigned)(oneEval ? 2 * nh : nh);
-                        if (oneEval) wi.evalLight = wi.evalCam;
-                        else { wi.evalLight.tasks = evalBase + 3 * nh; wi.evalLight.count = cnt + 6; wi.evalLight.cursor = cnt + 7; wi.evalLight.capacity = (unsigned)nh; }
-                        for (int s = 0; s <= m.mInitialM; s++) {
-                            if (s > 0 && s < m.mInitialM) CK(cudaMemsetAsync(cnt, 0, 8, sc));
-                            CK(launchInitialStep(fh, wi, s, sc)); p->launches += s == 0 ? 2 : 1;
-                            if (s < m.mInitialM) { CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, sc)); p->launches++; }
-                        }
-                        CK(launchMarch(wi.evalCam, wi.results, kc, p->scene.slots[kc.mip], 1, p->marchBlocks1, sc)); p->launches++;
-                        if (!oneEval) { CK(launchMarch(wi.evalLight, wi.results, klp, p->scene.slots[klp.mip], 1, p->marchBlocks1, sc)); p->launches++; }
-                        CK(launchInitialFinish(fh, wi, sc)); p->launches++;
-                    }
-                    if (chains == 2) { CK(cudaEventRecord(p->evJoin2, p->auxStream2)); CK(cudaStreamWaitEvent(st, p->evJoin2, 0)); }
+                if (initialWavefrontOk(p)) {
+                    rc = runInitialWavefront(p, fp, st); if (rc) return rc;
                     p->finalPhys = p->ia;
                     recordEv(p, 2, st);
                     break;
@@ -455,6 +520,36 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
             }
             recordEv(p, 2, st);
             break;
+        case 7: {
+            // Prefetch: K0 + K1 of the NEXT frame on the prefetch stream.  Call after stage 1 of the frame in flight (its K1 has
+            // released the K1 scratch) and before stage 2, so that the chain overlaps K2..K5.  No-op unless mPipelineFrames.
+            if (!p->mPipelineFrames || !active || m.mUseReference || !initialWavefrontOk(p) || p->pfValid) break;
+            if (!p->pfStream) {
+                CK(cudaStreamCreateWithFlags(&p->pfStream, cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&p->evPfGo, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->evPfDone, cudaEventDisableTiming));
+                CK(cudaEventCreate(&p->evPf0)); CK(cudaEventCreate(&p->evPf1));
+            }
+            FrameParams fn = fp;
+            const vrestir_camera& c = p->haveNextCam ? p->nextCam : p->cam;
+            auto f3of = [](const float* a) { return make_float3(a[0], a[1], a[2]); };
+            fn.camPos = f3of(c.posW); fn.camU = f3of(c.cameraU); fn.camV = f3of(c.cameraV); fn.camW = f3of(c.cameraW);
+            fn.frameCount = p->mFrameCount + 1;
+            fn.features = p->feat[p->featNext];
+            fn.cur = resView(p, p->in); fn.extCur = nullptr;
+            // everything enqueued so far on `st` (the previous frame, this frame's K1) is done with the target buffers / the scratch
+            CK(cudaEventRecord(p->evPfGo, st));
+            CK(cudaStreamWaitEvent(p->pfStream, p->evPfGo, 0));
+            setPersistingWindow(p, p->pfStream, true);
+            CK(cudaEventRecord(p->evPf0, p->pfStream));
+            CK(launchFeatures(fn, p->pfStream)); p->launches++;
+            rc = runInitialWavefront(p, fn, p->pfStream); if (rc) return rc;
+            CK(cudaEventRecord(p->evPf1, p->pfStream));
+            CK(cudaEventRecord(p->evPfDone, p->pfStream));
+            p->pfTimed = true;
+            makePrefetchKey(p, c, fn.frameCount, p->pfKey);
+            p->pfValid = true;
+            break;
+        }
         case 2:
             if (active && !m.mUseReference && m.mEnableTemporalReuse) {
                 if (p->mTemporalSampleAccumulated != 0) {   // gIsFirstFrame skips the kernel (VR/TemporalReuse.cs.slang:93)
@@ -561,9 +656,8 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
         case 6: {   // VR/VolumetricReSTIR.cpp:765-772 (+ :636 feature history, as a swap)
             if (active && !m.mUseReference && m.mEnableTemporalReuse) std::swap(p->featCur, p->featPrev);
             p->mTemporalSampleAccumulated = 1;
-            memcpy(p->scene.prevView, p->cam.viewMat, 64); memcpy(p->scene.prevProj, p->cam.projMat, 64);
-            p->scene.prevU = p->scene.camU; p->scene.prevV = p->scene.camV; p->scene.prevW = p->scene.camW; p->scene.prevPos = p->scene.camPos;
-            p->sceneDirty = true;
+            memcpy(p->prevCam.prevView, p->cam.viewMat, 64); memcpy(p->prevCam.prevProj, p->cam.projMat, 64);
+            p->prevCam.prevU = fp.camU; p->prevCam.prevV = fp.camV; p->prevCam.prevW = fp.camW; p->prevCam.prevPos = fp.camPos;
             if (!p->mFreezeFrame) p->mFrameCount++;
             break;
         }
@@ -673,9 +767,9 @@ int vrestir_destroy(vrestir_pass* p) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
     for (auto& d : p->dslots) freeSlot(d);
-    for (int i = 0; i < 3; i++) { if (p->res[i]) cudaFree(p->res[i]); if (p->ext[i]) cudaFree(p->ext[i]); }
-    for (int i = 0; i < 2; i++) if (p->feat[i]) cudaFree(p->feat[i]);
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState};
+    for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
+    for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); if (p->feat[i]) cudaFree(p->feat[i]); }
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
@@ -683,9 +777,8 @@ int vrestir_destroy(vrestir_pass* p) {
     if (p->evFork) cudaEventDestroy(p->evFork);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
     for (auto& e : p->evMarch) if (e) cudaEventDestroy(e);
-    if (p->auxStream2) cudaStreamDestroy(p->auxStream2);
-    if (p->evFork2) cudaEventDestroy(p->evFork2);
-    if (p->evJoin2) cudaEventDestroy(p->evJoin2);
+    if (p->pfStream) cudaStreamDestroy(p->pfStream);
+    for (cudaEvent_t e : {p->evPfGo, p->evPfDone, p->evPf0, p->evPf1}) if (e) cudaEventDestroy(e);
     delete p;
     return VRESTIR_OK;
 }
@@ -700,7 +793,7 @@ int vrestir_set_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
     if (p->d_lut) { cudaFree(p->d_lut); p->d_lut = nullptr; }
     if (g->blackbody_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, g->blackbody_lut, 2048, cudaMemcpyHostToDevice)); }
     p->scene.lut = (const float4*)p->d_lut;
-    p->haveVolume = true; p->sceneDirty = true; p->mOptionsChanged = true; p->persistBase = nullptr;
+    p->haveVolume = true; p->sceneDirty = true; p->mOptionsChanged = true; p->persistBase = p->persistBasePf = nullptr;
     applyOverrides(p);
     return VRESTIR_OK;
 }
@@ -721,14 +814,14 @@ int vrestir_advance_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
     for (int s = 0; s < VRESTIR_PREV_DENSITY_GRID_OFFSET - 1; s++) { int rc = uploadSlot(p, s, g->slots[s]); if (rc) return rc; }
     p->volBase = g->volume; p->volBase.lastFrameHasEmission = lastHasEmission; p->volBase.hasAnimation = 1;
     if (g->blackbody_lut && !p->d_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, g->blackbody_lut, 2048, cudaMemcpyHostToDevice)); p->scene.lut = (const float4*)p->d_lut; }
-    p->sceneDirty = true; p->persistBase = nullptr;
+    p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr;
     applyOverrides(p);
     return VRESTIR_OK;
 }
 
 int vrestir_set_camera(vrestir_pass* p, const vrestir_camera* cam) {
     if (!p || !cam) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
-    p->cam = *cam; p->haveCamera = true; p->sceneDirty = true;
+    p->cam = *cam; p->haveCamera = true;
     return VRESTIR_OK;
 }
 
@@ -855,7 +948,7 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
         else if (k == "mUseWavefront") p->mUseWavefront = value != 0;
         else if (k == "mInitialMode") p->mInitialMode = (int)value;
         else if (k == "mOverlapFeatures") p->mOverlapFeatures = value != 0;
-        else if (k == "mInitialChains") p->mInitialChains = (int)value;
+        else if (k == "mPipelineFrames") p->mPipelineFrames = value != 0;
         else if (k == "mMarchPairEngine") setPairEngine(value != 0);   // process-wide A/B switch of the march engine   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
@@ -886,11 +979,10 @@ int vrestir_get_frame_count(const vrestir_pass* p, int* fc) {
 /* previous-frame camera for staged parity tests of K2 (normally saved by stage 6) */
 int vrestir_set_prev_camera(vrestir_pass* p, const vrestir_camera* cam) {
     if (!p || !cam) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
-    DScene& s = p->scene;
+    DPrevCam& s = p->prevCam;
     memcpy(s.prevView, cam->viewMat, 64); memcpy(s.prevProj, cam->projMat, 64);
     s.prevU = make_float3(cam->cameraU[0], cam->cameraU[1], cam->cameraU[2]); s.prevV = make_float3(cam->cameraV[0], cam->cameraV[1], cam->cameraV[2]);
     s.prevW = make_float3(cam->cameraW[0], cam->cameraW[1], cam->cameraW[2]); s.prevPos = make_float3(cam->posW[0], cam->posW[1], cam->posW[2]);
-    p->sceneDirty = true;
     return VRESTIR_OK;
 }
 
@@ -902,7 +994,9 @@ int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* st
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
-    const bool overlap = p->mOverlapFeatures && !p->P.mUseReference && !p->mFreezeFrame;
+    // a matching prefetch already holds K0/K1 of this frame: stages 0/1 only adopt it (matching is re-checked there after the
+    // options / scene bookkeeping of the frame start)
+    const bool overlap = p->mOverlapFeatures && !p->P.mUseReference && !p->mFreezeFrame && !p->pfValid;
     p->framesOverlapped = overlap;
     if (overlap) {
         CK(cudaSetDevice(p->device));
@@ -918,6 +1012,7 @@ int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* st
         if ((rc = runStage(p, 0, 0, out_color, out_mvec, st))) return rc;
         if ((rc = runStage(p, 1, 0, out_color, out_mvec, st))) return rc;
     }
+    if ((rc = runStage(p, 7, 0, out_color, out_mvec, st))) return rc;   // mPipelineFrames: K0 + K1 of the next frame start now
     if ((rc = runStage(p, 2, 0, out_color, out_mvec, st))) return rc;
     if (p->P.mEnableSpatialReuse) { for (int r = 0; r < p->P.mSpatialReuseRounds; r++) if ((rc = runStage(p, 3, r, out_color, out_mvec, st))) return rc; }
     else recordEv(p, 4, st);
@@ -991,6 +1086,22 @@ int vrestir_debug_read_bandwidth(int device, size_t bytes, int iters, float* gbs
     float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
     *gbs = (float)((double)(bytes / 16 * 16) * iters / (ms * 1e-3) / 1e9);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
+    return VRESTIR_OK;
+}
+int vrestir_set_next_camera(vrestir_pass* p, const vrestir_camera* cam) {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    if (cam) { p->nextCam = *cam; p->haveNextCam = true; } else p->haveNextCam = false;
+    return VRESTIR_OK;
+}
+int vrestir_get_pipeline_stats(vrestir_pass* p, vrestir_pipeline_stats* out) {
+    if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    memset(out, 0, sizeof(*out));
+    out->adopted = p->pfAdopted; out->discarded = p->pfDiscarded;
+    if (p->pfTimed) {
+        CK(cudaSetDevice(p->device));
+        CK(cudaEventSynchronize(p->evPf1));
+        CK(cudaEventElapsedTime(&out->prefetch_ms, p->evPf0, p->evPf1));
+    }
     return VRESTIR_OK;
 }
 int vrestir_get_launch_count(const vrestir_pass* p, uint64_t* out) {

@@ -29,9 +29,8 @@ struct DScene {
     DSlot slots[VRESTIR_MAX_SLOTS];
     vrestir_volume_desc vol;
     const float4* lut;
-    float3 camPos, camU, camV, camW;
-    float prevView[16], prevProj[16];
-    float3 prevU, prevV, prevW, prevPos;
+    // the cameras are not here: the current one travels in FrameParams (kernel parameter), the previous frame's in DPrevCam —
+    // so this block only changes when the scene does, and the kernels of two frames in flight can share it
     int haveEnv, envW, envH;
     const float4* envTexels;
     float envIntensity; float3 envTint;
@@ -41,6 +40,12 @@ struct DScene {
     int lightCount; const vrestir_light* lights;
     int triCount; const vrestir_emissive_triangle* tris; const uint4* alias; const float* aliasWeights;
     float aliasWeightSum, emissiveMul;
+};
+
+// previous frame's camera (K2 only); uploaded on the main stream every frame
+struct DPrevCam {
+    float prevView[16], prevProj[16];
+    float3 prevU, prevV, prevW, prevPos;
 };
 
 struct SamplingOptions {   // VR/HostDeviceSharedDefinitions.h:82-138
@@ -58,6 +63,7 @@ struct ResBuf { float4* p0; float4* p1; };
 
 struct FrameParams {
     int W, H, rowBegin, rowEnd;
+    float3 camPos, camU, camV, camW;   // camera of the frame these parameters belong to (the frame in flight or the prefetched next one)
     int frameCount, numTotalRounds, maxBounces;
     int useReference, baselineSpp, initialM, useRussianRoulette, noReuse, useCoarserGrid;
     int visualizeTransmittance, outputMotionVec;
@@ -78,14 +84,14 @@ struct FrameParams {
 // Explicit tasks (originMode 0) are 3 x uint4, prepared by the emitter: (pos.xyz, tNear | dir.xyz, tFar | result index) with
 // the ray in the index space of the march mip and clipped to the volume box.  Camera tasks (originMode 1/2: origin = current /
 // previous camera position) are 2 x uint4: (thr0, thr1, thr2, threshold mask | world dir.xyz, result index).
-struct MarchKind { int mip, linear; float tStepScale; int originMode; };
+struct MarchKind { int mip, linear; float tStepScale; int originMode; float origin[3]; };   // origin: camera-task ray origin (originMode != 0)
 struct WfStream { uint4* tasks; unsigned* count; unsigned* cursor; unsigned capacity; };
 // per-pixel result block (floats): D[i*4+j] density of tap i's sample seen from ray j, C[j*3+k] camera transmittance along
 // ray j to the depth of tap i (k = i - (i > j)), L[i*4+j] light transmittance from that point
 enum { WF_BLOCK = 48, WF_D = 0, WF_C = 16, WF_L = 28 };
 struct WfBufs { WfStream cam, light; float* results; };
 // K1 lock-step candidate state: K1_STRIDE floats per pixel (vr_wavefront.cu)
-enum { K1_WORDS = 20, K1_STRIDE = 80 };
+enum { K1_WORDS = 20, K1_STRIDE = 80, K1_EVAL_BLOCK = 4 };   // K1_EVAL_BLOCK: floats per pixel of K1's p-hat results (density, camera Tr, light Tr)
 struct WfInitial { WfStream light; float* state; uint8_t* done; WfStream evalCam, evalLight; float* results; };
 // K2: four explicit-origin streams {current camera, current light, previous-frame camera, previous-frame light};
 // streams whose march configuration is identical alias the same buffer

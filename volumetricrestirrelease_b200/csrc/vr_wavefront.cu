@@ -44,7 +44,7 @@ VRD bool tapInImage(const FrameParams& fp, int x, int y, int s, int& tx, int& ty
     return tx >= 0 && tx < fp.W && ty >= 0 && ty < fp.H;
 }
 VRD float3 tapRayDir(const FrameParams& fp, int tx, int ty) {
-    return normalize(camRayDirNN(c_scene.camU, c_scene.camV, c_scene.camW, tx, ty, fp.W, fp.H));
+    return normalize(camRayDirNN(fp.camU, fp.camV, fp.camW, tx, ty, fp.W, fp.H));
 }
 
 // The tap loops are ROLLED (the four ray directions / tap depths live in shared memory): fully unrolled, the 12 inlined
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
             active = false;
         }
     }
-    const float3 origin = c_scene.camPos;
+    const float3 origin = fp.camPos;
     unsigned camBits = 0;     // bit j*3+k: camera ray j needs the transmittance to the depth of tap i, k = i - (i > j)
     unsigned lightBits = 0;   // bit i*4+j: light march from ray_j.at(depth_i)
     unsigned inImage = 0;     // bit s: tap s lies in the image
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128, VR_SCOMB_MINB) k_spatial_combine(FramePar
     const uint32_t mis = fp.spatialMIS;
     Reservoir output = loadReservoir(fp.cur, pixelId, 1);
     if (mis == VRESTIR_MIS_TALBOT) output = createNewReservoir();
-    const float3 origin = c_scene.camPos;
+    const float3 origin = fp.camPos;
     const float3 dir0 = tapRayDir(fp, x, y);
     const int startSampleId = mis == VRESTIR_MIS_TALBOT ? 0 : 1;
     for (int sampleId = startSampleId; sampleId < S; sampleId++) {
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
         }
     }
     if (MODE != 2) wfEmitRay(wi.light, hasTask, shadow, o.lightingMipLevel, false, wi.state, recBase + 18);
-    if (MODE != 1) wfEmitEval(wantEval, evalTap, c_scene.camPos, evalDir, false, wi.results, (unsigned)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK,
+    if (MODE != 1) wfEmitEval(wantEval, evalTap, fp.camPos, evalDir, false, wi.results, (unsigned)(pixelId - fp.rowBegin * fp.W) * K1_EVAL_BLOCK,
                               wi.evalCam, fp.spatial.visibilityMipLevel, wi.evalLight, fp.spatial.lightingMipLevel);
 }
 
@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfInitia
     const float4 a = fp.cur.p0[pixelId];   // (runningSum, M, depth, p_y)
     if (!(a.x > 0.f)) return;
     Reservoir r = loadReservoirRW(fp.cur, pixelId, 1);
-    const float* blk = wi.results + (size_t)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
-    const float p_hat = wfPHatV(r, c_scene.camPos, tapRayDir(fp, x, y), false, blk[0], blk[1], blk[2]);
+    const float* blk = wi.results + (size_t)(pixelId - fp.rowBegin * fp.W) * K1_EVAL_BLOCK;
+    const float p_hat = wfPHatV(r, fp.camPos, tapRayDir(fp, x, y), false, blk[0], blk[1], blk[2]);
     r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
     r.p_y = p_hat;
     fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfInitia
 enum { T2_E0 = 0, T2_E1 = 3, T2_FLAG = 6, T2_POS = 7, T2_SG = 9 };
 
 VRD float3 prevRayDir(const FrameParams& fp, int px, int py) {
-    return normalize(camRayDirNN(c_scene.prevU, c_scene.prevV, c_scene.prevW, px, py, fp.W, fp.H));
+    return normalize(camRayDirNN(c_prev.prevU, c_prev.prevV, c_prev.prevW, px, py, fp.W, fp.H));
 }
 
 #ifndef VR_TGATHER_MINB
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(128, VR_TGATHER_MINB) k_temporal_gather(FrameP
                 float3 v = VelocityWorld(pw) * c_scene.vol.velocityScale;
                 pw = pw - v;
             }
-            const float* Vm = c_scene.prevView; const float* Pm = c_scene.prevProj;
+            const float* Vm = c_prev.prevView; const float* Pm = c_prev.prevProj;
             float vp[4], cp[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) vp[j] = pw.x * Vm[0 + j] + pw.y * Vm[4 + j] + pw.z * Vm[8 + j] + 1.f * Vm[12 + j];
@@ -618,11 +618,11 @@ __global__ void __launch_bounds__(128, VR_TGATHER_MINB) k_temporal_gather(FrameP
             t1 = loadReservoir(fp.temporal, reprojScreenPos.y * W + reprojScreenPos.x, 1);
             dirPrev = prevRayDir(fp, reprojScreenPos.x, reprojScreenPos.y);
             if (t1.depth != kRayTMax) {
-                float3 worldPos = c_scene.prevPos + t1.depth * dirPrev;
+                float3 worldPos = c_prev.prevPos + t1.depth * dirPrev;
                 t1.depth = length(worldPos - ray.origin);
             }
             float centerPrevFrameDepth = t0.depth;
-            if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_scene.prevPos); }
+            if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_prev.prevPos); }
             // E1: resampleNeighbor(taps[1]) on the current ray
             if (t1.p_y > 0.f) {
                 if (isnan(t1.runningSum) || isinf(t1.runningSum)) t1.runningSum = 0.f;
@@ -636,8 +636,8 @@ __global__ void __launch_bounds__(128, VR_TGATHER_MINB) k_temporal_gather(FrameP
             t0.depth = centerPrevFrameDepth;   // usedDepth of the (i = 0, j = 1) term
         }
     }
-    wfEmitEval(wantE1, t1, c_scene.camPos, dirCur, false, wf.results, blkBase + T2_E1, wf.s[0], wf.mip[0], wf.s[1], wf.mip[1]);
-    wfEmitEval(wantE0, t0, c_scene.prevPos, dirPrev, true, wf.results, blkBase + T2_E0, wf.s[2], wf.mip[2], wf.s[3], wf.mip[3]);
+    wfEmitEval(wantE1, t1, fp.camPos, dirCur, false, wf.results, blkBase + T2_E1, wf.s[0], wf.mip[0], wf.s[1], wf.mip[1]);
+    wfEmitEval(wantE0, t0, c_prev.prevPos, dirPrev, true, wf.results, blkBase + T2_E0, wf.s[2], wf.mip[2], wf.s[3], wf.mip[3]);
 }
 
 __global__ void __launch_bounds__(128, VR_TCOMB_MINB) k_temporal_combine(FrameParams fp, WfBufs4 wf) {
@@ -661,11 +661,11 @@ __global__ void __launch_bounds__(128, VR_TCOMB_MINB) k_temporal_combine(FramePa
     const float MaxPrevM = fp.temporalMThreshold * curM;
     const float3 dirPrev = prevRayDir(fp, reprojScreenPos.x, reprojScreenPos.y);
     if (taps[1].depth != kRayTMax) {
-        float3 worldPos = c_scene.prevPos + taps[1].depth * dirPrev;
+        float3 worldPos = c_prev.prevPos + taps[1].depth * dirPrev;
         taps[1].depth = length(worldPos - ray.origin);
     }
     float centerPrevFrameDepth = taps[0].depth;
-    if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_scene.prevPos); }
+    if (centerPrevFrameDepth != kRayTMax) { float3 worldPos = ray.at(centerPrevFrameDepth); centerPrevFrameDepth = length(worldPos - c_prev.prevPos); }
     const int startSampleId = mis == VRESTIR_MIS_TALBOT ? 0 : 1;
     for (int i = startSampleId; i < numUsedReservoirs; i++) {
         float talbotMISWeight = 1.f;
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(128, VR_TCOMB_MINB) k_temporal_combine(FramePa
                 else {
                     // i == 0, j == 1: taps[0] at depth centerPrevFrameDepth on the previous frame's ray
                     Reservoir tp = taps[i]; tp.depth = centerPrevFrameDepth;
-                    float p_y = wfPHatV(tp, c_scene.prevPos, dirPrev, true, blk[T2_E0], blk[T2_E0 + 1], blk[T2_E0 + 2]);
+                    float p_y = wfPHatV(tp, c_prev.prevPos, dirPrev, true, blk[T2_E0], blk[T2_E0 + 1], blk[T2_E0 + 2]);
                     if (isinf(p_y) || isnan(p_y)) p_y = 0.f;
                     p_sum += p_y * correctedM;
                 }
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(128) k_final_gather(FrameParams fp, WfStream s
         if (cur.runningSum > 0.f) {
             const bool noReuse = fp.noReuse != 0;
             const bool bg = cur.depth == kRayTMax;
-            r = makeRay(c_scene.camPos, tapRayDir(fp, x, y), 0.f, cur.depth);
+            r = makeRay(fp.camPos, tapRayDir(fp, x, y), 0.f, cur.depth);
             const float3 pW = r.at(r.tMax);
             const float density = (bg || noReuse) ? 1.f : DensityWorldSpace(pW, 0);
             results[out] = density;
@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const flo
     const Reservoir cur = loadReservoir(fp.cur, pixelId, 1);
     if (cur.runningSum > 0.f) {
         const bool noReuse = fp.noReuse != 0;
-        float3 col = wfFV(cur, c_scene.camPos, tapRayDir(fp, x, y), false, noReuse, blk[0], noReuse ? 1.f : blk[1], blk[2]);
+        float3 col = wfFV(cur, fp.camPos, tapRayDir(fp, x, y), false, noReuse, blk[0], noReuse ? 1.f : blk[1], blk[2]);
         const float Wt = cur.p_y == 0.0f ? 1.f : cur.runningSum / (cur.p_y * cur.M);
         col = col * Wt;
         outputColor = outputColor + col;
@@ -759,8 +759,17 @@ __global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const flo
 
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 gridForWf(const FrameParams& fp) { return dim3((fp.W + 15) / 16, (fp.rowEnd - fp.rowBegin + 7) / 8); }
+// one warp (8x4 tile) per CTA
+static dim3 gridForWarp(const FrameParams& fp) { return dim3((fp.W + 7) / 8, (fp.rowEnd - fp.rowBegin + 3) / 4); }
+#ifndef VR_TRAV_BLOCK
+#define VR_TRAV_BLOCK 128
+#endif
+#ifndef VR_TGATHER_BLOCK
+#define VR_TGATHER_BLOCK 128
+#endif
 
 cudaError_t uploadSceneWavefront(const DScene& s, cudaStream_t st) { return cudaMemcpyToSymbolAsync(c_scene, &s, sizeof(DScene), 0, cudaMemcpyHostToDevice, st); }
+cudaError_t uploadPrevCamWavefront(const DPrevCam& s, cudaStream_t st) { return cudaMemcpyToSymbolAsync(c_prev, &s, sizeof(DPrevCam), 0, cudaMemcpyHostToDevice, st); }
 
 int marchBlocksPerSM(int nt) {
     int n = 0;
@@ -795,13 +804,13 @@ cudaError_t launchMarchAnalytic(const WfStream& s, float* results, const MarchKi
 cudaError_t launchFinalGather(const FrameParams& fp, const WfStream& s, float* results, cudaStream_t st) { k_final_gather<<<gridForWf(fp), 128, 0, st>>>(fp, s, results); return cudaGetLastError(); }
 cudaError_t launchFinalCombine(const FrameParams& fp, const float* results, cudaStream_t st) { k_final_combine<<<gridForWf(fp), 128, 0, st>>>(fp, results); return cudaGetLastError(); }
 cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st) {
-    if (s == 0) { k_initial_traverse<<<gridForWf(fp), 128, 0, st>>>(fp, wi); k_initial_step<0><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s); }
+    if (s == 0) { k_initial_traverse<<<VR_TRAV_BLOCK == 32 ? gridForWarp(fp) : gridForWf(fp), VR_TRAV_BLOCK, 0, st>>>(fp, wi); k_initial_step<0><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s); }
     else if (s < fp.initialM) k_initial_step<1><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
     else k_initial_step<2><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
     return cudaGetLastError();
 }
 cudaError_t launchInitialFinish(const FrameParams& fp, const WfInitial& wi, cudaStream_t st) { k_initial_finish<<<gridForWf(fp), 128, 0, st>>>(fp, wi); return cudaGetLastError(); }
-cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
+cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<VR_TGATHER_BLOCK == 32 ? gridForWarp(fp) : gridForWf(fp), VR_TGATHER_BLOCK, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 

@@ -203,6 +203,7 @@ class ShardedPass:
             return
         p.execute_stage(0, 0, out_color_ptr, out_mvec_ptr, stream)
         p.execute_stage(1, 0, out_color_ptr, out_mvec_ptr, stream)
+        p.execute_stage(7, 0, out_color_ptr, out_mvec_ptr, stream)   # "mPipelineFrames": K0/K1 of the next frame start now (else a no-op)
         for w in getattr(self, "_pending_history", []):   # the history halo of the previous frame travelled during K0/K1
             w.wait()
         self._pending_history = []

@@ -16,7 +16,7 @@ from . import _capi as capi
 kOutputChannels = {"accumulated_color": "RGBA32Float", "mvec": "RG32Float"}   # VR/VolumetricReSTIR.cpp:39-43
 
 TOP_LEVEL_KEYS = ("mOutputMotionVec", "mFreezeFrame", "volumeDensityScaleExtraControl", "volumeAlbedoExtraControl",
-                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mInitialMode", "mOverlapFeatures", "mMarchPairEngine", "mInitialChains")
+                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mInitialMode", "mOverlapFeatures", "mMarchPairEngine", "mPipelineFrames")
 # accepted for script compatibility, camera / env-light animation and UI live outside the hot path
 IGNORED_KEYS = ("mCameraMoveScale", "mCameraForwardScale", "mCameraFrameInterval", "mCameraPauseInterval",
                 "mCameraShakeTotalRounds", "mCameraShakeRoundsBeforePause", "mCameraAnimationMode", "mAnimateEnvLight",
@@ -142,6 +142,20 @@ class VolumetricReSTIR:
         cam = self._scene.camera.data(*self._frame)
         capi.check(self._lib.vrestir_set_camera(self._h, C.byref(cam)))
         return cam
+
+    def setNextCamera(self, camera=None):
+        """Frame pipelining ("mPipelineFrames"): announce the camera of the NEXT frame before executing the current one, so that
+        its K0/K1 can run ahead (include/vrestir.h).  `camera`: a scene Camera, or None to clear (= the camera stays put)."""
+        if camera is None:
+            capi.check(self._lib.vrestir_set_next_camera(self._h, None))
+            return
+        cam = camera.data(*self._frame)
+        capi.check(self._lib.vrestir_set_next_camera(self._h, C.byref(cam)))
+
+    def pipeline_stats(self):
+        t = capi.PipelineStats()
+        capi.check(self._lib.vrestir_get_pipeline_stats(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in capi.PipelineStats._fields_}
 
     def advanceVolume(self, volume):
         """Animated sequences: current grids become the prev-frame slots (F/Scene/Scene.cpp:825-863)."""
