@@ -332,7 +332,13 @@ int vrestir_set_next_camera(vrestir_pass* pass, const vrestir_camera* camera);
 typedef struct vrestir_pipeline_stats {
     uint64_t adopted, discarded;   /* prefetched frames used / thrown away since create */
     float prefetch_ms;             /* device time of the last prefetch chain (K0 + K1 of the next frame) on its stream */
+    float deferred_final_ms;       /* device time of the last deferred K5 on its stream (level 2) */
 } vrestir_pipeline_stats;
+/* "mPipelineFrames" = 2 additionally defers K5 (VR/FinalShading.cs.slang): it only reads the frame's final reservoirs, so it
+ * runs on a third internal stream next to K2/K3 of the NEXT frame.  out_color / out_mvec of vrestir_execute are then complete
+ * once the work enqueued here has run: call it with the stream (0 = default stream) that consumes the image.  A no-op at
+ * levels 0 and 1, where the image is complete in `stream` order of vrestir_execute itself.  vrestir_execute_host waits by itself. */
+int vrestir_wait_output(vrestir_pass* pass, void* stream);
 int vrestir_get_pipeline_stats(vrestir_pass* pass, vrestir_pipeline_stats* out);
 
 int vrestir_get_timings(vrestir_pass* pass, vrestir_timings* out);

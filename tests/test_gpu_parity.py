@@ -400,11 +400,13 @@ def test_full_size_properties_1080p():
     assert bad <= 5e-3
 
 
+@pytest.mark.parametrize("level", [1, 2])
 @pytest.mark.parametrize("motion", ["static", "announced", "unannounced"])
-def test_pipelined_frames_equal_serial(motion):
+def test_pipelined_frames_equal_serial(motion, level):
     """Frame pipelining ("mPipelineFrames": K0/K1 of frame f+1 run ahead on their own stream, next to K2..K5 of frame f) must not
     change a single bit of any frame — whether the prefetch is adopted (static camera, or a moving camera announced one frame
-    ahead with setNextCamera) or discarded (camera moved without notice)."""
+    ahead with setNextCamera) or discarded (camera moved without notice).  Level 2 also defers K5 to a third stream
+    (the consumer orders itself with wait_output)."""
     import copy
     import torch
     w, h, frames = 192, 112, 5
@@ -413,7 +415,7 @@ def test_pipelined_frames_equal_serial(motion):
     path = [tuple(pos0 + np.array([0.6, -0.4, 0.3]) * 2.0 * f) if motion != "static" else tuple(pos0) for f in range(frames + 1)]
 
     def run(pipelined):
-        gp = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams(), "mPipelineFrames": int(pipelined)})
+        gp = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams(), "mPipelineFrames": level if pipelined else 0})
         sc.camera.position = path[0]
         gp.setScene(sc, w, h)
         color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
@@ -426,8 +428,9 @@ def test_pipelined_frames_equal_serial(motion):
                 nxt.position = path[f + 1]
                 gp.setNextCamera(nxt)
             gp.execute(color.data_ptr())
-            torch.cuda.synchronize()
-            imgs.append(color.cpu().numpy().copy())
+            gp.wait_output()                     # default stream waits for the (possibly deferred) final shading
+            imgs.append(color.cpu().numpy().copy())   # .cpu() is ordered on the default stream
+        torch.cuda.synchronize()
         return imgs, gp.get_buffer(capi.BUF_RESERVOIR_TEMPORAL).copy(), gp.pipeline_stats()
 
     ref_imgs, ref_res, st0 = run(False)

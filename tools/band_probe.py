@@ -23,11 +23,12 @@ def main():
     ap.add_argument("--frames", type=int, default=10)
     ap.add_argument("--bgw", type=float, default=0.05)
     ap.add_argument("--only", type=int, nargs=2, default=None, help="render just this band (for an ncu launch list)")
+    ap.add_argument("--level", type=int, default=0, help="mPipelineFrames level")
     a = ap.parse_args()
     args = argparse.Namespace(width=a.width, height=a.height, dim=[577, 572, 438], kind="bunny", mips=4, bounces=1)
     W, H = a.width, a.height
     scene = bench.build_scene(args)
-    gp = VolumetricReSTIR.create({"mParams": bench.make_params(args)}, device=0)
+    gp = VolumetricReSTIR.create({"mParams": bench.make_params(args), "mPipelineFrames": a.level, "mPrefetchPriority": int(os.environ.get("VR_PF_PRIO", "1"))}, device=0)
     gp.setScene(scene, W, H)
     color = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     gp.setRowBand(0, H)
@@ -46,6 +47,7 @@ def main():
         e0.record()
         for _ in range(frames):
             gp.execute(color.data_ptr())
+        gp.wait_output()
         e1.record()
         torch.cuda.synchronize()
         st = {k: round(v, 3) for k, v in gp.timings().items()}
@@ -54,7 +56,7 @@ def main():
     if a.only:
         for _ in range(3):
             gp.execute(color.data_ptr())
-        ms, st = run(a.only[0], a.only[1], frames=3)
+        ms, st = run(a.only[0], a.only[1], frames=a.frames)
         print(json.dumps({"band": a.only, "ms": round(ms, 3), "stage": st}))
         return
     full, st = run(0, H)

@@ -39,13 +39,16 @@ def main():
     c_band = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     c_full = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     bad = 0
+    ref = []
+    for f in range(a.frames):   # the reference frames first: two passes alternating would re-upload the constant bank every frame
+        full.execute(c_full.data_ptr())   # and (correctly) throw every prefetch away
+        torch.cuda.synchronize()
+        ref.append(c_full[r0:r1].cpu().numpy().view(np.uint32).copy())
     for f in range(a.frames):
         sp.execute(c_band.data_ptr())
-        full.execute(c_full.data_ptr())
         torch.cuda.synchronize()
         x = c_band[r0:r1].cpu().numpy().view(np.uint32)
-        y = c_full[r0:r1].cpu().numpy().view(np.uint32)
-        bad += int((x != y).any(axis=-1).sum())
+        bad += int((x != ref[f]).any(axis=-1).sum())
     lit = float((c_full[..., :3].sum(-1) > 0).float().mean())
     t = torch.tensor([bad], device="cuda", dtype=torch.int64)
     dist.all_reduce(t)

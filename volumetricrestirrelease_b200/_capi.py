@@ -123,7 +123,7 @@ class MarchTimings(C.Structure):
 
 
 class PipelineStats(C.Structure):
-    _fields_ = [("adopted", C.c_uint64), ("discarded", C.c_uint64), ("prefetch_ms", _F)]
+    _fields_ = [("adopted", C.c_uint64), ("discarded", C.c_uint64), ("prefetch_ms", _F), ("deferred_final_ms", _F)]
 
 
 class SceneParams(C.Structure):
@@ -140,7 +140,7 @@ SYMBOLS = [
     "vrestir_set_analytic_lights", "vrestir_set_emissive_triangles", "vrestir_get_emissive_alias",
     "vrestir_get_env_alias", "vrestir_set_frame", "vrestir_update", "vrestir_set_params", "vrestir_get_params",
     "vrestir_set_frame_count", "vrestir_set_prev_camera", "vrestir_get_frame_count", "vrestir_execute",
-    "vrestir_execute_host", "vrestir_execute_stage", "vrestir_set_next_camera", "vrestir_get_pipeline_stats", "vrestir_get_timings", "vrestir_get_march_timings", "vrestir_debug_read_bandwidth", "vrestir_debug_long_rays", "vrestir_debug_wavefront_counters", "vrestir_get_launch_count",
+    "vrestir_execute_host", "vrestir_execute_stage", "vrestir_set_next_camera", "vrestir_get_pipeline_stats", "vrestir_wait_output", "vrestir_get_timings", "vrestir_get_march_timings", "vrestir_debug_read_bandwidth", "vrestir_debug_long_rays", "vrestir_debug_wavefront_counters", "vrestir_get_launch_count",
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
     "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
     "vrestir_scene_grid", "vrestir_scene_dense_mip", "vrestir_scene_stats", "vrestir_camera_look_at",
@@ -187,6 +187,7 @@ def lib():
     L.vrestir_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.vrestir_set_next_camera.argtypes = [vp, C.POINTER(Camera)]
     L.vrestir_get_pipeline_stats.argtypes = [vp, C.POINTER(PipelineStats)]
+    L.vrestir_wait_output.argtypes = [vp, vp]
     L.vrestir_get_march_timings.argtypes = [vp, C.POINTER(MarchTimings)]
     L.vrestir_debug_read_bandwidth.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
     L.vrestir_debug_long_rays.argtypes = [vp, vp, C.POINTER(C.c_uint32)]

@@ -88,7 +88,13 @@ struct vrestir_pass {
     // Frame pipelining (option mPipelineFrames): K0 + K1 of frame f+1 read no history, so they run on a stream of their own while
     // K2..K5 of frame f run on the caller's stream (the tail of every launch of one chain is filled by the other chain).
     // The prefetched frame is adopted by the next execute when its key (camera, frame counter, band, options) still matches.
-    bool mPipelineFrames = false, pfValid = false, haveNextCam = false;
+    // Level 2 additionally defers K5 (final shading only reads the frame's final reservoirs, which the next frame reads too but
+    // never writes): it runs on a third stream next to K2/K3 of the next frame; consumers order themselves after it with
+    // vrestir_wait_output.
+    int mPipelineFrames = 0; bool pfValid = false, haveNextCam = false, mPrefetchPriority = true;
+    cudaStream_t outStream = nullptr; cudaEvent_t evOutGo = nullptr, evOutDone[2] = {nullptr, nullptr}, evOut0 = nullptr, evOut1 = nullptr;
+    uint64_t outSeq = 0; bool outTimed = false;
+    uint4* k5Tasks = nullptr; float* k5Results = nullptr; unsigned* k5Counters = nullptr; size_t k5Pixels = 0;
     vrestir_camera nextCam{};
     struct PrefetchKey { float cam[12]; int frameCount, W, H, rowBegin, rowEnd; vrestir_params P; } pfKey{};
     cudaStream_t pfStream = nullptr; cudaEvent_t evPfGo = nullptr, evPfDone = nullptr, evPf0 = nullptr, evPf1 = nullptr;
@@ -331,6 +337,7 @@ int syncScene(vrestir_pass* p, cudaStream_t st) {
     if (!haveLast || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0) {
         // a prefetched K0/K1 was computed with the old constants and may still be reading them
         if (p->pfValid) { CK(cudaStreamWaitEvent(st, p->evPfDone, 0)); p->pfValid = false; p->pfDiscarded++; }
+        if (p->outSeq) CK(cudaStreamWaitEvent(st, p->evOutDone[(p->outSeq - 1) & 1], 0));
         CK(uploadScene(s, st));
         CK(uploadSceneWavefront(s, st));
         // the async copy reads `s` at enqueue time only when the source is pageable (staged); keep a private copy alive
@@ -422,6 +429,22 @@ int ensureInitialScratch(vrestir_pass* p) {
     return VRESTIR_OK;
 }
 
+// K5's own scratch: <= 2 analytic march tasks (camera, light) and K5_BLOCK result floats per pixel of the band
+int ensureFinalScratch(vrestir_pass* p) {
+    const size_t n = (size_t)(p->rowEnd - p->rowBegin) * p->W;
+    if (p->k5Pixels == n && p->k5Tasks) return VRESTIR_OK;
+    if (p->outStream) CK(cudaStreamSynchronize(p->outStream));
+    if (p->k5Tasks) cudaFree(p->k5Tasks);
+    if (p->k5Results) cudaFree(p->k5Results);
+    p->k5Tasks = nullptr; p->k5Results = nullptr; p->k5Pixels = 0;
+    if (n * 2 >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit task indices; shard the frame");
+    CK(cudaMalloc(&p->k5Tasks, 2 * n * 48));
+    CK(cudaMalloc(&p->k5Results, n * K5_BLOCK * sizeof(float)));
+    if (!p->k5Counters) CK(cudaMalloc(&p->k5Counters, 16));
+    p->k5Pixels = n;
+    return VRESTIR_OK;
+}
+
 // K1 as M + 1 lock-step waves over the band: traverse, then per candidate s {finish candidate s-1 / emit the light march of
 // candidate s, march}, the p-hat evaluation of the surviving sample under the spatial options, finish.  Works entirely in
 // its own scratch, on `st` (the caller's stream or the prefetch stream).  fp.cur is the output reservoir buffer.
@@ -477,6 +500,7 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
         if (p->mRandomizeFrameSeed) p->mFrameCount = rand_r(&p->randState) % 65536; else p->mFrameCount = 0;
         p->mTemporalSampleAccumulated = 0; p->mOptionsChanged = false;
     }
+    if ((stage == 0 || stage == -1) && p->outSeq >= 2) CK(cudaStreamWaitEvent(st, p->evOutDone[p->outSeq & 1], 0));   // deferred K5 of frame f-2
     rc = syncScene(p, st); if (rc) return rc;
     FrameParams fp; buildFrameParams(p, fp, out_color, out_mvec);
     const bool active = !p->mFreezeFrame;
@@ -525,7 +549,12 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
             // released the K1 scratch) and before stage 2, so that the chain overlaps K2..K5.  No-op unless mPipelineFrames.
             if (!p->mPipelineFrames || !active || m.mUseReference || !initialWavefrontOk(p) || p->pfValid) break;
             if (!p->pfStream) {
-                CK(cudaStreamCreateWithFlags(&p->pfStream, cudaStreamNonBlocking));
+                // High priority: the chain is ~13 short dependent launches; at default priority each of them queues behind the
+                // resident persistent CTAs of the main stream's march kernels and the chain stretches over the whole frame
+                // (measured: 2.3 ms alone -> 4.4 ms next to K2..K5 on a 1/8 band of a 4K frame), which makes it the critical path.
+                int prLeast = 0, prGreatest = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+                CK(cudaStreamCreateWithPriority(&p->pfStream, cudaStreamNonBlocking, p->mPrefetchPriority ? prGreatest : prLeast));
                 CK(cudaEventCreateWithFlags(&p->evPfGo, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->evPfDone, cudaEventDisableTiming));
                 CK(cudaEventCreate(&p->evPf0)); CK(cudaEventCreate(&p->evPf1));
             }
@@ -641,15 +670,34 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
             if (!out_color) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "out_color is null");
             if (p->mUseWavefront && m.mMaxBounces == 1 && !m.mUseReference && !m.mVisualizeTotalTransmittance &&
                 m.mFinalVisibilityTrackingMethod == VRESTIR_ANALYTIC_TRACKING && m.mFinalLightTrackingMethod == VRESTIR_ANALYTIC_TRACKING) {
-                rc = ensureWavefront(p); if (rc) return rc;
+                rc = ensureFinalScratch(p); if (rc) return rc;
                 if (!p->analyticBlocks) { int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device); p->analyticBlocks = sms * analyticBlocksPerSM(); }
-                WfStream s; s.tasks = p->wfLightTasks; s.count = p->wfCounters; s.cursor = p->wfCounters + 1; s.capacity = (unsigned)(2 * p->wfPixels);
-                CK(cudaMemsetAsync(p->wfCounters, 0, 8, st));
-                CK(launchFinalGather(fp, s, p->wfResults, st));
-                const MarchKind k = {0, 1, m.mFinalTStepScale, 0};
-                CK(launchMarchAnalytic(s, p->wfResults, k, p->scene.slots[0], p->analyticBlocks, st));
-                CK(launchFinalCombine(fp, p->wfResults, st));
+                const bool deferred = p->mPipelineFrames >= 2 && active;
+                cudaStream_t so = st;
+                if (deferred) {
+                    if (!p->outStream) {
+                        CK(cudaStreamCreateWithFlags(&p->outStream, cudaStreamNonBlocking));
+                        CK(cudaEventCreateWithFlags(&p->evOutGo, cudaEventDisableTiming));
+                        for (auto& e : p->evOutDone) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        CK(cudaEventCreate(&p->evOut0)); CK(cudaEventCreate(&p->evOut1));
+                    }
+                    so = p->outStream;
+                    CK(cudaEventRecord(p->evOutGo, st));
+                    CK(cudaStreamWaitEvent(so, p->evOutGo, 0));
+                    CK(cudaEventRecord(p->evOut0, so));
+                }
+                WfStream s; s.tasks = p->k5Tasks; s.count = p->k5Counters; s.cursor = p->k5Counters + 1; s.capacity = (unsigned)(2 * p->k5Pixels);
+                CK(cudaMemsetAsync(p->k5Counters, 0, 8, so));
+                CK(launchFinalGather(fp, s, p->k5Results, so));
+                const MarchKind k = {0, 1, m.mFinalTStepScale, 0, {0.f, 0.f, 0.f}};
+                CK(launchMarchAnalytic(s, p->k5Results, k, p->scene.slots[0], p->analyticBlocks, so));
+                CK(launchFinalCombine(fp, p->k5Results, so));
                 p->launches += 3;
+                if (deferred) {
+                    CK(cudaEventRecord(p->evOut1, so));
+                    CK(cudaEventRecord(p->evOutDone[p->outSeq & 1], so));
+                    p->outSeq++; p->outTimed = true;
+                }
             } else { CK(launchFinal(fp, st)); p->launches++; }
             recordEv(p, 6, st);
             break;
@@ -769,7 +817,7 @@ int vrestir_destroy(vrestir_pass* p) {
     for (auto& d : p->dslots) freeSlot(d);
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
     for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); if (p->feat[i]) cudaFree(p->feat[i]); }
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters};
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
@@ -777,6 +825,8 @@ int vrestir_destroy(vrestir_pass* p) {
     if (p->evFork) cudaEventDestroy(p->evFork);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
     for (auto& e : p->evMarch) if (e) cudaEventDestroy(e);
+    if (p->outStream) cudaStreamDestroy(p->outStream);
+    for (cudaEvent_t e : {p->evOutGo, p->evOutDone[0], p->evOutDone[1], p->evOut0, p->evOut1}) if (e) cudaEventDestroy(e);
     if (p->pfStream) cudaStreamDestroy(p->pfStream);
     for (cudaEvent_t e : {p->evPfGo, p->evPfDone, p->evPf0, p->evPf1}) if (e) cudaEventDestroy(e);
     delete p;
@@ -948,7 +998,8 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
         else if (k == "mUseWavefront") p->mUseWavefront = value != 0;
         else if (k == "mInitialMode") p->mInitialMode = (int)value;
         else if (k == "mOverlapFeatures") p->mOverlapFeatures = value != 0;
-        else if (k == "mPipelineFrames") p->mPipelineFrames = value != 0;
+        else if (k == "mPipelineFrames") p->mPipelineFrames = (int)value;
+        else if (k == "mPrefetchPriority") p->mPrefetchPriority = value != 0;
         else if (k == "mMarchPairEngine") setPairEngine(value != 0);   // process-wide A/B switch of the march engine   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
@@ -1037,6 +1088,7 @@ int vrestir_execute_host(vrestir_pass* p, float* out_color_host, float* out_mvec
     }
     int rc = vrestir_execute(p, (float*)p->d_hostColor, out_mvec_host ? (float*)p->d_hostMvec : nullptr, p->hostStream);
     if (rc) return rc;
+    if ((rc = vrestir_wait_output(p, p->hostStream))) return rc;
     const size_t off = (size_t)p->rowBegin * p->W, cnt = (size_t)(p->rowEnd - p->rowBegin) * p->W;
     CK(cudaMemcpyAsync(out_color_host + off * 4, p->d_hostColor + off, cnt * 16, cudaMemcpyDeviceToHost, p->hostStream));
     if (out_mvec_host) CK(cudaMemcpyAsync(out_mvec_host + off * 2, p->d_hostMvec + off, cnt * 8, cudaMemcpyDeviceToHost, p->hostStream));
@@ -1093,6 +1145,11 @@ int vrestir_set_next_camera(vrestir_pass* p, const vrestir_camera* cam) {
     if (cam) { p->nextCam = *cam; p->haveNextCam = true; } else p->haveNextCam = false;
     return VRESTIR_OK;
 }
+int vrestir_wait_output(vrestir_pass* p, void* stream) {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    if (p->outSeq) { CK(cudaSetDevice(p->device)); CK(cudaStreamWaitEvent((cudaStream_t)stream, p->evOutDone[(p->outSeq - 1) & 1], 0)); }
+    return VRESTIR_OK;
+}
 int vrestir_get_pipeline_stats(vrestir_pass* p, vrestir_pipeline_stats* out) {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     memset(out, 0, sizeof(*out));
@@ -1101,6 +1158,11 @@ int vrestir_get_pipeline_stats(vrestir_pass* p, vrestir_pipeline_stats* out) {
         CK(cudaSetDevice(p->device));
         CK(cudaEventSynchronize(p->evPf1));
         CK(cudaEventElapsedTime(&out->prefetch_ms, p->evPf0, p->evPf1));
+    }
+    if (p->outTimed) {
+        CK(cudaSetDevice(p->device));
+        CK(cudaEventSynchronize(p->evOut1));
+        CK(cudaEventElapsedTime(&out->deferred_final_ms, p->evOut0, p->evOut1));
     }
     return VRESTIR_OK;
 }

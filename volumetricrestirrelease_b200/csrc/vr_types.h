@@ -91,7 +91,7 @@ struct WfStream { uint4* tasks; unsigned* count; unsigned* cursor; unsigned capa
 enum { WF_BLOCK = 48, WF_D = 0, WF_C = 16, WF_L = 28 };
 struct WfBufs { WfStream cam, light; float* results; };
 // K1 lock-step candidate state: K1_STRIDE floats per pixel (vr_wavefront.cu)
-enum { K1_WORDS = 20, K1_STRIDE = 80, K1_EVAL_BLOCK = 4 };   // K1_EVAL_BLOCK: floats per pixel of K1's p-hat results (density, camera Tr, light Tr)
+enum { K1_WORDS = 20, K1_STRIDE = 80, K1_EVAL_BLOCK = 4, K5_BLOCK = 4 };   // K5_BLOCK: floats per pixel of K5's results (density, camera Tr, light Tr)   // K1_EVAL_BLOCK: floats per pixel of K1's p-hat results (density, camera Tr, light Tr)
 struct WfInitial { WfStream light; float* state; uint8_t* done; WfStream evalCam, evalLight; float* results; };
 // K2: four explicit-origin streams {current camera, current light, previous-frame camera, previous-frame light};
 // streams whose march configuration is identical alias the same buffer

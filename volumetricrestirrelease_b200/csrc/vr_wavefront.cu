@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(128) k_final_gather(FrameParams fp, WfStream s
     int x, y;
     const bool inFrame = pixelOf(fp, x, y);
     const int pixelId = inFrame ? y * fp.W + x : fp.rowBegin * fp.W;
-    const unsigned out = (unsigned)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
+    const unsigned out = (unsigned)(pixelId - fp.rowBegin * fp.W) * K5_BLOCK;
     bool hasCam = false, hasLight = false;
     Ray r = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f), sh = r;
     if (inFrame) {
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const flo
     int x, y;
     if (!pixelOf(fp, x, y)) return;
     const int pixelId = y * fp.W + x;
-    const float* blk = results + (size_t)(pixelId - fp.rowBegin * fp.W) * WF_BLOCK;
+    const float* blk = results + (size_t)(pixelId - fp.rowBegin * fp.W) * K5_BLOCK;
     float3 outputColor = f3(0.f);
     const Reservoir cur = loadReservoir(fp.cur, pixelId, 1);
     if (cur.runningSum > 0.f) {

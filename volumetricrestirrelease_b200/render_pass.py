@@ -16,7 +16,7 @@ from . import _capi as capi
 kOutputChannels = {"accumulated_color": "RGBA32Float", "mvec": "RG32Float"}   # VR/VolumetricReSTIR.cpp:39-43
 
 TOP_LEVEL_KEYS = ("mOutputMotionVec", "mFreezeFrame", "volumeDensityScaleExtraControl", "volumeAlbedoExtraControl",
-                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mInitialMode", "mOverlapFeatures", "mMarchPairEngine", "mPipelineFrames")
+                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mInitialMode", "mOverlapFeatures", "mMarchPairEngine", "mPipelineFrames", "mPrefetchPriority")
 # accepted for script compatibility, camera / env-light animation and UI live outside the hot path
 IGNORED_KEYS = ("mCameraMoveScale", "mCameraForwardScale", "mCameraFrameInterval", "mCameraPauseInterval",
                 "mCameraShakeTotalRounds", "mCameraShakeRoundsBeforePause", "mCameraAnimationMode", "mAnimateEnvLight",
@@ -151,6 +151,11 @@ class VolumetricReSTIR:
             return
         cam = camera.data(*self._frame)
         capi.check(self._lib.vrestir_set_next_camera(self._h, C.byref(cam)))
+
+    def wait_output(self, stream=None):
+        """"mPipelineFrames" = 2 (deferred final shading): make `stream` (a raw cudaStream_t; None = the default stream) wait
+        until the image of the last execute() is complete.  A no-op at the other levels."""
+        capi.check(self._lib.vrestir_wait_output(self._h, C.c_void_p(stream) if stream else None))
 
     def pipeline_stats(self):
         t = capi.PipelineStats()
