@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=360)
     ap.add_argument("--frames", type=int, default=4)
-    ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--level", type=int, default=2, help="mPipelineFrames level of the sharded pass")
     a = ap.parse_args()
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -30,7 +30,7 @@ def main():
     W, H = a.width, a.height
     scene = bench.build_scene(args)
     params = bench.make_params(args)
-    gp = VolumetricReSTIR.create({"mParams": params, "mPipelineFrames": int(not a.no_pipeline)}, device=local)
+    gp = VolumetricReSTIR.create({"mParams": params, "mPipelineFrames": a.level}, device=local)
     sp = ShardedPass(gp, W, H, rank, world, torch.device("cuda", local))
     gp.setScene(scene, W, H)
     r0, r1 = sp.balance(refine=0)
@@ -46,14 +46,14 @@ def main():
         ref.append(c_full[r0:r1].cpu().numpy().view(np.uint32).copy())
     for f in range(a.frames):
         sp.execute(c_band.data_ptr())
-        torch.cuda.synchronize()
+        gp.wait_output()
         x = c_band[r0:r1].cpu().numpy().view(np.uint32)
         bad += int((x != ref[f]).any(axis=-1).sum())
     lit = float((c_full[..., :3].sum(-1) > 0).float().mean())
     t = torch.tensor([bad], device="cuda", dtype=torch.int64)
     dist.all_reduce(t)
     if rank == 0:
-        print(f"[check_sharded] world {world} bands {sp.bands} frames {a.frames} pipelined {not a.no_pipeline}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
+        print(f"[check_sharded] world {world} bands {sp.bands} frames {a.frames} pipelining level {a.level}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
               f"pipeline {gp.pipeline_stats()}")
     dist.destroy_process_group()
     sys.exit(1 if int(t[0]) else 0)
