@@ -355,6 +355,31 @@ int vrestir_debug_read_bandwidth(int device, size_t bytes, int iters, float* gb_
 /* number of kernels this library launched since create (claim for bench.py's gpu_launches) */
 int vrestir_get_launch_count(const vrestir_pass* pass, uint64_t* out);
 
+/* ---- the passes behind VolumetricReSTIR.accumulated_color in the reference's scripts ---------------
+ * AccumulatePass (Source/RenderPasses/AccumulatePass/AccumulatePass.cpp:128-205, Accumulate.cs.slang:57-122): running mean
+ * of the frames, three precision modes (AccumulatePass.h:66-71; default Double), pass-through when "enableAccumulation" is
+ * off, "subFrameCount" stops after N frames while "autoReset" is on.  Scene / camera / refresh-flag changes reset the
+ * reference's counter through the render graph; here the owner calls vrestir_accum_reset. */
+enum { VRESTIR_ACCUM_DOUBLE = 0, VRESTIR_ACCUM_SINGLE = 1, VRESTIR_ACCUM_SINGLE_COMPENSATED = 2 };
+typedef struct vrestir_accumulator vrestir_accumulator;
+int vrestir_accum_create(int device, int width, int height, vrestir_accumulator** out);
+int vrestir_accum_destroy(vrestir_accumulator* acc);
+/* keys: "enableAccumulation", "autoReset", "precisionMode" (VRESTIR_ACCUM_*), "subFrameCount"; unknown -> VRESTIR_WARN_UNKNOWN_KEY */
+int vrestir_accum_update(vrestir_accumulator* acc, const char* key, double value);
+int vrestir_accum_reset(vrestir_accumulator* acc);
+int vrestir_accum_resize(vrestir_accumulator* acc, int width, int height);   /* a new resolution restarts the accumulation */
+int vrestir_accum_frame_count(const vrestir_accumulator* acc, int* out);
+/* input / output: device pointers, width*height float4; rows [row_begin,row_end) are accumulated (one call per frame and
+ * band owner).  Asynchronous on `stream`. */
+int vrestir_accum_execute(vrestir_accumulator* acc, const float* input, float* output, int row_begin, int row_end, void* stream);
+/* ErrorMeasurePass (Source/RenderPasses/ErrorMeasurePass/ErrorMeasurer.cs.slang:41-61, ErrorMeasurePass.cpp:217-259):
+ * per-pixel |source - reference| (squared / rgb-averaged on request, background pixels = world_position.w == 0 skipped when
+ * ignore_background and world_position is bound), summed and divided by the pixel count.  error_rgb_avg = {r, g, b,
+ * (r+g+b)/3}.  difference_out (device, float4 per pixel) may be NULL.  Synchronous (returns the numbers). */
+int vrestir_error_measure(int device, const float* source, const float* reference, const float* world_position, int width, int height,
+                          int ignore_background, int compute_squared_difference, int compute_average, float* difference_out,
+                          float error_rgb_avg[4], void* stream);
+
 /* Diagnostics: world-space rays whose hierarchical DDA ran >= 1024 outer iterations since the last call
  * (8 floats each: origin, dir, mip (+100 when vertex-centred), iterations; first 64) and their total count. */
 int vrestir_debug_long_rays(vrestir_pass* pass, float* out64x8, uint32_t* count);

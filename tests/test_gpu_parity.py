@@ -445,3 +445,71 @@ def test_pipelined_frames_equal_serial(motion, level):
         assert np.array_equal(imgs[f].view(np.uint32), ref_imgs[f].view(np.uint32)), f"frame {f} differs with pipelining ({motion})"
     assert np.array_equal(res.view(np.uint32), ref_res.view(np.uint32))
     assert (imgs[-1][..., :3].sum(-1) > 0).mean() > 0.05
+
+
+@pytest.mark.parametrize("mode", ["Double", "Single", "SingleCompensated"])
+def test_accumulate_pass_matches_oracle(mode):
+    """AccumulatePass on rendered frames: every running mean bit-identical to the numpy restatement; band
+    calls, pass-through, subFrameCount and reset follow AccumulatePass.cpp:128-205."""
+    import torch
+    from oracle import post_oracle as po
+    from volumetricrestirrelease_b200.post import AccumulatePass
+    w, h, frames = 96, 64, 6
+    sc = env_scene()
+    gp = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams()})
+    gp.setScene(sc, w, h)
+    color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    out = torch.zeros_like(color)
+    acc = AccumulatePass.create({"precisionMode": mode}, w, h)
+    ref = po.Accumulator(mode)
+    for f in range(frames):
+        gp.execute(color.data_ptr())
+        acc.execute(color.data_ptr(), out.data_ptr(), 0, 40)      # two band owners, one frame
+        acc2_rows = (40, h)
+        # the second band of the same frame must use the same frame counter: a second accumulator instance, as a second rank would own
+        if f == 0:
+            acc_b = AccumulatePass.create({"precisionMode": mode}, w, h)
+        acc_b.execute(color.data_ptr(), out.data_ptr(), *acc2_rows)
+        torch.cuda.synchronize()
+        want = ref.add(color.cpu().numpy())
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)), f"{mode}: frame {f}"
+    assert acc.frameCount == frames
+    # subFrameCount: accumulation stops after N frames, the output keeps the finished mean
+    acc.reset(); acc.updateDict({"subFrameCount": 2})
+    for f in range(4):
+        gp.execute(color.data_ptr())
+        acc.execute(color.data_ptr(), out.data_ptr())
+        torch.cuda.synchronize()
+        if f == 1:
+            kept = out.cpu().numpy().copy()
+    assert acc.frameCount == -1 and np.array_equal(out.cpu().numpy(), kept)
+    # disabled: pass-through
+    acc.updateDict({"enableAccumulation": False, "subFrameCount": 0}); acc.reset()
+    acc.execute(color.data_ptr(), out.data_ptr()); torch.cuda.synchronize()
+    assert torch.equal(out, color)
+
+
+def test_error_measure_pass_matches_oracle():
+    """ErrorMeasurePass: the per-pixel difference image bit-identical, the reduced numbers within 1e-6 relative (the sum order
+    differs from numpy's; the reference's own float4 tree reduction has no defined order either)."""
+    import torch
+    from oracle import post_oracle as po
+    from volumetricrestirrelease_b200.post import ErrorMeasurePass
+    w, h = 200, 120
+    rng = np.random.default_rng(5)
+    src = rng.random((h, w, 4)).astype(np.float32) * 3
+    ref = rng.random((h, w, 4)).astype(np.float32) * 3
+    wp = np.ones((h, w, 4), np.float32); wp[rng.random((h, w)) < 0.3, 3] = 0
+    ts, tr, tw = (torch.from_numpy(a).cuda() for a in (src, ref, wp))
+    diff = torch.zeros_like(ts)
+    for kw in ({}, {"ComputeSquaredDifference": False}, {"ComputeAverage": True}, {"IgnoreBackground": False}):
+        em = ErrorMeasurePass(kw)
+        m = em.execute(ts.data_ptr(), tr.data_ptr(), w, h, tw.data_ptr(), diff.data_ptr())
+        d, err, avg = po.error_measure(src, ref, wp, em.IgnoreBackground, em.ComputeSquaredDifference, em.ComputeAverage)
+        assert np.array_equal(diff.cpu().numpy()[..., :3].view(np.uint32), d.view(np.uint32)), kw
+        assert np.allclose(m["error"], err, rtol=1e-6, atol=0) and np.isclose(m["avgError"], avg, rtol=1e-6), kw
+        m2 = em.execute(ts.data_ptr(), tr.data_ptr(), w, h, tw.data_ptr())
+        assert m2["error"] == m["error"]                      # deterministic reduction
+        assert np.isclose(em.runningAvgError, avg, rtol=1e-6)    # EMA of two equal measurements
+    m = ErrorMeasurePass().execute(ts.data_ptr(), tr.data_ptr(), w, h)   # unbound world position: no background test
+    assert np.allclose(m["error"], po.error_measure(src, ref, None)[1], rtol=1e-6)

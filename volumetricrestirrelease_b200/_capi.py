@@ -144,6 +144,8 @@ SYMBOLS = [
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
     "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
     "vrestir_scene_grid", "vrestir_scene_dense_mip", "vrestir_scene_stats", "vrestir_camera_look_at",
+    "vrestir_accum_create", "vrestir_accum_destroy", "vrestir_accum_update", "vrestir_accum_reset", "vrestir_accum_resize",
+    "vrestir_accum_frame_count", "vrestir_accum_execute", "vrestir_error_measure",
     "vrestir_make_sky_envmap", "vrestir_make_emissive_shell", "vrestir_make_blackbody_lut", "vrestir_scene_load_vbx", "vrestir_scene_save_vbx",
 ]
 
@@ -185,6 +187,14 @@ def lib():
     L.vrestir_execute_host.argtypes = [vp, vp, vp]
     L.vrestir_execute_stage.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.vrestir_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.vrestir_accum_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.vrestir_accum_destroy.argtypes = [vp]
+    L.vrestir_accum_update.argtypes = [vp, C.c_char_p, C.c_double]
+    L.vrestir_accum_reset.argtypes = [vp]
+    L.vrestir_accum_resize.argtypes = [vp, C.c_int, C.c_int]
+    L.vrestir_accum_frame_count.argtypes = [vp, C.POINTER(C.c_int)]
+    L.vrestir_accum_execute.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+    L.vrestir_error_measure.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_float * 4), vp]
     L.vrestir_set_next_camera.argtypes = [vp, C.POINTER(Camera)]
     L.vrestir_get_pipeline_stats.argtypes = [vp, C.POINTER(PipelineStats)]
     L.vrestir_wait_output.argtypes = [vp, vp]
