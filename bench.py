@@ -375,6 +375,22 @@ def main():
                     "l2_read_peak_gbs": l2_peak, "frac_of_l2_peak": ach / l2_peak if l2_peak > 0 else None,
                     "note": "working set (mip-1 UNORM8 quads, 29 MB) is L2 resident: DRAM traffic << algorithmic bytes; the kernel is issue-bound "
                             "(SIMT divergence between DDA stepping and in-brick sampling), see profiles/"}
+            # achieved GB/s per stage = (B_vox + B_node + B_res) / stage time.  B_vox, B_node from the instrumented oracle
+            # (stored bytes per voxel of the mip each tap reads, 36 B per node visit), B_res = the reservoir / feature / colour
+            # bytes of the stage (R = 32 B); stage times = the unpipelined frame's (a stage timed alone on the GPU).
+            R = 32
+            res_bytes = {0: 8, 1: R, 2: 2 * R + 16 + R, 3: params.mSpatialSampleCount * R + 8 + R, 5: R + 16}
+            st_ms = serial_stage if pipelined else stage_acc
+            names = {0: "features_ms", 1: "initial_ms", 2: "temporal_ms", 3: "spatial_ms", 5: "final_ms"}
+            stages = {}
+            for k, nm in names.items():
+                c = per_px.get(k, {})
+                b = (c.get("voxel_bytes", 0) + 36.0 * c.get("node_visits", 0) + res_bytes[k]) * W * H
+                t = st_ms.get(nm, 0.0)
+                if t > 0:
+                    stages["K%d" % k] = {"algorithmic_GB": round(b / 1e9, 3), "ms": round(t, 3), "GBps": round(b / (t * 1e-3) / 1e9, 1),
+                                          "frac_hbm": round(b / (t * 1e-3) / 1e9 / hbm_peak, 3), "frac_l2": round(b / (t * 1e-3) / 1e9 / l2_peak, 3) if l2_peak > 0 else None}
+            roof["stages"] = stages
     line = {"metric": "ms/frame", "value": ms, "unit": "ms/frame", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(d=args.dim, m=args.mips, w=W, h=H, b=args.bounces), "parallelism": f"rows/{world}" + (f" (cost-balanced bands {sp.bands})" if world > 1 else ""),
