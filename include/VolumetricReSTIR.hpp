@@ -55,6 +55,10 @@ public:
         if (tris) check(vrestir_set_emissive_triangles(mpPass, tris, triCount, emissiveIntensityMultiplier));
     }
     void setCamera(const vrestir_camera& camera) { check(vrestir_set_camera(mpPass, &camera)); }
+    /// frame pipelining ("mPipelineFrames"): the camera of the NEXT frame, announced before execute() of the current one
+    void setNextCamera(const vrestir_camera* camera) { check(vrestir_set_next_camera(mpPass, camera)); }
+    /// "mPipelineFrames" = 2: order `cudaStream` after the (deferred) final shading of the last execute()
+    void waitOutput(void* cudaStream = nullptr) { check(vrestir_wait_output(mpPass, cudaStream)); }
     /// Scene::update for animated volumes: current grids become the previous-frame slots
     void advanceVolume(const vrestir_grid_desc& volume) { check(vrestir_advance_volume(mpPass, &volume)); }
 

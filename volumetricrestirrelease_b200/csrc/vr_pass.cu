@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -330,10 +333,15 @@ int syncScene(vrestir_pass* p, cudaStream_t st) {
     applyOverrides(p);
     DScene& s = p->scene;
     s.envSamplerType = p->envSamplerType;
-    // the constant banks are shared by every pass of this process on this device: upload whenever anything may differ
-    static thread_local DScene lastScene;
-    static thread_local DPrevCam lastPrev;
-    static thread_local bool haveLast = false;
+    // The constant banks are per device and shared by every pass of the process on it: remember what each device holds and
+    // upload whenever anything may differ.  (Passes that share a device must not have frames in flight at the same time.)
+    struct Uploaded { DScene scene; DPrevCam prev; bool have = false; };
+    static std::mutex mu;
+    static std::map<int, std::unique_ptr<Uploaded>> perDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    std::unique_ptr<Uploaded>& slot = perDevice[p->device];
+    if (!slot) slot.reset(new Uploaded());
+    DScene& lastScene = slot->scene; DPrevCam& lastPrev = slot->prev; bool& haveLast = slot->have;
     if (!haveLast || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0) {
         // a prefetched K0/K1 was computed with the old constants and may still be reading them
         if (p->pfValid) { CK(cudaStreamWaitEvent(st, p->evPfDone, 0)); p->pfValid = false; p->pfDiscarded++; }
