@@ -380,6 +380,25 @@ int vrestir_error_measure(int device, const float* source, const float* referenc
                           int ignore_background, int compute_squared_difference, int compute_average, float* difference_out,
                           float error_rgb_avg[4], void* stream);
 
+/* ---- mip / conservative-mip chain on the GPU (the converter's job in the reference) ------------------
+ * Builds, from a dense device-resident density grid ([z][y][x] floats), every level of the normal chain and of the
+ * conservative chain by the rule of gvdb-voxel-src/source/gvdb_library/src/gvdb_volume_gvdb.cpp:2703-2885 (conservative mip 0
+ * :2753-2801, down-sampling :2803-2862) and stores them the way the brick pool does (F/Scene/Scene.cpp:3139-3174): mip 0 of
+ * the normal chain as fp32 after the 1e-9 flush, every other level as UNORM8 codes of value / max_value (conservative codes
+ * never round a positive value to 0).  Bit-identical to the host builder behind vrestir_scene_create_from_dense. */
+typedef struct vrestir_mip_chain vrestir_mip_chain;
+typedef struct vrestir_mip_level {
+    const void* data;      /* device pointer: dim[0]*dim[1]*dim[2] floats (VRESTIR_ATLAS_F32) or bytes (VRESTIR_ATLAS_UNORM8), x fastest */
+    size_t bytes;
+    int32_t dim[3];
+    int32_t format;        /* VRESTIR_ATLAS_F32 / VRESTIR_ATLAS_UNORM8 */
+    float max_value;       /* max |v| of the level = the UNORM8 scale (densityCompressScaleFactor) */
+} vrestir_mip_level;
+int vrestir_mips_build_device(int device, const float* dense_mip0, const int32_t dim[3], int num_mips, vrestir_mip_chain** out, void* stream);
+int vrestir_mips_count(const vrestir_mip_chain* chain, int* out);
+int vrestir_mips_level(const vrestir_mip_chain* chain, int mip, int conservative, vrestir_mip_level* out);
+int vrestir_mips_destroy(vrestir_mip_chain* chain);
+
 /* Diagnostics: world-space rays whose hierarchical DDA ran >= 1024 outer iterations since the last call
  * (8 floats each: origin, dir, mip (+100 when vertex-centred), iterations; first 64) and their total count. */
 int vrestir_debug_long_rays(vrestir_pass* pass, float* out64x8, uint32_t* count);

@@ -513,3 +513,36 @@ def test_error_measure_pass_matches_oracle():
         assert np.isclose(em.runningAvgError, avg, rtol=1e-6)    # EMA of two equal measurements
     m = ErrorMeasurePass().execute(ts.data_ptr(), tr.data_ptr(), w, h)   # unbound world position: no background test
     assert np.allclose(m["error"], po.error_measure(src, ref, None)[1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("dim", [(96, 80, 72), (97, 63, 45)])
+def test_gpu_mip_builder_matches_host_builder(dim):
+    """the mip / conservative-mip chain built on the GPU from a dense grid stores exactly what the host
+    builder's brick pools store (fp32 mip 0 after the 1e-9 flush, UNORM8 codes + scale elsewhere), on even and odd
+    (3-tap polyphase) dimensions, normal and conservative chain."""
+    import torch
+    from volumetricrestirrelease_b200 import Scene
+    from volumetricrestirrelease_b200.mipbuild import build_mips
+    nx, ny, nz = dim
+    rng = np.random.default_rng(11)
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    blob = np.exp(-(((x - nx / 2) / (nx / 4)) ** 2 + ((y - ny / 2) / (ny / 4)) ** 2 + ((z - nz / 2) / (nz / 4)) ** 2))
+    dense = (np.clip(blob + 0.3 * rng.random((nz, ny, nx)) - 0.55, 0, None) * 2.0).astype(np.float32)   # sparse: zeros outside the blob
+    dense[dense < 0.05] = 0.0
+    dense[nz // 2, ny // 2, nx // 2] = 1e-12                                                             # below the 1e-9 flush
+    sc = Scene()
+    vol = sc.addGVDBVolume(dense=dense, numMips=4)
+    chain = build_mips(torch.from_numpy(dense).cuda(), 4)
+    built = 0
+    for m in range(chain.num_mips):
+        for cons in (False, True):
+            want = vol.dense_mip(m, cons)
+            t, scale = chain.level(m, cons)
+            got = t.cpu().numpy()
+            if got.dtype == np.uint8:
+                got = got.astype(np.float32) * np.float32(0.003921568859368563) * np.float32(scale)
+            assert got.shape == want.shape, (m, cons, got.shape, want.shape)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"mip {m} conservative {cons}: {(got != want).sum()} voxels differ"
+            built += 1
+    assert built == 8 and (dense == 0).mean() > 0.3
+    chain.close()

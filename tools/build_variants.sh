@@ -9,6 +9,6 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -std=c
 for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"
   ( nvcc $FLAGS $defs -c vr_wavefront.cu -o build/vr_wavefront_$name.o && \
-    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build_variants/libvrestir_$name.so build/vr_kernels.o build/vr_wavefront_$name.o build/vr_pass.o build/vr_scene.o -Xlinker -lpthread && echo built $name ) &
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build_variants/libvrestir_$name.so build/vr_kernels.o build/vr_wavefront_$name.o build/vr_pass.o build/vr_post.o build/vr_mipbuild.o build/vr_scene.o -Xlinker -lpthread && echo built $name ) &
 done
 wait

@@ -126,6 +126,10 @@ class PipelineStats(C.Structure):
     _fields_ = [("adopted", C.c_uint64), ("discarded", C.c_uint64), ("prefetch_ms", _F), ("deferred_final_ms", _F)]
 
 
+class MipLevel(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("bytes", C.c_size_t), ("dim", _I * 3), ("format", _I), ("max_value", _F)]
+
+
 class SceneParams(C.Structure):
     _fields_ = [("kind", _I), ("dim", _I * 3), ("num_mips", _I), ("seed", _U), ("frame_time", _F), ("sigma_a", _F * 3),
                 ("sigma_s", _F * 3), ("g", _F), ("density_scale", _F), ("voxel_size", _F), ("world_translation", _F * 3),
@@ -144,6 +148,7 @@ SYMBOLS = [
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
     "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
     "vrestir_scene_grid", "vrestir_scene_dense_mip", "vrestir_scene_stats", "vrestir_camera_look_at",
+    "vrestir_mips_build_device", "vrestir_mips_count", "vrestir_mips_level", "vrestir_mips_destroy",
     "vrestir_accum_create", "vrestir_accum_destroy", "vrestir_accum_update", "vrestir_accum_reset", "vrestir_accum_resize",
     "vrestir_accum_frame_count", "vrestir_accum_execute", "vrestir_error_measure",
     "vrestir_make_sky_envmap", "vrestir_make_emissive_shell", "vrestir_make_blackbody_lut", "vrestir_scene_load_vbx", "vrestir_scene_save_vbx",
@@ -187,6 +192,10 @@ def lib():
     L.vrestir_execute_host.argtypes = [vp, vp, vp]
     L.vrestir_execute_stage.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.vrestir_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.vrestir_mips_build_device.argtypes = [C.c_int, vp, C.POINTER(_I * 3), C.c_int, C.POINTER(vp), vp]
+    L.vrestir_mips_count.argtypes = [vp, C.POINTER(C.c_int)]
+    L.vrestir_mips_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(MipLevel)]
+    L.vrestir_mips_destroy.argtypes = [vp]
     L.vrestir_accum_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.vrestir_accum_destroy.argtypes = [vp]
     L.vrestir_accum_update.argtypes = [vp, C.c_char_p, C.c_double]

@@ -22,13 +22,16 @@
 namespace vrd {
 
 #ifndef VR_REFILL_MIN
-#define VR_REFILL_MIN 12
+#define VR_REFILL_MIN 16
 #endif
 #ifndef VR_SLOW_WEIGHT
 #define VR_SLOW_WEIGHT 2
 #endif
 #ifndef VR_STEPS_PER_VOTE
 #define VR_STEPS_PER_VOTE 3
+#endif
+#ifndef VR_PREFETCH_CHILD
+#define VR_PREFETCH_CHILD 1
 #endif
 
 // Lane states; state >> 1 is the group the majority vote counts: 0 parked, 1 level-1 stepping, 2 in-brick sampling, 3 slow
@@ -110,6 +113,7 @@ struct MarchTrav {
             int it = 0;
             while (it++ < 3 && (p.x < 0 || p.y < 0 || p.z < 0 || p.x > r || p.y > r || p.z > r)) { next(); step(); }
         }
+        if (phase == MARCH_TRAV) fetchChild(g);
     }
 
     // ---- slow events (group 3) -------------------------------------------------------------------------------------
@@ -137,30 +141,43 @@ struct MarchTrav {
         link1 = (uint32_t)h.w; vmin1 = nodePos(h);
         tMax1 = ty;
         prepare(vmin1, g.vdel[1], g.ivdel[1]);
-        phase = tx > tMax1 ? MARCH_ASCEND : MARCH_TRAV;
+        if (tx > tMax1) phase = MARCH_ASCEND; else { phase = MARCH_TRAV; fetchChild(g); }
     }
 
     // ---- level-1 stepping (group 1) ---------------------------------------------------------------------------------
     // MARCH_EXIT: tail of the outer iteration after the adapter returned (`dda.Step(); t.x += epsilon;` + level check)
-    VRD void exitBrick() {
+    VRD void exitBrick(const DSlot& g) {
         step();
-        phase = tx > tMax1 ? MARCH_ASCEND : MARCH_TRAV;
+        if (tx > tMax1) phase = MARCH_ASCEND; else { phase = MARCH_TRAV; fetchChild(g); }
     }
     // one iteration of the outer loop of VolumeTrackingGVDB inside a level-1 node, up to (not including) the adapter call
+    // child id of the level-1 cell p (ID_UNDEFL = empty)
+    VRD uint32_t childOf(const DSlot& g) const {
+        const unsigned b = (unsigned)((((p.z << g.dim[1]) + p.y) << g.dim[1]) + p.x);
+        if (link1 == ID_UNDEFL) return ID_UNDEFL;
+        // p == res passes the inclusive bound (VR/VolumeUtils.slang:231) and aliases into the list like the shader's
+        // ByteAddressBuffer load; outside the whole list D3D returns 0.  link1 < node count and the list holds < 2^31
+        // entries (checked at upload), so 32-bit arithmetic cannot wrap.
+        const unsigned idx = link1 * g.res3[1] + b;
+        return idx >= g.childCount32[1] ? 0u : __ldg(g.child[1] + idx);
+    }
+#if VR_PREFETCH_CHILD
+    // the child id of the cell a lane stands in is loaded when it steps INTO the cell (`brick` holds it while the lane is in
+    // MARCH_TRAV), so the load latency overlaps the vote and the other lanes' work instead of stalling the next step
+    VRD void fetchChild(const DSlot& g) { brick = inRange(p, g.res[1] + 1) ? childOf(g) : ID_UNDEFL; }
+#else
+    VRD void fetchChild(const DSlot&) {}
+#endif
     VRD void travStep(const DSlot& g) {
         if (!(iter < 4096 && inRange(p, g.res[1] + 1))) { phase = MARCH_DONE; return; }
         iter++;
         next();
-        const unsigned b = (unsigned)((((p.z << g.dim[1]) + p.y) << g.dim[1]) + p.x);
-        uint32_t child = ID_UNDEFL;
-        if (link1 != ID_UNDEFL) {
-            // p == res passes the inclusive bound (VR/VolumeUtils.slang:231) and aliases into the list like the shader's
-            // ByteAddressBuffer load; outside the whole list D3D returns 0.  link1 < node count and the list holds < 2^31
-            // entries (checked at upload), so 32-bit arithmetic cannot wrap.
-            const unsigned idx = link1 * g.res3[1] + b;
-            child = idx >= g.childCount32[1] ? 0u : __ldg(g.child[1] + idx);
-        }
-        if (child == ID_UNDEFL) { step(); if (tx > tMax1) phase = MARCH_ASCEND; return; }
+#if VR_PREFETCH_CHILD
+        const uint32_t child = brick;
+#else
+        const uint32_t child = childOf(g);
+#endif
+        if (child == ID_UNDEFL) { step(); if (tx > tMax1) phase = MARCH_ASCEND; else fetchChild(g); return; }
         brick = child;   // leaf node id until enterBrick() replaces it with the brick id
         phase = MARCH_ENTER;
     }
@@ -393,7 +410,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
         if (VR_SLOW_WEIGHT * nSlow >= max(nT, nS)) {
             if (grp == 3) m.slowStep(g);
         } else if (nT >= nS) {
-            if (m.phase == MARCH_EXIT) m.exitBrick();
+            if (m.phase == MARCH_EXIT) m.exitBrick(g);
 #pragma unroll 1
             for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.phase == MARCH_TRAV) m.travStep(g);
         } else {

@@ -103,7 +103,7 @@ VRD void pairTraverse(PairShared& S, const uint4* __restrict__ tasks, unsigned t
                         m.vmin1 = f3(S.vmin1[0][slot], S.vmin1[1][slot], S.vmin1[2][slot]);
                         m.tDel = make_float3(fabsf(g.vdel[1] * m.invDir.x), fabsf(g.vdel[1] * m.invDir.y), fabsf(g.vdel[1] * m.invDir.z));   // level-1 tDel (bricks are entered from level 1)
                         has = true;
-                        m.exitBrick();
+                        m.exitBrick(g);
                     }
                 }
                 head += take;
