@@ -327,7 +327,7 @@ int vrestir_execute_stage(vrestir_pass* pass, int stage, int arg, float* out_col
  * internal stream, next to K2..K5 of frame f; vrestir_execute(f+1) adopts them when the camera, frame counter, row band,
  * options and scene of frame f+1 are what the prefetch assumed, and otherwise discards them and runs K0/K1 itself (same
  * results either way, bit for bit).  The prefetch assumes the camera stays where it is unless the application announces the
- * next frame's camera here before vrestir_execute(f) (NULL clears it). */
+ * next frame's camera here before vrestir_execute(f) (one announcement covers one frame; NULL clears it). */
 int vrestir_set_next_camera(vrestir_pass* pass, const vrestir_camera* camera);
 typedef struct vrestir_pipeline_stats {
     uint64_t adopted, discarded;   /* prefetched frames used / thrown away since create */

@@ -135,7 +135,8 @@ int ensureBuffers(vrestir_pass* p) {
     const int B = p->P.mMaxBounces;
     if (p->allocW == p->W && p->allocH == p->H && p->allocB == B && p->res[0]) return VRESTIR_OK;
     const size_t n = N(p);
-    if (p->pfStream) CK(cudaStreamSynchronize(p->pfStream));
+    if (p->pfStream) CK(cudaStreamSynchronize(p->pfStream));     // a prefetch may be writing, a deferred K5 reading them
+    if (p->outStream) CK(cudaStreamSynchronize(p->outStream));
     p->pfValid = false;
     for (int i = 0; i < 4; i++) { if (p->res[i]) cudaFree(p->res[i]); p->res[i] = nullptr; }
     for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); p->ext[i] = nullptr; }
@@ -585,6 +586,7 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
             p->pfTimed = true;
             makePrefetchKey(p, c, fn.frameCount, p->pfKey);
             p->pfValid = true;
+            p->haveNextCam = false;   // an announcement covers one frame; without a new one the camera is assumed to stay
             break;
         }
         case 2:
