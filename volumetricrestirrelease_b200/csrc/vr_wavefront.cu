@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfInitia
 // (E1: the history sample on the current ray = resampleNeighbor; E0: the current sample on the previous-frame ray = the
 // Talbot MIS term).  Block slots: E0 = {0,1,2}, E1 = {3,4,5} (density, camera Tr, light Tr), 6 = state flag,
 // 7/8 = reprojected pixel, 9..12 = RNG state after the reprojection-depth sampling.
-enum { T2_E0 = 0, T2_E1 = 3, T2_FLAG = 6, T2_POS = 7, T2_SG = 9 };
+enum { T2_E0 = 0, T2_E1 = 3, T2_FLAG = 6, T2_POS = 7, T2_SG = 9, K2_BLOCK = 16 };   // 13 floats used: one 64-byte block per pixel
 
 VRD float3 prevRayDir(const FrameParams& fp, int px, int py) {
     return normalize(camRayDirNN(c_prev.prevU, c_prev.prevV, c_prev.prevW, px, py, fp.W, fp.H));
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(128, VR_TGATHER_MINB) k_temporal_gather(FrameP
     const bool inFrame = pixelOf(fp, x, y);
     const int W = fp.W, H = fp.H;
     const int pixelId = inFrame ? y * W + x : fp.rowBegin * W;
-    const unsigned blkBase = (unsigned)(pixelId - fp.rowBegin * W) * WF_BLOCK;
+    const unsigned blkBase = (unsigned)(pixelId - fp.rowBegin * W) * K2_BLOCK;
     float* blk = wf.results + blkBase;
     bool wantE0 = false, wantE1 = false;
     Reservoir t0 = createNewReservoir(), t1 = createNewReservoir();
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(128, VR_TCOMB_MINB) k_temporal_combine(FramePa
     if (!pixelOf(fp, x, y)) return;
     const int W = fp.W;
     const int pixelId = y * W + x;
-    const float* blk = wf.results + (size_t)(pixelId - fp.rowBegin * W) * WF_BLOCK;
+    const float* blk = wf.results + (size_t)(pixelId - fp.rowBegin * W) * K2_BLOCK;
     if (blk[T2_FLAG] == 0.f) return;
     SampleGenerator sg;
     sg.s0 = __float_as_uint(blk[T2_SG]); sg.s1 = __float_as_uint(blk[T2_SG + 1]); sg.s2 = __float_as_uint(blk[T2_SG + 2]); sg.s3 = __float_as_uint(blk[T2_SG + 3]);
