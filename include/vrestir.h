@@ -398,6 +398,13 @@ int vrestir_mips_build_device(int device, const float* dense_mip0, const int32_t
 int vrestir_mips_count(const vrestir_mip_chain* chain, int* out);
 int vrestir_mips_level(const vrestir_mip_chain* chain, int mip, int conservative, vrestir_mip_level* out);
 int vrestir_mips_destroy(vrestir_mip_chain* chain);
+/* Binds the density slots (every mip, normal and conservative) of `pass` to a GPU-built chain without a round trip of the
+ * voxels through the host: brick pools, quad repacks and brick bounds are produced on the device, only the brick-activity
+ * maps (1 byte per brick) visit the host, where the tree over them is built (like the host builder, bit-identical slots).
+ * `tmpl` = grid description of a host-built volume of the SAME dimensions (e.g. frame 0 of an animated sequence): it
+ * supplies the transforms, the volume description and the temperature / velocity grids.  advance != 0 has the semantics of
+ * vrestir_advance_volume (the current grids become the previous frame's, F/Scene/Scene.cpp:825-863). */
+int vrestir_set_volume_from_chain(vrestir_pass* pass, const vrestir_mip_chain* chain, const vrestir_grid_desc* tmpl, int advance);
 
 /* Diagnostics: world-space rays whose hierarchical DDA ran >= 1024 outer iterations since the last call
  * (8 floats each: origin, dir, mip (+100 when vertex-centred), iterations; first 64) and their total count. */

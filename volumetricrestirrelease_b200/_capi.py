@@ -148,7 +148,7 @@ SYMBOLS = [
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
     "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
     "vrestir_scene_grid", "vrestir_scene_dense_mip", "vrestir_scene_stats", "vrestir_camera_look_at",
-    "vrestir_mips_build_device", "vrestir_mips_count", "vrestir_mips_level", "vrestir_mips_destroy",
+    "vrestir_set_volume_from_chain", "vrestir_mips_build_device", "vrestir_mips_count", "vrestir_mips_level", "vrestir_mips_destroy",
     "vrestir_accum_create", "vrestir_accum_destroy", "vrestir_accum_update", "vrestir_accum_reset", "vrestir_accum_resize",
     "vrestir_accum_frame_count", "vrestir_accum_execute", "vrestir_error_measure",
     "vrestir_make_sky_envmap", "vrestir_make_emissive_shell", "vrestir_make_blackbody_lut", "vrestir_scene_load_vbx", "vrestir_scene_save_vbx",
@@ -196,6 +196,7 @@ def lib():
     L.vrestir_mips_count.argtypes = [vp, C.POINTER(C.c_int)]
     L.vrestir_mips_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(MipLevel)]
     L.vrestir_mips_destroy.argtypes = [vp]
+    L.vrestir_set_volume_from_chain.argtypes = [vp, vp, C.POINTER(GridDesc), C.c_int]
     L.vrestir_accum_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.vrestir_accum_destroy.argtypes = [vp]
     L.vrestir_accum_update.argtypes = [vp, C.c_char_p, C.c_double]

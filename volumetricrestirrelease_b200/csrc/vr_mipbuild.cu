@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/vrestir.h"
+#include "vr_mipbuild.h"
 
 namespace vr { int setError(int code, const std::string& msg); }
 using vr::setError;
@@ -27,7 +28,7 @@ using vr::setError;
 
 struct vrestir_mip_chain {
     int device = 0, numMips = 0;
-    struct Level { void* data = nullptr; float* raw = nullptr; int dim[3] = {0, 0, 0}; int format = 0; float maxValue = 1.f; size_t bytes = 0; };
+    struct Level { void* data = nullptr; float* raw = nullptr; uint8_t* active = nullptr; int dim[3] = {0, 0, 0}; int format = 0; float maxValue = 1.f; size_t bytes = 0; };
     Level lev[2][VRESTIR_NUM_MAX_MIPS];   // [conservative][mip]
     unsigned* maxBits = nullptr;          // one per level: bits of max |v|
 };
@@ -101,8 +102,55 @@ __global__ void k_store(const float* __restrict__ src, size_t n, const unsigned*
     } else ((float*)dst)[p] = v;
 }
 
+// brick activity: any non-zero RAW value in the 10^3 apron-inclusive block (the host builder's rule, before the 1e-9 flush)
+__global__ void k_activity(const float* __restrict__ raw, Dim d, int BX, int BY, int BZ, uint8_t* __restrict__ active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= BX * BY * BZ) return;
+    const int bx = b % BX, by = (b / BX) % BY, bz = b / (BX * BY);
+    bool any = false;
+    for (int z = bz * 8 - 1; z <= bz * 8 + 8 && !any; z++)
+        for (int y = by * 8 - 1; y <= by * 8 + 8 && !any; y++)
+            for (int x = bx * 8 - 1; x <= bx * 8 + 8; x++) if (at(raw, d, x, y, z) != 0.f) { any = true; break; }
+    active[b] = any ? 1 : 0;
+}
+
+__global__ void k_pack_bricks(const void* __restrict__ level, Dim d, int format, const vrestir_node* __restrict__ nodes0, size_t total, void* __restrict__ atlas) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const unsigned bi = (unsigned)(gid / VRESTIR_BRICK_VOXELS), r = (unsigned)(gid % VRESTIR_BRICK_VOXELS);
+    const int lx = r % 10, ly = (r / 10) % 10, lz = r / 100;
+    const int x = nodes0[bi].pos[0] + lx - 1, y = nodes0[bi].pos[1] + ly - 1, z = nodes0[bi].pos[2] + lz - 1;
+    const bool in = x >= 0 && y >= 0 && z >= 0 && x < d.nx && y < d.ny && z < d.nz;
+    const size_t o = in ? ((size_t)z * d.ny + y) * d.nx + x : 0;
+    if (format == VRESTIR_ATLAS_UNORM8) ((uint8_t*)atlas)[gid] = in ? ((const uint8_t*)level)[o] : (uint8_t)0;
+    else ((float*)atlas)[gid] = in ? ((const float*)level)[o] : 0.f;
+}
+
+__global__ void k_brick_bounds(const void* __restrict__ atlas, int format, float maxv, vrestir_node* __restrict__ nodes0, unsigned brickCount) {
+    const unsigned bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= brickCount) return;
+    const size_t base = (size_t)bi * VRESTIR_BRICK_VOXELS;
+    float mn = 3.402823466e+38f, mx = 0.f, sum = 0.f;
+    for (int i = -1; i <= 8; i++) for (int j = -1; j <= 8; j++) for (int k = -1; k <= 8; k++) {
+        const size_t idx = base + (size_t)((k + 1) * 10 + (j + 1)) * 10 + (i + 1);
+        const float v = format == VRESTIR_ATLAS_UNORM8 ? (float)((const uint8_t*)atlas)[idx] * 0.003921568859368563f * maxv : ((const float*)atlas)[idx];
+        mn = fminf(mn, v); mx = fmaxf(mx, v); sum += v;
+    }
+    nodes0[bi].bounds[0] = mn; nodes0[bi].bounds[1] = mx; nodes0[bi].bounds[2] = sum / 512.f; nodes0[bi].bounds[3] = 0.f;
+}
+
+// per brick [10][9][9] words, word(z,y,x) = codes (x,y) (x+1,y) (x,y+1) (x+1,y+1) of plane z
+__global__ void k_quad_repack(const uint8_t* __restrict__ atlas, size_t totalWords, uint32_t* __restrict__ quads) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= totalWords) return;
+    const unsigned b = (unsigned)(gid / 810), r = (unsigned)(gid % 810);
+    const int x = r % 9, y = (r / 9) % 9, z = r / 81;
+    const uint8_t* c = atlas + (size_t)b * VRESTIR_BRICK_VOXELS + (z * 10 + y) * 10 + x;
+    quads[gid] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[10] << 16) | ((uint32_t)c[11] << 24);
+}
+
 void freeChain(vrestir_mip_chain* c) {
-    for (auto& kind : c->lev) for (auto& l : kind) { if (l.data) cudaFree(l.data); if (l.raw) cudaFree(l.raw); l.data = nullptr; l.raw = nullptr; }
+    for (auto& kind : c->lev) for (auto& l : kind) { if (l.data) cudaFree(l.data); if (l.raw) cudaFree(l.raw); if (l.active) cudaFree(l.active); l.data = nullptr; l.raw = nullptr; l.active = nullptr; }
     if (c->maxBits) cudaFree(c->maxBits);
     c->maxBits = nullptr;
 }
@@ -156,8 +204,11 @@ int vrestir_mips_build_device(int device, const float* dense_mip0, const int32_t
             k_conservative0<<<gridOf(d), 128, 0, st>>>(cur, c->lev[1][0].raw, d);
             cons = c->lev[1][0].raw;
         }
+        const int BX = (d.nx + 7) / 8, BY = (d.ny + 7) / 8, BZ = (d.nz + 7) / 8;
         for (int k = 0; k < 2; k++) {
             const float* raw = k == 0 ? cur : cons;
+            CKF(cudaMalloc(&c->lev[k][m].active, (size_t)BX * BY * BZ));
+            k_activity<<<(BX * BY * BZ + 127) / 128, 128, 0, st>>>(raw, d, BX, BY, BZ, c->lev[k][m].active);
             unsigned* mb = c->maxBits + (k * VRESTIR_NUM_MAX_MIPS + m);
             k_absmax<<<std::min<size_t>((size_t)sms * 8, (n + 255) / 256), 256, 0, st>>>(raw, n, mb);
             k_store<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, n, mb, c->lev[k][m].format, k, c->lev[k][m].data);
@@ -208,3 +259,29 @@ int vrestir_mips_count(const vrestir_mip_chain* c, int* out) {
 }
 
 }  // extern "C"
+
+namespace vr {
+int chainLevelView(const vrestir_mip_chain* c, int mip, int conservative, ChainLevelView& out) {
+    if (!c || mip < 0 || mip >= c->numMips) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mip level not built");
+    const vrestir_mip_chain::Level& L = c->lev[conservative ? 1 : 0][mip];
+    out.data = L.data; out.active = L.active; out.format = L.format; out.maxValue = L.maxValue;
+    for (int i = 0; i < 3; i++) out.dim[i] = L.dim[i];
+    return VRESTIR_OK;
+}
+int chainDevice(const vrestir_mip_chain* c) { return c ? c->device : -1; }
+cudaError_t launchPackBricks(const void* level, const int dim[3], int format, const vrestir_node* nodes0, uint32_t brickCount, void* atlas, cudaStream_t st) {
+    const size_t total = (size_t)brickCount * VRESTIR_BRICK_VOXELS;
+    if (total) k_pack_bricks<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(level, Dim{dim[0], dim[1], dim[2]}, format, nodes0, total, atlas);
+    return cudaGetLastError();
+}
+cudaError_t launchBrickBounds(const void* atlas, int format, float maxValue, vrestir_node* nodes0, uint32_t brickCount, cudaStream_t st) {
+    if (brickCount) k_brick_bounds<<<(brickCount + 127) / 128, 128, 0, st>>>(atlas, format, maxValue, nodes0, brickCount);
+    return cudaGetLastError();
+}
+cudaError_t launchQuadRepack(const uint8_t* atlas, uint32_t brickCount, uint32_t* quads, cudaStream_t st) {
+    const size_t total = (size_t)brickCount * 810;
+    if (total) k_quad_repack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(atlas, total, quads);
+    return cudaGetLastError();
+}
+}  // namespace vr
+

@@ -19,6 +19,7 @@
 
 #include "vr_host.h"
 #include "vr_kernels.h"
+#include "vr_mipbuild.h"
 
 using namespace vrd;
 
@@ -234,12 +235,12 @@ int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
     const size_t bytes = (size_t)g.brick_count * g.atlas_channels * VRESTIR_BRICK_VOXELS * (g.atlas_format == VRESTIR_ATLAS_UNORM8 ? 1 : 4);
     if (bytes) {
         CK(cudaMalloc(&d.atlas, bytes + 16));
-        CK(cudaMemcpy(d.atlas, g.atlas, bytes, cudaMemcpyHostToDevice));
+        if (g.atlas) CK(cudaMemcpy(d.atlas, g.atlas, bytes, cudaMemcpyHostToDevice));   // NULL: the caller fills the pool on the device
         d.atlasBytes = bytes;
     }
     s.atlas = d.atlas;
     s.quads = nullptr;
-    if (bytes && g.atlas_format == VRESTIR_ATLAS_UNORM8 && g.atlas_channels == 1) {
+    if (bytes && g.atlas && g.atlas_format == VRESTIR_ATLAS_UNORM8 && g.atlas_channels == 1) {
         // device-only repack for trilinear fetches: per brick [10][9][9] words, word(z,y,x) = codes (x,y) (x+1,y) (x,y+1) (x+1,y+1) of plane z
         std::vector<uint32_t> q((size_t)g.brick_count * 810);
         const uint8_t* a = (const uint8_t*)g.atlas;
@@ -875,6 +876,80 @@ int vrestir_advance_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
     p->volBase = g->volume; p->volBase.lastFrameHasEmission = lastHasEmission; p->volBase.hasAnimation = 1;
     if (g->blackbody_lut && !p->d_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, g->blackbody_lut, 2048, cudaMemcpyHostToDevice)); p->scene.lut = (const float4*)p->d_lut; }
     p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr;
+    applyOverrides(p);
+    return VRESTIR_OK;
+}
+
+// Device-resident volume update: the density slots come from a GPU-built mip chain, everything else
+// (transforms, volume description, temperature / velocity grids) from `tmpl`, the grid description of a host-built volume
+// of the same dimensions (typically frame 0 of the sequence).  Only the brick-activity maps (1 byte per brick) visit the
+// host, where the tree over them is built; brick pools, quad repacks and brick bounds are produced on the device.
+int vrestir_set_volume_from_chain(vrestir_pass* p, const vrestir_mip_chain* chain, const vrestir_grid_desc* tmpl, int advance) {
+    if (!p || !chain || !tmpl) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (vr::chainDevice(chain) != p->device) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "the chain lives on another device");
+    if (advance && !p->haveVolume) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "advance before a volume was set");
+    if (!tmpl->slots[0].valid) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "template slot 0 (density mip 0) must be valid");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    if (advance) {   // like vrestir_advance_volume: the current density / temperature / velocity grids become the previous frame's
+        auto moveSlot = [&](int from, int to) {
+            freeSlot(p->dslots[to]);
+            p->dslots[to] = p->dslots[from]; p->dslots[from] = DevSlot{};
+            p->scene.slots[to] = p->scene.slots[from]; memset(&p->scene.slots[from], 0, sizeof(DSlot));
+        };
+        for (int i = 0; i < VRESTIR_NUM_MAX_MIPS; i++) if (VRESTIR_PREV_DENSITY_GRID_OFFSET + i < VRESTIR_MAX_SLOTS) moveSlot(i, VRESTIR_PREV_DENSITY_GRID_OFFSET + i);
+        moveSlot(VRESTIR_TEMPERATURE_GRID_ID, VRESTIR_TEMPERATURE_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
+        moveSlot(VRESTIR_VELOCITY_GRID_ID, VRESTIR_VELOCITY_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
+    }
+    int built = 0;
+    if (vrestir_mips_count(chain, &built)) return VRESTIR_ERR_INVALID_ARGUMENT;
+    const int lastSlot = advance ? VRESTIR_PREV_DENSITY_GRID_OFFSET - 1 : VRESTIR_MAX_SLOTS;
+    for (int s = 0; s < lastSlot; s++) {
+        const bool density = s < 2 * VRESTIR_NUM_MAX_MIPS;
+        const int mip = s % VRESTIR_NUM_MAX_MIPS, cons = s / VRESTIR_NUM_MAX_MIPS;
+        const vrestir_grid_slot& t = tmpl->slots[s];
+        if (!density || !t.valid) { int rc = uploadSlot(p, s, t); if (rc) return rc; continue; }   // non-density grids: host data of the template
+        if (mip >= built) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "the chain has fewer levels than the template volume");
+        vr::ChainLevelView lv;
+        int rc = vr::chainLevelView(chain, mip, cons, lv); if (rc) return rc;
+        if (lv.dim[0] != (int)t.bmax[0] || lv.dim[1] != (int)t.bmax[1] || lv.dim[2] != (int)t.bmax[2] || lv.format != t.atlas_format || t.atlas_channels != 1)
+            return setError(VRESTIR_ERR_INVALID_ARGUMENT, "chain level and template slot differ in size or format");
+        const int BX = (lv.dim[0] + 7) / 8, BY = (lv.dim[1] + 7) / 8, BZ = (lv.dim[2] + 7) / 8;
+        std::vector<uint8_t> active((size_t)BX * BY * BZ);
+        CK(cudaMemcpy(active.data(), lv.active, active.size(), cudaMemcpyDeviceToHost));
+        vr::Topology topo;
+        vr::buildTopology(active, lv.dim[0], lv.dim[1], lv.dim[2], topo);
+        vrestir_grid_slot g = t;   // dims, res, vdel, bounds, transform of the template
+        g.top_lev = topo.topLev;
+        for (int l = 0; l < 3; l++) {
+            g.node_count[l] = (uint32_t)topo.nodes[l].size(); g.nodes[l] = topo.nodes[l].empty() ? nullptr : topo.nodes[l].data();
+            g.childlist[l] = topo.child[l].empty() ? nullptr : topo.child[l].data(); g.childlist_count[l] = topo.child[l].size();
+        }
+        g.brick_count = topo.brickCount; g.atlas = nullptr;
+        g.max_value = lv.maxValue; g.compress_scale = lv.format == VRESTIR_ATLAS_UNORM8 ? lv.maxValue : 1.f;
+        rc = uploadSlot(p, s, g); if (rc) return rc;
+        DevSlot& d = p->dslots[s];
+        CK(vr::launchPackBricks(lv.data, lv.dim, lv.format, (const vrestir_node*)d.nodes[0], topo.brickCount, d.atlas, 0));
+        CK(vr::launchBrickBounds(d.atlas, lv.format, lv.maxValue, (vrestir_node*)d.nodes[0], topo.brickCount, 0));
+        if (lv.format == VRESTIR_ATLAS_UNORM8) {
+            d.quadBytes = (size_t)topo.brickCount * 810 * 4;
+            CK(cudaMalloc(&d.quads, d.quadBytes));
+            CK(vr::launchQuadRepack((const uint8_t*)d.atlas, topo.brickCount, (uint32_t*)d.quads, 0));
+            p->scene.slots[s].quads = (const uint32_t*)d.quads;
+        }
+        p->launches += 3;
+    }
+    CK(cudaDeviceSynchronize());
+    const int lastHasEmission = p->volBase.hasEmission;
+    p->volBase = tmpl->volume;
+    if (advance) { p->volBase.lastFrameHasEmission = lastHasEmission; p->volBase.hasAnimation = 1; }
+    if (!advance || !p->d_lut) {
+        if (p->d_lut) { cudaFree(p->d_lut); p->d_lut = nullptr; }
+        if (tmpl->blackbody_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, tmpl->blackbody_lut, 2048, cudaMemcpyHostToDevice)); }
+        p->scene.lut = (const float4*)p->d_lut;
+    }
+    p->haveVolume = true; p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr;
+    if (!advance) p->mOptionsChanged = true;
     applyOverrides(p);
     return VRESTIR_OK;
 }

@@ -196,6 +196,63 @@ struct BuiltSlot {
     bool used = false;
 };
 
+// Tree over the active bricks (GVDB 5-4-3 layout): level-1 nodes per 128^3 cell that has an active brick (z-major), level-0
+// nodes (bricks) in (node1, z, y, x) order, a level-2 root when more than one level-1 cell exists.  Shared by the host slot
+// builder below and by the device-resident path (vrestir_set_volume_from_chain), which feeds it a GPU-computed activity map.
+void buildTopology(std::vector<uint8_t>& active, int nx, int ny, int nz, Topology& out) {
+    const int BX = (nx + 7) / 8, BY = (ny + 7) / 8, BZ = (nz + 7) / 8;
+    // ensure at least one brick so the tree is well formed
+    bool anyActive = false; for (auto a : active) anyActive |= a != 0;
+    if (!anyActive) active[0] = 1;
+    const int N1X = (nx + 127) / 128, N1Y = (ny + 127) / 128, N1Z = (nz + 127) / 128;
+    const bool three = (N1X * N1Y * N1Z) > 1;
+    out.topLev = three ? 2 : 1;
+    std::vector<int32_t> n1id((size_t)N1X * N1Y * N1Z, -1);
+    for (int bz = 0; bz < BZ; bz++) for (int by = 0; by < BY; by++) for (int bx = 0; bx < BX; bx++)
+        if (active[((size_t)bz * BY + by) * BX + bx]) n1id[((size_t)(bz / 16) * N1Y + by / 16) * N1X + bx / 16] = 0;
+    uint32_t n1count = 0;
+    for (auto& v : n1id) if (v == 0) v = (int32_t)n1count++;
+    out.n1count = (int)n1count;
+    out.nodes[1].resize(n1count);
+    out.child[1].assign((size_t)n1count * 4096, 0xFFFFFFFFu);
+    uint32_t brickCount = 0;
+    for (int z1 = 0; z1 < N1Z; z1++) for (int y1 = 0; y1 < N1Y; y1++) for (int x1 = 0; x1 < N1X; x1++) {
+        int32_t id = n1id[((size_t)z1 * N1Y + y1) * N1X + x1];
+        if (id < 0) continue;
+        vrestir_node& n = out.nodes[1][id];
+        n.pos[0] = x1 * 128; n.pos[1] = y1 * 128; n.pos[2] = z1 * 128; n.link = (uint32_t)id;
+        n.bounds[0] = n.bounds[1] = n.bounds[2] = n.bounds[3] = 0.f;
+        for (int cz = 0; cz < 16; cz++) for (int cy = 0; cy < 16; cy++) for (int cx = 0; cx < 16; cx++) {
+            int bx = x1 * 16 + cx, by = y1 * 16 + cy, bz = z1 * 16 + cz;
+            if (bx >= BX || by >= BY || bz >= BZ || !active[((size_t)bz * BY + by) * BX + bx]) continue;
+            out.child[1][(size_t)id * 4096 + (((cz << 4) + cy) << 4) + cx] = brickCount++;
+        }
+    }
+    out.brickCount = brickCount;
+    out.nodes[0].resize(brickCount);
+    for (uint32_t id = 0; id < n1count; id++)
+        for (int b = 0; b < 4096; b++) {
+            uint32_t c = out.child[1][(size_t)id * 4096 + b];
+            if (c == 0xFFFFFFFFu) continue;
+            const vrestir_node& n1 = out.nodes[1][id];
+            vrestir_node& n = out.nodes[0][c];
+            n.pos[0] = n1.pos[0] + (b & 15) * 8; n.pos[1] = n1.pos[1] + ((b >> 4) & 15) * 8; n.pos[2] = n1.pos[2] + (b >> 8) * 8; n.link = c;
+            n.bounds[0] = n.bounds[1] = n.bounds[2] = n.bounds[3] = 0.f;
+        }
+    if (three) {
+        out.nodes[2].resize(1);
+        vrestir_node& r = out.nodes[2][0];
+        r.pos[0] = r.pos[1] = r.pos[2] = 0; r.link = 0; r.bounds[0] = r.bounds[1] = r.bounds[2] = r.bounds[3] = 0.f;
+        out.child[2].assign(32768, 0xFFFFFFFFu);
+        for (int z1 = 0; z1 < N1Z; z1++) for (int y1 = 0; y1 < N1Y; y1++) for (int x1 = 0; x1 < N1X; x1++) {
+            int32_t id = n1id[((size_t)z1 * N1Y + y1) * N1X + x1];
+            if (id >= 0) out.child[2][(((z1 << 5) + y1) << 5) + x1] = (uint32_t)id;
+        }
+    } else if (n1count == 0) {
+        out.nodes[1].resize(1);
+    }
+}
+
 static void buildSlot(const Dense& src, int format, bool conservative, BuiltSlot& out, vrestir_grid_slot& g) {
     const int BX = (src.nx + 7) / 8, BY = (src.ny + 7) / 8, BZ = (src.nz + 7) / 8;
     const int ch = src.ch;
@@ -216,53 +273,19 @@ static void buildSlot(const Dense& src, int format, bool conservative, BuiltSlot
                 active[((size_t)bz * BY + by) * BX + bx] = any;
             }
     });
-    // ensure at least one brick so the tree is well formed
-    bool anyActive = false; for (auto a : active) anyActive |= a != 0;
-    if (!anyActive) active[0] = 1;
-
-    const int N1X = (src.nx + 127) / 128, N1Y = (src.ny + 127) / 128, N1Z = (src.nz + 127) / 128;
-    const bool three = (N1X * N1Y * N1Z) > 1;
+    vr::Topology topo;
+    vr::buildTopology(active, src.nx, src.ny, src.nz, topo);
     g = vrestir_grid_slot{};
-    g.valid = 1; g.top_lev = three ? 2 : 1;
+    g.valid = 1; g.top_lev = topo.topLev;
     g.dim[0] = 3; g.dim[1] = 4; g.dim[2] = 5; g.res[0] = 8; g.res[1] = 16; g.res[2] = 32;
     g.vdel[0] = 1.f; g.vdel[1] = 8.f; g.vdel[2] = 128.f; g.noderange[0] = 8; g.noderange[1] = 128; g.noderange[2] = 4096;
-
-    // level-1 nodes: one per 128^3 cell that has an active brick (z-major order), level-0 nodes in (node1, z, y, x) order
-    std::vector<int32_t> n1id((size_t)N1X * N1Y * N1Z, -1);
-    for (int bz = 0; bz < BZ; bz++) for (int by = 0; by < BY; by++) for (int bx = 0; bx < BX; bx++)
-        if (active[((size_t)bz * BY + by) * BX + bx]) n1id[((size_t)(bz / 16) * N1Y + by / 16) * N1X + bx / 16] = 0;
-    uint32_t n1count = 0;
-    for (auto& v : n1id) if (v == 0) v = (int32_t)n1count++;
-    out.nodes[1].resize(n1count);
-    out.child[1].assign((size_t)n1count * 4096, 0xFFFFFFFFu);
-    uint32_t brickCount = 0;
-    for (int z1 = 0; z1 < N1Z; z1++) for (int y1 = 0; y1 < N1Y; y1++) for (int x1 = 0; x1 < N1X; x1++) {
-        int32_t id = n1id[((size_t)z1 * N1Y + y1) * N1X + x1];
-        if (id < 0) continue;
-        vrestir_node& n = out.nodes[1][id];
-        n.pos[0] = x1 * 128; n.pos[1] = y1 * 128; n.pos[2] = z1 * 128; n.link = (uint32_t)id;
-        n.bounds[0] = n.bounds[1] = n.bounds[2] = n.bounds[3] = 0.f;
-        for (int cz = 0; cz < 16; cz++) for (int cy = 0; cy < 16; cy++) for (int cx = 0; cx < 16; cx++) {
-            int bx = x1 * 16 + cx, by = y1 * 16 + cy, bz = z1 * 16 + cz;
-            if (bx >= BX || by >= BY || bz >= BZ || !active[((size_t)bz * BY + by) * BX + bx]) continue;
-            out.child[1][(size_t)id * 4096 + (((cz << 4) + cy) << 4) + cx] = brickCount++;
-        }
-    }
-    out.nodes[0].resize(brickCount);
+    const uint32_t brickCount = topo.brickCount;
+    for (int l = 0; l < 3; l++) { out.nodes[l] = std::move(topo.nodes[l]); out.child[l] = std::move(topo.child[l]); }
     const size_t bpv = format == VRESTIR_ATLAS_UNORM8 ? 1 : 4;
     out.atlas.assign((size_t)brickCount * ch * VRESTIR_BRICK_VOXELS * bpv, 0);
-    // fill bricks
-    std::vector<std::array<int, 3>> brickPos(brickCount);
-    for (uint32_t id = 0; id < n1count; id++)
-        for (int b = 0; b < 4096; b++) {
-            uint32_t c = out.child[1][(size_t)id * 4096 + b];
-            if (c == 0xFFFFFFFFu) continue;
-            const vrestir_node& n1 = out.nodes[1][id];
-            brickPos[c] = {n1.pos[0] + (b & 15) * 8, n1.pos[1] + ((b >> 4) & 15) * 8, n1.pos[2] + (b >> 8) * 8};
-        }
+    // fill bricks (positions and links of the level-0 nodes come from the topology)
     parallelFor((int)brickCount, [&](int bi) {
         vrestir_node& n = out.nodes[0][bi];
-        n.pos[0] = brickPos[bi][0]; n.pos[1] = brickPos[bi][1]; n.pos[2] = brickPos[bi][2]; n.link = (uint32_t)bi;
         for (int c = 0; c < ch; c++) {
             size_t base = ((size_t)bi * ch + c) * VRESTIR_BRICK_VOXELS;
             for (int z = -1; z <= 8; z++) for (int y = -1; y <= 8; y++) for (int x = -1; x <= 8; x++) {
@@ -291,18 +314,6 @@ static void buildSlot(const Dense& src, int format, bool conservative, BuiltSlot
         }
         n.bounds[0] = mn; n.bounds[1] = mx; n.bounds[2] = sum / 512.f; n.bounds[3] = 0.f;
     });
-    if (three) {
-        out.nodes[2].resize(1);
-        vrestir_node& r = out.nodes[2][0];
-        r.pos[0] = r.pos[1] = r.pos[2] = 0; r.link = 0; r.bounds[0] = r.bounds[1] = r.bounds[2] = r.bounds[3] = 0.f;
-        out.child[2].assign(32768, 0xFFFFFFFFu);
-        for (int z1 = 0; z1 < N1Z; z1++) for (int y1 = 0; y1 < N1Y; y1++) for (int x1 = 0; x1 < N1X; x1++) {
-            int32_t id = n1id[((size_t)z1 * N1Y + y1) * N1X + x1];
-            if (id >= 0) out.child[2][(((z1 << 5) + y1) << 5) + x1] = (uint32_t)id;
-        }
-    } else if (n1count == 0) {
-        out.nodes[1].resize(1);
-    }
     for (int l = 0; l < 3; l++) {
         g.node_count[l] = (uint32_t)out.nodes[l].size(); g.nodes[l] = out.nodes[l].empty() ? nullptr : out.nodes[l].data();
         g.childlist[l] = out.child[l].empty() ? nullptr : out.child[l].data(); g.childlist_count[l] = out.child[l].size();

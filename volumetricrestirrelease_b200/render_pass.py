@@ -143,6 +143,13 @@ class VolumetricReSTIR:
         capi.check(self._lib.vrestir_set_camera(self._h, C.byref(cam)))
         return cam
 
+    def setVolumeFromChain(self, chain, advance=False, template=None):
+        """Bind the density grids to a GPU-built mip chain (``mipbuild.build_mips``) without moving the voxels through the host.
+        ``template``: a host-built Volume of the same dimensions (default: the scene's volume) for transforms / description;
+        ``advance=True`` = ``advanceVolume`` semantics (current grids become the previous frame's)."""
+        tmpl = (template or self._scene.volume).grid
+        capi.check(self._lib.vrestir_set_volume_from_chain(self._h, chain._h, tmpl, int(advance)))
+
     def setNextCamera(self, camera=None):
         """Frame pipelining ("mPipelineFrames"): announce the camera of the NEXT frame before executing the current one, so that
         its K0/K1 can run ahead (include/vrestir.h).  `camera`: a scene Camera, or None to clear (= the camera stays put)."""
