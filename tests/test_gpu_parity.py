@@ -610,3 +610,11 @@ def test_volume_from_gpu_chain_renders_identically():
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"animated volume from chain differs at frame {f} ({kw})"
         chainB.close()
     assert (want[-1][..., :3].sum(-1) > 0).mean() > 0.05
+
+
+def test_ragged_frame_size_staged():
+    """A frame whose width / height are not multiples of the 16x8 CTA tile or the 8x4 warp tile (partial tiles on the right and
+    bottom edges): staged parity against the oracle through every stage, default options."""
+    w, h = 150, 91
+    out = _staged(VolumetricReSTIRParams(), env_scene(), w, h, frames=2)
+    _check_staged(out, w, h, "ragged 150x91")
