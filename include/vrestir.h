@@ -293,6 +293,11 @@ int vrestir_set_emissive_triangles(vrestir_pass* pass, const vrestir_emissive_tr
  * (F/Utils/Sampling/AliasTable.cpp:110-124) + original weights; env = per-texel keep-threshold + redirect texel. */
 int vrestir_get_emissive_alias(const vrestir_pass* pass, uint32_t* items4, float* weights, float* weight_sum);
 int vrestir_get_env_alias(const vrestir_pass* pass, float* thresholds, uint32_t* redirect, int* count);
+/* The host-side table builders on their own (no device needed): the emissive table exactly as AliasTable::AliasTable builds it
+ * from per-triangle flux with std::mt19937(123) (F/Utils/Sampling/AliasTable.cpp:46-126, EmissivePowerSampler.cpp:64-79), and
+ * the env-map table over `count` texel weights (what vrestir_set_envmap builds over the finest importance mip). */
+int vrestir_build_alias_table(const float* weights, int count, uint32_t* items4, float* weight_sum);
+int vrestir_build_env_alias(const float* texel_weights, int count, float* thresholds, uint32_t* redirect);
 
 /* Image size and the row band this pass instance owns ([row_begin,row_end) of `height`; whole frame = 0,height). */
 int vrestir_set_frame(vrestir_pass* pass, int width, int height, int row_begin, int row_end);

@@ -1,0 +1,343 @@
+"""Second, independent witness for the two deterministic transmittance estimators.  TEST INFRASTRUCTURE ONLY.
+
+Pure Python / numpy-float32 restatement, written directly from the reference's Slang and NOT from the product's CUDA or the
+C++ oracle, of:
+  * the iterative hierarchical DDA          VR/VolumeUtils.slang:171-282  + F/Scene/GVDB/gvdbDda.slang:86-157
+  * ray-marched transmittance               VR/VolumeTrackingAdapterGVDB.slang:140-208, VR/VolumeUtils.slang:350-362
+  * analytic (regular-tracking) transmittance, trilinear and point      VR/VolumeTrackingAdapterGVDB.slang:20-136
+  * WorldToMedium / IntersectVolumeBound / DensityInAtlas / FetchEightVoxelsInAtlas     VR/VolumeBase.slang:103-175,234-263
+  * getNode / getChild                      F/Scene/GVDB/gvdbNodes.slang:98-114
+for one ray at a time over a grid slot in the layout of include/vrestir.h (32-byte nodes, dense child lists, brick pool of
+10^3 blocks standing in for the 3-D atlas texture).  The texture unit is not in the reference source; it is restated as
+DESIGN.md section 2 pins it: exact fp32 trilinear filtering as fma-lerps in x, then y, then z over the 8 texels around
+(coordinate - 0.5), border colour 0, UNORM8 texels decoded as code * fl(1/255) after filtering.
+
+Every arithmetic step is done in np.float32 in the order the Slang expression tree gives, so the accumulated optical depth
+agrees with the C++ oracle to the last bit except where a fused multiply-add had to be emulated in double (one rounding in
+double, one to float).  tests/test_march_witness.py compares the two on random rays.
+"""
+import ctypes as C
+
+import numpy as np
+
+F = np.float32
+ID_UNDEFL = 0xFFFFFFFF
+MAX_BRICK_STEPS = 128
+K_UNORM8 = F(0.003921568859368563)     # fl(1/255)
+
+NODE = np.dtype([("pos", "<i4", 3), ("link", "<u4"), ("bounds", "<f4", 4)])
+
+
+def slot_arrays(g):
+    """numpy views of one vrestir_grid_slot (ctypes)."""
+    s = {"top_lev": int(g.top_lev), "dim": [int(v) for v in g.dim], "res": [int(v) for v in g.res],
+         "vdel": [F(v) for v in g.vdel], "bmin": np.array(list(g.bmin), dtype=F), "bmax": np.array(list(g.bmax), dtype=F),
+         "w2m": np.array(list(g.world_to_medium), dtype=F).reshape(4, 4), "format": int(g.atlas_format),
+         "channels": int(g.atlas_channels), "compress_scale": F(g.compress_scale), "max_value": F(g.max_value)}
+    s["nodes"], s["child"] = [], []
+    for l in range(3):
+        n = int(g.node_count[l])
+        s["nodes"].append(np.frombuffer(C.string_at(g.nodes[l], n * 32), dtype=NODE) if n and g.nodes[l] else np.zeros(0, NODE))
+        c = int(g.childlist_count[l])
+        s["child"].append(np.frombuffer(C.string_at(g.childlist[l], c * 4), dtype="<u4") if c and g.childlist[l] else np.zeros(0, "<u4"))
+    nvox = int(g.brick_count) * s["channels"] * 1000
+    if s["format"] == 1:
+        s["atlas"] = np.frombuffer(C.string_at(g.atlas, nvox), dtype=np.uint8)
+    else:
+        s["atlas"] = np.frombuffer(C.string_at(g.atlas, nvox * 4), dtype="<f4")
+    return s
+
+
+def _fma(a, b, c):
+    return F(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+def _lerp(a, b, t):
+    return _fma(t, F(b - a), a)
+
+
+def _v3(x, y, z):
+    return np.array([x, y, z], dtype=F)
+
+
+def _mul_point(p, M):   # row vector times matrix, w = 1 (the grids are affine: o.w == 1)
+    return _v3(*[F(F(F(p[0] * M[0, j]) + F(p[1] * M[1, j])) + F(p[2] * M[2, j])) + M[3, j] for j in range(3)])
+
+
+def _mul_vec(v, M):
+    return _v3(*[F(F(v[0] * M[0, j]) + F(v[1] * M[1, j])) + F(v[2] * M[2, j]) for j in range(3)])
+
+
+class _Texture:
+    """The atlas sampler over one brick: p is the coordinate relative to the brick's interior min corner (voxel centres at +0.5)."""
+
+    def __init__(self, slot):
+        self.s = slot
+
+    def texel(self, brick, ix, iy, iz):
+        if not (-1 <= ix <= 8 and -1 <= iy <= 8 and -1 <= iz <= 8):
+            return F(0)   # only reachable through the checked fetches; inside the apron block by construction otherwise
+        return F(self.s["atlas"][brick * self.s["channels"] * 1000 + ((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1)])
+
+    def decode(self, raw):
+        return F(raw * K_UNORM8) if self.s["format"] == 1 else raw
+
+    def point(self, brick, p):
+        return self.decode(self.texel(brick, int(np.floor(p[0])), int(np.floor(p[1])), int(np.floor(p[2]))))
+
+    def linear(self, brick, p):
+        q = p - F(0.5)
+        f0 = np.floor(q)
+        i = [int(f0[0]), int(f0[1]), int(f0[2])]
+        fr = q - f0
+        v = [[[self.texel(brick, i[0] + dx, i[1] + dy, i[2] + dz) for dx in (0, 1)] for dy in (0, 1)] for dz in (0, 1)]
+        c = [[_lerp(v[dz][dy][0], v[dz][dy][1], fr[0]) for dy in (0, 1)] for dz in (0, 1)]
+        d = [_lerp(c[dz][0], c[dz][1], fr[1]) for dz in (0, 1)]
+        return self.decode(_lerp(d[0], d[1], fr[2]))
+
+
+class _HDDA:   # F/Scene/GVDB/gvdbDda.slang:86-157
+    def set_from_ray(self, pos, dirv, tx, ty):
+        self.pos, self.dir = pos, dirv
+        self.pstep = np.array([1 if d > 0 else (-1 if d < 0 else 0) for d in dirv], dtype=np.int32)   # isign3
+        self.tx, self.ty = F(tx), F(ty)
+
+    def prepare(self, vmin, vdel):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.tDel = np.abs(F(vdel) / self.dir)
+            pflt = (self.pos + self.tx * self.dir - vmin) / F(vdel)
+            fl = np.floor(pflt)
+            self.tSide = ((fl - pflt + F(0.5)) * self.pstep.astype(F) + F(0.5)) * self.tDel + self.tx
+        self.p = fl.astype(np.int32)
+
+    def prepare_leaf(self, vmin):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.tDel = np.abs(F(1.0) / self.dir)
+            pflt = self.pos + self.tx * self.dir - vmin
+            fl = np.floor(pflt)
+            self.tSide = ((fl - pflt + F(0.5)) * self.pstep.astype(F) + F(0.5)) * self.tDel + self.tx
+        self.p = fl.astype(np.int32)
+
+    def next(self):
+        t = self.tSide
+        self.mask = np.array([int((t[0] < t[1]) & (t[0] <= t[2])), int((t[1] < t[2]) & (t[1] <= t[0])), int((t[2] < t[0]) & (t[2] <= t[1]))], dtype=np.int32)
+        self.ty = t[0] if self.mask[0] else (t[1] if self.mask[1] else t[2])
+
+    def step(self):
+        self.tx = self.ty
+        # `tSide += float3(mask) * tDel`; an axis with a zero direction has tDel = inf and mask 0 (0 * inf would be NaN:
+        # the repo documents its select-form deviation for that case; the witness rays never have a zero component)
+        self.tSide = (self.tSide + self.mask.astype(F) * self.tDel).astype(F)
+        self.p = self.p + self.mask * self.pstep
+
+    def copy(self):
+        o = _HDDA()
+        o.__dict__.update({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items()})
+        return o
+
+
+class RayMarchingAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:140-208
+    def __init__(self, linear, tstep):
+        self.Tr, self.linear, self.tStep, self.initialized = F(0), linear, F(tstep), False
+
+    def start(self):
+        self.initialized = True
+
+    def main(self, W, dda, vmin_leaf, brick, t):
+        tS = self.tStep
+        t = self.tNear + (np.floor((t - self.tNear) / tS) + F(0.5)) * tS
+        if t < dda.tx:
+            t = t + tS
+        mult = F(1.0)
+        wp = self.ray_o + t * self.ray_d
+        p = wp - vmin_leaf
+        wpt = mult * tS * self.ray_d
+        res = F(W.slot["res"][0])
+        it = 0
+        while it < MAX_BRICK_STEPS and bool(np.all((p >= 0) & (p < res))):
+            if t >= self.tFar:
+                self.Tr = np.exp(self.Tr)
+                return True, t
+            density = W.density_in_atlas(brick, p, self.linear)
+            sigma_t = density * W.sigma_t
+            self.Tr = self.Tr + F(F(-sigma_t) * (F(1.0) if it == 0 else mult)) * tS
+            p = p + wpt
+            t = t + mult * tS
+            it += 1
+        return False, t
+
+    def end(self):
+        self.Tr = np.exp(self.Tr) if self.initialized else F(1.0)
+
+
+class AnalyticAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:20-136
+    def __init__(self, linear):
+        self.Tr, self.linear = F(0), linear
+
+    def start(self):
+        pass
+
+    def main(self, W, dda, vmin_leaf, brick, t):
+        leaf = dda.copy()
+        leaf.prepare_leaf(vmin_leaf)
+        res0 = W.slot["res"][0]
+        it = 0
+        while it < MAX_BRICK_STEPS and bool(np.all((leaf.p >= 0) & (leaf.p < res0))):
+            leaf.next()
+            maxDeltaT = leaf.ty - t
+            if self.linear:
+                v = W.fetch_eight(brick, leaf.p)
+                v = [x * W.sigma_t for x in v]
+                v000, v100, v010, v110, v001, v101, v011, v111 = v
+                mxyz = v111 - v011 - v101 - v110 + v100 + v010 + v001 - v000
+                mxy = v000 - v100 - v010 + v110
+                mxz = v000 - v100 - v001 + v101
+                myz = v000 - v010 - v001 + v011
+                mx, my, mz = v100 - v000, v010 - v000, v001 - v000
+                d = self.ray_d
+                p0 = leaf.pos + leaf.tx * leaf.dir - (leaf.p.astype(F) + vmin_leaf)
+                c3 = mxyz * d[0] * d[1] * d[2]
+                c2 = (p0[2] * d[0] * d[1] + p0[1] * d[0] * d[2] + p0[0] * d[1] * d[2]) * mxyz + mxy * d[0] * d[1] + mxz * d[0] * d[2] + myz * d[1] * d[2]
+                c1 = ((p0[1] * p0[2] * d[0] + p0[0] * p0[2] * d[1] + p0[0] * p0[1] * d[2]) * mxyz + mx * d[0] + my * d[1] + mz * d[2]
+                      + (p0[1] * d[0] + p0[0] * d[1]) * mxy + (p0[2] * d[0] + p0[0] * d[2]) * mxz + (p0[2] * d[1] + p0[1] * d[2]) * myz)
+                c0 = (p0[0] * p0[1] * p0[2] * mxyz + p0[0] * p0[1] * mxy + p0[0] * p0[2] * mxz + p0[1] * p0[2] * myz + p0[0] * mx + p0[1] * my
+                      + p0[2] * mz + v000)
+                t_dist = min(self.tFar - t, maxDeltaT)
+                t2 = t_dist * t_dist
+                t3 = t2 * t_dist
+                t4 = t2 * t2
+                self.Tr = self.Tr + -(c3 * t4 / F(4) + c2 * t3 / F(3) + c1 * t2 / F(2) + c0 * t_dist)
+            else:
+                density = W.density_in_atlas(brick, leaf.p.astype(F) + F(0.5), False)
+                sigma_t = density * W.sigma_t
+                self.Tr = self.Tr + F(-min(self.tFar - t, maxDeltaT)) * sigma_t
+            if t + maxDeltaT >= self.tFar:
+                self.Tr = np.exp(self.Tr)
+                return True, t
+            t = t + maxDeltaT
+            leaf.step()
+            it += 1
+        return False, t
+
+    def end(self):
+        self.Tr = np.exp(self.Tr)
+
+
+class Witness:
+    def __init__(self, grid_desc, slot_index):
+        self.slot = slot_arrays(grid_desc.slots[slot_index])
+        v = grid_desc.volume
+        self.sigma_t = F(v.sigma_t)
+        self.dsf = F(v.densityScaleFactorByScaling)
+        self.tStepBase = F(v.tStep) * F(v.volumeWorldScaling)
+        self.tex = _Texture(self.slot)
+        self.mip = slot_index
+
+    # VR/VolumeBase.slang:252-263
+    def density_in_atlas(self, brick, p, linear):
+        s = self.tex.linear(brick, p) if linear else self.tex.point(brick, p)
+        return s * self.slot["compress_scale"] * self.dsf
+
+    def fetch_eight(self, brick, cell):
+        out = []
+        for i in range(8):
+            raw = self.tex.texel(brick, int(cell[0]) + i % 2, int(cell[1]) + (i % 4) // 2, int(cell[2]) + i // 4)
+            out.append(self.tex.decode(raw) * self.slot["compress_scale"] * self.dsf)
+        return out
+
+    def _node(self, lev, idx):
+        n = self.slot["nodes"][lev][idx]
+        return n["pos"].astype(F), int(n["link"])
+
+    def _child(self, lev, link, b):
+        if link == ID_UNDEFL:
+            return ID_UNDEFL
+        r3 = self.slot["res"][lev] ** 3
+        idx = link * r3 + b
+        lst = self.slot["child"][lev]
+        return int(lst[idx]) if 0 <= idx < len(lst) else 0     # ByteAddressBuffer.Load outside the buffer returns 0
+
+    # VR/VolumeUtils.slang:171-282
+    def track(self, origin_w, dir_w, tmax, adapter, vertex_center):
+        s = self.slot
+        eps = F(0.01)
+        lev = top = s["top_lev"]
+        nodeid = [0, 0, 0]
+        tMaxL = [F(0), F(0), F(0)]
+        o = _mul_point(np.asarray(origin_w, dtype=F), s["w2m"])
+        d = _mul_vec(np.asarray(dir_w, dtype=F), s["w2m"])
+        if vertex_center:
+            o = o - F(0.5)
+        bmin, bmax = s["bmin"].copy(), s["bmax"].copy()
+        if vertex_center:
+            bmin, bmax = bmin - F(0.5), bmax - F(0.5)
+        # Bounds3f::IntersectP (VR/VolumeBase.slang:137-158)
+        t0, t1 = F(0), F(tmax)
+        for i in range(3):
+            inv = F(1) / d[i]
+            tn = (bmin[i] - o[i]) * inv
+            tf = (bmax[i] - o[i]) * inv
+            if tn > tf:
+                tn, tf = tf, tn
+            t0 = tn if tn > t0 else t0
+            t1 = tf if tf < t1 else t1
+            if t0 > t1:
+                adapter.end()
+                return
+        tNear, tFar = t0, t1
+        adapter.tNear, adapter.tFar, adapter.ray_o, adapter.ray_d = tNear, tFar, o, d
+        adapter.start()
+        vmin, link = self._node(lev, 0)
+        tMaxL[lev] = tFar
+        dda = _HDDA()
+        dda.set_from_ray(o, d, tNear + eps, tFar)
+        dda.prepare(vmin, s["vdel"][lev])
+        if vertex_center:
+            it = 0
+            while it < 3 and bool(np.any((dda.p < 0) | (dda.p > s["res"][lev]))):
+                it += 1
+                dda.next(); dda.step(); dda.tx = dda.tx + eps
+        t = tNear
+        links = {lev: link}
+        vmins = {lev: vmin}
+        it = 0
+        while it < 4096 and 0 < lev <= top and bool(np.all((dda.p >= 0) & (dda.p <= s["res"][lev]))):
+            dda.next()
+            dm = s["dim"][lev]
+            b = (((int(dda.p[2]) << dm) + int(dda.p[1])) << dm) + int(dda.p[0])
+            child = self._child(lev, links[lev], b)
+            if child != ID_UNDEFL:
+                if lev == 1:
+                    nodeid[0] = child
+                    t = dda.tx - eps
+                    vmin_leaf, brick = self._node(0, child)
+                    stop, t = adapter.main(self, dda, vmin_leaf, brick, t)
+                    if stop:
+                        return
+                    dda.step(); dda.tx = dda.tx + eps
+                else:
+                    lev -= 1
+                    nodeid[lev] = child
+                    vmins[lev], links[lev] = self._node(lev, child)
+                    tMaxL[lev] = dda.ty
+                    dda.prepare(vmins[lev], s["vdel"][lev])
+            else:
+                dda.step(); dda.tx = dda.tx + eps
+            while lev <= top and dda.tx > tMaxL[lev]:
+                lev += 1
+                if lev <= top:
+                    dda.prepare(vmins[lev], s["vdel"][lev])
+            it += 1
+        adapter.end()
+
+    def ray_marching(self, origin_w, dir_w, tmax, linear=True, tstep_scale=1.0):
+        eff = self.mip - 19 if self.mip >= 19 else self.mip
+        eff = eff - 8 if eff >= 8 else eff
+        a = RayMarchingAdapter(linear, self.tStepBase * F(tstep_scale) * F(eff + 1))
+        self.track(origin_w, dir_w, tmax, a, False)
+        return float(a.Tr)
+
+    def analytic(self, origin_w, dir_w, tmax, linear=True):
+        a = AnalyticAdapter(linear)
+        self.track(origin_w, dir_w, tmax, a, linear)
+        return float(a.Tr)

@@ -35,8 +35,11 @@ def env_scene(kind="bunny", dim=(96, 96, 80), num_mips=4, density_scale=0.08, en
     return sc
 
 
-def make_pair(scene, params, w, h, dict_=None):
-    """(product pass on cuda:0, oracle pass) sharing the scene, the GPU-built importance map and alias tables."""
+def make_pair(scene, params, w, h, dict_=None, own_tables=False):
+    """(product pass on cuda:0, oracle pass) sharing the scene.  By default the oracle receives the GPU-built importance map
+    (checked against the oracle's own in test_env_importance_map) and the product's alias tables (checked against independent
+    numpy restatements of the reference builders in tests/test_alias_tables.py); own_tables=True hands the oracle the emissive
+    alias table rebuilt by that numpy restatement of F/Utils/Sampling/AliasTable.cpp instead of the product's."""
     d = dict(dict_ or {})
     gp = VolumetricReSTIR.create(dict({"mParams": params}, **d))
     gp.setScene(scene, w, h)
@@ -44,10 +47,13 @@ def make_pair(scene, params, w, h, dict_=None):
     env_alias = None
     if scene.envMap is not None:
         imp = gp.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
-        env_alias = gp.env_alias()
+        env_alias = gp.env_alias()   # product extension (no reference counterpart); its distribution is checked in test_alias_tables.py
     em = None
     if scene.emissiveTriangles is not None:
         em = gp.emissive_alias(len(scene.emissiveTriangles))
+        if own_tables:
+            from oracle import alias_oracle
+            em = alias_oracle.emissive_alias_table(scene.emissiveTriangles)
     op = vro.OraclePass(params)
     op.setScene(scene, w, h, importance=imp, emissive_alias=em, env_alias=env_alias)
     if d:
@@ -105,3 +111,81 @@ def rel_mse(a, b):
     b = b[..., :3].astype(np.float64)
     eps = 1e-2 * np.mean(b) ** 2
     return float(np.mean((a - b) ** 2 / (b ** 2 + eps)))
+
+
+FLIP_BUDGET = 1e-3        # north star: flips <= 0.1 % of pixels
+RADIANCE_RTOL = 1e-4      # north star: radiance within 1e-4 relative per pixel (non-flipped)
+
+
+def staged(params, scene, w, h, frames=2, want_mvec=False, dict_=None, camera_path=None, own_tables=False):
+    """Run `frames` frames stage by stage; after every stage the GPU state is overwritten with the oracle's, so each kernel
+    is compared on identical inputs.  Returns per-stage (flips, err) of the last frame + the final images.
+    camera_path: optional list of camera positions, one per frame (K2 reprojection with a moving camera).
+    own_tables: the oracle builds its own alias tables / importance map instead of receiving the product's."""
+    import torch
+    d = dict(dict_ or {})
+    if want_mvec:
+        d["mOutputMotionVec"] = 1
+    gp, op = make_pair(scene, params, w, h, d or None, own_tables=own_tables)
+    out = {}
+    color_g = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    mvec_g = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
+    color_c = np.zeros((h, w, 4), np.float32)
+    mvec_c = np.zeros((h, w, 2), np.float32)
+    B = params.mMaxBounces
+    rounds = params.mSpatialReuseRounds if params.mEnableSpatialReuse else 0
+
+    def sync(buf_ids):
+        for b in buf_ids:
+            gp.set_buffer(b, op.get_buffer(b))
+
+    for f in range(frames):
+        last = f == frames - 1
+        if camera_path is not None:
+            scene.camera.position = tuple(camera_path[f])
+            gp.updateCamera(); op.updateCamera()
+        for stage, arg in [(0, 0), (1, 0), (2, 0)] + [(3, r) for r in range(rounds)] + [(4, 0), (5, 0), (6, 0)]:
+            gp.execute_stage(stage, arg, color_g.data_ptr(), mvec_g.data_ptr())
+            op.execute_stage(stage, arg, color_c, mvec_c)
+            torch.cuda.synchronize()
+            if stage == 0:
+                fg = gp.get_buffer(capi.BUF_FEATURES).view(FEAT)
+                fc = op.get_buffer(capi.BUF_FEATURES).view(FEAT)
+                np.testing.assert_allclose(fg["transmittance"], fc["transmittance"], rtol=2e-5, atol=1e-7)
+                sync([capi.BUF_FEATURES])
+            elif stage in (1, 2):
+                bid = capi.BUF_RESERVOIR_0
+                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid))
+                if last:
+                    out["initial" if stage == 1 else "temporal"] = (flips, err)
+                sync([bid] + ([capi.BUF_EXTRA_0] if B > 1 else []))
+            elif stage == 3:
+                bid = capi.BUF_RESERVOIR_1 if arg % 2 == 0 else capi.BUF_RESERVOIR_0
+                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid))
+                if last:
+                    out[f"spatial{arg}"] = (flips, err)
+                sync([bid] + ([capi.BUF_EXTRA_1 if arg % 2 == 0 else capi.BUF_EXTRA_0] if B > 1 else []))
+            elif stage == 4:
+                if params.mEnableTemporalReuse:
+                    sync([capi.BUF_RESERVOIR_TEMPORAL] + ([capi.BUF_EXTRA_TEMPORAL] if B > 1 else []))
+            elif stage == 5 and last:
+                out["final"] = (color_g.cpu().numpy(), color_c.copy())
+                out["mvec"] = (mvec_g.cpu().numpy(), mvec_c.copy())
+    out["launches"] = gp.launch_count()
+    return out
+
+
+def check_staged(out, w, h, name, budget=FLIP_BUDGET):
+    for k, v in out.items():
+        if k in ("final", "mvec", "launches"):
+            continue
+        flips, err = v
+        print(f"[{name}:{k}] flips {int(flips.sum())}/{flips.size} ({flips.mean():.2e}) rel err {err:.3g}")
+        assert flips.mean() <= budget, k
+        assert err <= RADIANCE_RTOL, k
+    g, c = out["final"]
+    e = rel_err_image(g, c)
+    bad = (e > RADIANCE_RTOL).mean()
+    print(f"[{name}:final] radiance rel err max {float(e.max()):.3g}, frac > 1e-4: {bad:.2e}")
+    assert bad <= budget
+    assert (c[..., :3].sum(-1) > 0).mean() > 0.02, "the test image is (almost) black: nothing was compared"

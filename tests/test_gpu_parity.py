@@ -2,14 +2,14 @@
 import numpy as np
 import pytest
 
-from common import (FEAT, RES, capi, compare_reservoirs, config1_params, config1_scene, env_scene, gpu_frame,
+from common import (FEAT, FLIP_BUDGET, RADIANCE_RTOL, RES, capi, compare_reservoirs, config1_params, config1_scene, env_scene, gpu_frame,
                     make_pair, rel_err_image)
 from volumetricrestirrelease_b200 import VolumetricReSTIR, VolumetricReSTIRParams
 
 pytestmark = pytest.mark.gpu
 
-FLIP_BUDGET = 1e-3        # north star: flips <= 0.1 % of pixels
-RADIANCE_RTOL = 1e-4      # north star: radiance within 1e-4 relative per pixel (non-flipped)
+
+
 
 
 def _report(name, flips, err, e):
@@ -49,68 +49,7 @@ def test_env_importance_map():
     np.testing.assert_allclose(g, c, rtol=2e-5, atol=1e-7)
 
 
-def _staged(params, scene, w, h, frames=2, want_mvec=False):
-    """Run `frames` frames stage by stage; before every stage of the last frame the GPU state is overwritten with the
-    oracle's, so each kernel is compared on identical inputs.  Returns per-stage (flips, err)."""
-    import torch
-    gp, op = make_pair(scene, params, w, h, {"mOutputMotionVec": 1} if want_mvec else None)
-    out = {}
-    color_g = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
-    mvec_g = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
-    color_c = np.zeros((h, w, 4), np.float32)
-    mvec_c = np.zeros((h, w, 2), np.float32)
-    B = params.mMaxBounces
-    rounds = params.mSpatialReuseRounds if params.mEnableSpatialReuse else 0
-
-    def sync(buf_ids):
-        for b in buf_ids:
-            gp.set_buffer(b, op.get_buffer(b))
-
-    for f in range(frames):
-        last = f == frames - 1
-        for stage, arg in [(0, 0), (1, 0), (2, 0)] + [(3, r) for r in range(rounds)] + [(4, 0), (5, 0), (6, 0)]:
-            gp.execute_stage(stage, arg, color_g.data_ptr(), mvec_g.data_ptr())
-            op.execute_stage(stage, arg, color_c, mvec_c)
-            torch.cuda.synchronize()
-            if stage == 0:
-                fg = gp.get_buffer(capi.BUF_FEATURES).view(FEAT)
-                fc = op.get_buffer(capi.BUF_FEATURES).view(FEAT)
-                np.testing.assert_allclose(fg["transmittance"], fc["transmittance"], rtol=2e-5, atol=1e-7)
-                sync([capi.BUF_FEATURES])
-            elif stage in (1, 2):
-                bid = capi.BUF_RESERVOIR_0
-                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid))
-                if last:
-                    out["initial" if stage == 1 else "temporal"] = (flips, err)
-                sync([bid] + ([capi.BUF_EXTRA_0] if B > 1 else []))
-            elif stage == 3:
-                bid = capi.BUF_RESERVOIR_1 if arg % 2 == 0 else capi.BUF_RESERVOIR_0
-                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid))
-                if last:
-                    out[f"spatial{arg}"] = (flips, err)
-                sync([bid] + ([capi.BUF_EXTRA_1 if arg % 2 == 0 else capi.BUF_EXTRA_0] if B > 1 else []))
-            elif stage == 4:
-                if params.mEnableTemporalReuse:
-                    sync([capi.BUF_RESERVOIR_TEMPORAL] + ([capi.BUF_EXTRA_TEMPORAL] if B > 1 else []))
-            elif stage == 5 and last:
-                out["final"] = (color_g.cpu().numpy(), color_c.copy())
-                out["mvec"] = (mvec_g.cpu().numpy(), mvec_c.copy())
-    return out
-
-
-def _check_staged(out, w, h, name, budget=FLIP_BUDGET):
-    for k, v in out.items():
-        if k in ("final", "mvec"):
-            continue
-        flips, err = v
-        print(f"[{name}:{k}] flips {int(flips.sum())}/{flips.size} ({flips.mean():.2e}) rel err {err:.3g}")
-        assert flips.mean() <= budget, k
-        assert err <= RADIANCE_RTOL, k
-    g, c = out["final"]
-    e = rel_err_image(g, c)
-    bad = (e > RADIANCE_RTOL).mean()
-    print(f"[{name}:final] radiance rel err max {float(e.max()):.3g}, frac > 1e-4: {bad:.2e}")
-    assert bad <= budget
+from common import check_staged as _check_staged, staged as _staged  # noqa: E402
 
 
 def test_full_reuse_staged_env():

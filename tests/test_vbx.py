@@ -88,3 +88,46 @@ def test_vbx_errors(tmp_path):
     open(bad, "wb").write(b"\x01\x0b" + b"\0" * 100)      # version 1.11: no xform block
     with pytest.raises(capi.VRestirError):
         sc.loadGVDBVolume(os.path.join(str(tmp_path), "bad"))
+
+
+def test_vbx_malformed_files_are_rejected(tmp_path):
+    """A hostile / corrupted .vbx must come back as an error code: no exception through the C ABI, no out-of-range tree id
+    handed to the device.  Header layout: 2 B version, 48 B transform, 128 B xform + inverse, 24 B bounds, 8 B range, numGrids,
+    grid offset table, then per grid: name[256], dtype/comps/compress (3 B), voxel size (12 B), leafcnt, leafdim[3], apron, numChan,
+    atlasSz (8 B), topo/reuse/layout (1 + 4 + 1 B), axiscnt[3], axisres[3], levels, root (8 B), level table (9 ints per level)."""
+    sc = Scene()
+    sc.addGVDBVolume(dataFile="bunny", dim=(40, 40, 40), seed=5, numMips=1)
+    prefix = os.path.join(str(tmp_path), "v")
+    sc.volume.save_vbx(prefix)
+    good = open(prefix + "_mip0.vbx", "rb").read()
+    hdr = 2 + 48 + 128 + 24 + 8
+    grid = struct.unpack_from("<Q", good, hdr + 4)[0]
+    o_leafcnt = grid + 256 + 3 + 12
+    o_axisres = o_leafcnt + 4 + 12 + 4 + 4 + 8 + 1 + 4 + 1 + 12
+    o_levels = o_axisres + 12
+    o_table = o_levels + 4 + 8
+    levels = struct.unpack_from("<i", good, o_levels)[0]
+    assert levels == 2 and struct.unpack_from("<i", good, o_leafcnt)[0] == struct.unpack_from("<i", good, o_table + 5 * 4)[0]
+
+    def attempt(name, patch):
+        raw = bytearray(good)
+        patch(raw)
+        d = os.path.join(str(tmp_path), name)
+        os.makedirs(d)
+        open(os.path.join(d, "v_mip0.vbx"), "wb").write(bytes(raw))
+        with pytest.raises(capi.VRestirError):
+            Scene().loadGVDBVolume(os.path.join(d, "v"))
+
+    attempt("grids", lambda r: struct.pack_into("<i", r, hdr, 0x7FFFFFF0))                       # numGrids
+    attempt("negcnt", lambda r: (struct.pack_into("<i", r, o_leafcnt, -5), struct.pack_into("<i", r, o_table + 5 * 4, -5)))
+    attempt("hugecnt", lambda r: (struct.pack_into("<i", r, o_leafcnt, 0x7FFFFFFF), struct.pack_into("<i", r, o_table + 5 * 4, 0x7FFFFFFF)))
+    attempt("hugelist", lambda r: struct.pack_into("<i", r, o_table + 9 * 4 + 7 * 4, 0x7FFFFFFF))   # cnt1 of level 1
+    attempt("axisres", lambda r: struct.pack_into("<3i", r, o_axisres, 1 << 19, 1 << 19, 1 << 19))
+    attempt("negaxis", lambda r: struct.pack_into("<3i", r, o_axisres, -10, 10, 10))
+    attempt("truncated", lambda r: r.__delitem__(slice(len(r) // 2, len(r))))
+    # a child id beyond the brick pool: first entry of the level-1 child list (after the node pools)
+    cnt = [struct.unpack_from("<i", good, o_table + n * 36 + 5 * 4)[0] for n in range(levels)]
+    o_child = o_table + levels * 36 + sum(cnt) * 64
+    attempt("childid", lambda r: struct.pack_into("<Q", r, o_child, (cnt[0] + 7) << 16))
+    # the untouched file still loads
+    Scene().loadGVDBVolume(prefix)

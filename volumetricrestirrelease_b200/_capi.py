@@ -142,7 +142,7 @@ SYMBOLS = [
     "vrestir_last_error", "vrestir_version", "vrestir_default_params", "vrestir_create", "vrestir_destroy",
     "vrestir_set_volume", "vrestir_advance_volume", "vrestir_set_camera", "vrestir_set_envmap",
     "vrestir_set_analytic_lights", "vrestir_set_emissive_triangles", "vrestir_get_emissive_alias",
-    "vrestir_get_env_alias", "vrestir_set_frame", "vrestir_update", "vrestir_set_params", "vrestir_get_params",
+    "vrestir_get_env_alias", "vrestir_build_alias_table", "vrestir_build_env_alias", "vrestir_set_frame", "vrestir_update", "vrestir_set_params", "vrestir_get_params",
     "vrestir_set_frame_count", "vrestir_set_prev_camera", "vrestir_get_frame_count", "vrestir_execute",
     "vrestir_execute_host", "vrestir_execute_stage", "vrestir_set_next_camera", "vrestir_get_pipeline_stats", "vrestir_wait_output", "vrestir_get_timings", "vrestir_get_march_timings", "vrestir_debug_read_bandwidth", "vrestir_debug_long_rays", "vrestir_debug_wavefront_counters", "vrestir_get_launch_count",
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
@@ -182,6 +182,8 @@ def lib():
     L.vrestir_set_emissive_triangles.argtypes = [vp, C.POINTER(EmissiveTriangle), C.c_int, C.c_float]
     L.vrestir_get_emissive_alias.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
     L.vrestir_get_env_alias.argtypes = [vp, vp, vp, C.POINTER(C.c_int)]
+    L.vrestir_build_alias_table.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_float)]
+    L.vrestir_build_env_alias.argtypes = [vp, C.c_int, vp, vp]
     L.vrestir_set_frame.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.vrestir_update.argtypes = [vp, C.c_char_p, C.c_double]
     L.vrestir_set_params.argtypes = [vp, C.POINTER(Params)]

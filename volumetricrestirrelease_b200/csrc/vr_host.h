@@ -7,6 +7,8 @@
 
 namespace vr {
 int setError(int code, const std::string& msg);   // records vrestir_last_error() for this thread, returns code
+// call from a catch (...) handler of a C entry point: no C++ exception may unwind through the C ABI
+int caughtException();
 
 // tree over a brick-activity map (vr_scene.cpp)
 struct Topology {

@@ -16,6 +16,7 @@
 
 #include "../../include/vrestir.h"
 #include "vr_mipbuild.h"
+#include "vr_host.h"
 
 namespace vr { int setError(int code, const std::string& msg); }
 using vr::setError;
@@ -161,16 +162,16 @@ dim3 gridOf(Dim d) { return dim3((d.nx + 127) / 128, d.ny, d.nz); }
 
 extern "C" {
 
-int vrestir_mips_destroy(vrestir_mip_chain* c) {
+int vrestir_mips_destroy(vrestir_mip_chain* c) try {
     if (!c) return VRESTIR_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     freeChain(c);
     delete c;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_mips_build_device(int device, const float* dense_mip0, const int32_t dim[3], int num_mips, vrestir_mip_chain** out, void* stream) {
+int vrestir_mips_build_device(int device, const float* dense_mip0, const int32_t dim[3], int num_mips, vrestir_mip_chain** out, void* stream) try {
     if (!dense_mip0 || !dim || !out || dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
     if (dim[1] > 65535 || dim[2] > 65535) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "grid larger than 65535 in y or z");
     int count = 0;
@@ -241,22 +242,22 @@ int vrestir_mips_build_device(int device, const float* dense_mip0, const int32_t
         }
     *out = c;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_mips_level(const vrestir_mip_chain* c, int mip, int conservative, vrestir_mip_level* out) {
+int vrestir_mips_level(const vrestir_mip_chain* c, int mip, int conservative, vrestir_mip_level* out) try {
     if (!c || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (mip < 0 || mip >= c->numMips) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mip level not built");
     const vrestir_mip_chain::Level& L = c->lev[conservative ? 1 : 0][mip];
     out->data = L.data; out->bytes = L.bytes; out->format = L.format; out->max_value = L.maxValue;
     for (int i = 0; i < 3; i++) out->dim[i] = L.dim[i];
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_mips_count(const vrestir_mip_chain* c, int* out) {
+int vrestir_mips_count(const vrestir_mip_chain* c, int* out) try {
     if (!c || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     *out = c->numMips;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 }  // extern "C"
 

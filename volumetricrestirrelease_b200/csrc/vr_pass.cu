@@ -26,6 +26,12 @@ using namespace vrd;
 namespace vr {
 static thread_local std::string g_lastError;
 int setError(int code, const std::string& msg) { g_lastError = msg; return code; }
+int caughtException() {
+    try { throw; }
+    catch (const std::bad_alloc&) { return setError(VRESTIR_ERR_INVALID_ARGUMENT, "out of host memory (a size in the input is implausibly large)"); }
+    catch (const std::exception& e) { return setError(VRESTIR_ERR_INVALID_ARGUMENT, std::string("exception in the host code: ") + e.what()); }
+    catch (...) { return setError(VRESTIR_ERR_INVALID_ARGUMENT, "unknown exception in the host code"); }
+}
 }  // namespace vr
 using vr::setError;
 
@@ -88,6 +94,10 @@ struct vrestir_pass {
     int ia = 0, ib = 1, it = 2, in = 3;   // physical indices of ping-pong buffers 0/1, the temporal history and the prefetch target
     int finalPhys = 0;                 // physical buffer holding the final reservoirs of the frame in flight
     int featCur = 0, featPrev = 1, featNext = 2;
+    // VR/VolumetricReSTIR.cpp:636 copies the features into the history after every temporal frame.  Here the two buffers swap
+    // roles instead, and only when the NEXT active frame starts: until then feat[featCur] stays what the reference's feature
+    // buffer holds (K5's transmittance view on a freeze frame, BUF_FEATURES) and doubles as the history (BUF_FEATURES_TEMPORAL).
+    bool featSwapPending = false;
     DPrevCam prevCam{};
     // Frame pipelining (option mPipelineFrames): K0 + K1 of frame f+1 read no history, so they run on a stream of their own while
     // K2..K5 of frame f run on the caller's stream (the tail of every launch of one chain is filled by the other chain).
@@ -113,6 +123,7 @@ struct vrestir_pass {
     cudaStream_t auxStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaEvent_t evMarch[3] = {}; bool evMarchValid = false;
                                                                       // evMarch: around the two march launches of the last spatial round
+    cudaEvent_t evMainTail = nullptr; bool mainTailValid = false;   // recorded after every stage call: the constant banks are shared per device
     cudaStream_t hostStream = nullptr;
     float4* d_hostColor = nullptr; float2* d_hostMvec = nullptr; size_t hostColorPixels = 0;
     uint64_t launches = 0;
@@ -150,7 +161,7 @@ int ensureBuffers(vrestir_pass* p) {
     for (int i = 0; i < 3; i++) { CK(cudaMalloc(&p->feat[i], n * 8)); CK(cudaMemset(p->feat[i], 0, n * 8)); }
     CK(cudaMalloc(&p->refColor, n * 16)); CK(cudaMemset(p->refColor, 0, n * 16));
     p->allocW = p->W; p->allocH = p->H; p->allocB = B;
-    p->ia = 0; p->ib = 1; p->it = 2; p->in = 3; p->finalPhys = 0; p->featCur = 0; p->featPrev = 1; p->featNext = 2;
+    p->ia = 0; p->ib = 1; p->it = 2; p->in = 3; p->finalPhys = 0; p->featCur = 0; p->featPrev = 1; p->featNext = 2; p->featSwapPending = false;
     return VRESTIR_OK;
 }
 
@@ -331,20 +342,52 @@ void buildFrameParams(vrestir_pass* p, FrameParams& fp, float* out_color, float*
     fp.outColor = (float4*)out_color; fp.outMvec = (float2*)out_mvec;
 }
 
+// The __constant__ banks (scene block, previous camera) exist once per device and are shared by every pass of the process on
+// it.  The registry remembers what each device holds and which passes live there, so that an upload (a) happens whenever the
+// bank may hold another pass's data and (b) is ordered after EVERYTHING the other passes still have in flight that reads the
+// old contents: their main-stream work, a prefetched K0/K1 (which is then discarded: it would be adopted next to constants it
+// was not computed with only if they were identical, but its owner re-uploads anyway) and a deferred K5.
+struct Uploaded { DScene scene; DPrevCam prev; bool have = false; const vrestir_pass* owner = nullptr; std::vector<vrestir_pass*> passes; };
+std::mutex g_constMu;
+std::map<int, std::unique_ptr<Uploaded>> g_constPerDevice;
+void registerPass(vrestir_pass* p) {
+    std::lock_guard<std::mutex> lock(g_constMu);
+    std::unique_ptr<Uploaded>& slot = g_constPerDevice[p->device];
+    if (!slot) slot.reset(new Uploaded());
+    slot->passes.push_back(p);
+}
+void unregisterPass(vrestir_pass* p) {
+    std::lock_guard<std::mutex> lock(g_constMu);
+    auto it = g_constPerDevice.find(p->device);
+    if (it == g_constPerDevice.end() || !it->second) return;
+    auto& v = it->second->passes;
+    v.erase(std::remove(v.begin(), v.end(), p), v.end());
+    if (it->second->owner == p) { it->second->owner = nullptr; it->second->have = false; }
+}
+// make `st` wait for everything the OTHER passes of the device have in flight (they may read the constants about to change)
+int waitForOtherPasses(vrestir_pass* p, Uploaded& slot, cudaStream_t st) {
+    for (vrestir_pass* q : slot.passes) {
+        if (q == p) continue;
+        if (q->mainTailValid) CK(cudaStreamWaitEvent(st, q->evMainTail, 0));
+        if (q->pfValid) { CK(cudaStreamWaitEvent(st, q->evPfDone, 0)); q->pfValid = false; q->pfDiscarded++; }
+        if (q->outSeq) CK(cudaStreamWaitEvent(st, q->evOutDone[(q->outSeq - 1) & 1], 0));
+    }
+    return VRESTIR_OK;
+}
+
 int syncScene(vrestir_pass* p, cudaStream_t st) {
     applyOverrides(p);
     DScene& s = p->scene;
     s.envSamplerType = p->envSamplerType;
-    // The constant banks are per device and shared by every pass of the process on it: remember what each device holds and
-    // upload whenever anything may differ.  (Passes that share a device must not have frames in flight at the same time.)
-    struct Uploaded { DScene scene; DPrevCam prev; bool have = false; };
-    static std::mutex mu;
-    static std::map<int, std::unique_ptr<Uploaded>> perDevice;
-    std::lock_guard<std::mutex> lock(mu);
-    std::unique_ptr<Uploaded>& slot = perDevice[p->device];
+    std::lock_guard<std::mutex> lock(g_constMu);
+    std::unique_ptr<Uploaded>& slot = g_constPerDevice[p->device];
     if (!slot) slot.reset(new Uploaded());
     DScene& lastScene = slot->scene; DPrevCam& lastPrev = slot->prev; bool& haveLast = slot->have;
-    if (!haveLast || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0) {
+    const bool sceneDiffers = !haveLast || p->sceneDirty || memcmp(&lastScene, &s, sizeof(DScene)) != 0;
+    const bool prevDiffers = !haveLast || memcmp(&lastPrev, &p->prevCam, sizeof(DPrevCam)) != 0;
+    if ((sceneDiffers || prevDiffers) && slot->passes.size() > 1) { int rc = waitForOtherPasses(p, *slot, st); if (rc) return rc; }
+    if (sceneDiffers || prevDiffers) slot->owner = p;
+    if (sceneDiffers) {
         // a prefetched K0/K1 was computed with the old constants and may still be reading them
         if (p->pfValid) { CK(cudaStreamWaitEvent(st, p->evPfDone, 0)); p->pfValid = false; p->pfDiscarded++; }
         if (p->outSeq) CK(cudaStreamWaitEvent(st, p->evOutDone[(p->outSeq - 1) & 1], 0));
@@ -356,7 +399,7 @@ int syncScene(vrestir_pass* p, cudaStream_t st) {
             CK(cudaEventRecord(p->evPfGo, st)); CK(cudaStreamWaitEvent(p->pfStream, p->evPfGo, 0));
         }
     }
-    if (!haveLast || memcmp(&lastPrev, &p->prevCam, sizeof(DPrevCam)) != 0) {   // read by K2 only, which runs on `st`
+    if (prevDiffers) {   // read by K2 only, which runs on `st`
         CK(uploadPrevCam(p->prevCam, st));
         CK(uploadPrevCamWavefront(p->prevCam, st));
         lastPrev = p->prevCam;
@@ -485,7 +528,17 @@ int runInitialWavefront(vrestir_pass* p, const FrameParams& fp, cudaStream_t st)
     return VRESTIR_OK;
 }
 
+int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, cudaStream_t st);
 int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, cudaStream_t st) {
+    const int rc = runStageBody(p, stage, arg, out_color, out_mvec, st);
+    if (p && rc == VRESTIR_OK && stage != 6) {   // what other passes of the device must wait for before they touch the constant banks
+        if (!p->evMainTail) CK(cudaEventCreateWithFlags(&p->evMainTail, cudaEventDisableTiming));
+        CK(cudaEventRecord(p->evMainTail, st));
+        p->mainTailValid = true;
+    }
+    return rc;
+}
+int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, cudaStream_t st) {
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
     if (!p->haveVolume || !p->haveCamera || p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "volume/camera/frame not set");
     const vrestir_params& m = p->P;
@@ -512,8 +565,9 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
     }
     if ((stage == 0 || stage == -1) && p->outSeq >= 2) CK(cudaStreamWaitEvent(st, p->evOutDone[p->outSeq & 1], 0));   // deferred K5 of frame f-2
     rc = syncScene(p, st); if (rc) return rc;
-    FrameParams fp; buildFrameParams(p, fp, out_color, out_mvec);
     const bool active = !p->mFreezeFrame;
+    if ((stage == 0 || stage == -1) && active && p->featSwapPending) { std::swap(p->featCur, p->featPrev); p->featSwapPending = false; }
+    FrameParams fp; buildFrameParams(p, fp, out_color, out_mvec);
     switch (stage) {
         case -1:   // frame begin on the main stream when K0 runs concurrently on the auxiliary stream (vrestir_execute)
             recordEv(p, 7, st);
@@ -713,7 +767,7 @@ int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_m
             recordEv(p, 6, st);
             break;
         case 6: {   // VR/VolumetricReSTIR.cpp:765-772 (+ :636 feature history, as a swap)
-            if (active && !m.mUseReference && m.mEnableTemporalReuse) std::swap(p->featCur, p->featPrev);
+            if (active && !m.mUseReference && m.mEnableTemporalReuse) p->featSwapPending = true;   // the swap happens when the next active frame starts
             p->mTemporalSampleAccumulated = 1;
             memcpy(p->prevCam.prevView, p->cam.viewMat, 64); memcpy(p->prevCam.prevProj, p->cam.projMat, 64);
             p->prevCam.prevU = fp.camU; p->prevCam.prevV = fp.camV; p->prevCam.prevW = fp.camW; p->prevCam.prevPos = fp.camPos;
@@ -739,7 +793,7 @@ void buildAliasTable(std::vector<float> weights, std::vector<uint32_t>& itemsOut
     std::vector<float> thresholds(count);
     std::vector<uint32_t> redirect(count);
     uint32_t head = 0, tail = count - 1;
-    if (count == 1) { thresholds[0] = 1.f; redirect[0] = 0; }
+    // count == 1: the loop does not run and the single item stays {threshold 0, indexA 0, indexB 0}, as in the reference
     while (head != tail) {
         int i = permutation[head], j = permutation[tail];
         thresholds[i] = weights[i];
@@ -806,7 +860,7 @@ void vrestir_default_params(vrestir_params* o) {
     o->mFinalRandomSamplerType = VRESTIR_SAMPLER_R2; o->mFinalTStepScale = 0.2f;
 }
 
-int vrestir_create(const vrestir_params* params, int device, vrestir_pass** out) {
+int vrestir_create(const vrestir_params* params, int device, vrestir_pass** out) try {
     if (!out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null out");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -817,14 +871,17 @@ int vrestir_create(const vrestir_params* params, int device, vrestir_pass** out)
     p->device = device;
     if (params) p->P = *params; else vrestir_default_params(&p->P);
     memset(&p->scene, 0, sizeof(p->scene));
+    registerPass(p);
     *out = p;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_destroy(vrestir_pass* p) {
+int vrestir_destroy(vrestir_pass* p) try {
     if (!p) return VRESTIR_OK;
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
+    unregisterPass(p);
+    if (p->evMainTail) cudaEventDestroy(p->evMainTail);
     for (auto& d : p->dslots) freeSlot(d);
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
     for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); if (p->feat[i]) cudaFree(p->feat[i]); }
@@ -842,9 +899,9 @@ int vrestir_destroy(vrestir_pass* p) {
     for (cudaEvent_t e : {p->evPfGo, p->evPfDone, p->evPf0, p->evPf1}) if (e) cudaEventDestroy(e);
     delete p;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_set_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
+int vrestir_set_volume(vrestir_pass* p, const vrestir_grid_desc* g) try {
     if (!p || !g) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
@@ -857,9 +914,9 @@ int vrestir_set_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
     p->haveVolume = true; p->sceneDirty = true; p->mOptionsChanged = true; p->persistBase = p->persistBasePf = nullptr;
     applyOverrides(p);
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_advance_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
+int vrestir_advance_volume(vrestir_pass* p, const vrestir_grid_desc* g) try {
     if (!p || !g || !p->haveVolume) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "advance_volume before set_volume");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
@@ -878,13 +935,13 @@ int vrestir_advance_volume(vrestir_pass* p, const vrestir_grid_desc* g) {
     p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr;
     applyOverrides(p);
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 // Device-resident volume update: the density slots come from a GPU-built mip chain, everything else
 // (transforms, volume description, temperature / velocity grids) from `tmpl`, the grid description of a host-built volume
 // of the same dimensions (typically frame 0 of the sequence).  Only the brick-activity maps (1 byte per brick) visit the
 // host, where the tree over them is built; brick pools, quad repacks and brick bounds are produced on the device.
-int vrestir_set_volume_from_chain(vrestir_pass* p, const vrestir_mip_chain* chain, const vrestir_grid_desc* tmpl, int advance) {
+int vrestir_set_volume_from_chain(vrestir_pass* p, const vrestir_mip_chain* chain, const vrestir_grid_desc* tmpl, int advance) try {
     if (!p || !chain || !tmpl) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (vr::chainDevice(chain) != p->device) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "the chain lives on another device");
     if (advance && !p->haveVolume) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "advance before a volume was set");
@@ -952,15 +1009,15 @@ int vrestir_set_volume_from_chain(vrestir_pass* p, const vrestir_mip_chain* chai
     if (!advance) p->mOptionsChanged = true;
     applyOverrides(p);
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_set_camera(vrestir_pass* p, const vrestir_camera* cam) {
+int vrestir_set_camera(vrestir_pass* p, const vrestir_camera* cam) try {
     if (!p || !cam) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     p->cam = *cam; p->haveCamera = true;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_set_envmap(vrestir_pass* p, const vrestir_envmap_desc* env) {
+int vrestir_set_envmap(vrestir_pass* p, const vrestir_envmap_desc* env) try {
     if (!p || !env || !env->texels || env->width < 1 || env->height < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad env map");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
@@ -998,9 +1055,9 @@ int vrestir_set_envmap(vrestir_pass* p, const vrestir_envmap_desc* env) {
     s.envAliasThr = p->d_envAliasThr; s.envAliasRedirect = p->d_envAliasRedirect; s.envAliasCount = (unsigned)base.size();
     p->sceneDirty = true; p->mOptionsChanged = true;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_set_analytic_lights(vrestir_pass* p, const vrestir_light* lights, int count) {
+int vrestir_set_analytic_lights(vrestir_pass* p, const vrestir_light* lights, int count) try {
     if (!p || count < 0 || (count > 0 && !lights)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad lights");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
@@ -1010,9 +1067,9 @@ int vrestir_set_analytic_lights(vrestir_pass* p, const vrestir_light* lights, in
     p->scene.lights = (const vrestir_light*)p->d_lights; p->scene.lightCount = count;
     p->sceneDirty = true; p->mOptionsChanged = true;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_set_emissive_triangles(vrestir_pass* p, const vrestir_emissive_triangle* tris, int count, float mul) {
+int vrestir_set_emissive_triangles(vrestir_pass* p, const vrestir_emissive_triangle* tris, int count, float mul) try {
     if (!p || count < 0 || (count > 0 && !tris)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad triangles");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
@@ -1036,32 +1093,47 @@ int vrestir_set_emissive_triangles(vrestir_pass* p, const vrestir_emissive_trian
     s.aliasWeightSum = p->aliasWeightSum; s.emissiveMul = mul;
     p->sceneDirty = true; p->mOptionsChanged = true;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_get_emissive_alias(const vrestir_pass* p, uint32_t* items, float* weights, float* weight_sum) {
+int vrestir_get_emissive_alias(const vrestir_pass* p, uint32_t* items, float* weights, float* weight_sum) try {
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
     if (items && !p->aliasItems.empty()) memcpy(items, p->aliasItems.data(), p->aliasItems.size() * 4);
     if (weights && !p->aliasWeights.empty()) memcpy(weights, p->aliasWeights.data(), p->aliasWeights.size() * 4);
     if (weight_sum) *weight_sum = p->aliasWeightSum;
     return VRESTIR_OK;
-}
-int vrestir_get_env_alias(const vrestir_pass* p, float* thresholds, uint32_t* redirect, int* count) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_build_alias_table(const float* weights, int count, uint32_t* items4, float* weight_sum) try {
+    if (!weights || count < 1 || !items4) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
+    std::vector<uint32_t> items; float ws = 0.f;
+    buildAliasTable(std::vector<float>(weights, weights + count), items, ws);
+    memcpy(items4, items.data(), items.size() * 4);
+    if (weight_sum) *weight_sum = ws;
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+int vrestir_build_env_alias(const float* texel_weights, int count, float* thresholds, uint32_t* redirect) try {
+    if (!texel_weights || count < 1 || !thresholds || !redirect) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
+    std::vector<float> thr; std::vector<uint32_t> red;
+    buildEnvAlias(texel_weights, (uint32_t)count, thr, red);
+    memcpy(thresholds, thr.data(), thr.size() * 4); memcpy(redirect, red.data(), red.size() * 4);
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+int vrestir_get_env_alias(const vrestir_pass* p, float* thresholds, uint32_t* redirect, int* count) try {
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
     if (count) *count = (int)p->envAliasThr.size();
     if (thresholds && !p->envAliasThr.empty()) memcpy(thresholds, p->envAliasThr.data(), p->envAliasThr.size() * 4);
     if (redirect && !p->envAliasRedirect.empty()) memcpy(redirect, p->envAliasRedirect.data(), p->envAliasRedirect.size() * 4);
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_set_frame(vrestir_pass* p, int w, int h, int row_begin, int row_end) {
+int vrestir_set_frame(vrestir_pass* p, int w, int h, int row_begin, int row_end) try {
     if (!p || w <= 0 || h <= 0 || row_begin < 0 || row_end > h || row_begin >= row_end) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad frame / row band");
     if ((long long)w * h > (1ll << 30)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "frame too large");
     if (p->W != w || p->H != h) p->mOptionsChanged = true;
     p->W = w; p->H = h; p->rowBegin = row_begin; p->rowEnd = row_end;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_update(vrestir_pass* p, const char* key, double value) {
+int vrestir_update(vrestir_pass* p, const char* key, double value) try {
     if (!p || !key) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     std::string k(key);
     if (k.rfind("mParams.", 0) == 0) k = k.substr(8);
@@ -1093,40 +1165,40 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) {
     p->sceneDirty = true;
     if (!found) return setError(VRESTIR_WARN_UNKNOWN_KEY, std::string("Unknown field '") + key + "' in a VolumetricReSTIR dictionary");
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_set_params(vrestir_pass* p, const vrestir_params* params) {
+int vrestir_set_params(vrestir_pass* p, const vrestir_params* params) try {
     if (!p || !params) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     p->P = *params; p->mOptionsChanged = true; p->sceneDirty = true;
     return VRESTIR_OK;
-}
-int vrestir_get_params(const vrestir_pass* p, vrestir_params* out) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_get_params(const vrestir_pass* p, vrestir_params* out) try {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     *out = p->P; return VRESTIR_OK;
-}
-int vrestir_set_frame_count(vrestir_pass* p, int fc, int acc) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_set_frame_count(vrestir_pass* p, int fc, int acc) try {
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
     p->mFrameCount = fc; p->mTemporalSampleAccumulated = acc; p->mOptionsChanged = false; return VRESTIR_OK;
-}
-int vrestir_get_frame_count(const vrestir_pass* p, int* fc) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_get_frame_count(const vrestir_pass* p, int* fc) try {
     if (!p || !fc) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     *fc = p->mFrameCount; return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 /* previous-frame camera for staged parity tests of K2 (normally saved by stage 6) */
-int vrestir_set_prev_camera(vrestir_pass* p, const vrestir_camera* cam) {
+int vrestir_set_prev_camera(vrestir_pass* p, const vrestir_camera* cam) try {
     if (!p || !cam) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     DPrevCam& s = p->prevCam;
     memcpy(s.prevView, cam->viewMat, 64); memcpy(s.prevProj, cam->projMat, 64);
     s.prevU = make_float3(cam->cameraU[0], cam->cameraU[1], cam->cameraU[2]); s.prevV = make_float3(cam->cameraV[0], cam->cameraV[1], cam->cameraV[2]);
     s.prevW = make_float3(cam->cameraW[0], cam->cameraW[1], cam->cameraW[2]); s.prevPos = make_float3(cam->posW[0], cam->posW[1], cam->posW[2]);
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_execute_stage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, void* stream) {
+int vrestir_execute_stage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, void* stream) try {
     return runStage(p, stage, arg, out_color, out_mvec, (cudaStream_t)stream);
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* stream) {
+int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* stream) try {
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
@@ -1156,9 +1228,9 @@ int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* st
     if ((rc = runStage(p, 5, 0, out_color, out_mvec, st))) return rc;
     if ((rc = runStage(p, 6, 0, out_color, out_mvec, st))) return rc;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_execute_host(vrestir_pass* p, float* out_color_host, float* out_mvec_host) {
+int vrestir_execute_host(vrestir_pass* p, float* out_color_host, float* out_mvec_host) try {
     if (!p || !out_color_host) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set");
     CK(cudaSetDevice(p->device));
@@ -1179,9 +1251,9 @@ int vrestir_execute_host(vrestir_pass* p, float* out_color_host, float* out_mvec
     if (out_mvec_host) CK(cudaMemcpyAsync(out_mvec_host + off * 2, p->d_hostMvec + off, cnt * 8, cudaMemcpyDeviceToHost, p->hostStream));
     CK(cudaStreamSynchronize(p->hostStream));
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_get_timings(vrestir_pass* p, vrestir_timings* out) {
+int vrestir_get_timings(vrestir_pass* p, vrestir_timings* out) try {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     for (int i = 0; i <= 6; i++) if (!p->evValid[i]) return setError(VRESTIR_ERR_NOT_READY, "no completed frame");
     CK(cudaEventSynchronize(p->ev[6]));
@@ -1193,8 +1265,8 @@ int vrestir_get_timings(vrestir_pass* p, vrestir_timings* out) {
         CK(cudaEventElapsedTime(&out->total_ms, p->ev[7], p->ev[6]));
     }
     return VRESTIR_OK;
-}
-int vrestir_get_march_timings(vrestir_pass* p, vrestir_march_timings* out) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_get_march_timings(vrestir_pass* p, vrestir_march_timings* out) try {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (!p->evMarchValid) return setError(VRESTIR_ERR_NOT_READY, "no wavefront spatial round has run");
     CK(cudaSetDevice(p->device));
@@ -1206,8 +1278,8 @@ int vrestir_get_march_timings(vrestir_pass* p, vrestir_march_timings* out) {
     CK(cudaMemcpy(c, p->wfCounters + 8, 8, cudaMemcpyDeviceToHost));
     out->spatial_cam_tasks = c[0]; out->spatial_light_tasks = c[1];
     return VRESTIR_OK;
-}
-int vrestir_debug_read_bandwidth(int device, size_t bytes, int iters, float* gbs) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_debug_read_bandwidth(int device, size_t bytes, int iters, float* gbs) try {
     if (!gbs || bytes < 4096 || iters < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
     CK(cudaSetDevice(device));
     void* buf = nullptr; unsigned* sink = nullptr;
@@ -1224,18 +1296,18 @@ int vrestir_debug_read_bandwidth(int device, size_t bytes, int iters, float* gbs
     *gbs = (float)((double)(bytes / 16 * 16) * iters / (ms * 1e-3) / 1e9);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
     return VRESTIR_OK;
-}
-int vrestir_set_next_camera(vrestir_pass* p, const vrestir_camera* cam) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_set_next_camera(vrestir_pass* p, const vrestir_camera* cam) try {
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
     if (cam) { p->nextCam = *cam; p->haveNextCam = true; } else p->haveNextCam = false;
     return VRESTIR_OK;
-}
-int vrestir_wait_output(vrestir_pass* p, void* stream) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_wait_output(vrestir_pass* p, void* stream) try {
     if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
     if (p->outSeq) { CK(cudaSetDevice(p->device)); CK(cudaStreamWaitEvent((cudaStream_t)stream, p->evOutDone[(p->outSeq - 1) & 1], 0)); }
     return VRESTIR_OK;
-}
-int vrestir_get_pipeline_stats(vrestir_pass* p, vrestir_pipeline_stats* out) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_get_pipeline_stats(vrestir_pass* p, vrestir_pipeline_stats* out) try {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     memset(out, 0, sizeof(*out));
     out->adopted = p->pfAdopted; out->discarded = p->pfDiscarded;
@@ -1250,11 +1322,11 @@ int vrestir_get_pipeline_stats(vrestir_pass* p, vrestir_pipeline_stats* out) {
         CK(cudaEventElapsedTime(&out->deferred_final_ms, p->evOut0, p->evOut1));
     }
     return VRESTIR_OK;
-}
-int vrestir_get_launch_count(const vrestir_pass* p, uint64_t* out) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_get_launch_count(const vrestir_pass* p, uint64_t* out) try {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     *out = p->launches; return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 static int physOf(const vrestir_pass* p, int buffer) {
     switch (buffer) {
@@ -1263,7 +1335,7 @@ static int physOf(const vrestir_pass* p, int buffer) {
         default: return p->it;
     }
 }
-int vrestir_buffer_bytes(const vrestir_pass* p, int buffer, size_t* bytes) {
+int vrestir_buffer_bytes(const vrestir_pass* p, int buffer, size_t* bytes) try {
     if (!p || !bytes) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     const size_t n = N(p); const int B = p->P.mMaxBounces;
     switch (buffer) {
@@ -1274,8 +1346,8 @@ int vrestir_buffer_bytes(const vrestir_pass* p, int buffer, size_t* bytes) {
         default: return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad buffer id");
     }
     return VRESTIR_OK;
-}
-int vrestir_get_buffer(vrestir_pass* p, int buffer, void* dst, size_t bytes) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_get_buffer(vrestir_pass* p, int buffer, void* dst, size_t bytes) try {
     if (!p || (!dst && bytes)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     CK(cudaSetDevice(p->device));
     size_t need; int rc = vrestir_buffer_bytes(p, buffer, &need); if (rc) return rc;
@@ -1290,11 +1362,11 @@ int vrestir_get_buffer(vrestir_pass* p, int buffer, void* dst, size_t bytes) {
         cudaFree(tmp); CK(e);
     } else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) CK(cudaMemcpy(dst, p->ext[physOf(p, buffer)], bytes, cudaMemcpyDeviceToHost));
     else if (buffer == VRESTIR_BUF_FEATURES) CK(cudaMemcpy(dst, p->feat[p->featCur], bytes, cudaMemcpyDeviceToHost));
-    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) CK(cudaMemcpy(dst, p->feat[p->featPrev], bytes, cudaMemcpyDeviceToHost));
+    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) CK(cudaMemcpy(dst, p->feat[p->featSwapPending ? p->featCur : p->featPrev], bytes, cudaMemcpyDeviceToHost));
     else CK(cudaMemcpy(dst, p->d_importance, bytes, cudaMemcpyDeviceToHost));
     return VRESTIR_OK;
-}
-int vrestir_set_buffer(vrestir_pass* p, int buffer, const void* src, size_t bytes) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_set_buffer(vrestir_pass* p, int buffer, const void* src, size_t bytes) try {
     if (!p || (!src && bytes)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     CK(cudaSetDevice(p->device));
     size_t need; int rc = vrestir_buffer_bytes(p, buffer, &need); if (rc) return rc;
@@ -1310,11 +1382,15 @@ int vrestir_set_buffer(vrestir_pass* p, int buffer, const void* src, size_t byte
         cudaFree(tmp); CK(e);
     } else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) CK(cudaMemcpy(p->ext[physOf(p, buffer)], src, bytes, cudaMemcpyHostToDevice));
     else if (buffer == VRESTIR_BUF_FEATURES) CK(cudaMemcpy(p->feat[p->featCur], src, bytes, cudaMemcpyHostToDevice));
-    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) CK(cudaMemcpy(p->feat[p->featPrev], src, bytes, cudaMemcpyHostToDevice));
+    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) {
+        // while the swap is pending one buffer plays both roles: the history gets a buffer of its own before it is overwritten
+        p->featSwapPending = false;
+        CK(cudaMemcpy(p->feat[p->featPrev], src, bytes, cudaMemcpyHostToDevice));
+    }
     else CK(cudaMemcpy(p->d_importance, src, bytes, cudaMemcpyHostToDevice));
     return VRESTIR_OK;
-}
-int vrestir_device_buffer(vrestir_pass* p, int buffer, void** base, size_t* plane_stride_bytes, int* planes) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_device_buffer(vrestir_pass* p, int buffer, void** base, size_t* plane_stride_bytes, int* planes) try {
     if (!p || !base) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set");
     int rc = ensureBuffers(p); if (rc) return rc;
@@ -1322,17 +1398,17 @@ int vrestir_device_buffer(vrestir_pass* p, int buffer, void** base, size_t* plan
     if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) { *base = p->res[physOf(p, buffer)]; if (plane_stride_bytes) *plane_stride_bytes = n * 16; if (planes) *planes = 2; }
     else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) { *base = p->ext[physOf(p, buffer)]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
     else if (buffer == VRESTIR_BUF_FEATURES) { *base = p->feat[p->featCur]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
-    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) { *base = p->feat[p->featPrev]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
+    else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) { *base = p->feat[p->featSwapPending ? p->featCur : p->featPrev]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
     else return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad buffer id");
     return VRESTIR_OK;
-}
-int vrestir_spatial_input_buffer(const vrestir_pass* p, int round, int* buffer) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_spatial_input_buffer(const vrestir_pass* p, int round, int* buffer) try {
     if (!p || !buffer) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     *buffer = (round % 2 == 0) ? VRESTIR_BUF_RESERVOIR_0 : VRESTIR_BUF_RESERVOIR_1;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_debug_wavefront_counters(vrestir_pass* p, uint32_t out[16]) {
+int vrestir_debug_wavefront_counters(vrestir_pass* p, uint32_t out[16]) try {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     memset(out, 0, 64);
     if (!p->wfCounters) return VRESTIR_OK;
@@ -1348,8 +1424,8 @@ int vrestir_debug_wavefront_counters(vrestir_pass* p, uint32_t out[16]) {
         }
     }
     return VRESTIR_OK;
-}
-int vrestir_debug_long_rays(vrestir_pass* p, float* out64x8, uint32_t* count) {
+} catch (...) { return vr::caughtException(); }
+int vrestir_debug_long_rays(vrestir_pass* p, float* out64x8, uint32_t* count) try {
     if (!p || !out64x8 || !count) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
@@ -1357,6 +1433,6 @@ int vrestir_debug_long_rays(vrestir_pass* p, float* out64x8, uint32_t* count) {
     CK(readDebugRays(out64x8, &c));
     *count = c;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 }  // extern "C"

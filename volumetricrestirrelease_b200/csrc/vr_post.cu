@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/vrestir.h"
+#include "vr_host.h"
 
 namespace vr { int setError(int code, const std::string& msg); }
 using vr::setError;
@@ -123,7 +124,7 @@ void freeAccum(vrestir_accumulator* a) {
 
 extern "C" {
 
-int vrestir_accum_create(int device, int width, int height, vrestir_accumulator** out) {
+int vrestir_accum_create(int device, int width, int height, vrestir_accumulator** out) try {
     if (!out || width < 1 || height < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -133,18 +134,18 @@ int vrestir_accum_create(int device, int width, int height, vrestir_accumulator*
     a->device = device; a->W = width; a->H = height;
     *out = a;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_accum_destroy(vrestir_accumulator* a) {
+int vrestir_accum_destroy(vrestir_accumulator* a) try {
     if (!a) return VRESTIR_OK;
     cudaSetDevice(a->device);
     cudaDeviceSynchronize();
     freeAccum(a);
     delete a;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_accum_update(vrestir_accumulator* a, const char* key, double value) {
+int vrestir_accum_update(vrestir_accumulator* a, const char* key, double value) try {
     if (!a || !key) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     const std::string k(key);
     if (k == "enableAccumulation") a->enable = value != 0;
@@ -156,15 +157,15 @@ int vrestir_accum_update(vrestir_accumulator* a, const char* key, double value) 
         if (m != a->precision) { a->precision = m; a->frameCount = 0; }   // the sum buffers of the other mode hold nothing
     } else return setError(VRESTIR_WARN_UNKNOWN_KEY, "Unknown field '" + k + "' in an AccumulatePass dictionary");
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_accum_reset(vrestir_accumulator* a) {
+int vrestir_accum_reset(vrestir_accumulator* a) try {
     if (!a) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     a->frameCount = 0;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_accum_resize(vrestir_accumulator* a, int width, int height) {
+int vrestir_accum_resize(vrestir_accumulator* a, int width, int height) try {
     if (!a || width < 1 || height < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
     if (width != a->W || height != a->H) {   // AccumulatePass.cpp:120-126
         CKP(cudaSetDevice(a->device));
@@ -173,15 +174,15 @@ int vrestir_accum_resize(vrestir_accumulator* a, int width, int height) {
         a->W = width; a->H = height; a->frameCount = 0;
     }
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_accum_frame_count(const vrestir_accumulator* a, int* out) {
+int vrestir_accum_frame_count(const vrestir_accumulator* a, int* out) try {
     if (!a || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     *out = a->frameCount;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_accum_execute(vrestir_accumulator* a, const float* input, float* output, int row_begin, int row_end, void* stream) {
+int vrestir_accum_execute(vrestir_accumulator* a, const float* input, float* output, int row_begin, int row_end, void* stream) try {
     if (!a || !input || !output) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (row_begin < 0 || row_end > a->H || row_begin >= row_end) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad row band");
     cudaStream_t st = (cudaStream_t)stream;
@@ -208,7 +209,7 @@ int vrestir_accum_execute(vrestir_accumulator* a, const float* input, float* out
     else k_accum_double<<<blocks, threads, 0, st>>>(in4, out4, a->dsum, a->W, row_begin, rows, count);
     CKP(cudaGetLastError());
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 int vrestir_error_measure(int device, const float* source, const float* reference, const float* world_position, int width, int height,
                           int ignore_background, int compute_squared_difference, int compute_average, float* difference_out,

@@ -418,7 +418,7 @@ static int buildScene(const vrestir_scene_params* p, Dense&& density, Dense* tem
 
 extern "C" {
 
-int vrestir_scene_create(const vrestir_scene_params* p, vrestir_scene** out) {
+int vrestir_scene_create(const vrestir_scene_params* p, vrestir_scene** out) try {
     if (!p || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (p->dim[0] < 8 || p->dim[1] < 8 || p->dim[2] < 8 || p->dim[0] > 4096 || p->dim[1] > 4096 || p->dim[2] > 4096)
         return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "grid dimensions must be in [8, 4096]");
@@ -441,9 +441,9 @@ int vrestir_scene_create(const vrestir_scene_params* p, vrestir_scene** out) {
             }
     });
     return buildScene(p, std::move(d), wt ? &T : nullptr, wv ? &V : nullptr, out);
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_scene_create_from_dense(const vrestir_scene_params* p, const float* density, const float* temperature, const float* velocity_xyz, vrestir_scene** out) {
+int vrestir_scene_create_from_dense(const vrestir_scene_params* p, const float* density, const float* temperature, const float* velocity_xyz, vrestir_scene** out) try {
     if (!p || !density || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (p->dim[0] < 1 || p->dim[1] < 1 || p->dim[2] < 1 || p->dim[0] > 4096 || p->dim[1] > 4096 || p->dim[2] > 4096)
         return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "grid dimensions must be in [1, 4096]");
@@ -455,12 +455,12 @@ int vrestir_scene_create_from_dense(const vrestir_scene_params* p, const float* 
         for (size_t i = 0; i < d.n(); i++) for (int c = 0; c < 3; c++) V.v[(size_t)c * d.n() + i] = velocity_xyz[i * 3 + c];
     }
     return buildScene(p, std::move(d), temperature ? &T : nullptr, velocity_xyz ? &V : nullptr, out);
-}
+} catch (...) { return vr::caughtException(); }
 
 int vrestir_scene_destroy(vrestir_scene* s) { delete s; return VRESTIR_OK; }
 const vrestir_grid_desc* vrestir_scene_grid(const vrestir_scene* s) { return s ? &s->desc : nullptr; }
 
-int vrestir_scene_dense_mip(const vrestir_scene* s, int mip, int conservative, float* out, int32_t out_dim[3]) {
+int vrestir_scene_dense_mip(const vrestir_scene* s, int mip, int conservative, float* out, int32_t out_dim[3]) try {
     if (!s || mip < 0 || mip >= VRESTIR_NUM_MAX_MIPS) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad mip");
     const int slot = mip + (conservative ? VRESTIR_NUM_MAX_MIPS : 0);
     const vrestir_grid_slot& g = s->desc.slots[slot];
@@ -482,18 +482,18 @@ int vrestir_scene_dense_mip(const vrestir_scene* s, int mip, int conservative, f
         }
     }
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_scene_stats(const vrestir_scene* s, int slot, uint32_t* bricks, uint64_t* atlas_bytes) {
+int vrestir_scene_stats(const vrestir_scene* s, int slot, uint32_t* bricks, uint64_t* atlas_bytes) try {
     if (!s || slot < 0 || slot >= VRESTIR_MAX_SLOTS) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad slot");
     const vrestir_grid_slot& g = s->desc.slots[slot];
     if (bricks) *bricks = g.valid ? g.brick_count : 0;
     if (atlas_bytes) *atlas_bytes = g.valid ? (uint64_t)s->slots[slot].atlas.size() : 0;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 // F/Scene/Camera/Camera.cpp:150-189 (focalDistance = 10000 as in CameraData.slang:60; view = lookAt RH, proj = perspective RH)
-int vrestir_camera_look_at(const float pos[3], const float target[3], const float up[3], float fovY, float aspect, float nearZ, float farZ, vrestir_camera* out) {
+int vrestir_camera_look_at(const float pos[3], const float target[3], const float up[3], float fovY, float aspect, float nearZ, float farZ, vrestir_camera* out) try {
     if (!pos || !target || !up || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     auto sub = [](const float* a, const float* b, float* o) { for (int i = 0; i < 3; i++) o[i] = a[i] - b[i]; };
     auto nrm = [](float* a) { float l = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); for (int i = 0; i < 3; i++) a[i] /= l; };
@@ -516,9 +516,9 @@ int vrestir_camera_look_at(const float pos[3], const float target[3], const floa
     P[0] = 1.f / (aspect * th); P[5] = 1.f / th; P[10] = farZ / (nearZ - farZ); P[11] = -1.f; P[14] = -(farZ * nearZ) / (farZ - nearZ);
     out->nearZ = nearZ; out->farZ = farZ;
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_make_sky_envmap(int width, int height, uint32_t seed, float* out) {
+int vrestir_make_sky_envmap(int width, int height, uint32_t seed, float* out) try {
     if (width < 2 || height < 2 || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad env map size");
     const float sunDir[3] = {0.45f, 0.62f, -0.64f};
     parallelFor(height, [&](int y) {
@@ -541,9 +541,9 @@ int vrestir_make_sky_envmap(int width, int height, uint32_t seed, float* out) {
         }
     });
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_make_emissive_shell(int count, uint32_t seed, const float center[3], float radius, vrestir_emissive_triangle* out) {
+int vrestir_make_emissive_shell(int count, uint32_t seed, const float center[3], float radius, vrestir_emissive_triangle* out) try {
     if (count < 0 || !out || !center) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad arguments");
     for (int i = 0; i < count; i++) {
         auto rnd = [&](int k) { return lattice(i, k, 17, seed); };
@@ -576,11 +576,11 @@ int vrestir_make_emissive_shell(int count, uint32_t seed, const float center[3],
         T.Le[0] = power * (0.6f + 0.4f * hue); T.Le[1] = power * (0.6f + 0.4f * (1.f - std::fabs(2.f * hue - 1.f))); T.Le[2] = power * (1.f - 0.4f * hue);
     }
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 // Planck-law spectrum -> linear sRGB via Gaussian fits of the CIE 1931 colour-matching functions (Wyman et al. 2013),
 // normalised so that the hottest entry has max component 1; 128 entries for T = 50 K .. 6400 K (50 K steps).
-int vrestir_make_blackbody_lut(float* out) {
+int vrestir_make_blackbody_lut(float* out) try {
     if (!out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     auto g = [](double x, double mu, double s1, double s2) { double t = (x - mu) / (x < mu ? s1 : s2); return std::exp(-0.5 * t * t); };
     double rgb[128][3]; double mx = 0;
@@ -602,7 +602,7 @@ int vrestir_make_blackbody_lut(float* out) {
     }
     for (int i = 0; i < 128; i++) { for (int c = 0; c < 3; c++) out[i * 4 + c] = (float)(rgb[i][c] / mx); out[i * 4 + 3] = 0.f; }
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 }  // extern "C"
 
@@ -740,12 +740,18 @@ int saveSlotVbx(const vrestir_grid_slot& g, int channel, const std::string& path
 struct LoadedVbx {
     BuiltSlot built; vrestir_grid_slot g{};
     std::vector<float> voxels;   // [brick][10*10*10] floats
+    int32_t effMin[3] = {0, 0, 0}, effMax[3] = {0, 0, 0};   // mEffectiveVoxMin / mEffectiveVoxMax of the 1.12 header
 };
 
 int loadSlotVbx(const std::string& path, LoadedVbx& L) {
     File fp; fp.f = fopen(path.c_str(), "rb");
     if (!fp.f) return VRESTIR_ERR_NOT_READY;   // caller decides whether the file is optional
     auto bad = [&](const char* why) { return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, path + ": " + why); };
+    // every size below is checked against the file size before it reaches an allocation: a malformed file must come back
+    // as VRESTIR_ERR_INVALID_ARGUMENT, never as a bad_alloc / length_error unwinding through the C ABI
+    if (fseek(fp.f, 0, SEEK_END) != 0) return bad("cannot seek");
+    const int64_t fileSize = (int64_t)ftell(fp.f);
+    if (fileSize < 0 || fseek(fp.f, 0, SEEK_SET) != 0) return bad("cannot seek");
     uint8_t major = 0, minor = 0;
     if (!fp.rd(&major) || !fp.rd(&minor)) return bad("truncated header");
     float xf[16], ixf[16]; int32_t vmin[3] = {0, 0, 0}, vmax[3] = {0, 0, 0}; float valMin = 0.f, valMax = 1.f;
@@ -754,9 +760,10 @@ int loadSlotVbx(const std::string& path, LoadedVbx& L) {
     if (minor == 12) { if (!fp.rd(xf, 16) || !fp.rd(ixf, 16) || !fp.rd(vmin, 3) || !fp.rd(vmax, 3) || !fp.rd(&valMin) || !fp.rd(&valMax)) return bad("truncated 1.12 block"); haveX = true; }
     if (!haveX) return bad("only the reference's version 1.12 files (with xform / effective bounds) are supported");
     int32_t numGrids = 0; if (!fp.rd(&numGrids) || numGrids < 1) return bad("no grids");
+    if ((int64_t)numGrids * 8 > fileSize) return bad("grid count exceeds the file size");
     if (major >= 2) { uint8_t masks; fp.rd(&masks); if (masks) return bad("bitmask topologies are not supported"); }
     std::vector<uint64_t> offs(numGrids); if (!fp.rd(offs.data(), offs.size())) return bad("truncated grid table");
-    if (fseek(fp.f, (long)offs[0], SEEK_SET) != 0) return bad("bad grid offset");
+    if (offs[0] >= (uint64_t)fileSize || fseek(fp.f, (long)offs[0], SEEK_SET) != 0) return bad("bad grid offset");
     char name[256]; uint8_t dtype, comps, compress, topo, layout; float vs[3];
     int32_t leafcnt, leafdim[3], apron, numChan, reuse, axiscnt[3], axisres[3]; uint64_t atlasSz;
     if (!fp.rd(name, 256) || !fp.rd(&dtype) || !fp.rd(&comps) || !fp.rd(&compress) || !fp.rd(vs, 3) || !fp.rd(&leafcnt) || !fp.rd(leafdim, 3) || !fp.rd(&apron) ||
@@ -771,6 +778,15 @@ int loadSlotVbx(const std::string& path, LoadedVbx& L) {
     static const int wantLd[3] = {3, 4, 5};
     for (int n = 0; n < levels; n++) if (ld[n] != wantLd[n] || res[n] != (1 << ld[n]) || w0[n] != 64) return bad("tree configuration is not <3,4,5> with 64-byte nodes");
     if (cnt0[0] != leafcnt) return bad("atlas does not hold every brick");
+    if (leafcnt < 0) return bad("negative brick count");
+    for (int n = 0; n < levels; n++) {
+        if (cnt0[n] < 0 || cnt1[n] < 0 || w1[n] < 0) return bad("negative pool count");
+        if ((int64_t)cnt0[n] * 64 > fileSize || (int64_t)cnt1[n] * (int64_t)w1[n] > fileSize) return bad("pool larger than the file");
+        if (range[n][0] <= 0 || range[n][0] != range[n][1] || range[n][0] != range[n][2]) return bad("non-cubic node range");
+    }
+    if (cnt0[levels - 1] != 1) return bad("the top level must hold exactly one node");
+    for (int a = 0; a < 3; a++) if (axisres[a] < 0 || axisres[a] > (1 << 20)) return bad("bad atlas resolution");
+    if ((double)axisres[0] * (double)axisres[1] * (double)axisres[2] * 4.0 > (double)fileSize) return bad("atlas larger than the file");
     vrestir_grid_slot& g = L.g; g = vrestir_grid_slot{};
     BuiltSlot& B = L.built;
     std::vector<VbxNode> raw[3];
@@ -782,7 +798,12 @@ int loadSlotVbx(const std::string& path, LoadedVbx& L) {
         std::vector<uint64_t> rows((size_t)cnt1[n] * r3);
         if (!rows.empty() && !fp.rd(rows.data(), rows.size())) return bad("truncated child lists");
         B.child[n].resize(rows.size());
-        for (size_t i = 0; i < rows.size(); i++) B.child[n][i] = (uint32_t)(((rows[i] >> 32) & 0xFFFFull) << 16) | (uint32_t)((rows[i] >> 16) & 0xFFFFull);   // F/Scene/Scene.cpp:3037
+        for (size_t i = 0; i < rows.size(); i++) {
+            const uint32_t c = (uint32_t)(((rows[i] >> 32) & 0xFFFFull) << 16) | (uint32_t)((rows[i] >> 16) & 0xFFFFull);   // F/Scene/Scene.cpp:3037
+            // the traversal dereferences child ids unchecked: an id must be "no child" or a node of the level below
+            if (c != 0xFFFFFFFFu && c >= (uint32_t)cnt0[n - 1]) return bad("child id out of range");
+            B.child[n][i] = c;
+        }
     }
     int32_t chanType, chanStride;
     if (!fp.rd(&chanType) || !fp.rd(&chanStride) || chanStride != 4) return bad("atlas channel is not 4-byte float");
@@ -799,7 +820,10 @@ int loadSlotVbx(const std::string& path, LoadedVbx& L) {
             for (int k = 0; k < 3; k++) o.pos[k] = s.pos[k];
             o.bounds[0] = o.bounds[1] = o.bounds[2] = o.bounds[3] = 0.f;
             if (n == 0) o.link = (uint32_t)i;   // brick pool order = leaf order
-            else o.link = (uint32_t)(((s.childList >> 32) & 0xFFFFull) << 16) | (uint32_t)((s.childList >> 16) & 0xFFFFull);
+            else {
+                o.link = (uint32_t)(((s.childList >> 32) & 0xFFFFull) << 16) | (uint32_t)((s.childList >> 16) & 0xFFFFull);
+                if (o.link != 0xFFFFFFFFu && o.link >= (uint32_t)cnt1[n]) return bad("child-list id out of range");
+            }
         }
     }
     if (levels == 2) { g.dim[2] = 5; g.res[2] = 32; g.vdel[2] = 128.f; g.noderange[2] = 4096; }
@@ -812,7 +836,7 @@ int loadSlotVbx(const std::string& path, LoadedVbx& L) {
             L.voxels[(size_t)b * VRESTIR_BRICK_VOXELS + (size_t)((z + 1) * 10 + (y + 1)) * 10 + (x + 1)] = atlas[((size_t)az * axisres[1] + ay) * axisres[0] + ax];
         }
     }
-    for (int i = 0; i < 3; i++) { g.bmin[i] = (float)vmin[i]; g.bmax[i] = (float)vmax[i]; }
+    for (int i = 0; i < 3; i++) { g.bmin[i] = (float)vmin[i]; g.bmax[i] = (float)vmax[i]; L.effMin[i] = vmin[i]; L.effMax[i] = vmax[i]; }
     memcpy(g.xform, xf, 64); memcpy(g.invxform, ixf, 64);
     g.max_value = valMax; g.brick_count = (uint32_t)leafcnt;
     return VRESTIR_OK;
@@ -838,15 +862,17 @@ void finishLoadedSlot(LoadedVbx& L, int format, bool conservative, int channels,
                     B.atlas[idx] = (uint8_t)q;
                 } else memcpy(&B.atlas[idx * 4], &v, 4);
             }
+        // F/Scene/Scene.cpp:2981-3012: (min, max, avg) of the RAW float densities of the 10^3 block (x outermost), voxels outside
+        // the effective bounds count as 0, avg = sum / 512.  (The quantised values the kernels sample can exceed this max by
+        // half a UNORM8 step, exactly as the reference's BC4 texels can; the residual-ratio trackers stay unbiased.)
         float mn = 3.402823466e+38f, mx = 0.f, sum = 0.f;
-        const size_t base = (size_t)b * channels * VRESTIR_BRICK_VOXELS;
+        vrestir_node& n = B.nodes[0][b];
         for (int i = -1; i <= 8; i++) for (int j = -1; j <= 8; j++) for (int k = -1; k <= 8; k++) {
-            const size_t idx = base + (size_t)((k + 1) * 10 + (j + 1)) * 10 + (i + 1);
-            float d;
-            if (format == VRESTIR_ATLAS_UNORM8) d = (float)B.atlas[idx] * 0.003921568859368563f * maxv; else memcpy(&d, &B.atlas[idx * 4], 4);
+            float d = L.voxels[(size_t)b * VRESTIR_BRICK_VOXELS + (size_t)((k + 1) * 10 + (j + 1)) * 10 + (i + 1)];
+            if (n.pos[0] + i < L.effMin[0] || n.pos[0] + i > L.effMax[0] - 1 || n.pos[1] + j < L.effMin[1] || n.pos[1] + j > L.effMax[1] - 1 ||
+                n.pos[2] + k < L.effMin[2] || n.pos[2] + k > L.effMax[2] - 1) d = 0.f;
             mn = std::min(mn, d); mx = std::max(mx, d); sum += d;
         }
-        vrestir_node& n = B.nodes[0][b];
         n.bounds[0] = mn; n.bounds[1] = mx; n.bounds[2] = sum / 512.f; n.bounds[3] = 0.f;
     }
     for (int l = 0; l < 3; l++) {
@@ -874,7 +900,7 @@ void externalTransforms(vrestir_scene& s, int slot) {   // VR/VolumeBase.slang:1
 
 extern "C" {
 
-int vrestir_scene_save_vbx(const vrestir_scene* s, const char* dir_and_prefix) {
+int vrestir_scene_save_vbx(const vrestir_scene* s, const char* dir_and_prefix) try {
     if (!s || !dir_and_prefix) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     const std::string base(dir_and_prefix);
     for (int m = 0; m < VRESTIR_NUM_MAX_MIPS; m++)
@@ -889,9 +915,9 @@ int vrestir_scene_save_vbx(const vrestir_scene* s, const char* dir_and_prefix) {
     const vrestir_grid_slot& V = s->desc.slots[VRESTIR_VELOCITY_GRID_ID];
     if (V.valid) for (int c = 0; c < 3; c++) { int rc = saveSlotVbx(V, c, base + "_velocity_" + "xyz"[c] + ".vbx"); if (rc) return rc; }
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
-int vrestir_scene_load_vbx(const char* dir_and_prefix, int num_mips, const vrestir_scene_params* p, vrestir_scene** out) {
+int vrestir_scene_load_vbx(const char* dir_and_prefix, int num_mips, const vrestir_scene_params* p, vrestir_scene** out) try {
     if (!dir_and_prefix || !p || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     const std::string base(dir_and_prefix);
     std::unique_ptr<vrestir_scene> s(new vrestir_scene());
@@ -972,6 +998,6 @@ int vrestir_scene_load_vbx(const char* dir_and_prefix, int num_mips, const vrest
     s->params.num_mips = built;
     *out = s.release();
     return VRESTIR_OK;
-}
+} catch (...) { return vr::caughtException(); }
 
 }  // extern "C"
