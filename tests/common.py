@@ -142,7 +142,10 @@ def staged(params, scene, w, h, frames=2, want_mvec=False, dict_=None, camera_pa
     for f in range(frames):
         last = f == frames - 1
         if camera_path is not None:
-            scene.camera.position = tuple(camera_path[f])
+            if len(camera_path[f]) == 2:      # (position, target): a pan shifts the whole image
+                scene.camera.position, scene.camera.target = tuple(camera_path[f][0]), tuple(camera_path[f][1])
+            else:
+                scene.camera.position = tuple(camera_path[f])
             gp.updateCamera(); op.updateCamera()
         for stage, arg in [(0, 0), (1, 0), (2, 0)] + [(3, r) for r in range(rounds)] + [(4, 0), (5, 0), (6, 0)]:
             gp.execute_stage(stage, arg, color_g.data_ptr(), mvec_g.data_ptr())

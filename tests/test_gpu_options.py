@@ -1,0 +1,199 @@
+"""GPU-vs-oracle parity over the option surface the round-1 tests never touched ("What's weak" 3): every case runs
+two frames stage by stage (tests/common.staged) so that K1, K2, K3 and K5 are each compared on identical inputs; the camera
+moves between the frames where the option concerns reprojection.  North-star bounds: flips <= 0.1 % of pixels unless a case
+states otherwise, reservoir weights and radiance within 1e-4 relative on the non-flipped pixels."""
+import numpy as np
+import pytest
+
+from common import (FEAT, FLIP_BUDGET, RADIANCE_RTOL, capi, check_staged, compare_reservoirs, env_scene, gpu_frame, make_pair,
+                    rel_err_image, staged)
+from volumetricrestirrelease_b200 import VolumetricReSTIRParams
+
+pytestmark = pytest.mark.gpu
+
+W, H = 112, 72
+
+
+def _scene(**kw):
+    kw.setdefault("dim", (64, 64, 56))
+    kw.setdefault("density_scale", 0.15)
+    return env_scene(**kw)
+
+
+def _path(sc, step=(0.7, 0.2, -0.3), scale=20.0, frames=2, pan=False):
+    p0, t0 = np.array(sc.camera.position), np.array(sc.camera.target)
+    if pan:   # camera and target move together: every pixel shifts by several pixels per frame
+        return [(tuple(p0 + np.array(step) * scale * f), tuple(t0 + np.array(step) * scale * f)) for f in range(frames)]
+    return [tuple(p0 + np.array(step) * scale * f) for f in range(frames)]
+
+
+CASES = {
+    # Henyey-Greenstein: phase evaluation in every p-hat (B = 1) and the anisotropic branch of Sample_p (B = 2)
+    "g_forward": (dict(), dict(g=0.6), 1),
+    "g_backward": (dict(), dict(g=-0.3), 1),
+    "g_forward_two_bounces": (dict(mMaxBounces=2), dict(g=0.6), 5),
+    "g_backward_three_bounces": (dict(mMaxBounces=3), dict(g=-0.3), 5),
+    # trilinear distance sampling (regula falsi, VR/VolumeTrackingAdapterGVDB.slang:287-361), vertex-centred traversal
+    "initial_linear_sampler": (dict(mInitialVisibilityUseLinearSampler=1), dict(), 2),
+    "initial_linear_sampler_two_bounces": (dict(mInitialVisibilityUseLinearSampler=1, mMaxBounces=2), dict(), 5),
+    "hammersley": (dict(mRandomSamplerType=capi.kHammersley), dict(), 1),
+    "temporal_no_mis": (dict(mTemporalMISMethod=capi.kMISNone), dict(), 1),
+    "spatial_no_mis": (dict(mSpatialMISMethod=capi.kMISNone), dict(), 1),
+    "no_mis_at_all": (dict(mTemporalMISMethod=capi.kMISNone, mSpatialMISMethod=capi.kMISNone), dict(), 1),
+    "two_rounds_three_taps": (dict(mSpatialReuseRounds=2, mSpatialSampleCount=3), dict(), 1),
+    "six_taps_radius_20": (dict(mSpatialSampleCount=6, mSampleRadius=20.0), dict(), 1),
+    "spatial_ratio_tracking": (dict(mSpatialVisibilityTrackingMethod=capi.kRatioTracking, mSpatialLightingTrackingMethod=capi.kRatioTracking), dict(), 5),
+    "spatial_residual_ratio": (dict(mSpatialVisibilityTrackingMethod=capi.kResidualRatioTracking,
+                                    mSpatialLightingTrackingMethod=capi.kResidualRatioTracking), dict(), 5),
+    "spatial_analytic": (dict(mSpatialVisibilityTrackingMethod=capi.kAnalyticTracking, mSpatialLightingTrackingMethod=capi.kAnalyticTracking), dict(), 1),
+    "spatial_point_sampler": (dict(mSpatialVisibilityUseLinearSampler=0, mSpatialLightingUseLinearSampler=0), dict(), 1),
+    "spatial_step_scales": (dict(mSpatialVisibilityTStepScale=0.5, mSpatialLightingTStepScale=3.0, mSpatialLightingMipLevel=2), dict(), 1),
+    "base_mip_0": (dict(mInitialBaseMipLevel=0), dict(), 1),
+    "base_mip_2": (dict(mInitialBaseMipLevel=2), dict(), 1),
+    "initial_lighting_mip_0_analytic": (dict(mInitialLightingMipLevel=0, mInitialLightingTrackingMethod=capi.kAnalyticTracking), dict(), 1),
+    "initial_residual_ratio_two_light_samples": (dict(mInitialLightingTrackingMethod=capi.kResidualRatioTracking, mInitialLightSamples=2), dict(), 5),
+    "initial_no_light_visibility": (dict(mInitialLightSamples=0), dict(), 1),
+    "initial_m_1": (dict(mInitialM=1), dict(), 1),
+    "initial_m_7": (dict(mInitialM=7), dict(), 1),       # two candidate rounds of the distance sampler (4 + 3)
+    "final_ratio_two_samples": (dict(mFinalVisibilityTrackingMethod=capi.kRatioTracking, mFinalLightTrackingMethod=capi.kRatioTracking,
+                                     mFinalLightSamples=2, mFinalVisibilitySamples=2), dict(), 5),
+    "m_threshold_1": (dict(mTemporalReuseMThreshold=1.0), dict(), 1),
+    "no_russian_roulette_four_bounces": (dict(mMaxBounces=4, mInitialUseRussianRoulette=0, mInitialUseCoarserGridForIndirectBounce=0), dict(), 5),
+    "temporal_only": (dict(mEnableSpatialReuse=0), dict(), 1),
+    "spatial_only": (dict(mEnableTemporalReuse=0), dict(), 1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_option_staged(name):
+    kw, scene_kw, budget = CASES[name]
+    sc = _scene(**scene_kw)
+    out = staged(VolumetricReSTIRParams(**kw), sc, W, H, frames=2, camera_path=_path(sc))
+    check_staged(out, W, H, name, budget=budget * FLIP_BUDGET)
+
+
+@pytest.mark.parametrize("mode", [capi.kReprojectionLinear, capi.kReprojectionNone, capi.kReprojectionNoBackground])
+def test_reprojection_modes_moving_camera(mode):
+    """mTemporalReprojectionMode 0 / 1 / 2 with a camera that moves several pixels per frame, three frames; motion vectors too.
+    The framing leaves background pixels around the cloud, so mode 0's density-resampled reprojection depth (K2 background
+    path) and mode 2's skip of it both run."""
+    sc = _scene(distance=1.4)
+    out = staged(VolumetricReSTIRParams(mTemporalReprojectionMode=mode), sc, W, H, frames=3, want_mvec=True,
+                 camera_path=_path(sc, scale=6.0, frames=3, pan=True))
+    check_staged(out, W, H, f"reprojection mode {mode}")
+    g, c = out["mvec"]
+    assert (np.abs(g - c) > 1e-6).mean() <= FLIP_BUDGET
+    if mode != capi.kReprojectionNone:
+        assert (np.abs(c) > 0).mean() > 0.05, "the camera motion produced no motion vectors"
+
+
+def test_point_light_vs_oracle():
+    """Analytic point light (Li = I / d^2, Dirac pdf treated as 1) next to the env map, full reuse."""
+    sc = _scene()
+    lo, hi = sc.volume_bounds_world()
+    sc.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
+    out = staged(VolumetricReSTIRParams(mUseAnalyticLights=1), sc, W, H, frames=2, camera_path=_path(sc))
+    check_staged(out, W, H, "point light")
+    out = staged(VolumetricReSTIRParams(mUseAnalyticLights=1, mUseEnvironmentLights=0), sc, W, H, frames=2)
+    check_staged(out, W, H, "point light only")
+
+
+def test_env_alias_sampler_staged_and_unbiased():
+    """mEnvSamplerType = alias (north-star extension): staged parity, and the converged image agrees with the hierarchical
+    sampler's (both estimate the same integral: relMSE of the 64-frame means <= 2e-2, mean ratio within 2 %)."""
+    import torch
+    from common import rel_mse
+    sc = _scene()
+    out = staged(VolumetricReSTIRParams(), sc, W, H, frames=2, dict_={"mEnvSamplerType": 1}, camera_path=_path(sc))
+    check_staged(out, W, H, "env alias sampler")
+    means = []
+    for sampler in (0, 1):
+        gp, _ = make_pair(sc, VolumetricReSTIRParams(), W, H, {"mEnvSamplerType": sampler})
+        color = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        acc = torch.zeros_like(color)
+        for _ in range(64):
+            gp.execute(color.data_ptr())
+            acc += color
+        means.append((acc / 64).cpu().numpy())
+    r = rel_mse(means[1], means[0])
+    ratio = means[1][..., :3].mean() / means[0][..., :3].mean()
+    print(f"[env alias vs hierarchical, 64 frames] relMSE {r:.3e}, mean ratio {ratio:.4f}")
+    assert r <= 2e-2 and abs(ratio - 1) < 0.02
+
+
+def test_emissive_triangles_with_independent_alias_table():
+    """Emissive-triangle sampling where the ORACLE side uses the alias table rebuilt by the numpy restatement of AliasTable.cpp
+    (oracle/alias_oracle.py), not the product's: nothing the product computed reaches the oracle."""
+    sc = _scene()
+    lo, hi = sc.volume_bounds_world()
+    sc.addEmissiveShell(700, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
+    for B, budget in ((1, 1), (2, 5)):
+        p = VolumetricReSTIRParams(mUseEmissiveLights=1, mMaxBounces=B)
+        out = staged(p, sc, W, H, frames=2, own_tables=True, camera_path=_path(sc))
+        check_staged(out, W, H, f"emissive own tables B={B}", budget=budget * FLIP_BUDGET)
+    p = VolumetricReSTIRParams(mUseEmissiveLights=1, mUseEnvironmentLights=0)
+    out = staged(p, sc, W, H, frames=2, own_tables=True)
+    check_staged(out, W, H, "emissive only")
+
+
+def test_visualize_transmittance_and_freeze_frame():
+    """mVisualizeTotalTransmittance (K5 shows the K0 feature, gamma 2.2) and mFreezeFrame (K0-K4 skipped, K5 re-shades the kept
+    reservoirs with the previous frame's seed) against the oracle, through the whole-frame call."""
+    sc = _scene(distance=1.3)
+    gp, op = make_pair(sc, VolumetricReSTIRParams(mVisualizeTotalTransmittance=1), W, H)
+    for f in range(3):
+        if f == 2:
+            gp.updateDict({"mFreezeFrame": 1}); op.updateDict({"mFreezeFrame": 1})
+            # updateDict resets the frame counter like the reference; the frozen frame keeps showing the last features
+        g, c = gpu_frame(gp, W, H), op.execute()
+        np.testing.assert_allclose(g[..., :3], c[..., :3], rtol=3e-5, atol=1e-7)
+        assert 0.05 < (c[..., 0] < 0.999).mean() < 0.95
+    gp, op = make_pair(sc, VolumetricReSTIRParams(), W, H)
+    for f in range(4):
+        if f == 2:
+            gp.updateDict({"mFreezeFrame": 1}); op.updateDict({"mFreezeFrame": 1})
+            gp.set_frame_count(2, 1); op.set_frame_count(2, 1)       # keep history and counter across the option change
+        if f == 3:
+            gp.updateDict({"mFreezeFrame": 0}); op.updateDict({"mFreezeFrame": 0})
+            gp.set_frame_count(2, 1); op.set_frame_count(2, 1)
+        for b in (capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL):
+            gp.set_buffer(b, op.get_buffer(b))
+        g, c = gpu_frame(gp, W, H), op.execute()
+        e = rel_err_image(g, c)
+        print(f"[freeze frame test, frame {f}] frac > 1e-4: {(e > RADIANCE_RTOL).mean():.2e}")
+        assert (e > RADIANCE_RTOL).mean() <= 5e-3, f
+        fg = gp.get_buffer(capi.BUF_FEATURES).view(FEAT)["transmittance"]
+        fc = op.get_buffer(capi.BUF_FEATURES).view(FEAT)["transmittance"]
+        np.testing.assert_allclose(fg, fc, rtol=2e-5, atol=1e-7)       # BUF_FEATURES is the frame's own feature buffer, also when frozen
+
+
+def test_two_passes_on_one_device_interleaved():
+    """Two passes with different scenes and options share the device's constant banks: interleaving their frames (with frame
+    pipelining on, so each has a prefetched K0/K1 and a deferred K5 in flight when the other uploads) must give the frames each
+    renders alone."""
+    import torch
+    from volumetricrestirrelease_b200 import VolumetricReSTIR
+    scA, scB = _scene(), _scene(dim=(72, 48, 64), density_scale=0.3, seed=5)
+    pA, pB = VolumetricReSTIRParams(), VolumetricReSTIRParams(mSpatialSampleCount=3, mInitialM=2)
+
+    def run(pairs, order):
+        passes = []
+        for sc, p in pairs:
+            gp = VolumetricReSTIR.create({"mParams": p, "mPipelineFrames": 2})
+            gp.setScene(sc, W, H)
+            passes.append(gp)
+        cols = [torch.zeros((H, W, 4), dtype=torch.float32, device="cuda") for _ in passes]
+        imgs = [[] for _ in passes]
+        for k in order:
+            passes[k].execute(cols[k].data_ptr())
+            passes[k].wait_output()
+            imgs[k].append(cols[k].cpu().numpy().copy())
+        torch.cuda.synchronize()
+        return imgs
+
+    alone_a = run([(scA, pA)], [0] * 4)[0]
+    alone_b = run([(scB, pB)], [0] * 4)[0]
+    both = run([(scA, pA), (scB, pB)], [0, 1, 0, 1, 1, 0, 0, 1])
+    for f in range(4):
+        assert np.array_equal(both[0][f].view(np.uint32), alone_a[f].view(np.uint32)), f"pass A frame {f}"
+        assert np.array_equal(both[1][f].view(np.uint32), alone_b[f].view(np.uint32)), f"pass B frame {f}"

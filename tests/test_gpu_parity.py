@@ -159,10 +159,11 @@ def test_three_level_tree_full_reuse():
     _check_staged(out, w, h, "three-level tree")
 
 
-def _frames_buffers(params, scene, w, h, wavefront, frames=3):
+def _frames_buffers(params, scene, w, h, wavefront, frames=3, extra=None):
     """Run `frames` frames through the public execute() and return (image, final reservoirs) of the last one."""
     import torch
     d = {"mParams": params, "mUseWavefront": int(wavefront is not False), "mMarchPairEngine": int(wavefront == "pair")}
+    d.update(extra or {})
     if wavefront == 0:
         d["mInitialMode"] = 0
     gp = VolumetricReSTIR.create(d)
@@ -199,6 +200,67 @@ def test_wavefront_equals_per_pixel(variant):
         assert np.array_equal(res_w.view(np.uint32), res_s.view(np.uint32)), f"wavefront reservoirs (mode {mode}) differ from the per-pixel kernels"
         assert np.array_equal(img_w.view(np.uint32), img_s.view(np.uint32))
     assert (img_w[..., :3].sum(-1) > 0).mean() > 0.05
+
+
+@pytest.mark.parametrize("variant", ["two_bounces", "four_bounces", "three_bounces_emissive_point_light", "four_bounces_no_mis_two_rounds",
+                                     "final_ray_marching", "final_mixed_two_bounces", "spatial_analytic_two_bounces", "three_level_three_bounces"])
+def test_generic_task_streams_equal_per_pixel(variant):
+    """The generic task-stream path (the stage bodies run as an emit pass and a consume pass around the march engine: multi-bounce
+    option sets, ray-marched / mixed final shading, analytic spatial tracking) must be BIT-identical to the per-pixel kernels,
+    also when the stages run in several row chunks (small scratch budget).  Result blocks start as NaN (mDebugPoisonResults), so a
+    march the emit pass failed to foresee would surface in the image."""
+    w, h = 160, 96
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.15)
+    kw = {}
+    if variant == "two_bounces":
+        kw = dict(mMaxBounces=2)
+    elif variant == "four_bounces":
+        kw = dict(mMaxBounces=4)
+    elif variant == "three_bounces_emissive_point_light":
+        lo, hi = sc.volume_bounds_world()
+        sc.addEmissiveShell(400, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
+        sc.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
+        kw = dict(mMaxBounces=3, mUseEmissiveLights=1, mUseAnalyticLights=1)
+    elif variant == "four_bounces_no_mis_two_rounds":
+        kw = dict(mMaxBounces=4, mSpatialMISMethod=capi.kMISNone, mTemporalMISMethod=capi.kMISNone, mSpatialReuseRounds=2, mSpatialSampleCount=3)
+    elif variant == "final_ray_marching":
+        kw = dict(mFinalVisibilityTrackingMethod=capi.kRayMarching, mFinalLightTrackingMethod=capi.kRayMarching)
+    elif variant == "final_mixed_two_bounces":
+        kw = dict(mMaxBounces=2, mFinalVisibilityTrackingMethod=capi.kRayMarching, mFinalLightTrackingMethod=capi.kAnalyticTracking, mFinalTStepScale=0.5)
+    elif variant == "spatial_analytic_two_bounces":
+        kw = dict(mMaxBounces=2, mSpatialLightingTrackingMethod=capi.kAnalyticTracking, mSpatialLightingMipLevel=2, mSpatialVisibilityTStepScale=1.5)
+    elif variant == "three_level_three_bounces":
+        sc = env_scene(dim=(200, 180, 150), density_scale=0.2, num_mips=4, distance=0.9)
+        kw = dict(mMaxBounces=3)
+    p = VolumetricReSTIRParams(**kw)
+    img_s, res_s = _frames_buffers(p, sc, w, h, False)
+    for budget_mb in (4096, 3):
+        gp_extra = {"mDebugPoisonResults": 1, "mScratchBudgetMB": budget_mb}
+        img_w, res_w = _frames_buffers(p, sc, w, h, True, extra=gp_extra)
+        assert np.array_equal(res_w.view(np.uint32), res_s.view(np.uint32)), f"generic task-stream reservoirs differ from the per-pixel kernels (budget {budget_mb} MB)"
+        assert np.array_equal(img_w.view(np.uint32), img_s.view(np.uint32)), f"generic task-stream image differs (budget {budget_mb} MB)"
+    assert np.isfinite(img_w).all() and (img_w[..., :3].sum(-1) > 0).mean() > 0.05
+
+
+def test_generic_task_streams_are_used_and_chunked():
+    """The multi-bounce frame really runs through the emit / march / consume kernels (launch count), and a small scratch budget
+    splits the stages into row chunks."""
+    import torch
+    w, h = 160, 96
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.15)
+    color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    counts = []
+    for budget_mb in (4096, 3):
+        gp = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams(mMaxBounces=3), "mScratchBudgetMB": budget_mb})
+        gp.setScene(sc, w, h)
+        gp.execute(color.data_ptr()); gp.execute(color.data_ptr())
+        n0 = gp.launch_count()
+        gp.execute(color.data_ptr())
+        torch.cuda.synchronize()
+        counts.append(gp.launch_count() - n0)
+    # K0 + K1 (per-pixel) + K2 {emit, 1 march, consume} + K3 {emit, camera march, 1 march, consume} + K5 {emit, 1 march, consume}
+    assert counts[0] == 2 + 3 + 4 + 3, counts
+    assert counts[1] > counts[0], counts
 
 
 def _plume_scene(frame_time, dim=(64, 96, 64)):
@@ -292,6 +354,96 @@ def test_accumulated_full_reuse_relmse():
     print(f"[accumulated {frames} frames] relMSE gpu vs oracle {r:.3e}, mean gpu {acc_g[..., :3].mean():.6f} cpu {acc_c[..., :3].mean():.6f}")
     assert r <= 1e-3
     assert abs(acc_g[..., :3].mean() / acc_c[..., :3].mean() - 1) < 2e-3
+
+
+def test_converged_4096_frames_relmse():
+    """North star: "converged 4096-frame accumulations with full reuse must match within relMSE 1e-3".  4096 frames of the default
+    pass (temporal + spatial reuse) accumulated by the product's AccumulatePass (double precision) against the oracle's frames
+    accumulated in numpy, at reduced resolution so that the oracle finishes in seconds; plus the unbiasedness of the converged
+    image against the reference's own ground-truth mode (mUseReference, 4096 spp): mean ratio within 1 %."""
+    import torch
+    from common import rel_mse
+    from volumetricrestirrelease_b200.post import AccumulatePass
+    w, h, frames = 64, 40, 4096
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.15)
+    gp, op = make_pair(sc, VolumetricReSTIRParams(), w, h)
+    color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    out = torch.zeros_like(color)
+    acc = AccumulatePass.create({"precisionMode": "Double"}, w, h)
+    acc_c = np.zeros((h, w, 4), np.float64)
+    for _ in range(frames):
+        gp.execute(color.data_ptr())
+        acc.execute(color.data_ptr(), out.data_ptr())
+        acc_c += op.execute()
+    torch.cuda.synchronize()
+    acc_g = out.cpu().numpy().astype(np.float64)
+    acc_c /= frames
+    r = rel_mse(acc_g, acc_c)
+    print(f"[converged {frames} frames] relMSE gpu vs oracle {r:.3e}, mean gpu {acc_g[..., :3].mean():.6f} cpu {acc_c[..., :3].mean():.6f}")
+    assert r <= 1e-3
+    assert abs(acc_g[..., :3].mean() / acc_c[..., :3].mean() - 1) < 1e-3
+    ref = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams(mUseReference=1, mBaselineSamplePerPixel=64)})
+    ref.setScene(sc, w, h)
+    acc_r = np.zeros((h, w, 4), np.float64)
+    for _ in range(64):
+        ref.execute(color.data_ptr())
+        torch.cuda.synchronize()
+        acc_r += color.cpu().numpy()
+    acc_r /= 64
+    ratio = acc_g[..., :3].mean() / acc_r[..., :3].mean()
+    print(f"[converged vs mUseReference 4096 spp] mean ratio {ratio:.4f}, relMSE {rel_mse(acc_g, acc_r):.3e}")
+    assert abs(ratio - 1) < 0.01
+
+
+def test_full_size_crop_with_history_1080p():
+    """BASELINE.json configs[1] at full size, a frame WITH history (frame 2: K2 merges the previous frame's reservoirs, K3 reads
+    merged neighbours): the GPU renders frames 0 and 1 through the public call; its history (temporal reservoirs, features,
+    previous camera, frame counter) is handed to the oracle, and frame 2 is compared on two 64x64 crops (cloud centre and a
+    silhouette region), every stage of the oracle run on the crop + the halo the later stages read."""
+    import torch
+    import bench
+    from oracle import vro
+
+    class A:
+        pass
+    args = A()
+    args.width, args.height, args.dim, args.kind, args.mips, args.bounces = 1920, 1080, [577, 572, 438], "bunny", 4, 1
+    sc = bench.build_scene(args)
+    p = bench.make_params(args)
+    w, h = args.width, args.height
+    gp = VolumetricReSTIR.create({"mParams": p})
+    gp.setScene(sc, w, h)
+    color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        gp.execute(color.data_ptr())
+    torch.cuda.synchronize()
+    op = vro.OraclePass(p)
+    op.setScene(sc, w, h, importance=gp.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32), env_alias=gp.env_alias())
+    c0 = np.zeros((h, w, 4), np.float32)
+    op.execute_stage(6, 0, c0)                      # saves the (static) camera as the previous frame's
+    op.set_frame_count(2, 1)
+    assert gp.frame_count() == 2
+    for b in (capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL):
+        op.set_buffer(b, gp.get_buffer(b))
+    gp.execute(color.data_ptr()); torch.cuda.synchronize()
+    g2 = color.cpu().numpy()
+    T, halo = 64, 10
+    merged = 0
+    for x0, y0 in ((w // 2 - 32, h // 2 - 32), (w // 2 - 420, h // 2 - 200)):
+        for stage in (0, 1, 2):
+            op.set_crop(x0 - halo, y0 - halo, x0 + T + halo, y0 + T + halo)
+            op.execute_stage(stage, 0, c0)
+        m = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w)["M"][y0:y0 + T, x0:x0 + T]
+        merged += int((m > 4).sum())              # K2 merged history: M = 4 candidates + min(history M, 4 * 4)
+        for stage in (3, 4, 5):
+            op.set_crop(x0, y0, x0 + T, y0 + T)
+            op.execute_stage(stage, 0, c0)
+        e = rel_err_image(g2[y0:y0 + T, x0:x0 + T], c0[y0:y0 + T, x0:x0 + T])
+        bad = (e > RADIANCE_RTOL).mean()
+        print(f"[1080p frame 2 crop at ({x0},{y0}) vs oracle] frac > 1e-4: {bad:.2e}, max {e.max():.3g}")
+        assert bad <= 5e-3
+        op.set_frame_count(2, 1)                  # stage 0 of the next crop must not restart the epoch
+    assert merged > T * T // 2, "the crops did not contain merged history"
 
 
 def test_full_size_properties_1080p():

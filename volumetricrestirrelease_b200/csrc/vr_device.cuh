@@ -14,12 +14,14 @@
 // functions (expf/logf/sinf/cosf/atan2f/acosf/powf) may differ in the last ulp.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include <float.h>
 #include "../../include/vrestir.h"
 #include "vr_types.h"
 
 namespace vrd {
+namespace cg = cooperative_groups;
 
 #define VRD __device__ __forceinline__
 #define VRD_NOINLINE static __device__ __noinline__
@@ -1245,23 +1247,39 @@ VRD bool lightRayAndLd(const MediumInteraction& mi, int lightID, float2 lightUV,
     }
     return isValidSample;
 }
-template <class = void>
-VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2 lightUV, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool cullNonOpaqueGeometry) {
+// March provider of the target-function evaluation.  The transmittances an evaluation needs (camera ray to the first vertex,
+// one scatter segment per indirect bounce, last vertex to the light) are independent of each other and of the random-number
+// stream whenever the tracking method is deterministic, so the evaluation code is written once against this policy:
+//   InlineMarch   computes each transmittance in place (per-pixel kernels, and every stochastic tracking method);
+//   EmitMarch / ConsumeMarch (vr_wavefront.cu) run the SAME stage code twice: the first pass turns every march into a task
+//   of a compacted stream and continues with a placeholder, the second pass reads the marched results — identical
+//   arithmetic, different schedule.
+// A march is identified by (evaluation id set with beginEval, slot): slot 0 camera, 1..3 scatter segment of bounce 0..2, 4 light.
+enum { MARCH_SLOT_CAMERA = 0, MARCH_SLOT_SCATTER0 = 1, MARCH_SLOT_LIGHT = 4, MARCH_SLOTS = 5 };
+struct InlineMarch {
+    static constexpr bool kStore = true;    // the pass writes the stage's outputs
+    VRD void beginEval(int) {}
+    VRD float visibility(int, const Ray& ray, SampleGenerator& sg, int samples, int mip, bool linear, uint32_t method, float tStepScale) {
+        return computeVisibility(ray, sg, samples, mip, linear, method, tStepScale);
+    }
+};
+
+template <class MP>
+VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2 lightUV, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool cullNonOpaqueGeometry, MP& mp) {
     Ray shadowRay; float3 Ld;
     const bool isValidSample = lightRayAndLd(mi, lightID, lightUV, isLastFrame, shadowRay, Ld);
     const bool useLastFrameGrid = c_scene.vol.usePrevGridForReproj && isLastFrame && c_scene.vol.hasAnimation;
     const int densityGridOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
     float Tr = 1.f;
     if (isValidSample)
-        Tr = computeVisibility(shadowRay, sg, o.lightSamples, cullNonOpaqueGeometry ? o.lightingMipLevel + densityGridOffset : 0, o.lightingUseLinearSampler,
-                               o.lightingTrackingMethod, o.lightingTStepScale);
+        Tr = mp.visibility(MARCH_SLOT_LIGHT, shadowRay, sg, o.lightSamples, cullNonOpaqueGeometry ? o.lightingMipLevel + densityGridOffset : 0, o.lightingUseLinearSampler,
+                           o.lightingTrackingMethod, o.lightingTStepScale);
     return Tr * Ld;
 }
 
 // VR/ReSTIRHelper.slang:91-423 (no SURFACE_SCENE / VERTEX_REUSE)
-template <int B, class Extra>
-__device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool noReuse, bool isFinalShading,
-                              float externalVis = -1.f) {   // externalVis: IExternalVisibilityProvider of VR/ArrayDataProvider.slang:48-63 (bounce 0)
+template <int B, class Extra, class MP>
+__device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool noReuse, bool isFinalShading, MP& mp) {
     const vrestir_volume_desc& vd = c_scene.vol;
     const bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
     const int mipLevelOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
@@ -1278,10 +1296,8 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
     {
         float density = (isBackgroundSample || noReuse) ? 1.f : DensityWorldSpace(p_World, mipLevelOffset);
         if (density == 0.f) return f3(0.f);
-        if (!noReuse) {
-            if (externalVis != -1.f) visibility = externalVis;
-            else visibility = computeVisibility(ray, sg, o.visibilitySamples, o.visibilityMipLevel + mipLevelOffset, o.visibilityUseLinearSampler, o.visibilityTrackingMethod, o.visibilityTStepScale);
-        }
+        if (!noReuse)
+            visibility = mp.visibility(MARCH_SLOT_CAMERA, ray, sg, o.visibilitySamples, o.visibilityMipLevel + mipLevelOffset, o.visibilityUseLinearSampler, o.visibilityTrackingMethod, o.visibilityTStepScale);
         float3 sigma_s = isBackgroundSample ? f3(1.f) : (isSelfEmission ? sigA : sigS);
         if (noReuse && !isBackgroundSample) sigma_s = sigma_s / vd.sigma_t;
         F = F * (visibility * density * sigma_s);
@@ -1330,8 +1346,8 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
                     if (all_eq0(F)) return f3(0.f);
                     float scatterVisibility = 1.f;
                     if (!noReuse)
-                        scatterVisibility = computeVisibility(scatterRay, sg, o.visibilitySamples, o.visibilityMipLevel + mipLevelOffset, o.visibilityUseLinearSampler,
-                                                              o.visibilityTrackingMethod, o.visibilityTStepScale);
+                        scatterVisibility = mp.visibility(MARCH_SLOT_SCATTER0 + bounceId, scatterRay, sg, o.visibilitySamples, o.visibilityMipLevel + mipLevelOffset, o.visibilityUseLinearSampler,
+                                                          o.visibilityTrackingMethod, o.visibilityTStepScale);
                     F = F * scatterVisibility;
                     mi.wo = -scatterRay.dir;
                     mi.p = p_World;
@@ -1341,22 +1357,24 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
                 else mi = makeMI(scatterRay.at(scatterRay.tMax), -scatterRay.dir, true);
             }
             if (!isScatterSelfEmission && any_gt0(F))
-                F = F * evaluate_L_in_volume(mi, tap.lightID, tap.lightUV, sg, o, isLastFrame, !isFinalShading);
+                F = F * evaluate_L_in_volume(mi, tap.lightID, tap.lightUV, sg, o, isLastFrame, !isFinalShading, mp);
         }
     }
     return F;
 }
-template <int B, class Extra>
-VRD float evaluate_P_hat(const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, const Reservoir& tap, bool isLastFrame) {
-    float3 F = evaluate_F_<B>(tap, extra, ray, sg, o, isLastFrame, false, false);
+template <int B, class Extra, class MP>
+VRD float evaluate_P_hat(const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, const Reservoir& tap, bool isLastFrame, MP& mp) {
+    float3 F = evaluate_F_<B>(tap, extra, ray, sg, o, isLastFrame, false, false, mp);
     return luminance(F);
 }
-template <int B, class Extra>
-VRD void resampleNeighbor(Reservoir& tap, const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o) {
+template <int B, class Extra, class MP>
+VRD void resampleNeighbor(Reservoir& tap, const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, MP& mp) {
     if (tap.runningSum == 0.f) return;
-    float p_y_hat = evaluate_P_hat<B>(ray, sg, extra, o, tap, false);
+    float p_y_hat = evaluate_P_hat<B>(ray, sg, extra, o, tap, false, mp);
     float weight = p_y_hat / tap.p_y;
-    if (isinf(weight) || isnan(weight)) weight = 0.f;
+    // an emit pass (placeholder transmittances of 1) must keep every sample the real pass can keep: with a denormal p_y the
+    // placeholder ratio overflows where the real one is finite
+    if (isinf(weight) || isnan(weight)) weight = MP::kStore ? 0.f : 1.f;
     tap.runningSum *= weight;
     tap.p_y = p_y_hat;
 }
@@ -1394,6 +1412,25 @@ VRD void wfEmitRay(const WfStream& s, bool want, const Ray& rW, int mip, bool ve
             q[1] = make_uint4(__float_as_uint(pr.dir.x), __float_as_uint(pr.dir.y), __float_as_uint(pr.dir.z), __float_as_uint(pr.tFar));
             q[2] = make_uint4(out, 0u, 0u, 0u);
         }
+    }
+}
+
+// The same from divergent code (the emit pass of the generic task-stream path calls it from inside the evaluation): the lanes
+// that happen to be converged here share one atomic (cooperative-groups coalesced group).  Task order in the stream depends on
+// that grouping, results do not: every task carries its result index.
+VRD void wfEmitRayAny(const WfStream& s, const Ray& rW, int mip, bool vertexCenter, float* results, unsigned out) {
+    PreparedRay pr;
+    if (!wfPrepare(rW, mip, vertexCenter, pr)) { results[out] = 1.f; return; }
+    cg::coalesced_group grp = cg::coalesced_threads();
+    unsigned base = 0;
+    if (grp.thread_rank() == 0) base = atomicAdd(s.count, (unsigned)grp.size());
+    base = grp.shfl(base, 0);
+    const unsigned pos = base + grp.thread_rank();
+    if (pos < s.capacity) {
+        uint4* q = s.tasks + 3 * (size_t)pos;
+        q[0] = make_uint4(__float_as_uint(pr.pos.x), __float_as_uint(pr.pos.y), __float_as_uint(pr.pos.z), __float_as_uint(pr.tNear));
+        q[1] = make_uint4(__float_as_uint(pr.dir.x), __float_as_uint(pr.dir.y), __float_as_uint(pr.dir.z), __float_as_uint(pr.tFar));
+        q[2] = make_uint4(out, 0u, 0u, 0u);
     }
 }
 

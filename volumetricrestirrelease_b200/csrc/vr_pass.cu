@@ -136,6 +136,10 @@ struct vrestir_pass {
     size_t wfPixels = 0;
     int marchBlocks1 = 0, marchBlocks3 = 0, analyticBlocks = 0;
     float* wfInitialState = nullptr; size_t wfInitialPixels = 0;   // lock-step wavefront K1
+    // generic task-stream path (multi-bounce option sets): one grow-only arena {tasks | results}, carved per stage and per row chunk
+    void* mbArena = nullptr; size_t mbArenaBytes = 0; unsigned* mbCounters = nullptr;
+    size_t mScratchBudget = (size_t)4 << 30;   // "mScratchBudgetMB": a stage whose worst-case task scratch exceeds this runs in row chunks
+    uint64_t mbChunks = 0; bool mDebugPoison = false;   // "mDebugPoisonResults": result blocks start as NaN, so a march the emit pass missed shows up in the image
 };
 
 namespace {
@@ -204,6 +208,114 @@ void wavefrontKinds(const vrestir_pass* p, MarchKind& cam, MarchKind& light) {
     const vrestir_params& m = p->P;
     cam = MarchKind{m.mSpatialVisibilityMipLevel, m.mSpatialVisibilityUseLinearSampler, m.mSpatialVisibilityTStepScale, 1, {p->cam.posW[0], p->cam.posW[1], p->cam.posW[2]}};
     light = MarchKind{m.mSpatialLightingMipLevel, m.mSpatialLightingUseLinearSampler, m.mSpatialLightingTStepScale, 0, {0.f, 0.f, 0.f}};
+}
+
+// ---- generic task-stream path ---------------------------------------------------------------------------------------------
+// which stages of the current option set can run as emit / march / consume passes (deterministic tracking only: a stochastic
+// tracker draws from the pixel's random-number stream inside the march)
+bool genericStageOk(const vrestir_pass* p, int stage) {
+    const vrestir_params& m = p->P;
+    if (!p->mUseWavefront || m.mUseReference || m.mMaxBounces < 1 || m.mMaxBounces > 4) return false;
+    auto det = [](uint32_t method) { return method == VRESTIR_RAY_MARCHING || method == VRESTIR_ANALYTIC_TRACKING; };
+    if (stage == 5) return !m.mVisualizeTotalTransmittance && det(m.mFinalVisibilityTrackingMethod) && det(m.mFinalLightTrackingMethod);
+    // K2 / K3 evaluate under the spatial options; analytic tracking with the point sampler has no march kernel
+    auto ok = [&](uint32_t method, int linear) { return method == VRESTIR_RAY_MARCHING || (method == VRESTIR_ANALYTIC_TRACKING && linear); };
+    if (!ok(m.mSpatialVisibilityTrackingMethod, m.mSpatialVisibilityUseLinearSampler) || !ok(m.mSpatialLightingTrackingMethod, m.mSpatialLightingUseLinearSampler)) return false;
+    // the shared camera marches of K3 are ray-marched (multi-threshold march engine)
+    if (stage == 3) return m.mSpatialSampleCount <= 4 && m.mSpatialVisibilityTrackingMethod == VRESTIR_RAY_MARCHING;
+    return true;
+}
+struct MarchRole { int mip, linear; float scale; uint32_t method; int perPixel; };
+
+// One stage (2 temporal, 3 spatial, 5 final) over the band of `fp`, in row chunks whose worst-case scratch fits the budget.
+int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStream_t st) {
+    const vrestir_params& m = p->P;
+    const int B = m.mMaxBounces;
+    const bool prevGrid = p->scene.vol.usePrevGridForReproj && p->scene.vol.hasAnimation;
+    const int off = prevGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
+    // worst-case marches per pixel and configuration (an evaluation = 1 camera + (B-1) scatter segments under the visibility options + 1 light march)
+    std::vector<MarchRole> roles;
+    const SamplingOptions& o = stage == 5 ? fp.fin : fp.spatial;
+    int stride = 0, camTasks = 0;
+    if (stage == 2) {
+        stride = MB_K2_STRIDE;
+        roles.push_back({o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, o.visibilityTrackingMethod, B});        // E(1,0): history sample on the current ray
+        roles.push_back({o.lightingMipLevel, o.lightingUseLinearSampler, o.lightingTStepScale, o.lightingTrackingMethod, 1});
+        roles.push_back({o.visibilityMipLevel + off, o.visibilityUseLinearSampler, o.visibilityTStepScale, o.visibilityTrackingMethod, B});  // E(0,1): current sample on the previous frame's ray
+        roles.push_back({o.lightingMipLevel + off, o.lightingUseLinearSampler, o.lightingTStepScale, o.lightingTrackingMethod, 1});
+    } else if (stage == 3) {
+        stride = MB_K3_STRIDE; camTasks = 4;
+        roles.push_back({o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, o.visibilityTrackingMethod, 12 * (B - 1)});
+        roles.push_back({o.lightingMipLevel, o.lightingUseLinearSampler, o.lightingTStepScale, o.lightingTrackingMethod, 12});
+    } else {
+        stride = MB_K5_STRIDE;
+        roles.push_back({o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, o.visibilityTrackingMethod, B});
+        roles.push_back({0, o.lightingUseLinearSampler, o.lightingTStepScale, o.lightingTrackingMethod, 1});   // final shading marches the light ray through mip 0
+    }
+    // identical configurations share a stream
+    std::vector<MarchRole> uniq;
+    for (const MarchRole& r : roles) {
+        if (r.perPixel <= 0) continue;
+        bool merged = false;
+        for (MarchRole& u : uniq)
+            if (u.mip == r.mip && u.linear == r.linear && u.scale == r.scale && (u.method == VRESTIR_ANALYTIC_TRACKING) == (r.method == VRESTIR_ANALYTIC_TRACKING)) { u.perPixel += r.perPixel; merged = true; break; }
+        if (!merged) uniq.push_back(r);
+    }
+    if (uniq.size() > 4) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "internal: more than four march configurations in one stage");
+    for (const MarchRole& u : uniq)
+        if (u.mip < 0 || u.mip >= VRESTIR_MAX_SLOTS || !p->scene.slots[u.mip].valid) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "a reuse stage names a grid slot that is not bound");
+    size_t tasksPerPixel = 0; for (const MarchRole& u : uniq) tasksPerPixel += (size_t)u.perPixel;
+    const size_t bytesPerPixel = tasksPerPixel * 48 + (size_t)camTasks * 32 + (size_t)stride * 4;
+    const int bandRows = fp.rowEnd - fp.rowBegin;
+    size_t maxRows = p->mScratchBudget / (bytesPerPixel * (size_t)fp.W);
+    maxRows = std::min<size_t>(maxRows, ((size_t)1 << 32) / ((size_t)fp.W * (size_t)std::max<size_t>(stride, 1)) - 1);   // 32-bit result indices
+    int chunkRows = (int)std::min<size_t>((size_t)bandRows, std::max<size_t>(8, maxRows / 8 * 8));
+    const size_t chunkPixels = (size_t)chunkRows * fp.W;
+    const size_t need = chunkPixels * bytesPerPixel + 256;
+    if (p->mbArenaBytes < need) {
+        CK(cudaStreamSynchronize(st));
+        if (p->mbArena) cudaFree(p->mbArena);
+        p->mbArena = nullptr; p->mbArenaBytes = 0;
+        CK(cudaMalloc(&p->mbArena, need));
+        p->mbArenaBytes = need;
+    }
+    if (!p->mbCounters) CK(cudaMalloc(&p->mbCounters, 64));
+    if (!p->marchBlocks1 || !p->analyticBlocks) {
+        int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+        p->marchBlocks1 = sms * marchBlocksPerSM(1); p->marchBlocks3 = sms * marchBlocksPerSM(3); p->analyticBlocks = sms * analyticBlocksPerSM();
+    }
+    // carve: [results | camera tasks | stream 0 | stream 1 | ...]
+    char* base = (char*)p->mbArena;
+    float* results = (float*)base; base += (chunkPixels * stride * 4 + 15) / 16 * 16;
+    WfStream cam{}; cam.tasks = (uint4*)base; cam.count = p->mbCounters; cam.cursor = p->mbCounters + 1; cam.capacity = (unsigned)(chunkPixels * camTasks);
+    base += chunkPixels * camTasks * 32;
+    MarchStreams ms{}; ms.n = (int)uniq.size();
+    for (int k = 0; k < ms.n; k++) {
+        ms.s[k].tasks = (uint4*)base; ms.s[k].count = p->mbCounters + 2 + 2 * k; ms.s[k].cursor = p->mbCounters + 3 + 2 * k;
+        ms.s[k].capacity = (unsigned)std::min<size_t>(chunkPixels * (size_t)uniq[k].perPixel, 0xffffffffull);
+        base += chunkPixels * (size_t)uniq[k].perPixel * 48;
+        ms.mip[k] = uniq[k].mip; ms.linear[k] = uniq[k].linear ? 1 : 0; ms.scale[k] = uniq[k].scale; ms.analytic[k] = uniq[k].method == VRESTIR_ANALYTIC_TRACKING ? 1 : 0;
+    }
+    for (int r0 = fp.rowBegin; r0 < fp.rowEnd; r0 += chunkRows) {
+        FrameParams fc = fp;
+        fc.rowBegin = r0; fc.rowEnd = std::min(fp.rowEnd, r0 + chunkRows);
+        CK(cudaMemsetAsync(p->mbCounters, 0, 64, st));
+        if (p->mDebugPoison) CK(cudaMemsetAsync(results, 0xFF, chunkPixels * stride * 4, st));
+        CK(launchStageEmit(stage, fc, ms, cam, results, st)); p->launches++;
+        if (camTasks) {
+            const MarchKind kc = {o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, 1, {fp.camPos.x, fp.camPos.y, fp.camPos.z}};
+            CK(launchMarch(cam, results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st)); p->launches++;
+        }
+        for (int k = 0; k < ms.n; k++) {
+            const MarchKind kk = {ms.mip[k], ms.linear[k], ms.scale[k], 0, {0.f, 0.f, 0.f}};
+            if (ms.analytic[k]) CK(launchMarchAnalytic(ms.s[k], results, kk, p->scene.slots[kk.mip], p->analyticBlocks, st));
+            else CK(launchMarch(ms.s[k], results, kk, p->scene.slots[kk.mip], 1, p->marchBlocks1, st));
+            p->launches++;
+        }
+        CK(launchStageConsume(stage, fc, results, st)); p->launches++;
+        p->mbChunks++;
+    }
+    return VRESTIR_OK;
 }
 
 void freeSlot(DevSlot& d) {
@@ -683,7 +795,8 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
                             if (unique[k]) { CK(launchMarch(wf.s[k], wf.results, kinds[k], p->scene.slots[kinds[k].mip], 1, p->marchBlocks1, st)); p->launches++; }
                         CK(launchTemporalCombine(fp, wf, st));
                         p->launches += 2;
-                    } else { CK(launchTemporal(fp, st)); p->launches++; }
+                    } else if (genericStageOk(p, 2)) { rc = runStageGeneric(p, 2, fp, st); if (rc) return rc; }
+                    else { CK(launchTemporal(fp, st)); p->launches++; }
                 }
                 p->finalPhys = p->ia;
             }
@@ -714,7 +827,8 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
                     CK(cudaMemcpyAsync(p->wfCounters + 9, p->wfCounters + 2, 4, cudaMemcpyDeviceToDevice, st));
                     CK(launchSpatialCombine(fp, wf, st));
                     p->launches += 4;
-                } else { CK(launchSpatial(fp, st)); p->launches++; }
+                } else if (genericStageOk(p, 3)) { rc = runStageGeneric(p, 3, fp, st); if (rc) return rc; }
+                else { CK(launchSpatial(fp, st)); p->launches++; }
                 p->finalPhys = out;
             }
             if (!(m.mEnableSpatialReuse && arg + 1 < m.mSpatialReuseRounds)) recordEv(p, 4, st);
@@ -763,7 +877,8 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
                     CK(cudaEventRecord(p->evOutDone[p->outSeq & 1], so));
                     p->outSeq++; p->outTimed = true;
                 }
-            } else { CK(launchFinal(fp, st)); p->launches++; }
+            } else if (genericStageOk(p, 5)) { rc = runStageGeneric(p, 5, fp, st); if (rc) return rc; }
+            else { CK(launchFinal(fp, st)); p->launches++; }
             recordEv(p, 6, st);
             break;
         case 6: {   // VR/VolumetricReSTIR.cpp:765-772 (+ :636 feature history, as a swap)
@@ -885,7 +1000,7 @@ int vrestir_destroy(vrestir_pass* p) try {
     for (auto& d : p->dslots) freeSlot(d);
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
     for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); if (p->feat[i]) cudaFree(p->feat[i]); }
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters};
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters, p->mbArena, p->mbCounters};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
@@ -1156,6 +1271,8 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) try {
         else if (k == "mInitialMode") p->mInitialMode = (int)value;
         else if (k == "mOverlapFeatures") p->mOverlapFeatures = value != 0;
         else if (k == "mPipelineFrames") p->mPipelineFrames = (int)value;
+        else if (k == "mDebugPoisonResults") p->mDebugPoison = value != 0;
+        else if (k == "mScratchBudgetMB") p->mScratchBudget = (size_t)std::max(1.0, value) << 20;
         else if (k == "mPrefetchPriority") p->mPrefetchPriority = value != 0;
         else if (k == "mMarchPairEngine") setPairEngine(value != 0);   // process-wide A/B switch of the march engine   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }

@@ -97,4 +97,10 @@ struct WfInitial { WfStream light; float* state; uint8_t* done; WfStream evalCam
 // streams whose march configuration is identical alias the same buffer
 struct WfBufs4 { WfStream s[4]; int mip[4]; float* results; };
 
+// Generic (multi-bounce) task-stream path: the stage bodies of vr_stages.cuh run as an emit pass and a consume pass.  Every
+// march configuration a stage can ask for is one stream; a pixel's results live at [pixel * stride + eval * MARCH_SLOTS + slot]
+// (+ MB_CAM for the shared multi-threshold camera marches of K3).
+struct MarchStreams { WfStream s[4]; int mip[4], linear[4], analytic[4]; float scale[4]; int n; };
+enum { MB_K2_STRIDE = 20, MB_K3_STRIDE = 96, MB_K3_CAM = 80, MB_K5_STRIDE = 8 };
+
 }  // namespace vrd

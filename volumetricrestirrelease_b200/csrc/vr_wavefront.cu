@@ -14,6 +14,7 @@
 // Ld; the camera transmittances of one ray share ONE multi-depth march (4 camera tasks per pixel instead of 12
 // marches), the light marches are 12 independent tasks.
 #include "vr_march_pair.cuh"
+#include "vr_stages.cuh"
 #include "vr_kernels.h"
 
 #ifndef VR_MARCH_MINB
@@ -757,6 +758,141 @@ __global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const flo
     fp.outColor[pixelId] = o;
 }
 
+// ------------------------------------------------------------------------------------------------ generic task-stream path
+// Multi-bounce option sets (and every deterministic-tracking option set the specialised kernels above do not cover): the stage
+// bodies of vr_stages.cuh — the very code of the per-pixel kernels — run twice around the march engine.
+//   emit     every transmittance the evaluation asks for becomes a prepared task of the stream that holds its march
+//            configuration and the evaluation continues with the placeholder 1 (a superset of the marches the real run
+//            needs: a real transmittance can only cut the evaluation shorter); nothing is stored;
+//   march    the persistent-lane engine (k_march / k_march_analytic) over each stream;
+//   consume  the same body again, every transmittance read from the result block; stores the stage's outputs.
+// Bit-identical to the per-pixel kernels by construction (same code, same operands), also for 2-4 bounces, emissive triangles
+// and analytic lights.  In K3 the camera marches of one ray are still shared: slot-0 marches become thresholds of <= 4
+// multi-threshold camera tasks per pixel.
+struct EmitMarch {
+    static constexpr bool kStore = false;
+    const MarchStreams& ms; float* results; unsigned base; unsigned eval = 0; unsigned camBits = 0; bool sharedCamera;
+    __device__ EmitMarch(const MarchStreams& m, float* r, unsigned b, bool shared) : ms(m), results(r), base(b), sharedCamera(shared) {}
+    VRD void beginEval(int id) { eval = (unsigned)id; }
+    VRD float visibility(int slot, const Ray& ray, SampleGenerator&, int, int mip, bool linear, uint32_t method, float tStepScale) {
+        if (sharedCamera && slot == MARCH_SLOT_CAMERA) {   // K3: tap i seen from ray j = threshold k of camera task j
+            const unsigned i = eval >> 2, j = eval & 3u;
+            camBits |= 1u << (j * 3u + (i - (i > j ? 1u : 0u)));
+            return 1.f;
+        }
+        const unsigned out = base + eval * MARCH_SLOTS + (unsigned)slot;
+        const int analytic = method == VRESTIR_ANALYTIC_TRACKING ? 1 : 0;
+        WfStream sel; sel.tasks = nullptr; sel.count = sel.cursor = nullptr; sel.capacity = 0;   // selected by predication: a dynamic index would spill the parameter block
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (!sel.tasks && q < ms.n && ms.mip[q] == mip && ms.linear[q] == (linear ? 1 : 0) && ms.analytic[q] == analytic && ms.scale[q] == tStepScale) sel = ms.s[q];
+        if (!sel.tasks) { results[out] = __int_as_float(0x7fc00000); return 1.f; }   // no stream for this configuration (host bug): poison the result
+        // analytic tracking with the linear sampler traverses vertex-centred (VR/VolumeUtils.slang:284-292)
+        wfEmitRayAny(sel, ray, mip, analytic && linear, results, out);
+        return 1.f;
+    }
+};
+struct ConsumeMarch {
+    static constexpr bool kStore = true;
+    const float* results; unsigned base; unsigned eval = 0; bool sharedCamera;
+    __device__ ConsumeMarch(const float* r, unsigned b, bool shared) : results(r), base(b), sharedCamera(shared) {}
+    VRD void beginEval(int id) { eval = (unsigned)id; }
+    VRD float visibility(int slot, const Ray&, SampleGenerator&, int, int, bool, uint32_t, float) {
+        if (sharedCamera && slot == MARCH_SLOT_CAMERA) {
+            const unsigned i = eval >> 2, j = eval & 3u;
+            return results[base + MB_K3_CAM + j * 3u + (i - (i > j ? 1u : 0u))];
+        }
+        return results[base + eval * MARCH_SLOTS + (unsigned)slot];
+    }
+};
+
+#ifndef VR_MB_MINB
+#define VR_MB_MINB 4
+#endif
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_temporal_emit(FrameParams fp, MarchStreams ms, float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    EmitMarch mp(ms, results, (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * MB_K2_STRIDE, false);
+    temporalPixel<B>(fp, x, y, mp);
+}
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_temporal_consume(FrameParams fp, const float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    ConsumeMarch mp(results, (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * MB_K2_STRIDE, false);
+    temporalPixel<B>(fp, x, y, mp);
+}
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_spatial_emit(FrameParams fp, MarchStreams ms, WfStream cam, float* results) {
+    int x, y;
+    const bool inFrame = pixelOf(fp, x, y);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int W = fp.W;
+    const unsigned blkBase = inFrame ? (unsigned)(y * W + x - fp.rowBegin * W) * MB_K3_STRIDE : 0u;
+    unsigned camBits = 0;
+    if (inFrame) {
+        EmitMarch mp(ms, results, blkBase, true);
+        spatialPixel<B>(fp, x, y, mp);
+        camBits = mp.camBits;
+    }
+    // the warp is converged again: camera tasks grouped by ray index, one reservation per warp (as k_spatial_gather)
+    unsigned camCnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) camCnt += ((camBits >> (3 * j)) & 7u) ? 1u : 0u;
+    const unsigned camTot = __reduce_add_sync(FULL, camCnt);
+    if (camTot == 0) return;
+    unsigned camBase = 0;
+    if (lane == 0) camBase = atomicAdd(cam.count, camTot);
+    camBase = __shfl_sync(FULL, camBase, 0);
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        const unsigned m = (camBits >> (3 * j)) & 7u;
+        const unsigned bal = __ballot_sync(FULL, m != 0);
+        if (m) {
+            const unsigned pos = camBase + __popc(bal & lt);
+            int tx, ty; tapInImage(fp, x, y, j, tx, ty);
+            const float3 d = tapRayDir(fp, tx, ty);
+            float thr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {   // threshold k of ray j is the depth of tap i = k + (k >= j)
+                if (!((m >> k) & 1u)) continue;
+                const int i = k + (k >= j ? 1 : 0);
+                int txi, tyi; tapInImage(fp, x, y, i, txi, tyi);
+                thr[k] = __ldg(&fp.cur.p0[tyi * W + txi]).z;
+            }
+            if (pos < cam.capacity) {
+                cam.tasks[2 * (size_t)pos] = make_uint4(__float_as_uint(thr[0]), __float_as_uint(thr[1]), __float_as_uint(thr[2]), m);
+                cam.tasks[2 * (size_t)pos + 1] = make_uint4(__float_as_uint(d.x), __float_as_uint(d.y), __float_as_uint(d.z), blkBase + MB_K3_CAM + j * 3);
+            }
+        }
+        camBase += __popc(bal);
+    }
+}
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_spatial_consume(FrameParams fp, const float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    ConsumeMarch mp(results, (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * MB_K3_STRIDE, true);
+    spatialPixel<B>(fp, x, y, mp);
+}
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_final_emit(FrameParams fp, MarchStreams ms, float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    EmitMarch mp(ms, results, (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * MB_K5_STRIDE, false);
+    finalPixel<B>(fp, x, y, mp);
+}
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_final_consume(FrameParams fp, const float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    ConsumeMarch mp(results, (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * MB_K5_STRIDE, false);
+    finalPixel<B>(fp, x, y, mp);
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 gridForWf(const FrameParams& fp) { return dim3((fp.W + 15) / 16, (fp.rowEnd - fp.rowBegin + 7) / 8); }
 // one warp (8x4 tile) per CTA
@@ -813,5 +949,26 @@ cudaError_t launchInitialFinish(const FrameParams& fp, const WfInitial& wi, cuda
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<VR_TGATHER_BLOCK == 32 ? gridForWarp(fp) : gridForWf(fp), VR_TGATHER_BLOCK, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
+
+#define VR_DISPATCH_MB(kern, fp, st, ...)                                                        \
+    switch ((fp).maxBounces) {                                                                   \
+        case 1: kern<1><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                      \
+        case 2: kern<2><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                      \
+        case 3: kern<3><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                      \
+        default: kern<4><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                     \
+    }
+// stage: 2 temporal, 3 spatial, 5 final
+cudaError_t launchStageEmit(int stage, const FrameParams& fp, const MarchStreams& ms, const WfStream& cam, float* results, cudaStream_t st) {
+    if (stage == 2) { VR_DISPATCH_MB(k_temporal_emit, fp, st, fp, ms, results); }
+    else if (stage == 3) { VR_DISPATCH_MB(k_spatial_emit, fp, st, fp, ms, cam, results); }
+    else { VR_DISPATCH_MB(k_final_emit, fp, st, fp, ms, results); }
+    return cudaGetLastError();
+}
+cudaError_t launchStageConsume(int stage, const FrameParams& fp, const float* results, cudaStream_t st) {
+    if (stage == 2) { VR_DISPATCH_MB(k_temporal_consume, fp, st, fp, results); }
+    else if (stage == 3) { VR_DISPATCH_MB(k_spatial_consume, fp, st, fp, results); }
+    else { VR_DISPATCH_MB(k_final_consume, fp, st, fp, results); }
+    return cudaGetLastError();
+}
 
 }  // namespace vrd
