@@ -320,6 +320,11 @@ int vrestir_get_frame_count(const vrestir_pass* pass, int* frame_count);
 int vrestir_execute(vrestir_pass* pass, float* out_color, float* out_mvec, void* stream);
 /* Same frame through host buffers (pinned or pageable): runs execute and copies the band back, synchronous. */
 int vrestir_execute_host(vrestir_pass* pass, float* out_color_host, float* out_mvec_host);
+/* The same without blocking: returns once the frame and its read-back are enqueued (the read-back of frame f overlaps the
+ * rendering of frame f+1); vrestir_host_wait blocks until every enqueued frame has landed in its host buffer.  Use pinned
+ * host memory, and do not touch a buffer between the call that fills it and the wait. */
+int vrestir_execute_host_async(vrestir_pass* pass, float* out_color_host, float* out_mvec_host);
+int vrestir_host_wait(vrestir_pass* pass);
 
 /* Individual stages (for staged parity tests and multi-GPU drivers that interleave halo exchanges).
  * stage: 0 features, 1 initial, 2 temporal, 3 spatial round `arg`, 4 copy-to-history, 5 final shading,
@@ -451,6 +456,15 @@ int vrestir_scene_create(const vrestir_scene_params* p, vrestir_scene** out);
 /* Build from a caller-supplied dense density array (dim x*y*z floats, x fastest); temperature/velocity may be NULL. */
 int vrestir_scene_create_from_dense(const vrestir_scene_params* p, const float* density, const float* temperature,
                                     const float* velocity_xyz, vrestir_scene** out);
+/* Description without voxels (dimensions, formats, transforms, VolumeDesc of every density level): the template of
+ * vrestir_set_volume_from_chain for grids that only ever exist on the device. */
+int vrestir_scene_create_template(const vrestir_scene_params* p, vrestir_scene** out);
+/* The procedural density field of `p` evaluated on the device into dense_out (dim x*y*z floats, x fastest; device memory):
+ * identical voxels to vrestir_scene_create's host generator for every kind but the plume. */
+int vrestir_make_procedural_device(int device, const vrestir_scene_params* p, float* dense_out, void* stream);
+/* Host copy of the volume bound to `pass` (tree with the device-computed brick bounds, child lists, brick pools) as a scene:
+ * lets a CPU checker evaluate a grid that was built on the device.  Destroy with vrestir_scene_destroy. */
+int vrestir_download_volume(vrestir_pass* pass, vrestir_scene** out);
 int vrestir_scene_destroy(vrestir_scene* s);
 const vrestir_grid_desc* vrestir_scene_grid(const vrestir_scene* s);
 /* dense copy of one mip (debug / tests): conservative = 0/1 */

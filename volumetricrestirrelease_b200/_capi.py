@@ -144,9 +144,9 @@ SYMBOLS = [
     "vrestir_set_analytic_lights", "vrestir_set_emissive_triangles", "vrestir_get_emissive_alias",
     "vrestir_get_env_alias", "vrestir_build_alias_table", "vrestir_build_env_alias", "vrestir_set_frame", "vrestir_update", "vrestir_set_params", "vrestir_get_params",
     "vrestir_set_frame_count", "vrestir_set_prev_camera", "vrestir_get_frame_count", "vrestir_execute",
-    "vrestir_execute_host", "vrestir_execute_stage", "vrestir_set_next_camera", "vrestir_get_pipeline_stats", "vrestir_wait_output", "vrestir_get_timings", "vrestir_get_march_timings", "vrestir_debug_read_bandwidth", "vrestir_debug_long_rays", "vrestir_debug_wavefront_counters", "vrestir_get_launch_count",
+    "vrestir_execute_host", "vrestir_execute_host_async", "vrestir_host_wait", "vrestir_execute_stage", "vrestir_set_next_camera", "vrestir_get_pipeline_stats", "vrestir_wait_output", "vrestir_get_timings", "vrestir_get_march_timings", "vrestir_debug_read_bandwidth", "vrestir_debug_long_rays", "vrestir_debug_wavefront_counters", "vrestir_get_launch_count",
     "vrestir_buffer_bytes", "vrestir_get_buffer", "vrestir_set_buffer", "vrestir_device_buffer",
-    "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
+    "vrestir_spatial_input_buffer", "vrestir_scene_create", "vrestir_scene_create_template", "vrestir_make_procedural_device", "vrestir_download_volume", "vrestir_scene_create_from_dense", "vrestir_scene_destroy",
     "vrestir_scene_grid", "vrestir_scene_dense_mip", "vrestir_scene_stats", "vrestir_camera_look_at",
     "vrestir_set_volume_from_chain", "vrestir_mips_build_device", "vrestir_mips_count", "vrestir_mips_level", "vrestir_mips_destroy",
     "vrestir_accum_create", "vrestir_accum_destroy", "vrestir_accum_update", "vrestir_accum_reset", "vrestir_accum_resize",
@@ -192,6 +192,8 @@ def lib():
     L.vrestir_get_frame_count.argtypes = [vp, C.POINTER(C.c_int)]
     L.vrestir_execute.argtypes = [vp, vp, vp, vp]
     L.vrestir_execute_host.argtypes = [vp, vp, vp]
+    L.vrestir_execute_host_async.argtypes = [vp, vp, vp]
+    L.vrestir_host_wait.argtypes = [vp]
     L.vrestir_execute_stage.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.vrestir_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.vrestir_mips_build_device.argtypes = [C.c_int, vp, C.POINTER(_I * 3), C.c_int, C.POINTER(vp), vp]
@@ -221,6 +223,9 @@ def lib():
     L.vrestir_device_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
     L.vrestir_spatial_input_buffer.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     L.vrestir_scene_create.argtypes = [C.POINTER(SceneParams), C.POINTER(vp)]
+    L.vrestir_scene_create_template.argtypes = [C.POINTER(SceneParams), C.POINTER(vp)]
+    L.vrestir_make_procedural_device.argtypes = [C.c_int, C.POINTER(SceneParams), vp, vp]
+    L.vrestir_download_volume.argtypes = [vp, C.POINTER(vp)]
     L.vrestir_scene_create_from_dense.argtypes = [C.POINTER(SceneParams), vp, vp, vp, C.POINTER(vp)]
     L.vrestir_scene_destroy.argtypes = [vp]
     L.vrestir_scene_grid.argtypes = [vp]

@@ -16,5 +16,12 @@ struct Topology {
     std::vector<uint32_t> child[3];
     uint32_t brickCount = 0; int n1count = 0; int topLev = 1;
 };
+struct HostSlotVectors { std::vector<vrestir_node>* nodes[3]; std::vector<uint32_t>* child[3]; std::vector<uint8_t>* atlas; vrestir_grid_slot* desc; };
+}
+struct vrestir_scene;
+namespace vr {
+vrestir_scene* newHostScene(const vrestir_volume_desc& vol);
+HostSlotVectors hostSlotVectors(vrestir_scene* s, int slot);
+void attachBlackbodyLut(vrestir_scene* s);
 void buildTopology(std::vector<uint8_t>& active /* (nz+7)/8 x (ny+7)/8 x (nx+7)/8, may get its first entry set */, int nx, int ny, int nz, Topology& out);
 }

@@ -17,6 +17,7 @@
 #include "../../include/vrestir.h"
 #include "vr_mipbuild.h"
 #include "vr_host.h"
+#include "vr_procedural.h"
 
 namespace vr { int setError(int code, const std::string& msg); }
 using vr::setError;
@@ -150,6 +151,15 @@ __global__ void k_quad_repack(const uint8_t* __restrict__ atlas, size_t totalWor
     quads[gid] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[10] << 16) | ((uint32_t)c[11] << 24);
 }
 
+// the procedural density field of a synthetic scene, evaluated per voxel on the device (grids too large to build on the host:
+// SURVEY.md 8d config 5, ~2048^3); same expressions as the host generator (vr_procedural.h)
+__global__ void k_procedural(vrestir_scene_params sp, float* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= sp.dim[0]) return;
+    const float u = ((float)x + 0.5f) / (float)sp.dim[0], v = ((float)y + 0.5f) / (float)sp.dim[1], w = ((float)z + 0.5f) / (float)sp.dim[2];
+    dst[((size_t)z * sp.dim[1] + y) * sp.dim[0] + x] = vr::shapeDensity(sp, u, v, w, nullptr, nullptr);
+}
+
 void freeChain(vrestir_mip_chain* c) {
     for (auto& kind : c->lev) for (auto& l : kind) { if (l.data) cudaFree(l.data); if (l.raw) cudaFree(l.raw); if (l.active) cudaFree(l.active); l.data = nullptr; l.raw = nullptr; l.active = nullptr; }
     if (c->maxBits) cudaFree(c->maxBits);
@@ -241,6 +251,19 @@ int vrestir_mips_build_device(int device, const float* dense_mip0, const int32_t
             if (c->lev[k][m].raw) { cudaFree(c->lev[k][m].raw); c->lev[k][m].raw = nullptr; }
         }
     *out = c;
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+
+int vrestir_make_procedural_device(int device, const vrestir_scene_params* sp, float* dense_out, void* stream) try {
+    if (!sp || !dense_out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (sp->dim[0] < 1 || sp->dim[1] < 1 || sp->dim[2] < 1 || sp->dim[1] > 65535 || sp->dim[2] > 65535) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad grid dimensions");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return setError(VRESTIR_ERR_CUDA, std::string("no CUDA device: the device generator has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= count) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad device index");
+    CKM(cudaSetDevice(device));
+    k_procedural<<<gridOf(Dim{sp->dim[0], sp->dim[1], sp->dim[2]}), 128, 0, (cudaStream_t)stream>>>(*sp, dense_out);
+    CKM(cudaGetLastError());
     return VRESTIR_OK;
 } catch (...) { return vr::caughtException(); }
 

@@ -43,7 +43,10 @@ using vr::setError;
 
 namespace {
 
-struct DevSlot { void* nodes[3] = {nullptr, nullptr, nullptr}; void* child[3] = {nullptr, nullptr, nullptr}; void* atlas = nullptr; size_t atlasBytes = 0; void* quads = nullptr; size_t quadBytes = 0; };
+struct DevSlot {
+    void* nodes[3] = {nullptr, nullptr, nullptr}; void* child[3] = {nullptr, nullptr, nullptr}; void* atlas = nullptr; size_t atlasBytes = 0; void* quads = nullptr; size_t quadBytes = 0;
+    vrestir_grid_slot meta{};   // what the slot was uploaded from, host pointers cleared (vrestir_download_volume)
+};
 
 struct KeyDesc { const char* name; size_t off; int type; };
 #define K_I(f) {#f, offsetof(vrestir_params, f), 0}
@@ -124,8 +127,10 @@ struct vrestir_pass {
     cudaEvent_t evMarch[3] = {}; bool evMarchValid = false;
                                                                       // evMarch: around the two march launches of the last spatial round
     cudaEvent_t evMainTail = nullptr; bool mainTailValid = false;   // recorded after every stage call: the constant banks are shared per device
-    cudaStream_t hostStream = nullptr;
-    float4* d_hostColor = nullptr; float2* d_hostMvec = nullptr; size_t hostColorPixels = 0;
+    // host-buffer path (vrestir_execute_host[_async]): two device frames, render on hostStream, read-back on hostCopyStream
+    cudaStream_t hostStream = nullptr, hostCopyStream = nullptr;
+    float4* d_hostColor[2] = {nullptr, nullptr}; float2* d_hostMvec[2] = {nullptr, nullptr}; size_t hostColorPixels = 0;
+    cudaEvent_t evHostRendered[2] = {nullptr, nullptr}, evHostLanded[2] = {nullptr, nullptr}; uint64_t hostSeq = 0;
     uint64_t launches = 0;
     vrestir_timings timings{};
     void* persistBase = nullptr; size_t persistBytes = 0; void* persistBasePf = nullptr; size_t persistBytesPf = 0;
@@ -302,15 +307,28 @@ int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStrea
         CK(cudaMemsetAsync(p->mbCounters, 0, 64, st));
         if (p->mDebugPoison) CK(cudaMemsetAsync(results, 0xFF, chunkPixels * stride * 4, st));
         CK(launchStageEmit(stage, fc, ms, cam, results, st)); p->launches++;
+        const bool timeMarches = stage == 3 && r0 == fp.rowBegin;   // the march launches of the (first chunk of the) spatial round: roofline input
+        if (timeMarches) {
+            for (auto& e : p->evMarch) if (!e) CK(cudaEventCreate(&e));
+            if (!p->wfCounters) CK(cudaMalloc(&p->wfCounters, 128));
+            CK(cudaEventRecord(p->evMarch[0], st));
+        }
         if (camTasks) {
             const MarchKind kc = {o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, 1, {fp.camPos.x, fp.camPos.y, fp.camPos.z}};
             CK(launchMarch(cam, results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st)); p->launches++;
         }
+        if (timeMarches) CK(cudaEventRecord(p->evMarch[1], st));
         for (int k = 0; k < ms.n; k++) {
             const MarchKind kk = {ms.mip[k], ms.linear[k], ms.scale[k], 0, {0.f, 0.f, 0.f}};
             if (ms.analytic[k]) CK(launchMarchAnalytic(ms.s[k], results, kk, p->scene.slots[kk.mip], p->analyticBlocks, st));
             else CK(launchMarch(ms.s[k], results, kk, p->scene.slots[kk.mip], 1, p->marchBlocks1, st));
             p->launches++;
+        }
+        if (timeMarches) {
+            CK(cudaEventRecord(p->evMarch[2], st));
+            p->evMarchValid = true;
+            CK(cudaMemcpyAsync(p->wfCounters + 8, p->mbCounters, 4, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(p->wfCounters + 9, p->mbCounters + 2, 4, cudaMemcpyDeviceToDevice, st));
         }
         CK(launchStageConsume(stage, fc, results, st)); p->launches++;
         p->mbChunks++;
@@ -322,7 +340,7 @@ void freeSlot(DevSlot& d) {
     for (int l = 0; l < 3; l++) { if (d.nodes[l]) cudaFree(d.nodes[l]); if (d.child[l]) cudaFree(d.child[l]); d.nodes[l] = d.child[l] = nullptr; }
     if (d.atlas) cudaFree(d.atlas);
     if (d.quads) cudaFree(d.quads);
-    d.atlas = nullptr; d.atlasBytes = 0; d.quads = nullptr; d.quadBytes = 0;
+    d.atlas = nullptr; d.atlasBytes = 0; d.quads = nullptr; d.quadBytes = 0; d.meta = vrestir_grid_slot{};
 }
 
 int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
@@ -362,6 +380,9 @@ int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
         d.atlasBytes = bytes;
     }
     s.atlas = d.atlas;
+    d.meta = g;
+    for (int l = 0; l < 3; l++) { d.meta.nodes[l] = nullptr; d.meta.childlist[l] = nullptr; }
+    d.meta.atlas = nullptr;
     s.quads = nullptr;
     if (bytes && g.atlas && g.atlas_format == VRESTIR_ATLAS_UNORM8 && g.atlas_channels == 1) {
         // device-only repack for trilinear fetches: per brick [10][9][9] words, word(z,y,x) = codes (x,y) (x+1,y) (x,y+1) (x+1,y+1) of plane z
@@ -1000,10 +1021,12 @@ int vrestir_destroy(vrestir_pass* p) try {
     for (auto& d : p->dslots) freeSlot(d);
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
     for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); if (p->feat[i]) cudaFree(p->feat[i]); }
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor, p->d_hostMvec, p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters, p->mbArena, p->mbCounters};
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor[0], p->d_hostColor[1], p->d_hostMvec[0], p->d_hostMvec[1], p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters, p->mbArena, p->mbCounters};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
+    if (p->hostCopyStream) cudaStreamDestroy(p->hostCopyStream);
+    for (cudaEvent_t e : {p->evHostRendered[0], p->evHostRendered[1], p->evHostLanded[0], p->evHostLanded[1]}) if (e) cudaEventDestroy(e);
     if (p->auxStream) cudaStreamDestroy(p->auxStream);
     if (p->evFork) cudaEventDestroy(p->evFork);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
@@ -1123,6 +1146,36 @@ int vrestir_set_volume_from_chain(vrestir_pass* p, const vrestir_mip_chain* chai
     p->haveVolume = true; p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr;
     if (!advance) p->mOptionsChanged = true;
     applyOverrides(p);
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+
+// Host copy of the volume as it is bound on the device (nodes with the device-computed brick bounds, child lists, brick pools):
+// what a checker needs to evaluate the same grid on the CPU when the grid was built on the device (vrestir_set_volume_from_chain).
+int vrestir_download_volume(vrestir_pass* p, vrestir_scene** out) try {
+    if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!p->haveVolume) return setError(VRESTIR_ERR_NOT_READY, "no volume bound");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    vrestir_scene* sc = vr::newHostScene(p->volBase);
+    for (int slot = 0; slot < VRESTIR_MAX_SLOTS; slot++) {
+        const DevSlot& d = p->dslots[slot];
+        if (!p->scene.slots[slot].valid) continue;
+        vr::HostSlotVectors h = vr::hostSlotVectors(sc, slot);
+        *h.desc = d.meta;
+        for (int l = 0; l < 3; l++) {
+            h.nodes[l]->resize(d.meta.node_count[l]);
+            if (d.meta.node_count[l] && d.nodes[l]) CK(cudaMemcpy(h.nodes[l]->data(), d.nodes[l], (size_t)d.meta.node_count[l] * sizeof(vrestir_node), cudaMemcpyDeviceToHost));
+            h.child[l]->resize(d.meta.childlist_count[l]);
+            if (d.meta.childlist_count[l] && d.child[l]) CK(cudaMemcpy(h.child[l]->data(), d.child[l], (size_t)d.meta.childlist_count[l] * 4, cudaMemcpyDeviceToHost));
+            h.desc->nodes[l] = h.nodes[l]->empty() ? nullptr : h.nodes[l]->data();
+            h.desc->childlist[l] = h.child[l]->empty() ? nullptr : h.child[l]->data();
+        }
+        h.atlas->resize(d.atlasBytes);
+        if (d.atlasBytes) CK(cudaMemcpy(h.atlas->data(), d.atlas, d.atlasBytes, cudaMemcpyDeviceToHost));
+        h.desc->atlas = h.atlas->empty() ? nullptr : h.atlas->data();
+    }
+    if (p->d_lut) vr::attachBlackbodyLut(sc);
+    *out = sc;
     return VRESTIR_OK;
 } catch (...) { return vr::caughtException(); }
 
@@ -1347,27 +1400,50 @@ int vrestir_execute(vrestir_pass* p, float* out_color, float* out_mvec, void* st
     return VRESTIR_OK;
 } catch (...) { return vr::caughtException(); }
 
-int vrestir_execute_host(vrestir_pass* p, float* out_color_host, float* out_mvec_host) try {
+// Host-buffer entry points: what a CPU-side caller of the plugin sees.  The frame renders into one of two device images on the
+// pass's own stream; its read-back into the caller's buffer runs on a copy stream, so with the _async form the next frame
+// renders while the previous one travels (pinned host memory makes the copy truly asynchronous).
+int vrestir_execute_host_async(vrestir_pass* p, float* out_color_host, float* out_mvec_host) try {
     if (!p || !out_color_host) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set");
     CK(cudaSetDevice(p->device));
-    if (!p->hostStream) CK(cudaStreamCreateWithFlags(&p->hostStream, cudaStreamNonBlocking));
+    if (!p->hostStream) {
+        CK(cudaStreamCreateWithFlags(&p->hostStream, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&p->hostCopyStream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&p->evHostRendered[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->evHostLanded[i], cudaEventDisableTiming)); }
+    }
     const size_t n = N(p);
     if (p->hostColorPixels != n) {
-        if (p->d_hostColor) cudaFree(p->d_hostColor);
-        if (p->d_hostMvec) cudaFree(p->d_hostMvec);
-        CK(cudaMalloc(&p->d_hostColor, n * 16)); CK(cudaMalloc(&p->d_hostMvec, n * 8));
-        CK(cudaMemsetAsync(p->d_hostColor, 0, n * 16, p->hostStream)); CK(cudaMemsetAsync(p->d_hostMvec, 0, n * 8, p->hostStream));
-        p->hostColorPixels = n;
+        CK(cudaStreamSynchronize(p->hostStream)); CK(cudaStreamSynchronize(p->hostCopyStream));
+        for (int i = 0; i < 2; i++) {
+            if (p->d_hostColor[i]) cudaFree(p->d_hostColor[i]);
+            if (p->d_hostMvec[i]) cudaFree(p->d_hostMvec[i]);
+            CK(cudaMalloc(&p->d_hostColor[i], n * 16)); CK(cudaMalloc(&p->d_hostMvec[i], n * 8));
+            CK(cudaMemsetAsync(p->d_hostColor[i], 0, n * 16, p->hostStream)); CK(cudaMemsetAsync(p->d_hostMvec[i], 0, n * 8, p->hostStream));
+        }
+        p->hostColorPixels = n; p->hostSeq = 0;
     }
-    int rc = vrestir_execute(p, (float*)p->d_hostColor, out_mvec_host ? (float*)p->d_hostMvec : nullptr, p->hostStream);
+    const int b = (int)(p->hostSeq & 1);
+    if (p->hostSeq >= 2) CK(cudaStreamWaitEvent(p->hostStream, p->evHostLanded[b], 0));   // the device image is free once its last read-back landed
+    int rc = vrestir_execute(p, (float*)p->d_hostColor[b], out_mvec_host ? (float*)p->d_hostMvec[b] : nullptr, p->hostStream);
     if (rc) return rc;
-    if ((rc = vrestir_wait_output(p, p->hostStream))) return rc;
+    CK(cudaEventRecord(p->evHostRendered[b], p->hostStream));
+    CK(cudaStreamWaitEvent(p->hostCopyStream, p->evHostRendered[b], 0));
+    if ((rc = vrestir_wait_output(p, p->hostCopyStream))) return rc;                         // deferred final shading (mPipelineFrames 2)
     const size_t off = (size_t)p->rowBegin * p->W, cnt = (size_t)(p->rowEnd - p->rowBegin) * p->W;
-    CK(cudaMemcpyAsync(out_color_host + off * 4, p->d_hostColor + off, cnt * 16, cudaMemcpyDeviceToHost, p->hostStream));
-    if (out_mvec_host) CK(cudaMemcpyAsync(out_mvec_host + off * 2, p->d_hostMvec + off, cnt * 8, cudaMemcpyDeviceToHost, p->hostStream));
-    CK(cudaStreamSynchronize(p->hostStream));
+    CK(cudaMemcpyAsync(out_color_host + off * 4, p->d_hostColor[b] + off, cnt * 16, cudaMemcpyDeviceToHost, p->hostCopyStream));
+    if (out_mvec_host) CK(cudaMemcpyAsync(out_mvec_host + off * 2, p->d_hostMvec[b] + off, cnt * 8, cudaMemcpyDeviceToHost, p->hostCopyStream));
+    CK(cudaEventRecord(p->evHostLanded[b], p->hostCopyStream));
+    p->hostSeq++;
     return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+int vrestir_host_wait(vrestir_pass* p) try {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null pass");
+    if (p->hostCopyStream) { CK(cudaSetDevice(p->device)); CK(cudaStreamSynchronize(p->hostCopyStream)); }
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+int vrestir_execute_host(vrestir_pass* p, float* out_color_host, float* out_mvec_host) try {
+    const int rc = vrestir_execute_host_async(p, out_color_host, out_mvec_host);
+    return rc ? rc : vrestir_host_wait(p);
 } catch (...) { return vr::caughtException(); }
 
 int vrestir_get_timings(vrestir_pass* p, vrestir_timings* out) try {

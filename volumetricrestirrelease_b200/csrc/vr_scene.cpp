@@ -11,6 +11,7 @@
 // node.pos / node.link instead of 16-bit packed pos/value) are described in include/vrestir.h and DESIGN.md.
 #include "../../include/vrestir.h"
 #include "vr_host.h"
+#include "vr_procedural.h"
 
 #include <algorithm>
 #include <atomic>
@@ -38,35 +39,6 @@ template <class F> static void parallelFor(int n, F f) {
     for (auto& t : th) t.join();
 }
 
-static inline uint32_t hash3(int x, int y, int z, uint32_t seed) {
-    uint32_t h = seed * 0x9E3779B1u + 0x7F4A7C15u;
-    h ^= (uint32_t)x * 0x85EBCA6Bu; h = (h << 13) | (h >> 19); h *= 0xC2B2AE35u;
-    h ^= (uint32_t)y * 0x27D4EB2Fu; h = (h << 15) | (h >> 17); h *= 0x165667B1u;
-    h ^= (uint32_t)z * 0x9E3779B1u; h = (h << 11) | (h >> 21); h *= 0x85EBCA77u;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
-    return h;
-}
-static inline float lattice(int x, int y, int z, uint32_t seed) { return (float)(hash3(x, y, z, seed) >> 8) * (1.0f / 16777216.0f); }
-static inline float smooth(float t) { return t * t * (3.f - 2.f * t); }
-static float valueNoise(float x, float y, float z, uint32_t seed) {
-    float fx = std::floor(x), fy = std::floor(y), fz = std::floor(z);
-    int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-    float tx = smooth(x - fx), ty = smooth(y - fy), tz = smooth(z - fz);
-    float c[8];
-    for (int i = 0; i < 8; i++) c[i] = lattice(ix + (i & 1), iy + ((i >> 1) & 1), iz + (i >> 2), seed);
-    float x00 = c[0] + tx * (c[1] - c[0]), x10 = c[2] + tx * (c[3] - c[2]), x01 = c[4] + tx * (c[5] - c[4]), x11 = c[6] + tx * (c[7] - c[6]);
-    float y0 = x00 + ty * (x10 - x00), y1 = x01 + ty * (x11 - x01);
-    return y0 + tz * (y1 - y0);
-}
-static float fbm(float x, float y, float z, uint32_t seed, int octaves = 5) {
-    float sum = 0.f, amp = 0.5f, norm = 0.f;
-    for (int o = 0; o < octaves; o++) {
-        sum += amp * valueNoise(x, y, z, seed + 101u * (uint32_t)o);
-        norm += amp; amp *= 0.5f; x *= 2.f; y *= 2.f; z *= 2.f;
-    }
-    return sum / norm;
-}
-
 struct Dense {
     int nx = 0, ny = 0, nz = 0, ch = 1;
     std::vector<float> v;   // [ch][z][y][x]
@@ -77,69 +49,6 @@ struct Dense {
     }
 };
 
-// ------------------------------------------------------------------------------------------------ procedural fields
-static float ellipsoid(float x, float y, float z, float cx, float cy, float cz, float rx, float ry, float rz) {
-    float dx = (x - cx) / rx, dy = (y - cy) / ry, dz = (z - cz) / rz;
-    return 1.f - std::sqrt(dx * dx + dy * dy + dz * dz);   // > 0 inside
-}
-static float shapeDensity(const vrestir_scene_params& sp, float u, float v, float w, float* temperature, float vel[3]) {
-    // (u,v,w) in [0,1]^3 over the grid; returns density in [0,1]
-    const uint32_t seed = sp.seed;
-    const float f = 6.f;
-    switch (sp.kind) {
-        case 0: {   // sphere (radius 0.375 of the box) x fBm, SURVEY.md 8(d) config 1
-            float dx = u - 0.5f, dy = v - 0.5f, dz = w - 0.5f;
-            float r = std::sqrt(dx * dx + dy * dy + dz * dz);
-            if (r > 0.375f) return 0.f;
-            float n = fbm(u * f, v * f, w * f, seed);
-            float edge = std::min(1.f, (0.375f - r) * 16.f);
-            return std::max(0.f, n - 0.35f) / 0.65f * edge;
-        }
-        case 1: {   // bunny-cloud-like blob: body + head + two ears, eroded by fBm
-            float s = -1.f;
-            s = std::max(s, ellipsoid(u, v, w, 0.50f, 0.36f, 0.52f, 0.36f, 0.30f, 0.34f));
-            s = std::max(s, ellipsoid(u, v, w, 0.30f, 0.62f, 0.50f, 0.20f, 0.19f, 0.21f));
-            s = std::max(s, ellipsoid(u, v, w, 0.27f, 0.85f, 0.40f, 0.065f, 0.16f, 0.08f));
-            s = std::max(s, ellipsoid(u, v, w, 0.30f, 0.85f, 0.61f, 0.065f, 0.16f, 0.08f));
-            s = std::max(s, ellipsoid(u, v, w, 0.82f, 0.30f, 0.52f, 0.10f, 0.10f, 0.10f));
-            if (s < -0.25f) return 0.f;
-            float n = fbm(u * 7.f, v * 7.f, w * 7.f, seed);
-            float d = s * 2.2f + (n - 0.5f) * 1.1f;
-            return std::min(1.f, std::max(0.f, d) * 2.5f);
-        }
-        case 2: {   // plume: rising turbulent column, advected upward with frame_time
-            float t = sp.frame_time;
-            float cx = 0.5f + 0.06f * std::sin(6.f * v + 0.7f * t), cz = 0.5f + 0.06f * std::cos(5.f * v + 0.9f * t);
-            float rad = 0.07f + 0.22f * v;
-            float dx = u - cx, dz = w - cz;
-            float r = std::sqrt(dx * dx + dz * dz) / rad;
-            float rise = std::min(1.f, 0.25f + 0.05f * t);
-            float body = (r < 1.f && v < rise) ? (1.f - r) : 0.f;
-            float n = fbm(u * 8.f, (v - 0.04f * t) * 8.f, w * 8.f, seed);
-            float d = body * std::max(0.f, n - 0.3f) * 2.4f * std::min(1.f, (rise - v) * 12.f);
-            d = std::min(1.f, std::max(0.f, d));
-            if (temperature) *temperature = d > 0.f ? 2000.f * std::max(0.f, 1.f - v / std::max(rise, 1e-3f)) * std::min(1.f, d * 3.f) : 0.f;
-            if (vel) {   // curl-like swirl + rise, |v| <= 2 voxels / frame (index units of mip 0)
-                float sw = 1.2f * (n - 0.5f);
-                vel[0] = d > 0.f ? -dz / std::max(rad, 1e-3f) * sw : 0.f;
-                vel[1] = d > 0.f ? 1.5f * (1.f - 0.5f * r) : 0.f;
-                vel[2] = d > 0.f ? dx / std::max(rad, 1e-3f) * sw : 0.f;
-            }
-            return d;
-        }
-        case 3: {   // dense cloud filling most of the box
-            float n = fbm(u * 5.f, v * 5.f, w * 5.f, seed);
-            float bx = std::min(std::min(u, 1.f - u), std::min(std::min(v, 1.f - v), std::min(w, 1.f - w)));
-            float edge = std::min(1.f, bx * 12.f);
-            return std::min(1.f, std::max(0.f, n - 0.38f) * 3.0f) * edge;
-        }
-        default: {  // thin fBm shells
-            float n = fbm(u * 10.f, v * 10.f, w * 10.f, seed, 4);
-            float sh = 1.f - std::fabs(n - 0.5f) * 60.f;
-            return std::max(0.f, sh);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------ mip chain
 // conservative mip 0: zero voxels take the mean of their positive 27-neighbourhood (GV/.../gvdb_volume_gvdb.cpp:2753-2801)
@@ -366,6 +275,27 @@ static void setTransforms(vrestir_scene& s, int slot, const int dim0[3], const i
     }
 }
 
+// VolumeDesc (F/Scene/Scene.cpp:3246-3298)
+static void fillVolumeDesc(vrestir_scene& sc, int builtMips, bool temperature, bool velocity) {
+    vrestir_scene* s = &sc;
+    const vrestir_scene_params* p = &sc.params;
+    vrestir_volume_desc& v = s->desc.volume;
+    for (int i = 0; i < 3; i++) { v.sigma_a[i] = p->sigma_a[i]; v.sigma_s[i] = p->sigma_s[i]; }
+    v.sigma_t = p->sigma_s[0] + p->sigma_a[0];
+    v.PhaseFunctionConstantG = p->g;
+    v.densityScaleFactor = p->density_scale;
+    v.densityScaleFactorByScaling = p->density_scale / p->world_scaling;
+    const float* X = s->desc.slots[0].xform;
+    auto len3 = [](const float* r) { return std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); };
+    v.tStep = (len3(X) + len3(X + 4) + len3(X + 8)) / 3.f;
+    v.hasEmission = temperature ? 1 : 0; v.hasVelocity = velocity ? 1 : 0; v.hasAnimation = 0; v.lastFrameHasEmission = 0;
+    v.LeScale = p->LeScale; v.temperatureCutOff = p->temperatureCutOff; v.temperatureScale = p->temperatureScale;
+    v.velocityScale = 1.f; v.numMips = builtMips; v.usePrevGridForReproj = 0;
+    v.volumeWorldScaling = p->world_scaling;
+    v.superVoxelWorldSpaceDiagonalLength = 8.f * std::sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2] + X[4] * X[4] + X[5] * X[5] + X[6] * X[6] + X[8] * X[8] + X[9] * X[9] + X[10] * X[10]);
+    if (temperature) { s->lut.resize(512); vrestir_make_blackbody_lut(s->lut.data()); s->desc.blackbody_lut = s->lut.data(); }
+}
+
 static int buildScene(const vrestir_scene_params* p, Dense&& density, Dense* temperature, Dense* velocity, vrestir_scene** out) {
     auto* s = new vrestir_scene();
     s->params = *p;
@@ -396,22 +326,7 @@ static int buildScene(const vrestir_scene_params* p, Dense&& density, Dense* tem
         buildSlot(*velocity, VRESTIR_ATLAS_F32, false, s->slots[VRESTIR_VELOCITY_GRID_ID], s->desc.slots[VRESTIR_VELOCITY_GRID_ID]);
         setTransforms(*s, VRESTIR_VELOCITY_GRID_ID, dim0, dim0);
     }
-    // VolumeDesc (F/Scene/Scene.cpp:3246-3298)
-    vrestir_volume_desc& v = s->desc.volume;
-    for (int i = 0; i < 3; i++) { v.sigma_a[i] = p->sigma_a[i]; v.sigma_s[i] = p->sigma_s[i]; }
-    v.sigma_t = p->sigma_s[0] + p->sigma_a[0];
-    v.PhaseFunctionConstantG = p->g;
-    v.densityScaleFactor = p->density_scale;
-    v.densityScaleFactorByScaling = p->density_scale / p->world_scaling;
-    const float* X = s->desc.slots[0].xform;
-    auto len3 = [](const float* r) { return std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); };
-    v.tStep = (len3(X) + len3(X + 4) + len3(X + 8)) / 3.f;
-    v.hasEmission = temperature ? 1 : 0; v.hasVelocity = velocity ? 1 : 0; v.hasAnimation = 0; v.lastFrameHasEmission = 0;
-    v.LeScale = p->LeScale; v.temperatureCutOff = p->temperatureCutOff; v.temperatureScale = p->temperatureScale;
-    v.velocityScale = 1.f; v.numMips = builtMips; v.usePrevGridForReproj = 0;
-    v.volumeWorldScaling = p->world_scaling;
-    v.superVoxelWorldSpaceDiagonalLength = 8.f * std::sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2] + X[4] * X[4] + X[5] * X[5] + X[6] * X[6] + X[8] * X[8] + X[9] * X[9] + X[10] * X[10]);
-    if (temperature) { s->lut.resize(512); vrestir_make_blackbody_lut(s->lut.data()); s->desc.blackbody_lut = s->lut.data(); }
+    fillVolumeDesc(*s, builtMips, temperature != nullptr, velocity != nullptr);
     *out = s;
     return VRESTIR_OK;
 }
@@ -443,6 +358,41 @@ int vrestir_scene_create(const vrestir_scene_params* p, vrestir_scene** out) try
     return buildScene(p, std::move(d), wt ? &T : nullptr, wv ? &V : nullptr, out);
 } catch (...) { return vr::caughtException(); }
 
+// A scene description without voxels: dimensions, formats, transforms and the volume description of every density level —
+// the template vrestir_set_volume_from_chain needs when the grid itself only ever exists on the device.
+int vrestir_scene_create_template(const vrestir_scene_params* p, vrestir_scene** out) try {
+    if (!p || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (p->dim[0] < 8 || p->dim[1] < 8 || p->dim[2] < 8 || p->dim[0] > 4096 || p->dim[1] > 4096 || p->dim[2] > 4096)
+        return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "grid dimensions must be in [8, 4096]");
+    auto* s = new vrestir_scene();
+    s->params = *p;
+    const int dim0[3] = {p->dim[0], p->dim[1], p->dim[2]};
+    const int numMips = std::max(1, std::min(VRESTIR_NUM_MAX_MIPS, p->num_mips));
+    int d[3] = {dim0[0], dim0[1], dim0[2]};
+    int built = 0;
+    for (int m = 0; m < numMips; m++) {
+        for (int c = 0; c < 2; c++) {
+            const int slot = m + c * VRESTIR_NUM_MAX_MIPS;
+            vrestir_grid_slot& g = s->desc.slots[slot];
+            g = vrestir_grid_slot{};
+            g.valid = 1; g.top_lev = ((d[0] + 127) / 128) * ((d[1] + 127) / 128) * ((d[2] + 127) / 128) > 1 ? 2 : 1;
+            g.dim[0] = 3; g.dim[1] = 4; g.dim[2] = 5; g.res[0] = 8; g.res[1] = 16; g.res[2] = 32;
+            g.vdel[0] = 1.f; g.vdel[1] = 8.f; g.vdel[2] = 128.f; g.noderange[0] = 8; g.noderange[1] = 128; g.noderange[2] = 4096;
+            g.bmax[0] = (float)d[0]; g.bmax[1] = (float)d[1]; g.bmax[2] = (float)d[2];
+            g.max_value = 1.f; g.compress_scale = 1.f;
+            g.atlas_format = (m == 0 && c == 0) ? VRESTIR_ATLAS_F32 : VRESTIR_ATLAS_UNORM8; g.atlas_channels = 1;
+            setTransforms(*s, slot, dim0, d);
+        }
+        built = m + 1;
+        if (d[0] < 2 || d[1] < 2 || d[2] < 2) break;
+        for (int a = 0; a < 3; a++) d[a] = std::max(1, d[a] / 2);
+    }
+    s->params.num_mips = built;
+    fillVolumeDesc(*s, built, false, false);
+    *out = s;
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+
 int vrestir_scene_create_from_dense(const vrestir_scene_params* p, const float* density, const float* temperature, const float* velocity_xyz, vrestir_scene** out) try {
     if (!p || !density || !out) return vr::setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (p->dim[0] < 1 || p->dim[1] < 1 || p->dim[2] < 1 || p->dim[0] > 4096 || p->dim[1] > 4096 || p->dim[2] > 4096)
@@ -456,6 +406,19 @@ int vrestir_scene_create_from_dense(const vrestir_scene_params* p, const float* 
     }
     return buildScene(p, std::move(d), temperature ? &T : nullptr, velocity_xyz ? &V : nullptr, out);
 } catch (...) { return vr::caughtException(); }
+
+}  // extern "C"
+namespace vr {
+// host copy of a device-resident volume (vrestir_download_volume in vr_pass.cu): the caller fills the vectors of each slot
+vrestir_scene* newHostScene(const vrestir_volume_desc& vol) { auto* s = new vrestir_scene(); s->desc.volume = vol; return s; }
+HostSlotVectors hostSlotVectors(vrestir_scene* s, int slot) {
+    BuiltSlot& b = s->slots[slot];
+    b.used = true;
+    return HostSlotVectors{{&b.nodes[0], &b.nodes[1], &b.nodes[2]}, {&b.child[0], &b.child[1], &b.child[2]}, &b.atlas, &s->desc.slots[slot]};
+}
+void attachBlackbodyLut(vrestir_scene* s) { s->lut.resize(512); vrestir_make_blackbody_lut(s->lut.data()); s->desc.blackbody_lut = s->lut.data(); }
+}  // namespace vr
+extern "C" {
 
 int vrestir_scene_destroy(vrestir_scene* s) { delete s; return VRESTIR_OK; }
 const vrestir_grid_desc* vrestir_scene_grid(const vrestir_scene* s) { return s ? &s->desc : nullptr; }

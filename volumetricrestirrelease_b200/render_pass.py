@@ -122,7 +122,10 @@ class VolumetricReSTIR:
         self._frame = (int(width), int(height))
         L = self._lib
         capi.check(L.vrestir_set_frame(self._h, int(width), int(height), int(row_begin), int(height if row_end is None else row_end)))
-        capi.check(L.vrestir_set_volume(self._h, scene.volume.grid))
+        if getattr(scene.volume, "chain", None) is not None:     # device-built volume: bind the GPU chain over the voxel-less template
+            capi.check(L.vrestir_set_volume_from_chain(self._h, scene.volume.chain._h, scene.volume.grid, 0))
+        else:
+            capi.check(L.vrestir_set_volume(self._h, scene.volume.grid))
         self.updateCamera()
         env = scene.envmap_desc()
         if env is not None:
@@ -149,6 +152,13 @@ class VolumetricReSTIR:
         ``advance=True`` = ``advanceVolume`` semantics (current grids become the previous frame's)."""
         tmpl = (template or self._scene.volume).grid
         capi.check(self._lib.vrestir_set_volume_from_chain(self._h, chain._h, tmpl, int(advance)))
+
+    def downloadVolume(self):
+        """Host copy (a scene ``Volume``) of the grids bound on the device, e.g. to hand a device-built volume to a CPU checker."""
+        from .scene import Volume
+        h = C.c_void_p()
+        capi.check(self._lib.vrestir_download_volume(self._h, C.byref(h)))
+        return Volume(h)
 
     def setNextCamera(self, camera=None):
         """Frame pipelining ("mPipelineFrames"): announce the camera of the NEXT frame before executing the current one, so that
@@ -196,6 +206,14 @@ class VolumetricReSTIR:
         capi.check(self._lib.vrestir_execute_host(self._h, out_color.ctypes.data,
                                                   out_mvec.ctypes.data if out_mvec is not None else None))
         return out_color
+
+    def execute_host_async(self, out_color_ptr, out_mvec_ptr=None):
+        """Host-buffer path without blocking: `out_color_ptr` is the address of a (pinned) host buffer of width*height float4;
+        the read-back of this frame overlaps the next frame.  Call host_wait() before reading the buffer."""
+        capi.check(self._lib.vrestir_execute_host_async(self._h, C.c_void_p(out_color_ptr), C.c_void_p(out_mvec_ptr) if out_mvec_ptr else None))
+
+    def host_wait(self):
+        capi.check(self._lib.vrestir_host_wait(self._h))
 
     # ------------------------------------------------------------------------------------------------ introspection
     def timings(self):

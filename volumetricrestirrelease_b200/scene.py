@@ -64,7 +64,16 @@ class Volume:
         """Write every grid of the volume as GVDB .vbx files (<prefix>_mip<k>[c].vbx, _temperature.vbx, _velocity_{x,y,z}.vbx)."""
         capi.check(capi.lib().vrestir_scene_save_vbx(self._h, str(dir_and_prefix).encode()))
 
+    def release_chain(self):
+        """Device-built volumes: free the dense mip chain (tens of GB for a 2048^3 grid) once a pass has bound its brick pools."""
+        ch = getattr(self, "chain", None)
+        if ch is not None:
+            ch.close()
+            self.chain = None
+        self.dense = None
+
     def close(self):
+        self.release_chain()
         if self._h:
             capi.lib().vrestir_scene_destroy(self._h)
             self._h = None
@@ -141,6 +150,29 @@ class Scene:
             capi.check(capi.lib().vrestir_scene_create(C.byref(sp), C.byref(h)))
         self.volume = Volume(h)
         return self.volume
+
+    def addGVDBVolumeDevice(self, device=0, sigma_a=(1, 1, 1), sigma_s=(9, 9, 9), g=0.0, dataFile="shells", numMips=4, densityScale=1.0,
+                            worldTranslation=(0, 0, 0), worldScaling=1.0, dim=(2048, 2048, 2048), seed=5, voxelSize=1.0, keep_dense=False):
+        """A procedural volume that only ever exists on the GPU (grids too large for the host builder):
+        the density field is evaluated per voxel on the device, the mip / conservative-mip chain is built there
+        (``mipbuild.build_mips``) and ``VolumetricReSTIR.setScene`` binds it with ``vrestir_set_volume_from_chain``.
+        ``self.volume`` is a voxel-less template (dimensions, transforms, VolumeDesc) carrying the chain."""
+        import torch
+        from .mipbuild import build_mips
+        sp = _scene_params(dataFile, dim, numMips, seed, sigma_a, sigma_s, g, densityScale, voxelSize, worldTranslation, worldScaling,
+                           False, False, 0.005, 1.0, 100.0, 0.0)
+        h = C.c_void_p()
+        capi.check(capi.lib().vrestir_scene_create_template(C.byref(sp), C.byref(h)))
+        vol = Volume(h)
+        dev = torch.device("cuda", device)
+        dense = torch.empty((int(dim[2]), int(dim[1]), int(dim[0])), dtype=torch.float32, device=dev)
+        capi.check(capi.lib().vrestir_make_procedural_device(int(device), C.byref(sp), C.c_void_p(dense.data_ptr()), None))
+        torch.cuda.synchronize(dev)
+        vol.chain = build_mips(dense, numMips)
+        vol.dense = dense if keep_dense else None
+        del dense
+        self.volume = vol
+        return vol
 
     def loadGVDBVolume(self, dir_and_prefix, sigma_a=(1, 1, 1), sigma_s=(9, 9, 9), g=0.0, numMips=4, densityScale=1.0,
                        LeScale=0.005, temperatureCutoff=1.0, temperatureScale=100.0, worldTranslation=(0, 0, 0),
