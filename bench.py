@@ -286,9 +286,10 @@ def parity_with_history(gp, scene, params, W, H, color, oracle_scene=None):
     reuse = bool(params.mEnableTemporalReuse)
     op.execute_stage(6, 0, c0)
     op.set_frame_count(gp.frame_count(), 1)
+    history = {}
     if reuse:
         for b in (capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL) + ((capi.BUF_EXTRA_TEMPORAL,) if B > 1 else ()):
-            op.set_buffer(b, gp.get_buffer(b))
+            history[b] = gp.get_buffer(b).copy()
     fc = gp.frame_count()
     gp.execute(color.data_ptr()); torch.cuda.synchronize()
     g = color.cpu().numpy()
@@ -299,8 +300,11 @@ def parity_with_history(gp, scene, params, W, H, color, oracle_scene=None):
     crops = [(W // 2 - T // 2, H // 2 - T // 2), (max(0, W // 2 - int(0.22 * W)), max(0, H // 2 - int(0.19 * H)))]
     num = den = 0.0
     gs, cs, flips, px = [], [], 0, 0
+    fields = {}
     for x0, y0 in crops:
         op.set_frame_count(fc, 1)
+        for b, raw in history.items():      # the oracle's history copies (K4, feature copy) are whole-buffer: hand the GPU's history over per crop
+            op.set_buffer(b, raw)
         for stage in (0, 1, 2):
             op.set_crop(x0 - halo, y0 - halo, x0 + T + halo, y0 + T + halo)
             op.execute_stage(stage, 0, c0)
@@ -313,11 +317,13 @@ def parity_with_history(gp, scene, params, W, H, color, oracle_scene=None):
         f = (a["lightID"] != cres["lightID"]) | (a["sampledPixel"] != cres["sampledPixel"]) | (a["M"] != cres["M"])
         f |= ~np.isclose(a["depth"], cres["depth"], rtol=1e-5, atol=0) & ~(a["depth"] == cres["depth"])
         flips += int(f.sum()); px += f.size
+        per_field = {k: int((a[k] != cres[k]).sum()) for k in ("lightID", "sampledPixel", "M", "depth")}
+        fields = {k: fields.get(k, 0) + v for k, v in per_field.items()}
     ga, ca = np.concatenate(gs), np.concatenate(cs)
     eps = 1e-2 * np.mean(ca) ** 2
     relmse = float(np.mean((ga - ca) ** 2 / (ca ** 2 + eps)))
     rel = np.abs(ga - ca) / np.maximum(np.abs(ca), 1e-6)
-    return {"relmse_vs_oracle": relmse, "flip_frac": flips / max(1, px), "frac_pixels_rel_err_gt_1e-4": float((rel.max(axis=-1) > 1e-4).mean()),
+    return {"relmse_vs_oracle": relmse, "flip_frac": flips / max(1, px), "pixels_with_differing_field": fields, "frac_pixels_rel_err_gt_1e-4": float((rel.max(axis=-1) > 1e-4).mean()),
             "frame": int(fc), "crops": [[x0, y0, T, T] for x0, y0 in crops], "mean_gpu": float(ga.mean()), "mean_oracle": float(ca.mean())}
 
 

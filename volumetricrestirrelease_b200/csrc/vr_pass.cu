@@ -66,6 +66,8 @@ const KeyDesc kKeys[] = {
 
 }  // namespace
 
+struct ScratchArena { void* base = nullptr; size_t bytes = 0; unsigned* counters = nullptr; };
+
 struct vrestir_pass {
     int device = 0;
     vrestir_params P{};
@@ -91,7 +93,7 @@ struct vrestir_pass {
     int W = 0, H = 0, rowBegin = 0, rowEnd = 0;
     int allocW = 0, allocH = 0, allocB = 0;
     float4* res[4] = {nullptr, nullptr, nullptr, nullptr};
-    float3* ext[3] = {nullptr, nullptr, nullptr};
+    float3* ext[4] = {nullptr, nullptr, nullptr, nullptr};
     int2* feat[3] = {nullptr, nullptr, nullptr};
     float4* refColor = nullptr;
     int ia = 0, ib = 1, it = 2, in = 3;   // physical indices of ping-pong buffers 0/1, the temporal history and the prefetch target
@@ -143,7 +145,10 @@ struct vrestir_pass {
     float* wfInitialState = nullptr; size_t wfInitialPixels = 0;   // lock-step wavefront K1
     // generic task-stream path (multi-bounce option sets): one grow-only arena {tasks | results}, carved per stage and per row chunk
     void* mbArena = nullptr; size_t mbArenaBytes = 0; unsigned* mbCounters = nullptr;
+    ScratchArena k1mb, k1mbEval;   // multi-bounce K1 owns its scratch (it may run on the prefetch stream next to the other stages)
     size_t mScratchBudget = (size_t)4 << 30;   // "mScratchBudgetMB": a stage whose worst-case task scratch exceeds this runs in row chunks
+    // march launches of the last spatial round when it ran in row chunks (generic path): one event triple + task counts per chunk
+    std::vector<cudaEvent_t> evMarchChunks; int marchChunksUsed = 0; unsigned* d_marchCounts = nullptr;
     uint64_t mbChunks = 0; bool mDebugPoison = false;   // "mDebugPoisonResults": result blocks start as NaN, so a march the emit pass missed shows up in the image
 };
 
@@ -160,11 +165,11 @@ int ensureBuffers(vrestir_pass* p) {
     if (p->outStream) CK(cudaStreamSynchronize(p->outStream));
     p->pfValid = false;
     for (int i = 0; i < 4; i++) { if (p->res[i]) cudaFree(p->res[i]); p->res[i] = nullptr; }
-    for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); p->ext[i] = nullptr; }
+    for (int i = 0; i < 4; i++) { if (p->ext[i]) cudaFree(p->ext[i]); p->ext[i] = nullptr; }
     for (int i = 0; i < 3; i++) { if (p->feat[i]) cudaFree(p->feat[i]); p->feat[i] = nullptr; }
     if (p->refColor) { cudaFree(p->refColor); p->refColor = nullptr; }
     for (int i = 0; i < 4; i++) { CK(cudaMalloc(&p->res[i], n * 32)); CK(cudaMemset(p->res[i], 0, n * 32)); }
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 4; i++) {   // one per reservoir buffer (ping, pong, history, prefetch target)
         if (B > 1) { CK(cudaMalloc(&p->ext[i], n * (size_t)(B - 1) * 12)); CK(cudaMemset(p->ext[i], 0, n * (size_t)(B - 1) * 12)); }
     }
     for (int i = 0; i < 3; i++) { CK(cudaMalloc(&p->feat[i], n * 8)); CK(cudaMemset(p->feat[i], 0, n * 8)); }
@@ -233,7 +238,18 @@ bool genericStageOk(const vrestir_pass* p, int stage) {
 struct MarchRole { int mip, linear; float scale; uint32_t method; int perPixel; };
 
 // One stage (2 temporal, 3 spatial, 5 final) over the band of `fp`, in row chunks whose worst-case scratch fits the budget.
-int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStream_t st) {
+int growArena(ScratchArena& a, size_t need, cudaStream_t st) {
+    if (a.bytes < need) {
+        CK(cudaStreamSynchronize(st));
+        if (a.base) cudaFree(a.base);
+        a.base = nullptr; a.bytes = 0;
+        CK(cudaMalloc(&a.base, need));
+        a.bytes = need;
+    }
+    if (!a.counters) CK(cudaMalloc(&a.counters, 64));
+    return VRESTIR_OK;
+}
+int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStream_t st, ScratchArena* arenaOverride = nullptr, size_t reservedBytesPerPixel = 0, int forcedChunkRows = 0) {
     const vrestir_params& m = p->P;
     const int B = m.mMaxBounces;
     const bool prevGrid = p->scene.vol.usePrevGridForReproj && p->scene.vol.hasAnimation;
@@ -242,7 +258,11 @@ int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStrea
     std::vector<MarchRole> roles;
     const SamplingOptions& o = stage == 5 ? fp.fin : fp.spatial;
     int stride = 0, camTasks = 0;
-    if (stage == 2) {
+    if (stage == 1) {   // K1's final p-hat of the streamed reservoir (VR/TraceRays.cs.slang:176-183)
+        stride = MB_K1_EVAL_STRIDE;
+        roles.push_back({o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, o.visibilityTrackingMethod, B});
+        roles.push_back({o.lightingMipLevel, o.lightingUseLinearSampler, o.lightingTStepScale, o.lightingTrackingMethod, 1});
+    } else if (stage == 2) {
         stride = MB_K2_STRIDE;
         roles.push_back({o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, o.visibilityTrackingMethod, B});        // E(1,0): history sample on the current ray
         roles.push_back({o.lightingMipLevel, o.lightingUseLinearSampler, o.lightingTStepScale, o.lightingTrackingMethod, 1});
@@ -272,31 +292,29 @@ int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStrea
     size_t tasksPerPixel = 0; for (const MarchRole& u : uniq) tasksPerPixel += (size_t)u.perPixel;
     const size_t bytesPerPixel = tasksPerPixel * 48 + (size_t)camTasks * 32 + (size_t)stride * 4;
     const int bandRows = fp.rowEnd - fp.rowBegin;
-    size_t maxRows = p->mScratchBudget / (bytesPerPixel * (size_t)fp.W);
+    size_t maxRows = p->mScratchBudget / ((bytesPerPixel + reservedBytesPerPixel) * (size_t)fp.W);
     maxRows = std::min<size_t>(maxRows, ((size_t)1 << 32) / ((size_t)fp.W * (size_t)std::max<size_t>(stride, 1)) - 1);   // 32-bit result indices
     int chunkRows = (int)std::min<size_t>((size_t)bandRows, std::max<size_t>(8, maxRows / 8 * 8));
+    if (forcedChunkRows) chunkRows = forcedChunkRows;   // the caller already runs on a chunk of its own
     const size_t chunkPixels = (size_t)chunkRows * fp.W;
     const size_t need = chunkPixels * bytesPerPixel + 256;
-    if (p->mbArenaBytes < need) {
-        CK(cudaStreamSynchronize(st));
-        if (p->mbArena) cudaFree(p->mbArena);
-        p->mbArena = nullptr; p->mbArenaBytes = 0;
-        CK(cudaMalloc(&p->mbArena, need));
-        p->mbArenaBytes = need;
-    }
-    if (!p->mbCounters) CK(cudaMalloc(&p->mbCounters, 64));
+    ScratchArena mainArena{p->mbArena, p->mbArenaBytes, p->mbCounters};
+    ScratchArena& arena = arenaOverride ? *arenaOverride : mainArena;
+    { int rcA = growArena(arena, need, st); if (rcA) return rcA; }
+    if (!arenaOverride) { p->mbArena = arena.base; p->mbArenaBytes = arena.bytes; p->mbCounters = arena.counters; }
+    unsigned* const counters = arena.counters;
     if (!p->marchBlocks1 || !p->analyticBlocks) {
         int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
         p->marchBlocks1 = sms * marchBlocksPerSM(1); p->marchBlocks3 = sms * marchBlocksPerSM(3); p->analyticBlocks = sms * analyticBlocksPerSM();
     }
     // carve: [results | camera tasks | stream 0 | stream 1 | ...]
-    char* base = (char*)p->mbArena;
+    char* base = (char*)arena.base;
     float* results = (float*)base; base += (chunkPixels * stride * 4 + 15) / 16 * 16;
-    WfStream cam{}; cam.tasks = (uint4*)base; cam.count = p->mbCounters; cam.cursor = p->mbCounters + 1; cam.capacity = (unsigned)(chunkPixels * camTasks);
+    WfStream cam{}; cam.tasks = (uint4*)base; cam.count = counters; cam.cursor = counters + 1; cam.capacity = (unsigned)(chunkPixels * camTasks);
     base += chunkPixels * camTasks * 32;
     MarchStreams ms{}; ms.n = (int)uniq.size();
     for (int k = 0; k < ms.n; k++) {
-        ms.s[k].tasks = (uint4*)base; ms.s[k].count = p->mbCounters + 2 + 2 * k; ms.s[k].cursor = p->mbCounters + 3 + 2 * k;
+        ms.s[k].tasks = (uint4*)base; ms.s[k].count = counters + 2 + 2 * k; ms.s[k].cursor = counters + 3 + 2 * k;
         ms.s[k].capacity = (unsigned)std::min<size_t>(chunkPixels * (size_t)uniq[k].perPixel, 0xffffffffull);
         base += chunkPixels * (size_t)uniq[k].perPixel * 48;
         ms.mip[k] = uniq[k].mip; ms.linear[k] = uniq[k].linear ? 1 : 0; ms.scale[k] = uniq[k].scale; ms.analytic[k] = uniq[k].method == VRESTIR_ANALYTIC_TRACKING ? 1 : 0;
@@ -304,20 +322,23 @@ int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStrea
     for (int r0 = fp.rowBegin; r0 < fp.rowEnd; r0 += chunkRows) {
         FrameParams fc = fp;
         fc.rowBegin = r0; fc.rowEnd = std::min(fp.rowEnd, r0 + chunkRows);
-        CK(cudaMemsetAsync(p->mbCounters, 0, 64, st));
+        CK(cudaMemsetAsync(counters, 0, 64, st));
         if (p->mDebugPoison) CK(cudaMemsetAsync(results, 0xFF, chunkPixels * stride * 4, st));
         CK(launchStageEmit(stage, fc, ms, cam, results, st)); p->launches++;
-        const bool timeMarches = stage == 3 && r0 == fp.rowBegin;   // the march launches of the (first chunk of the) spatial round: roofline input
+        const int chunkIdx = (r0 - fp.rowBegin) / chunkRows;
+        const bool timeMarches = stage == 3 && chunkIdx < 64;   // the march launches of the spatial round, per chunk: roofline input
+        cudaEvent_t* evc = nullptr;
         if (timeMarches) {
-            for (auto& e : p->evMarch) if (!e) CK(cudaEventCreate(&e));
-            if (!p->wfCounters) CK(cudaMalloc(&p->wfCounters, 128));
-            CK(cudaEventRecord(p->evMarch[0], st));
+            while ((int)p->evMarchChunks.size() < 3 * (chunkIdx + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); p->evMarchChunks.push_back(e); }
+            if (!p->d_marchCounts) CK(cudaMalloc(&p->d_marchCounts, 128 * sizeof(unsigned)));
+            evc = &p->evMarchChunks[3 * chunkIdx];
+            CK(cudaEventRecord(evc[0], st));
         }
         if (camTasks) {
             const MarchKind kc = {o.visibilityMipLevel, o.visibilityUseLinearSampler, o.visibilityTStepScale, 1, {fp.camPos.x, fp.camPos.y, fp.camPos.z}};
             CK(launchMarch(cam, results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st)); p->launches++;
         }
-        if (timeMarches) CK(cudaEventRecord(p->evMarch[1], st));
+        if (timeMarches) CK(cudaEventRecord(evc[1], st));
         for (int k = 0; k < ms.n; k++) {
             const MarchKind kk = {ms.mip[k], ms.linear[k], ms.scale[k], 0, {0.f, 0.f, 0.f}};
             if (ms.analytic[k]) CK(launchMarchAnalytic(ms.s[k], results, kk, p->scene.slots[kk.mip], p->analyticBlocks, st));
@@ -325,10 +346,10 @@ int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStrea
             p->launches++;
         }
         if (timeMarches) {
-            CK(cudaEventRecord(p->evMarch[2], st));
-            p->evMarchValid = true;
-            CK(cudaMemcpyAsync(p->wfCounters + 8, p->mbCounters, 4, cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(p->wfCounters + 9, p->mbCounters + 2, 4, cudaMemcpyDeviceToDevice, st));
+            CK(cudaEventRecord(evc[2], st));
+            p->evMarchValid = true; p->marchChunksUsed = chunkIdx + 1;
+            CK(cudaMemcpyAsync(p->d_marchCounts + 2 * chunkIdx, counters, 4, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(p->d_marchCounts + 2 * chunkIdx + 1, counters + 2, 4, cudaMemcpyDeviceToDevice, st));
         }
         CK(launchStageConsume(stage, fc, results, st)); p->launches++;
         p->mbChunks++;
@@ -661,6 +682,55 @@ int runInitialWavefront(vrestir_pass* p, const FrameParams& fp, cudaStream_t st)
     return VRESTIR_OK;
 }
 
+// lock-step wavefront K1 for 2-4 bounces (vr_wavefront.cu): reuse on, <= 4 candidates, ray-marched light visibility, deterministic
+// tracking under the spatial options (the final p-hat)
+bool initialWavefrontMBOk(const vrestir_pass* p) {
+    const vrestir_params& m = p->P;
+    const bool noReuse = !m.mEnableSpatialReuse && !m.mEnableTemporalReuse;
+    return p->mUseWavefront && m.mMaxBounces >= 2 && m.mMaxBounces <= 4 && !m.mUseReference && !noReuse && m.mInitialM <= 4 &&
+           m.mInitialLightingTrackingMethod == VRESTIR_RAY_MARCHING && m.mInitialLightSamples <= 1 && p->mInitialMode == 1 && genericStageOk(p, 2);
+}
+// K1 as <= M * B waves over the band (in row chunks under the scratch budget): traverse, then per wave {advance every pixel to
+// its next shadow march, march}, then the p-hat of the streamed reservoir as an emit / march / consume pass.
+int runInitialWavefrontMB(vrestir_pass* p, const FrameParams& fp, cudaStream_t st) {
+    const vrestir_params& m = p->P;
+    const int B = m.mMaxBounces, M = m.mInitialM;
+    const size_t stateBytes = (size_t)K1MB_STRIDE * 4 + 16 + 48;                              // state block, done flag (+ padding), one light task
+    const size_t evalBytes = (size_t)(B + 1) * 48 + (size_t)MB_K1_EVAL_STRIDE * 4;
+    size_t maxRows = p->mScratchBudget / ((stateBytes + evalBytes) * (size_t)fp.W);
+    maxRows = std::min<size_t>(maxRows, ((size_t)1 << 32) / ((size_t)fp.W * K1MB_STRIDE) - 1);   // 32-bit record indices
+    const int bandRows = fp.rowEnd - fp.rowBegin;
+    const int chunkRows = (int)std::min<size_t>((size_t)bandRows, std::max<size_t>(8, maxRows / 8 * 8));
+    const size_t chunkPixels = (size_t)chunkRows * fp.W;
+    { int rc = growArena(p->k1mb, chunkPixels * stateBytes + 256, st); if (rc) return rc; }
+    if (!p->marchBlocks1) {
+        int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+        p->marchBlocks1 = sms * marchBlocksPerSM(1); p->marchBlocks3 = sms * marchBlocksPerSM(3);
+    }
+    const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0, {0.f, 0.f, 0.f}};
+    WfInitialMB wi;
+    wi.state = (float*)p->k1mb.base;
+    wi.done = (uint8_t*)(wi.state + chunkPixels * K1MB_STRIDE);
+    wi.light.tasks = (uint4*)((char*)wi.done + (chunkPixels + 15) / 16 * 16);
+    wi.light.count = p->k1mb.counters; wi.light.cursor = p->k1mb.counters + 1; wi.light.capacity = (unsigned)chunkPixels;
+    for (int r0 = fp.rowBegin; r0 < fp.rowEnd; r0 += chunkRows) {
+        FrameParams fc = fp;
+        fc.rowBegin = r0; fc.rowEnd = std::min(fp.rowEnd, r0 + chunkRows);
+        CK(cudaMemsetAsync(p->k1mb.counters, 0, 8, st));
+        CK(launchInitialMBTraverse(fc, wi, st));
+        CK(launchInitialMBStep(fc, wi, 1, st));
+        p->launches += 2;
+        for (int w = 0; w < M * B; w++) {
+            CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
+            CK(cudaMemsetAsync(p->k1mb.counters, 0, 8, st));
+            CK(launchInitialMBStep(fc, wi, 0, st));
+            p->launches += 2;
+        }
+        int rc = runStageGeneric(p, 1, fc, st, &p->k1mbEval, 0, fc.rowEnd - fc.rowBegin); if (rc) return rc;
+    }
+    return VRESTIR_OK;
+}
+
 int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, cudaStream_t st);
 int runStage(vrestir_pass* p, int stage, int arg, float* out_color, float* out_mvec, cudaStream_t st) {
     const int rc = runStageBody(p, stage, arg, out_color, out_mvec, st);
@@ -730,8 +800,8 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
                     CK(cudaStreamWaitEvent(st, p->evPfDone, 0)); p->pfValid = false; p->pfDiscarded++;
                 }
                 fp.cur = resView(p, p->ia); fp.extCur = p->ext[p->ia];
-                if (initialWavefrontOk(p)) {
-                    rc = runInitialWavefront(p, fp, st); if (rc) return rc;
+                if (initialWavefrontOk(p) || initialWavefrontMBOk(p)) {
+                    rc = initialWavefrontOk(p) ? runInitialWavefront(p, fp, st) : runInitialWavefrontMB(p, fp, st); if (rc) return rc;
                     p->finalPhys = p->ia;
                     recordEv(p, 2, st);
                     break;
@@ -744,7 +814,7 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
         case 7: {
             // Prefetch: K0 + K1 of the NEXT frame on the prefetch stream.  Call after stage 1 of the frame in flight (its K1 has
             // released the K1 scratch) and before stage 2, so that the chain overlaps K2..K5.  No-op unless mPipelineFrames.
-            if (!p->mPipelineFrames || !active || m.mUseReference || !initialWavefrontOk(p) || p->pfValid) break;
+            if (!p->mPipelineFrames || !active || m.mUseReference || !(initialWavefrontOk(p) || initialWavefrontMBOk(p)) || p->pfValid) break;
             if (!p->pfStream) {
                 // High priority: the chain is ~13 short dependent launches; at default priority each of them queues behind the
                 // resident persistent CTAs of the main stream's march kernels and the chain stretches over the whole frame
@@ -761,14 +831,14 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
             fn.camPos = f3of(c.posW); fn.camU = f3of(c.cameraU); fn.camV = f3of(c.cameraV); fn.camW = f3of(c.cameraW);
             fn.frameCount = p->mFrameCount + 1;
             fn.features = p->feat[p->featNext];
-            fn.cur = resView(p, p->in); fn.extCur = nullptr;
+            fn.cur = resView(p, p->in); fn.extCur = p->ext[p->in];
             // everything enqueued so far on `st` (the previous frame, this frame's K1) is done with the target buffers / the scratch
             CK(cudaEventRecord(p->evPfGo, st));
             CK(cudaStreamWaitEvent(p->pfStream, p->evPfGo, 0));
             setPersistingWindow(p, p->pfStream, true);
             CK(cudaEventRecord(p->evPf0, p->pfStream));
             CK(launchFeatures(fn, p->pfStream)); p->launches++;
-            rc = runInitialWavefront(p, fn, p->pfStream); if (rc) return rc;
+            rc = initialWavefrontOk(p) ? runInitialWavefront(p, fn, p->pfStream) : runInitialWavefrontMB(p, fn, p->pfStream); if (rc) return rc;
             CK(cudaEventRecord(p->evPf1, p->pfStream));
             CK(cudaEventRecord(p->evPfDone, p->pfStream));
             p->pfTimed = true;
@@ -843,7 +913,7 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
                     CK(cudaEventRecord(p->evMarch[1], st));
                     CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
                     CK(cudaEventRecord(p->evMarch[2], st));
-                    p->evMarchValid = true;
+                    p->evMarchValid = true; p->marchChunksUsed = 0;
                     CK(cudaMemcpyAsync(p->wfCounters + 8, p->wfCounters, 4, cudaMemcpyDeviceToDevice, st));       // task counts of this round (diagnostics)
                     CK(cudaMemcpyAsync(p->wfCounters + 9, p->wfCounters + 2, 4, cudaMemcpyDeviceToDevice, st));
                     CK(launchSpatialCombine(fp, wf, st));
@@ -1020,8 +1090,9 @@ int vrestir_destroy(vrestir_pass* p) try {
     if (p->evMainTail) cudaEventDestroy(p->evMainTail);
     for (auto& d : p->dslots) freeSlot(d);
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
-    for (int i = 0; i < 3; i++) { if (p->ext[i]) cudaFree(p->ext[i]); if (p->feat[i]) cudaFree(p->feat[i]); }
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor[0], p->d_hostColor[1], p->d_hostMvec[0], p->d_hostMvec[1], p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters, p->mbArena, p->mbCounters};
+    for (int i = 0; i < 4; i++) if (p->ext[i]) cudaFree(p->ext[i]);
+    for (int i = 0; i < 3; i++) if (p->feat[i]) cudaFree(p->feat[i]);
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor[0], p->d_hostColor[1], p->d_hostMvec[0], p->d_hostMvec[1], p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters, p->mbArena, p->mbCounters, p->d_marchCounts, p->k1mb.base, p->k1mb.counters, p->k1mbEval.base, p->k1mbEval.counters};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
@@ -1031,6 +1102,7 @@ int vrestir_destroy(vrestir_pass* p) try {
     if (p->evFork) cudaEventDestroy(p->evFork);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
     for (auto& e : p->evMarch) if (e) cudaEventDestroy(e);
+    for (auto& e : p->evMarchChunks) if (e) cudaEventDestroy(e);
     if (p->outStream) cudaStreamDestroy(p->outStream);
     for (cudaEvent_t e : {p->evOutGo, p->evOutDone[0], p->evOutDone[1], p->evOut0, p->evOut1}) if (e) cudaEventDestroy(e);
     if (p->pfStream) cudaStreamDestroy(p->pfStream);
@@ -1463,6 +1535,20 @@ int vrestir_get_march_timings(vrestir_pass* p, vrestir_march_timings* out) try {
     if (!p || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
     if (!p->evMarchValid) return setError(VRESTIR_ERR_NOT_READY, "no wavefront spatial round has run");
     CK(cudaSetDevice(p->device));
+    if (p->marchChunksUsed > 0) {   // generic path: sum over the row chunks of the round
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned> cnt(2 * p->marchChunksUsed);
+        CK(cudaMemcpy(cnt.data(), p->d_marchCounts, cnt.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        out->spatial_cam_ms = out->spatial_light_ms = 0.f; out->spatial_cam_tasks = out->spatial_light_tasks = 0;
+        for (int c = 0; c < p->marchChunksUsed; c++) {
+            float a = 0.f, b = 0.f;
+            CK(cudaEventElapsedTime(&a, p->evMarchChunks[3 * c], p->evMarchChunks[3 * c + 1]));
+            CK(cudaEventElapsedTime(&b, p->evMarchChunks[3 * c + 1], p->evMarchChunks[3 * c + 2]));
+            out->spatial_cam_ms += a; out->spatial_light_ms += b;
+            out->spatial_cam_tasks += cnt[2 * c]; out->spatial_light_tasks += cnt[2 * c + 1];
+        }
+        return VRESTIR_OK;
+    }
     CK(cudaEventSynchronize(p->evMarch[2]));
     CK(cudaEventElapsedTime(&out->spatial_cam_ms, p->evMarch[0], p->evMarch[1]));
     CK(cudaEventElapsedTime(&out->spatial_light_ms, p->evMarch[1], p->evMarch[2]));

@@ -101,6 +101,13 @@ struct WfBufs4 { WfStream s[4]; int mip[4]; float* results; };
 // march configuration a stage can ask for is one stream; a pixel's results live at [pixel * stride + eval * MARCH_SLOTS + slot]
 // (+ MB_CAM for the shared multi-threshold camera marches of K3).
 struct MarchStreams { WfStream s[4]; int mip[4], linear[4], analytic[4]; float scale[4]; int n; };
-enum { MB_K2_STRIDE = 20, MB_K3_STRIDE = 96, MB_K3_CAM = 80, MB_K5_STRIDE = 8 };
+enum { MB_K2_STRIDE = 20, MB_K3_STRIDE = 96, MB_K3_CAM = 80, MB_K5_STRIDE = 8, MB_K1_EVAL_STRIDE = 8 };
+// Multi-bounce K1 as lock-step waves (vr_wavefront.cu): per-pixel state block of K1MB_STRIDE floats
+//   [0,4) RNG  [4,16) hd/pd/ot of the <= 4 distance candidates  [16,24) streamed (final) reservoir  [24,32) per-candidate
+//   (combined) reservoir  [32,41) path: ray origin, ray dir, pathPdf, pathPHat, primary depth  [41,43) candidate / bounce cursor
+//   [44,53) extra-bounce records of the final reservoir  [56,65) of the current candidate  [68,86) the bounce waiting for its
+//   shadow march  [95] the marched visibility
+enum { MBK_SG = 0, MBK_HD = 4, MBK_FIN = 16, MBK_COMB = 24, MBK_PATH = 32, MBK_CUR = 41, MBK_FINX = 44, MBK_EXTRA = 56, MBK_PEND = 68, MBK_VIS = 95, K1MB_STRIDE = 96 };
+struct WfInitialMB { WfStream light; float* state; uint8_t* done; };
 
 }  // namespace vrd

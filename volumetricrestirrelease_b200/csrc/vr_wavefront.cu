@@ -893,6 +893,309 @@ __global__ void __launch_bounds__(128, VR_MB_MINB) k_final_consume(FrameParams f
     finalPixel<B>(fp, x, y, mp);
 }
 
+// ------------------------------------------------------------------------------------------------ K1, 2-4 bounces, lock-step
+// VR/TraceRays.cs.slang:64-201 + VR/ComputeInitialSample.slang:4-395 for B > 1 as a resumable per-pixel state machine: the
+// candidate / bounce loop is cut at the shadow march of SampleDirectLighting, exactly where the single-bounce lock-step kernels
+// above cut it.  One wave = every pixel advances to its NEXT shadow march (bounces that need none — the path left the volume,
+// hit an empty voxel, drew an invalid light sample — are completed on the way), the march engine runs that wave's marches, the
+// next wave consumes them.  A pixel's random-number stream is consumed in the reference's order because the pixel itself
+// still runs its candidates and bounces one after the other; only the marches of DIFFERENT pixels are batched.  <= M * B waves.
+// The final p-hat under the spatial options (VR/TraceRays.cs.slang:176-183) goes through the generic emit / consume passes.
+struct MBPend {   // a bounce between its light sample and its shadow march
+    unsigned flags;   // bit0 mi.isValid, bit1 light sample valid, bit2 shadow march pending
+    float curHitDist, Tr, density;
+    float3 Li; float ph, outLightPdf; float3 Le; int lightID; float2 lightUV; float3 mip;
+};
+VRD void mbStorePend(float* r, const MBPend& c) {
+    float4* q = (float4*)r;
+    q[0] = make_float4(__uint_as_float(c.flags), c.curHitDist, c.Tr, c.density);
+    q[1] = make_float4(c.Li.x, c.Li.y, c.Li.z, c.ph);
+    q[2] = make_float4(c.outLightPdf, c.Le.x, c.Le.y, c.Le.z);
+    q[3] = make_float4(__int_as_float(c.lightID), c.lightUV.x, c.lightUV.y, c.mip.x);
+    r[16] = c.mip.y; r[17] = c.mip.z;
+}
+VRD MBPend mbLoadPend(const float* r) {
+    const float4* q = (const float4*)r;
+    const float4 a = q[0], b = q[1], c4 = q[2], d = q[3];
+    MBPend c;
+    c.flags = __float_as_uint(a.x); c.curHitDist = a.y; c.Tr = a.z; c.density = a.w;
+    c.Li = f3(b.x, b.y, b.z); c.ph = b.w; c.outLightPdf = c4.x; c.Le = f3(c4.y, c4.z, c4.w);
+    c.lightID = __float_as_int(d.x); c.lightUV = make_float2(d.y, d.z); c.mip = f3(d.w, r[16], r[17]);
+    return c;
+}
+VRD void mbStoreRes(float* r, const Reservoir& v) {
+    ((float4*)r)[0] = make_float4(v.runningSum, v.M, v.depth, v.p_y);
+    ((float4*)r)[1] = make_float4(v.lightUV.x, v.lightUV.y, __int_as_float(v.lightID), __int_as_float(v.sampledPixel));
+}
+VRD Reservoir mbLoadRes(const float* r) {
+    const float4 a = ((const float4*)r)[0], b = ((const float4*)r)[1];
+    Reservoir v = createNewReservoir();
+    v.runningSum = a.x; v.M = a.y; v.depth = a.z; v.p_y = a.w; v.lightUV = make_float2(b.x, b.y); v.lightID = __float_as_int(b.z); v.sampledPixel = __float_as_int(b.w);
+    return v;
+}
+
+#ifndef VR_MBSTEP_MINB
+#define VR_MBSTEP_MINB 4
+#endif
+// first != 0: the wave after k_initial_traverse (state holds the RNG and the distance candidates only)
+template <int B>
+__global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FrameParams fp, WfInitialMB wi, int first) {
+    int x, y;
+    const bool inFrame = pixelOf(fp, x, y);
+    const int pixelId = inFrame ? y * fp.W + x : fp.rowBegin * fp.W;
+    const unsigned local = (unsigned)(pixelId - fp.rowBegin * fp.W);
+    const unsigned recBase = local * K1MB_STRIDE;
+    float* st = wi.state + recBase;
+    const SamplingOptions& options = fp.initial;
+    const vrestir_volume_desc& vd = c_scene.vol;
+    const int M = fp.initialM;
+    bool hasTask = false;
+    Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
+    if (inFrame && (first || !wi.done[local])) {
+        const float3 sigA = v3(vd.sigma_a), sigS = v3(vd.sigma_s);
+        const Ray primary = primaryRay(fp, x, y);
+        SampleGenerator sg;
+        { const float4 g4 = ((const float4*)(st + MBK_SG))[0]; sg.s0 = __float_as_uint(g4.x); sg.s1 = __float_as_uint(g4.y); sg.s2 = __float_as_uint(g4.z); sg.s3 = __float_as_uint(g4.w); }
+        Reservoir finalReservoir, combinedReservoir;
+        Ray ray = primary;
+        float pathPdf = 1.f, pathPHat = 1.f, primaryScatterDepth = 0.f;
+        int s = 0, bounce = 0;
+        float3 extra[B - 1], finalExtra[B - 1];
+        if (first) {
+            finalReservoir = createNewReservoir(); combinedReservoir = createNewReservoir();
+#pragma unroll
+            for (int i = 0; i < B - 1; i++) { extra[i] = f3(0.f); finalExtra[i] = f3(0.f); }
+        } else {
+            finalReservoir = mbLoadRes(st + MBK_FIN); combinedReservoir = mbLoadRes(st + MBK_COMB);
+            ray.origin = f3(st[MBK_PATH], st[MBK_PATH + 1], st[MBK_PATH + 2]); ray.dir = f3(st[MBK_PATH + 3], st[MBK_PATH + 4], st[MBK_PATH + 5]);
+            pathPdf = st[MBK_PATH + 6]; pathPHat = st[MBK_PATH + 7]; primaryScatterDepth = st[MBK_PATH + 8];
+            s = __float_as_int(st[MBK_CUR]); bounce = __float_as_int(st[MBK_CUR + 1]);
+#pragma unroll
+            for (int i = 0; i < B - 1; i++) {
+                extra[i] = f3(st[MBK_EXTRA + 3 * i], st[MBK_EXTRA + 3 * i + 1], st[MBK_EXTRA + 3 * i + 2]);
+                finalExtra[i] = f3(st[MBK_FINX + 3 * i], st[MBK_FINX + 3 * i + 1], st[MBK_FINX + 3 * i + 2]);
+            }
+        }
+        bool resume = !first;
+        bool finished = false;
+        MBPend c;
+        for (int guard = 0; guard < 4 * B + 8 && !finished; guard++) {
+            Reservoir outReservoir = createNewReservoir();
+            outReservoir.M = 1;
+            float vis = 1.f;
+            if (!resume) {
+                // ---- VR/ComputeInitialSample.slang:48-230: the bounce up to the shadow march of its light sample
+                float curHitDist, pdfDist = 0.f, Tr;
+                MediumInteraction mi;
+                if (bounce >= 1) {
+                    int curMip = options.visibilityMipLevel;
+                    if (fp.useCoarserGrid) curMip = min((options.visibilityMipLevel >= VRESTIR_NUM_MAX_MIPS ? VRESTIR_NUM_MAX_MIPS : 0) + vd.numMips - 1, curMip + 1);
+                    float hd[4], pd[4], ot[4];
+                    SampleMediumAnalyticGeneric(ray, sg, options.visibilityUseLinearSampler, hd, curMip, pd, ot, 1);
+                    curHitDist = hd[0]; pdfDist = pd[0]; Tr = ot[0];
+                } else {
+                    curHitDist = st[MBK_HD + s]; pdfDist = st[MBK_HD + 4 + s]; Tr = st[MBK_HD + 8 + s];
+                }
+                mi = makeMI(ray.at(curHitDist), -ray.dir, curHitDist != kRayTMax);
+                pathPdf *= pdfDist;
+                if (bounce == 0) primaryScatterDepth = mi.isValid ? curHitDist : kRayTMax;
+                else extra[bounce - 1] = encodeWiDist(make_float4(ray.dir.x, ray.dir.y, ray.dir.z, !mi.isValid ? kRayTMax : curHitDist));
+                c.flags = mi.isValid ? 1u : 0u; c.curHitDist = curHitDist; c.Tr = Tr; c.density = 0.f;
+                c.Li = f3(0.f); c.ph = 0.f; c.outLightPdf = 0.f; c.Le = f3(0.f); c.lightID = 0; c.lightUV = make_float2(0, 0); c.mip = mi.p;
+                if (mi.isValid) c.density = DensityWorldSpace(mi.p, 0);
+                const bool hitEmpty0 = (!mi.isValid && bounce > 0) || (mi.isValid && c.density == 0.f);
+                if (!hitEmpty0 && mi.isValid) {
+                    c.lightID = -1;
+                    if (vd.hasEmission && c.density > 0.f) c.Le = EmissionWorldSpace(mi.p);
+                    SceneLightSample ls;
+                    const bool lvalid = sampleSceneLights(mi.p, options.useEnvironmentLights, options.useAnalyticLights, options.useEmissiveLights, sg, ls, c.lightID, c.lightUV);
+                    c.outLightPdf = lvalid ? ls.pdfArea : 0.f;
+                    if (lvalid) {
+                        c.flags |= 2u;
+                        c.Li = ls.Li;
+                        c.ph = mi.phaseFunction(mi.wo, ls.dir);
+                        if (options.lightSamples != 0) {
+                            c.flags |= 4u;
+                            hasTask = true;
+                            shadow = makeRay(mi.p, ls.rayDir, 0, ls.rayDistance);
+                            break;   // the wave ends here for this pixel: state is stored below, the march engine takes over
+                        }
+                    }
+                }
+            } else {
+                c = mbLoadPend(st + MBK_PEND);
+                vis = st[MBK_VIS];
+                resume = false;
+            }
+            // ---- VR/ComputeInitialSample.slang:76-393: the rest of the bounce
+            const bool valid = c.flags & 1u;
+            const float curHitDist = c.curHitDist;
+            bool hitEmpty = false;
+            if (bounce == 0) {
+                outReservoir.sampledPixel = encodeMaxIndirectBounces(outReservoir.sampledPixel, 0);
+                outReservoir.depth = valid ? curHitDist : kRayTMax;
+                outReservoir.p_y = pathPdf;
+            } else {
+                outReservoir.depth = primaryScatterDepth;
+                outReservoir.sampledPixel = encodeMaxIndirectBounces(outReservoir.sampledPixel, bounce);
+                outReservoir.p_y = pathPdf;
+            }
+            const float actualVolumeDensity = valid ? c.density : 0.f;
+            if ((!valid && bounce > 0) || (valid && actualVolumeDensity == 0)) { outReservoir.p_y = 0.f; outReservoir.runningSum = 0.f; hitEmpty = true; }
+            float pdfDir = 1.f;
+            float3 wi_ = f3(0.f);
+            if (!hitEmpty) {
+                if (valid) {
+                    const float3 albedo = sigS / vd.sigma_t;
+                    outReservoir.lightID = c.lightID;
+                    outReservoir.lightUV = c.lightUV;
+                    const float outLightPdf = c.outLightPdf;
+                    float3 Ld = f3(0.f);
+                    const float3 Le = c.Le;
+                    const float3 one_minus_albedo = f3(1.f) - albedo;
+                    if (c.flags & 2u) {   // SampleDirectLighting (VR/VolumeUtils.slang:454-492) with the marched visibility
+                        float3 Li = c.Li;
+                        if (c.flags & 4u) Li = Li * vis;
+                        Ld = Ld + c.ph * Li / 1.f;
+                    }
+                    const MediumInteraction mi = makeMI(c.mip, -ray.dir, true);
+                    const float3 wo = -ray.dir;
+                    pdfDir = mi.Sample_p(wo, wi_, sampleNext2D(sg));
+                    float p_src = outReservoir.p_y;
+                    {
+                        float lumE = luminance(one_minus_albedo * Le);
+                        float emissionRatio = lumE / (lumE + luminance(albedo * Ld));
+                        if (isnan(emissionRatio)) emissionRatio = 0.f;
+                        if (sampleNext1D(sg) < emissionRatio) { p_src *= emissionRatio; outReservoir.lightID = VRESTIR_SELF_EMISSION_LIGHT_ID; }
+                        else p_src *= outLightPdf * (1 - emissionRatio);
+                    }
+                    outReservoir.runningSum = p_src == 0.f ? 0.f : 1.f;
+                    outReservoir.p_y = p_src;
+                    {
+                        float p_y;
+                        pathPHat *= c.Tr;
+                        pathPHat *= actualVolumeDensity;
+                        if (outReservoir.lightID == VRESTIR_SELF_EMISSION_LIGHT_ID) p_y = pathPHat * luminance(sigA * Le);
+                        else p_y = pathPHat * luminance(sigS * Ld * outLightPdf);
+                        pathPHat *= luminance(sigS) * pdfDir;
+                        if (outReservoir.runningSum > 0.f) {
+                            outReservoir.runningSum = outReservoir.p_y == 0.f ? 0.f : p_y / outReservoir.p_y;
+                            if (outReservoir.lightID == VRESTIR_SELF_EMISSION_LIGHT_ID && bounce > 0) {
+                                encodeEmissivePosition(c.mip, outReservoir.lightID, outReservoir.lightUV);
+                                p_y /= (curHitDist * curHitDist);
+                                outReservoir.sampledPixel = encodePathTag(outReservoir.sampledPixel, 1);
+                            }
+                            outReservoir.p_y = p_y;
+                        }
+                    }
+                    pathPdf *= pdfDir;
+                    if (bounce < B - 1) {
+                        ray = makeRay(c.mip, wi_, 0, kRayTMax);
+                        if (fp.useRussianRoulette && bounce >= 2) {
+                            if (sampleNext1D(sg) < albedo.x) pathPdf *= albedo.x;
+                            else { hitEmpty = true; combinedReservoir.M++; }
+                        }
+                    }
+                } else {
+                    const float3 Le = envEval(ray.dir);
+                    pathPHat *= c.Tr;
+                    const float p_y = pathPHat * luminance(Le);
+                    outReservoir.runningSum = outReservoir.p_y == 0.f ? 0.f : p_y / outReservoir.p_y;
+                    outReservoir.p_y = p_y;
+                    hitEmpty = true;
+                }
+            }
+            simpleResampleStep<B>(outReservoir, combinedReservoir, sg);
+            if (hitEmpty || bounce == B - 1) {
+                // ---- the candidate is complete (VR/ComputeInitialSample.slang:395, VR/TraceRays.cs.slang:153-172)
+                combinedReservoir.M = 1;
+                const bool isSelected = simpleResampleStep<B>(combinedReservoir, finalReservoir, sg);
+                if (isSelected) {
+                    const int mib = decodeMaxIndirectBounces<B>(finalReservoir.sampledPixel);
+#pragma unroll
+                    for (int b = 0; b < B - 1; b++) if (b < mib) finalExtra[b] = extra[b];
+                }
+                s++; bounce = 0;
+                ray = primary; pathPdf = 1.f; pathPHat = 1.f; primaryScatterDepth = 0.f;
+                combinedReservoir = createNewReservoir();
+                if (s >= M) finished = true;
+            } else bounce++;
+        }
+        if (finished) {
+            // the streamed reservoir; its p-hat under the spatial options is evaluated by the emit / consume passes that follow
+            wi.done[local] = 1;
+            storeReservoir(fp.cur, pixelId, finalReservoir);
+            const int mib = decodeMaxIndirectBounces<B>(finalReservoir.sampledPixel);
+#pragma unroll
+            for (int b = 0; b < B - 1; b++) if (b < mib) fp.extCur[(size_t)pixelId * (B - 1) + b] = finalExtra[b];
+        } else {
+            if (first) wi.done[local] = 0;
+            ((float4*)(st + MBK_SG))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
+            mbStoreRes(st + MBK_FIN, finalReservoir); mbStoreRes(st + MBK_COMB, combinedReservoir);
+            st[MBK_PATH] = ray.origin.x; st[MBK_PATH + 1] = ray.origin.y; st[MBK_PATH + 2] = ray.origin.z;
+            st[MBK_PATH + 3] = ray.dir.x; st[MBK_PATH + 4] = ray.dir.y; st[MBK_PATH + 5] = ray.dir.z;
+            st[MBK_PATH + 6] = pathPdf; st[MBK_PATH + 7] = pathPHat; st[MBK_PATH + 8] = primaryScatterDepth;
+            st[MBK_CUR] = __int_as_float(s); st[MBK_CUR + 1] = __int_as_float(bounce);
+#pragma unroll
+            for (int i = 0; i < B - 1; i++) {
+                st[MBK_EXTRA + 3 * i] = extra[i].x; st[MBK_EXTRA + 3 * i + 1] = extra[i].y; st[MBK_EXTRA + 3 * i + 2] = extra[i].z;
+                st[MBK_FINX + 3 * i] = finalExtra[i].x; st[MBK_FINX + 3 * i + 1] = finalExtra[i].y; st[MBK_FINX + 3 * i + 2] = finalExtra[i].z;
+            }
+            mbStorePend(st + MBK_PEND, c);
+        }
+    }
+    wfEmitRay(wi.light, hasTask, shadow, options.lightingMipLevel, false, wi.state, recBase + MBK_VIS);
+}
+
+// distance candidates of the primary ray into the multi-bounce state block (same traversal as k_initial_traverse)
+__global__ void __launch_bounds__(128, VR_TRAV_MINB) k_initial_mb_traverse(FrameParams fp, WfInitialMB wi) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    const int pixelId = y * fp.W + x;
+    float* st = wi.state + (size_t)(pixelId - fp.rowBegin * fp.W) * K1MB_STRIDE;
+    SampleGenerator sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
+    const Ray ray = primaryRay(fp, x, y);
+    float hds[4] = {0, 0, 0, 0}, pds[4] = {0, 0, 0, 0}, ots[4] = {0, 0, 0, 0};
+    SampleMediumAnalyticGeneric(ray, sg, fp.initial.visibilityUseLinearSampler, hds, fp.initial.visibilityMipLevel, pds, ots, fp.initialM);
+    ((float4*)(st + MBK_HD))[0] = make_float4(hds[0], hds[1], hds[2], hds[3]);
+    ((float4*)(st + MBK_HD))[1] = make_float4(pds[0], pds[1], pds[2], pds[3]);
+    ((float4*)(st + MBK_HD))[2] = make_float4(ots[0], ots[1], ots[2], ots[3]);
+    ((float4*)(st + MBK_SG))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
+}
+
+// VR/TraceRays.cs.slang:176-183 for the streamed reservoir of a pixel: p-hat under the spatial options, then
+// runningSum *= p_hat / p_y.  Run as an emit pass and a consume pass (march provider) like the reuse stages.
+template <int B, class MP>
+__device__ __forceinline__ void initialFinishPixel(const FrameParams& fp, int x, int y, MP& mp) {
+    const int pixelId = y * fp.W + x;
+    Reservoir r = loadReservoirRW(fp.cur, pixelId, B);
+    // the reference evaluates p-hat unconditionally and uses it only when runningSum > 0; ray-marched p-hat draws no random numbers
+    if (!(r.runningSum > 0.f)) return;
+    ExtraProviderRW prov; prov.global = fp.extCur;
+    const Ray ray = primaryRay(fp, x, y);
+    mp.beginEval(0);
+    SampleGenerator none; none.s0 = none.s1 = none.s2 = none.s3 = 0;   // deterministic tracking: never drawn from
+    const float p_hat = evaluate_P_hat<B>(ray, none, prov, fp.spatial, r, false, mp);
+    if (!MP::kStore) return;
+    r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
+    r.p_y = p_hat;
+    fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
+}
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_initial_finish_emit(FrameParams fp, MarchStreams ms, float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    EmitMarch mp(ms, results, (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * MB_K1_EVAL_STRIDE, false);
+    initialFinishPixel<B>(fp, x, y, mp);
+}
+template <int B>
+__global__ void __launch_bounds__(128, VR_MB_MINB) k_initial_finish_consume(FrameParams fp, const float* results) {
+    int x, y;
+    if (!pixelOf(fp, x, y)) return;
+    ConsumeMarch mp(results, (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * MB_K1_EVAL_STRIDE, false);
+    initialFinishPixel<B>(fp, x, y, mp);
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 gridForWf(const FrameParams& fp) { return dim3((fp.W + 15) / 16, (fp.rowEnd - fp.rowBegin + 7) / 8); }
 // one warp (8x4 tile) per CTA
@@ -957,15 +1260,26 @@ cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaSt
         case 3: kern<3><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                      \
         default: kern<4><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                     \
     }
-// stage: 2 temporal, 3 spatial, 5 final
+cudaError_t launchInitialMBTraverse(const FrameParams& fp, const WfInitialMB& wi, cudaStream_t st) { k_initial_mb_traverse<<<gridForWf(fp), 128, 0, st>>>(fp, wi); return cudaGetLastError(); }
+cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, cudaStream_t st) {
+    switch (fp.maxBounces) {
+        case 2: k_initial_mb_step<2><<<gridForWf(fp), 128, 0, st>>>(fp, wi, first); break;
+        case 3: k_initial_mb_step<3><<<gridForWf(fp), 128, 0, st>>>(fp, wi, first); break;
+        default: k_initial_mb_step<4><<<gridForWf(fp), 128, 0, st>>>(fp, wi, first); break;
+    }
+    return cudaGetLastError();
+}
+// stage: 1 = K1's final p-hat, 2 temporal, 3 spatial, 5 final
 cudaError_t launchStageEmit(int stage, const FrameParams& fp, const MarchStreams& ms, const WfStream& cam, float* results, cudaStream_t st) {
-    if (stage == 2) { VR_DISPATCH_MB(k_temporal_emit, fp, st, fp, ms, results); }
+    if (stage == 1) { VR_DISPATCH_MB(k_initial_finish_emit, fp, st, fp, ms, results); }
+    else if (stage == 2) { VR_DISPATCH_MB(k_temporal_emit, fp, st, fp, ms, results); }
     else if (stage == 3) { VR_DISPATCH_MB(k_spatial_emit, fp, st, fp, ms, cam, results); }
     else { VR_DISPATCH_MB(k_final_emit, fp, st, fp, ms, results); }
     return cudaGetLastError();
 }
 cudaError_t launchStageConsume(int stage, const FrameParams& fp, const float* results, cudaStream_t st) {
-    if (stage == 2) { VR_DISPATCH_MB(k_temporal_consume, fp, st, fp, results); }
+    if (stage == 1) { VR_DISPATCH_MB(k_initial_finish_consume, fp, st, fp, results); }
+    else if (stage == 2) { VR_DISPATCH_MB(k_temporal_consume, fp, st, fp, results); }
     else if (stage == 3) { VR_DISPATCH_MB(k_spatial_consume, fp, st, fp, results); }
     else { VR_DISPATCH_MB(k_final_consume, fp, st, fp, results); }
     return cudaGetLastError();
