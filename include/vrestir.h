@@ -390,6 +390,26 @@ int vrestir_error_measure(int device, const float* source, const float* referenc
                           int ignore_background, int compute_squared_difference, int compute_average, float* difference_out,
                           float error_rgb_avg[4], void* stream);
 
+/* ToneMapper (Source/RenderPasses/ToneMapper/ToneMapper.cpp, ToneMapping.ps.slang, Luminance.ps.slang): exposure (manual from
+ * f-number / shutter / film speed, or auto from the average log-luminance of the frame), exposure compensation, CAT02 white
+ * balance (F/Utils/Color/ColorUtils.h:200-216), one of six operators, optional clamp.  Defaults = the reference's
+ * (ToneMapper.h:111-125, operator Aces).  vrestir_tonemap_params_from_settings is host-only (no device needed). */
+enum { VRESTIR_TONEMAP_LINEAR = 0, VRESTIR_TONEMAP_REINHARD = 1, VRESTIR_TONEMAP_REINHARD_MODIFIED = 2, VRESTIR_TONEMAP_HEJI_HABLE_ALU = 3,
+       VRESTIR_TONEMAP_HABLE_UC2 = 4, VRESTIR_TONEMAP_ACES = 5 };
+typedef struct vrestir_tonemap_settings {
+    float exposureCompensation; int32_t autoExposure; float filmSpeed; int32_t whiteBalance; float whitePoint;
+    uint32_t op; int32_t clamp; float whiteMaxLuminance, whiteScale, fNumber, shutter;
+} vrestir_tonemap_settings;
+typedef struct vrestir_tonemap_params {   /* what the shader's constant buffer holds (ToneMapperParams.slang:52-59) + the pass's defines */
+    uint32_t op; int32_t autoExposure, clamp; float whiteScale, whiteMaxLuminance; float colorTransform[9];
+} vrestir_tonemap_params;
+void vrestir_tonemap_default_settings(vrestir_tonemap_settings* out);
+int vrestir_tonemap_params_from_settings(const vrestir_tonemap_settings* settings, vrestir_tonemap_params* out);
+/* src / dst: device pointers, width*height float4 (may alias).  avg_log_luminance_out (host, nullable): the auto-exposure
+ * average (log2) — requesting it makes the call synchronous.  Asynchronous on `stream` otherwise. */
+int vrestir_tonemap_execute(int device, const vrestir_tonemap_params* params, const float* src, float* dst, int width, int height,
+                            float* avg_log_luminance_out, void* stream);
+
 /* ---- mip / conservative-mip chain on the GPU (the converter's job in the reference) ------------------
  * Builds, from a dense device-resident density grid ([z][y][x] floats), every level of the normal chain and of the
  * conservative chain by the rule of gvdb-voxel-src/source/gvdb_library/src/gvdb_volume_gvdb.cpp:2703-2885 (conservative mip 0

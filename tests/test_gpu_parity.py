@@ -612,6 +612,36 @@ def test_error_measure_pass_matches_oracle():
     assert np.allclose(m["error"], po.error_measure(src, ref, None)[1], rtol=1e-6)
 
 
+@pytest.mark.parametrize("op", ["Linear", "Reinhard", "ReinhardModified", "HejiHableAlu", "HableUc2", "Aces"])
+def test_tone_mapper_matches_oracle(op):
+    """ToneMapper (the display end of the reference's graphs) on a rendered frame: every operator, manual and
+    auto exposure, white balance, clamp on / off, against the numpy restatement (fp32 kernel vs fp64 numpy: 2e-5 relative)."""
+    import torch
+    from oracle import post_oracle as po
+    from volumetricrestirrelease_b200.post import ToneMapper
+    w, h = 150, 91       # not a power of two: the luminance target is 128 x 64
+    sc = env_scene()
+    gp = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams()})
+    gp.setScene(sc, w, h)
+    color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    out = torch.zeros_like(color)
+    gp.execute(color.data_ptr()); torch.cuda.synchronize()
+    img = color.cpu().numpy()
+    for kw in ({}, {"autoExposure": True}, {"whiteBalance": True, "whitePoint": 4000.0, "exposureCompensation": 0.7, "clamp": False},
+               {"fNumber": 1.4, "shutter": 2.0, "filmSpeed": 200.0, "whiteScale": 6.0, "whiteMaxLuminance": 2.5}):
+        tm = ToneMapper(dict(kw, operator=op))
+        avg = tm.execute(color.data_ptr(), out.data_ptr(), w, h, want_average=True)
+        torch.cuda.synchronize()
+        M = po.tonemap_color_transform(**{k: v for k, v in kw.items() if k in ("exposureCompensation", "autoExposure", "filmSpeed", "whiteBalance", "whitePoint", "fNumber", "shutter")})
+        want = po.tonemap(img, M, op, kw.get("autoExposure", False), kw.get("clamp", True), kw.get("whiteScale", 11.2), kw.get("whiteMaxLuminance", 1.0))
+        if kw.get("autoExposure"):
+            assert abs(avg - po.tonemap_avg_log_luminance(img)) < 2e-5 * max(1.0, abs(avg))
+        got = out.cpu().numpy()
+        np.testing.assert_allclose(got[..., :3], want[..., :3], rtol=3e-5, atol=2e-6, err_msg=str((op, kw)), equal_nan=True)
+        assert np.array_equal(got[..., 3], img[..., 3])
+        assert got[..., :3].std() > 1e-3
+
+
 @pytest.mark.parametrize("dim", [(96, 80, 72), (97, 63, 45)])
 def test_gpu_mip_builder_matches_host_builder(dim):
     """the mip / conservative-mip chain built on the GPU from a dense grid stores exactly what the host

@@ -39,3 +39,22 @@ def test_error_measure_known_answers():
     assert np.allclose(err, [1.5 / 4, 2.0 / 4, 3.0 / 4])
     d, err, avg = po.error_measure(src, ref, None, ignore_background=True, squared=False, average=True)   # unbound world position: no background test
     assert np.allclose(d[0, 0], 2.0) and np.allclose(d[1, 1], 0.5 / 3) and np.allclose(err, (2.0 + 0.5 / 3) / 4)
+
+
+def test_tonemap_color_transform_host_side():
+    """ToneMapper::updateColorTransform / calculateWhiteBalanceTransformRGB_Rec709 through the ABI's host-only entry point
+    against the numpy restatement; the D65 white point is preserved exactly at 6500 K (ColorUtils.h:190-193)."""
+    import ctypes as C
+    from oracle import post_oracle as po
+    from volumetricrestirrelease_b200 import capi
+    from volumetricrestirrelease_b200.post import ToneMapper
+    for kw in ({}, {"whiteBalance": True, "whitePoint": 3200.0}, {"whiteBalance": True, "whitePoint": 9000.0, "exposureCompensation": 1.5},
+               {"fNumber": 2.8, "shutter": 60.0, "filmSpeed": 400.0}, {"autoExposure": True, "exposureCompensation": -1.0}):
+        tm = ToneMapper(kw)
+        M = np.array(list(tm.params().colorTransform), dtype=np.float64).reshape(3, 3).T      # stored transposed for the row-vector product
+        want = po.tonemap_color_transform(**kw)
+        np.testing.assert_allclose(M, want, rtol=2e-6, atol=1e-7)
+    tm = ToneMapper({"whiteBalance": True, "whitePoint": 6500.0})
+    M = np.array(list(tm.params().colorTransform), dtype=np.float64).reshape(3, 3).T
+    np.testing.assert_allclose(M @ np.ones(3), np.ones(3), rtol=1e-5)
+    assert abs(ToneMapper({"exposureValue": 5.0}).exposureValue - 5.0) < 1e-5

@@ -126,6 +126,15 @@ class PipelineStats(C.Structure):
     _fields_ = [("adopted", C.c_uint64), ("discarded", C.c_uint64), ("prefetch_ms", _F), ("deferred_final_ms", _F)]
 
 
+class TonemapSettings(C.Structure):
+    _fields_ = [("exposureCompensation", _F), ("autoExposure", _I), ("filmSpeed", _F), ("whiteBalance", _I), ("whitePoint", _F), ("op", _U),
+                ("clamp", _I), ("whiteMaxLuminance", _F), ("whiteScale", _F), ("fNumber", _F), ("shutter", _F)]
+
+
+class TonemapParams(C.Structure):
+    _fields_ = [("op", _U), ("autoExposure", _I), ("clamp", _I), ("whiteScale", _F), ("whiteMaxLuminance", _F), ("colorTransform", _F * 9)]
+
+
 class MipLevel(C.Structure):
     _fields_ = [("data", C.c_void_p), ("bytes", C.c_size_t), ("dim", _I * 3), ("format", _I), ("max_value", _F)]
 
@@ -151,6 +160,7 @@ SYMBOLS = [
     "vrestir_set_volume_from_chain", "vrestir_mips_build_device", "vrestir_mips_count", "vrestir_mips_level", "vrestir_mips_destroy",
     "vrestir_accum_create", "vrestir_accum_destroy", "vrestir_accum_update", "vrestir_accum_reset", "vrestir_accum_resize",
     "vrestir_accum_frame_count", "vrestir_accum_execute", "vrestir_error_measure",
+    "vrestir_tonemap_default_settings", "vrestir_tonemap_params_from_settings", "vrestir_tonemap_execute",
     "vrestir_make_sky_envmap", "vrestir_make_emissive_shell", "vrestir_make_blackbody_lut", "vrestir_scene_load_vbx", "vrestir_scene_save_vbx",
 ]
 
@@ -209,6 +219,10 @@ def lib():
     L.vrestir_accum_frame_count.argtypes = [vp, C.POINTER(C.c_int)]
     L.vrestir_accum_execute.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
     L.vrestir_error_measure.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_float * 4), vp]
+    L.vrestir_tonemap_default_settings.argtypes = [C.POINTER(TonemapSettings)]
+    L.vrestir_tonemap_default_settings.restype = None
+    L.vrestir_tonemap_params_from_settings.argtypes = [C.POINTER(TonemapSettings), C.POINTER(TonemapParams)]
+    L.vrestir_tonemap_execute.argtypes = [C.c_int, C.POINTER(TonemapParams), vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), vp]
     L.vrestir_set_next_camera.argtypes = [vp, C.POINTER(Camera)]
     L.vrestir_get_pipeline_stats.argtypes = [vp, C.POINTER(PipelineStats)]
     L.vrestir_wait_output.argtypes = [vp, vp]

@@ -31,7 +31,8 @@ cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaS
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st);
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchInitialMBTraverse(const FrameParams& fp, const WfInitialMB& wi, cudaStream_t st);
-cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, cudaStream_t st);
+int initialMBStepBlocksPerSM();
+cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, int blocks, cudaStream_t st);
 // generic task-stream path (stage = 1 K1's final p-hat, 2 temporal, 3 spatial, 5 final): the stage body as an emit pass / a consume pass
 cudaError_t launchStageEmit(int stage, const FrameParams& fp, const MarchStreams& ms, const WfStream& cam, float* results, cudaStream_t st);
 cudaError_t launchStageConsume(int stage, const FrameParams& fp, const float* results, cudaStream_t st);

@@ -695,7 +695,7 @@ bool initialWavefrontMBOk(const vrestir_pass* p) {
 int runInitialWavefrontMB(vrestir_pass* p, const FrameParams& fp, cudaStream_t st) {
     const vrestir_params& m = p->P;
     const int B = m.mMaxBounces, M = m.mInitialM;
-    const size_t stateBytes = (size_t)K1MB_STRIDE * 4 + 16 + 48;                              // state block, done flag (+ padding), one light task
+    const size_t stateBytes = (size_t)K1MB_STRIDE * 4 + 2 * 48;                               // state block, one light task in each of the two (ping-pong) streams
     const size_t evalBytes = (size_t)(B + 1) * 48 + (size_t)MB_K1_EVAL_STRIDE * 4;
     size_t maxRows = p->mScratchBudget / ((stateBytes + evalBytes) * (size_t)fp.W);
     maxRows = std::min<size_t>(maxRows, ((size_t)1 << 32) / ((size_t)fp.W * K1MB_STRIDE) - 1);   // 32-bit record indices
@@ -708,22 +708,30 @@ int runInitialWavefrontMB(vrestir_pass* p, const FrameParams& fp, cudaStream_t s
         p->marchBlocks1 = sms * marchBlocksPerSM(1); p->marchBlocks3 = sms * marchBlocksPerSM(3);
     }
     const MarchKind kl = {m.mInitialLightingMipLevel, m.mInitialLightingUseLinearSampler, m.mInitialLightingTStepScale, 0, {0.f, 0.f, 0.f}};
-    WfInitialMB wi;
-    wi.state = (float*)p->k1mb.base;
-    wi.done = (uint8_t*)(wi.state + chunkPixels * K1MB_STRIDE);
-    wi.light.tasks = (uint4*)((char*)wi.done + (chunkPixels + 15) / 16 * 16);
-    wi.light.count = p->k1mb.counters; wi.light.cursor = p->k1mb.counters + 1; wi.light.capacity = (unsigned)chunkPixels;
+    // two task streams in turn: the step kernel of wave w walks the task list of wave w-1 (= the pixels still running) and fills the other one
+    WfStream streams[2];
+    float* const state = (float*)p->k1mb.base;
+    for (int k = 0; k < 2; k++) {
+        streams[k].tasks = (uint4*)(state + chunkPixels * K1MB_STRIDE) + (size_t)k * 3 * chunkPixels;
+        streams[k].count = p->k1mb.counters + 2 * k; streams[k].cursor = p->k1mb.counters + 2 * k + 1; streams[k].capacity = (unsigned)chunkPixels;
+    }
+    static int stepBlocksPerSM = 0;
+    if (!stepBlocksPerSM) stepBlocksPerSM = initialMBStepBlocksPerSM();
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    const int stepBlocks = (int)std::min<size_t>((chunkPixels + 127) / 128, (size_t)sms * stepBlocksPerSM);
     for (int r0 = fp.rowBegin; r0 < fp.rowEnd; r0 += chunkRows) {
         FrameParams fc = fp;
         fc.rowBegin = r0; fc.rowEnd = std::min(fp.rowEnd, r0 + chunkRows);
-        CK(cudaMemsetAsync(p->k1mb.counters, 0, 8, st));
+        WfInitialMB wi; wi.state = state; wi.light = streams[0]; wi.prev = streams[1];
+        CK(cudaMemsetAsync(p->k1mb.counters, 0, 16, st));
         CK(launchInitialMBTraverse(fc, wi, st));
-        CK(launchInitialMBStep(fc, wi, 1, st));
+        CK(launchInitialMBStep(fc, wi, 1, 0, st));
         p->launches += 2;
         for (int w = 0; w < M * B; w++) {
             CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
-            CK(cudaMemsetAsync(p->k1mb.counters, 0, 8, st));
-            CK(launchInitialMBStep(fc, wi, 0, st));
+            std::swap(wi.light, wi.prev);
+            CK(cudaMemsetAsync(wi.light.count, 0, 8, st));
+            CK(launchInitialMBStep(fc, wi, 0, stepBlocks, st));
             p->launches += 2;
         }
         int rc = runStageGeneric(p, 1, fc, st, &p->k1mbEval, 0, fc.rowEnd - fc.rowBegin); if (rc) return rc;

@@ -113,6 +113,83 @@ __global__ void k_error_final(const double* __restrict__ partial, int blocks, do
     }
 }
 
+// ---- ToneMapper (Source/RenderPasses/ToneMapper/{ToneMapping,Luminance}.ps.slang) ----------------------------------------
+__device__ __forceinline__ float tmLuminance(float3 c) { return c.x * 0.299f + c.y * 0.587f + c.z * 0.114f; }
+// Luminance.ps.slang:37-42 rendered into the lower-power-of-two target of ToneMapper::createLuminanceFbo with the linear
+// sampler (Falcor's default addressing: wrap): log2(max(1e-4, luminance(bilinear(src))))
+__global__ void k_tm_luminance(const float4* __restrict__ src, int w, int h, float* __restrict__ dst, int w2, int h2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= w2) return;
+    const float u = ((float)i + 0.5f) / (float)w2 * (float)w - 0.5f, v = ((float)j + 0.5f) / (float)h2 * (float)h - 0.5f;
+    const float u0 = floorf(u), v0 = floorf(v), fu = u - u0, fv = v - v0;
+    int x0 = (int)u0 % w, y0 = (int)v0 % h; if (x0 < 0) x0 += w; if (y0 < 0) y0 += h;
+    const int x1 = (x0 + 1) % w, y1 = (y0 + 1) % h;
+    const float4 a = src[(size_t)y0 * w + x0], b = src[(size_t)y0 * w + x1], c = src[(size_t)y1 * w + x0], d = src[(size_t)y1 * w + x1];
+    float3 t, bt, r;
+    t.x = __fmaf_rn(fu, b.x - a.x, a.x); t.y = __fmaf_rn(fu, b.y - a.y, a.y); t.z = __fmaf_rn(fu, b.z - a.z, a.z);
+    bt.x = __fmaf_rn(fu, d.x - c.x, c.x); bt.y = __fmaf_rn(fu, d.y - c.y, c.y); bt.z = __fmaf_rn(fu, d.z - c.z, c.z);
+    r.x = __fmaf_rn(fv, bt.x - t.x, t.x); r.y = __fmaf_rn(fv, bt.y - t.y, t.y); r.z = __fmaf_rn(fv, bt.z - t.z, t.z);
+    dst[(size_t)j * w2 + i] = log2f(fmaxf(0.0001f, tmLuminance(r)));
+}
+// generateMips: one 2x2 box level, ((a + b) + (c + d)) * 0.25 (a 1-wide / 1-high level averages the two texels it has)
+__global__ void k_tm_mip(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst, int dw, int dh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= dw) return;
+    const int x0 = min(2 * i, sw - 1), x1 = min(2 * i + 1, sw - 1), y0 = min(2 * j, sh - 1), y1 = min(2 * j + 1, sh - 1);
+    dst[(size_t)j * dw + i] = ((src[(size_t)y0 * sw + x0] + src[(size_t)y0 * sw + x1]) + (src[(size_t)y1 * sw + x0] + src[(size_t)y1 * sw + x1])) * 0.25f;
+}
+__device__ __forceinline__ float3 tmUc2(float3 c) {
+    const float A = 0.22f, B = 0.3f, C = 0.1f, D = 0.2f, E = 0.01f, F = 0.3f;
+    float3 o;
+    o.x = ((c.x * (A * c.x + C * B) + D * E) / (c.x * (A * c.x + B) + D * F)) - (E / F);
+    o.y = ((c.y * (A * c.y + C * B) + D * E) / (c.y * (A * c.y + B) + D * F)) - (E / F);
+    o.z = ((c.z * (A * c.z + C * B) + D * E) / (c.z * (A * c.z + B) + D * F)) - (E / F);
+    return o;
+}
+// ToneMapping.ps.slang:142-167
+__global__ void k_tonemap(const float4* __restrict__ src, float4* __restrict__ dst, size_t n, vrestir_tonemap_params P, const float* __restrict__ avgLogLum) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float4 color = src[p];
+    float3 c = make_float3(color.x, color.y, color.z);
+    if (P.autoExposure) {
+        const float avgLuminance = exp2f(*avgLogLum);
+        const float k = 0.042f / avgLuminance;
+        c.x *= k; c.y *= k; c.z *= k;
+    }
+    const float* M = P.colorTransform;   // mul(color, (float3x3)M): row vector times matrix, row-major storage
+    float3 t = make_float3(c.x * M[0] + c.y * M[3] + c.z * M[6], c.x * M[1] + c.y * M[4] + c.z * M[7], c.x * M[2] + c.y * M[5] + c.z * M[8]);
+    switch (P.op) {
+        case VRESTIR_TONEMAP_REINHARD: { const float l = tmLuminance(t), r = l / (l + 1.f), k = r / l; t.x *= k; t.y *= k; t.z *= k; break; }
+        case VRESTIR_TONEMAP_REINHARD_MODIFIED: {
+            const float l = tmLuminance(t), r = l * (1.f + l / (P.whiteMaxLuminance * P.whiteMaxLuminance)) * (1.f + l), k = r / l;
+            t.x *= k; t.y *= k; t.z *= k; break;
+        }
+        case VRESTIR_TONEMAP_HEJI_HABLE_ALU: {
+            t.x = fmaxf(0.f, t.x - 0.004f); t.y = fmaxf(0.f, t.y - 0.004f); t.z = fmaxf(0.f, t.z - 0.004f);
+            t.x = (t.x * (6.2f * t.x + 0.5f)) / (t.x * (6.2f * t.x + 1.7f) + 0.06f);
+            t.y = (t.y * (6.2f * t.y + 0.5f)) / (t.y * (6.2f * t.y + 1.7f) + 0.06f);
+            t.z = (t.z * (6.2f * t.z + 0.5f)) / (t.z * (6.2f * t.z + 1.7f) + 0.06f);
+            t.x = powf(t.x, 2.2f); t.y = powf(t.y, 2.2f); t.z = powf(t.z, 2.2f); break;
+        }
+        case VRESTIR_TONEMAP_HABLE_UC2: {
+            t = tmUc2(make_float3(2.f * t.x, 2.f * t.y, 2.f * t.z));
+            const float ws = 1.f / tmUc2(make_float3(P.whiteScale, P.whiteScale, P.whiteScale)).x;
+            t.x *= ws; t.y *= ws; t.z *= ws; break;
+        }
+        case VRESTIR_TONEMAP_ACES: {
+            t.x *= 0.6f; t.y *= 0.6f; t.z *= 0.6f;
+            const float A = 2.51f, B = 0.03f, C = 2.43f, D = 0.59f, E = 0.14f;
+            t.x = __saturatef((t.x * (A * t.x + B)) / (t.x * (C * t.x + D) + E));
+            t.y = __saturatef((t.y * (A * t.y + B)) / (t.y * (C * t.y + D) + E));
+            t.z = __saturatef((t.z * (A * t.z + B)) / (t.z * (C * t.z + D) + E)); break;
+        }
+        default: break;   // linear
+    }
+    if (P.clamp) { t.x = __saturatef(t.x); t.y = __saturatef(t.y); t.z = __saturatef(t.z); }
+    dst[p] = make_float4(t.x, t.y, t.z, color.w);
+}
+
 void freeAccum(vrestir_accumulator* a) {
     if (a->sum) cudaFree(a->sum);
     if (a->corr) cudaFree(a->corr);
@@ -237,5 +314,90 @@ int vrestir_error_measure(int device, const float* source, const float* referenc
     error_rgb_avg[3] = (error_rgb_avg[0] + error_rgb_avg[1] + error_rgb_avg[2]) / 3.f;
     return VRESTIR_OK;
 }
+
+
+// ---- ToneMapper host side (Source/RenderPasses/ToneMapper/ToneMapper.cpp:502-522, F/Utils/Color/ColorUtils.h:60-216) -------
+namespace {
+void mat3mul(const double* a, const double* b, double* o) { double t[9]; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += a[i * 3 + k] * b[k * 3 + j]; t[i * 3 + j] = s; } memcpy(o, t, sizeof(t)); }
+// matrices below are written row-major for column vectors (c' = M c); the reference's glm initialisers list columns
+const double kRGBtoXYZ[9] = {0.4123907992659595, 0.3575843393838780, 0.1804807884018343, 0.2126390058715104, 0.7151686787677559, 0.0721923153607337, 0.0193308187155918, 0.1191947797946259, 0.9505321522496608};
+const double kXYZtoRGB[9] = {3.2409699419045213, -1.5373831775700935, -0.4986107602930033, -0.9692436362808798, 1.8759675015077206, 0.0415550574071756, 0.0556300796969936, -0.2039769588889765, 1.0569715142428784};
+const double kXYZtoLMS[9] = {0.7328, 0.4296, -0.1624, -0.7036, 1.6975, 0.0061, 0.0030, 0.0136, 0.9834};
+const double kLMStoXYZ[9] = {1.096123820835514, -0.278869000218287, 0.182745179382773, 0.454369041975359, 0.473533154307412, 0.072097803717229, -0.009627608738429, -0.005698031216113, 1.015325639954543};
+void temperatureToXYZ(float T, float out[3]) {   // colorTemperatureToXYZ, Y = 1
+    const double t = T, t2 = t * t, t3 = t * t * t;
+    double xc = T < 4000.f ? -0.2661239e9 / t3 - 0.2343580e6 / t2 + 0.8776956e3 / t + 0.179910 : -3.0258469e9 / t3 + 2.1070379e6 / t2 + 0.2226347e3 / t + 0.240390;
+    const double x = xc, x2 = x * x, x3 = x * x * x;
+    double yc = T < 2222.f ? -1.1063814 * x3 - 1.34811020 * x2 + 2.18555832 * x - 0.20219683
+              : (T < 4000.f ? -0.9549476 * x3 - 1.37418593 * x2 + 2.09137015 * x - 0.16748867 : 3.0817580 * x3 - 5.87338670 * x2 + 3.75112997 * x - 0.37001483);
+    const float xf = (float)xc, yf = (float)yc;
+    out[0] = xf * 1.f / yf; out[1] = 1.f; out[2] = (1.f - xf - yf) * 1.f / yf;
+}
+}  // namespace
+
+void vrestir_tonemap_default_settings(vrestir_tonemap_settings* s) {
+    if (!s) return;
+    memset(s, 0, sizeof(*s));
+    s->exposureCompensation = 0.f; s->autoExposure = 0; s->filmSpeed = 100.f; s->whiteBalance = 0; s->whitePoint = 6500.f;
+    s->op = VRESTIR_TONEMAP_ACES; s->clamp = 1; s->whiteMaxLuminance = 1.f; s->whiteScale = 11.2f; s->fNumber = 1.f; s->shutter = 1.f;
+}
+int vrestir_tonemap_params_from_settings(const vrestir_tonemap_settings* s, vrestir_tonemap_params* out) try {
+    if (!s || !out) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->op > VRESTIR_TONEMAP_ACES) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "unknown tone-mapping operator");
+    double wb[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (s->whiteBalance) {
+        if (s->whitePoint < 1667.f || s->whitePoint > 25000.f) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "white point outside 1667 K .. 25000 K");
+        double MA[9], invMA[9];
+        mat3mul(kXYZtoLMS, kRGBtoXYZ, MA); mat3mul(kXYZtoRGB, kLMStoXYZ, invMA);
+        float d65[3], src[3]; temperatureToXYZ(6500.f, d65); temperatureToXYZ(s->whitePoint, src);
+        double D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 3; i++) {
+            float wd = 0.f, ws = 0.f;
+            for (int k = 0; k < 3; k++) { wd += (float)kXYZtoLMS[i * 3 + k] * d65[k]; ws += (float)kXYZtoLMS[i * 3 + k] * src[k]; }
+            D[i * 4] = (double)(wd / ws);
+        }
+        double t[9]; mat3mul(D, MA, t); mat3mul(invMA, t, wb);
+    }
+    const float exposureScale = powf(2.f, s->exposureCompensation);
+    float manual = 1.f;
+    if (!s->autoExposure) manual = ((1.f / 100.f) * s->filmSpeed) / (s->shutter * s->fNumber * s->fNumber);
+    // the shader computes mul(color, (float3x3)colorTransform) with the glm (column-vector) matrix uploaded as is, i.e. color * M^T
+    // in HLSL's row-vector reading = M * color: store M^T so that the kernel's row-vector product gives M * color
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out->colorTransform[j * 3 + i] = (float)wb[i * 3 + j] * exposureScale * manual;
+    out->op = s->op; out->autoExposure = s->autoExposure; out->clamp = s->clamp; out->whiteScale = std::max(0.001f, s->whiteScale); out->whiteMaxLuminance = s->whiteMaxLuminance;
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+
+int vrestir_tonemap_execute(int device, const vrestir_tonemap_params* P, const float* src, float* dst, int width, int height, float* avg_log_luminance_out, void* stream) try {
+    if (!P || !src || !dst || width < 1 || height < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad argument");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return setError(VRESTIR_ERR_CUDA, std::string("no CUDA device: the tone mapper has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    CKP(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* lum = nullptr;
+    const float* avg = nullptr;
+    if (P->autoExposure) {
+        int w2 = 1, h2 = 1; while (w2 * 2 <= width) w2 *= 2; while (h2 * 2 <= height) h2 *= 2;     // getLowerPowerOf2
+        size_t total = 0; for (int a = w2, b = h2;; a = std::max(1, a / 2), b = std::max(1, b / 2)) { total += (size_t)a * b; if (a == 1 && b == 1) break; }
+        CKP(cudaMallocAsync((void**)&lum, total * sizeof(float), st));
+        k_tm_luminance<<<dim3((w2 + 127) / 128, h2), 128, 0, st>>>((const float4*)src, width, height, lum, w2, h2);
+        float* cur = lum; int cw = w2, ch = h2;
+        while (cw > 1 || ch > 1) {
+            const int nw = std::max(1, cw / 2), nh = std::max(1, ch / 2);
+            float* nxt = cur + (size_t)cw * ch;
+            k_tm_mip<<<dim3((nw + 127) / 128, nh), 128, 0, st>>>(cur, cw, ch, nxt, nw, nh);
+            cur = nxt; cw = nw; ch = nh;
+        }
+        avg = cur;
+        if (avg_log_luminance_out) CKP(cudaMemcpyAsync(avg_log_luminance_out, avg, 4, cudaMemcpyDeviceToHost, st));
+    }
+    const size_t n = (size_t)width * height;
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)src, (float4*)dst, n, *P, avg);
+    CKP(cudaGetLastError());
+    if (lum) CKP(cudaFreeAsync(lum, st));
+    if (avg_log_luminance_out && P->autoExposure) CKP(cudaStreamSynchronize(st));
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
 
 }  // extern "C"

@@ -937,21 +937,18 @@ VRD Reservoir mbLoadRes(const float* r) {
 #ifndef VR_MBSTEP_MINB
 #define VR_MBSTEP_MINB 4
 #endif
-// first != 0: the wave after k_initial_traverse (state holds the RNG and the distance candidates only)
+// One pixel advances to its next shadow march (or finishes).  first: the wave after k_initial_mb_traverse (the state block holds
+// the RNG and the distance candidates only).  Returns whether a march was emitted (`shadow`), i.e. whether the pixel goes on.
 template <int B>
-__global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FrameParams fp, WfInitialMB wi, int first) {
-    int x, y;
-    const bool inFrame = pixelOf(fp, x, y);
-    const int pixelId = inFrame ? y * fp.W + x : fp.rowBegin * fp.W;
-    const unsigned local = (unsigned)(pixelId - fp.rowBegin * fp.W);
+__device__ __forceinline__ bool mbAdvancePixel(const FrameParams& fp, const WfInitialMB& wi, bool first, bool active, int x, int y, unsigned local, Ray& shadow) {
+    const int pixelId = fp.rowBegin * fp.W + (int)local;
     const unsigned recBase = local * K1MB_STRIDE;
     float* st = wi.state + recBase;
     const SamplingOptions& options = fp.initial;
     const vrestir_volume_desc& vd = c_scene.vol;
     const int M = fp.initialM;
     bool hasTask = false;
-    Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
-    if (inFrame && (first || !wi.done[local])) {
+    if (active) {
         const float3 sigA = v3(vd.sigma_a), sigS = v3(vd.sigma_s);
         const Ray primary = primaryRay(fp, x, y);
         SampleGenerator sg;
@@ -1123,13 +1120,11 @@ __global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FramePa
         }
         if (finished) {
             // the streamed reservoir; its p-hat under the spatial options is evaluated by the emit / consume passes that follow
-            wi.done[local] = 1;
             storeReservoir(fp.cur, pixelId, finalReservoir);
             const int mib = decodeMaxIndirectBounces<B>(finalReservoir.sampledPixel);
 #pragma unroll
             for (int b = 0; b < B - 1; b++) if (b < mib) fp.extCur[(size_t)pixelId * (B - 1) + b] = finalExtra[b];
         } else {
-            if (first) wi.done[local] = 0;
             ((float4*)(st + MBK_SG))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
             mbStoreRes(st + MBK_FIN, finalReservoir); mbStoreRes(st + MBK_COMB, combinedReservoir);
             st[MBK_PATH] = ray.origin.x; st[MBK_PATH + 1] = ray.origin.y; st[MBK_PATH + 2] = ray.origin.z;
@@ -1144,8 +1139,33 @@ __global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FramePa
             mbStorePend(st + MBK_PEND, c);
         }
     }
-    wfEmitRay(wi.light, hasTask, shadow, options.lightingMipLevel, false, wi.state, recBase + MBK_VIS);
+    return hasTask;
 }
+// first != 0: one thread per pixel of the band (8x4 tiles); afterwards: grid-stride over the previous wave's task list
+template <int B>
+__global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FrameParams fp, WfInitialMB wi, int first) {
+    if (first) {
+        int x, y;
+        const bool inFrame = pixelOf(fp, x, y);
+        const unsigned local = inFrame ? (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) : 0u;
+        Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
+        const bool hasTask = mbAdvancePixel<B>(fp, wi, true, inFrame, x, y, local, shadow);
+        wfEmitRay(wi.light, hasTask, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
+        return;
+    }
+    const unsigned total = min(*wi.prev.count, wi.prev.capacity);
+    for (unsigned t0 = blockIdx.x * blockDim.x; t0 < total; t0 += gridDim.x * blockDim.x) {   // block-uniform trip count: wfEmitRay is warp-collective
+        const unsigned t = t0 + threadIdx.x;
+        const bool active = t < total;
+        unsigned local = 0;
+        if (active) local = __ldg(&wi.prev.tasks[3 * (size_t)t + 2]).x / K1MB_STRIDE;   // the task's result slot identifies its pixel
+        const int pixelId = fp.rowBegin * fp.W + (int)local;
+        Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
+        const bool hasTask = mbAdvancePixel<B>(fp, wi, false, active, pixelId % fp.W, pixelId / fp.W, local, shadow);
+        wfEmitRay(wi.light, hasTask, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
+    }
+}
+
 
 // distance candidates of the primary ray into the multi-bounce state block (same traversal as k_initial_traverse)
 __global__ void __launch_bounds__(128, VR_TRAV_MINB) k_initial_mb_traverse(FrameParams fp, WfInitialMB wi) {
@@ -1261,11 +1281,14 @@ cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaSt
         default: kern<4><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                     \
     }
 cudaError_t launchInitialMBTraverse(const FrameParams& fp, const WfInitialMB& wi, cudaStream_t st) { k_initial_mb_traverse<<<gridForWf(fp), 128, 0, st>>>(fp, wi); return cudaGetLastError(); }
-cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, cudaStream_t st) {
+int initialMBStepBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_initial_mb_step<4>, 128, 0); return n > 0 ? n : 1; }
+// first: one thread per pixel of the band; afterwards `blocks` CTAs stride over the previous wave's task list
+cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, int blocks, cudaStream_t st) {
+    const dim3 grid = first ? gridForWf(fp) : dim3((unsigned)blocks);
     switch (fp.maxBounces) {
-        case 2: k_initial_mb_step<2><<<gridForWf(fp), 128, 0, st>>>(fp, wi, first); break;
-        case 3: k_initial_mb_step<3><<<gridForWf(fp), 128, 0, st>>>(fp, wi, first); break;
-        default: k_initial_mb_step<4><<<gridForWf(fp), 128, 0, st>>>(fp, wi, first); break;
+        case 2: k_initial_mb_step<2><<<grid, 128, 0, st>>>(fp, wi, first); break;
+        case 3: k_initial_mb_step<3><<<grid, 128, 0, st>>>(fp, wi, first); break;
+        default: k_initial_mb_step<4><<<grid, 128, 0, st>>>(fp, wi, first); break;
     }
     return cudaGetLastError();
 }

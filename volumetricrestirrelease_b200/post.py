@@ -111,3 +111,66 @@ class ErrorMeasurePass:
             self.runningError = tuple(s * r + (np.float32(1) - s) * e for r, e in zip(self.runningError, err))
             self.runningAvgError = s * self.runningAvgError + (np.float32(1) - s) * avg
         return self.measurements
+
+
+TONEMAP_OPERATORS = {"Linear": 0, "Reinhard": 1, "ReinhardModified": 2, "HejiHableAlu": 3, "HableUc2": 4, "Aces": 5}
+
+
+class ToneMapper:
+    """``createPass("ToneMapper", {"autoExposure": ..., "exposureCompensation": ..., "operator": ToneMapOp.Aces, ...})`` — the
+    display end of the reference's graphs (Source/RenderPasses/ToneMapper/ToneMapper.cpp:36-49 keys, ToneMapper.h:111-125 defaults).
+    Clamps of the setters as in ToneMapper.cpp:401-479."""
+
+    KEYS = ("exposureCompensation", "autoExposure", "exposureValue", "filmSpeed", "whiteBalance", "whitePoint", "operator", "clamp",
+            "whiteMaxLuminance", "whiteScale", "fNumber", "shutter")
+
+    def __init__(self, d=None, device=0):
+        self._lib = capi.lib()
+        self.device = device
+        self._s = capi.TonemapSettings()
+        self._lib.vrestir_tonemap_default_settings(C.byref(self._s))
+        self.avgLogLuminance = None
+        for k, v in dict(d or {}).items():
+            self.set(k, v)
+
+    def set(self, key, value):
+        s = self._s
+        clampf = lambda v, lo, hi: max(lo, min(hi, float(v)))
+        if key == "exposureCompensation": s.exposureCompensation = clampf(value, -12.0, 12.0)
+        elif key == "autoExposure": s.autoExposure = int(bool(value))
+        elif key == "filmSpeed": s.filmSpeed = clampf(value, 1.0, 6400.0)
+        elif key == "whiteBalance": s.whiteBalance = int(bool(value))
+        elif key == "whitePoint": s.whitePoint = clampf(value, 1905.0, 25000.0)
+        elif key == "operator": s.op = TONEMAP_OPERATORS[value] if isinstance(value, str) else int(value)
+        elif key == "clamp": s.clamp = int(bool(value))
+        elif key == "whiteMaxLuminance": s.whiteMaxLuminance = float(value)
+        elif key == "whiteScale": s.whiteScale = max(0.001, float(value))
+        elif key == "fNumber": s.fNumber = clampf(value, 0.1, 100.0)
+        elif key == "shutter": s.shutter = clampf(value, 0.1, 10000.0)
+        elif key == "exposureValue":   # aperture priority (the default exposure mode): the shutter follows the EV (ToneMapper.cpp:294-303)
+            import math
+            ev = clampf(value, math.log2(0.1 * 0.1 * 0.1), math.log2(10000.0 * 100.0 * 100.0))
+            s.shutter = clampf(2.0 ** ev / (s.fNumber * s.fNumber), 0.1, 10000.0)
+        else:
+            import warnings
+            warnings.warn(f"Unknown field '{key}' in a ToneMapper dictionary")
+
+    @property
+    def exposureValue(self):
+        import math
+        return math.log2(self._s.shutter * self._s.fNumber * self._s.fNumber)
+
+    def params(self):
+        p = capi.TonemapParams()
+        capi.check(self._lib.vrestir_tonemap_params_from_settings(C.byref(self._s), C.byref(p)))
+        return p
+
+    def execute(self, src_ptr, dst_ptr, width, height, stream=None, want_average=False):
+        """src / dst: CUDA addresses of width*height float4.  want_average: also return the auto-exposure average log2 luminance."""
+        p = self.params()
+        avg = C.c_float(0.0)
+        capi.check(self._lib.vrestir_tonemap_execute(int(self.device), C.byref(p), C.c_void_p(src_ptr), C.c_void_p(dst_ptr), int(width), int(height),
+                                                     C.byref(avg) if (want_average and self._s.autoExposure) else None, C.c_void_p(stream) if stream else None))
+        if want_average and self._s.autoExposure:
+            self.avgLogLuminance = avg.value
+        return self.avgLogLuminance if want_average else None
