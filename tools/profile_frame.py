@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1)
     ap.add_argument("--pipeline", type=int, default=0)
     ap.add_argument("--per-pixel", action="store_true")
+    ap.add_argument("--set", action="append", default=[], help="pass dictionary entry key=value (e.g. mSortLightTasks=0)")
     a = ap.parse_args()
     sys.argv = [sys.argv[0], "--config", str(a.config)] + (["--width", str(a.width)] if a.width else []) + (["--height", str(a.height)] if a.height else [])
     args = bench.parse()
@@ -33,6 +34,8 @@ def main():
     R = bench.Runner(args, args.width, args.height, scene, params, a.pipeline, 0, 1, 0, volumes)
     if args.config == 5:
         scene.volume.release_chain()
+    if a.set:
+        R.gp.updateDict({kv.split("=")[0]: float(kv.split("=")[1]) for kv in a.set})
     for _ in range(a.warm):
         R.step()
     torch.cuda.synchronize()

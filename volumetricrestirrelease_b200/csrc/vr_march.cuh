@@ -373,8 +373,10 @@ struct AnalyticMarcher : MarchTrav {
 
 // Persistent-lane pool over one task stream.  tasks: 3 (explicit, prepared) or 2 (camera) x uint4 per task; total: tasks in
 // the stream; cursor: next unclaimed.
+// perm (nullable): the order in which the tasks are claimed (bucket order, k_bin_scatter); identity otherwise
 template <class M>
-__device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g) {
+__device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g,
+                                          const unsigned* __restrict__ perm = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -393,7 +395,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
                 base = __shfl_sync(FULL, base, 0);
                 if (m.phase < 2) {
                     const unsigned idx = base + __popc(parked & ltMask);
-                    if (idx < total) m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * idx, kind, g);
+                    if (idx < total) m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g);
                 }
                 if (base + n >= total) drained = true;
             }
