@@ -197,3 +197,22 @@ def test_two_passes_on_one_device_interleaved():
     for f in range(4):
         assert np.array_equal(both[0][f].view(np.uint32), alone_a[f].view(np.uint32)), f"pass A frame {f}"
         assert np.array_equal(both[1][f].view(np.uint32), alone_b[f].view(np.uint32)), f"pass B frame {f}"
+
+
+def test_hand_assembled_vbx_asset_renders_like_the_oracle():
+    """The .vbx asset assembled byte by byte from GVDB_FILESPEC.txt (tests/golden/vbx_fixture, checked voxel for voxel in
+    tests/test_vbx.py) loaded through vrestir_scene_load_vbx and rendered with full reuse: staged parity against the oracle."""
+    import os
+    from volumetricrestirrelease_b200 import Scene
+    prefix = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vbx_fixture", "blobs")
+    sc = Scene()
+    sc.loadGVDBVolume(prefix, sigma_a=(1, 1, 1), sigma_s=(9, 9, 9), numMips=3, densityScale=1.5)
+    sc.setEnvMap((256, 128), seed=7)
+    sc.setEnvMapIntensity(1.5)
+    sc.frame_camera(1.0)
+    out = staged(VolumetricReSTIRParams(), sc, W, H, frames=2, camera_path=_path(sc, scale=0.5))
+    check_staged(out, W, H, "vbx fixture")
+    # brick bounds of a loaded asset feed the residual-ratio tracker
+    p = VolumetricReSTIRParams(mFinalVisibilityTrackingMethod=capi.kResidualRatioTracking, mFinalLightTrackingMethod=capi.kResidualRatioTracking)
+    out = staged(p, sc, W, H, frames=1)
+    check_staged(out, W, H, "vbx fixture, residual ratio tracking", budget=5 * FLIP_BUDGET)

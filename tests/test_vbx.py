@@ -131,3 +131,54 @@ def test_vbx_malformed_files_are_rejected(tmp_path):
     attempt("childid", lambda r: struct.pack_into("<Q", r, o_child, (cnt[0] + 7) << 16))
     # the untouched file still loads
     Scene().loadGVDBVolume(prefix)
+
+
+def test_hand_assembled_vbx_fixture_loads_voxel_exact():
+    """Second witness for the .vbx reader: the asset under tests/golden/vbx_fixture was assembled byte by byte by a Python
+    script written from GVDB_FILESPEC.txt and the reference loader's read order (tests/golden/make_vbx_fixture.py), with bricks
+    stored in reverse atlas order.  Every voxel of every level must come back: mip 0 exactly (fp32), the coarse / conservative
+    levels within half a UNORM8 code of the level's maximum (the loader quantises them like F/Scene/Scene.cpp:3164-3174), and a
+    conservative code is never 0 where the value is positive."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_vbx_fixture", os.path.join(here, "golden", "make_vbx_fixture.py"))
+    fx = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fx)
+    prefix = os.path.join(here, "golden", "vbx_fixture", "blobs")
+    # the committed files are what the script writes today (the fixture cannot drift from its generator)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        for m, c, dense in fx.levels():
+            name = f"blobs_mip{m}{'c' if c else ''}.vbx"
+            fx.write_vbx(os.path.join(tmp, name), dense, fx.DIM)
+            assert open(os.path.join(tmp, name), "rb").read() == open(os.path.join(here, "golden", "vbx_fixture", name), "rb").read(), name
+    sc = Scene()
+    vol = sc.loadGVDBVolume(prefix, numMips=fx.NUM_MIPS, densityScale=0.5)
+    g = vol.grid.contents
+    assert g.volume.numMips == fx.NUM_MIPS
+    for m, c, dense in fx.levels():
+        slot = m + (8 if c else 0)
+        s = g.slots[slot]
+        assert s.valid and s.top_lev == 1 and tuple(int(v) for v in s.bmax) == dense.shape[::-1]
+        got = vol.dense_mip(m, c)
+        assert got.shape == dense.shape
+        if m == 0 and not c:
+            assert np.array_equal(got.view(np.uint32), dense.view(np.uint32))
+            assert s.atlas_format == 0
+        else:
+            mx = float(dense.max())
+            assert s.atlas_format == 1 and abs(s.max_value - mx) <= 1e-6 * mx
+            # rounding to the nearest code; a conservative level lifts a positive value below half a code to code 1
+            assert np.abs(got - dense).max() <= (1.0 if c else 0.5) * mx / 255 * 1.0001
+            if c:
+                assert ((got > 0) == (dense / mx >= 1e-9)).all()      # conservative: positive stays positive
+        # transforms of the level: voxel (0,0,0) corner and the far corner map to the same model-space box for every mip
+        M = np.array(list(s.xform), dtype=np.float64).reshape(4, 4)
+        lo = np.array([0, 0, 0, 1.0]) @ M
+        hi = np.array([dense.shape[2], dense.shape[1], dense.shape[0], 1.0]) @ M
+        np.testing.assert_allclose(lo[:3], [-0.5 * d * fx.VOXEL for d in fx.DIM], rtol=1e-6)
+        np.testing.assert_allclose(hi[:3], [0.5 * d * fx.VOXEL for d in fx.DIM], rtol=1e-6)
+    # brick bounds of mip 0 from the raw floats (F/Scene/Scene.cpp:2981-3012): max over all bricks = the grid maximum
+    n0 = g.slots[0].node_count[0]
+    mx = max(g.slots[0].nodes[0][i].bounds[1] for i in range(n0))
+    assert mx == float(fx.field().max())
