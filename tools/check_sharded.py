@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--height", type=int, default=360)
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--level", type=int, default=2, help="mPipelineFrames level of the sharded pass")
+    ap.add_argument("--motion", type=float, default=0.0, help="camera step per frame in world units (large: the history all-gather fallback must kick in)")
     a = ap.parse_args()
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -40,11 +41,15 @@ def main():
     c_full = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     bad = 0
     ref = []
+    pos0 = np.array(scene.camera.position)
+    path = [tuple(pos0 + np.array([0.3, 1.0, 0.1]) * a.motion * f) for f in range(a.frames)]
     for f in range(a.frames):   # the reference frames first: two passes alternating would re-upload the constant bank every frame
+        scene.camera.position = path[f]; full.updateCamera()
         full.execute(c_full.data_ptr())   # and (correctly) throw every prefetch away
         torch.cuda.synchronize()
         ref.append(c_full[r0:r1].cpu().numpy().view(np.uint32).copy())
     for f in range(a.frames):
+        scene.camera.position = path[f]; gp.updateCamera()
         sp.execute(c_band.data_ptr())
         gp.wait_output()
         x = c_band[r0:r1].cpu().numpy().view(np.uint32)
@@ -54,7 +59,7 @@ def main():
     dist.all_reduce(t)
     if rank == 0:
         print(f"[check_sharded] world {world} bands {sp.bands} frames {a.frames} pipelining level {a.level}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
-              f"pipeline {gp.pipeline_stats()}")
+              f"pipeline {gp.pipeline_stats()}, history all-gathers {sp.history_gathers}")
     dist.destroy_process_group()
     sys.exit(1 if int(t[0]) else 0)
 

@@ -105,6 +105,35 @@ def exchange_row_halo(planes, band, halo, rank, world_size, bands=None, group=No
     return works
 
 
+def gather_row_bands(planes, bands, rank, group=None):
+    """Temporal-history fallback: make every rank's band of `planes` visible on all ranks.  One broadcast per
+    band and plane (bands differ in size when cost-balanced).  Stream-ordered like the halo exchange, no host synchronisation."""
+    works = []
+    for t in planes:
+        for r, (a, b) in enumerate(bands):
+            if b > a:
+                works.append(dist.broadcast(t[a:b], src=r, group=group, async_op=True))
+    return works
+
+
+def reprojection_row_bound(cam_prev, cam_cur, corners_world, height):
+    """Upper bound, in image rows, on how far a world point inside the volume's bounding box can move between the previous and
+    the current camera (K2 reads the history at the reprojected pixel, VR/TemporalReuse.cs.slang:168-209).  Both projections of
+    the 8 box corners; a projective map moves interior points of the box at most ~ as far as its most-moved corner, a 25 % +
+    2-row margin covers the perspective non-linearity.  Returns inf when a corner lies behind either camera."""
+    def rows(cam):
+        V = np.array(list(cam.viewMat), dtype=np.float64).reshape(4, 4)
+        P = np.array(list(cam.projMat), dtype=np.float64).reshape(4, 4)
+        c = np.concatenate([corners_world, np.ones((len(corners_world), 1))], axis=1) @ V @ P
+        if (c[:, 3] <= 1e-6).any():
+            return None
+        return (-0.5 * c[:, 1] / c[:, 3] + 0.5) * height
+    a, b = rows(cam_prev), rows(cam_cur)
+    if a is None or b is None:
+        return float("inf")
+    return float(np.abs(a - b).max()) * 1.25 + 2.0
+
+
 class ShardedPass:
     """Drives one ``VolumetricReSTIR`` pass per rank over its row band with halo exchanges between the stages."""
 
@@ -118,6 +147,8 @@ class ShardedPass:
         self.temporal_halo = temporal_halo
         min_band = min(b[1] - b[0] for b in self.bands)
         self.max_halo = min_band
+        self._prev_cam = None
+        self.history_gathers = 0      # frames whose history went through the all-gather fallback (motion beyond the halo)
 
     def balance(self, background_weight=0.05, refine=0, out_color_ptr=None):
         """Re-partition the rows by estimated cost (the scaling limiter of row sharding is load imbalance,
@@ -132,7 +163,7 @@ class ShardedPass:
         FEAT_DTYPE = np.dtype([("noReflectiveSurface", np.int32), ("transmittance", np.float32)])
         if self.world == 1:
             return self.band
-        min_rows = max(16, self.temporal_halo)
+        min_rows = max(16, self.temporal_halo, int(math.ceil(self.p.params.mSampleRadius)))
         self.p.setRowBand(0, self.H)
         self.p.execute_stage(0)
         feat = self.p.get_buffer(capi.BUF_FEATURES).view(FEAT_DTYPE).reshape(self.H, self.W)
@@ -185,7 +216,10 @@ class ShardedPass:
     def _exchange(self, buffers, halo, wait=True):
         if self.world == 1:
             return []
-        halo = min(int(halo), self.max_halo)
+        if int(halo) > self.max_halo:
+            # a tap would land in rows that no neighbour ever sent: the sharded frame would silently differ from the single-GPU one
+            raise capi.VRestirError(capi.ERR_INVALID_ARGUMENT, f"halo of {int(halo)} rows exceeds the smallest row band ({self.max_halo} rows): "
+                                    "use fewer ranks, a smaller mSampleRadius or larger bands")
         planes = []
         for b in buffers:
             planes += self._planes(b)
@@ -207,6 +241,17 @@ class ShardedPass:
         for w in getattr(self, "_pending_history", []):   # the history halo of the previous frame travelled during K0/K1
             w.wait()
         self._pending_history = []
+        if prm.mEnableTemporalReuse and not prm.mUseReference and self._history_needs_gather():
+            # the camera of THIS frame (known only now) reprojects further than the halo that travelled, or the volume carries a
+            # velocity field: every band of the history is made visible everywhere before K2 reads it
+            B_ = prm.mMaxBounces
+            bufs = [capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL] + ([capi.BUF_EXTRA_TEMPORAL] if B_ > 1 else [])
+            planes = []
+            for b in bufs:
+                planes += self._planes(b)
+            for w in gather_row_bands(planes, self.bands, self.rank):
+                w.wait()
+            self.history_gathers += 1
         p.execute_stage(2, 0, out_color_ptr, out_mvec_ptr, stream)
         if prm.mEnableSpatialReuse and not prm.mUseReference:
             for r in range(prm.mSpatialReuseRounds):
@@ -218,6 +263,21 @@ class ShardedPass:
         p.execute_stage(5, 0, out_color_ptr, out_mvec_ptr, stream)
         p.execute_stage(6, 0, out_color_ptr, out_mvec_ptr, stream)
         if prm.mEnableTemporalReuse and not prm.mUseReference:
-            # history for the next frame's K2: reprojected taps land within `temporal_halo` rows of the band
+            # history for the next frame's K2.  Reprojected taps normally land within `temporal_halo` rows of the band (halo
+            # exchange with the two neighbours); when the camera moved further than that between the last two frames (the best
+            # predictor of the next step), or the volume carries a velocity field, every band is made visible everywhere.
             bufs = [capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL] + ([capi.BUF_EXTRA_TEMPORAL] if B > 1 else [])
-            self._pending_history = self._exchange(bufs, self.temporal_halo, wait=False)
+            self._pending_history = self._exchange(bufs, min(self.temporal_halo, self.max_halo), wait=False)
+            self._prev_cam = self.p._scene.camera.data(self.W, self.H)      # the camera this history was rendered with
+
+    def _history_needs_gather(self):
+        """Called at the start of a frame, when its camera is known: can K2's reprojected taps leave band + halo?"""
+        sc = self.p._scene
+        if self._prev_cam is None or self.p.frame_count() == 0:
+            return False                                   # no history yet (first frame of an option epoch)
+        vd = sc.volume.grid.contents.volume
+        if vd.hasVelocity and vd.hasAnimation:
+            return True                                    # the velocity field moves the reprojection point arbitrarily
+        lo, hi = sc.volume_bounds_world()
+        corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], dtype=np.float64)
+        return reprojection_row_bound(self._prev_cam, sc.camera.data(self.W, self.H), corners, self.H) > min(self.temporal_halo, self.max_halo)
