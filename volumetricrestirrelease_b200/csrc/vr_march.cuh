@@ -33,6 +33,12 @@ namespace vrd {
 #ifndef VR_PREFETCH_CHILD
 #define VR_PREFETCH_CHILD 1
 #endif
+// FAST sampler, optional: the two texel words of a sample are loaded one step ahead (when the lane steps to the position, not
+// when it samples it).  Meant to shorten the tail of a launch (a lone long ray pays the load latency every step).  Measured
+// neutral at 1080p and on a 640x360 frame (floor regime), slower with the extra registers: off (profiles/r02_negative_results.txt)
+#ifndef VR_SAMPLE_PREFETCH
+#define VR_SAMPLE_PREFETCH 0
+#endif
 
 // Lane states; state >> 1 is the group the majority vote counts: 0 parked, 1 level-1 stepping, 2 in-brick sampling, 3 slow
 // events.  The events of a ray (brick entry / exit, leaving or entering a level-1 node, steps at the root level) are not
@@ -193,6 +199,19 @@ struct RayMarcher : MarchTrav {
     unsigned pending, todo, outIdx;
     bool initialized;
     float3 pb; float t; int biter;   // in-brick sampling
+#if VR_SAMPLE_PREFETCH
+    uint32_t pw0, pw1; float pfx, pfy, pfz;   // texel words and filter fractions of the sample at pb (FAST sampler)
+    VRD void prefetchSample(const DSlot& g) {
+        if (!FAST) return;
+        if (!(pb.x >= 0 && pb.y >= 0 && pb.z >= 0 && pb.x < 8.f && pb.y < 8.f && pb.z < 8.f)) return;   // the step that would sample it leaves the brick instead
+        int ix, iy, iz;
+        const float qx = pb.x - 0.5f, qy = pb.y - 0.5f, qz = pb.z - 0.5f;
+        const float fx0 = fastFloor(qx, ix), fy0 = fastFloor(qy, iy), fz0 = fastFloor(qz, iz);
+        pfx = qx - fx0; pfy = qy - fy0; pfz = qz - fz0;
+        const uint32_t* q = g.quads + (brick * 810u + (unsigned)(((iz + 1) * 9 + (iy + 1)) * 9 + (ix + 1)));
+        pw0 = __ldg(q); pw1 = __ldg(q + 81);
+    }
+#endif
 
     VRD void writeOut(float* results) {
 #pragma unroll
@@ -256,15 +275,23 @@ struct RayMarcher : MarchTrav {
         pb = wp - nodePos(leaf);
         biter = 0;
         phase = MARCH_BRICK;
+#if VR_SAMPLE_PREFETCH
+        prefetchSample(g);
+#endif
     }
 
     VRD float sampleFast(const DSlot& g) {   // sampleBrickLinear<false> on the quad repack, same filter arithmetic
+#if VR_SAMPLE_PREFETCH
+        const float fx = pfx, fy = pfy, fz = pfz;
+        const uint32_t w0 = pw0, w1 = pw1;
+#else
         int ix, iy, iz;
         const float qx = pb.x - 0.5f, qy = pb.y - 0.5f, qz = pb.z - 0.5f;
         const float fx0 = fastFloor(qx, ix), fy0 = fastFloor(qy, iy), fz0 = fastFloor(qz, iz);
         const float fx = qx - fx0, fy = qy - fy0, fz = qz - fz0;
         const uint32_t* q = g.quads + (brick * 810u + (unsigned)(((iz + 1) * 9 + (iy + 1)) * 9 + (ix + 1)));
         const uint32_t w0 = __ldg(q), w1 = __ldg(q + 81);
+#endif
         // x-lerps: the codes arrive as 2^23 + b; (2^23 + b1) - (2^23 + b0) == b1 - b0 exactly, so only the base corner of each
         // pair is converted (lerpf(a, b, t) = fma(t, b - a, a))
         const float m000 = byteToMagic(w0, 0), m100 = byteToMagic(w0, 1), m010 = byteToMagic(w0, 2), m110 = byteToMagic(w0, 3);
@@ -296,6 +323,9 @@ struct RayMarcher : MarchTrav {
         pb = pb + wpt;
         t += 1.f * tStep;
         biter++;
+#if VR_SAMPLE_PREFETCH
+        if (biter < MAX_BRICK_STEPS) prefetchSample(g);
+#endif
     }
 };
 
