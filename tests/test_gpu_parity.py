@@ -162,7 +162,7 @@ def test_three_level_tree_full_reuse():
 def _frames_buffers(params, scene, w, h, wavefront, frames=3, extra=None):
     """Run `frames` frames through the public execute() and return (image, final reservoirs) of the last one."""
     import torch
-    d = {"mParams": params, "mUseWavefront": int(wavefront is not False), "mMarchPairEngine": int(wavefront == "pair")}
+    d = {"mParams": params, "mUseWavefront": int(wavefront is not False)}
     d.update(extra or {})
     if wavefront == 0:
         d["mInitialMode"] = 0
@@ -194,8 +194,7 @@ def test_wavefront_equals_per_pixel(variant):
     sc = sc or env_scene()
     p = VolumetricReSTIRParams(**kw)
     img_s, res_s = _frames_buffers(p, sc, w, h, False)
-    modes = (True, 0) + (("pair",) if variant == "three_level" else ())
-    for mode in modes:   # True: default wavefront pipeline (lock-step K1); 0: wavefront K2/K3/K5 with the per-pixel K1; "pair": phase-specialised march engine
+    for mode in (True, 0):   # True: default wavefront pipeline (lock-step K1); 0: wavefront K2/K3/K5 with the per-pixel K1
         img_w, res_w = _frames_buffers(p, sc, w, h, mode)
         assert np.array_equal(res_w.view(np.uint32), res_s.view(np.uint32)), f"wavefront reservoirs (mode {mode}) differ from the per-pixel kernels"
         assert np.array_equal(img_w.view(np.uint32), img_s.view(np.uint32))

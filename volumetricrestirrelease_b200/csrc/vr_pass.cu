@@ -1418,7 +1418,6 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) try {
         else if (k == "mDebugPoisonResults") p->mDebugPoison = value != 0;
         else if (k == "mScratchBudgetMB") p->mScratchBudget = (size_t)std::max(1.0, value) << 20;
         else if (k == "mPrefetchPriority") p->mPrefetchPriority = value != 0;
-        else if (k == "mMarchPairEngine") setPairEngine(value != 0);   // process-wide A/B switch of the march engine   // 0 forces the per-pixel kernels (A/B tests)
         else if (k == "randomizeFrameSeed") { if (!p->mRandomizeFrameSeed) p->randState = 123; p->mRandomizeFrameSeed = true; }
         else found = false;
     }
@@ -1713,14 +1712,6 @@ int vrestir_debug_wavefront_counters(vrestir_pass* p, uint32_t out[16]) try {
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, p->wfCounters, 64, cudaMemcpyDeviceToHost));
-    {   // watchdog records of the paired march engine (none in a healthy run): count in out[15], first record in out[10..14]
-        static unsigned rec[64 * 16]; unsigned cnt = 0;
-        if (readPairWatchdog(rec, &cnt) == cudaSuccess) {
-            out[15] = cnt;
-            if (cnt) { fprintf(stderr, "[vrestir] paired march engine watchdog tripped %u times\n", cnt);
-                for (unsigned k = 0; k < cnt && k < 8; k++) { fprintf(stderr, "  rec%u:", k); for (int j = 0; j < 11; j++) fprintf(stderr, " %u", rec[k * 16 + j]); fprintf(stderr, "\n"); } }
-        }
-    }
     return VRESTIR_OK;
 } catch (...) { return vr::caughtException(); }
 int vrestir_debug_long_rays(vrestir_pass* p, float* out64x8, uint32_t* count) try {

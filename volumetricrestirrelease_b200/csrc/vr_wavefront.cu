@@ -13,7 +13,7 @@
 // seen from ray j for i != j (12 values).  p-hat = Tr(camera ray j -> depth_i) * density * sigma * Tr(point -> light) *
 // Ld; the camera transmittances of one ray share ONE multi-depth march (4 camera tasks per pixel instead of 12
 // marches), the light marches are 12 independent tasks.
-#include "vr_march_pair.cuh"
+#include "vr_march.cuh"
 #include "vr_stages.cuh"
 #include "vr_kernels.h"
 
@@ -56,10 +56,6 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const WfStream s, unsigned*
         const unsigned key = s.tasks[3 * (size_t)i + 2].y & (VR_RAY_BUCKETS - 1);
         perm[atomicAdd(&binCursor[key], 1u)] = i;
     }
-}
-// phase-specialised engine (vr_march_pair.cuh): explicit prepared tasks, single threshold, FAST sampler
-__global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march_pair(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
-    marchPairs(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
 }
 #ifndef VR_ANALYTIC_MINB
 #define VR_ANALYTIC_MINB 8
@@ -1267,14 +1263,6 @@ int marchBlocksPerSM(int nt) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march<3, true>, 128, 0);
     return n > 0 ? n : 1;
 }
-cudaError_t readPairWatchdog(unsigned* out64x16, unsigned* count) {
-    cudaError_t e = cudaMemcpyFromSymbol(count, g_pairDbgCount, 4);
-    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out64x16, g_pairDbg, sizeof(unsigned) * 64 * 16);
-    return e;
-}
-static int g_pairEngine = 0;   // measured slower than the voted engine (11.2 vs 9.7 ms/frame: +32 % instructions for the hand-offs), kept as an option
-void setPairEngine(int on) { g_pairEngine = on; }
-int pairBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march_pair, 128, 0); return n > 0 ? n : 1; }
 // bucket order of the stream's tasks into perm[0, count): hist = the emitting kernel's histogram, binCursor = scratch (VR_RAY_BUCKETS words)
 cudaError_t launchBucketOrder(const WfStream& s, const unsigned* hist, unsigned* binCursor, unsigned* perm, int blocks, cudaStream_t st) {
     k_bin_scan<<<1, 1024, 0, st>>>(hist, binCursor);
@@ -1284,12 +1272,6 @@ cudaError_t launchBucketOrder(const WfStream& s, const unsigned* hist, unsigned*
 cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st, const unsigned* perm) {
     // FAST: trilinear sampler on a single-channel UNORM8 pool with the quad repack (every coarse / conservative mip)
     const bool fast = kind.linear && grid.format == VRESTIR_ATLAS_UNORM8 && grid.quads != nullptr;
-    if (g_pairEngine && nt == 1 && fast && kind.originMode == 0) {
-        static int pairBlocks = 0;
-        if (!pairBlocks) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); pairBlocks = sms * pairBlocksPerSM(); }
-        k_march_pair<<<pairBlocks, 128, 0, st>>>(s, results, kind, grid);
-        return cudaGetLastError();
-    }
     if (nt == 1) { if (fast) k_march<1, true><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); else k_march<1, false><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); }
     else { if (fast) k_march<3, true><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); else k_march<3, false><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); }
     return cudaGetLastError();
