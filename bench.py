@@ -81,7 +81,10 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ scenes
-def build_scene(args, device=0, frame_time=0.0):
+PLUME_T0 = 15.0     # config 3: the plume has risen through the whole grid (3.7 k of 23.7 k bricks)
+
+
+def build_scene(args, device=0, frame_time=None):
     """The synthetic scene of the selected configuration.  Config 5 is generated and mip-mapped on the device."""
     from volumetricrestirrelease_b200 import Scene
     cfg = CONFIGS[getattr(args, "config", 2)]
@@ -96,7 +99,7 @@ def build_scene(args, device=0, frame_time=0.0):
     if n == 3:
         sc.addGVDBVolume(sigma_a=(6, 6, 6), sigma_s=(14, 14, 14), g=0.0, dataFile=args.kind, numMips=args.mips, densityScale=cfg["density_scale"],
                          hasVelocity=True, hasEmission=True, LeScale=0.01, temperatureCutoff=1.0, temperatureScale=100.0,
-                         dim=tuple(args.dim), seed=3, voxelSize=cfg["voxel"], frameTime=frame_time)
+                         dim=tuple(args.dim), seed=3, voxelSize=cfg["voxel"], frameTime=PLUME_T0 if frame_time is None else frame_time)
         sc.setEnvMap((2048, 1024), seed=7)
         sc.setEnvMapIntensity(0.5)
         sc.frame_camera(0.9, direction=(0.35, 0.15, 1.0))
@@ -474,9 +477,10 @@ def main():
     scene = build_scene(args, device=local)
     params = make_params(args)
     volumes = []
-    if args.config == 3:      # animated sequence: 6 prebuilt frames of the plume, cycled; every step advances the volume
-        volumes = [build_scene(args, frame_time=0.35 * f).volume for f in range(1, 7)]
-    pipelined = not args.no_pipeline
+    if args.config == 3:      # animated sequence: 6 prebuilt frames of the fully risen plume, cycled; every step advances the volume
+        volumes = [build_scene(args, frame_time=PLUME_T0 + 0.35 * f).volume for f in range(1, 7)]
+    # a new volume every frame invalidates K0/K1 computed ahead (they would be discarded): animated sequences run un-pipelined
+    pipelined = not args.no_pipeline and not volumes
     level = args.pipeline_level if pipelined else 0
     R = Runner(args, W, H, scene, params, level, rank, world, local, volumes)
     gp = R.gp
@@ -643,6 +647,8 @@ def main():
                 ach = alg / (t3 * 1e-3) / 1e9
                 # which roof: the reuse mips of configs 1-4 are L2 resident by design (DRAM traffic << algorithmic bytes, ncu);
                 # a grid larger than L2 (config 5) streams from HBM
+                # (measured DRAM bytes of these launches, profiles/traffic_k_march.json, against the algorithmic bytes: even the
+                # 2048^3 grid of config 5, whose pools are 25x L2, is served mostly by L2 — neighbouring rays share bricks)
                 l2_bound = traffic is None and args.config != 5 or (traffic is not None and traffic < 0.5 * alg)
                 peak = l2_peak if l2_bound else hbm_peak
                 roof = {"kernel": "k_march (march engine; camera + light launches of one spatial-reuse round)", "bound": "l2" if l2_bound else "hbm",

@@ -30,7 +30,7 @@ def main():
     import torch
     scene = bench.build_scene(args)
     params = bench.make_params(args)
-    volumes = [bench.build_scene(args, frame_time=0.35 * f).volume for f in range(1, 4)] if args.config == 3 else []
+    volumes = [bench.build_scene(args, frame_time=bench.PLUME_T0 + 0.35 * f).volume for f in range(1, 4)] if args.config == 3 else []
     R = bench.Runner(args, args.width, args.height, scene, params, a.pipeline, 0, 1, 0, volumes)
     if args.config == 5:
         scene.volume.release_chain()
