@@ -926,11 +926,28 @@ VRD float impLoad(uint32_t x, uint32_t y, int mip) {
 // Top of the importance mip chain (mips with dim <= 32: 32^2 + 16^2 + ... + 1 = 1365 floats) staged in shared memory by
 // kernels whose critical path is the 36-load dependent chain of the hierarchical warp (K1 step kernels).
 constexpr int IMP_TOP_DIM = 32, IMP_TOP_FLOATS = 1365;
-VRD void stageImportanceTop(float* smem) {   // every thread of the CTA calls; caller syncs
+constexpr int IMP_TOP_BYTES = (IMP_TOP_FLOATS * 4 + 15) / 16 * 16;   // bulk copies move multiples of 16 B (the map is allocated with the slack)
+// The 5.5 KB block is one contiguous piece of the importance chain: a single thread hands it to the bulk-copy engine
+// (cp.async.bulk, global -> shared, completion on an mbarrier) and the CTA waits on the barrier — no per-thread load / store
+// loop, no __syncthreads.  smem must be 16-byte aligned; every thread of the CTA calls and returns with the data visible.
+VRD void stageImportanceTop(float* smem, uint64_t* bar) {
     if (c_scene.impDim < IMP_TOP_DIM) return;
     int first = 0; while ((c_scene.impDim >> first) > IMP_TOP_DIM) first++;
-    const unsigned base = c_scene.impOffset[first];
-    for (int i = threadIdx.x; i < IMP_TOP_FLOATS; i += blockDim.x) smem[i] = __ldg(&c_scene.importance[base + i]);
+    const float* src = c_scene.importance + c_scene.impOffset[first];
+    const unsigned barAddr = (unsigned)__cvta_generic_to_shared(bar), dstAddr = (unsigned)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // the barrier is initialised before anybody polls it
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"((unsigned)IMP_TOP_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dstAddr), "l"(src), "r"((unsigned)IMP_TOP_BYTES), "r"(barAddr) : "memory");
+    }
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(barAddr) : "memory");
 }
 VRD float impLoadT(uint32_t x, uint32_t y, int mip, const float* impTop) {
     const int dim = c_scene.impDim >> mip;

@@ -1293,7 +1293,7 @@ int vrestir_set_envmap(vrestir_pass* p, const vrestir_envmap_desc* env) try {
     size_t total = 0; for (int i = 0; i < mips; i++) { s.impOffset[i] = (unsigned)total; total += (size_t)(dim >> i) * (dim >> i); }
     s.impDim = dim; s.impBaseMip = mips - 1;
     if (p->d_importance) cudaFree(p->d_importance);
-    CK(cudaMalloc(&p->d_importance, total * 4));
+    CK(cudaMalloc(&p->d_importance, total * 4 + 16));   // + slack: the top of the chain is staged with 16-byte bulk copies
     p->importanceCount = total;
     s.importance = p->d_importance;
     CK(uploadScene(s, 0)); CK(cudaDeviceSynchronize());

@@ -456,9 +456,10 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 8 : (MODE == 0 ? VR_STEP0_MIN
     Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
     Reservoir evalTap = createNewReservoir();
     float3 evalDir = f3(0.f, 0.f, 1.f);
-    __shared__ float impTop[IMP_TOP_FLOATS];
+    __shared__ __align__(16) float impTop[IMP_TOP_BYTES / 4];
+    __shared__ uint64_t impBar;
     const bool stageImp = MODE != 2 && o.useEnvironmentLights && c_scene.haveEnv && c_scene.envSamplerType != VRESTIR_ENV_SAMPLER_ALIAS && c_scene.impDim >= IMP_TOP_DIM;
-    if (stageImp) { stageImportanceTop(impTop); __syncthreads(); }
+    if (stageImp) stageImportanceTop(impTop, &impBar);
     uint8_t* doneFlag = wi.done + (size_t)(pixelId - fp.rowBegin * fp.W);
     // pixels whose four distance candidates all left the volume were finished by step 0 (no light sample, no march)
     if (inFrame && (MODE == 0 || !*doneFlag)) {
