@@ -15,6 +15,7 @@ What the line reports:
                      orbit that is announced one frame ahead (vrestir_set_next_camera) — every frame's stages run exactly once
   value_serial       the same frames without pipelining (one dependent chain per frame); config.stage_ms are its stage times
   value_static       pipelined, static camera (the round-1 headline, for continuity)
+  value_streamed     config 3 only: every step uploads its volume from host memory (value binds frames resident on the device)
   e2e                the same metric through the C ABI's host-buffer call (vrestir_execute_host_async: camera + scene constants
                      up, the rendered frame down into pinned host memory, every step, inside the timed region)
   parity             relMSE and flip fraction of a frame WITH history against the CPU oracle on crops of the same frame
@@ -269,7 +270,7 @@ def cpu_sample(args, scene, params, importance, env_alias, tiles, steps=1, warm_
 RES = np.dtype([("runningSum", "<f4"), ("M", "<f4"), ("depth", "<f4"), ("p_y", "<f4"), ("lightUV", "<f4", 2), ("lightID", "<i4"), ("sampledPixel", "<i4")])
 
 
-def parity_with_history(gp, scene, params, W, H, color, oracle_scene=None):
+def parity_with_history(gp, scene, params, W, H, color, oracle_scene=None, frame_ids=None, volumes=None):
     """relMSE / flip fraction of a frame WITH history against the oracle (BASELINE metric's second half).  The GPU renders
     frames 0 and 1 of a fresh epoch; its history is handed to the oracle; frame 2 is compared on two 64x64 crops (the oracle
     runs K0-K2 on crop + 10 px halo, K3-K5 on the crop).  relMSE = mean((a-b)^2 / (b^2 + 1e-2 mean(b)^2))."""
@@ -278,13 +279,21 @@ def parity_with_history(gp, scene, params, W, H, color, oracle_scene=None):
     from volumetricrestirrelease_b200 import capi
     B = params.mMaxBounces
     gp.updateDict({"mPipelineFrames": 0})
-    for _ in range(2):
+    for f in range(2):
+        if frame_ids:          # animated sequence: every frame binds the next resident volume
+            gp.advanceVolumeResident(frame_ids[f])
         gp.execute(color.data_ptr())
     torch.cuda.synchronize()
     op = vro.OraclePass(params)
+    if frame_ids:              # the oracle renders frame 2 with volume 1 as the previous frame's grids and volume 2 as the current
+        oracle_scene = copy.copy(scene)
+        oracle_scene.volume = volumes[1]
     em = gp.emissive_alias(len(scene.emissiveTriangles)) if scene.emissiveTriangles is not None else None
     imp = gp.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32) if scene.envMap is not None else None
     op.setScene(oracle_scene or scene, W, H, importance=imp, env_alias=gp.env_alias() if scene.envMap is not None else None, emissive_alias=em)
+    if frame_ids:
+        op.advanceVolume(volumes[2])
+        gp.advanceVolumeResident(frame_ids[2])
     c0 = np.zeros((H, W, 4), np.float32)
     reuse = bool(params.mEnableTemporalReuse)
     op.execute_stage(6, 0, c0)
@@ -395,6 +404,9 @@ class Runner:
         self.band = self.sp.balance(refine=0)
         self.gp.setRowBand(*self.band)
         self.volumes = volumes or []
+        # animated sequences: every frame is uploaded once and stays resident, as in the reference (F/Scene/Scene.cpp:825-863)
+        self.frame_ids = [self.gp.addVolumeFrame(v) for v in self.volumes]
+        self.streamed = False          # True: every step uploads its volume from host memory instead (vrestir_advance_volume)
         self.frame = 0
         self.path = orbit_positions(scene, 4096) if args.camera == "orbit" else None
         self.cam_index = 0
@@ -404,8 +416,7 @@ class Runner:
 
     def step(self, out_ptr=None, moving=True):
         gp, sc = self.gp, self.scene
-        if self.volumes:
-            gp.advanceVolume(self.volumes[self.frame % len(self.volumes)])
+        self.advance()
         if self.path is not None and moving:
             sc.camera.position = self.path[self.cam_index % len(self.path)]
             gp.updateCamera()
@@ -415,6 +426,15 @@ class Runner:
             self.cam_index += 1
         self.sp.execute(out_ptr or self.color.data_ptr())
         self.frame += 1
+
+    def advance(self):
+        if not self.volumes:
+            return
+        k = self.frame % len(self.volumes)
+        if self.streamed:
+            self.gp.advanceVolume(self.volumes[k])
+        else:
+            self.gp.advanceVolumeResident(self.frame_ids[k])
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -499,6 +519,11 @@ def main():
     stage_acc = R.stage_times(min(args.steps, 10))
     pstats = gp.pipeline_stats()
     static_ms = None
+    streamed_ms = None
+    if volumes and not args.no_extras:      # the same frames with the volume uploaded from host memory every step
+        R.streamed = True
+        streamed_ms, _ = R.timed(args.steps, args.warmup)
+        R.streamed = False
     if pipelined and not args.no_extras and not volumes and R.path is not None:
         gp.setNextCamera(None)
         static_ms, _ = R.timed(args.steps, args.warmup, moving=False)
@@ -529,8 +554,7 @@ def main():
     r0, r1 = R.band
     if world == 1:
         def e2e_step(i):
-            if volumes:
-                gp.advanceVolume(volumes[R.frame % len(volumes)])
+            R.advance()
             if R.path is not None:
                 scene.camera.position = R.path[R.cam_index % len(R.path)]
                 nxt = copy.copy(scene.camera)
@@ -617,7 +641,7 @@ def main():
         oracle_scene = copy.copy(scene)
         oracle_scene.volume = gp.downloadVolume()      # the device-built grid, for the CPU checker
     if not args.no_parity and world == 1:
-        parity = parity_with_history(gp, scene, params, W, H, R.color, oracle_scene)
+        parity = parity_with_history(gp, scene, params, W, H, R.color, oracle_scene, R.frame_ids, volumes)
 
     cpu, roof = None, None
     if not args.no_cpu_baseline and world == 1:
@@ -681,10 +705,12 @@ def main():
                            "prefetch_chain_ms": round(pstats["prefetch_ms"], 3), "deferred_final_ms": round(pstats["deferred_final_ms"], 3),
                            "adopted": int(pstats["adopted"]), "discarded": int(pstats["discarded"])} if pipelined else {"on": False})}
     if volumes:
-        cfg["animation"] = f"every step advances the volume (vrestir_advance_volume, {len(volumes)} prebuilt frames cycled: host-to-device upload of the grids inside the timed region)"
+        cfg["animation"] = (f"every step advances the volume: {len(volumes)} frames resident on the device, cycled (vrestir_advance_volume_resident; the reference "
+                            f"keeps a sequence's frames resident too); value_streamed = the same frames with every step's grids uploaded from pageable host memory "
+                            f"inside the timed region (vrestir_advance_volume)")
     line = {"metric": "ms/frame", "value": ms, "unit": "ms/frame", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "value_pipelined": ms, "value_serial": serial_ms, "value_static": static_ms,
+            "value_pipelined": ms, "value_serial": serial_ms, "value_static": static_ms, "value_streamed": streamed_ms,
             "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms/frame", "h2d_bytes_per_step": int(capi.C.sizeof(capi.Camera) + 8192),
                     "d2h_bytes_per_step": int((r1 - r0) * W * 16),

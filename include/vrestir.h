@@ -283,6 +283,15 @@ int vrestir_set_volume(vrestir_pass* pass, const vrestir_grid_desc* grid);
 /* Animated volumes: rebinds the previous call's grids to the prev-frame slots (19..28) and uploads `grid` as current
  * (F/Scene/Scene.cpp:825-863). */
 int vrestir_advance_volume(vrestir_pass* pass, const vrestir_grid_desc* grid);
+/* Resident animation frames.  The reference keeps every frame of an animated sequence on the GPU and switches the bound grids
+ * and the volume description once per frame (F/Scene/Scene.cpp:825-863: mVolumeDescArray[mVDBAnimationFrameId]).
+ * vrestir_volume_frame_add uploads the current-frame slots of `grid` once and returns the frame's index;
+ * vrestir_advance_volume_resident(index) has the semantics of vrestir_advance_volume with that frame as the new volume but only
+ * rebinds pointers (no copy, no allocation, no device-wide wait).  vrestir_volume_frames_clear releases the frames (a volume
+ * must be set again if the pass was still bound to one). */
+int vrestir_volume_frame_add(vrestir_pass* pass, const vrestir_grid_desc* grid, int* out_index);
+int vrestir_advance_volume_resident(vrestir_pass* pass, int index);
+int vrestir_volume_frames_clear(vrestir_pass* pass);
 int vrestir_set_camera(vrestir_pass* pass, const vrestir_camera* camera);
 int vrestir_set_envmap(vrestir_pass* pass, const vrestir_envmap_desc* env);
 int vrestir_set_analytic_lights(vrestir_pass* pass, const vrestir_light* lights, int count);

@@ -331,6 +331,43 @@ def test_plume_animated_sequence_staged(wavefront):
         assert v <= 5e-3, (k, v)   # libm-ulp differences in the black-body / velocity lookups flip a few more selections
 
 
+def test_resident_volume_frames_match_streamed_advance():
+    """Animated sequence with every frame resident on the device (vrestir_volume_frame_add + vrestir_advance_volume_resident,
+    the reference's protocol: F/Scene/Scene.cpp:825-863) renders the same bits as uploading each frame's grids on advance;
+    frames are revisited (cycled), bound twice in a row, and cleared while bound."""
+    import torch
+    w, h = 128, 96
+    params = VolumetricReSTIRParams()
+    vols = [_plume_scene(0.35 * f).volume for f in range(3)]
+    imgs = []
+    for resident in (False, True):
+        sc = _plume_scene(0.0)
+        gp = VolumetricReSTIR.create({"mParams": params, "mOutputMotionVec": 1})
+        gp.setScene(sc, w, h)
+        ids = [gp.addVolumeFrame(v) for v in vols] if resident else None
+        color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        out = []
+        for f, k in enumerate([1, 2, 0, 0, 1]):
+            if resident:
+                gp.advanceVolumeResident(ids[k])
+            else:
+                gp.advanceVolume(vols[k])
+            gp.execute(color.data_ptr()); torch.cuda.synchronize()
+            out.append(color.cpu().numpy().copy())
+        imgs.append(out)
+        if resident:
+            gp.clearVolumeFrames()
+            with pytest.raises(capi.VRestirError):
+                gp.execute(color.data_ptr())          # the bound frame is gone: a volume has to be set again
+            with pytest.raises(capi.VRestirError):
+                gp.advanceVolumeResident(0)
+            gp.setScene(sc, w, h)
+            gp.execute(color.data_ptr()); torch.cuda.synchronize()
+    for a, b in zip(*imgs):
+        assert (a[..., :3].sum(-1) > 0).mean() > 0.02
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_accumulated_full_reuse_relmse():
     """North-star convergence check: frames accumulated with full temporal + spatial reuse on the GPU (default wavefront path,
     whole-frame execute) against the oracle's accumulation over the same frames, relMSE = mean((a-b)^2 / (b^2 + eps)) with

@@ -149,7 +149,7 @@ class SceneParams(C.Structure):
 # every symbol include/vrestir.h declares (checked by tests/test_capi_symbols.py against the header text)
 SYMBOLS = [
     "vrestir_last_error", "vrestir_version", "vrestir_default_params", "vrestir_create", "vrestir_destroy",
-    "vrestir_set_volume", "vrestir_advance_volume", "vrestir_set_camera", "vrestir_set_envmap",
+    "vrestir_set_volume", "vrestir_advance_volume", "vrestir_volume_frame_add", "vrestir_advance_volume_resident", "vrestir_volume_frames_clear", "vrestir_set_camera", "vrestir_set_envmap",
     "vrestir_set_analytic_lights", "vrestir_set_emissive_triangles", "vrestir_get_emissive_alias",
     "vrestir_get_env_alias", "vrestir_build_alias_table", "vrestir_build_env_alias", "vrestir_set_frame", "vrestir_update", "vrestir_set_params", "vrestir_get_params",
     "vrestir_set_frame_count", "vrestir_set_prev_camera", "vrestir_get_frame_count", "vrestir_execute",
@@ -185,6 +185,9 @@ def lib():
     L.vrestir_destroy.argtypes = [vp]
     L.vrestir_set_volume.argtypes = [vp, C.POINTER(GridDesc)]
     L.vrestir_advance_volume.argtypes = [vp, C.POINTER(GridDesc)]
+    L.vrestir_volume_frame_add.argtypes = [vp, C.POINTER(GridDesc), C.POINTER(C.c_int)]
+    L.vrestir_advance_volume_resident.argtypes = [vp, C.c_int]
+    L.vrestir_volume_frames_clear.argtypes = [vp]
     L.vrestir_set_camera.argtypes = [vp, C.POINTER(Camera)]
     L.vrestir_set_prev_camera.argtypes = [vp, C.POINTER(Camera)]
     L.vrestir_set_envmap.argtypes = [vp, C.POINTER(EnvMapDesc)]

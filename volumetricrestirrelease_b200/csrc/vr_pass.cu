@@ -46,6 +46,7 @@ namespace {
 struct DevSlot {
     void* nodes[3] = {nullptr, nullptr, nullptr}; void* child[3] = {nullptr, nullptr, nullptr}; void* atlas = nullptr; size_t atlasBytes = 0; void* quads = nullptr; size_t quadBytes = 0;
     vrestir_grid_slot meta{};   // what the slot was uploaded from, host pointers cleared (vrestir_download_volume)
+    bool borrowed = false;      // the allocations belong to a resident animation frame (vrestir_volume_frame_add)
 };
 
 struct KeyDesc { const char* name; size_t off; int type; };
@@ -80,6 +81,9 @@ struct vrestir_pass {
     vrestir_volume_desc volBase{};
     bool sceneDirty = true, haveVolume = false, haveCamera = false;
     DevSlot dslots[VRESTIR_MAX_SLOTS];
+    // resident animation frames (vrestir_volume_frame_add): the current-frame slots of each, bound by pointer on advance
+    struct ResidentFrame { DevSlot d[VRESTIR_PREV_DENSITY_GRID_OFFSET]; DSlot s[VRESTIR_PREV_DENSITY_GRID_OFFSET]; vrestir_volume_desc vol{}; };
+    std::vector<std::unique_ptr<ResidentFrame>> volumeFrames;
     void* d_lut = nullptr; void* d_lutPrev = nullptr;
     vrestir_camera cam{};
     // env
@@ -366,16 +370,17 @@ int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStrea
 }
 
 void freeSlot(DevSlot& d) {
-    for (int l = 0; l < 3; l++) { if (d.nodes[l]) cudaFree(d.nodes[l]); if (d.child[l]) cudaFree(d.child[l]); d.nodes[l] = d.child[l] = nullptr; }
-    if (d.atlas) cudaFree(d.atlas);
-    if (d.quads) cudaFree(d.quads);
-    d.atlas = nullptr; d.atlasBytes = 0; d.quads = nullptr; d.quadBytes = 0; d.meta = vrestir_grid_slot{};
+    if (!d.borrowed) {
+        for (int l = 0; l < 3; l++) { if (d.nodes[l]) cudaFree(d.nodes[l]); if (d.child[l]) cudaFree(d.child[l]); }
+        if (d.atlas) cudaFree(d.atlas);
+        if (d.quads) cudaFree(d.quads);
+    }
+    d = DevSlot{};
 }
+bool ownsMemory(const DevSlot& d) { return !d.borrowed && (d.atlas || d.quads || d.nodes[0] || d.nodes[1] || d.nodes[2]); }
 
-int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
-    DevSlot& d = p->dslots[slot];
+int uploadSlotTo(DevSlot& d, DSlot& s, const vrestir_grid_slot& g) {
     freeSlot(d);
-    DSlot& s = p->scene.slots[slot];
     memset(&s, 0, sizeof(s));
     if (!g.valid) return VRESTIR_OK;
     if (g.top_lev < 1 || g.top_lev > 2) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "top_lev must be 1 or 2");
@@ -415,23 +420,14 @@ int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) {
     s.quads = nullptr;
     if (bytes && g.atlas && g.atlas_format == VRESTIR_ATLAS_UNORM8 && g.atlas_channels == 1) {
         // device-only repack for trilinear fetches: per brick [10][9][9] words, word(z,y,x) = codes (x,y) (x+1,y) (x,y+1) (x+1,y+1) of plane z
-        std::vector<uint32_t> q((size_t)g.brick_count * 810);
-        const uint8_t* a = (const uint8_t*)g.atlas;
-        for (uint32_t b = 0; b < g.brick_count; b++) {
-            const uint8_t* blk = a + (size_t)b * VRESTIR_BRICK_VOXELS;
-            uint32_t* o = q.data() + (size_t)b * 810;
-            for (int z = 0; z < 10; z++) for (int y = 0; y < 9; y++) for (int x = 0; x < 9; x++) {
-                const uint8_t* c = blk + (z * 10 + y) * 10 + x;
-                o[(z * 9 + y) * 9 + x] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[10] << 16) | ((uint32_t)c[11] << 24);
-            }
-        }
-        d.quadBytes = q.size() * 4;
+        d.quadBytes = (size_t)g.brick_count * 810 * 4;
         CK(cudaMalloc(&d.quads, d.quadBytes));
-        CK(cudaMemcpy(d.quads, q.data(), d.quadBytes, cudaMemcpyHostToDevice));
+        CK(vr::launchQuadRepack((const uint8_t*)d.atlas, g.brick_count, (uint32_t*)d.quads, 0));
         s.quads = (const uint32_t*)d.quads;
     }
     return VRESTIR_OK;
 }
+int uploadSlot(vrestir_pass* p, int slot, const vrestir_grid_slot& g) { return uploadSlotTo(p->dslots[slot], p->scene.slots[slot], g); }
 
 void applyOverrides(vrestir_pass* p) {   // VR/VolumetricReSTIR.cpp:211-235
     vrestir_volume_desc v = p->volBase;
@@ -1107,6 +1103,7 @@ int vrestir_destroy(vrestir_pass* p) try {
     unregisterPass(p);
     if (p->evMainTail) cudaEventDestroy(p->evMainTail);
     for (auto& d : p->dslots) freeSlot(d);
+    for (auto& fr : p->volumeFrames) for (auto& d : fr->d) freeSlot(d);
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
     for (int i = 0; i < 4; i++) if (p->ext[i]) cudaFree(p->ext[i]);
     for (int i = 0; i < 3; i++) if (p->feat[i]) cudaFree(p->feat[i]);
@@ -1144,24 +1141,92 @@ int vrestir_set_volume(vrestir_pass* p, const vrestir_grid_desc* g) try {
     return VRESTIR_OK;
 } catch (...) { return vr::caughtException(); }
 
+// The current density / temperature / velocity grids become the previous frame's (F/Scene/Scene.cpp:825-863).  Memory owned by
+// the displaced previous-frame slots is released, so everything in flight has to be done first; borrowed (resident) slots just
+// change hands.
+static int shiftSlotsToPrev(vrestir_pass* p) {
+    auto prevOf = [](int s) { return s < VRESTIR_NUM_MAX_MIPS ? VRESTIR_PREV_DENSITY_GRID_OFFSET + s : s + VRESTIR_PREV_EXTRA_GRID_OFFSET; };
+    const int from[] = {VRESTIR_TEMPERATURE_GRID_ID, VRESTIR_VELOCITY_GRID_ID};
+    bool frees = false;
+    for (int i = 0; i < VRESTIR_NUM_MAX_MIPS; i++) if (prevOf(i) < VRESTIR_MAX_SLOTS) frees |= ownsMemory(p->dslots[prevOf(i)]);
+    for (int f : from) frees |= ownsMemory(p->dslots[prevOf(f)]);
+    if (frees) CK(cudaDeviceSynchronize());
+    auto moveSlot = [&](int a, int b) {
+        freeSlot(p->dslots[b]);
+        p->dslots[b] = p->dslots[a]; p->dslots[a] = DevSlot{};
+        p->scene.slots[b] = p->scene.slots[a]; memset(&p->scene.slots[a], 0, sizeof(DSlot));
+    };
+    for (int i = 0; i < VRESTIR_NUM_MAX_MIPS; i++) if (prevOf(i) < VRESTIR_MAX_SLOTS) moveSlot(i, prevOf(i));
+    for (int f : from) moveSlot(f, prevOf(f));
+    return VRESTIR_OK;
+}
+
 int vrestir_advance_volume(vrestir_pass* p, const vrestir_grid_desc* g) try {
     if (!p || !g || !p->haveVolume) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "advance_volume before set_volume");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
-    auto moveSlot = [&](int from, int to) {
-        freeSlot(p->dslots[to]);
-        p->dslots[to] = p->dslots[from]; p->dslots[from] = DevSlot{};
-        p->scene.slots[to] = p->scene.slots[from]; memset(&p->scene.slots[from], 0, sizeof(DSlot));
-    };
-    for (int i = 0; i < VRESTIR_NUM_MAX_MIPS; i++) if (VRESTIR_PREV_DENSITY_GRID_OFFSET + i < VRESTIR_MAX_SLOTS) moveSlot(i, VRESTIR_PREV_DENSITY_GRID_OFFSET + i);
-    moveSlot(VRESTIR_TEMPERATURE_GRID_ID, VRESTIR_TEMPERATURE_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
-    moveSlot(VRESTIR_VELOCITY_GRID_ID, VRESTIR_VELOCITY_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
+    { int rc = shiftSlotsToPrev(p); if (rc) return rc; }
     const int lastHasEmission = p->volBase.hasEmission;
     for (int s = 0; s < VRESTIR_PREV_DENSITY_GRID_OFFSET - 1; s++) { int rc = uploadSlot(p, s, g->slots[s]); if (rc) return rc; }
     p->volBase = g->volume; p->volBase.lastFrameHasEmission = lastHasEmission; p->volBase.hasAnimation = 1;
     if (g->blackbody_lut && !p->d_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, g->blackbody_lut, 2048, cudaMemcpyHostToDevice)); p->scene.lut = (const float4*)p->d_lut; }
     p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr;
     applyOverrides(p);
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+
+// Resident animation frames.  The reference keeps every frame of an animated sequence on the GPU and switches the bound grids
+// and the volume description per frame (F/Scene/Scene.cpp:825-863, mVolumeDescArray[mVDBAnimationFrameId]); these two calls
+// are that protocol: add uploads a frame once, advance_resident rebinds pointers (no copy, no allocation, no device-wide wait).
+int vrestir_volume_frame_add(vrestir_pass* p, const vrestir_grid_desc* g, int* out_index) try {
+    if (!p || !g) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!g->slots[0].valid) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "slot 0 (density mip 0) must be valid");
+    CK(cudaSetDevice(p->device));
+    auto fr = std::make_unique<vrestir_pass::ResidentFrame>();
+    for (int s = 0; s < VRESTIR_PREV_DENSITY_GRID_OFFSET - 1; s++) {
+        int rc = uploadSlotTo(fr->d[s], fr->s[s], g->slots[s]);
+        if (rc) { for (auto& d : fr->d) freeSlot(d); return rc; }
+    }
+    CK(cudaDeviceSynchronize());
+    fr->vol = g->volume;
+    if (g->blackbody_lut && !p->d_lut) { CK(cudaMalloc(&p->d_lut, 2048)); CK(cudaMemcpy(p->d_lut, g->blackbody_lut, 2048, cudaMemcpyHostToDevice)); p->scene.lut = (const float4*)p->d_lut; p->sceneDirty = true; }
+    p->volumeFrames.push_back(std::move(fr));
+    if (out_index) *out_index = (int)p->volumeFrames.size() - 1;
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+
+int vrestir_advance_volume_resident(vrestir_pass* p, int index) try {
+    if (!p || !p->haveVolume) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "advance_volume_resident before set_volume");
+    if (index < 0 || index >= (int)p->volumeFrames.size()) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "no resident frame with this index");
+    CK(cudaSetDevice(p->device));
+    { int rc = shiftSlotsToPrev(p); if (rc) return rc; }
+    const vrestir_pass::ResidentFrame& fr = *p->volumeFrames[index];
+    bool frees = false;
+    for (int s = 0; s < VRESTIR_PREV_DENSITY_GRID_OFFSET - 1; s++) frees |= ownsMemory(p->dslots[s]);
+    if (frees) CK(cudaDeviceSynchronize());
+    for (int s = 0; s < VRESTIR_PREV_DENSITY_GRID_OFFSET - 1; s++) {
+        freeSlot(p->dslots[s]);
+        p->dslots[s] = fr.d[s]; p->dslots[s].borrowed = true;
+        p->scene.slots[s] = fr.s[s];
+    }
+    const int lastHasEmission = p->volBase.hasEmission;
+    p->volBase = fr.vol; p->volBase.lastFrameHasEmission = lastHasEmission; p->volBase.hasAnimation = 1;
+    p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr;
+    applyOverrides(p);
+    return VRESTIR_OK;
+} catch (...) { return vr::caughtException(); }
+
+// Releases the resident frames; slots still bound to one of them are unbound first (a volume must be set again before rendering).
+int vrestir_volume_frames_clear(vrestir_pass* p) try {
+    if (!p) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "null argument");
+    if (p->volumeFrames.empty()) return VRESTIR_OK;
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    bool unbound = false;
+    for (int s = 0; s < VRESTIR_MAX_SLOTS; s++) if (p->dslots[s].borrowed) { p->dslots[s] = DevSlot{}; memset(&p->scene.slots[s], 0, sizeof(DSlot)); unbound = true; }
+    for (auto& fr : p->volumeFrames) for (auto& d : fr->d) freeSlot(d);
+    p->volumeFrames.clear();
+    if (unbound) { p->haveVolume = false; p->sceneDirty = true; p->persistBase = p->persistBasePf = nullptr; }
     return VRESTIR_OK;
 } catch (...) { return vr::caughtException(); }
 
@@ -1176,16 +1241,7 @@ int vrestir_set_volume_from_chain(vrestir_pass* p, const vrestir_mip_chain* chai
     if (!tmpl->slots[0].valid) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "template slot 0 (density mip 0) must be valid");
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
-    if (advance) {   // like vrestir_advance_volume: the current density / temperature / velocity grids become the previous frame's
-        auto moveSlot = [&](int from, int to) {
-            freeSlot(p->dslots[to]);
-            p->dslots[to] = p->dslots[from]; p->dslots[from] = DevSlot{};
-            p->scene.slots[to] = p->scene.slots[from]; memset(&p->scene.slots[from], 0, sizeof(DSlot));
-        };
-        for (int i = 0; i < VRESTIR_NUM_MAX_MIPS; i++) if (VRESTIR_PREV_DENSITY_GRID_OFFSET + i < VRESTIR_MAX_SLOTS) moveSlot(i, VRESTIR_PREV_DENSITY_GRID_OFFSET + i);
-        moveSlot(VRESTIR_TEMPERATURE_GRID_ID, VRESTIR_TEMPERATURE_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
-        moveSlot(VRESTIR_VELOCITY_GRID_ID, VRESTIR_VELOCITY_GRID_ID + VRESTIR_PREV_EXTRA_GRID_OFFSET);
-    }
+    if (advance) { int rc = shiftSlotsToPrev(p); if (rc) return rc; }   // like vrestir_advance_volume
     int built = 0;
     if (vrestir_mips_count(chain, &built)) return VRESTIR_ERR_INVALID_ARGUMENT;
     const int lastSlot = advance ? VRESTIR_PREV_DENSITY_GRID_OFFSET - 1 : VRESTIR_MAX_SLOTS;

@@ -185,6 +185,24 @@ class VolumetricReSTIR:
         self._scene.volume = volume
         capi.check(self._lib.vrestir_advance_volume(self._h, volume.grid))
 
+    def addVolumeFrame(self, volume):
+        """Uploads one frame of an animated sequence and keeps it on the device (the reference holds all frames of a sequence
+        resident: F/Scene/Scene.cpp:825-863); returns its index for advanceVolumeResident."""
+        idx = C.c_int(-1)
+        capi.check(self._lib.vrestir_volume_frame_add(self._h, volume.grid, C.byref(idx)))
+        self._frames = getattr(self, "_frames", [])
+        self._frames.append(volume)
+        return idx.value
+
+    def advanceVolumeResident(self, index):
+        """advanceVolume with a resident frame as the new volume: pointers are rebound, nothing is copied."""
+        capi.check(self._lib.vrestir_advance_volume_resident(self._h, int(index)))
+        self._scene.volume = self._frames[index]
+
+    def clearVolumeFrames(self):
+        capi.check(self._lib.vrestir_volume_frames_clear(self._h))
+        self._frames = []
+
     # ------------------------------------------------------------------------------------------------ execution
     def execute(self, out_color_ptr, out_mvec_ptr=None, stream=None):
         """Device-pointer path: `out_color_ptr` is a CUDA address of width*height float4 (e.g. tensor.data_ptr())."""
