@@ -250,7 +250,10 @@ enum {
     VRESTIR_BUF_FEATURES = 6,                    /* mReservoirFeatureBuffer: {int noReflectiveSurface; float transmittance} */
     VRESTIR_BUF_FEATURES_TEMPORAL = 7,
     VRESTIR_BUF_ENV_IMPORTANCE = 8,              /* importance map, all mips, finest first (512^2 + 256^2 + ... + 1) */
-    VRESTIR_BUF_COUNT = 9
+    VRESTIR_BUF_PPARTIAL_0 = 9,                  /* Reservoir::p_partial of buffer 0 / 1 / temporal (VERTEX_REUSE, HostDeviceSharedDefinitions.h:29-31), */
+    VRESTIR_BUF_PPARTIAL_1 = 10,                 /* one float per pixel; present when mVertexReuse && mMaxBounces > 1 */
+    VRESTIR_BUF_PPARTIAL_TEMPORAL = 11,
+    VRESTIR_BUF_COUNT = 12
 };
 
 /* Host-visible reservoir record (VR/HostDeviceSharedDefinitions.h:16-45 + extraBounceStartId). Device storage is SoA. */

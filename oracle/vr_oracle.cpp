@@ -160,6 +160,7 @@ struct Reservoir {  // VR/HostDeviceSharedDefinitions.h:16-45 (+ extraBounceStar
     float2 lightUV;
     int lightID, sampledPixel;
     int extraBounceStartId;
+    float p_partial;   // VERTEX_REUSE (:29-31): the suffix of p-hat past the reuse vertex, kept for the spatial pass
 };
 struct ExtraBounce { float3 wi_dist; };          // VR/HostDeviceSharedDefinitions.h:53-56
 struct Features { int noReflectiveSurface; float transmittance; };  // :67-71
@@ -1266,7 +1267,11 @@ inline float3 v3(const float* a) { return f3(a[0], a[1], a[2]); }
 inline float3 decodeEmissivePosition(int lightID, float2 lightUV) { float z; memcpy(&z, &lightID, 4); return f3(lightUV.x, lightUV.y, z); }
 inline void encodeEmissivePosition(float3 pos, int& lightID, float2& lightUV) { memcpy(&lightID, &pos.z, 4); lightUV = {pos.x, pos.y}; }
 struct float4_ { float x, y, z, w; };
-inline float4_ decodeWiDist(float3 in) {
+inline float4_ decodeWiDist(float3 in, bool reuseAsVertex = false) {
+    if (reuseAsVertex) {   // VERTEX_REUSE: the record holds a world-space vertex (w = -1) or "left the medium"
+        if (in.x == kRayTMax) return {0.f, 0.f, 0.f, kRayTMax};
+        return {in.x, in.y, in.z, -1.f};
+    }
     float3 wi; wi.x = in.x; wi.y = in.y;
     wi.z = sqrtf(1 - (in.x * in.x + in.y * in.y));
     if (std::isnan(wi.z)) wi.z = 0.f;
@@ -1280,13 +1285,14 @@ inline int decodePathTag(int storage) { return (storage >> 16) & 0xF; }
 inline int encodePathTag(int storage, int tag) { return (int)(((uint32_t)tag << 16) | ((uint32_t)storage & 0xFFF0FFFFu)); }
 
 // VR/Reservoir.slang:8-87
-inline Reservoir createNewReservoir() { return {0.f, 0.f, FLT_MAX, 0.f, {0, 0}, 0, 0, 0}; }
+inline Reservoir createNewReservoir() { return {0.f, 0.f, FLT_MAX, 0.f, {0, 0}, 0, 0, 0, 0.f}; }
 inline void takeSample(const Reservoir& r, Reservoir& state, bool sel, int maxBounces) {
     state.depth = sel ? r.depth : state.depth;
     state.p_y = sel ? r.p_y : state.p_y;
     state.lightUV = sel ? r.lightUV : state.lightUV;
     state.lightID = sel ? r.lightID : state.lightID;
     if (maxBounces > 1) state.extraBounceStartId = sel ? r.extraBounceStartId : state.extraBounceStartId;
+    if (maxBounces > 1) state.p_partial = sel ? r.p_partial : state.p_partial;   // VERTEX_REUSE (Reservoir.slang:46-47,76-77); stays 0 without it
     state.sampledPixel = sel ? r.sampledPixel : state.sampledPixel;
 }
 inline bool simpleResampleStep(const Reservoir& reservoir, Reservoir& state, SampleGenerator& sg, int maxBounces) {
@@ -1310,8 +1316,8 @@ inline bool simpleResampleStepWithMaxM(const Reservoir& reservoir, float MThresh
 }
 
 // VR/ReSTIRHelper.slang:435-496
-inline float3 evaluate_L_in_volume(const Ctx& c, const MediumInteraction& mi, int lightID, float2 lightUV, SampleGenerator& sg, const SamplingOptions& options,
-                                   bool isLastFrame, bool cullNonOpaqueGeometry) {
+inline float3 evaluate_L_in_volume(const Ctx& c, const MediumInteraction& mi, int lightID, float2 lightUV, float& precomputedVisibility, SampleGenerator& sg,
+                                   const SamplingOptions& options, bool lightVisibilityReuse, bool isLastFrame, bool cullNonOpaqueGeometry) {
     const Pass& P = c.p;
     Ray shadowRay{}; float3 Ld = f3(0.f); bool isValidSample = true;
     bool useLastFrameGrid = c.vd().usePrevGridForReproj && isLastFrame && c.vd().hasAnimation;
@@ -1333,20 +1339,28 @@ inline float3 evaluate_L_in_volume(const Ctx& c, const MediumInteraction& mi, in
         }
     }
     float Tr = 1.f;
-    if (isValidSample)
-        Tr = computeVisibility(c, shadowRay, sg, options.lightSamples, cullNonOpaqueGeometry ? options.lightingMipLevel + densityGridOffset : 0,
-                               options.lightingUseLinearSampler, options.lightingTrackingMethod, options.lightingTStepScale);
+    if (isValidSample) {
+        if (lightVisibilityReuse) Tr = precomputedVisibility;   // VERTEX_REUSE: the shadow-ray transmittance stored by the sample's own pixel
+        else {
+            Tr = computeVisibility(c, shadowRay, sg, options.lightSamples, cullNonOpaqueGeometry ? options.lightingMipLevel + densityGridOffset : 0,
+                                   options.lightingUseLinearSampler, options.lightingTrackingMethod, options.lightingTStepScale);
+            precomputedVisibility = Tr;
+        }
+    }
     return Tr * Ld;
 }
 
 // extra-bounce data provider (VR/ArrayDataProvider.slang)
 struct ExtraProvider { const ExtraBounce* data; ExtraBounce get(int i) const { return data[i]; } };
 
-// VR/ReSTIRHelper.slang:91-423 (MAX_BOUNCES runtime, no SURFACE_SCENE, no VERTEX_REUSE)
-inline float3 evaluate_F_(const Ctx& c, const Reservoir& tap, const ExtraProvider& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& options,
-                          bool isLastFrame, bool noReuse, bool /*spatialReuse*/, bool isFinalShading) {
+// VR/ReSTIRHelper.slang:91-423 (MAX_BOUNCES and VERTEX_REUSE runtime, no SURFACE_SCENE).  `tap` is REUSETYPE = inout under
+// VERTEX_REUSE: the evaluation leaves the suffix of F past the reuse vertex in tap.p_partial unless spatialReuse reads it.
+inline float3 evaluate_F_(const Ctx& c, Reservoir& tap, const ExtraProvider& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& options,
+                          bool isLastFrame, bool noReuse, bool spatialReuse, bool isFinalShading) {
     const Pass& P = c.p; const auto& vd = c.vd();
     const int maxBounces = P.P.mMaxBounces;
+    const bool vertexReuse = P.P.mVertexReuse && maxBounces > 1;
+    const int S = options.vertexReuseStartBounce;
     bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
     int mipLevelOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
     bool isBackgroundSample = tap.depth == kRayTMax;
@@ -1370,6 +1384,7 @@ inline float3 evaluate_F_(const Ctx& c, const Reservoir& tap, const ExtraProvide
         if (noReuse && !isBackgroundSample) sigma_s = sigma_s / vd.sigma_t;
         F *= visibility * density * sigma_s;
     }
+    float3 P_prefix = f3(1.f);
     int bounceId = 0;
     if (any_gt0(F)) {
         if (isBackgroundSample) {
@@ -1384,8 +1399,8 @@ inline float3 evaluate_F_(const Ctx& c, const Reservoir& tap, const ExtraProvide
                 int numIndirectBounces = maxIndirectBounces;
                 for (; bounceId < numIndirectBounces; bounceId++) {
                     bool isCurrentVertexEmissive = isScatterSelfEmission && bounceId == numIndirectBounces - 1;
-                    float4_ wiDist = decodeWiDist(extra.get(tap.extraBounceStartId + bounceId).wi_dist);
-                    if (isCurrentVertexEmissive) {
+                    float4_ wiDist = decodeWiDist(extra.get(tap.extraBounceStartId + bounceId).wi_dist, vertexReuse && bounceId + 1 >= S);
+                    if (isCurrentVertexEmissive && !(vertexReuse && bounceId + 1 >= S)) {
                         float3 e = decodeEmissivePosition(tap.lightID, tap.lightUV);
                         wiDist = {e.x, e.y, e.z, -1.f};
                     }
@@ -1402,6 +1417,10 @@ inline float3 evaluate_F_(const Ctx& c, const Reservoir& tap, const ExtraProvide
                     float bsdf = mi.phaseFunction(mi.wo, scatterRay.dir);
                     F *= bsdf;
                     if (all_eq0(F)) return f3(0.f);
+                    if (vertexReuse && bounceId == S) {   // :289-296 (the bounce past the reuse vertex)
+                        if (spatialReuse) return F * tap.p_partial;
+                        P_prefix = F;
+                    }
                     if (wiDist.w == -1.f) p_World = f3(wiDist.x, wiDist.y, wiDist.z);
                     else p_World = scatterRay.at(scatterRay.tMax);
                     float3 sigma_s; float scatterDensity;
@@ -1413,7 +1432,7 @@ inline float3 evaluate_F_(const Ctx& c, const Reservoir& tap, const ExtraProvide
                         scatterDensity = 1.f;
                     }
                     F *= scatterDensity * sigma_s;
-                    if (isCurrentVertexEmissive) F *= 1.f / (dist * dist);
+                    if (vertexReuse ? (bounceId + 1 == S || (isCurrentVertexEmissive && bounceId + 1 < S)) : isCurrentVertexEmissive) F *= 1.f / (dist * dist);
                     if (all_eq0(F)) return f3(0.f);
                     float scatterVisibility = 1.f;
                     if (!noReuse)
@@ -1427,22 +1446,34 @@ inline float3 evaluate_F_(const Ctx& c, const Reservoir& tap, const ExtraProvide
                 if (isScatterSelfEmission) F *= EmissionWorldSpace(c, p_World, useLastFrameGrid);
                 else mi = {scatterRay.at(scatterRay.tMax), -scatterRay.dir, vd.PhaseFunctionConstantG, true};
             }
-            if (!isScatterSelfEmission && any_gt0(F))
-                F *= evaluate_L_in_volume(c, mi, tap.lightID, tap.lightUV, sg, options, isLastFrame, !isFinalShading);
+            if (!isScatterSelfEmission && any_gt0(F)) {
+                float precomputedVisibility = vertexReuse ? tap.p_partial : 1.f;
+                const bool lightVisibilityReuse = vertexReuse && bounceId == S && spatialReuse;
+                F *= evaluate_L_in_volume(c, mi, tap.lightID, tap.lightUV, precomputedVisibility, sg, options, lightVisibilityReuse, isLastFrame, !isFinalShading);
+                if (vertexReuse && bounceId == S && !spatialReuse) tap.p_partial = precomputedVisibility;
+            }
         }
     }
+    // :415-420 — componentwise F / P_prefix as written there (a zero prefix component gives NaN like the shader)
+    if (vertexReuse && bounceId > S && !spatialReuse) tap.p_partial = luminance(F / P_prefix);
     return F;
 }
 // VR/ReSTIRHelper.slang:426-441
-inline float evaluate_P_hat(const Ctx& c, const Ray& ray, SampleGenerator& sg, const ExtraProvider& extra, const SamplingOptions& options, const Reservoir& tap,
+inline float evaluate_P_hat(const Ctx& c, const Ray& ray, SampleGenerator& sg, const ExtraProvider& extra, const SamplingOptions& options, Reservoir& tap,
                             bool isLastFrame = false, bool nonBinary = true, bool spatialReuse = false) {
     float3 F = evaluate_F_(c, tap, extra, ray, sg, options, isLastFrame, false, spatialReuse, false);
     return (!nonBinary && any_gt0(F)) ? 1.f : luminance(F);
 }
-inline float3 evaluate_F(const Ctx& c, const Reservoir& tap, const ExtraProvider& extra, const Ray& ray, SampleGenerator& sg, const SamplingOptions& options, bool noReuse) {
+// VR/ReSTIRHelper.slang:600-607 (evaluatePHatReadOnly: the reservoir is passed by value, p_partial of the caller's copy stays)
+inline float evaluatePHatReadOnly(const Ctx& c, const Ray& ray, SampleGenerator& sg, const ExtraProvider& extra, const SamplingOptions& options, Reservoir tap,
+                                  bool isLastFrame, bool nonBinary, bool spatialReuse) {
+    return evaluate_P_hat(c, ray, sg, extra, options, tap, isLastFrame, nonBinary, spatialReuse);
+}
+inline float3 evaluate_F(const Ctx& c, Reservoir tap, const ExtraProvider& extra, const Ray& ray, SampleGenerator& sg, const SamplingOptions& options, bool noReuse) {
     return evaluate_F_(c, tap, extra, ray, sg, options, false, noReuse, false, true);
 }
-// VR/ReSTIRHelper.slang:560-597 (resampleNeighbor / resampleNeighborSpatialReuse differ only in the spatialReuse flag, unused without VERTEX_REUSE)
+// VR/ReSTIRHelper.slang:560-597 (resampleNeighbor / resampleNeighborSpatialReuse differ only in the spatialReuse flag; under VERTEX_REUSE
+// the temporal variant overwrites tap.p_partial, the spatial one reads it)
 inline bool resampleNeighbor(const Ctx& c, Reservoir& tap, const Ray& ray, SampleGenerator& sg, const ExtraProvider& extra, const SamplingOptions& options, bool spatial) {
     if (tap.runningSum == 0.f) return true;
     float p_y_hat = evaluate_P_hat(c, ray, sg, extra, options, tap, false, true, spatial);
@@ -1460,6 +1491,7 @@ inline Reservoir ComputeInitialSample(const Ctx& c, const Ray& primaryRay, float
                                       ExtraBounce* extrabounceReservoir) {
     const Pass& P = c.p; const auto& vd = c.vd();
     const float3 sigA = v3(vd.sigma_a), sigS = v3(vd.sigma_s);
+    const bool vertexReuse = P.P.mVertexReuse && maxBounces > 1;
     float pathPdf = 1.f, pathPHat = 1.f;
     Ray ray = primaryRay;
     Reservoir combinedReservoir = createNewReservoir();
@@ -1491,6 +1523,10 @@ inline Reservoir ComputeInitialSample(const Ctx& c, const Ray& primaryRay, float
             mi = {ray.at(curHitDist), -ray.dir, vd.PhaseFunctionConstantG, curHitDist != kRayTMax};
         }
         pathPdf *= pdfDist;
+        if (vertexReuse && bounce == options.vertexReuseStartBounce && curHitDist != kRayTMax) {   // :88-94 area measure at the reuse vertex
+            pathPdf /= curHitDist * curHitDist;
+            pathPHat /= curHitDist * curHitDist;
+        }
         bool hitEmpty = false;
         float actualVolumeDensity = 0.f;
         if (bounce == 0) {
@@ -1502,7 +1538,10 @@ inline Reservoir ComputeInitialSample(const Ctx& c, const Ray& primaryRay, float
             outReservoir.depth = primaryScatterDepth;
             if (maxBounces > 1) {
                 outReservoir.sampledPixel = encodeMaxIndirectBounces(outReservoir.sampledPixel, bounce);
-                extrabounceReservoir[bounce - 1].wi_dist = encodeWiDist({ray.dir.x, ray.dir.y, ray.dir.z, !mi.isValid ? kRayTMax : curHitDist});
+                if (!vertexReuse || bounce < options.vertexReuseStartBounce)
+                    extrabounceReservoir[bounce - 1].wi_dist = encodeWiDist({ray.dir.x, ray.dir.y, ray.dir.z, !mi.isValid ? kRayTMax : curHitDist});
+                else   // :116-125 world-space vertex
+                    extrabounceReservoir[bounce - 1].wi_dist = !mi.isValid ? f3(kRayTMax) : mi.p;
             }
             outReservoir.p_y = pathPdf;
         }
@@ -1550,8 +1589,10 @@ inline Reservoir ComputeInitialSample(const Ctx& c, const Ray& primaryRay, float
                     if (outReservoir.runningSum > 0.f) {
                         outReservoir.runningSum = outReservoir.p_y == 0.f ? 0.f : p_y / outReservoir.p_y;
                         if (outReservoir.lightID == VRESTIR_SELF_EMISSION_LIGHT_ID && bounce > 0) {
-                            encodeEmissivePosition(mi.p, outReservoir.lightID, outReservoir.lightUV);
-                            p_y /= (curHitDist * curHitDist);
+                            if (!vertexReuse || bounce < options.vertexReuseStartBounce) {   // :324-331
+                                encodeEmissivePosition(mi.p, outReservoir.lightID, outReservoir.lightUV);
+                                p_y /= (curHitDist * curHitDist);
+                            }
                             outReservoir.sampledPixel = encodePathTag(outReservoir.sampledPixel, 1);
                         }
                         outReservoir.p_y = p_y;
@@ -1742,6 +1783,7 @@ void stageInitial(Pass& p, const FrameSetup& fs) {
         ExtraProvider prov{finalExtra};
         Reservoir tapForEval = finalReservoir; tapForEval.extraBounceStartId = 0;
         float p_hat = evaluate_P_hat(c, ray, sg, prov, fs.spatial, tapForEval, false, true, false);
+        finalReservoir.p_partial = tapForEval.p_partial;   // TraceRays.cs.slang:176-177 passes finalReservoir itself (inout under VERTEX_REUSE)
         if (finalReservoir.runningSum > 0.f) {
             finalReservoir.runningSum *= finalReservoir.p_y == 0.f ? 0.f : p_hat / finalReservoir.p_y;
             finalReservoir.p_y = p_hat;
@@ -1868,7 +1910,7 @@ void stageTemporal(Pass& p, const FrameSetup& fs, float* out_mvec) {
                         Ray neighborRay = {nOrigin, nDir, 0, usedDepth};
                         float backupDepth = taps[i].depth;
                         taps[i].depth = usedDepth;
-                        float p_y = evaluate_P_hat(c, neighborRay, sg, i == 0 ? curProv : tempProv, opt, taps[i], j > 0, true, false);
+                        float p_y = evaluatePHatReadOnly(c, neighborRay, sg, i == 0 ? curProv : tempProv, opt, taps[i], j > 0, true, false);
                         taps[i].depth = backupDepth;
                         if (std::isinf(p_y) || std::isnan(p_y)) p_y = 0.f;
                         p_sum += p_y * correctedM;
@@ -1948,7 +1990,7 @@ void stageSpatial(Pass& p, const FrameSetup& fs, int roundIdIn, int inBuf) {
                     else {
                         float3 neighborRayDir = normalize(camRayDirNN(U, V, Wv, tx2, ty2, W, H));
                         Ray neighborRay = {ray.origin, neighborRayDir, 0, tap.depth};
-                        float p_y = evaluate_P_hat(c, neighborRay, sg, prov, opt, tap, false, true, true);
+                        float p_y = evaluatePHatReadOnly(c, neighborRay, sg, prov, opt, tap, false, true, true);
                         if (std::isinf(p_y) || std::isnan(p_y)) p_y = 0.f;
                         p_sum += p_y * tap2.M;
                     }
@@ -2065,7 +2107,7 @@ int finalBuffer(const Pass& p) {  // totalRoundId % 2 after the spatial rounds (
 
 int runStage(Pass& p, int stage, int arg, float* out_color, float* out_mvec) {
     if (!p.haveVolume || !p.haveCamera || p.W <= 0) return fail(VRESTIR_ERR_NOT_READY, "volume/camera/frame not set");
-    if (p.P.mUseSurfaceScene || p.P.mVertexReuse) return fail(VRESTIR_ERR_UNSUPPORTED, "surface scene / vertex reuse out of scope");
+    if (p.P.mUseSurfaceScene) return fail(VRESTIR_ERR_UNSUPPORTED, "surface scene out of scope");
     ensureBuffers(p);
     applyOverrides(p);
     FrameSetup fs = buildFrameSetup(p.P);
@@ -2264,17 +2306,22 @@ int vro_buffer_bytes(const vro_pass* p, int buffer, size_t* bytes) {
         case VRESTIR_BUF_EXTRA_0: case VRESTIR_BUF_EXTRA_1: case VRESTIR_BUF_EXTRA_TEMPORAL: *bytes = n * (size_t)std::max(0, B - 1) * 12; break;
         case VRESTIR_BUF_FEATURES: case VRESTIR_BUF_FEATURES_TEMPORAL: *bytes = n * 8; break;
         case VRESTIR_BUF_ENV_IMPORTANCE: *bytes = p->importance.size() * 4; break;
+        case VRESTIR_BUF_PPARTIAL_0: case VRESTIR_BUF_PPARTIAL_1: case VRESTIR_BUF_PPARTIAL_TEMPORAL: *bytes = n * 4; break;
         default: return fail(VRESTIR_ERR_INVALID_ARGUMENT, "bad buffer id");
     }
     return VRESTIR_OK;
 }
-static std::vector<Reservoir>* resBuf(vro_pass* p, int b) { return b == VRESTIR_BUF_RESERVOIR_0 ? &p->res[0] : b == VRESTIR_BUF_RESERVOIR_1 ? &p->res[1] : &p->resT; }
+static std::vector<Reservoir>* resBuf(vro_pass* p, int b) {
+    return (b == VRESTIR_BUF_RESERVOIR_0 || b == VRESTIR_BUF_PPARTIAL_0) ? &p->res[0] : (b == VRESTIR_BUF_RESERVOIR_1 || b == VRESTIR_BUF_PPARTIAL_1) ? &p->res[1] : &p->resT;
+}
+static bool isPPartial(int b) { return b >= VRESTIR_BUF_PPARTIAL_0 && b <= VRESTIR_BUF_PPARTIAL_TEMPORAL; }
 static std::vector<ExtraBounce>* extBuf(vro_pass* p, int b) { return b == VRESTIR_BUF_EXTRA_0 ? &p->ext[0] : b == VRESTIR_BUF_EXTRA_1 ? &p->ext[1] : &p->extT; }
 int vro_get_buffer(vro_pass* p, int buffer, void* dst, size_t bytes) {
     ensureBuffers(*p);
     size_t need; int rc = vro_buffer_bytes(p, buffer, &need); if (rc) return rc;
     if (need != bytes) return fail(VRESTIR_ERR_INVALID_ARGUMENT, "size mismatch");
-    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
+    if (isPPartial(buffer)) { auto* v = resBuf(p, buffer); float* o = (float*)dst; for (size_t i = 0; i < v->size(); i++) o[i] = (*v)[i].p_partial; }
+    else if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
         auto* v = resBuf(p, buffer); auto* o = (vrestir_reservoir*)dst;
         for (size_t i = 0; i < v->size(); i++) { const Reservoir& r = (*v)[i]; o[i] = {r.runningSum, r.M, r.depth, r.p_y, {r.lightUV.x, r.lightUV.y}, r.lightID, r.sampledPixel}; }
     } else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) { if (bytes) memcpy(dst, extBuf(p, buffer)->data(), bytes); }
@@ -2288,10 +2335,11 @@ int vro_set_buffer(vro_pass* p, int buffer, const void* src, size_t bytes) {
     size_t need; int rc = vro_buffer_bytes(p, buffer, &need); if (rc) return rc;
     if (need != bytes) return fail(VRESTIR_ERR_INVALID_ARGUMENT, "size mismatch");
     int B = p->P.mMaxBounces;
-    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
+    if (isPPartial(buffer)) { auto* v = resBuf(p, buffer); const float* o = (const float*)src; for (size_t i = 0; i < v->size(); i++) (*v)[i].p_partial = o[i]; }
+    else if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
         auto* v = resBuf(p, buffer); auto* o = (const vrestir_reservoir*)src;
-        for (size_t i = 0; i < v->size(); i++)
-            (*v)[i] = {o[i].runningSum, o[i].M, o[i].depth, o[i].p_y, {o[i].lightUV[0], o[i].lightUV[1]}, o[i].lightID, o[i].sampledPixel, B > 1 ? (int)i * (B - 1) : 0};
+        for (size_t i = 0; i < v->size(); i++)   // p_partial (its own buffer id) is kept
+            (*v)[i] = {o[i].runningSum, o[i].M, o[i].depth, o[i].p_y, {o[i].lightUV[0], o[i].lightUV[1]}, o[i].lightID, o[i].sampledPixel, B > 1 ? (int)i * (B - 1) : 0, (*v)[i].p_partial};
     } else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) { if (bytes) memcpy(extBuf(p, buffer)->data(), src, bytes); }
     else if (buffer == VRESTIR_BUF_FEATURES) memcpy(p->feat.data(), src, bytes);
     else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) memcpy(p->featT.data(), src, bytes);

@@ -70,7 +70,7 @@ def gpu_frame(gp, w, h, want_mvec=False):
     return (color.cpu().numpy(), mvec.cpu().numpy()) if want_mvec else color.cpu().numpy()
 
 
-def compare_reservoirs(a, b, rel=1e-4):
+def compare_reservoirs(a, b, rel=1e-4, pp=None):
     """Returns (flip mask, max relative error of the float fields on non-flipped pixels).
 
     North-star protocol: integer bookkeeping must be bit-exact wherever no candidate selection flipped.  A pixel counts
@@ -88,6 +88,12 @@ def compare_reservoirs(a, b, rel=1e-4):
         fa, fb = a[f].astype(np.float64), b[f].astype(np.float64)
         e = np.abs(fa - fb) / np.maximum(np.abs(fb), 1e-30)
         e[fa == fb] = 0
+        e[~np.isfinite(e)] = np.inf
+        errs = np.maximum(errs, e)
+    if pp is not None:     # (gpu, oracle) p_partial planes (vertex reuse): compared where the reservoir holds a sample
+        fa, fb = pp[0].astype(np.float64).reshape(a.shape), pp[1].astype(np.float64).reshape(a.shape)
+        e = np.abs(fa - fb) / np.maximum(np.abs(fb), 1e-30)
+        e[(fa == fb) | (np.isnan(fa) & np.isnan(fb)) | ~(b["runningSum"] > 0)] = 0
         e[~np.isfinite(e)] = np.inf
         errs = np.maximum(errs, e)
     flips |= errs > rel
@@ -134,10 +140,17 @@ def staged(params, scene, w, h, frames=2, want_mvec=False, dict_=None, camera_pa
     mvec_c = np.zeros((h, w, 2), np.float32)
     B = params.mMaxBounces
     rounds = params.mSpatialReuseRounds if params.mEnableSpatialReuse else 0
+    vr = bool(params.mVertexReuse) and B > 1
+    twin = {capi.BUF_RESERVOIR_0: capi.BUF_PPARTIAL_0, capi.BUF_RESERVOIR_1: capi.BUF_PPARTIAL_1, capi.BUF_RESERVOIR_TEMPORAL: capi.BUF_PPARTIAL_TEMPORAL}
 
     def sync(buf_ids):
         for b in buf_ids:
             gp.set_buffer(b, op.get_buffer(b))
+            if vr and b in twin:
+                gp.set_buffer(twin[b], op.get_buffer(twin[b]))
+
+    def pp(bid):
+        return (gp.get_buffer(twin[bid]).view(np.float32), op.get_buffer(twin[bid]).view(np.float32)) if vr else None
 
     for f in range(frames):
         last = f == frames - 1
@@ -158,13 +171,13 @@ def staged(params, scene, w, h, frames=2, want_mvec=False, dict_=None, camera_pa
                 sync([capi.BUF_FEATURES])
             elif stage in (1, 2):
                 bid = capi.BUF_RESERVOIR_0
-                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid))
+                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid), pp=pp(bid))
                 if last:
                     out["initial" if stage == 1 else "temporal"] = (flips, err)
                 sync([bid] + ([capi.BUF_EXTRA_0] if B > 1 else []))
             elif stage == 3:
                 bid = capi.BUF_RESERVOIR_1 if arg % 2 == 0 else capi.BUF_RESERVOIR_0
-                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid))
+                flips, err = compare_reservoirs(gp.get_buffer(bid), op.get_buffer(bid), pp=pp(bid))
                 if last:
                     out[f"spatial{arg}"] = (flips, err)
                 sync([bid] + ([capi.BUF_EXTRA_1 if arg % 2 == 0 else capi.BUF_EXTRA_0] if B > 1 else []))

@@ -96,6 +96,41 @@ def test_multibounce_staged(B):
     _check_staged(out, w, h, f"B={B}", budget=5e-3)
 
 
+@pytest.mark.parametrize("B,S,scene", [(3, 1, "env"), (4, 2, "env"), (3, 1, "plume"), (3, 2, "plume")])
+def test_vertex_reuse_staged(B, S, scene):
+    """mVertexReuse (VERTEX_REUSE of the reference: paths are reconnected at world-space vertices from bounce S on, the spatial
+    pass reuses the stored suffix p_partial instead of re-marching it), every stage against the oracle on identical inputs,
+    including the p_partial plane.  The plume scene exercises the emissive scatter vertices on both sides of S."""
+    w, h = 96, 64
+    p = VolumetricReSTIRParams(mMaxBounces=B, mVertexReuse=1, mVertexReuseStartBounce=S)
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.15) if scene == "env" else _plume_scene(0.0)
+    out = _staged(p, sc, w, h, frames=2)
+    _check_staged(out, w, h, f"vertex reuse B={B} S={S} {scene}", budget=5e-3)
+
+
+def test_vertex_reuse_changes_the_frame_and_needs_two_bounces():
+    """With one bounce the flag is inert (the reference cannot even compile that combination); with more it renders a different
+    (equally unbiased: tests/test_oracle_properties.py) frame, and the p_partial buffers exist only then."""
+    import torch
+    w, h = 96, 64
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.15)
+    imgs = {}
+    for B, vr in ((1, 0), (1, 1), (3, 0), (3, 1)):
+        gp = VolumetricReSTIR.create({"mParams": VolumetricReSTIRParams(mMaxBounces=B, mVertexReuse=vr)})
+        gp.setScene(sc, w, h)
+        for _ in range(2):
+            imgs[B, vr] = gpu_frame(gp, w, h)
+        if B > 1 and vr:
+            pp = gp.get_buffer(capi.BUF_PPARTIAL_TEMPORAL).view(np.float32)
+            assert pp.size == w * h and (pp != 0).mean() > 0.05
+        else:
+            with pytest.raises(capi.VRestirError):
+                gp.get_buffer(capi.BUF_PPARTIAL_0)
+    assert np.array_equal(imgs[1, 0].view(np.uint32), imgs[1, 1].view(np.uint32))
+    assert not np.array_equal(imgs[3, 0], imgs[3, 1])
+    assert abs(imgs[3, 1][..., :3].mean() / imgs[3, 0][..., :3].mean() - 1) < 0.1
+
+
 def test_emissive_triangles_and_env():
     w, h = 96, 64
     sc = env_scene(dim=(64, 64, 56), density_scale=0.15)
@@ -202,7 +237,8 @@ def test_wavefront_equals_per_pixel(variant):
 
 
 @pytest.mark.parametrize("variant", ["two_bounces", "four_bounces", "three_bounces_emissive_point_light", "four_bounces_no_mis_two_rounds",
-                                     "final_ray_marching", "final_mixed_two_bounces", "spatial_analytic_two_bounces", "three_level_three_bounces"])
+                                     "final_ray_marching", "final_mixed_two_bounces", "spatial_analytic_two_bounces", "three_level_three_bounces",
+                                     "three_bounces_vertex_reuse", "four_bounces_vertex_reuse_from_2"])
 def test_generic_task_streams_equal_per_pixel(variant):
     """The generic task-stream path (the stage bodies run as an emit pass and a consume pass around the march engine: multi-bounce
     option sets, ray-marched / mixed final shading, analytic spatial tracking) must be BIT-identical to the per-pixel kernels,
@@ -231,6 +267,10 @@ def test_generic_task_streams_equal_per_pixel(variant):
     elif variant == "three_level_three_bounces":
         sc = env_scene(dim=(200, 180, 150), density_scale=0.2, num_mips=4, distance=0.9)
         kw = dict(mMaxBounces=3)
+    elif variant == "three_bounces_vertex_reuse":
+        kw = dict(mMaxBounces=3, mVertexReuse=1, mVertexReuseStartBounce=1)
+    elif variant == "four_bounces_vertex_reuse_from_2":
+        kw = dict(mMaxBounces=4, mVertexReuse=1, mVertexReuseStartBounce=2)
     p = VolumetricReSTIRParams(**kw)
     img_s, res_s = _frames_buffers(p, sc, w, h, False)
     for budget_mb in (4096, 3):

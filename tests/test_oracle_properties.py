@@ -133,6 +133,8 @@ def test_neighbor_offsets_r2_and_hammersley():
     VolumetricReSTIRParams(),
     VolumetricReSTIRParams(mMaxBounces=2),
     VolumetricReSTIRParams(mEnableTemporalReuse=0, mEnableSpatialReuse=0),
+    VolumetricReSTIRParams(mMaxBounces=3, mVertexReuse=1, mVertexReuseStartBounce=1),    # VERTEX_REUSE: reconnection at world-space vertices
+    VolumetricReSTIRParams(mMaxBounces=3, mVertexReuse=1, mVertexReuseStartBounce=2),
 ])
 def test_restir_is_unbiased_against_the_reference_path_tracer(params):
     """The pass's own notion of ground truth: mUseReference (brute-force volumetric path tracer)."""

@@ -28,7 +28,7 @@ kRatioTracking, kAnalyticTracking, kRayMarching, kResidualRatioTracking, kAnalog
 kReprojectionLinear, kReprojectionNone, kReprojectionNoBackground = 0, 1, 2
 
 (BUF_RESERVOIR_0, BUF_RESERVOIR_1, BUF_RESERVOIR_TEMPORAL, BUF_EXTRA_0, BUF_EXTRA_1, BUF_EXTRA_TEMPORAL, BUF_FEATURES,
- BUF_FEATURES_TEMPORAL, BUF_ENV_IMPORTANCE) = range(9)
+ BUF_FEATURES_TEMPORAL, BUF_ENV_IMPORTANCE, BUF_PPARTIAL_0, BUF_PPARTIAL_1, BUF_PPARTIAL_TEMPORAL) = range(12)
 
 _I, _U, _F = C.c_int32, C.c_uint32, C.c_float
 

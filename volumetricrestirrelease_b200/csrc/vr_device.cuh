@@ -107,24 +107,28 @@ VRD float2 sampleNext2D(SampleGenerator& sg) { float2 r; r.x = sampleNext1D(sg);
 
 // ------------------------------------------------------------------------------------------------ records
 struct Ray { float3 origin, dir; float tMin, tMax; VRD float3 at(float t) const { return origin + dir * t; } };
-struct Reservoir { float runningSum, M, depth, p_y; float2 lightUV; int lightID, sampledPixel; int extraBounceStartId; };
+// p_partial: VERTEX_REUSE only (VR/HostDeviceSharedDefinitions.h:29-31) — the part of p-hat past the reuse vertex; plane p2 of a ResBuf
+struct Reservoir { float runningSum, M, depth, p_y; float2 lightUV; int lightID, sampledPixel; int extraBounceStartId; float p_partial; };
 
-VRD Reservoir createNewReservoir() { Reservoir r; r.runningSum = 0.f; r.M = 0.f; r.depth = FLT_MAX; r.p_y = 0.f; r.lightUV = make_float2(0, 0); r.lightID = 0; r.sampledPixel = 0; r.extraBounceStartId = 0; return r; }
+VRD Reservoir createNewReservoir() { Reservoir r; r.runningSum = 0.f; r.M = 0.f; r.depth = FLT_MAX; r.p_y = 0.f; r.lightUV = make_float2(0, 0); r.lightID = 0; r.sampledPixel = 0; r.extraBounceStartId = 0; r.p_partial = 0.f; return r; }
 VRD Reservoir loadReservoir(const ResBuf& b, int pixelId, int B) {
     float4 a = __ldg(&b.p0[pixelId]), c = __ldg(&b.p1[pixelId]);
     Reservoir r; r.runningSum = a.x; r.M = a.y; r.depth = a.z; r.p_y = a.w; r.lightUV = make_float2(c.x, c.y);
     r.lightID = __float_as_int(c.z); r.sampledPixel = __float_as_int(c.w); r.extraBounceStartId = B > 1 ? pixelId * (B - 1) : 0;
+    r.p_partial = (B > 1 && b.p2) ? __ldg(&b.p2[pixelId]) : 0.f;
     return r;
 }
 VRD Reservoir loadReservoirRW(const ResBuf& b, int pixelId, int B) {   // buffer written by this kernel: no read-only path
     float4 a = b.p0[pixelId], c = b.p1[pixelId];
     Reservoir r; r.runningSum = a.x; r.M = a.y; r.depth = a.z; r.p_y = a.w; r.lightUV = make_float2(c.x, c.y);
     r.lightID = __float_as_int(c.z); r.sampledPixel = __float_as_int(c.w); r.extraBounceStartId = B > 1 ? pixelId * (B - 1) : 0;
+    r.p_partial = (B > 1 && b.p2) ? b.p2[pixelId] : 0.f;
     return r;
 }
 VRD void storeReservoir(const ResBuf& b, int pixelId, const Reservoir& r) {
     b.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
     b.p1[pixelId] = make_float4(r.lightUV.x, r.lightUV.y, __int_as_float(r.lightID), __int_as_float(r.sampledPixel));
+    if (b.p2) b.p2[pixelId] = r.p_partial;
 }
 
 // ------------------------------------------------------------------------------------------------ tree access
@@ -1185,7 +1189,11 @@ VRD float3 camRayDirNN(float3 U, float3 V, float3 Wv, int px, int py, int W, int
 // ------------------------------------------------------------------------------------------------ ReSTIR helpers
 VRD float3 decodeEmissivePosition(int lightID, float2 lightUV) { return f3(lightUV.x, lightUV.y, __int_as_float(lightID)); }
 VRD void encodeEmissivePosition(float3 pos, int& lightID, float2& lightUV) { lightID = __float_as_int(pos.z); lightUV = make_float2(pos.x, pos.y); }
-VRD float4 decodeWiDist(float3 in) {
+VRD float4 decodeWiDist(float3 in, bool reuseAsVertex = false) {
+    if (reuseAsVertex) {   // VERTEX_REUSE (VR/ReSTIRHelper.slang:21-27): a world-space vertex (w = -1) or "left the medium"
+        if (in.x == kRayTMax) return make_float4(0.f, 0.f, 0.f, kRayTMax);
+        return make_float4(in.x, in.y, in.z, -1.f);
+    }
     float3 wi; wi.x = in.x; wi.y = in.y;
     wi.z = sqrtf(1 - (in.x * in.x + in.y * in.y));
     if (isnan(wi.z)) wi.z = 0.f;
@@ -1204,6 +1212,7 @@ template <int B> VRD void takeSample(const Reservoir& r, Reservoir& state, bool 
     state.lightUV = sel ? r.lightUV : state.lightUV;
     state.lightID = sel ? r.lightID : state.lightID;
     if (B > 1) state.extraBounceStartId = sel ? r.extraBounceStartId : state.extraBounceStartId;
+    if (B > 1) state.p_partial = sel ? r.p_partial : state.p_partial;   // VERTEX_REUSE (VR/Reservoir.slang:46-47,76-77); 0 everywhere without it
     state.sampledPixel = sel ? r.sampledPixel : state.sampledPixel;
 }
 // VR/Reservoir.slang:26-87
@@ -1282,22 +1291,32 @@ struct InlineMarch {
 };
 
 template <class MP>
-VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2 lightUV, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool cullNonOpaqueGeometry, MP& mp) {
+VRD float3 evaluate_L_in_volume(const MediumInteraction& mi, int lightID, float2 lightUV, float& precomputedVisibility, SampleGenerator& sg, const SamplingOptions& o, bool lightVisibilityReuse,
+                                bool isLastFrame, bool cullNonOpaqueGeometry, MP& mp) {
     Ray shadowRay; float3 Ld;
     const bool isValidSample = lightRayAndLd(mi, lightID, lightUV, isLastFrame, shadowRay, Ld);
     const bool useLastFrameGrid = c_scene.vol.usePrevGridForReproj && isLastFrame && c_scene.vol.hasAnimation;
     const int densityGridOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
     float Tr = 1.f;
-    if (isValidSample)
-        Tr = mp.visibility(MARCH_SLOT_LIGHT, shadowRay, sg, o.lightSamples, cullNonOpaqueGeometry ? o.lightingMipLevel + densityGridOffset : 0, o.lightingUseLinearSampler,
-                           o.lightingTrackingMethod, o.lightingTStepScale);
+    if (isValidSample) {
+        if (lightVisibilityReuse) Tr = precomputedVisibility;   // VERTEX_REUSE: the shadow-ray transmittance the sample's own pixel stored
+        else {
+            Tr = mp.visibility(MARCH_SLOT_LIGHT, shadowRay, sg, o.lightSamples, cullNonOpaqueGeometry ? o.lightingMipLevel + densityGridOffset : 0, o.lightingUseLinearSampler,
+                               o.lightingTrackingMethod, o.lightingTStepScale);
+            precomputedVisibility = Tr;
+        }
+    }
     return Tr * Ld;
 }
 
-// VR/ReSTIRHelper.slang:91-423 (no SURFACE_SCENE / VERTEX_REUSE)
+// VR/ReSTIRHelper.slang:91-423 (no SURFACE_SCENE).  VERTEX_REUSE is a run-time choice: o.vertexReuseStartBounce is the
+// reference's S when mVertexReuse is on and VR_NO_VERTEX_REUSE (larger than any bounce count) otherwise, which turns every
+// VERTEX_REUSE condition below into its #else branch.  `tap` is inout (REUSETYPE): unless spatialReuse reads it, the
+// evaluation leaves the part of F past the reuse vertex in tap.p_partial.
 template <int B, class Extra, class MP>
-__device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool noReuse, bool isFinalShading, MP& mp) {
+__device__ float3 evaluate_F_(Reservoir& tap, const Extra& extra, Ray ray, SampleGenerator& sg, const SamplingOptions& o, bool isLastFrame, bool noReuse, bool spatialReuse, bool isFinalShading, MP& mp) {
     const vrestir_volume_desc& vd = c_scene.vol;
+    const int S = o.vertexReuseStartBounce;
     const bool useLastFrameGrid = vd.usePrevGridForReproj && isLastFrame && vd.hasAnimation;
     const int mipLevelOffset = useLastFrameGrid ? VRESTIR_PREV_DENSITY_GRID_OFFSET : 0;
     bool isBackgroundSample = tap.depth == kRayTMax;
@@ -1319,6 +1338,7 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
         if (noReuse && !isBackgroundSample) sigma_s = sigma_s / vd.sigma_t;
         F = F * (visibility * density * sigma_s);
     }
+    float3 P_prefix = f3(1.f);
     int bounceId = 0;
     if (any_gt0(F)) {
         if (isBackgroundSample) {
@@ -1333,8 +1353,8 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
                 const int numIndirectBounces = maxIndirectBounces;
                 for (; bounceId < numIndirectBounces; bounceId++) {
                     bool isCurrentVertexEmissive = isScatterSelfEmission && bounceId == numIndirectBounces - 1;
-                    float4 wiDist = decodeWiDist(extra.get(tap.extraBounceStartId + bounceId));
-                    if (isCurrentVertexEmissive) { float3 e = decodeEmissivePosition(tap.lightID, tap.lightUV); wiDist = make_float4(e.x, e.y, e.z, -1.f); }
+                    float4 wiDist = decodeWiDist(extra.get(tap.extraBounceStartId + bounceId), bounceId + 1 >= S);
+                    if (isCurrentVertexEmissive && bounceId + 1 < S) { float3 e = decodeEmissivePosition(tap.lightID, tap.lightUV); wiDist = make_float4(e.x, e.y, e.z, -1.f); }
                     if (wiDist.w == kRayTMax) return f3(0.f);
                     float dist = 1.f;
                     if (wiDist.w == -1.f) {
@@ -1348,6 +1368,10 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
                     float bsdf = mi.phaseFunction(mi.wo, scatterRay.dir);
                     F = F * bsdf;
                     if (all_eq0(F)) return f3(0.f);
+                    if (bounceId == S) {   // :289-296, the bounce past the reuse vertex
+                        if (spatialReuse) return F * tap.p_partial;
+                        P_prefix = F;
+                    }
                     if (wiDist.w == -1.f) p_World = f3(wiDist.x, wiDist.y, wiDist.z);
                     else p_World = scatterRay.at(scatterRay.tMax);
                     float3 sigma_s; float scatterDensity;
@@ -1359,7 +1383,7 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
                         scatterDensity = 1.f;
                     }
                     F = F * (scatterDensity * sigma_s);
-                    if (isCurrentVertexEmissive) F = F * (1.f / (dist * dist));
+                    if (bounceId + 1 == S || (isCurrentVertexEmissive && bounceId + 1 < S)) F = F * (1.f / (dist * dist));
                     if (all_eq0(F)) return f3(0.f);
                     float scatterVisibility = 1.f;
                     if (!noReuse)
@@ -1373,21 +1397,34 @@ __device__ float3 evaluate_F_(const Reservoir& tap, const Extra& extra, Ray ray,
                 if (isScatterSelfEmission) F = F * EmissionWorldSpace(p_World, useLastFrameGrid);
                 else mi = makeMI(scatterRay.at(scatterRay.tMax), -scatterRay.dir, true);
             }
-            if (!isScatterSelfEmission && any_gt0(F))
-                F = F * evaluate_L_in_volume(mi, tap.lightID, tap.lightUV, sg, o, isLastFrame, !isFinalShading, mp);
+            if (!isScatterSelfEmission && any_gt0(F)) {
+                float precomputedVisibility = tap.p_partial;
+                const bool lightVisibilityReuse = B > 1 && bounceId == S && spatialReuse;
+                F = F * evaluate_L_in_volume(mi, tap.lightID, tap.lightUV, precomputedVisibility, sg, o, lightVisibilityReuse, isLastFrame, !isFinalShading, mp);
+                if (B > 1 && bounceId == S && !spatialReuse) tap.p_partial = precomputedVisibility;
+            }
         }
     }
+    // :415-420, componentwise as written there
+    if (B > 1 && bounceId > S && !spatialReuse) tap.p_partial = luminance(F / P_prefix);
     return F;
 }
+// `tap` is inout: VR/ReSTIRHelper.slang:426-441 under REUSETYPE = inout
 template <int B, class Extra, class MP>
-VRD float evaluate_P_hat(const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, const Reservoir& tap, bool isLastFrame, MP& mp) {
-    float3 F = evaluate_F_<B>(tap, extra, ray, sg, o, isLastFrame, false, false, mp);
+VRD float evaluate_P_hat(const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, Reservoir& tap, bool isLastFrame, bool spatialReuse, MP& mp) {
+    float3 F = evaluate_F_<B>(tap, extra, ray, sg, o, isLastFrame, false, spatialReuse, false, mp);
     return luminance(F);
 }
+// VR/ReSTIRHelper.slang:600-607: the reservoir travels by value, the caller's p_partial stays
 template <int B, class Extra, class MP>
-VRD void resampleNeighbor(Reservoir& tap, const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, MP& mp) {
+VRD float evaluatePHatReadOnly(const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, Reservoir tap, bool isLastFrame, bool spatialReuse, MP& mp) {
+    return evaluate_P_hat<B>(ray, sg, extra, o, tap, isLastFrame, spatialReuse, mp);
+}
+// VR/ReSTIRHelper.slang:560-597: resampleNeighbor (spatialReuse = false, overwrites tap.p_partial) / resampleNeighborSpatialReuse
+template <int B, class Extra, class MP>
+VRD void resampleNeighbor(Reservoir& tap, const Ray& ray, SampleGenerator& sg, const Extra& extra, const SamplingOptions& o, bool spatialReuse, MP& mp) {
     if (tap.runningSum == 0.f) return;
-    float p_y_hat = evaluate_P_hat<B>(ray, sg, extra, o, tap, false, mp);
+    float p_y_hat = evaluate_P_hat<B>(ray, sg, extra, o, tap, false, spatialReuse, mp);
     float weight = p_y_hat / tap.p_y;
     // an emit pass (placeholder transmittances of 1) must keep every sample the real pass can keep: with a denormal p_y the
     // placeholder ratio overflows where the real one is finite

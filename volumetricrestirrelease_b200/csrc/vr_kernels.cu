@@ -69,6 +69,10 @@ __device__ Reservoir ComputeInitialSample(const Ray& primaryRay_, float precompu
             mi = makeMI(ray.at(curHitDist), -ray.dir, curHitDist != kRayTMax);
         }
         pathPdf *= pdfDist;
+        if (B > 1 && bounce == options.vertexReuseStartBounce && curHitDist != kRayTMax) {   // VERTEX_REUSE :88-94, area measure at the reuse vertex
+            pathPdf /= curHitDist * curHitDist;
+            pathPHat /= curHitDist * curHitDist;
+        }
         bool hitEmpty = false;
         float actualVolumeDensity = 0.f;
         if (bounce == 0) {
@@ -80,7 +84,8 @@ __device__ Reservoir ComputeInitialSample(const Ray& primaryRay_, float precompu
             outReservoir.depth = primaryScatterDepth;
             if (B > 1) {
                 outReservoir.sampledPixel = encodeMaxIndirectBounces(outReservoir.sampledPixel, bounce);
-                extrabounceReservoir[bounce - 1] = encodeWiDist(make_float4(ray.dir.x, ray.dir.y, ray.dir.z, !mi.isValid ? kRayTMax : curHitDist));
+                if (bounce < options.vertexReuseStartBounce) extrabounceReservoir[bounce - 1] = encodeWiDist(make_float4(ray.dir.x, ray.dir.y, ray.dir.z, !mi.isValid ? kRayTMax : curHitDist));
+                else extrabounceReservoir[bounce - 1] = !mi.isValid ? f3(kRayTMax) : mi.p;   // VERTEX_REUSE :116-125, world-space vertex
             }
             outReservoir.p_y = pathPdf;
         }
@@ -124,8 +129,10 @@ __device__ Reservoir ComputeInitialSample(const Ray& primaryRay_, float precompu
                     if (outReservoir.runningSum > 0.f) {
                         outReservoir.runningSum = outReservoir.p_y == 0.f ? 0.f : p_y / outReservoir.p_y;
                         if (outReservoir.lightID == VRESTIR_SELF_EMISSION_LIGHT_ID && bounce > 0) {
-                            encodeEmissivePosition(mi.p, outReservoir.lightID, outReservoir.lightUV);
-                            p_y /= (curHitDist * curHitDist);
+                            if (bounce < options.vertexReuseStartBounce) {   // VERTEX_REUSE :324-331
+                                encodeEmissivePosition(mi.p, outReservoir.lightID, outReservoir.lightUV);
+                                p_y /= (curHitDist * curHitDist);
+                            }
                             outReservoir.sampledPixel = encodePathTag(outReservoir.sampledPixel, 1);
                         }
                         outReservoir.p_y = p_y;
@@ -230,7 +237,8 @@ __global__ void __launch_bounds__(128, VR_MINB) k_initial(FrameParams fp) {
     ExtraProvider prov; prov.global = nullptr; prov.local = finalExtra;
     Reservoir tapForEval = finalReservoir; tapForEval.extraBounceStartId = 0;
     InlineMarch mp;
-    float p_hat = evaluate_P_hat<B>(ray, sg, prov, fp.spatial, tapForEval, false, mp);
+    float p_hat = evaluate_P_hat<B>(ray, sg, prov, fp.spatial, tapForEval, false, false, mp);
+    finalReservoir.p_partial = tapForEval.p_partial;   // TraceRays.cs.slang:176-177: finalReservoir itself is the inout argument
     if (finalReservoir.runningSum > 0.f) {
         finalReservoir.runningSum *= finalReservoir.p_y == 0.f ? 0.f : p_hat / finalReservoir.p_y;
         finalReservoir.p_y = p_hat;

@@ -95,7 +95,7 @@ struct vrestir_pass {
     std::vector<uint32_t> aliasItems; std::vector<float> aliasWeights; float aliasWeightSum = 0.f;
 
     int W = 0, H = 0, rowBegin = 0, rowEnd = 0;
-    int allocW = 0, allocH = 0, allocB = 0;
+    int allocW = 0, allocH = 0, allocB = 0; bool allocVR = false;
     float4* res[4] = {nullptr, nullptr, nullptr, nullptr};
     float3* ext[4] = {nullptr, nullptr, nullptr, nullptr};
     int2* feat[3] = {nullptr, nullptr, nullptr};
@@ -163,11 +163,17 @@ struct vrestir_pass {
 namespace {
 
 size_t N(const vrestir_pass* p) { return (size_t)p->W * p->H; }
-ResBuf resView(const vrestir_pass* p, int phys) { ResBuf b; b.p0 = p->res[phys]; b.p1 = p->res[phys] + N(p); return b; }
+bool vertexReuseOn(const vrestir_pass* p) { return p->P.mVertexReuse && p->P.mMaxBounces > 1; }   // VR/VolumetricReSTIR.cpp:363,376
+// planes of one reservoir buffer: p0 | p1 (16 B per pixel each) | p2 = p_partial (4 B per pixel, only with vertex reuse)
+ResBuf resView(const vrestir_pass* p, int phys) {
+    ResBuf b; b.p0 = p->res[phys]; b.p1 = p->res[phys] + N(p); b.p2 = vertexReuseOn(p) ? (float*)(p->res[phys] + 2 * N(p)) : nullptr;
+    return b;
+}
 
 int ensureBuffers(vrestir_pass* p) {
     const int B = p->P.mMaxBounces;
-    if (p->allocW == p->W && p->allocH == p->H && p->allocB == B && p->res[0]) return VRESTIR_OK;
+    const bool vr = vertexReuseOn(p);
+    if (p->allocW == p->W && p->allocH == p->H && p->allocB == B && p->allocVR == vr && p->res[0]) return VRESTIR_OK;
     const size_t n = N(p);
     if (p->pfStream) CK(cudaStreamSynchronize(p->pfStream));     // a prefetch may be writing, a deferred K5 reading them
     if (p->outStream) CK(cudaStreamSynchronize(p->outStream));
@@ -176,13 +182,14 @@ int ensureBuffers(vrestir_pass* p) {
     for (int i = 0; i < 4; i++) { if (p->ext[i]) cudaFree(p->ext[i]); p->ext[i] = nullptr; }
     for (int i = 0; i < 3; i++) { if (p->feat[i]) cudaFree(p->feat[i]); p->feat[i] = nullptr; }
     if (p->refColor) { cudaFree(p->refColor); p->refColor = nullptr; }
-    for (int i = 0; i < 4; i++) { CK(cudaMalloc(&p->res[i], n * 32)); CK(cudaMemset(p->res[i], 0, n * 32)); }
+    const size_t resBytes = n * (vr ? 36 : 32);
+    for (int i = 0; i < 4; i++) { CK(cudaMalloc(&p->res[i], resBytes)); CK(cudaMemset(p->res[i], 0, resBytes)); }
     for (int i = 0; i < 4; i++) {   // one per reservoir buffer (ping, pong, history, prefetch target)
         if (B > 1) { CK(cudaMalloc(&p->ext[i], n * (size_t)(B - 1) * 12)); CK(cudaMemset(p->ext[i], 0, n * (size_t)(B - 1) * 12)); }
     }
     for (int i = 0; i < 3; i++) { CK(cudaMalloc(&p->feat[i], n * 8)); CK(cudaMemset(p->feat[i], 0, n * 8)); }
     CK(cudaMalloc(&p->refColor, n * 16)); CK(cudaMemset(p->refColor, 0, n * 16));
-    p->allocW = p->W; p->allocH = p->H; p->allocB = B;
+    p->allocW = p->W; p->allocH = p->H; p->allocB = B; p->allocVR = vr;
     p->ia = 0; p->ib = 1; p->it = 2; p->in = 3; p->finalPhys = 0; p->featCur = 0; p->featPrev = 1; p->featNext = 2; p->featSwapPending = false;
     return VRESTIR_OK;
 }
@@ -443,7 +450,7 @@ SamplingOptions mkOpt(uint32_t vt, uint32_t lt, int ls, int lm, int vs, int vm, 
     o.visibilityTrackingMethod = vt; o.lightingTrackingMethod = lt; o.lightSamples = ls; o.lightingMipLevel = lm; o.visibilitySamples = vs; o.visibilityMipLevel = vm;
     o.visibilityUseLinearSampler = vl; o.lightingUseLinearSampler = ll; o.visibilityTStepScale = vts; o.lightingTStepScale = lts;
     o.useEnvironmentLights = m.mUseEnvironmentLights; o.useAnalyticLights = m.mUseAnalyticLights; o.useEmissiveLights = m.mUseEmissiveLights;
-    o.vertexReuseStartBounce = m.mVertexReuseStartBounce;
+    o.vertexReuseStartBounce = (m.mVertexReuse && m.mMaxBounces > 1) ? m.mVertexReuseStartBounce : VR_NO_VERTEX_REUSE;
     return o;
 }
 
@@ -758,7 +765,6 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
     if (!p->haveVolume || !p->haveCamera || p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "volume/camera/frame not set");
     const vrestir_params& m = p->P;
     if (m.mUseSurfaceScene) return setError(VRESTIR_ERR_UNSUPPORTED, "mUseSurfaceScene: surface scenes are outside the hot-path scope (SURVEY.md 8f rank 4)");
-    if (m.mVertexReuse) return setError(VRESTIR_ERR_UNSUPPORTED, "mVertexReuse is not implemented");
     if (m.mMaxBounces < 1 || m.mMaxBounces > VRESTIR_MAX_BOUNCES) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mMaxBounces must be 1..4");
     if (m.mSpatialSampleCount < 1 || m.mSpatialSampleCount > 32) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mSpatialSampleCount must be 1..32");
     if (m.mInitialM < 1) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "mInitialM must be >= 1");
@@ -1683,8 +1689,8 @@ int vrestir_get_launch_count(const vrestir_pass* p, uint64_t* out) try {
 
 static int physOf(const vrestir_pass* p, int buffer) {
     switch (buffer) {
-        case VRESTIR_BUF_RESERVOIR_0: case VRESTIR_BUF_EXTRA_0: return p->ia;
-        case VRESTIR_BUF_RESERVOIR_1: case VRESTIR_BUF_EXTRA_1: return p->ib;
+        case VRESTIR_BUF_RESERVOIR_0: case VRESTIR_BUF_EXTRA_0: case VRESTIR_BUF_PPARTIAL_0: return p->ia;
+        case VRESTIR_BUF_RESERVOIR_1: case VRESTIR_BUF_EXTRA_1: case VRESTIR_BUF_PPARTIAL_1: return p->ib;
         default: return p->it;
     }
 }
@@ -1696,6 +1702,9 @@ int vrestir_buffer_bytes(const vrestir_pass* p, int buffer, size_t* bytes) try {
         case VRESTIR_BUF_EXTRA_0: case VRESTIR_BUF_EXTRA_1: case VRESTIR_BUF_EXTRA_TEMPORAL: *bytes = n * (size_t)std::max(0, B - 1) * 12; break;
         case VRESTIR_BUF_FEATURES: case VRESTIR_BUF_FEATURES_TEMPORAL: *bytes = n * 8; break;
         case VRESTIR_BUF_ENV_IMPORTANCE: *bytes = p->importanceCount * 4; break;
+        case VRESTIR_BUF_PPARTIAL_0: case VRESTIR_BUF_PPARTIAL_1: case VRESTIR_BUF_PPARTIAL_TEMPORAL:
+            if (!vertexReuseOn(p)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "p_partial exists only with mVertexReuse and mMaxBounces > 1");
+            *bytes = n * 4; break;
         default: return setError(VRESTIR_ERR_INVALID_ARGUMENT, "bad buffer id");
     }
     return VRESTIR_OK;
@@ -1708,7 +1717,8 @@ int vrestir_get_buffer(vrestir_pass* p, int buffer, void* dst, size_t bytes) try
     if (buffer != VRESTIR_BUF_ENV_IMPORTANCE) { if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set"); rc = ensureBuffers(p); if (rc) return rc; }
     CK(cudaDeviceSynchronize());
     if (!bytes) return VRESTIR_OK;
-    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
+    if (buffer >= VRESTIR_BUF_PPARTIAL_0 && buffer <= VRESTIR_BUF_PPARTIAL_TEMPORAL) CK(cudaMemcpy(dst, resView(p, physOf(p, buffer)).p2, bytes, cudaMemcpyDeviceToHost));
+    else if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
         vrestir_reservoir* tmp; CK(cudaMalloc(&tmp, bytes));
         cudaError_t e = launchResToAos(resView(p, physOf(p, buffer)), tmp, (int)N(p), 0); p->launches++;
         if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, bytes, cudaMemcpyDeviceToHost);
@@ -1727,7 +1737,8 @@ int vrestir_set_buffer(vrestir_pass* p, int buffer, const void* src, size_t byte
     if (buffer != VRESTIR_BUF_ENV_IMPORTANCE) { if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set"); rc = ensureBuffers(p); if (rc) return rc; }
     CK(cudaDeviceSynchronize());
     if (!bytes) return VRESTIR_OK;
-    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
+    if (buffer >= VRESTIR_BUF_PPARTIAL_0 && buffer <= VRESTIR_BUF_PPARTIAL_TEMPORAL) CK(cudaMemcpy(resView(p, physOf(p, buffer)).p2, src, bytes, cudaMemcpyHostToDevice));
+    else if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) {
         vrestir_reservoir* tmp; CK(cudaMalloc(&tmp, bytes));
         cudaError_t e = cudaMemcpy(tmp, src, bytes, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) { e = launchResFromAos(resView(p, physOf(p, buffer)), tmp, (int)N(p), 0); p->launches++; }
@@ -1748,7 +1759,11 @@ int vrestir_device_buffer(vrestir_pass* p, int buffer, void** base, size_t* plan
     if (p->W <= 0) return setError(VRESTIR_ERR_NOT_READY, "frame not set");
     int rc = ensureBuffers(p); if (rc) return rc;
     const size_t n = N(p);
-    if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) { *base = p->res[physOf(p, buffer)]; if (plane_stride_bytes) *plane_stride_bytes = n * 16; if (planes) *planes = 2; }
+    if (buffer >= VRESTIR_BUF_PPARTIAL_0 && buffer <= VRESTIR_BUF_PPARTIAL_TEMPORAL) {
+        if (!vertexReuseOn(p)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "p_partial exists only with mVertexReuse and mMaxBounces > 1");
+        *base = resView(p, physOf(p, buffer)).p2; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1;
+    }
+    else if (buffer <= VRESTIR_BUF_RESERVOIR_TEMPORAL) { *base = p->res[physOf(p, buffer)]; if (plane_stride_bytes) *plane_stride_bytes = n * 16; if (planes) *planes = 2; }
     else if (buffer <= VRESTIR_BUF_EXTRA_TEMPORAL) { *base = p->ext[physOf(p, buffer)]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
     else if (buffer == VRESTIR_BUF_FEATURES) { *base = p->feat[p->featCur]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }
     else if (buffer == VRESTIR_BUF_FEATURES_TEMPORAL) { *base = p->feat[p->featSwapPending ? p->featCur : p->featPrev]; if (plane_stride_bytes) *plane_stride_bytes = 0; if (planes) *planes = 1; }

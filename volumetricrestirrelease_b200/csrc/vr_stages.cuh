@@ -93,7 +93,7 @@ __device__ __forceinline__ void temporalPixel(const FrameParams& fp, int x, int 
         if (taps[i].p_y > 0.f) {
             neighbor_py = taps[i].p_y;
             if (isnan(taps[i].runningSum) || isinf(taps[i].runningSum)) taps[i].runningSum = 0.f;
-            if (i > 0) { mp.beginEval(i * 2); resampleNeighbor<B>(taps[i], ray, sg, tempProv, fp.spatial, mp); }
+            if (i > 0) { mp.beginEval(i * 2); resampleNeighbor<B>(taps[i], ray, sg, tempProv, fp.spatial, false, mp); }
         } else { taps[i].p_y = 0.f; taps[i].runningSum = 0.f; }
         if (mis == VRESTIR_MIS_TALBOT && taps[i].runningSum > 0.f) {
             float p_sum = 0, p_qi = 0, k = 0;
@@ -113,8 +113,8 @@ __device__ __forceinline__ void temporalPixel(const FrameParams& fp, int x, int 
                     taps[i].depth = usedDepth;
                     float p_y;
                     mp.beginEval(i * 2 + j);
-                    if (i == 0) p_y = evaluate_P_hat<B>(neighborRay, sg, curProv, fp.spatial, taps[i], j > 0, mp);
-                    else p_y = evaluate_P_hat<B>(neighborRay, sg, tempProv, fp.spatial, taps[i], j > 0, mp);
+                    if (i == 0) p_y = evaluatePHatReadOnly<B>(neighborRay, sg, curProv, fp.spatial, taps[i], j > 0, false, mp);
+                    else p_y = evaluatePHatReadOnly<B>(neighborRay, sg, tempProv, fp.spatial, taps[i], j > 0, false, mp);
                     taps[i].depth = backupDepth;
                     if (isinf(p_y) || isnan(p_y)) p_y = 0.f;
                     p_sum += p_y * correctedM;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void spatialPixel(const FrameParams& fp, int x, int y
         if (!(tx >= 0 && tx < W && ty >= 0 && ty < H)) continue;
         Reservoir tap = loadReservoir(fp.cur, ty * W + tx, B);
         float MISWeight = 1.f;
-        if (sampleId > 0) { mp.beginEval(sampleId * 4); resampleNeighbor<B>(tap, ray, sg, prov, fp.spatial, mp); }
+        if (sampleId > 0) { mp.beginEval(sampleId * 4); resampleNeighbor<B>(tap, ray, sg, prov, fp.spatial, true, mp); }
         if (mis == VRESTIR_MIS_TALBOT && tap.runningSum > 0.f) {
             float p_sum = 0, p_qi = 0, k = 0;
             for (int j = 0; j < fp.sampleCount; j++) {
@@ -187,7 +187,7 @@ __device__ __forceinline__ void spatialPixel(const FrameParams& fp, int x, int y
                     float3 neighborRayDir = normalize(camRayDirNN(fp.camU, fp.camV, fp.camW, tx2, ty2, W, H));
                     Ray neighborRay = makeRay(ray.origin, neighborRayDir, 0, tap.depth);
                     mp.beginEval(sampleId * 4 + j);
-                    float p_y = evaluate_P_hat<B>(neighborRay, sg, prov, fp.spatial, tap, false, mp);
+                    float p_y = evaluatePHatReadOnly<B>(neighborRay, sg, prov, fp.spatial, tap, false, true, mp);
                     if (isinf(p_y) || isnan(p_y)) p_y = 0.f;
                     p_sum += p_y * t2.y;
                 }
@@ -227,7 +227,7 @@ __device__ __forceinline__ void finalPixel(const FrameParams& fp, int x, int y, 
             ray.tMax = cur.depth;
             ExtraProvider prov; prov.global = fp.extCur; prov.local = nullptr;
             mp.beginEval(0);
-            float3 col = evaluate_F_<B>(cur, prov, ray, sg, fp.fin, false, fp.noReuse != 0, true, mp);
+            float3 col = evaluate_F_<B>(cur, prov, ray, sg, fp.fin, false, fp.noReuse != 0, false, true, mp);
             float Wt = cur.p_y == 0.0f ? 1.f : cur.runningSum / (cur.p_y * cur.M);
             col = col * Wt;
             outputColor = outputColor + col;

@@ -59,7 +59,8 @@ struct SamplingOptions {   // VR/HostDeviceSharedDefinitions.h:82-138
 
 // SoA reservoir storage: plane 0 = (runningSum, M, depth, p_y), plane 1 = (lightUV.x, lightUV.y, lightID, sampledPixel);
 // extraBounceStartId is implied by the pixel the record is read from (pixel * (B-1)).
-struct ResBuf { float4* p0; float4* p1; };
+struct ResBuf { float4* p0; float4* p1; float* p2; };   // p2: Reservoir::p_partial, nullptr unless mVertexReuse && mMaxBounces > 1
+#define VR_NO_VERTEX_REUSE (1 << 30)                  // SamplingOptions::vertexReuseStartBounce when vertex reuse is off
 
 struct FrameParams {
     int W, H, rowBegin, rowEnd;

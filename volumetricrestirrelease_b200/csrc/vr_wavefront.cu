@@ -1023,8 +1023,13 @@ __device__ __forceinline__ bool mbAdvancePixel(const FrameParams& fp, const WfIn
                 }
                 mi = makeMI(ray.at(curHitDist), -ray.dir, curHitDist != kRayTMax);
                 pathPdf *= pdfDist;
+                if (bounce == options.vertexReuseStartBounce && curHitDist != kRayTMax) {   // VERTEX_REUSE :88-94
+                    pathPdf /= curHitDist * curHitDist;
+                    pathPHat /= curHitDist * curHitDist;
+                }
                 if (bounce == 0) primaryScatterDepth = mi.isValid ? curHitDist : kRayTMax;
-                else extra[bounce - 1] = encodeWiDist(make_float4(ray.dir.x, ray.dir.y, ray.dir.z, !mi.isValid ? kRayTMax : curHitDist));
+                else if (bounce < options.vertexReuseStartBounce) extra[bounce - 1] = encodeWiDist(make_float4(ray.dir.x, ray.dir.y, ray.dir.z, !mi.isValid ? kRayTMax : curHitDist));
+                else extra[bounce - 1] = !mi.isValid ? f3(kRayTMax) : mi.p;   // VERTEX_REUSE :116-125
                 c.flags = mi.isValid ? 1u : 0u; c.curHitDist = curHitDist; c.Tr = Tr; c.density = 0.f;
                 c.Li = f3(0.f); c.ph = 0.f; c.outLightPdf = 0.f; c.Le = f3(0.f); c.lightID = 0; c.lightUV = make_float2(0, 0); c.mip = mi.p;
                 if (mi.isValid) c.density = DensityWorldSpace(mi.p, 0);
@@ -1106,8 +1111,10 @@ __device__ __forceinline__ bool mbAdvancePixel(const FrameParams& fp, const WfIn
                         if (outReservoir.runningSum > 0.f) {
                             outReservoir.runningSum = outReservoir.p_y == 0.f ? 0.f : p_y / outReservoir.p_y;
                             if (outReservoir.lightID == VRESTIR_SELF_EMISSION_LIGHT_ID && bounce > 0) {
-                                encodeEmissivePosition(c.mip, outReservoir.lightID, outReservoir.lightUV);
-                                p_y /= (curHitDist * curHitDist);
+                                if (bounce < options.vertexReuseStartBounce) {   // VERTEX_REUSE :324-331
+                                    encodeEmissivePosition(c.mip, outReservoir.lightID, outReservoir.lightUV);
+                                    p_y /= (curHitDist * curHitDist);
+                                }
                                 outReservoir.sampledPixel = encodePathTag(outReservoir.sampledPixel, 1);
                             }
                             outReservoir.p_y = p_y;
@@ -1218,16 +1225,20 @@ __device__ __forceinline__ void initialFinishPixel(const FrameParams& fp, int x,
     const int pixelId = y * fp.W + x;
     Reservoir r = loadReservoirRW(fp.cur, pixelId, B);
     // the reference evaluates p-hat unconditionally and uses it only when runningSum > 0; ray-marched p-hat draws no random numbers
-    if (!(r.runningSum > 0.f)) return;
+    // (under VERTEX_REUSE the evaluation also leaves p_partial behind, so it is not skipped)
+    if (!(r.runningSum > 0.f) && !fp.cur.p2) return;
     ExtraProviderRW prov; prov.global = fp.extCur;
     const Ray ray = primaryRay(fp, x, y);
     mp.beginEval(0);
     SampleGenerator none; none.s0 = none.s1 = none.s2 = none.s3 = 0;   // deterministic tracking: never drawn from
-    const float p_hat = evaluate_P_hat<B>(ray, none, prov, fp.spatial, r, false, mp);
+    const float p_hat = evaluate_P_hat<B>(ray, none, prov, fp.spatial, r, false, false, mp);
     if (!MP::kStore) return;
-    r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
-    r.p_y = p_hat;
-    fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
+    if (r.runningSum > 0.f) {
+        r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
+        r.p_y = p_hat;
+        fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
+    }
+    if (fp.cur.p2) fp.cur.p2[pixelId] = r.p_partial;
 }
 template <int B>
 __global__ void __launch_bounds__(128, VR_MB_MINB) k_initial_finish_emit(FrameParams fp, MarchStreams ms, float* results) {

@@ -207,11 +207,21 @@ class ShardedPass:
                 out.append(device_view(base + k * stride, n * 16, self.device).view(self.H, self.W * 16))
         elif buffer in (capi.BUF_FEATURES, capi.BUF_FEATURES_TEMPORAL):
             out.append(device_view(base, n * 8, self.device).view(self.H, self.W * 8))
+        elif buffer in (capi.BUF_PPARTIAL_0, capi.BUF_PPARTIAL_1, capi.BUF_PPARTIAL_TEMPORAL):
+            out.append(device_view(base, n * 4, self.device).view(self.H, self.W * 4))
         else:
             B = self.p.params.mMaxBounces
             if B > 1 and base:
                 out.append(device_view(base, n * (B - 1) * 12, self.device).view(self.H, self.W * (B - 1) * 12))
         return out
+
+    def _with_ppartial(self, bufs):
+        """Reservoir buffers travel with their p_partial plane when vertex reuse is on (VR/HostDeviceSharedDefinitions.h:29-31)."""
+        prm = self.p.params
+        if not (prm.mVertexReuse and prm.mMaxBounces > 1):
+            return bufs
+        twin = {capi.BUF_RESERVOIR_0: capi.BUF_PPARTIAL_0, capi.BUF_RESERVOIR_1: capi.BUF_PPARTIAL_1, capi.BUF_RESERVOIR_TEMPORAL: capi.BUF_PPARTIAL_TEMPORAL}
+        return bufs + [twin[b] for b in bufs if b in twin]
 
     def _exchange(self, buffers, halo, wait=True):
         if self.world == 1:
@@ -221,7 +231,7 @@ class ShardedPass:
             raise capi.VRestirError(capi.ERR_INVALID_ARGUMENT, f"halo of {int(halo)} rows exceeds the smallest row band ({self.max_halo} rows): "
                                     "use fewer ranks, a smaller mSampleRadius or larger bands")
         planes = []
-        for b in buffers:
+        for b in self._with_ppartial(list(buffers)):
             planes += self._planes(b)
         # NCCL send/recv are ordered after the pass's kernels through torch's current stream (the pass launches on the same,
         # default, stream) and work.wait() only makes that stream wait: no host synchronisation
@@ -247,7 +257,7 @@ class ShardedPass:
             B_ = prm.mMaxBounces
             bufs = [capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_FEATURES_TEMPORAL] + ([capi.BUF_EXTRA_TEMPORAL] if B_ > 1 else [])
             planes = []
-            for b in bufs:
+            for b in self._with_ppartial(bufs):
                 planes += self._planes(b)
             for w in gather_row_bands(planes, self.bands, self.rank):
                 w.wait()
