@@ -68,7 +68,7 @@ enum {
     VRESTIR_OK = 0,
     VRESTIR_WARN_UNKNOWN_KEY = 1,        /* mirrors logWarning on unknown dict key, VR/VolumetricReSTIR.h:309 */
     VRESTIR_ERR_INVALID_ARGUMENT = -1,
-    VRESTIR_ERR_UNSUPPORTED = -2,        /* option outside the hot-path scope (surface scene, vertex reuse, ...) */
+    VRESTIR_ERR_UNSUPPORTED = -2,        /* option outside the hot-path scope (surface scene, ...) */
     VRESTIR_ERR_CUDA = -3,
     VRESTIR_ERR_NOT_READY = -4,          /* execute() before set_volume()/set_camera() */
     VRESTIR_ERR_IO = -5
