@@ -1,4 +1,6 @@
 """Shared scene/config factories for the tests (SURVEY.md section 8d configurations at test sizes)."""
+import os
+
 import numpy as np
 
 from oracle import vro
@@ -121,6 +123,8 @@ def rel_mse(a, b):
 
 FLIP_BUDGET = 1e-3        # north star: flips <= 0.1 % of pixels
 RADIANCE_RTOL = 1e-4      # north star: radiance within 1e-4 relative per pixel (non-flipped)
+# K0 transmittance, exact build: libm-ulp level; the contraction-enabled build is held to the north-star 1e-4 (test_gpu_fast_build.py)
+FEATURE_RTOL = float(os.environ.get("VRESTIR_FEATURE_RTOL", "2e-5"))
 
 
 def staged(params, scene, w, h, frames=2, want_mvec=False, dict_=None, camera_path=None, own_tables=False):
@@ -167,7 +171,7 @@ def staged(params, scene, w, h, frames=2, want_mvec=False, dict_=None, camera_pa
             if stage == 0:
                 fg = gp.get_buffer(capi.BUF_FEATURES).view(FEAT)
                 fc = op.get_buffer(capi.BUF_FEATURES).view(FEAT)
-                np.testing.assert_allclose(fg["transmittance"], fc["transmittance"], rtol=2e-5, atol=1e-7)
+                np.testing.assert_allclose(fg["transmittance"], fc["transmittance"], rtol=FEATURE_RTOL, atol=1e-7)
                 sync([capi.BUF_FEATURES])
             elif stage in (1, 2):
                 bid = capi.BUF_RESERVOIR_0

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from common import (FEAT, FLIP_BUDGET, RADIANCE_RTOL, RES, capi, compare_reservoirs, config1_params, config1_scene, env_scene, gpu_frame,
+from common import (FEAT, FEATURE_RTOL, FLIP_BUDGET, RADIANCE_RTOL, RES, capi, compare_reservoirs, config1_params, config1_scene, env_scene, gpu_frame,
                     make_pair, rel_err_image)
 from volumetricrestirrelease_b200 import VolumetricReSTIR, VolumetricReSTIRParams
 
@@ -27,7 +27,7 @@ def test_config1_single_frame_no_reuse(M):
     fg = gp.get_buffer(capi.BUF_FEATURES).view(FEAT)
     fc = op.get_buffer(capi.BUF_FEATURES).view(FEAT)
     assert (fg["noReflectiveSurface"] == fc["noReflectiveSurface"]).all()
-    np.testing.assert_allclose(fg["transmittance"], fc["transmittance"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(fg["transmittance"], fc["transmittance"], rtol=FEATURE_RTOL, atol=1e-7)
     flips, err = compare_reservoirs(gp.get_buffer(capi.BUF_RESERVOIR_0), op.get_buffer(capi.BUF_RESERVOIR_0))
     e = rel_err_image(img_gpu, img_cpu, mask=~flips.reshape(h, w))
     _report(f"config1 M={M}", flips, err, e)
