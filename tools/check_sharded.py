@@ -23,15 +23,28 @@ def main():
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--level", type=int, default=2, help="mPipelineFrames level of the sharded pass")
     ap.add_argument("--motion", type=float, default=0.0, help="camera step per frame in world units (large: the history all-gather fallback must kick in)")
+    ap.add_argument("--bounces", type=int, default=1)
+    ap.add_argument("--vertex-reuse", type=int, default=0, help="mVertexReuse with this start bounce (0: off); the p_partial plane travels with the halos")
+    ap.add_argument("--emissive", type=int, default=0, help="number of emissive triangles around the volume (mUseEmissiveLights)")
+    ap.add_argument("--scratch-mb", type=int, default=0, help="mScratchBudgetMB of the sharded pass (small: the generic stages run in row chunks)")
     a = ap.parse_args()
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    args = argparse.Namespace(width=a.width, height=a.height, dim=[289, 286, 219], kind="bunny", mips=4, bounces=1)
+    args = argparse.Namespace(width=a.width, height=a.height, dim=[289, 286, 219], kind="bunny", mips=4, bounces=a.bounces)
     W, H = a.width, a.height
     scene = bench.build_scene(args)
     params = bench.make_params(args)
-    gp = VolumetricReSTIR.create({"mParams": params, "mPipelineFrames": a.level}, device=local)
+    if a.vertex_reuse:
+        params.mVertexReuse, params.mVertexReuseStartBounce = 1, a.vertex_reuse
+    if a.emissive:
+        lo, hi = scene.volume_bounds_world()
+        scene.addEmissiveShell(a.emissive, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
+        params.mUseEmissiveLights = 1
+    d = {"mParams": params, "mPipelineFrames": a.level}
+    if a.scratch_mb:
+        d["mScratchBudgetMB"] = a.scratch_mb
+    gp = VolumetricReSTIR.create(d, device=local)
     sp = ShardedPass(gp, W, H, rank, world, torch.device("cuda", local))
     gp.setScene(scene, W, H)
     r0, r1 = sp.balance(refine=0)
@@ -58,7 +71,8 @@ def main():
     t = torch.tensor([bad], device="cuda", dtype=torch.int64)
     dist.all_reduce(t)
     if rank == 0:
-        print(f"[check_sharded] world {world} bands {sp.bands} frames {a.frames} pipelining level {a.level}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
+        print(f"[check_sharded] world {world} bands {sp.bands} frames {a.frames} pipelining level {a.level} bounces {a.bounces} vertex reuse {a.vertex_reuse} "
+              f"emissive {a.emissive}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
               f"pipeline {gp.pipeline_stats()}, history all-gathers {sp.history_gathers}")
     dist.destroy_process_group()
     sys.exit(1 if int(t[0]) else 0)
