@@ -238,7 +238,7 @@ def test_wavefront_equals_per_pixel(variant):
 
 @pytest.mark.parametrize("variant", ["two_bounces", "four_bounces", "three_bounces_emissive_point_light", "four_bounces_no_mis_two_rounds",
                                      "final_ray_marching", "final_mixed_two_bounces", "spatial_analytic_two_bounces", "three_level_three_bounces",
-                                     "three_bounces_vertex_reuse", "four_bounces_vertex_reuse_from_2"])
+                                     "three_bounces_vertex_reuse", "four_bounces_vertex_reuse_from_2", "three_bounces_trilinear_initial"])
 def test_generic_task_streams_equal_per_pixel(variant):
     """The generic task-stream path (the stage bodies run as an emit pass and a consume pass around the march engine: multi-bounce
     option sets, ray-marched / mixed final shading, analytic spatial tracking) must be BIT-identical to the per-pixel kernels,
@@ -271,6 +271,8 @@ def test_generic_task_streams_equal_per_pixel(variant):
         kw = dict(mMaxBounces=3, mVertexReuse=1, mVertexReuseStartBounce=1)
     elif variant == "four_bounces_vertex_reuse_from_2":
         kw = dict(mMaxBounces=4, mVertexReuse=1, mVertexReuseStartBounce=2)
+    elif variant == "three_bounces_trilinear_initial":   # the indirect bounces' free-flight sampling runs in k_initial_mb_bounce_traverse, not the engine
+        kw = dict(mMaxBounces=3, mInitialVisibilityUseLinearSampler=1)
     p = VolumetricReSTIRParams(**kw)
     img_s, res_s = _frames_buffers(p, sc, w, h, False)
     for budget_mb in (4096, 3):
@@ -297,9 +299,9 @@ def test_generic_task_streams_are_used_and_chunked():
         gp.execute(color.data_ptr())
         torch.cuda.synchronize()
         counts.append(gp.launch_count() - n0)
-    # K0 + K1 {traverse, first step, M * B x (march, step), p-hat emit / march / consume} + K2 {emit, 1 march, consume}
+    # K0 + K1 {traverse, first step, M * (2B - 1) x (march, bounce traverse, step), p-hat emit / march / consume} + K2 {emit, 1 march, consume}
     # + K3 {emit, camera march, 1 march, consume} + K5 {emit, 1 march, consume}
-    assert counts[0] == 1 + (2 + 2 * 4 * 3 + 3) + 3 + 4 + 3, counts
+    assert counts[0] == 1 + (2 + 3 * 4 * (2 * 3 - 1) + 3) + 3 + 4 + 3, counts
     assert counts[1] > counts[0], counts
 
 

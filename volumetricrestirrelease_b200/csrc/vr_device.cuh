@@ -1461,10 +1461,11 @@ VRD unsigned rayBucket(const PreparedRay& pr) {
     return ((unsigned)(ub * 16 + vb) << 8) | ((h >> 7) & 0xFFu);
 }
 // Append one prepared task per lane with `want` to a stream; every lane of the warp must call (one atomic per warp).
-VRD void wfEmitRay(const WfStream& s, bool want, const Ray& rW, int mip, bool vertexCenter, float* results, unsigned out) {
+// missValue: what a ray that misses the volume box leaves in its result slot (transmittance 1; kRayTMax for a distance task)
+VRD void wfEmitRay(const WfStream& s, bool want, const Ray& rW, int mip, bool vertexCenter, float* results, unsigned out, float missValue = 1.f) {
     PreparedRay pr;
     bool has = false;
-    if (want) { has = wfPrepare(rW, mip, vertexCenter, pr); if (!has) results[out] = 1.f; }
+    if (want) { has = wfPrepare(rW, mip, vertexCenter, pr); if (!has) results[out] = missValue; }
     const unsigned bal = __ballot_sync(0xffffffffu, has);
     if (!bal) return;
     const int lane = threadIdx.x & 31;

@@ -31,6 +31,10 @@ cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cuda
 cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 cudaError_t launchInitialMBTraverse(const FrameParams& fp, const WfInitialMB& wi, cudaStream_t st);
 int initialMBStepBlocksPerSM();
+int initialMBBounceTraverseBlocksPerSM();
+int distanceBlocksPerSM();
+cudaError_t launchMarchDistance(const WfStream& s, float* state, const MarchKind& kind, const DSlot& grid, int blocks, cudaStream_t st);
+cudaError_t launchInitialMBBounceTraverse(const FrameParams& fp, const WfInitialMB& wi, int blocks, cudaStream_t st);
 cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, int blocks, cudaStream_t st);
 // generic task-stream path (stage = 1 K1's final p-hat, 2 temporal, 3 spatial, 5 final): the stage body as an emit pass / a consume pass
 cudaError_t launchStageEmit(int stage, const FrameParams& fp, const MarchStreams& ms, const WfStream& cam, float* results, cudaStream_t st);

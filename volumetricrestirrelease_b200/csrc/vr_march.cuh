@@ -220,7 +220,7 @@ struct RayMarcher : MarchTrav {
         phase = MARCH_IDLE;
     }
 
-    VRD void setup(const uint4* q, const MarchKind& kind, const DSlot& g) {
+    VRD void setup(const uint4* q, const MarchKind& kind, const DSlot& g, const float*) {
         const int mip = kind.mip;
         int eff = mip >= VRESTIR_PREV_DENSITY_GRID_OFFSET ? mip - VRESTIR_PREV_DENSITY_GRID_OFFSET : mip;
         eff = eff >= VRESTIR_NUM_MAX_MIPS ? eff - VRESTIR_NUM_MAX_MIPS : eff;
@@ -340,7 +340,7 @@ struct AnalyticMarcher : MarchTrav {
 
     VRD void writeOut(float* results) { results[outIdx] = expf(Tr); phase = MARCH_IDLE; }
 
-    VRD void setup(const uint4* q, const MarchKind& kind, const DSlot& g) {
+    VRD void setup(const uint4* q, const MarchKind& kind, const DSlot& g, const float*) {
         const uint4 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2);   // prepared task (vertex-centred box)
         outIdx = c.x;
         Tr = 0.f;
@@ -401,6 +401,86 @@ struct AnalyticMarcher : MarchTrav {
     }
 };
 
+// ---- free-flight distance sampling (SampleMediumAnalyticAdapter with the point sampler and ONE sample,
+// VR/VolumeTrackingAdapterGVDB.slang:210-437): the in-brick phase walks the voxel cells of the brick with a leaf DDA and draws one
+// exponential step per non-empty cell from the task's OWN random-number stream, exactly as the per-pixel traversal does.  Used
+// for the indirect bounces of multi-bounce K1: the task's result slot lies in the pixel's state block (MBK_TRAV: hit distance,
+// pdf, transmittance), the generator is read from and written back to MBK_SG of the same block.
+struct DistanceMarcher : MarchTrav {
+    unsigned outIdx;
+    float3 lSide; int3 lp; float lty;   // leaf DDA
+    float t; int biter;
+    float opticalThickness, hit, outTr, pdf;
+    SampleGenerator sg;
+
+    VRD void writeOut(float* results) {
+        if (hit == -1.f) { hit = kRayTMax; outTr = expf(-opticalThickness); pdf = outTr; }   // ExecuteEndStep
+        results[outIdx] = hit; results[outIdx + 1] = pdf; results[outIdx + 2] = outTr;
+        ((float4*)(results + (outIdx - MBK_TRAV + MBK_SG)))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
+        phase = MARCH_IDLE;
+    }
+    VRD void setup(const uint4* q, const MarchKind& kind, const DSlot& g, const float* results) {
+        const uint4 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2);   // prepared task
+        outIdx = c.x;
+        const float4 g4 = ((const float4*)(results + (outIdx - MBK_TRAV + MBK_SG)))[0];
+        sg.s0 = __float_as_uint(g4.x); sg.s1 = __float_as_uint(g4.y); sg.s2 = __float_as_uint(g4.z); sg.s3 = __float_as_uint(g4.w);
+        opticalThickness = 0.f; hit = -1.f; outTr = 0.f; pdf = 0.f;
+        tNear = __uint_as_float(a.w); tFar = __uint_as_float(b.w);
+        beginPrepared(make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)),
+                      make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), g, false);
+    }
+    VRD void enterBrick(const DSlot& g) {
+        const int4 leaf = __ldg((const int4*)&g.nodes[0][brick]);
+        brick = (uint32_t)leaf.w;
+        const float3 vminLeaf = nodePos(leaf);
+        t = tx - 0.01f;
+        // HDDAState::PrepareLeaf on a copy of the level-1 state
+        const float3 tDelL = make_float3(fabsf(invDir.x), fabsf(invDir.y), fabsf(invDir.z));
+        const float3 pFlt = pos + tx * dir - vminLeaf;
+        const float3 fl = make_float3(floorf(pFlt.x), floorf(pFlt.y), floorf(pFlt.z));
+        const float3 sgn = make_float3(dir.x >= 0 ? 1.f : -1.f, dir.y >= 0 ? 1.f : -1.f, dir.z >= 0 ? 1.f : -1.f);
+        lSide = ((fl - pFlt + f3(0.5f)) * sgn + f3(0.5f)) * tDelL + f3(tx);
+        lp = make_int3((int)fl.x, (int)fl.y, (int)fl.z);
+        biter = 0;
+        phase = MARCH_BRICK;
+    }
+    // one voxel cell of the brick
+    VRD void sampleStep(const DSlot& g, bool) {
+        if (!(biter < MAX_BRICK_STEPS && inRange(lp, 8))) { phase = MARCH_EXIT; return; }
+        // leaf.Next()
+        const bool mx = (lSide.x < lSide.y) & (lSide.x <= lSide.z);
+        const bool my = (lSide.y < lSide.z) & (lSide.y <= lSide.x);
+        const bool mz = (lSide.z < lSide.x) & (lSide.z <= lSide.y);
+        lty = mx ? lSide.x : (my ? lSide.y : lSide.z);
+        const float maxDeltaT = fminf(tFar - t, lty - t);
+        const float currentTMax = fminf(tFar, lty);
+        const float density = DensityInAtlas<true>(g, brick, make_float3((float)lp.x, (float)lp.y, (float)lp.z) + f3(0.5f), false);
+        const float sigma_t = density * c_scene.vol.sigma_t;
+        // an empty cell can never be hit (-log(1-u)/0 is +inf or NaN -> kRayTMax); only the draw counts
+        if (sigma_t == 0.f) (void)sg.next();
+        else {
+            const float dT = -logf(1 - sampleNext1D(sg)) / sigma_t;
+            float curT = t + dT;
+            if (isnan(curT) || isinf(curT)) curT = kRayTMax;
+            if (curT < currentTMax) {
+                hit = curT;
+                outTr = expf(-(dT * sigma_t + opticalThickness));
+                pdf = sigma_t * outTr;
+                phase = MARCH_DONE;
+                return;
+            }
+        }
+        t = currentTMax;
+        opticalThickness += maxDeltaT * sigma_t;
+        if (t >= tFar) { phase = MARCH_DONE; return; }   // ExecuteEndStep in writeOut
+        // leaf.Step()
+        if (mx) { lSide.x += fabsf(invDir.x); lp.x += stepI.x; }
+        if (my) { lSide.y += fabsf(invDir.y); lp.y += stepI.y; }
+        if (mz) { lSide.z += fabsf(invDir.z); lp.z += stepI.z; }
+        biter++;
+    }
+};
+
 // Persistent-lane pool over one task stream.  tasks: 3 (explicit, prepared) or 2 (camera) x uint4 per task; total: tasks in
 // the stream; cursor: next unclaimed.
 // perm (nullable): the order in which the tasks are claimed (bucket order, k_bin_scatter); identity otherwise
@@ -425,7 +505,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
                 base = __shfl_sync(FULL, base, 0);
                 if (m.phase < 2) {
                     const unsigned idx = base + __popc(parked & ltMask);
-                    if (idx < total) m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g);
+                    if (idx < total) m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g, results);
                 }
                 if (base + n >= total) drained = true;
             }

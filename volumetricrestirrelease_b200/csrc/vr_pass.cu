@@ -706,7 +706,7 @@ bool initialWavefrontMBOk(const vrestir_pass* p) {
 int runInitialWavefrontMB(vrestir_pass* p, const FrameParams& fp, cudaStream_t st) {
     const vrestir_params& m = p->P;
     const int B = m.mMaxBounces, M = m.mInitialM;
-    const size_t stateBytes = (size_t)K1MB_STRIDE * 4 + 2 * 48;                               // state block, one light task in each of the two (ping-pong) streams
+    const size_t stateBytes = (size_t)K1MB_STRIDE * 4 + 3 * 48 + 2 * 4;                       // state block, one light task in each of the two (ping-pong) streams, one free-flight task, one entry in each traversal list
     const size_t evalBytes = (size_t)(B + 1) * 48 + (size_t)MB_K1_EVAL_STRIDE * 4;
     size_t maxRows = p->mScratchBudget / ((stateBytes + evalBytes) * (size_t)fp.W);
     maxRows = std::min<size_t>(maxRows, ((size_t)1 << 32) / ((size_t)fp.W * K1MB_STRIDE) - 1);   // 32-bit record indices
@@ -726,24 +726,47 @@ int runInitialWavefrontMB(vrestir_pass* p, const FrameParams& fp, cudaStream_t s
         streams[k].tasks = (uint4*)(state + chunkPixels * K1MB_STRIDE) + (size_t)k * 3 * chunkPixels;
         streams[k].count = p->k1mb.counters + 2 * k; streams[k].cursor = p->k1mb.counters + 2 * k + 1; streams[k].capacity = (unsigned)chunkPixels;
     }
-    static int stepBlocksPerSM = 0;
-    if (!stepBlocksPerSM) stepBlocksPerSM = initialMBStepBlocksPerSM();
+    WfStream travStream;                                                                     // free-flight tasks of the indirect bounces (march engine, point sampler)
+    travStream.tasks = streams[1].tasks + 3 * chunkPixels; travStream.count = p->k1mb.counters + 4; travStream.cursor = p->k1mb.counters + 5; travStream.capacity = (unsigned)chunkPixels;
+    unsigned* const travLists = (unsigned*)(travStream.tasks + 3 * chunkPixels);             // two lists of chunkPixels entries behind the task streams
+    const bool travEngine = !m.mInitialVisibilityUseLinearSampler;
+    int travMip = fp.initial.visibilityMipLevel;                                             // VR/ComputeInitialSample.slang:60-66 (mbBounceMip)
+    if (m.mInitialUseCoarserGridForIndirectBounce) travMip = std::min((travMip >= VRESTIR_NUM_MAX_MIPS ? VRESTIR_NUM_MAX_MIPS : 0) + p->scene.vol.numMips - 1, travMip + 1);
+    const MarchKind kt = {travMip, 0, 1.f, 0, {0.f, 0.f, 0.f}};
+    static int distBlocksPerSM = 0;
+    if (!distBlocksPerSM) distBlocksPerSM = distanceBlocksPerSM();
+    static int stepBlocksPerSM = 0, travBlocksPerSM = 0;
+    if (!stepBlocksPerSM) { stepBlocksPerSM = initialMBStepBlocksPerSM(); travBlocksPerSM = initialMBBounceTraverseBlocksPerSM(); }
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     const int stepBlocks = (int)std::min<size_t>((chunkPixels + 127) / 128, (size_t)sms * stepBlocksPerSM);
+    const int travBlocks = (int)std::min<size_t>((chunkPixels + 127) / 128, (size_t)sms * travBlocksPerSM);
     for (int r0 = fp.rowBegin; r0 < fp.rowEnd; r0 += chunkRows) {
         FrameParams fc = fp;
         fc.rowBegin = r0; fc.rowEnd = std::min(fp.rowEnd, r0 + chunkRows);
-        WfInitialMB wi; wi.state = state; wi.light = streams[0]; wi.prev = streams[1];
-        CK(cudaMemsetAsync(p->k1mb.counters, 0, 16, st));
+        WfInitialMB wi; wi.state = state; wi.light = streams[0]; wi.prev = streams[1]; wi.trav = travStream;
+        unsigned* const travCounts = p->k1mb.counters + 8;
+        int cur = 0;
+        wi.travList = travLists; wi.travCount = travCounts; wi.prevTravList = travLists + chunkPixels; wi.prevTravCount = travCounts + 1;
+        CK(cudaMemsetAsync(p->k1mb.counters, 0, 64, st));
         CK(launchInitialMBTraverse(fc, wi, st));
         CK(launchInitialMBStep(fc, wi, 1, 0, st));
         p->launches += 2;
-        for (int w = 0; w < M * B; w++) {
+        // every wave advances every running pixel to its next suspension: the shadow march of a bounce (<= B per candidate) or the
+        // free-flight traversal of an indirect bounce (<= B - 1 per candidate)
+        for (int w = 0; w < M * (2 * B - 1); w++) {
             CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
             std::swap(wi.light, wi.prev);
+            cur ^= 1;
+            wi.prevTravList = wi.travList; wi.prevTravCount = wi.travCount;
+            wi.travList = travLists + (size_t)cur * chunkPixels; wi.travCount = travCounts + cur;
+            if (travEngine) {
+                CK(launchMarchDistance(wi.trav, wi.state, kt, p->scene.slots[kt.mip], sms * distBlocksPerSM, st));
+                CK(cudaMemsetAsync(wi.trav.count, 0, 8, st));
+            } else CK(launchInitialMBBounceTraverse(fc, wi, travBlocks, st));
             CK(cudaMemsetAsync(wi.light.count, 0, 8, st));
+            CK(cudaMemsetAsync(wi.travCount, 0, 4, st));
             CK(launchInitialMBStep(fc, wi, 0, stepBlocks, st));
-            p->launches += 2;
+            p->launches += 3;
         }
         int rc = runStageGeneric(p, 1, fc, st, &p->k1mbEval, 0, fc.rowEnd - fc.rowBegin); if (rc) return rc;
     }

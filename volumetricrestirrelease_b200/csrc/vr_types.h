@@ -112,9 +112,12 @@ enum { MB_K2_STRIDE = 20, MB_K3_STRIDE = 96, MB_K3_CAM = 80, MB_K5_STRIDE = 8, M
 //   [44,53) extra-bounce records of the final reservoir  [56,65) of the current candidate  [68,86) the bounce waiting for its
 //   shadow march  [95] the marched visibility.  After the first wave the kernels iterate over the previous wave's task list
 //   instead of the pixel grid, so warps stay full while most pixels have already finished.
-enum { MBK_SG = 0, MBK_HD = 4, MBK_FIN = 16, MBK_COMB = 24, MBK_PATH = 32, MBK_CUR = 41, MBK_FINX = 44, MBK_EXTRA = 56, MBK_PEND = 68, MBK_VIS = 95, K1MB_STRIDE = 96 };
+enum { MBK_SG = 0, MBK_HD = 4, MBK_FIN = 16, MBK_COMB = 24, MBK_PATH = 32, MBK_CUR = 41, MBK_KIND = 43, MBK_FINX = 44, MBK_EXTRA = 56, MBK_PEND = 68, MBK_TRAV = 86,
+       MBK_VIS = 95, K1MB_STRIDE = 96 };   // KIND: what the pixel waits for (0 shadow march, 1 bounce traversal); TRAV: hit distance / pdf / transmittance of that traversal
 // light: the stream this wave's shadow marches go to; prev: the stream of the previous wave, whose task list doubles as the
 // compacted list of the pixels that are still running (every pixel that emitted a march continues in the next wave)
-struct WfInitialMB { WfStream light, prev; float* state; };
+// travList / travCount: the pixels (band-local indices) this wave leaves waiting for a bounce traversal; prevTrav*: the previous wave's
+// trav: the prepared free-flight tasks of those pixels for the march engine (point sampler; unused with the trilinear one)
+struct WfInitialMB { WfStream light, prev, trav; float* state; unsigned* travList; unsigned* travCount; const unsigned* prevTravList; const unsigned* prevTravCount; };
 
 }  // namespace vrd

@@ -967,15 +967,19 @@ VRD Reservoir mbLoadRes(const float* r) {
 #endif
 // One pixel advances to its next shadow march (or finishes).  first: the wave after k_initial_mb_traverse (the state block holds
 // the RNG and the distance candidates only).  Returns whether a march was emitted (`shadow`), i.e. whether the pixel goes on.
+// Suspension points: the shadow march of a bounce's light sample (march engine) and the free-flight sampling of an indirect
+// bounce (k_initial_mb_bounce_traverse) — with that traversal inline the step kernel ran it at 3-4 lanes per instruction
+// and missed the instruction cache (profiles/r02_ncu_full_k_initial_mb_step.txt).  Returns 0: finished, 1: shadow march
+// emitted (`shadow`), 2: waiting for its bounce traversal.
 template <int B>
-__device__ __forceinline__ bool mbAdvancePixel(const FrameParams& fp, const WfInitialMB& wi, bool first, bool active, int x, int y, unsigned local, Ray& shadow) {
+__device__ __forceinline__ int mbAdvancePixel(const FrameParams& fp, const WfInitialMB& wi, bool first, bool active, int x, int y, unsigned local, Ray& shadow) {
     const int pixelId = fp.rowBegin * fp.W + (int)local;
     const unsigned recBase = local * K1MB_STRIDE;
     float* st = wi.state + recBase;
     const SamplingOptions& options = fp.initial;
     const vrestir_volume_desc& vd = c_scene.vol;
     const int M = fp.initialM;
-    bool hasTask = false;
+    bool hasTask = false, waitTrav = false;
     if (active) {
         const float3 sigA = v3(vd.sigma_a), sigS = v3(vd.sigma_s);
         const Ray primary = primaryRay(fp, x, y);
@@ -1001,7 +1005,8 @@ __device__ __forceinline__ bool mbAdvancePixel(const FrameParams& fp, const WfIn
                 finalExtra[i] = f3(st[MBK_FINX + 3 * i], st[MBK_FINX + 3 * i + 1], st[MBK_FINX + 3 * i + 2]);
             }
         }
-        bool resume = !first;
+        bool resume = !first && __float_as_int(st[MBK_KIND]) == 0;      // after a shadow march
+        bool resumeTrav = !first && !resume;                             // after a bounce traversal
         bool finished = false;
         MBPend c;
         for (int guard = 0; guard < 4 * B + 8 && !finished; guard++) {
@@ -1013,11 +1018,10 @@ __device__ __forceinline__ bool mbAdvancePixel(const FrameParams& fp, const WfIn
                 float curHitDist, pdfDist = 0.f, Tr;
                 MediumInteraction mi;
                 if (bounce >= 1) {
-                    int curMip = options.visibilityMipLevel;
-                    if (fp.useCoarserGrid) curMip = min((options.visibilityMipLevel >= VRESTIR_NUM_MAX_MIPS ? VRESTIR_NUM_MAX_MIPS : 0) + vd.numMips - 1, curMip + 1);
-                    float hd[4], pd[4], ot[4];
-                    SampleMediumAnalyticGeneric(ray, sg, options.visibilityUseLinearSampler, hd, curMip, pd, ot, 1);
-                    curHitDist = hd[0]; pdfDist = pd[0]; Tr = ot[0];
+                    // SampleMediumAnalyticGeneric(ray, sg, ..., 1 sample) runs in k_initial_mb_bounce_traverse on the stored ray and RNG state
+                    if (!resumeTrav) { waitTrav = true; shadow = ray; break; }
+                    resumeTrav = false;
+                    curHitDist = st[MBK_TRAV]; pdfDist = st[MBK_TRAV + 1]; Tr = st[MBK_TRAV + 2];
                 } else {
                     curHitDist = st[MBK_HD + s]; pdfDist = st[MBK_HD + 4 + s]; Tr = st[MBK_HD + 8 + s];
                 }
@@ -1165,16 +1169,41 @@ __device__ __forceinline__ bool mbAdvancePixel(const FrameParams& fp, const WfIn
             st[MBK_PATH] = ray.origin.x; st[MBK_PATH + 1] = ray.origin.y; st[MBK_PATH + 2] = ray.origin.z;
             st[MBK_PATH + 3] = ray.dir.x; st[MBK_PATH + 4] = ray.dir.y; st[MBK_PATH + 5] = ray.dir.z;
             st[MBK_PATH + 6] = pathPdf; st[MBK_PATH + 7] = pathPHat; st[MBK_PATH + 8] = primaryScatterDepth;
-            st[MBK_CUR] = __int_as_float(s); st[MBK_CUR + 1] = __int_as_float(bounce);
+            st[MBK_CUR] = __int_as_float(s); st[MBK_CUR + 1] = __int_as_float(bounce); st[MBK_KIND] = __int_as_float(waitTrav ? 1 : 0);
 #pragma unroll
             for (int i = 0; i < B - 1; i++) {
                 st[MBK_EXTRA + 3 * i] = extra[i].x; st[MBK_EXTRA + 3 * i + 1] = extra[i].y; st[MBK_EXTRA + 3 * i + 2] = extra[i].z;
                 st[MBK_FINX + 3 * i] = finalExtra[i].x; st[MBK_FINX + 3 * i + 1] = finalExtra[i].y; st[MBK_FINX + 3 * i + 2] = finalExtra[i].z;
             }
-            mbStorePend(st + MBK_PEND, c);
+            if (!waitTrav) mbStorePend(st + MBK_PEND, c);
         }
     }
-    return hasTask;
+    return hasTask ? 1 : (waitTrav ? 2 : 0);
+}
+// the mip an indirect bounce samples its free-flight distance on (VR/ComputeInitialSample.slang:60-66)
+VRD int mbBounceMip(const FrameParams& fp) {
+    int curMip = fp.initial.visibilityMipLevel;
+    if (fp.useCoarserGrid) curMip = min((fp.initial.visibilityMipLevel >= VRESTIR_NUM_MAX_MIPS ? VRESTIR_NUM_MAX_MIPS : 0) + c_scene.vol.numMips - 1, curMip + 1);
+    return curMip;
+}
+// append the pixels waiting for a bounce traversal to the wave's list (one atomic per warp; every lane of the warp calls)
+VRD void mbEmitTrav(const WfInitialMB& wi, bool want, unsigned local) {
+    const unsigned bal = __ballot_sync(0xffffffffu, want);
+    if (!bal) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(wi.travCount, (unsigned)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (want) wi.travList[base + __popc(bal & ((1u << lane) - 1u))] = local;
+}
+// A pixel that waits for its bounce traversal: entry in the wave's list (the next step walks it) and, with the point sampler, the
+// free-flight sampling as a prepared task of the march engine (DistanceMarcher; a ray that misses the volume box is final here:
+// hit distance kRayTMax, pdf 1, transmittance 1 — SampleMediumAnalyticAdapter::ExecuteEndStep before ExecuteStartStep)
+VRD void mbEmitWaiting(const FrameParams& fp, const WfInitialMB& wi, bool want, unsigned local, const Ray& bounceRay) {
+    mbEmitTrav(wi, want, local);
+    if (fp.initial.visibilityUseLinearSampler) return;   // k_initial_mb_bounce_traverse walks the list instead
+    if (want) { wi.state[local * K1MB_STRIDE + MBK_TRAV + 1] = 1.f; wi.state[local * K1MB_STRIDE + MBK_TRAV + 2] = 1.f; }
+    wfEmitRay(wi.trav, want, bounceRay, mbBounceMip(fp), false, wi.state, local * K1MB_STRIDE + MBK_TRAV, kRayTMax);
 }
 // first != 0: one thread per pixel of the band (8x4 tiles); afterwards: grid-stride over the previous wave's task list
 template <int B>
@@ -1184,20 +1213,48 @@ __global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FramePa
         const bool inFrame = pixelOf(fp, x, y);
         const unsigned local = inFrame ? (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) : 0u;
         Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
-        const bool hasTask = mbAdvancePixel<B>(fp, wi, true, inFrame, x, y, local, shadow);
-        wfEmitRay(wi.light, hasTask, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
+        const int r = mbAdvancePixel<B>(fp, wi, true, inFrame, x, y, local, shadow);
+        wfEmitRay(wi.light, r == 1, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
+        mbEmitWaiting(fp, wi, r == 2, local, shadow);
         return;
     }
-    const unsigned total = min(*wi.prev.count, wi.prev.capacity);
-    for (unsigned t0 = blockIdx.x * blockDim.x; t0 < total; t0 += gridDim.x * blockDim.x) {   // block-uniform trip count: wfEmitRay is warp-collective
+    // the pixels still running = the previous wave's march tasks + its traversal list
+    const unsigned nMarch = min(*wi.prev.count, wi.prev.capacity), total = nMarch + *wi.prevTravCount;
+    for (unsigned t0 = blockIdx.x * blockDim.x; t0 < total; t0 += gridDim.x * blockDim.x) {   // block-uniform trip count: the emits are warp-collective
         const unsigned t = t0 + threadIdx.x;
         const bool active = t < total;
         unsigned local = 0;
-        if (active) local = __ldg(&wi.prev.tasks[3 * (size_t)t + 2]).x / K1MB_STRIDE;   // the task's result slot identifies its pixel
+        if (active) local = t < nMarch ? __ldg(&wi.prev.tasks[3 * (size_t)t + 2]).x / K1MB_STRIDE   // the task's result slot identifies its pixel
+                                       : __ldg(&wi.prevTravList[t - nMarch]);
         const int pixelId = fp.rowBegin * fp.W + (int)local;
         Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
-        const bool hasTask = mbAdvancePixel<B>(fp, wi, false, active, pixelId % fp.W, pixelId / fp.W, local, shadow);
-        wfEmitRay(wi.light, hasTask, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
+        const int r = mbAdvancePixel<B>(fp, wi, false, active, pixelId % fp.W, pixelId / fp.W, local, shadow);
+        wfEmitRay(wi.light, r == 1, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
+        mbEmitWaiting(fp, wi, r == 2, local, shadow);
+    }
+}
+
+// the engine form of the same (point sampler): one DistanceMarcher task per waiting pixel
+__global__ void __launch_bounds__(128, VR_ANALYTIC_MINB) k_march_distance(const WfStream s, float* state, const MarchKind kind, const DSlot g) {
+    marchPool<DistanceMarcher>(s.tasks, min(*s.count, s.capacity), s.cursor, state, kind, g);
+}
+
+// Free-flight sampling of one indirect bounce per listed pixel (VR/ComputeInitialSample.slang:60-72: one analytic-tracking sample
+// along the scattered ray on the visibility mip or its coarser neighbour), with the pixel's own RNG stream: ray and generator
+// come from the state block, hit distance / pdf / transmittance and the advanced generator go back into it.
+__global__ void __launch_bounds__(128, VR_TRAV_MINB) k_initial_mb_bounce_traverse(FrameParams fp, WfInitialMB wi) {
+    const unsigned total = *wi.prevTravCount;
+    const SamplingOptions& options = fp.initial;
+    const int curMip = mbBounceMip(fp);
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        float* st = wi.state + (size_t)__ldg(&wi.prevTravList[t]) * K1MB_STRIDE;
+        SampleGenerator sg;
+        { const float4 g4 = ((const float4*)(st + MBK_SG))[0]; sg.s0 = __float_as_uint(g4.x); sg.s1 = __float_as_uint(g4.y); sg.s2 = __float_as_uint(g4.z); sg.s3 = __float_as_uint(g4.w); }
+        const Ray ray = makeRay(f3(st[MBK_PATH], st[MBK_PATH + 1], st[MBK_PATH + 2]), f3(st[MBK_PATH + 3], st[MBK_PATH + 4], st[MBK_PATH + 5]), 0, kRayTMax);
+        float hd[4], pd[4], ot[4];
+        SampleMediumAnalyticGeneric(ray, sg, options.visibilityUseLinearSampler, hd, curMip, pd, ot, 1);
+        st[MBK_TRAV] = hd[0]; st[MBK_TRAV + 1] = pd[0]; st[MBK_TRAV + 2] = ot[0];
+        ((float4*)(st + MBK_SG))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
     }
 }
 
@@ -1312,6 +1369,12 @@ cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaSt
         default: kern<4><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                     \
     }
 cudaError_t launchInitialMBTraverse(const FrameParams& fp, const WfInitialMB& wi, cudaStream_t st) { k_initial_mb_traverse<<<gridForWf(fp), 128, 0, st>>>(fp, wi); return cudaGetLastError(); }
+int distanceBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march_distance, 128, 0); return n > 0 ? n : 1; }
+cudaError_t launchMarchDistance(const WfStream& s, float* state, const MarchKind& kind, const DSlot& grid, int blocks, cudaStream_t st) { k_march_distance<<<blocks, 128, 0, st>>>(s, state, kind, grid); return cudaGetLastError(); }
+int initialMBBounceTraverseBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_initial_mb_bounce_traverse, 128, 0); return n > 0 ? n : 1; }
+cudaError_t launchInitialMBBounceTraverse(const FrameParams& fp, const WfInitialMB& wi, int blocks, cudaStream_t st) {
+    k_initial_mb_bounce_traverse<<<blocks, 128, 0, st>>>(fp, wi); return cudaGetLastError();
+}
 int initialMBStepBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_initial_mb_step<4>, 128, 0); return n > 0 ? n : 1; }
 // first: one thread per pixel of the band; afterwards `blocks` CTAs stride over the previous wave's task list
 cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, int blocks, cudaStream_t st) {
