@@ -753,6 +753,7 @@ int runInitialWavefrontMB(vrestir_pass* p, const FrameParams& fp, cudaStream_t s
         p->launches += 2;
         // every wave advances every running pixel to its next suspension: the shadow march of a bounce (<= B per candidate) or the
         // free-flight traversal of an indirect bounce (<= B - 1 per candidate)
+        // (running the two marches of a wave on two streams was measured: 143.1 -> 142.3 ms, either one fills the GPU — kept serial)
         for (int w = 0; w < M * (2 * B - 1); w++) {
             CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
             std::swap(wi.light, wi.prev);

@@ -972,7 +972,7 @@ VRD Reservoir mbLoadRes(const float* r) {
 // and missed the instruction cache (profiles/r02_ncu_full_k_initial_mb_step.txt).  Returns 0: finished, 1: shadow march
 // emitted (`shadow`), 2: waiting for its bounce traversal.
 template <int B>
-__device__ __forceinline__ int mbAdvancePixel(const FrameParams& fp, const WfInitialMB& wi, bool first, bool active, int x, int y, unsigned local, Ray& shadow) {
+__device__ __forceinline__ int mbAdvancePixel(const FrameParams& fp, const WfInitialMB& wi, bool first, bool active, int x, int y, unsigned local, Ray& shadow, const float* impTop) {
     const int pixelId = fp.rowBegin * fp.W + (int)local;
     const unsigned recBase = local * K1MB_STRIDE;
     float* st = wi.state + recBase;
@@ -1042,7 +1042,7 @@ __device__ __forceinline__ int mbAdvancePixel(const FrameParams& fp, const WfIni
                     c.lightID = -1;
                     if (vd.hasEmission && c.density > 0.f) c.Le = EmissionWorldSpace(mi.p);
                     SceneLightSample ls;
-                    const bool lvalid = sampleSceneLights(mi.p, options.useEnvironmentLights, options.useAnalyticLights, options.useEmissiveLights, sg, ls, c.lightID, c.lightUV);
+                    const bool lvalid = sampleSceneLights(mi.p, options.useEnvironmentLights, options.useAnalyticLights, options.useEmissiveLights, sg, ls, c.lightID, c.lightUV, impTop);
                     c.outLightPdf = lvalid ? ls.pdfArea : 0.f;
                     if (lvalid) {
                         c.flags |= 2u;
@@ -1208,12 +1208,19 @@ VRD void mbEmitWaiting(const FrameParams& fp, const WfInitialMB& wi, bool want, 
 // first != 0: one thread per pixel of the band (8x4 tiles); afterwards: grid-stride over the previous wave's task list
 template <int B>
 __global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FrameParams fp, WfInitialMB wi, int first) {
+    // top levels of the importance map in shared memory (one bulk copy per CTA): the hierarchical descent of every env-light sample
+    // starts with IMP_TOP levels of dependent loads that otherwise each wait for L2
+    __shared__ __align__(16) float impTopS[IMP_TOP_BYTES / 4];
+    __shared__ uint64_t impBar;
+    const bool stageImp = fp.initial.useEnvironmentLights && c_scene.haveEnv && c_scene.envSamplerType != VRESTIR_ENV_SAMPLER_ALIAS && c_scene.impDim >= IMP_TOP_DIM;
+    if (stageImp) stageImportanceTop(impTopS, &impBar);
+    const float* impTop = stageImp ? impTopS : nullptr;
     if (first) {
         int x, y;
         const bool inFrame = pixelOf(fp, x, y);
         const unsigned local = inFrame ? (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) : 0u;
         Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
-        const int r = mbAdvancePixel<B>(fp, wi, true, inFrame, x, y, local, shadow);
+        const int r = mbAdvancePixel<B>(fp, wi, true, inFrame, x, y, local, shadow, impTop);
         wfEmitRay(wi.light, r == 1, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
         mbEmitWaiting(fp, wi, r == 2, local, shadow);
         return;
@@ -1228,7 +1235,7 @@ __global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FramePa
                                        : __ldg(&wi.prevTravList[t - nMarch]);
         const int pixelId = fp.rowBegin * fp.W + (int)local;
         Ray shadow = makeRay(f3(0.f), f3(0.f, 0.f, 1.f), 0.f, 0.f);
-        const int r = mbAdvancePixel<B>(fp, wi, false, active, pixelId % fp.W, pixelId / fp.W, local, shadow);
+        const int r = mbAdvancePixel<B>(fp, wi, false, active, pixelId % fp.W, pixelId / fp.W, local, shadow, impTop);
         wfEmitRay(wi.light, r == 1, shadow, fp.initial.lightingMipLevel, false, wi.state, local * K1MB_STRIDE + MBK_VIS);
         mbEmitWaiting(fp, wi, r == 2, local, shadow);
     }
