@@ -376,11 +376,62 @@ int runStageGeneric(vrestir_pass* p, int stage, const FrameParams& fp, cudaStrea
     return VRESTIR_OK;
 }
 
+// Device blocks of the grid slots come from a per-device cache: an animated sequence that uploads a new volume every frame
+// (vrestir_advance_volume, vrestir_set_volume_from_chain) releases and requests ~100 blocks of nearly the same sizes per frame,
+// and cudaMalloc / cudaFree (a device-wide synchronisation each) cost more than the copies.  A released block is handed out
+// again for a request of up to its capacity and at least 3/4 of it.  Callers synchronise the device before releasing blocks
+// that in-flight work may still read (they did so before their cudaFree, too).
+struct SlotBlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free;      // capacity -> block
+    std::map<void*, size_t> capacity;       // every live or cached block handed out by slotAlloc
+    size_t cachedBytes = 0;
+};
+std::map<int, std::unique_ptr<SlotBlockCache>> g_slotCaches;
+std::mutex g_slotCachesMu;
+constexpr size_t kSlotCacheLimit = (size_t)4 << 30;
+SlotBlockCache& slotCache() {
+    int dev = 0; cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_slotCachesMu);
+    auto& c = g_slotCaches[dev];
+    if (!c) c.reset(new SlotBlockCache());
+    return *c;
+}
+cudaError_t slotAlloc(void** out, size_t bytes) {
+    SlotBlockCache& c = slotCache();
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        auto it = c.free.lower_bound(bytes);
+        if (it != c.free.end() && it->first - bytes <= it->first / 4) {
+            *out = it->second; c.cachedBytes -= it->first; c.free.erase(it);
+            return cudaSuccess;
+        }
+    }
+    const cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lock(c.mu); c.capacity[*out] = bytes; }
+    return e;
+}
+void slotRelease(void* ptr) {
+    if (!ptr) return;
+    SlotBlockCache& c = slotCache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.capacity.find(ptr);
+    if (it == c.capacity.end()) { cudaFree(ptr); return; }
+    if (c.cachedBytes + it->second > kSlotCacheLimit) { c.capacity.erase(it); cudaFree(ptr); return; }
+    c.free.emplace(it->second, ptr); c.cachedBytes += it->second;
+}
+void slotCacheTrim() {   // vrestir_destroy: cached blocks go back to the driver
+    SlotBlockCache& c = slotCache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (auto& kv : c.free) { c.capacity.erase(kv.second); cudaFree(kv.second); }
+    c.free.clear(); c.cachedBytes = 0;
+}
+
 void freeSlot(DevSlot& d) {
     if (!d.borrowed) {
-        for (int l = 0; l < 3; l++) { if (d.nodes[l]) cudaFree(d.nodes[l]); if (d.child[l]) cudaFree(d.child[l]); }
-        if (d.atlas) cudaFree(d.atlas);
-        if (d.quads) cudaFree(d.quads);
+        for (int l = 0; l < 3; l++) { slotRelease(d.nodes[l]); slotRelease(d.child[l]); }
+        slotRelease(d.atlas);
+        slotRelease(d.quads);
     }
     d = DevSlot{};
 }
@@ -395,11 +446,11 @@ int uploadSlotTo(DevSlot& d, DSlot& s, const vrestir_grid_slot& g) {
     for (int l = 0; l < 3; l++) {
         s.dim[l] = g.dim[l]; s.res[l] = g.res[l]; s.vdel[l] = g.vdel[l];
         if (g.node_count[l] && g.nodes[l]) {
-            CK(cudaMalloc(&d.nodes[l], (size_t)g.node_count[l] * sizeof(vrestir_node)));
+            CK(slotAlloc(&d.nodes[l], (size_t)g.node_count[l] * sizeof(vrestir_node)));
             CK(cudaMemcpy(d.nodes[l], g.nodes[l], (size_t)g.node_count[l] * sizeof(vrestir_node), cudaMemcpyHostToDevice));
         }
         if (g.childlist_count[l] && g.childlist[l]) {
-            CK(cudaMalloc(&d.child[l], (size_t)g.childlist_count[l] * 4));
+            CK(slotAlloc(&d.child[l], (size_t)g.childlist_count[l] * 4));
             CK(cudaMemcpy(d.child[l], g.childlist[l], (size_t)g.childlist_count[l] * 4, cudaMemcpyHostToDevice));
         }
         if (g.childlist_count[l] >= (1ull << 31)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "child list too large");
@@ -416,7 +467,7 @@ int uploadSlotTo(DevSlot& d, DSlot& s, const vrestir_grid_slot& g) {
     s.max_value = g.max_value; s.compress_scale = g.compress_scale; s.format = g.atlas_format; s.channels = g.atlas_channels;
     const size_t bytes = (size_t)g.brick_count * g.atlas_channels * VRESTIR_BRICK_VOXELS * (g.atlas_format == VRESTIR_ATLAS_UNORM8 ? 1 : 4);
     if (bytes) {
-        CK(cudaMalloc(&d.atlas, bytes + 16));
+        CK(slotAlloc(&d.atlas, bytes + 16));
         if (g.atlas) CK(cudaMemcpy(d.atlas, g.atlas, bytes, cudaMemcpyHostToDevice));   // NULL: the caller fills the pool on the device
         d.atlasBytes = bytes;
     }
@@ -428,7 +479,7 @@ int uploadSlotTo(DevSlot& d, DSlot& s, const vrestir_grid_slot& g) {
     if (bytes && g.atlas && g.atlas_format == VRESTIR_ATLAS_UNORM8 && g.atlas_channels == 1) {
         // device-only repack for trilinear fetches: per brick [10][9][9] words, word(z,y,x) = codes (x,y) (x+1,y) (x,y+1) (x+1,y+1) of plane z
         d.quadBytes = (size_t)g.brick_count * 810 * 4;
-        CK(cudaMalloc(&d.quads, d.quadBytes));
+        CK(slotAlloc(&d.quads, d.quadBytes));
         CK(vr::launchQuadRepack((const uint8_t*)d.atlas, g.brick_count, (uint32_t*)d.quads, 0));
         s.quads = (const uint32_t*)d.quads;
     }
@@ -1134,6 +1185,7 @@ int vrestir_destroy(vrestir_pass* p) try {
     if (p->evMainTail) cudaEventDestroy(p->evMainTail);
     for (auto& d : p->dslots) freeSlot(d);
     for (auto& fr : p->volumeFrames) for (auto& d : fr->d) freeSlot(d);
+    slotCacheTrim();
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
     for (int i = 0; i < 4; i++) if (p->ext[i]) cudaFree(p->ext[i]);
     for (int i = 0; i < 3; i++) if (p->feat[i]) cudaFree(p->feat[i]);
@@ -1304,7 +1356,7 @@ int vrestir_set_volume_from_chain(vrestir_pass* p, const vrestir_mip_chain* chai
         CK(vr::launchBrickBounds(d.atlas, lv.format, lv.maxValue, (vrestir_node*)d.nodes[0], topo.brickCount, 0));
         if (lv.format == VRESTIR_ATLAS_UNORM8) {
             d.quadBytes = (size_t)topo.brickCount * 810 * 4;
-            CK(cudaMalloc(&d.quads, d.quadBytes));
+            CK(slotAlloc(&d.quads, d.quadBytes));
             CK(vr::launchQuadRepack((const uint8_t*)d.atlas, topo.brickCount, (uint32_t*)d.quads, 0));
             p->scene.slots[s].quads = (const uint32_t*)d.quads;
         }
