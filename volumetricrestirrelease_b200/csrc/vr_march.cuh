@@ -329,6 +329,93 @@ struct RayMarcher : MarchTrav {
     }
 };
 
+// ---- the same marcher with the traversal DECOUPLED from the sampling (marchPoolQ).  In the reference's loop a ray alternates
+// "find the next brick" and "sample it"; the lanes of a warp drift apart and the vote of marchPool leaves the minority phase
+// idle (13-15 of 32 lanes per instruction, ncu).  Nothing in the sampling feeds back into the traversal except "stop": the brick
+// sequence of a ray and the DDA time at which each brick is entered depend on the ray alone.  So every lane keeps a small FIFO of
+// (leaf node, entry time) in shared memory: its traversal runs ahead and pushes, its sampler pops and accumulates in the same
+// order (same partial sums).  Most busy lanes can then take part in EITHER phase, whichever the warp runs.
+#ifndef VR_QUEUE_DEPTH
+#define VR_QUEUE_DEPTH 8
+#endif
+// phase choice: 0 = every round the phase more lanes can take part in; k > 0 = hysteresis, a phase is kept until fewer than k/8 of
+// the busy lanes can take part.  Measured: hysteresis is slower for every k, so are weighted votes and popping the next brick in
+// the middle of a sampling round (profiles/r02_queue_engine.txt)
+#ifndef VR_QUEUE_KEEP
+#define VR_QUEUE_KEEP 0
+#endif
+template <int NT, bool FAST>
+struct RayMarcherQ : RayMarcher<NT, FAST> {
+    using Base = RayMarcher<NT, FAST>;
+    uint32_t cbrick;        // brick being sampled
+    unsigned qh, qt;        // FIFO read / write counters
+    bool live, inBrick, cdone;
+
+    // MarchTrav::travStep with the adapter call replaced by a push; the tail of the outer iteration (exitBrick) follows at once
+    VRD void travStepQ(const DSlot& g, uint2* q) {
+        if (!(this->iter < 4096 && inRange(this->p, g.res[1] + 1))) { this->phase = MARCH_DONE; return; }
+        this->iter++;
+        this->next();
+#if VR_PREFETCH_CHILD
+        const uint32_t child = this->brick;
+#else
+        const uint32_t child = this->childOf(g);
+#endif
+        if (child != ID_UNDEFL) { q[(qt % VR_QUEUE_DEPTH) * 128] = make_uint2(child, __float_as_uint(this->tx)); qt++; }
+        this->step();
+        if (this->tx > this->tMax1) this->phase = MARCH_ASCEND; else this->fetchChild(g);
+    }
+    // prologue of MediumTrRayMarchingAdapter::ExecuteMainStep for the oldest queued brick
+    VRD void enterBrickQ(const DSlot& g, const uint2* q) {
+        const uint2 e = q[(qh % VR_QUEUE_DEPTH) * 128]; qh++;
+        const int4 leaf = __ldg((const int4*)&g.nodes[0][e.x]);
+        cbrick = (uint32_t)leaf.w;
+        const float txe = __uint_as_float(e.y);
+        float tt = txe - 0.01f;
+        tt = this->tNear + (floorf((tt - this->tNear) / this->tStep) + 0.5f) * this->tStep;
+        if (tt < txe) tt += this->tStep;
+        this->t = tt;
+        const float3 wp = this->pos + tt * this->dir;
+        this->pb = wp - nodePos(leaf);
+        this->biter = 0;
+        inBrick = true;
+    }
+    VRD float sampleFastQ(const DSlot& g) {   // RayMarcher::sampleFast on cbrick
+        int ix, iy, iz;
+        const float qx = this->pb.x - 0.5f, qy = this->pb.y - 0.5f, qz = this->pb.z - 0.5f;
+        const float fx0 = fastFloor(qx, ix), fy0 = fastFloor(qy, iy), fz0 = fastFloor(qz, iz);
+        const float fx = qx - fx0, fy = qy - fy0, fz = qz - fz0;
+        const uint32_t* q = g.quads + (cbrick * 810u + (unsigned)(((iz + 1) * 9 + (iy + 1)) * 9 + (ix + 1)));
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 81);
+        const float m000 = byteToMagic(w0, 0), m100 = byteToMagic(w0, 1), m010 = byteToMagic(w0, 2), m110 = byteToMagic(w0, 3);
+        const float m001 = byteToMagic(w1, 0), m101 = byteToMagic(w1, 1), m011 = byteToMagic(w1, 2), m111 = byteToMagic(w1, 3);
+        const float c00 = __fmaf_rn(fx, m100 - m000, m000 - 8388608.f), c10 = __fmaf_rn(fx, m110 - m010, m010 - 8388608.f);
+        const float c01 = __fmaf_rn(fx, m101 - m001, m001 - 8388608.f), c11 = __fmaf_rn(fx, m111 - m011, m011 - 8388608.f);
+        const float c0 = lerpf(c00, c10, fy), c1 = lerpf(c01, c11, fy);
+        return lerpf(c0, c1, fz) * kUnorm8;
+    }
+    VRD void sampleStepQ(const DSlot& g, bool linear) {
+        const float res = 8.f;
+        if (!(this->biter < MAX_BRICK_STEPS && this->pb.x >= 0 && this->pb.y >= 0 && this->pb.z >= 0 && this->pb.x < res && this->pb.y < res && this->pb.z < res)) {
+            inBrick = false;
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < NT; k++)
+            if ((this->pending >> k) & 1u) { if (this->t >= this->thrEff[k]) { this->out[k] = this->Tr; this->pending &= ~(1u << k); } }
+        if (!this->pending || this->Tr < -110.f) { cdone = true; inBrick = false; return; }
+        float density;
+        if (FAST) density = sampleFastQ(g) * g.compress_scale * c_scene.vol.densityScaleFactorByScaling;
+        else density = DensityInAtlas<false>(g, cbrick, this->pb, linear);
+        const float sigma_t = density * c_scene.vol.sigma_t;
+        this->Tr += -sigma_t * 1.f * this->tStep;
+        const float3 wpt = 1.f * this->tStep * this->dir;
+        this->pb = this->pb + wpt;
+        this->t += 1.f * this->tStep;
+        this->biter++;
+    }
+};
+
 // ---- exact transmittance of the trilinear interpolant (MediumTrAnalyticAdapter with the linear sampler,
 // VR/VolumeTrackingAdapterGVDB.slang:20-136; vertex-centred traversal): the in-brick phase walks the 8^3 voxel cells of the
 // brick with a leaf DDA and integrates the cubic sigma(t) of every cell in closed form.  One explicit-origin task, one result.
@@ -529,6 +616,74 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
             if (m.phase == MARCH_ENTER) m.enterBrick(g);
 #pragma unroll 1
             for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.phase == MARCH_BRICK) m.sampleStep(g, linear);
+        }
+    }
+}
+
+
+// Pool of 32 persistent lanes over one task stream for RayMarcherQ (see there).  q: VR_QUEUE_DEPTH x 128 entries of shared memory
+// per CTA, [slot][thread].
+template <int NT, bool FAST>
+__device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g,
+                                           const unsigned* __restrict__ perm, uint2* qBase) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const bool linear = kind.linear != 0;
+    uint2* const q = qBase + threadIdx.x;
+    RayMarcherQ<NT, FAST> m;
+    m.phase = MARCH_IDLE; m.live = false; m.inBrick = false; m.cdone = false; m.qh = m.qt = 0;
+    bool drained = false;
+    bool sampling = false;   // warp-uniform: the phase the pool is in (hysteresis: it stays until fewer than VR_QUEUE_KEEP / 8 of the busy lanes can take part)
+    for (;;) {
+        // finished: the sampler stopped (thresholds passed / transmittance underflowed) or the traversal ended and everything queued is sampled
+        bool fin = m.live && (m.cdone || (m.phase == MARCH_DONE && !m.inBrick && m.qh == m.qt));
+        unsigned parked = __ballot_sync(FULL, !m.live || fin);
+        if (__popc(parked) >= VR_REFILL_MIN) {
+            if (fin) { m.writeOut(results); m.live = false; fin = false; }
+            if (!drained) {
+                const unsigned n = __popc(parked);
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(cursor, n);
+                base = __shfl_sync(FULL, base, 0);
+                if (!m.live) {
+                    const unsigned idx = base + __popc(parked & ltMask);
+                    if (idx < total) {
+                        m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g, results);
+                        m.live = true; m.inBrick = false; m.cdone = false; m.qh = m.qt = 0;
+                    }
+                }
+                if (base + n >= total) drained = true;
+            }
+            fin = m.live && (m.cdone || (m.phase == MARCH_DONE && !m.inBrick && m.qh == m.qt));   // box misses of this refill
+            parked = __ballot_sync(FULL, !m.live || fin);
+            if (parked == FULL) {
+                if (__ballot_sync(FULL, fin)) continue;
+                if (drained) break;
+                continue;
+            }
+        }
+        const bool canS = m.live && !fin && (m.inBrick || m.qh != m.qt);
+        const bool canT = m.live && !fin && m.phase == MARCH_TRAV && (m.qt - m.qh) < (unsigned)VR_QUEUE_DEPTH;
+        const bool canK = m.live && !fin && (m.phase == MARCH_ASCEND || m.phase == MARCH_ROOT);
+        const int nT = __popc(__ballot_sync(FULL, canT)), nS = __popc(__ballot_sync(FULL, canS)), nK = __popc(__ballot_sync(FULL, canK));
+#if VR_QUEUE_KEEP == 0
+        sampling = nT < nS;   // the phase more lanes can take part in
+#else
+        const int nBusy = 32 - __popc(parked);
+        if (sampling) { if (8 * nS < VR_QUEUE_KEEP * nBusy && nT > nS) sampling = false; }
+        else if (8 * nT < VR_QUEUE_KEEP * nBusy && nS > nT) sampling = true;
+#endif
+        if (nK && VR_SLOW_WEIGHT * nK >= max(nT, nS)) {
+            if (canK) m.slowStep(g);
+        } else if (!sampling) {
+#pragma unroll 1
+            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++)
+                if (m.live && !fin && m.phase == MARCH_TRAV && (m.qt - m.qh) < (unsigned)VR_QUEUE_DEPTH) m.travStepQ(g, q);
+        } else {
+            if (canS && !m.inBrick) m.enterBrickQ(g, q);
+#pragma unroll 1
+            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.inBrick) m.sampleStepQ(g, linear);
         }
     }
 }

@@ -24,9 +24,17 @@
 namespace vrd {
 
 // ------------------------------------------------------------------------------------------------ march kernels
+#ifndef VR_QUEUE_ENGINE
+#define VR_QUEUE_ENGINE 1
+#endif
 template <int NT, bool FAST>
 __global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march(const WfStream s, float* results, const MarchKind kind, const DSlot g, const unsigned* perm) {
+#if VR_QUEUE_ENGINE
+    __shared__ uint2 brickQueue[VR_QUEUE_DEPTH * 128];
+    marchPoolQ<NT, FAST>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, perm, brickQueue);
+#else
     marchPool<RayMarcher<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, perm);
+#endif
 }
 // ---- bucket order of an explicit-task stream (counting sort over VR_RAY_BUCKETS coherence buckets; the histogram comes from
 // the emitting kernel, the key sits in the task's third word) ----
