@@ -488,6 +488,71 @@ struct AnalyticMarcher : MarchTrav {
     }
 };
 
+// AnalyticMarcher with the traversal decoupled from the cell walk (see RayMarcherQ): the FIFO holds (leaf node, DDA entry time)
+struct AnalyticMarcherQ : AnalyticMarcher {
+    uint32_t cbrick;
+    unsigned qh, qt;
+    bool live, inBrick, cdone;
+    VRD void travStepQ(const DSlot& g, uint2* q) {
+        if (!(iter < 4096 && inRange(p, g.res[1] + 1))) { phase = MARCH_DONE; return; }
+        iter++;
+        next();
+#if VR_PREFETCH_CHILD
+        const uint32_t child = brick;
+#else
+        const uint32_t child = childOf(g);
+#endif
+        if (child != ID_UNDEFL) { q[(qt % VR_QUEUE_DEPTH) * 128] = make_uint2(child, __float_as_uint(tx)); qt++; }
+        step();
+        if (tx > tMax1) phase = MARCH_ASCEND; else fetchChild(g);
+    }
+    VRD void enterBrickQ(const DSlot& g, const uint2* q) {   // AnalyticMarcher::enterBrick for the oldest queued brick
+        const uint2 e = q[(qh % VR_QUEUE_DEPTH) * 128]; qh++;
+        const int4 leaf = __ldg((const int4*)&g.nodes[0][e.x]);
+        cbrick = (uint32_t)leaf.w;
+        vminLeaf = nodePos(leaf);
+        const float txe = __uint_as_float(e.y);
+        t = txe - 0.01f;
+        const float3 tDelL = make_float3(fabsf(invDir.x), fabsf(invDir.y), fabsf(invDir.z));
+        const float3 pFlt = pos + txe * dir - vminLeaf;
+        const float3 fl = make_float3(floorf(pFlt.x), floorf(pFlt.y), floorf(pFlt.z));
+        const float3 sgn = make_float3(dir.x >= 0 ? 1.f : -1.f, dir.y >= 0 ? 1.f : -1.f, dir.z >= 0 ? 1.f : -1.f);
+        lSide = ((fl - pFlt + f3(0.5f)) * sgn + f3(0.5f)) * tDelL + f3(txe);
+        lp = make_int3((int)fl.x, (int)fl.y, (int)fl.z);
+        ltx = txe;
+        biter = 0;
+        inBrick = true;
+    }
+    VRD void sampleStepQ(const DSlot& g, bool) {   // AnalyticMarcher::sampleStep on cbrick
+        if (!(biter < MAX_BRICK_STEPS && inRange(lp, 8))) { inBrick = false; return; }
+        const bool mx = (lSide.x < lSide.y) & (lSide.x <= lSide.z);
+        const bool my = (lSide.y < lSide.z) & (lSide.y <= lSide.x);
+        const bool mz = (lSide.z < lSide.x) & (lSide.z <= lSide.y);
+        lty = mx ? lSide.x : (my ? lSide.y : lSide.z);
+        const float maxDeltaT = lty - t;
+        float v[8];
+        if (g.format == VRESTIR_ATLAS_F32 && g.channels == 1) {
+            const float* a = (const float*)g.atlas + (cbrick * (unsigned)VRESTIR_BRICK_VOXELS + (unsigned)(((lp.z + 1) * 10 + (lp.y + 1)) * 10 + (lp.x + 1)));
+            const float s1 = g.compress_scale, s2 = c_scene.vol.densityScaleFactorByScaling;
+            v[0] = __ldg(a) * s1 * s2; v[1] = __ldg(a + 1) * s1 * s2; v[2] = __ldg(a + 10) * s1 * s2; v[3] = __ldg(a + 11) * s1 * s2;
+            v[4] = __ldg(a + 100) * s1 * s2; v[5] = __ldg(a + 101) * s1 * s2; v[6] = __ldg(a + 110) * s1 * s2; v[7] = __ldg(a + 111) * s1 * s2;
+        } else FetchEightVoxels(g, cbrick, lp, v);
+        const float3 p0 = pos + ltx * dir - (make_float3((float)lp.x, (float)lp.y, (float)lp.z) + vminLeaf);
+        float c3, c2, c1, c0;
+        trilinearCubic(v, c_scene.vol.sigma_t, dir, p0, c3, c2, c1, c0);
+        const float t_dist = fminf(tFar - t, maxDeltaT);
+        const float t2 = t_dist * t_dist, t3 = t2 * t_dist, t4 = t2 * t2;
+        Tr += -(c3 * t4 / 4 + c2 * t3 / 3 + c1 * t2 / 2 + c0 * t_dist);
+        if (t + maxDeltaT >= tFar || Tr < -110.f) { cdone = true; inBrick = false; return; }
+        t += maxDeltaT;
+        ltx = lty;
+        if (mx) { lSide.x += fabsf(invDir.x); lp.x += stepI.x; }
+        if (my) { lSide.y += fabsf(invDir.y); lp.y += stepI.y; }
+        if (mz) { lSide.z += fabsf(invDir.z); lp.z += stepI.z; }
+        biter++;
+    }
+};
+
 // ---- free-flight distance sampling (SampleMediumAnalyticAdapter with the point sampler and ONE sample,
 // VR/VolumeTrackingAdapterGVDB.slang:210-437): the in-brick phase walks the voxel cells of the brick with a leaf DDA and draws one
 // exponential step per non-empty cell from the task's OWN random-number stream, exactly as the per-pixel traversal does.  Used
@@ -623,7 +688,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
 
 // Pool of 32 persistent lanes over one task stream for RayMarcherQ (see there).  q: VR_QUEUE_DEPTH x 128 entries of shared memory
 // per CTA, [slot][thread].
-template <int NT, bool FAST>
+template <class MQ>
 __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g,
                                            const unsigned* __restrict__ perm, uint2* qBase) {
     const unsigned FULL = 0xffffffffu;
@@ -631,7 +696,7 @@ __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsi
     const unsigned ltMask = (1u << lane) - 1u;
     const bool linear = kind.linear != 0;
     uint2* const q = qBase + threadIdx.x;
-    RayMarcherQ<NT, FAST> m;
+    MQ m;
     m.phase = MARCH_IDLE; m.live = false; m.inBrick = false; m.cdone = false; m.qh = m.qt = 0;
     bool drained = false;
     bool sampling = false;   // warp-uniform: the phase the pool is in (hysteresis: it stays until fewer than VR_QUEUE_KEEP / 8 of the busy lanes can take part)

@@ -31,7 +31,7 @@ template <int NT, bool FAST>
 __global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march(const WfStream s, float* results, const MarchKind kind, const DSlot g, const unsigned* perm) {
 #if VR_QUEUE_ENGINE
     __shared__ uint2 brickQueue[VR_QUEUE_DEPTH * 128];
-    marchPoolQ<NT, FAST>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, perm, brickQueue);
+    marchPoolQ<RayMarcherQ<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, perm, brickQueue);
 #else
     marchPool<RayMarcher<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, perm);
 #endif
@@ -68,8 +68,16 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const WfStream s, unsigned*
 #ifndef VR_ANALYTIC_MINB
 #define VR_ANALYTIC_MINB 8
 #endif
+#ifndef VR_QUEUE_ANALYTIC
+#define VR_QUEUE_ANALYTIC 1
+#endif
 __global__ void __launch_bounds__(128, VR_ANALYTIC_MINB) k_march_analytic(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
+#if VR_QUEUE_ANALYTIC
+    __shared__ uint2 brickQueue[VR_QUEUE_DEPTH * 128];
+    marchPoolQ<AnalyticMarcherQ>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, nullptr, brickQueue);
+#else
     marchPool<AnalyticMarcher>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ K3 gather
