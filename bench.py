@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap K0/K1 of frame f+1 with K2..K5 of frame f")
     ap.add_argument("--pipeline-level", type=int, default=2, help="1: K0/K1 of the next frame run ahead; 2: K5 additionally deferred to a third stream")
     ap.add_argument("--per-pixel", action="store_true", help="force the per-pixel kernels (A/B against the task-stream path)")
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE", help="extra pass-dictionary entry (A/B of a tuning switch, e.g. mPrimaryDistanceEngine=0)")
     a = ap.parse_args()
     c = CONFIGS[a.config]
     for k in ("width", "height", "dim", "kind", "mips", "bounces"):
@@ -397,6 +398,8 @@ class Runner:
         d = {"mParams": params, "mPipelineFrames": level}
         if args.per_pixel:
             d["mUseWavefront"] = 0
+        for kv in getattr(args, "set", []) or []:
+            d[kv.split("=")[0]] = float(kv.split("=")[1])
         self.gp = VolumetricReSTIR.create(d, device=local)
         self.sp = ShardedPass(self.gp, W, H, rank, world, torch.device("cuda", local))
         self.gp.setScene(scene, W, H)

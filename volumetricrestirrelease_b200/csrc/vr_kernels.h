@@ -33,6 +33,9 @@ cudaError_t launchInitialMBTraverse(const FrameParams& fp, const WfInitialMB& wi
 int initialMBStepBlocksPerSM();
 int initialMBBounceTraverseBlocksPerSM();
 int distanceBlocksPerSM();
+int primaryDistanceBlocksPerSM();
+cudaError_t launchPrimaryDistance(const FrameParams& fp, float* state, unsigned stride, unsigned hdOffset, unsigned* cursor, const DSlot& grid, int blocks, cudaStream_t st);
+cudaError_t launchInitialStepOnly(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st);
 cudaError_t launchMarchDistance(const WfStream& s, float* state, const MarchKind& kind, const DSlot& grid, int blocks, cudaStream_t st);
 cudaError_t launchInitialMBBounceTraverse(const FrameParams& fp, const WfInitialMB& wi, int blocks, cudaStream_t st);
 cudaError_t launchInitialMBStep(const FrameParams& fp, const WfInitialMB& wi, int first, int blocks, cudaStream_t st);

@@ -686,11 +686,126 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
 }
 
 
+// ---- K1's primary free-flight sampling (SampleMediumAnalyticGeneric with the point sampler, up to 4 samples along the camera ray
+// of a pixel, VR/TraceRays.cs.slang:111-128 + VR/VolumeTrackingAdapterGVDB.slang:210-437) on the decoupled pool.  Tasks are
+// IMPLICIT: task i is pixel i of the band in 8x4-tile order; setup seeds the pixel's generator, builds its camera ray and clips
+// it.  A sample is written to the pixel's state block the moment it is found (hit distances | pdfs | transmittances, 4 floats
+// each, at `out`; the generator 4 floats before them), so only the mask of pending samples lives in registers.
+struct PrimaryDistanceCtx { FrameParams fp; float* state; unsigned stride, hdOffset; int numSamples; };
+struct DistanceMarcherQ : MarchTrav {
+    static constexpr bool kImplicitTasks = true;
+    unsigned outIdx;
+    float3 lSide; int3 lp;
+    float t; int biter;
+    float opticalThickness;
+    unsigned pendingSamples;
+    SampleGenerator sg;
+    uint32_t cbrick;
+    unsigned qh, qt;
+    bool live, inBrick, cdone;
+
+    VRD void writeOut(float* results) {
+        // ExecuteEndStep for the samples still pending (the traversal left the volume), then the generator
+        const float tr = expf(-opticalThickness);
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            if ((pendingSamples >> s) & 1u) { results[outIdx + s] = kRayTMax; results[outIdx + 4 + s] = tr; results[outIdx + 8 + s] = tr; }
+        ((float4*)(results + outIdx - 4))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
+        phase = MARCH_IDLE;
+    }
+    // returns false for a slot of the tile grid outside the frame
+    VRD bool setupIndex(unsigned idx, const MarchKind& kind, const DSlot& g, const PrimaryDistanceCtx& c) {
+        const FrameParams& fp = c.fp;
+        const unsigned tilesX = (unsigned)(fp.W + 7) / 8u, tile = idx >> 5, within = idx & 31u;
+        const int x = (int)((tile % tilesX) * 8u + (within & 7u)), y = fp.rowBegin + (int)((tile / tilesX) * 4u + (within >> 3));
+        if (x >= fp.W || y >= fp.rowEnd) return false;
+        outIdx = (unsigned)(y * fp.W + x - fp.rowBegin * fp.W) * c.stride + c.hdOffset;
+        sg = SampleGenerator::create((uint32_t)x, (uint32_t)y, (uint32_t)(fp.numTotalRounds * fp.frameCount));
+        float* out = c.state + outIdx;
+        ((float4*)out)[0] = make_float4(0.f, 0.f, 0.f, 0.f); ((float4*)out)[1] = make_float4(0.f, 0.f, 0.f, 0.f); ((float4*)out)[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        opticalThickness = 0.f;
+        pendingSamples = (1u << c.numSamples) - 1u;
+        const Ray rW = primaryRay(fp, x, y);
+        if (!beginTraversal(rW, g, false)) {
+            // the camera ray misses the volume box: ExecuteEndStep before ExecuteStartStep
+#pragma unroll
+            for (int s = 0; s < 4; s++) if (s < c.numSamples) { out[s] = kRayTMax; out[4 + s] = 1.f; out[8 + s] = 1.f; }
+            pendingSamples = 0u;
+            phase = MARCH_DONE;
+        }
+        return true;
+    }
+    VRD void travStepQ(const DSlot& g, uint2* q) {
+        if (!(iter < 4096 && inRange(p, g.res[1] + 1))) { phase = MARCH_DONE; return; }
+        iter++;
+        next();
+#if VR_PREFETCH_CHILD
+        const uint32_t child = brick;
+#else
+        const uint32_t child = childOf(g);
+#endif
+        if (child != ID_UNDEFL) { q[(qt % VR_QUEUE_DEPTH) * 128] = make_uint2(child, __float_as_uint(tx)); qt++; }
+        step();
+        if (tx > tMax1) phase = MARCH_ASCEND; else fetchChild(g);
+    }
+    VRD void enterBrickQ(const DSlot& g, const uint2* q) {
+        const uint2 e = q[(qh % VR_QUEUE_DEPTH) * 128]; qh++;
+        const int4 leaf = __ldg((const int4*)&g.nodes[0][e.x]);
+        cbrick = (uint32_t)leaf.w;
+        const float3 vminLeaf = nodePos(leaf);
+        const float txe = __uint_as_float(e.y);
+        t = txe - 0.01f;
+        const float3 tDelL = make_float3(fabsf(invDir.x), fabsf(invDir.y), fabsf(invDir.z));
+        const float3 pFlt = pos + txe * dir - vminLeaf;
+        const float3 fl = make_float3(floorf(pFlt.x), floorf(pFlt.y), floorf(pFlt.z));
+        const float3 sgn = make_float3(dir.x >= 0 ? 1.f : -1.f, dir.y >= 0 ? 1.f : -1.f, dir.z >= 0 ? 1.f : -1.f);
+        lSide = ((fl - pFlt + f3(0.5f)) * sgn + f3(0.5f)) * tDelL + f3(txe);
+        lp = make_int3((int)fl.x, (int)fl.y, (int)fl.z);
+        biter = 0;
+        inBrick = true;
+    }
+    // one voxel cell: every pending sample draws (VR/VolumeTrackingAdapterGVDB.slang:300-361, point sampler)
+    VRD void sampleStepQ(const DSlot& g, bool, float* results) {
+        if (!(biter < MAX_BRICK_STEPS && inRange(lp, 8))) { inBrick = false; return; }
+        const bool mx = (lSide.x < lSide.y) & (lSide.x <= lSide.z);
+        const bool my = (lSide.y < lSide.z) & (lSide.y <= lSide.x);
+        const bool mz = (lSide.z < lSide.x) & (lSide.z <= lSide.y);
+        const float lty = mx ? lSide.x : (my ? lSide.y : lSide.z);
+        const float maxDeltaT = fminf(tFar - t, lty - t);
+        const float currentTMax = fminf(tFar, lty);
+        const float density = DensityInAtlas<true>(g, cbrick, make_float3((float)lp.x, (float)lp.y, (float)lp.z) + f3(0.5f), false);
+        const float sigma_t = density * c_scene.vol.sigma_t;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (!((pendingSamples >> s) & 1u)) continue;
+            if (sigma_t == 0.f) { (void)sg.next(); continue; }   // an empty cell can never be hit; only the draw counts
+            const float dT = -logf(1 - sampleNext1D(sg)) / sigma_t;
+            float curT = t + dT;
+            if (isnan(curT) || isinf(curT)) curT = kRayTMax;
+            if (curT < currentTMax) {
+                const float tr = expf(-(dT * sigma_t + opticalThickness));
+                results[outIdx + s] = curT; results[outIdx + 4 + s] = sigma_t * tr; results[outIdx + 8 + s] = tr;
+                pendingSamples &= ~(1u << s);
+            }
+        }
+        if (!pendingSamples) { cdone = true; inBrick = false; return; }
+        t = currentTMax;
+        opticalThickness += maxDeltaT * sigma_t;
+        if (t >= tFar) { cdone = true; inBrick = false; return; }   // ExecuteEndStep in writeOut
+        if (mx) { lSide.x += fabsf(invDir.x); lp.x += stepI.x; }
+        if (my) { lSide.y += fabsf(invDir.y); lp.y += stepI.y; }
+        if (mz) { lSide.z += fabsf(invDir.z); lp.z += stepI.z; }
+        biter++;
+    }
+};
+
 // Pool of 32 persistent lanes over one task stream for RayMarcherQ (see there).  q: VR_QUEUE_DEPTH x 128 entries of shared memory
 // per CTA, [slot][thread].
-template <class MQ>
+template <class T> struct MarcherTraits { static constexpr bool kImplicit = false; };
+template <> struct MarcherTraits<DistanceMarcherQ> { static constexpr bool kImplicit = true; };
+template <class MQ, class Ctx = int>
 __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g,
-                                           const unsigned* __restrict__ perm, uint2* qBase) {
+                                           const unsigned* __restrict__ perm, uint2* qBase, const Ctx* ctx = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -714,8 +829,10 @@ __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsi
                 if (!m.live) {
                     const unsigned idx = base + __popc(parked & ltMask);
                     if (idx < total) {
-                        m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g, results);
-                        m.live = true; m.inBrick = false; m.cdone = false; m.qh = m.qt = 0;
+                        bool have = true;
+                        if constexpr (MarcherTraits<MQ>::kImplicit) have = m.setupIndex(idx, kind, g, *ctx);
+                        else m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g, results);
+                        if (have) { m.live = true; m.inBrick = false; m.cdone = false; m.qh = m.qt = 0; }
                     }
                 }
                 if (base + n >= total) drained = true;
@@ -748,7 +865,10 @@ __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsi
         } else {
             if (canS && !m.inBrick) m.enterBrickQ(g, q);
 #pragma unroll 1
-            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) if (m.inBrick) m.sampleStepQ(g, linear);
+            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) {
+                if constexpr (MarcherTraits<MQ>::kImplicit) { if (m.inBrick) m.sampleStepQ(g, linear, results); }
+                else { if (m.inBrick) m.sampleStepQ(g, linear); }
+            }
         }
     }
 }

@@ -148,6 +148,8 @@ struct vrestir_pass {
     // off by default — measured: 13.2 -> 13.8 lanes per instruction, light march 1.67 -> 1.61 ms, the sort itself 0.17 ms: a net loss
     // (profiles/r02_sorted_light_marches.txt)
     bool mSortLightTasks = false; unsigned* wfBins = nullptr; unsigned* wfPerm = nullptr;
+    // "mPrimaryDistanceEngine": K1's free-flight sampling along the camera rays runs on the march engine (point sampler) instead of the per-pixel traversal kernel
+    bool mPrimaryDistanceEngine = true; int primaryBlocks = 0;
     size_t wfPixels = 0;
     int marchBlocks1 = 0, marchBlocks3 = 0, analyticBlocks = 0;
     float* wfInitialState = nullptr; size_t wfInitialPixels = 0;   // lock-step wavefront K1
@@ -733,9 +735,15 @@ int runInitialWavefront(vrestir_pass* p, const FrameParams& fp, cudaStream_t st)
     wi.evalCam.tasks = p->k1EvalTasks; wi.evalCam.count = cnt + 4; wi.evalCam.cursor = cnt + 5; wi.evalCam.capacity = (unsigned)(oneEval ? 2 * n : n);
     if (oneEval) wi.evalLight = wi.evalCam;
     else { wi.evalLight.tasks = p->k1EvalTasks + 3 * n; wi.evalLight.count = cnt + 6; wi.evalLight.cursor = cnt + 7; wi.evalLight.capacity = (unsigned)n; }
+    const bool primaryEngine = p->mPrimaryDistanceEngine && !m.mInitialVisibilityUseLinearSampler;
+    if (primaryEngine && !p->primaryBlocks) { int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device); p->primaryBlocks = sms * primaryDistanceBlocksPerSM(); }
     for (int s = 0; s <= m.mInitialM; s++) {
         if (s > 0 && s < m.mInitialM) CK(cudaMemsetAsync(cnt, 0, 8, st));
-        CK(launchInitialStep(fp, wi, s, st)); p->launches += s == 0 ? 2 : 1;
+        if (s == 0 && primaryEngine) {
+            CK(launchPrimaryDistance(fp, wi.state, K1_STRIDE, 24 /* K1_HD */, cnt + 12, p->scene.slots[fp.initial.visibilityMipLevel], p->primaryBlocks, st));
+            CK(launchInitialStepOnly(fp, wi, 0, st));
+        } else CK(launchInitialStep(fp, wi, s, st));
+        p->launches += s == 0 ? 2 : 1;
         if (s < m.mInitialM) { CK(launchMarch(wi.light, wi.state, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st)); p->launches++; }
     }
     CK(launchMarch(wi.evalCam, wi.results, kc, p->scene.slots[kc.mip], 1, p->marchBlocks1, st)); p->launches++;
@@ -799,7 +807,10 @@ int runInitialWavefrontMB(vrestir_pass* p, const FrameParams& fp, cudaStream_t s
         int cur = 0;
         wi.travList = travLists; wi.travCount = travCounts; wi.prevTravList = travLists + chunkPixels; wi.prevTravCount = travCounts + 1;
         CK(cudaMemsetAsync(p->k1mb.counters, 0, 64, st));
-        CK(launchInitialMBTraverse(fc, wi, st));
+        if (p->mPrimaryDistanceEngine && travEngine) {
+            if (!p->primaryBlocks) p->primaryBlocks = sms * primaryDistanceBlocksPerSM();
+            CK(launchPrimaryDistance(fc, wi.state, K1MB_STRIDE, MBK_HD, p->k1mb.counters + 12, p->scene.slots[fc.initial.visibilityMipLevel], p->primaryBlocks, st));
+        } else CK(launchInitialMBTraverse(fc, wi, st));
         CK(launchInitialMBStep(fc, wi, 1, 0, st));
         p->launches += 2;
         // every wave advances every running pixel to its next suspension: the shadow march of a bounce (<= B per candidate) or the
@@ -1553,6 +1564,7 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) try {
         else if (k == "mOverlapFeatures") p->mOverlapFeatures = value != 0;
         else if (k == "mPipelineFrames") p->mPipelineFrames = (int)value;
         else if (k == "mSortLightTasks") p->mSortLightTasks = value != 0;
+        else if (k == "mPrimaryDistanceEngine") p->mPrimaryDistanceEngine = value != 0;
         else if (k == "mDebugPoisonResults") p->mDebugPoison = value != 0;
         else if (k == "mScratchBudgetMB") p->mScratchBudget = (size_t)std::max(1.0, value) << 20;
         else if (k == "mPrefetchPriority") p->mPrefetchPriority = value != 0;

@@ -1257,6 +1257,16 @@ __global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FramePa
     }
 }
 
+// K1's primary free-flight sampling on the decoupled engine (point sampler): implicit tasks, one per pixel of the band
+#ifndef VR_PRIMARY_MINB
+#define VR_PRIMARY_MINB 6
+#endif
+__global__ void __launch_bounds__(128, VR_PRIMARY_MINB) k_march_primary_distance(const PrimaryDistanceCtx c, unsigned* cursor, const MarchKind kind, const DSlot g) {
+    __shared__ uint2 brickQueue[VR_QUEUE_DEPTH * 128];
+    const unsigned tilesX = (unsigned)(c.fp.W + 7) / 8u, tilesY = (unsigned)(c.fp.rowEnd - c.fp.rowBegin + 3) / 4u;
+    marchPoolQ<DistanceMarcherQ, PrimaryDistanceCtx>(nullptr, tilesX * tilesY * 32u, cursor, c.state, kind, g, nullptr, brickQueue, &c);
+}
+
 // the engine form of the same (point sampler): one DistanceMarcher task per waiting pixel
 __global__ void __launch_bounds__(128, VR_ANALYTIC_MINB) k_march_distance(const WfStream s, float* state, const MarchKind kind, const DSlot g) {
     marchPool<DistanceMarcher>(s.tasks, min(*s.count, s.capacity), s.cursor, state, kind, g);
@@ -1379,6 +1389,8 @@ cudaError_t launchInitialStep(const FrameParams& fp, const WfInitial& wi, int s,
     else k_initial_step<2><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s);
     return cudaGetLastError();
 }
+// step 0 without the per-pixel traversal kernel (the primary distances came from launchPrimaryDistance)
+cudaError_t launchInitialStepOnly(const FrameParams& fp, const WfInitial& wi, int s, cudaStream_t st) { k_initial_step<0><<<gridForWf(fp), 128, 0, st>>>(fp, wi, s); return cudaGetLastError(); }
 cudaError_t launchInitialFinish(const FrameParams& fp, const WfInitial& wi, cudaStream_t st) { k_initial_finish<<<gridForWf(fp), 128, 0, st>>>(fp, wi); return cudaGetLastError(); }
 cudaError_t launchTemporalGather(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_gather<<<VR_TGATHER_BLOCK == 32 ? gridForWarp(fp) : gridForWf(fp), VR_TGATHER_BLOCK, 0, st>>>(fp, wf); return cudaGetLastError(); }
 cudaError_t launchTemporalCombine(const FrameParams& fp, const WfBufs4& wf, cudaStream_t st) { k_temporal_combine<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }
@@ -1392,6 +1404,14 @@ cudaError_t launchSpatialCombine(const FrameParams& fp, const WfBufs& wf, cudaSt
         default: kern<4><<<gridForWf(fp), 128, 0, st>>>(__VA_ARGS__); break;                     \
     }
 cudaError_t launchInitialMBTraverse(const FrameParams& fp, const WfInitialMB& wi, cudaStream_t st) { k_initial_mb_traverse<<<gridForWf(fp), 128, 0, st>>>(fp, wi); return cudaGetLastError(); }
+int primaryDistanceBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march_primary_distance, 128, 0); return n > 0 ? n : 1; }
+// state: per-pixel blocks of `stride` floats; the 12 result floats go to `hdOffset`, the generator 4 floats before them
+cudaError_t launchPrimaryDistance(const FrameParams& fp, float* state, unsigned stride, unsigned hdOffset, unsigned* cursor, const DSlot& grid, int blocks, cudaStream_t st) {
+    PrimaryDistanceCtx c; c.fp = fp; c.state = state; c.stride = stride; c.hdOffset = hdOffset; c.numSamples = fp.initialM;
+    const MarchKind kind = {fp.initial.visibilityMipLevel, 0, 1.f, 0, {0.f, 0.f, 0.f}};
+    k_march_primary_distance<<<blocks, 128, 0, st>>>(c, cursor, kind, grid);
+    return cudaGetLastError();
+}
 int distanceBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march_distance, 128, 0); return n > 0 ? n : 1; }
 cudaError_t launchMarchDistance(const WfStream& s, float* state, const MarchKind& kind, const DSlot& grid, int blocks, cudaStream_t st) { k_march_distance<<<blocks, 128, 0, st>>>(s, state, kind, grid); return cudaGetLastError(); }
 int initialMBBounceTraverseBlocksPerSM() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_initial_mb_bounce_traverse, 128, 0); return n > 0 ? n : 1; }
