@@ -1004,7 +1004,7 @@ __device__ __forceinline__ int mbAdvancePixel(const FrameParams& fp, const WfIni
         Reservoir finalReservoir, combinedReservoir;
         Ray ray = primary;
         float pathPdf = 1.f, pathPHat = 1.f, primaryScatterDepth = 0.f;
-        int s = 0, bounce = 0;
+        int s = 0, bounce = 0, kind = 0;
         float3 extra[B - 1], finalExtra[B - 1];
         if (first) {
             finalReservoir = createNewReservoir(); combinedReservoir = createNewReservoir();
@@ -1012,16 +1012,26 @@ __device__ __forceinline__ int mbAdvancePixel(const FrameParams& fp, const WfIni
             for (int i = 0; i < B - 1; i++) { extra[i] = f3(0.f); finalExtra[i] = f3(0.f); }
         } else {
             finalReservoir = mbLoadRes(st + MBK_FIN); combinedReservoir = mbLoadRes(st + MBK_COMB);
-            ray.origin = f3(st[MBK_PATH], st[MBK_PATH + 1], st[MBK_PATH + 2]); ray.dir = f3(st[MBK_PATH + 3], st[MBK_PATH + 4], st[MBK_PATH + 5]);
-            pathPdf = st[MBK_PATH + 6]; pathPHat = st[MBK_PATH + 7]; primaryScatterDepth = st[MBK_PATH + 8];
-            s = __float_as_int(st[MBK_CUR]); bounce = __float_as_int(st[MBK_CUR + 1]);
+            // PATH (9 floats) | CUR (2) | KIND, FINX and EXTRA (9 floats each, padded to 12): 16-byte loads
+            float pc[12], fx[12], ex[12];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float4 a = ((const float4*)(st + MBK_PATH))[k], b = ((const float4*)(st + MBK_FINX))[k], c4 = ((const float4*)(st + MBK_EXTRA))[k];
+                pc[4 * k] = a.x; pc[4 * k + 1] = a.y; pc[4 * k + 2] = a.z; pc[4 * k + 3] = a.w;
+                fx[4 * k] = b.x; fx[4 * k + 1] = b.y; fx[4 * k + 2] = b.z; fx[4 * k + 3] = b.w;
+                ex[4 * k] = c4.x; ex[4 * k + 1] = c4.y; ex[4 * k + 2] = c4.z; ex[4 * k + 3] = c4.w;
+            }
+            ray.origin = f3(pc[0], pc[1], pc[2]); ray.dir = f3(pc[3], pc[4], pc[5]);
+            pathPdf = pc[6]; pathPHat = pc[7]; primaryScatterDepth = pc[8];
+            s = __float_as_int(pc[MBK_CUR - MBK_PATH]); bounce = __float_as_int(pc[MBK_CUR + 1 - MBK_PATH]);
+            kind = __float_as_int(pc[MBK_KIND - MBK_PATH]);
 #pragma unroll
             for (int i = 0; i < B - 1; i++) {
-                extra[i] = f3(st[MBK_EXTRA + 3 * i], st[MBK_EXTRA + 3 * i + 1], st[MBK_EXTRA + 3 * i + 2]);
-                finalExtra[i] = f3(st[MBK_FINX + 3 * i], st[MBK_FINX + 3 * i + 1], st[MBK_FINX + 3 * i + 2]);
+                extra[i] = f3(ex[3 * i], ex[3 * i + 1], ex[3 * i + 2]);
+                finalExtra[i] = f3(fx[3 * i], fx[3 * i + 1], fx[3 * i + 2]);
             }
         }
-        bool resume = !first && __float_as_int(st[MBK_KIND]) == 0;      // after a shadow march
+        bool resume = !first && kind == 0;      // after a shadow march
         bool resumeTrav = !first && !resume;                             // after a bounce traversal
         bool finished = false;
         MBPend c;
@@ -1182,14 +1192,20 @@ __device__ __forceinline__ int mbAdvancePixel(const FrameParams& fp, const WfIni
         } else {
             ((float4*)(st + MBK_SG))[0] = make_float4(__uint_as_float(sg.s0), __uint_as_float(sg.s1), __uint_as_float(sg.s2), __uint_as_float(sg.s3));
             mbStoreRes(st + MBK_FIN, finalReservoir); mbStoreRes(st + MBK_COMB, combinedReservoir);
-            st[MBK_PATH] = ray.origin.x; st[MBK_PATH + 1] = ray.origin.y; st[MBK_PATH + 2] = ray.origin.z;
-            st[MBK_PATH + 3] = ray.dir.x; st[MBK_PATH + 4] = ray.dir.y; st[MBK_PATH + 5] = ray.dir.z;
-            st[MBK_PATH + 6] = pathPdf; st[MBK_PATH + 7] = pathPHat; st[MBK_PATH + 8] = primaryScatterDepth;
-            st[MBK_CUR] = __int_as_float(s); st[MBK_CUR + 1] = __int_as_float(bounce); st[MBK_KIND] = __int_as_float(waitTrav ? 1 : 0);
+            ((float4*)(st + MBK_PATH))[0] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x);
+            ((float4*)(st + MBK_PATH))[1] = make_float4(ray.dir.y, ray.dir.z, pathPdf, pathPHat);
+            ((float4*)(st + MBK_PATH))[2] = make_float4(primaryScatterDepth, __int_as_float(s), __int_as_float(bounce), __int_as_float(waitTrav ? 1 : 0));
+            float fx[12], ex[12];
 #pragma unroll
-            for (int i = 0; i < B - 1; i++) {
-                st[MBK_EXTRA + 3 * i] = extra[i].x; st[MBK_EXTRA + 3 * i + 1] = extra[i].y; st[MBK_EXTRA + 3 * i + 2] = extra[i].z;
-                st[MBK_FINX + 3 * i] = finalExtra[i].x; st[MBK_FINX + 3 * i + 1] = finalExtra[i].y; st[MBK_FINX + 3 * i + 2] = finalExtra[i].z;
+            for (int i = 0; i < 4; i++) {
+                const bool have = i < B - 1;
+                ex[3 * i] = have ? extra[i < B - 1 ? i : 0].x : 0.f; ex[3 * i + 1] = have ? extra[i < B - 1 ? i : 0].y : 0.f; ex[3 * i + 2] = have ? extra[i < B - 1 ? i : 0].z : 0.f;
+                fx[3 * i] = have ? finalExtra[i < B - 1 ? i : 0].x : 0.f; fx[3 * i + 1] = have ? finalExtra[i < B - 1 ? i : 0].y : 0.f; fx[3 * i + 2] = have ? finalExtra[i < B - 1 ? i : 0].z : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                ((float4*)(st + MBK_EXTRA))[k] = make_float4(ex[4 * k], ex[4 * k + 1], ex[4 * k + 2], ex[4 * k + 3]);
+                ((float4*)(st + MBK_FINX))[k] = make_float4(fx[4 * k], fx[4 * k + 1], fx[4 * k + 2], fx[4 * k + 3]);
             }
             if (!waitTrav) mbStorePend(st + MBK_PEND, c);
         }
