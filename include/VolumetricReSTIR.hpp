@@ -61,10 +61,17 @@ public:
     void waitOutput(void* cudaStream = nullptr) { check(vrestir_wait_output(mpPass, cudaStream)); }
     /// Scene::update for animated volumes: current grids become the previous-frame slots
     void advanceVolume(const vrestir_grid_desc& volume) { check(vrestir_advance_volume(mpPass, &volume)); }
+    /// animated sequences whose frames stay on the device (the reference's protocol, F/Scene/Scene.cpp:825-863): upload once, bind per frame
+    int addVolumeFrame(const vrestir_grid_desc& volume) { int index = -1; check(vrestir_volume_frame_add(mpPass, &volume, &index)); return index; }
+    void advanceVolumeResident(int index) { check(vrestir_advance_volume_resident(mpPass, index)); }
+    void clearVolumeFrames() { check(vrestir_volume_frames_clear(mpPass)); }
 
     /// execute(pRenderContext, renderData): renderData["accumulated_color"] / ["mvec"] are device pointers here
     void execute(float* accumulated_color, float* mvec = nullptr, void* cudaStream = nullptr) { check(vrestir_execute(mpPass, accumulated_color, mvec, cudaStream)); }
     void executeHost(float* accumulated_color_host, float* mvec_host = nullptr) { check(vrestir_execute_host(mpPass, accumulated_color_host, mvec_host)); }
+    /// the same without blocking: the read-back of this frame travels while the next one renders; hostWait() before reading the buffer
+    void executeHostAsync(float* accumulated_color_host, float* mvec_host = nullptr) { check(vrestir_execute_host_async(mpPass, accumulated_color_host, mvec_host)); }
+    void hostWait() { check(vrestir_host_wait(mpPass)); }
 
     /// updateDict(): any key resets the frame counter and the temporal history (VR/VolumetricReSTIR.cpp:1339)
     void updateDict(const Dictionary& dict, bool initial = false) {
