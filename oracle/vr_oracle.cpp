@@ -2391,6 +2391,14 @@ int vro_env_sample(vro_pass* p, float u0, float u1, float out_dir[3], float* out
     out_dir[0] = s.dir.x; out_dir[1] = s.dir.y; out_dir[2] = s.dir.z; *out_pdf = s.pdf; out_Le[0] = s.Le.x; out_Le[1] = s.Le.y; out_Le[2] = s.Le.z;
     return 1;
 }
+float vro_phase_hg(float cos_theta, float g) { return PhaseHG(cos_theta, g); }
+float vro_sample_phase(float g, const float wo[3], float u0, float u1, float out_wi[3]) {
+    MediumInteraction mi{f3(0.f), v3(wo), g, true};
+    float3 wi = f3(0.f);
+    const float pdf = mi.Sample_p(v3(wo), wi, {u0, u1});
+    out_wi[0] = wi.x; out_wi[1] = wi.y; out_wi[2] = wi.z;
+    return pdf;
+}
 void vro_neighbor_offsets(vro_pass* p, int frame_count, int round, int32_t* out_xy) {
     const auto& m = p->P;
     int seed = ((m.mSpatialReuseRounds + 1) * frame_count + round) % 16;

@@ -70,10 +70,22 @@ def lib():
         L.vro_env_eval.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3)]
         L.vro_env_sample.argtypes = [vp, C.c_float, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float), C.POINTER(C.c_float * 3)]
         L.vro_neighbor_offsets.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.vro_phase_hg.argtypes = [C.c_float, C.c_float]; L.vro_phase_hg.restype = C.c_float
+        L.vro_sample_phase.argtypes = [C.c_float, C.POINTER(C.c_float * 3), C.c_float, C.c_float, C.POINTER(C.c_float * 3)]; L.vro_sample_phase.restype = C.c_float
         L.vro_encode_wi_dist.argtypes = [C.POINTER(C.c_float * 4), C.POINTER(C.c_float * 3)]
         L.vro_decode_wi_dist.argtypes = [C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 4)]
         _lib = L
     return _lib
+
+
+def phase_hg(cos_theta, g):
+    return float(lib().vro_phase_hg(cos_theta, g))
+
+
+def sample_phase(g, wo, u0, u1):
+    w = (C.c_float * 3)(*wo); out = (C.c_float * 3)()
+    pdf = float(lib().vro_sample_phase(g, C.byref(w), u0, u1, C.byref(out)))
+    return np.array(out[:], dtype=np.float32), pdf
 
 
 def check(rc):
@@ -175,6 +187,17 @@ class OraclePass:
         o = (C.c_float * 3)(*origin)
         d = (C.c_float * 3)(*direction)
         return float(lib().vro_transmittance(self._h, C.byref(o), C.byref(d), tmax, method, mip, int(linear), tstep_scale, *seed))
+
+    def env_eval(self, direction):
+        d = (C.c_float * 3)(*direction); out = (C.c_float * 3)()
+        lib().vro_env_eval(self._h, C.byref(d), C.byref(out))
+        return np.array(out[:], dtype=np.float32)
+
+    def env_sample(self, u0, u1):
+        """(direction, pdf, Le) of EnvMapSampler::sample for the random pair (u0, u1)."""
+        d = (C.c_float * 3)(); le = (C.c_float * 3)(); pdf = C.c_float()
+        lib().vro_env_sample(self._h, u0, u1, C.byref(d), C.byref(pdf), C.byref(le))
+        return np.array(d[:], dtype=np.float32), float(pdf.value), np.array(le[:], dtype=np.float32)
 
     def density_world(self, pos, mip=0):
         o = (C.c_float * 3)(*pos)
