@@ -5,6 +5,8 @@ C++ oracle, of:
   * the iterative hierarchical DDA          VR/VolumeUtils.slang:171-282  + F/Scene/GVDB/gvdbDda.slang:86-157
   * ray-marched transmittance               VR/VolumeTrackingAdapterGVDB.slang:140-208, VR/VolumeUtils.slang:350-362
   * analytic (regular-tracking) transmittance, trilinear and point      VR/VolumeTrackingAdapterGVDB.slang:20-136
+  * free-flight distance sampling (K1's candidate generation), point and trilinear, with the pixel's own xoshiro128** stream
+                                            VR/VolumeTrackingAdapterGVDB.slang:210-437, F/Utils/Sampling/UniformSampleGenerator.slang
   * WorldToMedium / IntersectVolumeBound / DensityInAtlas / FetchEightVoxelsInAtlas     VR/VolumeBase.slang:103-175,234-263
   * getNode / getChild                      F/Scene/GVDB/gvdbNodes.slang:98-114
 for one ray at a time over a grid slot in the layout of include/vrestir.h (32-byte nodes, dense child lists, brick pool of
@@ -223,6 +225,155 @@ class AnalyticAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:20-136
         self.Tr = np.exp(self.Tr)
 
 
+class Xoshiro:
+    """UniformSampleGenerator (F/Utils/Sampling/UniformSampleGenerator.slang:49-72): SplitMix64 seeded with
+    (interleave_32bit(pixel), sampleNumber) fills the state of xoshiro128** (Pseudorandom/Xoshiro.slang:47-66,
+    SplitMix64.slang:52-58, F/Utils/Math/BitTricks.slang:45-61); sampleNext1D = (next() >> 8) * 2^-24."""
+    M32, M64 = 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF
+
+    def __init__(self, px, py, sample_number):
+        def spread(v):
+            v &= 0xFFFF
+            v = (v | (v << 8)) & 0x00FF00FF
+            v = (v | (v << 4)) & 0x0F0F0F0F
+            v = (v | (v << 2)) & 0x33333333
+            return (v | (v << 1)) & 0x55555555
+        self._sm = ((sample_number & self.M32) << 32) | (spread(px) | (spread(py) << 1))
+        s0, s1 = self._splitmix(), self._splitmix()
+        self.s = [s0 & self.M32, s0 >> 32, s1 & self.M32, s1 >> 32]
+
+    def _splitmix(self):
+        self._sm = (self._sm + 0x9E3779B97F4A7C15) & self.M64
+        z = self._sm
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & self.M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & self.M64
+        return z ^ (z >> 31)
+
+    @staticmethod
+    def _rotl(x, k):
+        return ((x << k) | (x >> (32 - k))) & 0xFFFFFFFF
+
+    def next(self):
+        s = self.s
+        result = (self._rotl((s[0] * 5) & self.M32, 7) * 9) & self.M32
+        t = (s[1] << 9) & self.M32
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = self._rotl(s[3], 11)
+        return result
+
+    def next1d(self):
+        return F(self.next() >> 8) * F(2.0 ** -24)
+
+
+class DistanceSamplingAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:210-437 (SampleMediumAnalyticAdapterGVDB)
+    """Free-flight distance sampling of up to 4 samples along one ray: per voxel cell an exponential step per pending sample (point
+    sampler) or regula falsi on the cubic optical depth of the trilinear interpolant against pre-drawn targets (linear sampler)."""
+    K_RAY_TMAX = F(3.402823466e+38)
+
+    def __init__(self, num_samples, linear, rng):
+        self.n, self.linear, self.rng = num_samples, linear, rng
+        self.hit = [F(0)] * 4; self.outTr = [F(0)] * 4; self.pdf = [F(0)] * 4
+        self.opt = F(0); self.initialized = False
+
+    def start(self):
+        for i in range(self.n):
+            self.hit[i] = F(-1)
+        self.initialized = True
+
+    @staticmethod
+    def _tau(t, c3, c2, c1, c0):
+        t2 = t * t; t3 = t2 * t; t4 = t2 * t2
+        return c3 * t4 / F(4) + c2 * t3 / F(3) + c1 * t2 / F(2) + c0 * t
+
+    def main(self, W, dda, vmin_leaf, brick, t):
+        leaf = dda.copy()
+        leaf.prepare_leaf(vmin_leaf)
+        res0 = W.slot["res"][0]
+        it = 0
+        while it < MAX_BRICK_STEPS and bool(np.all((leaf.p >= 0) & (leaf.p < res0))):
+            leaf.next()
+            maxDeltaT = min(self.tFar - t, leaf.ty - t)
+            currentTMax = min(self.tFar, leaf.ty)
+            finished = 0
+            if self.linear:
+                v = [x * W.sigma_t for x in W.fetch_eight(brick, leaf.p)]
+                v000, v100, v010, v110, v001, v101, v011, v111 = v
+                mxyz = v111 - v011 - v101 - v110 + v100 + v010 + v001 - v000
+                mxy = v000 - v100 - v010 + v110
+                mxz = v000 - v100 - v001 + v101
+                myz = v000 - v010 - v001 + v011
+                mx, my, mz = v100 - v000, v010 - v000, v001 - v000
+                d = self.ray_d
+                p0 = leaf.pos + leaf.tx * leaf.dir - (leaf.p.astype(F) + vmin_leaf)
+                c3 = mxyz * d[0] * d[1] * d[2]
+                c2 = (p0[2] * d[0] * d[1] + p0[1] * d[0] * d[2] + p0[0] * d[1] * d[2]) * mxyz + mxy * d[0] * d[1] + mxz * d[0] * d[2] + myz * d[1] * d[2]
+                c1 = ((p0[1] * p0[2] * d[0] + p0[0] * p0[2] * d[1] + p0[0] * p0[1] * d[2]) * mxyz + mx * d[0] + my * d[1] + mz * d[2]
+                      + (p0[1] * d[0] + p0[0] * d[1]) * mxy + (p0[2] * d[0] + p0[0] * d[2]) * mxz + (p0[2] * d[1] + p0[1] * d[2]) * myz)
+                c0 = (p0[0] * p0[1] * p0[2] * mxyz + p0[0] * p0[1] * mxy + p0[0] * p0[2] * mxz + p0[1] * p0[2] * myz + p0[0] * mx + p0[1] * my
+                      + p0[2] * mz + v000)
+                delta = self._tau(maxDeltaT, c3, c2, c1, c0)
+                for i in range(self.n):
+                    if self.hit[i] == F(-1):
+                        if self.opt + delta >= self.outTr[i]:
+                            target = self.outTr[i] - self.opt
+                            t_low, t_high, tau_low, tau_high, t_sol = F(0), maxDeltaT, F(0), delta, F(0)
+                            k = 0
+                            while k < 32 and t_high - t_low > maxDeltaT * F(0.001):
+                                k += 1
+                                t_sol = t_low + (t_high - t_low) * (target - tau_low) / (tau_high - tau_low)
+                                tau = self._tau(t_sol, c3, c2, c1, c0)
+                                if tau < target:
+                                    t_low, tau_low = t_sol, tau
+                                else:
+                                    t_high, tau_high = t_sol, tau
+                            self.hit[i] = t + t_sol
+                            self.outTr[i] = np.exp(-self.outTr[i])
+                            t2 = t_sol * t_sol
+                            self.pdf[i] = (c3 * (t2 * t_sol) + c2 * t2 + c1 * t_sol + c0) * self.outTr[i]
+                            finished += 1
+                    else:
+                        finished += 1
+            else:
+                density = W.density_in_atlas(brick, leaf.p.astype(F) + F(0.5), False)
+                sigma_t = density * W.sigma_t
+                for i in range(self.n):
+                    if self.hit[i] == F(-1):
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            dT = -np.log(F(1) - self.rng.next1d()) / sigma_t
+                            curT = t + dT
+                        if np.isnan(curT) or np.isinf(curT):
+                            curT = self.K_RAY_TMAX
+                        if curT < currentTMax:
+                            self.hit[i] = curT
+                            self.outTr[i] = np.exp(-(dT * sigma_t + self.opt))
+                            self.pdf[i] = sigma_t * self.outTr[i]
+                            finished += 1
+                    else:
+                        finished += 1
+                delta = maxDeltaT * sigma_t
+            if finished == self.n:
+                return True, t
+            t = currentTMax
+            self.opt = self.opt + delta
+            if t >= self.tFar:
+                self.end()
+                return True, t
+            leaf.step()
+            it += 1
+        return False, t
+
+    def end(self):
+        for i in range(self.n):
+            if self.initialized:
+                if self.hit[i] == F(-1):
+                    self.hit[i] = self.K_RAY_TMAX
+                    self.outTr[i] = np.exp(-self.opt)
+                    self.pdf[i] = self.outTr[i]
+            else:
+                self.hit[i], self.outTr[i], self.pdf[i] = self.K_RAY_TMAX, F(1), F(1)
+
+
 class Witness:
     def __init__(self, grid_desc, slot_index):
         self.slot = slot_arrays(grid_desc.slots[slot_index])
@@ -336,6 +487,16 @@ class Witness:
         a = RayMarchingAdapter(linear, self.tStepBase * F(tstep_scale) * F(eff + 1))
         self.track(origin_w, dir_w, tmax, a, False)
         return float(a.Tr)
+
+    def sample_distances(self, origin_w, dir_w, num_samples, linear, rng):
+        """SampleMediumAnalytic (VR/VolumeUtils.slang: the linear sampler draws its optical-depth targets first and walks the
+        vertex-centred grid, the point sampler draws per cell): returns (hit distances, pdfs, transmittances) of the samples."""
+        a = DistanceSamplingAdapter(num_samples, linear, rng)
+        if linear:
+            for i in range(num_samples):
+                a.outTr[i] = -np.log(F(1) - rng.next1d())
+        self.track(origin_w, dir_w, DistanceSamplingAdapter.K_RAY_TMAX, a, linear)
+        return [float(x) for x in a.hit], [float(x) for x in a.pdf], [float(x) for x in a.outTr]
 
     def analytic(self, origin_w, dir_w, tmax, linear=True):
         a = AnalyticAdapter(linear)

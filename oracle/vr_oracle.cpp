@@ -2366,6 +2366,17 @@ float vro_transmittance(vro_pass* p, const float o[3], const float d[3], float t
     Ray r = {v3(o), v3(d), 0, tmax};
     return computeVisibility(c, r, sg, 1, mip, linear != 0, (uint32_t)method, tss);
 }
+// SampleMediumAnalyticGeneric along one ray with the generator of (pixel, sample number): out12 = hit distances | pdfs | transmittances
+// (4 each), out_state = the generator after the call
+void vro_sample_distances(vro_pass* p, const float o[3], const float d[3], int mip, int linear, int n, uint32_t spx, uint32_t spy, uint32_t sn, float out12[12], uint32_t out_state[4]) {
+    applyOverrides(*p);
+    Ctx c(*p); SampleGenerator sg = SampleGenerator::create(spx, spy, sn);
+    Ray r = {v3(o), v3(d), 0, kRayTMax};
+    float hd[4] = {0, 0, 0, 0}, pd[4] = {0, 0, 0, 0}, ot[4] = {0, 0, 0, 0};
+    SampleMediumAnalyticGeneric(c, r, sg, linear != 0, hd, mip, pd, ot, n);
+    for (int i = 0; i < 4; i++) { out12[i] = hd[i]; out12[4 + i] = pd[i]; out12[8 + i] = ot[i]; }
+    out_state[0] = sg.s[0]; out_state[1] = sg.s[1]; out_state[2] = sg.s[2]; out_state[3] = sg.s[3];
+}
 float vro_density_world(vro_pass* p, const float pos[3], int mip) { applyOverrides(*p); Ctx c(*p); return DensityWorldSpace(c, v3(pos), mip); }
 int vro_dump_brick_visits(vro_pass* p, const float o[3], const float d[3], int mip, int vertex_center, int max_cells, int32_t* out_xyz, float* out_t) {
     applyOverrides(*p);

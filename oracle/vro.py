@@ -70,6 +70,7 @@ def lib():
         L.vro_env_eval.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3)]
         L.vro_env_sample.argtypes = [vp, C.c_float, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float), C.POINTER(C.c_float * 3)]
         L.vro_neighbor_offsets.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.vro_sample_distances.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
         L.vro_phase_hg.argtypes = [C.c_float, C.c_float]; L.vro_phase_hg.restype = C.c_float
         L.vro_sample_phase.argtypes = [C.c_float, C.POINTER(C.c_float * 3), C.c_float, C.c_float, C.POINTER(C.c_float * 3)]; L.vro_sample_phase.restype = C.c_float
         L.vro_encode_wi_dist.argtypes = [C.POINTER(C.c_float * 4), C.POINTER(C.c_float * 3)]
@@ -198,6 +199,13 @@ class OraclePass:
         d = (C.c_float * 3)(); le = (C.c_float * 3)(); pdf = C.c_float()
         lib().vro_env_sample(self._h, u0, u1, C.byref(d), C.byref(pdf), C.byref(le))
         return np.array(d[:], dtype=np.float32), float(pdf.value), np.array(le[:], dtype=np.float32)
+
+    def sample_distances(self, origin, direction, mip, linear, n, seed):
+        """SampleMediumAnalyticGeneric along one ray: (hit distances[4], pdfs[4], transmittances[4], generator state after)."""
+        o = (C.c_float * 3)(*origin); d = (C.c_float * 3)(*direction)
+        out = np.zeros(12, dtype=np.float32); st = np.zeros(4, dtype=np.uint32)
+        lib().vro_sample_distances(self._h, C.byref(o), C.byref(d), mip, int(linear), n, seed[0], seed[1], seed[2], out.ctypes.data, st.ctypes.data)
+        return out[0:4], out[4:8], out[8:12], st
 
     def density_world(self, pos, mip=0):
         o = (C.c_float * 3)(*pos)

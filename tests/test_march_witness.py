@@ -50,3 +50,45 @@ def test_oracle_transmittance_matches_slang_witness(dim, three_level):
             assert np.isclose(got, want, rtol=4e-6, atol=1e-30), (kind, mip, linear, o, d, tmax, got, want)
             nontrivial += 0.02 < want < 0.98
     assert nontrivial > len(cases) * n * 0.4      # most rays end with an intermediate transmittance: the accumulated sums are compared
+
+
+def test_xoshiro_witness_matches_the_oracle_stream():
+    """The witness's own generator (written from the Slang / the public-domain xoshiro128**) against the oracle's words."""
+    from oracle.march_witness import Xoshiro
+    for px, py, n in ((0, 0, 0), (17, 5, 3), (1919, 1079, 4095), (65535, 65535, 2 ** 31)):
+        words = np.zeros(16, dtype=np.uint32); floats = np.zeros(16, dtype=np.float32)
+        vro.lib().vro_rng_words(px, py, n, 16, words.ctypes.data, floats.ctypes.data)
+        g = Xoshiro(px, py, n)
+        assert [g.next() for _ in range(16)] == [int(w) for w in words]
+        g = Xoshiro(px, py, n)
+        assert [float(g.next1d()) for _ in range(16)] == [float(f) for f in floats]
+
+
+@pytest.mark.parametrize("dim,three_level", [((64, 64, 56), False), ((200, 150, 140), True)])
+def test_oracle_distance_sampling_matches_slang_witness(dim, three_level):
+    """K1's candidate generation: free-flight distances along a ray (up to 4 samples, point sampler on the conservative mip and
+    trilinear sampler on the plain mip), each ray with its own random-number stream: hit distances, pdfs, transmittances and the
+    number of draws consumed (the generator state after the call) must agree."""
+    from oracle.march_witness import Xoshiro
+    sc = env_scene(dim=dim, density_scale=0.02 if not three_level else 0.008, num_mips=3)
+    grid = sc.volume.grid.contents
+    op = vro.OraclePass(VolumetricReSTIRParams())
+    op.setScene(sc, 16, 16, importance=np.zeros(349525, np.float32))
+    n_rays = 14 if three_level else 24
+    hits = exits = 0
+    for mip, linear, ns in ((9, False, 4), (8, False, 1), (1, True, 4), (10, False, 2)):
+        w = Witness(grid, mip)
+        for k, (o, d, _) in enumerate(_rays(sc, n_rays, seed=100 + mip)):
+            seed = (k * 7 + 1, k * 3 + 2, k + mip)
+            hd, pd, ot, state = op.sample_distances(o, d, mip, linear, ns, seed)
+            rng = Xoshiro(*seed)
+            whd, wpd, wot = w.sample_distances(o, d, ns, linear, rng)
+            assert [int(x) for x in state] == rng.s, (mip, linear, k)          # same number of draws
+            for i in range(ns):
+                if whd[i] > 1e37:
+                    assert hd[i] > 1e37; exits += 1
+                else:
+                    assert np.isclose(hd[i], whd[i], rtol=3e-6), (mip, linear, k, i, hd[i], whd[i]); hits += 1
+                assert np.isclose(pd[i], wpd[i], rtol=2e-5, atol=1e-30) and np.isclose(ot[i], wot[i], rtol=2e-5, atol=1e-30), (mip, linear, k, i)
+            assert all(hd[i] == 0 and pd[i] == 0 and ot[i] == 0 for i in range(ns, 4))
+    assert hits > 40 and exits > 10          # both outcomes are exercised
