@@ -341,6 +341,15 @@ struct RayMarcher : MarchTrav {
 // phase choice: 0 = every round the phase more lanes can take part in; k > 0 = hysteresis, a phase is kept until fewer than k/8 of
 // the busy lanes can take part.  Measured: hysteresis is slower for every k, so are weighted votes and popping the next brick in
 // the middle of a sampling round (profiles/r02_queue_engine.txt)
+// steps per vote of the decoupled pool, per phase.  Traversal steps are cheap (43 instructions) and a traversing lane rarely runs out
+// of work inside a round (the FIFO absorbs what it finds), so long traversal rounds amortise the vote; a brick yields only a few
+// samples, so long sampling rounds idle (sweep in profiles/r02_queue_engine.txt)
+#ifndef VR_Q_STEPS_TRAV
+#define VR_Q_STEPS_TRAV 8
+#endif
+#ifndef VR_Q_STEPS_SAMPLE
+#define VR_Q_STEPS_SAMPLE 3
+#endif
 #ifndef VR_QUEUE_KEEP
 #define VR_QUEUE_KEEP 0
 #endif
@@ -860,12 +869,12 @@ __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsi
             if (canK) m.slowStep(g);
         } else if (!sampling) {
 #pragma unroll 1
-            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++)
+            for (int rep = 0; rep < VR_Q_STEPS_TRAV; rep++)
                 if (m.live && !fin && m.phase == MARCH_TRAV && (m.qt - m.qh) < (unsigned)VR_QUEUE_DEPTH) m.travStepQ(g, q);
         } else {
             if (canS && !m.inBrick) m.enterBrickQ(g, q);
 #pragma unroll 1
-            for (int rep = 0; rep < VR_STEPS_PER_VOTE; rep++) {
+            for (int rep = 0; rep < VR_Q_STEPS_SAMPLE; rep++) {
                 if constexpr (MarcherTraits<MQ>::kImplicit) { if (m.inBrick) m.sampleStepQ(g, linear, results); }
                 else { if (m.inBrick) m.sampleStepQ(g, linear); }
             }
