@@ -344,6 +344,11 @@ struct RayMarcher : MarchTrav {
 // steps per vote of the decoupled pool, per phase.  Traversal steps are cheap (43 instructions) and a traversing lane rarely runs out
 // of work inside a round (the FIFO absorbs what it finds), so long traversal rounds amortise the vote; a brick yields only a few
 // samples, so long sampling rounds idle (sweep in profiles/r02_queue_engine.txt)
+// parked lanes at which the decoupled pool refills (the plain pool: VR_REFILL_MIN = 16).  Its busy lanes lose less to a late
+// refill than to refilling with few lanes: 20-24 is the flat optimum of the sweep
+#ifndef VR_Q_REFILL_MIN
+#define VR_Q_REFILL_MIN 24
+#endif
 #ifndef VR_Q_STEPS_TRAV
 #define VR_Q_STEPS_TRAV 8
 #endif
@@ -828,7 +833,7 @@ __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsi
         // finished: the sampler stopped (thresholds passed / transmittance underflowed) or the traversal ended and everything queued is sampled
         bool fin = m.live && (m.cdone || (m.phase == MARCH_DONE && !m.inBrick && m.qh == m.qt));
         unsigned parked = __ballot_sync(FULL, !m.live || fin);
-        if (__popc(parked) >= VR_REFILL_MIN) {
+        if (__popc(parked) >= VR_Q_REFILL_MIN) {
             if (fin) { m.writeOut(results); m.live = false; fin = false; }
             if (!drained) {
                 const unsigned n = __popc(parked);
