@@ -345,12 +345,13 @@ struct RayMarcher : MarchTrav {
 // of work inside a round (the FIFO absorbs what it finds), so long traversal rounds amortise the vote; a brick yields only a few
 // samples, so long sampling rounds idle (sweep in profiles/r02_queue_engine.txt)
 // parked lanes at which the decoupled pool refills (the plain pool: VR_REFILL_MIN = 16).  Its busy lanes lose less to a late
-// refill than to refilling with few lanes: 20-24 is the flat optimum of the sweep
+// refill than to refilling with few lanes: 20-24 is the flat optimum on the sparse headline scene, 16-20 on the dense / huge grids
+// of configs 4 and 5; 20 with 6 traversal steps is the compromise
 #ifndef VR_Q_REFILL_MIN
-#define VR_Q_REFILL_MIN 24
+#define VR_Q_REFILL_MIN 20
 #endif
 #ifndef VR_Q_STEPS_TRAV
-#define VR_Q_STEPS_TRAV 8
+#define VR_Q_STEPS_TRAV 6
 #endif
 #ifndef VR_Q_STEPS_SAMPLE
 #define VR_Q_STEPS_SAMPLE 3
