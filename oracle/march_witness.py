@@ -396,6 +396,29 @@ class Witness:
             out.append(self.tex.decode(raw) * self.slot["compress_scale"] * self.dsf)
         return out
 
+    # F/Scene/GVDB/gvdbNodes.slang:141-280 (getNode by position) + F/Scene/GVDB/gvdb.slang:6-31 (getValueAtPoint) +
+    # VR/VolumeBase.slang:232-241 (Density / DensityWorldSpace): trilinear point query of this slot at a world-space position
+    def density_world(self, p_world):
+        s = self.slot
+        pos = _mul_point(np.asarray(p_world, dtype=F), s["w2m"])
+        if bool(np.any(pos < s["bmin"])) or bool(np.any(pos >= s["bmax"])):
+            return F(0)
+        lev = s["top_lev"]
+        vmin, link = self._node(lev, 0)
+        while lev > 0:
+            span = F(s["res"][lev] * s["vdel"][lev])            # noderange of the level: 4096 / 128 voxels
+            if bool(np.any(pos < vmin)) or bool(np.any(pos >= vmin + span)):
+                return F(0)
+            pc = ((pos - vmin) / F(s["vdel"][lev])).astype(np.int64)
+            dm = s["dim"][lev]
+            b = (((int(pc[2]) << dm) + int(pc[1])) << dm) + int(pc[0])
+            child = self._child(lev, link, b)
+            if child == ID_UNDEFL:
+                return F(0)
+            lev -= 1
+            vmin, link = self._node(lev, child)
+        return self.tex.linear(link, pos - vmin) * self.dsf
+
     def _node(self, lev, idx):
         n = self.slot["nodes"][lev][idx]
         return n["pos"].astype(F), int(n["link"])

@@ -2377,6 +2377,19 @@ void vro_sample_distances(vro_pass* p, const float o[3], const float d[3], int m
     for (int i = 0; i < 4; i++) { out12[i] = hd[i]; out12[4 + i] = pd[i]; out12[8 + i] = ot[i]; }
     out_state[0] = sg.s[0]; out_state[1] = sg.s[1]; out_state[2] = sg.s[2]; out_state[3] = sg.s[3];
 }
+// p-hat of a single-bounce reservoir (depth, lightUV, lightID) of pixel (px, py) under the spatial options: what K1's finish, K2 and K3 evaluate
+float vro_p_hat(vro_pass* p, int px, int py, float depth, float uvx, float uvy, int lightID) {
+    applyOverrides(*p);
+    Ctx c(*p);
+    const FrameSetup fs = buildFrameSetup(p->P);
+    const float3 U = v3(p->cam.cameraU), V = v3(p->cam.cameraV), Wv = v3(p->cam.cameraW), pos = v3(p->cam.posW);
+    Ray ray = {pos, normalize(camRayDirNN(U, V, Wv, px, py, p->W, p->H)), 0, kRayTMax};
+    Reservoir tap = createNewReservoir();
+    tap.runningSum = 1.f; tap.M = 1.f; tap.depth = depth; tap.p_y = 1.f; tap.lightUV = {uvx, uvy}; tap.lightID = lightID;
+    SampleGenerator sg = SampleGenerator::create(0, 0, 0);
+    ExtraProvider prov{nullptr};
+    return evaluate_P_hat(c, ray, sg, prov, fs.spatial, tap, false, true, false);
+}
 float vro_density_world(vro_pass* p, const float pos[3], int mip) { applyOverrides(*p); Ctx c(*p); return DensityWorldSpace(c, v3(pos), mip); }
 int vro_dump_brick_visits(vro_pass* p, const float o[3], const float d[3], int mip, int vertex_center, int max_cells, int32_t* out_xyz, float* out_t) {
     applyOverrides(*p);

@@ -87,6 +87,7 @@ void vro_env_eval(vro_pass* p, const float dir[3], float out_rgb[3]);
 int vro_env_sample(vro_pass* p, float u0, float u1, float out_dir[3], float* out_pdf, float out_Le[3]);
 /* spatial neighbour offsets of a round (R2 in double / Hammersley), VR/SpatialReuse.cs.slang:64-81,109 */
 void vro_sample_distances(vro_pass* p, const float o[3], const float d[3], int mip, int linear, int n, uint32_t spx, uint32_t spy, uint32_t sn, float out12[12], uint32_t out_state[4]);
+float vro_p_hat(vro_pass* p, int px, int py, float depth, float uvx, float uvy, int lightID);
 float vro_phase_hg(float cos_theta, float g);
 float vro_sample_phase(float g, const float wo[3], float u0, float u1, float out_wi[3]);
 void vro_neighbor_offsets(vro_pass* p, int frame_count, int round, int32_t* out_xy);

@@ -70,6 +70,7 @@ def lib():
         L.vro_env_eval.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3)]
         L.vro_env_sample.argtypes = [vp, C.c_float, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float), C.POINTER(C.c_float * 3)]
         L.vro_neighbor_offsets.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.vro_p_hat.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]; L.vro_p_hat.restype = C.c_float
         L.vro_sample_distances.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
         L.vro_phase_hg.argtypes = [C.c_float, C.c_float]; L.vro_phase_hg.restype = C.c_float
         L.vro_sample_phase.argtypes = [C.c_float, C.POINTER(C.c_float * 3), C.c_float, C.c_float, C.POINTER(C.c_float * 3)]; L.vro_sample_phase.restype = C.c_float
@@ -206,6 +207,10 @@ class OraclePass:
         out = np.zeros(12, dtype=np.float32); st = np.zeros(4, dtype=np.uint32)
         lib().vro_sample_distances(self._h, C.byref(o), C.byref(d), mip, int(linear), n, seed[0], seed[1], seed[2], out.ctypes.data, st.ctypes.data)
         return out[0:4], out[4:8], out[8:12], st
+
+    def p_hat(self, px, py, depth, light_uv, light_id):
+        """evaluate_P_hat of a single-bounce reservoir of pixel (px, py) under the spatial sampling options."""
+        return float(lib().vro_p_hat(self._h, px, py, depth, light_uv[0], light_uv[1], light_id))
 
     def density_world(self, pos, mip=0):
         o = (C.c_float * 3)(*pos)
