@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1)
     ap.add_argument("--pipeline", type=int, default=0)
     ap.add_argument("--per-pixel", action="store_true")
-    ap.add_argument("--set", action="append", default=[], help="pass dictionary entry key=value (e.g. mSortLightTasks=0)")
+    ap.add_argument("--set", action="append", default=[], help="pass dictionary entry key=value (e.g. mPrimaryDistanceEngine=0)")
     a = ap.parse_args()
     sys.argv = [sys.argv[0], "--config", str(a.config)] + (["--width", str(a.width)] if a.width else []) + (["--height", str(a.height)] if a.height else [])
     args = bench.parse()

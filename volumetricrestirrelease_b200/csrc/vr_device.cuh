@@ -1447,19 +1447,6 @@ VRD bool wfPrepare(const Ray& rW, int mip, bool vertexCenter, PreparedRay& o) {
     o.pos = ray.origin; o.dir = ray.dir;
     return IntersectP(mn, mx, ray, o.tNear, o.tFar);
 }
-// Coherence bucket of a prepared ray: direction bin (16 x 16 octahedral) in the high byte, hashed origin cell (16^3 voxels of
-// the march mip) in the low byte.  Rays of one bucket start in the same region and run the same way, so a warp that marches
-// them meets bricks and empty space in step.  Only the ORDER of the marches depends on it, never a result.
-VRD unsigned rayBucket(const PreparedRay& pr) {
-    const float3 o = pr.pos + pr.tNear * pr.dir;
-    const int cx = (int)(o.x * 0.0625f), cy = (int)(o.y * 0.0625f), cz = (int)(o.z * 0.0625f);
-    const float inv = 1.f / (fabsf(pr.dir.x) + fabsf(pr.dir.y) + fabsf(pr.dir.z));
-    float u = pr.dir.x * inv, v = pr.dir.y * inv;
-    if (pr.dir.z < 0.f) { const float tu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f), tv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f); u = tu; v = tv; }
-    const int ub = min(15, max(0, (int)((u * 0.5f + 0.5f) * 16.f))), vb = min(15, max(0, (int)((v * 0.5f + 0.5f) * 16.f)));
-    const unsigned h = ((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u);
-    return ((unsigned)(ub * 16 + vb) << 8) | ((h >> 7) & 0xFFu);
-}
 // Append one prepared task per lane with `want` to a stream; every lane of the warp must call (one atomic per warp).
 // missValue: what a ray that misses the volume box leaves in its result slot (transmittance 1; kRayTMax for a distance task)
 VRD void wfEmitRay(const WfStream& s, bool want, const Ray& rW, int mip, bool vertexCenter, float* results, unsigned out, float missValue = 1.f) {

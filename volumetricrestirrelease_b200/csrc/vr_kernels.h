@@ -17,8 +17,7 @@ cudaError_t launchImportanceMip(const float* src, float* dst, int d, cudaStream_
 cudaError_t uploadSceneWavefront(const DScene& s, cudaStream_t st);
 cudaError_t uploadPrevCamWavefront(const DPrevCam& s, cudaStream_t st);
 int marchBlocksPerSM(int nt);
-cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st, const unsigned* perm = nullptr);
-cudaError_t launchBucketOrder(const WfStream& s, const unsigned* hist, unsigned* binCursor, unsigned* perm, int blocks, cudaStream_t st);
+cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st);
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st);
 int analyticBlocksPerSM();
 cudaError_t launchMarchAnalytic(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int blocks, cudaStream_t st);

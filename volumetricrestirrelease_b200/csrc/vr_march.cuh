@@ -650,10 +650,8 @@ struct DistanceMarcher : MarchTrav {
 
 // Persistent-lane pool over one task stream.  tasks: 3 (explicit, prepared) or 2 (camera) x uint4 per task; total: tasks in
 // the stream; cursor: next unclaimed.
-// perm (nullable): the order in which the tasks are claimed (bucket order, k_bin_scatter); identity otherwise
 template <class M>
-__device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g,
-                                          const unsigned* __restrict__ perm = nullptr) {
+__device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -672,7 +670,7 @@ __device__ __forceinline__ void marchPool(const uint4* __restrict__ tasks, unsig
                 base = __shfl_sync(FULL, base, 0);
                 if (m.phase < 2) {
                     const unsigned idx = base + __popc(parked & ltMask);
-                    if (idx < total) m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g, results);
+                    if (idx < total) m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * idx, kind, g, results);
                 }
                 if (base + n >= total) drained = true;
             }
@@ -820,7 +818,7 @@ template <class T> struct MarcherTraits { static constexpr bool kImplicit = fals
 template <> struct MarcherTraits<DistanceMarcherQ> { static constexpr bool kImplicit = true; };
 template <class MQ, class Ctx = int>
 __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsigned total, unsigned* cursor, float* results, const MarchKind& kind, const DSlot& g,
-                                           const unsigned* __restrict__ perm, uint2* qBase, const Ctx* ctx = nullptr) {
+                                           uint2* qBase, const Ctx* ctx = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -846,7 +844,7 @@ __device__ __forceinline__ void marchPoolQ(const uint4* __restrict__ tasks, unsi
                     if (idx < total) {
                         bool have = true;
                         if constexpr (MarcherTraits<MQ>::kImplicit) have = m.setupIndex(idx, kind, g, *ctx);
-                        else m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * (perm ? __ldg(perm + idx) : idx), kind, g, results);
+                        else m.setup(tasks + (size_t)(kind.originMode == 0 ? 3 : 2) * idx, kind, g, results);
                         if (have) { m.live = true; m.inBrick = false; m.cdone = false; m.qh = m.qt = 0; }
                     }
                 }

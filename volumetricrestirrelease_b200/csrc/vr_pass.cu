@@ -144,10 +144,8 @@ struct vrestir_pass {
     bool mUseWavefront = true;
     int mInitialMode = 1;   // K1: 0 per-pixel kernel, 1 lock-step wavefront (default)
     uint4* wfCamTasks = nullptr; uint4* wfLightTasks = nullptr; float* wfResults = nullptr; unsigned* wfCounters = nullptr;
-    // "mSortLightTasks": K3's light marches run in coherence-bucket order (counting sort: histogram from the gather kernel)
     // off by default — measured: 13.2 -> 13.8 lanes per instruction, light march 1.67 -> 1.61 ms, the sort itself 0.17 ms: a net loss
     // (profiles/r02_sorted_light_marches.txt)
-    bool mSortLightTasks = false; unsigned* wfBins = nullptr; unsigned* wfPerm = nullptr;
     // "mPrimaryDistanceEngine": K1's free-flight sampling along the camera rays runs on the march engine (point sampler) instead of the per-pixel traversal kernel
     bool mPrimaryDistanceEngine = true; int primaryBlocks = 0;
     size_t wfPixels = 0;
@@ -203,14 +201,11 @@ int ensureWavefront(vrestir_pass* p) {
     if (p->wfCamTasks) cudaFree(p->wfCamTasks);
     if (p->wfLightTasks) cudaFree(p->wfLightTasks);
     if (p->wfResults) cudaFree(p->wfResults);
-    if (p->wfPerm) cudaFree(p->wfPerm);
-    p->wfCamTasks = p->wfLightTasks = nullptr; p->wfResults = nullptr; p->wfPerm = nullptr; p->wfPixels = 0;
+    p->wfCamTasks = p->wfLightTasks = nullptr; p->wfResults = nullptr; p->wfPixels = 0;
     if (n * 12 >= (1ull << 32) || n * WF_BLOCK >= (1ull << 32)) return setError(VRESTIR_ERR_INVALID_ARGUMENT, "row band too large for 32-bit task indices; shard the frame");
     CK(cudaMalloc(&p->wfCamTasks, n * 4 * 32));
     CK(cudaMalloc(&p->wfLightTasks, n * 12 * 48));   // explicit (prepared) tasks are 48 B
     CK(cudaMalloc(&p->wfResults, n * WF_BLOCK * sizeof(float)));
-    CK(cudaMalloc(&p->wfPerm, n * 12 * sizeof(unsigned)));
-    if (!p->wfBins) CK(cudaMalloc(&p->wfBins, 2 * VR_RAY_BUCKETS * sizeof(unsigned)));   // histogram | bin cursors
     if (!p->wfCounters) CK(cudaMalloc(&p->wfCounters, 128));   // 32 counters: two chains x {stream count / cursor pairs}
     p->wfPixels = n;
     if (!p->marchBlocks1) {
@@ -224,7 +219,6 @@ WfBufs wfView(const vrestir_pass* p) {
     w.cam.tasks = p->wfCamTasks; w.cam.count = p->wfCounters; w.cam.cursor = p->wfCounters + 1; w.cam.capacity = (unsigned)(p->wfPixels * 4);
     w.light.tasks = p->wfLightTasks; w.light.count = p->wfCounters + 2; w.light.cursor = p->wfCounters + 3; w.light.capacity = (unsigned)(p->wfPixels * 12);
     w.results = p->wfResults;
-    w.lightHist = p->mSortLightTasks ? p->wfBins : nullptr;
     return w;
 }
 // the wavefront forms cover the default option family (single bounce, ray-marched p-hat under the spatial options);
@@ -1008,16 +1002,14 @@ int runStageBody(vrestir_pass* p, int stage, int arg, float* out_color, float* o
                     rc = ensureWavefront(p); if (rc) return rc;
                     const WfBufs wf = wfView(p);
                     CK(cudaMemsetAsync(p->wfCounters, 0, 16, st));
-                    if (wf.lightHist) CK(cudaMemsetAsync(wf.lightHist, 0, VR_RAY_BUCKETS * sizeof(unsigned), st));
                     CK(launchSpatialGather(fp, wf, st));
-                    if (wf.lightHist) { CK(launchBucketOrder(wf.light, wf.lightHist, p->wfBins + VR_RAY_BUCKETS, p->wfPerm, p->marchBlocks1 / 2, st)); p->launches += 2; }
                     MarchKind kc, kl;
                     wavefrontKinds(p, kc, kl);
                     for (auto& e : p->evMarch) if (!e) CK(cudaEventCreate(&e));
                     CK(cudaEventRecord(p->evMarch[0], st));
                     CK(launchMarch(wf.cam, wf.results, kc, p->scene.slots[kc.mip], 3, p->marchBlocks3, st));
                     CK(cudaEventRecord(p->evMarch[1], st));
-                    CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st, wf.lightHist ? p->wfPerm : nullptr));
+                    CK(launchMarch(wf.light, wf.results, kl, p->scene.slots[kl.mip], 1, p->marchBlocks1, st));
                     CK(cudaEventRecord(p->evMarch[2], st));
                     p->evMarchValid = true; p->marchChunksUsed = 0;
                     CK(cudaMemcpyAsync(p->wfCounters + 8, p->wfCounters, 4, cudaMemcpyDeviceToDevice, st));       // task counts of this round (diagnostics)
@@ -1200,7 +1192,7 @@ int vrestir_destroy(vrestir_pass* p) try {
     for (int i = 0; i < 4; i++) if (p->res[i]) cudaFree(p->res[i]);
     for (int i = 0; i < 4; i++) if (p->ext[i]) cudaFree(p->ext[i]);
     for (int i = 0; i < 3; i++) if (p->feat[i]) cudaFree(p->feat[i]);
-    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor[0], p->d_hostColor[1], p->d_hostMvec[0], p->d_hostMvec[1], p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfBins, p->wfPerm, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters, p->mbArena, p->mbCounters, p->d_marchCounts, p->k1mb.base, p->k1mb.counters, p->k1mbEval.base, p->k1mbEval.counters};
+    void* ptrs[] = {p->refColor, p->d_lut, p->d_lutPrev, p->d_env, p->d_importance, p->d_envAliasThr, p->d_envAliasRedirect, p->d_lights, p->d_tris, p->d_alias, p->d_aliasWeights, p->d_hostColor[0], p->d_hostColor[1], p->d_hostMvec[0], p->d_hostMvec[1], p->wfCamTasks, p->wfLightTasks, p->wfResults, p->wfCounters, p->wfInitialState, p->k1LightTasks, p->k1EvalTasks, p->k1Results, p->k1Counters, p->k5Tasks, p->k5Results, p->k5Counters, p->mbArena, p->mbCounters, p->d_marchCounts, p->k1mb.base, p->k1mb.counters, p->k1mbEval.base, p->k1mbEval.counters};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->hostStream) cudaStreamDestroy(p->hostStream);
@@ -1563,7 +1555,6 @@ int vrestir_update(vrestir_pass* p, const char* key, double value) try {
         else if (k == "mInitialMode") p->mInitialMode = (int)value;
         else if (k == "mOverlapFeatures") p->mOverlapFeatures = value != 0;
         else if (k == "mPipelineFrames") p->mPipelineFrames = (int)value;
-        else if (k == "mSortLightTasks") p->mSortLightTasks = value != 0;
         else if (k == "mPrimaryDistanceEngine") p->mPrimaryDistanceEngine = value != 0;
         else if (k == "mDebugPoisonResults") p->mDebugPoison = value != 0;
         else if (k == "mScratchBudgetMB") p->mScratchBudget = (size_t)std::max(1.0, value) << 20;

@@ -90,10 +90,7 @@ struct WfStream { uint4* tasks; unsigned* count; unsigned* cursor; unsigned capa
 // per-pixel result block (floats): D[i*4+j] density of tap i's sample seen from ray j, C[j*3+k] camera transmittance along
 // ray j to the depth of tap i (k = i - (i > j)), L[i*4+j] light transmittance from that point
 enum { WF_BLOCK = 48, WF_D = 0, WF_C = 16, WF_L = 28 };
-// lightHist (nullable): histogram over VR_RAY_BUCKETS coherence buckets of the light tasks, filled by the gather kernel when the
-// stream is to be marched in bucket order (mSortLightTasks)
-enum { VR_RAY_BUCKETS = 65536 };
-struct WfBufs { WfStream cam, light; float* results; unsigned* lightHist; };
+struct WfBufs { WfStream cam, light; float* results; };
 // K1 lock-step candidate state: K1_STRIDE floats per pixel (vr_wavefront.cu)
 enum { K1_WORDS = 20, K1_STRIDE = 80, K1_EVAL_BLOCK = 4, K5_BLOCK = 4 };   // K5_BLOCK: floats per pixel of K5's results (density, camera Tr, light Tr)   // K1_EVAL_BLOCK: floats per pixel of K1's p-hat results (density, camera Tr, light Tr)
 struct WfInitial { WfStream light; float* state; uint8_t* done; WfStream evalCam, evalLight; float* results; };

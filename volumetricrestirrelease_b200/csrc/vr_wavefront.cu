@@ -28,42 +28,13 @@ namespace vrd {
 #define VR_QUEUE_ENGINE 1
 #endif
 template <int NT, bool FAST>
-__global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march(const WfStream s, float* results, const MarchKind kind, const DSlot g, const unsigned* perm) {
+__global__ void __launch_bounds__(128, VR_MARCH_MINB) k_march(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
 #if VR_QUEUE_ENGINE
     __shared__ uint2 brickQueue[VR_QUEUE_DEPTH * 128];
-    marchPoolQ<RayMarcherQ<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, perm, brickQueue);
+    marchPoolQ<RayMarcherQ<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, brickQueue);
 #else
-    marchPool<RayMarcher<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, perm);
+    marchPool<RayMarcher<NT, FAST>>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
 #endif
-}
-// ---- bucket order of an explicit-task stream (counting sort over VR_RAY_BUCKETS coherence buckets; the histogram comes from
-// the emitting kernel, the key sits in the task's third word) ----
-__global__ void __launch_bounds__(1024) k_bin_scan(const unsigned* __restrict__ hist, unsigned* __restrict__ binCursor) {
-    __shared__ unsigned warpSums[32];
-    const int per = VR_RAY_BUCKETS / 1024;
-    const unsigned* h = hist + threadIdx.x * per;
-    unsigned local = 0;
-    for (int i = 0; i < per; i++) local += h[i];
-    unsigned incl = local;
-    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
-    if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned w = warpSums[threadIdx.x];
-        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += v; }
-        warpSums[threadIdx.x] = w;
-    }
-    __syncthreads();
-    unsigned run = incl - local + ((threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u);
-    unsigned* c = binCursor + threadIdx.x * per;
-    for (int i = 0; i < per; i++) { c[i] = run; run += h[i]; }
-}
-__global__ void __launch_bounds__(256) k_bin_scatter(const WfStream s, unsigned* __restrict__ binCursor, unsigned* __restrict__ perm) {
-    const unsigned total = min(*s.count, s.capacity);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned key = s.tasks[3 * (size_t)i + 2].y & (VR_RAY_BUCKETS - 1);
-        perm[atomicAdd(&binCursor[key], 1u)] = i;
-    }
 }
 #ifndef VR_ANALYTIC_MINB
 #define VR_ANALYTIC_MINB 8
@@ -74,7 +45,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const WfStream s, unsigned*
 __global__ void __launch_bounds__(128, VR_ANALYTIC_MINB) k_march_analytic(const WfStream s, float* results, const MarchKind kind, const DSlot g) {
 #if VR_QUEUE_ANALYTIC
     __shared__ uint2 brickQueue[VR_QUEUE_DEPTH * 128];
-    marchPoolQ<AnalyticMarcherQ>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, nullptr, brickQueue);
+    marchPoolQ<AnalyticMarcherQ>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g, brickQueue);
 #else
     marchPool<AnalyticMarcher>(s.tasks, min(*s.count, s.capacity), s.cursor, results, kind, g);
 #endif
@@ -210,11 +181,9 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
                 wfPrepare(sh, fp.spatial.lightingMipLevel, false, pr);
                 if (pos < wf.light.capacity) {
                     uint4* q = wf.light.tasks + 3 * (size_t)pos;
-                    unsigned bucket = 0;
-                    if (wf.lightHist) { bucket = rayBucket(pr); atomicAdd(&wf.lightHist[bucket], 1u); }
                     q[0] = make_uint4(__float_as_uint(pr.pos.x), __float_as_uint(pr.pos.y), __float_as_uint(pr.pos.z), __float_as_uint(pr.tNear));
                     q[1] = make_uint4(__float_as_uint(pr.dir.x), __float_as_uint(pr.dir.y), __float_as_uint(pr.dir.z), __float_as_uint(pr.tFar));
-                    q[2] = make_uint4(blkBase + WF_L + i * 4 + j, bucket, 0u, 0u);
+                    q[2] = make_uint4(blkBase + WF_L + i * 4 + j, 0u, 0u, 0u);
                 }
             }
             lightBase += __popc(bal);
@@ -1280,7 +1249,7 @@ __global__ void __launch_bounds__(128, VR_MBSTEP_MINB) k_initial_mb_step(FramePa
 __global__ void __launch_bounds__(128, VR_PRIMARY_MINB) k_march_primary_distance(const PrimaryDistanceCtx c, unsigned* cursor, const MarchKind kind, const DSlot g) {
     __shared__ uint2 brickQueue[VR_QUEUE_DEPTH * 128];
     const unsigned tilesX = (unsigned)(c.fp.W + 7) / 8u, tilesY = (unsigned)(c.fp.rowEnd - c.fp.rowBegin + 3) / 4u;
-    marchPoolQ<DistanceMarcherQ, PrimaryDistanceCtx>(nullptr, tilesX * tilesY * 32u, cursor, c.state, kind, g, nullptr, brickQueue, &c);
+    marchPoolQ<DistanceMarcherQ, PrimaryDistanceCtx>(nullptr, tilesX * tilesY * 32u, cursor, c.state, kind, g, brickQueue, &c);
 }
 
 // the engine form of the same (point sampler): one DistanceMarcher task per waiting pixel
@@ -1381,17 +1350,11 @@ int marchBlocksPerSM(int nt) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march<3, true>, 128, 0);
     return n > 0 ? n : 1;
 }
-// bucket order of the stream's tasks into perm[0, count): hist = the emitting kernel's histogram, binCursor = scratch (VR_RAY_BUCKETS words)
-cudaError_t launchBucketOrder(const WfStream& s, const unsigned* hist, unsigned* binCursor, unsigned* perm, int blocks, cudaStream_t st) {
-    k_bin_scan<<<1, 1024, 0, st>>>(hist, binCursor);
-    k_bin_scatter<<<blocks, 256, 0, st>>>(s, binCursor, perm);
-    return cudaGetLastError();
-}
-cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st, const unsigned* perm) {
+cudaError_t launchMarch(const WfStream& s, float* results, const MarchKind& kind, const DSlot& grid, int nt, int blocks, cudaStream_t st) {
     // FAST: trilinear sampler on a single-channel UNORM8 pool with the quad repack (every coarse / conservative mip)
     const bool fast = kind.linear && grid.format == VRESTIR_ATLAS_UNORM8 && grid.quads != nullptr;
-    if (nt == 1) { if (fast) k_march<1, true><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); else k_march<1, false><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); }
-    else { if (fast) k_march<3, true><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); else k_march<3, false><<<blocks, 128, 0, st>>>(s, results, kind, grid, perm); }
+    if (nt == 1) { if (fast) k_march<1, true><<<blocks, 128, 0, st>>>(s, results, kind, grid); else k_march<1, false><<<blocks, 128, 0, st>>>(s, results, kind, grid); }
+    else { if (fast) k_march<3, true><<<blocks, 128, 0, st>>>(s, results, kind, grid); else k_march<3, false><<<blocks, 128, 0, st>>>(s, results, kind, grid); }
     return cudaGetLastError();
 }
 cudaError_t launchSpatialGather(const FrameParams& fp, const WfBufs& wf, cudaStream_t st) { k_spatial_gather<<<gridForWf(fp), 128, 0, st>>>(fp, wf); return cudaGetLastError(); }

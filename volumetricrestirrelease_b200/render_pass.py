@@ -16,7 +16,7 @@ from . import _capi as capi
 kOutputChannels = {"accumulated_color": "RGBA32Float", "mvec": "RG32Float"}   # VR/VolumetricReSTIR.cpp:39-43
 
 TOP_LEVEL_KEYS = ("mOutputMotionVec", "mFreezeFrame", "volumeDensityScaleExtraControl", "volumeAlbedoExtraControl",
-                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mInitialMode", "mOverlapFeatures", "mPipelineFrames", "mPrefetchPriority", "mScratchBudgetMB", "mDebugPoisonResults", "mSortLightTasks", "mPrimaryDistanceEngine")
+                  "volumeAnisotropyExtraControl", "mEnvSamplerType", "mUseWavefront", "mInitialMode", "mOverlapFeatures", "mPipelineFrames", "mPrefetchPriority", "mScratchBudgetMB", "mDebugPoisonResults", "mPrimaryDistanceEngine")
 # accepted for script compatibility, camera / env-light animation and UI live outside the hot path
 IGNORED_KEYS = ("mCameraMoveScale", "mCameraForwardScale", "mCameraFrameInterval", "mCameraPauseInterval",
                 "mCameraShakeTotalRounds", "mCameraShakeRoundsBeforePause", "mCameraAnimationMode", "mAnimateEnvLight",
