@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128) k_spatial_gather(FrameParams fp, WfBufs w
                             PreparedRay pr;   // rays that miss the volume box are resolved here (transmittance 1)
                             if (wfPrepare(sh, fp.spatial.lightingMipLevel, false, pr)) lightBits |= 1u << (i * 4 + j);
                             else blk[WF_L + i * 4 + j] = 1.f;
-                        }
+                        } else blk[WF_L + i * 4 + j] = 1.f;   // invalid light sample: the consumer loads the slot (wfLoadEval)
                     }
                 } else if (j == 0) alive = false;   // p-hat on the centre ray is 0: the tap is dropped, no MIS terms
             }
@@ -223,8 +223,24 @@ VRD float3 wfFV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFram
 VRD float wfPHatV(const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, float density, float visibility, float lightTr) {
     return luminance(wfFV(tap, origin, dir, isLastFrame, false, density, visibility, lightTr));
 }
+// The three results of one evaluation, loading only the slots its producer defined: the camera transmittance exists when the density
+// is non-zero, the light transmittance when the sample is neither a background nor a self-emission sample (wfFV ignores the others)
+VRD void wfLoadEval(const Reservoir& tap, const float* pd, const float* pc, const float* pl, float& density, float& vis, float& lightTr) {
+    density = *pd; vis = 1.f; lightTr = 1.f;
+    if (density != 0.f) {
+        vis = *pc;
+        if (tap.depth != kRayTMax && tap.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) lightTr = *pl;
+    }
+}
+VRD float wfPHatE(const Reservoir& tap, float3 origin, float3 dir, bool isLastFrame, const float* e) {   // e: density, camera Tr, light Tr
+    float density, vis, lightTr;
+    wfLoadEval(tap, e, e + 1, e + 2, density, vis, lightTr);
+    return wfPHatV(tap, origin, dir, isLastFrame, density, vis, lightTr);
+}
 VRD float wfPHat(const Reservoir& tap, float3 origin, float3 dir, const float* blk, int i, int j) {
-    return wfPHatV(tap, origin, dir, false, blk[WF_D + i * 4 + j], blk[WF_C + j * 3 + (i - (i > j ? 1 : 0))], blk[WF_L + i * 4 + j]);
+    float density, vis, lightTr;
+    wfLoadEval(tap, blk + WF_D + i * 4 + j, blk + WF_C + j * 3 + (i - (i > j ? 1 : 0)), blk + WF_L + i * 4 + j, density, vis, lightTr);
+    return wfPHatV(tap, origin, dir, false, density, vis, lightTr);
 }
 // Gather side of one p-hat evaluation: density point query, then (when the sample can contribute) one camera march task
 // (explicit origin, threshold = tap.depth) and one light march task.  Result slots: out+0 density, out+1 camera Tr, out+2 light Tr.
@@ -245,6 +261,7 @@ VRD void wfEmitEval(bool want, const Reservoir& tap, float3 origin, float3 dir, 
             if (!bg && tap.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
                 float3 Ld;
                 hasLight = lightRayAndLd(makeMI(pW, -dir, true), tap.lightID, tap.lightUV, isLastFrame, sh, Ld);
+                if (!hasLight) results[out + 2] = 1.f;   // invalid light sample: no march, but the consumer loads the slot (wfLoadEval)
             }
         }
     }
@@ -544,7 +561,7 @@ __global__ void __launch_bounds__(128) k_initial_finish(FrameParams fp, WfInitia
     if (!(a.x > 0.f)) return;
     Reservoir r = loadReservoirRW(fp.cur, pixelId, 1);
     const float* blk = wi.results + (size_t)(pixelId - fp.rowBegin * fp.W) * K1_EVAL_BLOCK;
-    const float p_hat = wfPHatV(r, fp.camPos, tapRayDir(fp, x, y), false, blk[0], blk[1], blk[2]);
+    const float p_hat = wfPHatE(r, fp.camPos, tapRayDir(fp, x, y), false, blk);
     r.runningSum *= r.p_y == 0.f ? 0.f : p_hat / r.p_y;
     r.p_y = p_hat;
     fp.cur.p0[pixelId] = make_float4(r.runningSum, r.M, r.depth, r.p_y);
@@ -688,7 +705,7 @@ __global__ void __launch_bounds__(128, VR_TCOMB_MINB) k_temporal_combine(FramePa
             neighbor_py = taps[i].p_y;
             if (isnan(taps[i].runningSum) || isinf(taps[i].runningSum)) taps[i].runningSum = 0.f;
             if (i > 0 && taps[i].runningSum != 0.f) {   // resampleNeighbor
-                const float p_y_hat = wfPHatV(taps[i], ray.origin, ray.dir, false, blk[T2_E1], blk[T2_E1 + 1], blk[T2_E1 + 2]);
+                const float p_y_hat = wfPHatE(taps[i], ray.origin, ray.dir, false, blk + T2_E1);
                 float weight = p_y_hat / taps[i].p_y;
                 if (isinf(weight) || isnan(weight)) weight = 0.f;
                 taps[i].runningSum *= weight;
@@ -705,7 +722,7 @@ __global__ void __launch_bounds__(128, VR_TCOMB_MINB) k_temporal_combine(FramePa
                 else {
                     // i == 0, j == 1: taps[0] at depth centerPrevFrameDepth on the previous frame's ray
                     Reservoir tp = taps[i]; tp.depth = centerPrevFrameDepth;
-                    float p_y = wfPHatV(tp, c_prev.prevPos, dirPrev, true, blk[T2_E0], blk[T2_E0 + 1], blk[T2_E0 + 2]);
+                    float p_y = wfPHatE(tp, c_prev.prevPos, dirPrev, true, blk + T2_E0);
                     if (isinf(p_y) || isnan(p_y)) p_y = 0.f;
                     p_sum += p_y * correctedM;
                 }
@@ -738,11 +755,13 @@ __global__ void __launch_bounds__(128) k_final_gather(FrameParams fp, WfStream s
             const float3 pW = r.at(r.tMax);
             const float density = (bg || noReuse) ? 1.f : DensityWorldSpace(pW, 0);
             results[out] = density;
+            if (noReuse) results[out + 1] = 1.f;   // no camera march without reuse, but the consumer loads the slot (wfLoadEval)
             if (density != 0.f) {
                 hasCam = !noReuse;
                 if (!bg && cur.lightID != VRESTIR_SELF_EMISSION_LIGHT_ID) {
                     float3 Ld;
                     hasLight = lightRayAndLd(makeMI(pW, -r.dir, true), cur.lightID, cur.lightUV, false, sh, Ld);
+                    if (!hasLight) results[out + 2] = 1.f;   // (see wfEmitEval)
                 }
             }
         }
@@ -761,7 +780,9 @@ __global__ void __launch_bounds__(128) k_final_combine(FrameParams fp, const flo
     const Reservoir cur = loadReservoir(fp.cur, pixelId, 1);
     if (cur.runningSum > 0.f) {
         const bool noReuse = fp.noReuse != 0;
-        float3 col = wfFV(cur, fp.camPos, tapRayDir(fp, x, y), false, noReuse, blk[0], noReuse ? 1.f : blk[1], blk[2]);
+        float density, vis, lightTr;
+        wfLoadEval(cur, blk, blk + 1, blk + 2, density, vis, lightTr);
+        float3 col = wfFV(cur, fp.camPos, tapRayDir(fp, x, y), false, noReuse, density, noReuse ? 1.f : vis, lightTr);
         const float Wt = cur.p_y == 0.0f ? 1.f : cur.runningSum / (cur.p_y * cur.M);
         col = col * Wt;
         outputColor = outputColor + col;
