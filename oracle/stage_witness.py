@@ -1,0 +1,157 @@
+"""Stage-level witnesses (TEST INFRASTRUCTURE): the target function p-hat and the spatial-reuse pass, written from the reference's
+Slang and composed from the lower-level witnesses (march_witness: transmittance, point query, xoshiro; light_witness: env map,
+phase function) — not from oracle/vr_oracle.cpp or the CUDA kernels.  Single bounce, env-map light, ray-marched transmittances (the
+default option family).
+
+  camera ray                    F/Scene/Camera/Camera.slang:160-228 (computeRayPinholeScaled(pixel, 1, 0.5))
+  evaluate_F_ / evaluate_P_hat  VR/ReSTIRHelper.slang:91-200,426-441 + evaluate_L_in_volume :442-496 (env light)
+  option -> mip / sampler       VR/VolumetricReSTIR.cpp:455-500 (gSpatialSamplingOptions)
+  spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
+                                simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
+                                R2Params / round seeds VR/VolumetricReSTIR.cpp:452-455,674-680
+"""
+import math
+
+import numpy as np
+
+from . import light_witness as lw
+from .march_witness import Witness, Xoshiro
+
+F = np.float32
+K_RAY_TMAX = F(3.402823466e+38)
+SELF_EMISSION = -3
+
+
+class Frame:
+    """Scene + options + camera of one frame, with the per-mip march witnesses cached."""
+
+    def __init__(self, scene, params, width, height):
+        self.sc, self.P, self.w, self.h = scene, params, width, height
+        self.grid = scene.volume.grid.contents
+        cam = scene.camera.data(width, height)
+        self.origin = np.array(cam.posW[:], dtype=F)
+        self.U, self.V, self.Wv = (np.array(getattr(cam, k)[:], dtype=F) for k in ("cameraU", "cameraV", "cameraW"))
+        self._wit = {}
+
+    def wit(self, mip):
+        if mip not in self._wit:
+            self._wit[mip] = Witness(self.grid, mip)
+        return self._wit[mip]
+
+    def ray_dir(self, px, py):
+        p = np.array([(F(px) + F(0.5)) / F(self.w), (F(py) + F(0.5)) / F(self.h)], dtype=F)
+        ndc = np.array([F(2) * p[0] + F(-1), F(-2) * p[1] + F(1)], dtype=F)
+        d = ndc[0] * self.U + ndc[1] * self.V + self.Wv
+        return (d / np.sqrt(np.dot(d, d))).astype(F)
+
+    def p_hat(self, d, depth, light_uv, light_id):
+        """luminance(evaluate_F_) of a single-bounce sample (depth along direction d from the camera, env light stored as (uv, id))."""
+        P, vol = self.P, self.grid.volume
+        o = self.origin
+        vis_lin, lig_lin = bool(P.mSpatialVisibilityUseLinearSampler), bool(P.mSpatialLightingUseLinearSampler)
+        if depth == K_RAY_TMAX:
+            vis = F(self.wit(P.mSpatialVisibilityMipLevel).ray_marching(o, d, float(K_RAY_TMAX), vis_lin, P.mSpatialVisibilityTStepScale))
+            return F(lw.luminance(vis * lw.env_eval(self.sc.envMap, d, self.sc.envMapIntensity)))
+        pw = (o + d * F(depth)).astype(F)
+        density = self.wit(0).density_world(pw)
+        if density == 0:
+            return F(0)
+        vis = F(self.wit(P.mSpatialVisibilityMipLevel).ray_marching(o, d, float(depth), vis_lin, P.mSpatialVisibilityTStepScale))
+        Fv = (vis * density * np.array(vol.sigma_s[:], dtype=F)).astype(F)
+        if not bool(np.any(Fv > 0)):
+            return F(lw.luminance(Fv))
+        if light_id == SELF_EMISSION or light_id >= 0:
+            raise NotImplementedError("witness covers env-map lights")
+        zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
+        z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
+        wi = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
+        Ld = lw.env_eval(self.sc.envMap, wi, self.sc.envMapIntensity) * F(lw.phase_hg(float(np.dot(-d, wi)), vol.PhaseFunctionConstantG))
+        tr = F(self.wit(P.mSpatialLightingMipLevel).ray_marching(pw, wi, float(K_RAY_TMAX), lig_lin, P.mSpatialLightingTStepScale))
+        return F(lw.luminance((Fv * (tr * Ld)).astype(F)))
+
+
+def neighbor_offset(P, sample_id, frame_id):
+    """generateNeighborOffset, R2 sequence (fp64 multiplier) + sample_disk, truncated to int2."""
+    if sample_id == 0:
+        u = (F(0), F(0))
+    else:
+        m = float(frame_id * P.mSpatialSampleCount + sample_id)
+        u = (F((0.754877669 * m) % 1.0), F((0.569840296 * m) % 1.0))
+    r = np.sqrt(u[0]).astype(F)
+    phi = F(6.28318530717958647692) * u[1]
+    px, py = F(r * np.cos(phi).astype(F)), F(r * np.sin(phi).astype(F))
+    rad = F(P.mSampleRadius)
+    return int(np.trunc(rad * px)), int(np.trunc(rad * py))
+
+
+def _resample_step(tap, state, rng):
+    """simpleResampleStep: tap / state are dicts with runningSum, M, depth, p_y, lightUV, lightID, sampledPixel."""
+    w = tap["runningSum"]
+    state["M"] = F(state["M"] + tap["M"])
+    if not w > 0:
+        return False
+    state["runningSum"] = F(state["runningSum"] + w)
+    sel = bool(rng.next1d() * state["runningSum"] < w)
+    if sel:
+        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel"):
+            state[k] = tap[k]
+    return sel
+
+
+def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0):
+    """SpatialReuse.cs.slang main() for one pixel (Talbot MIS or none, R2 sampler).  res_in: (H, W) structured reservoirs;
+    features: (H, W) structured {noReflectiveSurface, transmittance}.  Returns the output reservoir as a dict."""
+    P, w, h = frame.P, frame.w, frame.h
+    talbot = P.mSpatialMISMethod == 1
+    rec = lambda r: dict(runningSum=F(r["runningSum"]), M=F(r["M"]), depth=F(r["depth"]), p_y=F(r["p_y"]),
+                         lightUV=np.array(r["lightUV"], dtype=F), lightID=int(r["lightID"]), sampledPixel=int(r["sampledPixel"]))
+    r2_seed = ((P.mSpatialReuseRounds + 1) * frame_count + round_id) % 16
+    round_offset = int(bool(P.mEnableTemporalReuse)) + 1
+    num_rounds = P.mSpatialReuseRounds + round_offset + 1
+    rng = Xoshiro(px, py, num_rounds * frame_count + round_id + round_offset)
+    center = rec(res_in[py, px])
+    if features[py, px]["transmittance"] == 1.0:          # IsSelfBackground: passed through
+        return center
+    output = dict(runningSum=F(0), M=F(0), depth=K_RAY_TMAX, p_y=F(0), lightUV=np.zeros(2, F), lightID=0, sampledPixel=0) if talbot else center
+    d0 = frame.ray_dir(px, py)
+    S = P.mSpatialSampleCount
+    offs = [neighbor_offset(P, s, r2_seed) for s in range(S)]
+    inside = lambda x, y: 0 <= x < w and 0 <= y < h
+    for s in range(0 if talbot else 1, S):
+        tx, ty = px + offs[s][0], py + offs[s][1]
+        if not inside(tx, ty):
+            continue
+        tap = rec(res_in[ty, tx])
+        neighbor_py = tap["p_y"]
+        if s > 0 and tap["runningSum"] != 0:            # resampleNeighborSpatialReuse
+            ph = frame.p_hat(d0, tap["depth"], tap["lightUV"], tap["lightID"])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                weight = F(ph / tap["p_y"])
+            if np.isinf(weight) or np.isnan(weight):
+                weight = F(0)
+            tap["runningSum"] = F(tap["runningSum"] * weight)
+            tap["p_y"] = ph
+        mis = F(1)
+        if talbot and tap["runningSum"] > 0:
+            p_sum, p_qi, k = F(0), F(0), F(0)
+            for j in range(S):
+                jx, jy = px + offs[j][0], py + offs[j][1]
+                if not inside(jx, jy):
+                    continue
+                tap2 = res_in[jy, jx]
+                m2 = F(tap2["M"])
+                k = F(k + m2)
+                if j == 0:
+                    p_qi = tap["p_y"]; p_sum = F(p_sum + tap["p_y"] * m2)
+                elif s == j:
+                    p_qi = F(tap2["p_y"]); p_sum = F(p_sum + F(tap2["p_y"]) * m2)
+                else:
+                    p_y = frame.p_hat(frame.ray_dir(jx, jy), tap["depth"], tap["lightUV"], tap["lightID"])
+                    if np.isinf(p_y) or np.isnan(p_y):
+                        p_y = F(0)
+                    p_sum = F(p_sum + p_y * m2)
+            if p_sum > 0:
+                mis = F(p_qi * k / p_sum)
+        tap["runningSum"] = F(tap["runningSum"] * mis)
+        _resample_step(tap, output, rng)
+    return output

@@ -150,6 +150,11 @@ class OraclePass:
             else:
                 check(lib().vro_update(self._h, k.encode(), float(v)))
 
+    def frame_count(self):
+        fc = C.c_int()
+        check(lib().vro_get_frame_count(self._h, C.byref(fc)))
+        return fc.value
+
     def set_frame_count(self, fc, acc=1):
         check(lib().vro_set_frame_count(self._h, fc, acc))
 

@@ -1,0 +1,50 @@
+"""The oracle's spatial-reuse pass (K3: neighbour offsets, resampling at the centre ray, Talbot MIS over all taps, weighted reservoir
+streaming with the pixel's random-number stream) against oracle/stage_witness.py, a Python restatement written from
+VR/SpatialReuse.cs.slang on top of the independent transmittance / light / RNG witnesses."""
+import numpy as np
+import pytest
+
+from common import FEAT, RES, env_scene
+from oracle import stage_witness as sw
+from oracle import vro
+from volumetricrestirrelease_b200 import VolumetricReSTIRParams, capi
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(mSpatialMISMethod=capi.kMISNone, mSampleRadius=6.0, mSpatialSampleCount=3)])
+def test_spatial_reuse_matches_the_slang_witness(kw):
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.06, env_size=(128, 64))
+    params = VolumetricReSTIRParams(**kw)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()                                                 # frame 0 (fills the history)
+    frame_count = op.frame_count()
+    for stage in (0, 1, 2):
+        op.execute_stage(stage, 0, color)
+    res_in = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    feat = op.get_buffer(capi.BUF_FEATURES).view(FEAT).reshape(h, w).copy()
+    op.execute_stage(3, 0, color)
+    res_out = op.get_buffer(capi.BUF_RESERVOIR_1).view(RES).reshape(h, w)
+    frame = sw.Frame(sc, params, w, h)
+    assert frame_count >= 1
+    rng = np.random.default_rng(11)
+    ys, xs = np.nonzero(feat["transmittance"] != 1.0)
+    checked = changed = 0
+    for k in rng.permutation(len(ys))[:9]:
+        x, y = int(xs[k]), int(ys[k])
+        got = res_out[y, x]
+        want = sw.spatial_reuse_pixel(frame, res_in, feat, x, y, frame_count)
+        assert int(got["lightID"]) == want["lightID"] and int(got["sampledPixel"]) == want["sampledPixel"], (x, y)
+        assert float(got["M"]) == float(want["M"]) and float(got["depth"]) == float(want["depth"]), (x, y)
+        assert np.array_equal(np.asarray(got["lightUV"], np.float32), want["lightUV"]), (x, y)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=5e-5, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
+        checked += 1
+        changed += float(got["depth"]) != float(res_in[y, x]["depth"])
+    assert checked == 9 and changed >= 2                     # some pixels ended up with a neighbour's sample
+    # a pixel whose ray misses the medium passes through
+    bys, bxs = np.nonzero(feat["transmittance"] == 1.0)
+    if len(bys):
+        x, y = int(bxs[0]), int(bys[0])
+        assert res_out[y, x] == res_in[y, x]
