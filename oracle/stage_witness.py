@@ -6,6 +6,9 @@ default option family).
   camera ray                    F/Scene/Camera/Camera.slang:160-228 (computeRayPinholeScaled(pixel, 1, 0.5))
   evaluate_F_ / evaluate_P_hat  VR/ReSTIRHelper.slang:91-200,426-441 + evaluate_L_in_volume :442-496 (env light)
   option -> mip / sampler       VR/VolumetricReSTIR.cpp:455-500 (gSpatialSamplingOptions)
+  initial candidates (K1)       VR/TraceRays.cs.slang:64-183, VR/ComputeInitialSample.slang:4-395 (one bounce), SampleDirectLighting /
+                                sampleSceneLights VR/VolumeUtils.slang:12-66,454-492 (env-map light), gInitialSamplingOptions
+                                VR/VolumetricReSTIR.cpp:457-470
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
                                 R2Params / round seeds VR/VolumetricReSTIR.cpp:452-455,674-680
@@ -155,3 +158,91 @@ def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0
         tap["runningSum"] = F(tap["runningSum"] * mis)
         _resample_step(tap, output, rng)
     return output
+
+
+def _new_reservoir():
+    return dict(runningSum=F(0), M=F(0), depth=K_RAY_TMAX, p_y=F(0), lightUV=np.zeros(2, F), lightID=0, sampledPixel=0)
+
+
+def _initial_candidate(frame, d, hd, pd, tr, rng, mips):
+    """ComputeInitialSample for one bounce: the candidate at distance hd along the camera ray (pdf pd, transmittance tr)."""
+    P, vol, o = frame.P, frame.grid.volume, frame.origin
+    out = _new_reservoir()
+    out["M"] = F(1)
+    valid = hd != K_RAY_TMAX
+    path_pdf = F(F(1) * pd)
+    out["depth"] = hd if valid else K_RAY_TMAX
+    out["p_y"] = path_pdf
+    sig_s, sig_a = np.array(vol.sigma_s[:], dtype=F), np.array(vol.sigma_a[:], dtype=F)
+    if valid:
+        pw = (o + d * hd).astype(F)
+        density = frame.wit(0).density_world(pw)
+        if density == 0:
+            out["p_y"] = F(0); out["runningSum"] = F(0)
+            return out
+        albedo = (sig_s / F(vol.sigma_t)).astype(F)
+        # SampleDirectLighting -> sampleSceneLights (env lights only: the selection draw always picks them)
+        rng.next1d()
+        u0 = rng.next1d(); u1 = rng.next1d()
+        wi, pdf, _ = lw.env_sample(mips, u0, u1)
+        pdf = F(F(1) * F(pdf))
+        Le = lw.env_eval(frame.sc.envMap, wi, frame.sc.envMapIntensity)
+        Li = (Le / pdf).astype(F) if pdf > 0 else np.zeros(3, F)
+        out["lightID"] = -2 if wi[2] < 0 else -1
+        out["lightUV"] = np.array([wi[0], wi[1]], dtype=F)
+        light_pdf = pdf
+        if bool(np.any(np.isnan(wi))):
+            light_pdf, Ld = F(0), np.zeros(3, F)
+        else:
+            if P.mInitialLightSamples != 0:
+                vis = F(frame.wit(P.mInitialLightingMipLevel).ray_marching(pw, wi, float(K_RAY_TMAX), bool(P.mInitialLightingUseLinearSampler), P.mInitialLightingTStepScale))
+                Li = (Li * vis).astype(F)
+            Ld = (F(lw.phase_hg(float(np.dot(-d, wi)), vol.PhaseFunctionConstantG)) * Li / F(1)).astype(F)
+        p_src = out["p_y"]
+        lum_e = lw.luminance(((F(1) - albedo) * np.zeros(3, F)).astype(F))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = F(lum_e / (lum_e + lw.luminance((albedo * Ld).astype(F))))
+        if np.isnan(ratio):
+            ratio = F(0)
+        if rng.next1d() < ratio:
+            p_src = F(p_src * ratio); out["lightID"] = SELF_EMISSION
+        else:
+            p_src = F(p_src * (light_pdf * (F(1) - ratio)))
+        out["runningSum"] = F(0) if p_src == 0 else F(1)
+        out["p_y"] = p_src
+        path_phat = F(F(F(1) * tr) * density)
+        p_y = F(path_phat * lw.luminance(((sig_s * Ld) * light_pdf).astype(F)))
+        if out["runningSum"] > 0:
+            out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
+            out["p_y"] = p_y
+    else:
+        Le = lw.env_eval(frame.sc.envMap, d, frame.sc.envMapIntensity)
+        p_y = F(F(F(1) * tr) * lw.luminance(Le))
+        out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
+        out["p_y"] = p_y
+    return out
+
+
+def initial_sampling_pixel(frame, px, py, frame_count, importance_mips):
+    """TraceRays.cs.slang main() for one pixel (one bounce, reuse on, env-map light): M candidates by free-flight sampling along the
+    camera ray, each with one importance-sampled env direction and its ray-marched shadow, streamed through a reservoir; then the
+    p-hat of the streamed sample under the spatial options replaces the candidate-time target.  Returns the stored reservoir."""
+    P = frame.P
+    total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
+    rng = Xoshiro(px, py, total_rounds * frame_count)
+    d = frame.ray_dir(px, py)
+    final = _new_reservoir()
+    linear = bool(P.mInitialVisibilityUseLinearSampler)
+    vis_mip = P.mInitialBaseMipLevel if linear else P.mInitialBaseMipLevel + 8
+    rounds = (P.mInitialM + 3) // 4
+    for r in range(rounds):
+        n = P.mInitialM - 4 * (rounds - 1) if r == rounds - 1 else 4
+        hd, pd, ot = frame.wit(vis_mip).sample_distances(frame.origin, d, n, linear, rng)
+        for s in range(n):
+            cand = _initial_candidate(frame, d, F(hd[s]), F(pd[s]), F(ot[s]), rng, importance_mips)
+            _resample_step(cand, final, rng)
+    p_hat = frame.p_hat(d, final["depth"], final["lightUV"], final["lightID"])
+    if final["runningSum"] > 0:
+        final["runningSum"] = F(final["runningSum"] * (F(0) if final["p_y"] == 0 else F(p_hat / final["p_y"])))
+        final["p_y"] = p_hat
+    return final
