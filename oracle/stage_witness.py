@@ -9,6 +9,7 @@ default option family).
   initial candidates (K1)       VR/TraceRays.cs.slang:64-183, VR/ComputeInitialSample.slang:4-395 (one bounce), SampleDirectLighting /
                                 sampleSceneLights VR/VolumeUtils.slang:12-66,454-492 (env-map light), gInitialSamplingOptions
                                 VR/VolumetricReSTIR.cpp:457-470
+  final shading (K5)            VR/FinalShading.cs.slang:95-141, finalOptions VR/VolumetricReSTIR.cpp:484-496
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
                                 R2Params / round seeds VR/VolumetricReSTIR.cpp:452-455,674-680
@@ -47,30 +48,51 @@ class Frame:
         d = ndc[0] * self.U + ndc[1] * self.V + self.Wv
         return (d / np.sqrt(np.dot(d, d))).astype(F)
 
-    def p_hat(self, d, depth, light_uv, light_id):
-        """luminance(evaluate_F_) of a single-bounce sample (depth along direction d from the camera, env light stored as (uv, id))."""
-        P, vol = self.P, self.grid.volume
+    def _transmittance(self, final, which, origin, direction, tmax):
+        """Ray-marched under the spatial options; exact transmittance of the trilinear mip-0 interpolant (analytic tracking, the
+        default of the final shading, VR/VolumetricReSTIR.cpp:484-496) when `final`."""
+        P = self.P
+        if final:
+            return F(self.wit(0).analytic(origin, direction, tmax, True))
+        if which == "camera":
+            return F(self.wit(P.mSpatialVisibilityMipLevel).ray_marching(origin, direction, tmax, bool(P.mSpatialVisibilityUseLinearSampler), P.mSpatialVisibilityTStepScale))
+        return F(self.wit(P.mSpatialLightingMipLevel).ray_marching(origin, direction, tmax, bool(P.mSpatialLightingUseLinearSampler), P.mSpatialLightingTStepScale))
+
+    def eval_F(self, d, depth, light_uv, light_id, final=False):
+        """evaluate_F_ of a single-bounce sample (depth along direction d from the camera, env light stored as (uv, id)): float3."""
+        vol = self.grid.volume
         o = self.origin
-        vis_lin, lig_lin = bool(P.mSpatialVisibilityUseLinearSampler), bool(P.mSpatialLightingUseLinearSampler)
         if depth == K_RAY_TMAX:
-            vis = F(self.wit(P.mSpatialVisibilityMipLevel).ray_marching(o, d, float(K_RAY_TMAX), vis_lin, P.mSpatialVisibilityTStepScale))
-            return F(lw.luminance(vis * lw.env_eval(self.sc.envMap, d, self.sc.envMapIntensity)))
+            vis = self._transmittance(final, "camera", o, d, float(K_RAY_TMAX))
+            return (vis * lw.env_eval(self.sc.envMap, d, self.sc.envMapIntensity)).astype(F)
         pw = (o + d * F(depth)).astype(F)
         density = self.wit(0).density_world(pw)
         if density == 0:
-            return F(0)
-        vis = F(self.wit(P.mSpatialVisibilityMipLevel).ray_marching(o, d, float(depth), vis_lin, P.mSpatialVisibilityTStepScale))
+            return np.zeros(3, F)
+        vis = self._transmittance(final, "camera", o, d, float(depth))
         Fv = (vis * density * np.array(vol.sigma_s[:], dtype=F)).astype(F)
         if not bool(np.any(Fv > 0)):
-            return F(lw.luminance(Fv))
+            return Fv
         if light_id == SELF_EMISSION or light_id >= 0:
             raise NotImplementedError("witness covers env-map lights")
         zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
         z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
         wi = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
         Ld = lw.env_eval(self.sc.envMap, wi, self.sc.envMapIntensity) * F(lw.phase_hg(float(np.dot(-d, wi)), vol.PhaseFunctionConstantG))
-        tr = F(self.wit(P.mSpatialLightingMipLevel).ray_marching(pw, wi, float(K_RAY_TMAX), lig_lin, P.mSpatialLightingTStepScale))
-        return F(lw.luminance((Fv * (tr * Ld)).astype(F)))
+        tr = self._transmittance(final, "light", pw, wi, float(K_RAY_TMAX))
+        return (Fv * (tr * Ld)).astype(F)
+
+    def p_hat(self, d, depth, light_uv, light_id):
+        return F(lw.luminance(self.eval_F(d, depth, light_uv, light_id)))
+
+    def final_shading(self, px, py, r):
+        """FinalShading.cs.slang:95-141 for one pixel: F of the stored sample under the final options times the RIS weight W."""
+        if not r["runningSum"] > 0:
+            return np.zeros(3, F)
+        col = self.eval_F(self.ray_dir(px, py), F(r["depth"]), np.asarray(r["lightUV"], dtype=F), int(r["lightID"]), final=True)
+        W = F(1) if r["p_y"] == 0 else F(F(r["runningSum"]) / F(F(r["p_y"]) * F(r["M"])))
+        out = (col * W).astype(F)
+        return np.zeros(3, F) if bool(np.any(np.isnan(out) | np.isinf(out))) else out
 
 
 def neighbor_offset(P, sample_id, frame_id):

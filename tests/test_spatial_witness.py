@@ -48,3 +48,32 @@ def test_spatial_reuse_matches_the_slang_witness(kw):
     if len(bys):
         x, y = int(bxs[0]), int(bys[0])
         assert res_out[y, x] == res_in[y, x]
+
+
+def test_final_shading_matches_the_slang_witness():
+    """K5: F of the stored sample under the final options (exact transmittance of the trilinear mip-0 interpolant for the camera and
+    the light ray) times the RIS weight runningSum / (p_y M), against the radiance the oracle wrote."""
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.06, env_size=(128, 64))
+    params = VolumetricReSTIRParams()
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    color = np.zeros((h, w, 4), np.float32)
+    for stage in (0, 1, 2, 3, 4):
+        op.execute_stage(stage, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_TEMPORAL).view(RES).reshape(h, w).copy()      # the frame's final reservoirs (history after K4)
+    op.execute_stage(5, 0, color)
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(2)
+    ys, xs = np.nonzero((res["runningSum"] > 0) & (res["depth"] < 1e37))
+    lit = 0
+    for k in rng.permutation(len(ys))[:10]:
+        x, y = int(xs[k]), int(ys[k])
+        want = frame.final_shading(x, y, res[y, x])
+        np.testing.assert_allclose(color[y, x, :3], want, rtol=5e-5, atol=1e-9)
+        lit += bool(want.sum() > 0)
+    assert lit >= 6
+    by, bx = np.nonzero((res["runningSum"] > 0) & (res["depth"] > 1e37))
+    for k in range(min(3, len(by))):
+        np.testing.assert_allclose(color[by[k], bx[k], :3], frame.final_shading(int(bx[k]), int(by[k]), res[by[k], bx[k]]), rtol=5e-5, atol=1e-9)
