@@ -374,6 +374,44 @@ class DistanceSamplingAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:210-437 (S
                 self.hit[i], self.outTr[i], self.pdf[i] = self.K_RAY_TMAX, F(1), F(1)
 
 
+class CellSamplingAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:439-515 (SampleVolumeCellByDensityAdapterGVDB)
+    """One voxel cell of the ray, chosen with probability proportional to exp(-optical depth so far) * sigma_t of the cell (weighted
+    reservoir sampling with one draw per cell whose running sum is positive): the reprojection point of K2 for background samples."""
+
+    def __init__(self, rng):
+        self.rng = rng
+        self.bound, self.interval, self.running, self.Tr = F(0), (F(-1), F(-1)), F(0), F(0)
+
+    def start(self):
+        self.interval = (F(-1), F(-1))
+
+    def main(self, W, dda, vmin_leaf, brick, t):
+        leaf = dda.copy()
+        leaf.prepare_leaf(vmin_leaf)
+        res0 = W.slot["res"][0]
+        it = 0
+        while it < MAX_BRICK_STEPS and bool(np.all((leaf.p >= 0) & (leaf.p < res0))):
+            density = W.density_in_atlas(brick, leaf.p.astype(F) + F(0.5), False)
+            leaf.next()
+            maxDeltaT = leaf.ty - t
+            sigma_t = density * W.sigma_t
+            weight = np.exp(self.Tr) * sigma_t
+            self.running = self.running + weight
+            if self.running > 0 and self.rng.next1d() < weight / self.running:
+                self.bound = density
+                self.interval = (t, min(self.tFar, t + maxDeltaT))
+            self.Tr = self.Tr + F(-maxDeltaT) * sigma_t
+            if t + maxDeltaT >= self.tFar:
+                return True, t
+            t = t + maxDeltaT
+            leaf.step()
+            it += 1
+        return False, t
+
+    def end(self):
+        pass
+
+
 class Witness:
     def __init__(self, grid_desc, slot_index):
         self.slot = slot_arrays(grid_desc.slots[slot_index])
@@ -520,6 +558,16 @@ class Witness:
                 a.outTr[i] = -np.log(F(1) - rng.next1d())
         self.track(origin_w, dir_w, DistanceSamplingAdapter.K_RAY_TMAX, a, linear)
         return [float(x) for x in a.hit], [float(x) for x in a.pdf], [float(x) for x in a.outTr]
+
+    def rejection_sample_point(self, origin_w, dir_w, rng):
+        """RejectionSampleRandomPointByDensity (VR/VolumeUtils.slang:572-581): a depth inside the selected cell, or kRayTMax."""
+        a = CellSamplingAdapter(rng)
+        self.track(origin_w, dir_w, DistanceSamplingAdapter.K_RAY_TMAX, a, False)
+        if a.interval[0] == F(-1):
+            return DistanceSamplingAdapter.K_RAY_TMAX
+        depth = a.interval[0] + (a.interval[1] - a.interval[0]) * rng.next1d()
+        rng.next1d()          # sampledY (unused)
+        return F(depth)
 
     def analytic(self, origin_w, dir_w, tmax, linear=True):
         a = AnalyticAdapter(linear)

@@ -9,6 +9,8 @@ default option family).
   initial candidates (K1)       VR/TraceRays.cs.slang:64-183, VR/ComputeInitialSample.slang:4-395 (one bounce), SampleDirectLighting /
                                 sampleSceneLights VR/VolumeUtils.slang:12-66,454-492 (env-map light), gInitialSamplingOptions
                                 VR/VolumetricReSTIR.cpp:457-470
+  temporal reuse (K2)           VR/TemporalReuse.cs.slang:80-377 (linear reprojection, Talbot MIS or none; no velocity grid),
+                                resampleNeighbor VR/ReSTIRHelper.slang:582-597, simpleResampleStepWithMaxM VR/Reservoir.slang:57-87
   final shading (K5)            VR/FinalShading.cs.slang:95-141, finalOptions VR/VolumetricReSTIR.cpp:484-496
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
@@ -268,3 +270,120 @@ def initial_sampling_pixel(frame, px, py, frame_count, importance_mips):
         final["runningSum"] = F(final["runningSum"] * (F(0) if final["p_y"] == 0 else F(p_hat / final["p_y"])))
         final["p_y"] = p_hat
     return final
+
+
+def _resample_step_max_m(tap, max_m, state, rng):
+    """simpleResampleStepWithMaxM."""
+    corrected = F(min(max_m, tap["M"]))
+    w = F(0) if corrected == 0 else F(F(corrected / tap["M"]) * tap["runningSum"])
+    state["M"] = F(state["M"] + corrected)
+    if not w > 0:
+        return False
+    state["runningSum"] = F(state["runningSum"] + w)
+    sel = bool(rng.next1d() * state["runningSum"] < w)
+    if sel:
+        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel"):
+            state[k] = tap[k]
+    return sel
+
+
+def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, frame_count, prev_cam=None):
+    """TemporalReuse.cs.slang main() for one pixel of a frame with history.  prev_cam: (posW, U, V, W, view[16], proj[16]) of the
+    previous frame (default: the current camera, i.e. a static camera).  Returns the reservoir K2 leaves in the current buffer."""
+    P, w, h = frame.P, frame.w, frame.h
+    rec = lambda r: dict(runningSum=F(r["runningSum"]), M=F(r["M"]), depth=F(r["depth"]), p_y=F(r["p_y"]),
+                         lightUV=np.array(r["lightUV"], dtype=F), lightID=int(r["lightID"]), sampledPixel=int(r["sampledPixel"]))
+    cam = frame.sc.camera.data(w, h)
+    if prev_cam is None:
+        prev_cam = (frame.origin, frame.U, frame.V, frame.Wv, np.array(cam.viewMat[:], dtype=F), np.array(cam.projMat[:], dtype=F))
+    p_pos, pU, pV, pW, p_view, p_proj = prev_cam
+    talbot = P.mTemporalMISMethod == 1
+    total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
+    rng = Xoshiro(px, py, total_rounds * frame_count + 1)          # gRoundOffset = numInitialSamplingRounds
+    taps = [rec(res_cur[py, px]), None]
+    d = frame.ray_dir(px, py)
+    o = frame.origin
+    output = _new_reservoir() if talbot else dict(taps[0])
+    is_bg = feat_cur[py, px]["transmittance"] == 1.0 and bool(feat_cur[py, px]["noReflectiveSurface"])
+    fallback, reproj = True, (0, 0)
+    if P.mTemporalReprojectionMode != 1:                          # != kReprojectionNone
+        depth = taps[0]["depth"]
+        if depth == K_RAY_TMAX and P.mTemporalReprojectionMode != 2 and not is_bg:
+            depth = frame.wit(8 + P.mTemporalReprojectionMipLevel).rejection_sample_point(o, d, rng)
+        pw = (o + d * depth).astype(F)
+        view = np.array([pw[0] * p_view[0 + j] + pw[1] * p_view[4 + j] + pw[2] * p_view[8 + j] + F(1) * p_view[12 + j] for j in range(4)], dtype=F)
+        clip = np.array([view[0] * p_proj[0 + j] + view[1] * p_proj[4 + j] + view[2] * p_proj[8 + j] + view[3] * p_proj[12 + j] for j in range(4)], dtype=F)
+        if depth == K_RAY_TMAX:
+            scr = (F(px) + F(0.5), F(py) + F(0.5)); scr_i = (px, py)
+        else:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sx, sy = F(clip[0] / clip[3]), F(clip[1] / clip[3])
+            scr = (F(F(F(0.5) * sx + F(0.5)) * F(w)), F(F(F(-0.5) * sy + F(0.5)) * F(h)))
+            scr_i = (int(np.trunc(scr[0])), int(np.trunc(scr[1])))
+        idx = (scr_i[1] * w + scr_i[0]) & 0xFFFFFFFF
+        tf = feat_prev.reshape(-1)[idx] if idx < w * h else None          # out-of-range structured-buffer reads return 0
+        tap_bg = tf is not None and tf["transmittance"] == 1.0 and bool(tf["noReflectiveSurface"])
+        if is_bg and not tap_bg:
+            return taps[0]                                            # K1's reservoir stays
+        scr_i = (int(np.trunc(scr[0])), int(np.trunc(scr[1])))
+        reproj = scr_i
+        if 0 <= scr_i[0] < w and 0 <= scr_i[1] < h:
+            taps[1] = rec(res_prev[scr_i[1], scr_i[0]]); fallback = False
+    if fallback:
+        reproj = (px, py); taps[1] = rec(res_prev[py, px])
+    max_prev_m = F(F(P.mTemporalReuseMThreshold) * taps[0]["M"])
+
+    def prev_dir(x, y):
+        p = np.array([(F(x) + F(0.5)) / F(w), (F(y) + F(0.5)) / F(h)], dtype=F)
+        ndc = np.array([F(2) * p[0] + F(-1), F(-2) * p[1] + F(1)], dtype=F)
+        v = ndc[0] * pU + ndc[1] * pV + pW
+        return (v / np.sqrt(np.dot(v, v))).astype(F)
+    temporal_original_depth = taps[1]["depth"]
+    if taps[1]["depth"] != K_RAY_TMAX:
+        world = (p_pos + taps[1]["depth"] * prev_dir(*reproj)).astype(F)
+        diff = world - o
+        taps[1]["depth"] = F(np.sqrt(np.dot(diff, diff)))
+    center_prev_depth = taps[0]["depth"]
+    if center_prev_depth != K_RAY_TMAX:
+        diff = (o + d * center_prev_depth).astype(F) - p_pos
+        center_prev_depth = F(np.sqrt(np.dot(diff, diff)))
+    saved_origin = frame.origin
+    for i in range(0 if talbot else 1, 2):
+        mis, neighbor_py = F(1), F(0)
+        if taps[i]["p_y"] > 0:
+            neighbor_py = taps[i]["p_y"]
+            if np.isnan(taps[i]["runningSum"]) or np.isinf(taps[i]["runningSum"]):
+                taps[i]["runningSum"] = F(0)
+            if i > 0 and taps[i]["runningSum"] != 0:               # resampleNeighbor on the current ray
+                ph = frame.p_hat(d, taps[i]["depth"], taps[i]["lightUV"], taps[i]["lightID"])
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    weight = F(ph / taps[i]["p_y"])
+                if np.isinf(weight) or np.isnan(weight):
+                    weight = F(0)
+                taps[i]["runningSum"] = F(taps[i]["runningSum"] * weight); taps[i]["p_y"] = ph
+        else:
+            taps[i]["p_y"] = F(0); taps[i]["runningSum"] = F(0)
+        if talbot and taps[i]["runningSum"] > 0:
+            p_sum, p_qi, k = F(0), F(0), F(0)
+            for j in range(2):
+                cm = F(min(max_prev_m, taps[j]["M"]))
+                k = F(k + cm)
+                if j == 0:
+                    p_qi = taps[i]["p_y"]; p_sum = F(p_sum + taps[i]["p_y"] * cm)
+                elif i == j:
+                    p_qi = neighbor_py; p_sum = F(p_sum + neighbor_py * cm)
+                else:                                             # i == 0, j == 1: the current sample seen from the previous frame's ray
+                    used_depth = center_prev_depth
+                    frame.origin = p_pos
+                    try:
+                        p_y = frame.p_hat(prev_dir(*reproj), used_depth, taps[i]["lightUV"], taps[i]["lightID"])
+                    finally:
+                        frame.origin = saved_origin
+                    if np.isinf(p_y) or np.isnan(p_y):
+                        p_y = F(0)
+                    p_sum = F(p_sum + p_y * cm)
+            if p_sum > 0:
+                mis = F(p_qi * k / p_sum)
+        taps[i]["runningSum"] = F(taps[i]["runningSum"] * mis)
+        _resample_step_max_m(taps[i], max_prev_m, output, rng)
+    return output

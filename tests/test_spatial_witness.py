@@ -77,3 +77,50 @@ def test_final_shading_matches_the_slang_witness():
     by, bx = np.nonzero((res["runningSum"] > 0) & (res["depth"] > 1e37))
     for k in range(min(3, len(by))):
         np.testing.assert_allclose(color[by[k], bx[k], :3], frame.final_shading(int(bx[k]), int(by[k]), res[by[k], bx[k]]), rtol=5e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("kw,move", [(dict(), False), (dict(mTemporalMISMethod=capi.kMISNone, mTemporalReuseMThreshold=2.0), False), (dict(), True)])
+def test_temporal_reuse_matches_the_slang_witness(kw, move):
+    """K2 on a frame with history: reprojection of the stored depth (or of a density-sampled point for a background sample) through
+    the previous frame's view-projection, resampling of the history sample on the current ray, Talbot MIS between the two samples,
+    M-capped reservoir streaming — static camera and a camera that moved between the frames."""
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.06, env_size=(128, 64))
+    params = VolumetricReSTIRParams(**kw)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    cam0 = sc.camera.data(w, h)
+    prev_cam = tuple(np.array(getattr(cam0, k)[:], dtype=np.float32) for k in ("posW", "cameraU", "cameraV", "cameraW", "viewMat", "projMat"))
+    if move:
+        pos = np.array(sc.camera.position); sc.camera.position = tuple(pos + np.array([0.25, -0.15, 0.1]))
+        op.updateCamera()
+    frame_count = op.frame_count()
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res_cur = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    res_prev = op.get_buffer(capi.BUF_RESERVOIR_TEMPORAL).view(RES).reshape(h, w).copy()
+    feat_cur = op.get_buffer(capi.BUF_FEATURES).view(FEAT).reshape(h, w).copy()
+    feat_prev = op.get_buffer(capi.BUF_FEATURES_TEMPORAL).view(FEAT).reshape(h, w).copy()
+    op.execute_stage(2, 0, color)
+    res_out = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w)
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(4)
+    vol = feat_cur["transmittance"] != 1.0
+    escaped = res_cur["depth"] > 1e30                 # K1 kept a background sample: K2 reprojects a density-sampled point of the ray
+    picks = []
+    for mask, n in ((vol & ~escaped, 8), (vol & escaped, 4)):
+        ys, xs = np.nonzero(mask)
+        assert len(ys) >= n
+        picks += [(int(xs[k]), int(ys[k])) for k in rng.permutation(len(ys))[:n]]
+    from_history = 0
+    for x, y in picks:
+        got = res_out[y, x]
+        want = sw.temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, x, y, frame_count, prev_cam)
+        assert int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        assert np.allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=1e-7), (x, y)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=1e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
+        from_history += float(got["M"]) > float(res_cur[y, x]["M"])
+    assert from_history >= 8            # the history really took part
