@@ -172,6 +172,41 @@ class RayMarchingAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:140-208
         self.Tr = np.exp(self.Tr) if self.initialized else F(1.0)
 
 
+class FeatureMarchAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:518-602 (ReservoirFeatureRayMarchingAdapterGVDB)
+    """K0's total camera-ray transmittance: the same stepping as RayMarchingAdapter without the far-end test, stopping once the
+    transmittance so far is below 1 %."""
+
+    def __init__(self, linear, tstep):
+        self.Tr, self.linear, self.tStep, self.initialized, self.accu = F(0), linear, F(tstep), False, F(1)
+
+    def start(self):
+        self.initialized = True
+
+    def main(self, W, dda, vmin_leaf, brick, t):
+        tS = self.tStep
+        t = self.tNear + (np.floor((t - self.tNear) / tS) + F(0.5)) * tS
+        if t < dda.tx:
+            t = t + tS
+        p = (self.ray_o + t * self.ray_d) - vmin_leaf
+        wpt = tS * self.ray_d
+        res = F(W.slot["res"][0])
+        it = 0
+        while it < MAX_BRICK_STEPS and bool(np.all((p >= 0) & (p < res))):
+            if np.exp(self.Tr) < F(0.01):
+                self.end()
+                return True, t
+            sigma_t = W.density_in_atlas(brick, p, self.linear) * W.sigma_t
+            self.Tr = self.Tr + F(-sigma_t) * tS
+            p = p + wpt
+            t = t + tS
+            it += 1
+        return False, t
+
+    def end(self):
+        if self.initialized:
+            self.accu = np.exp(self.Tr)
+
+
 class AnalyticAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:20-136
     def __init__(self, linear):
         self.Tr, self.linear = F(0), linear
@@ -548,6 +583,12 @@ class Witness:
         a = RayMarchingAdapter(linear, self.tStepBase * F(tstep_scale) * F(eff + 1))
         self.track(origin_w, dir_w, tmax, a, False)
         return float(a.Tr)
+
+    def feature_transmittance(self, origin_w, dir_w, tstep_scale=1.0, linear=True):
+        """ReservoirFeatureRayMarchingGeneric (VR/VolumeUtils.slang:366-380) on this mip."""
+        a = FeatureMarchAdapter(linear, self.tStepBase * F(tstep_scale))
+        self.track(origin_w, dir_w, DistanceSamplingAdapter.K_RAY_TMAX, a, False)
+        return float(a.accu)
 
     def sample_distances(self, origin_w, dir_w, num_samples, linear, rng):
         """SampleMediumAnalytic (VR/VolumeUtils.slang: the linear sampler draws its optical-depth targets first and walks the

@@ -4,7 +4,7 @@ free-flight sampling, the hierarchical env sampler, the phase function, transmit
 import numpy as np
 import pytest
 
-from common import RES, env_scene
+from common import FEAT, RES, env_scene
 from oracle import light_witness as lw
 from oracle import stage_witness as sw
 from oracle import vro
@@ -43,3 +43,29 @@ def test_initial_sampling_matches_the_slang_witness(kw):
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
         checked += 1; volume += float(got["depth"]) < 1e37
     assert checked == 12 and volume >= 6
+
+
+@pytest.mark.parametrize("kw,density", [(dict(), 0.06), (dict(mInitialVisibilityTStepScale=2.0), 0.6)])
+def test_features_match_the_slang_witness(kw, density):
+    """K0 (GenerateFeatures.cs.slang:57-102): per-pixel camera-ray transmittance by ray marching mip 0 with the trilinear sampler and
+    the 1 % early out; pixels that miss the volume keep 1."""
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=density, env_size=(128, 64))
+    params = VolumetricReSTIRParams(**kw)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    feat = op.get_buffer(capi.BUF_FEATURES).view(FEAT).reshape(h, w)
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(5)
+    vy, vx = np.nonzero(feat["transmittance"] != 1.0)
+    my, mx = np.nonzero(feat["transmittance"] == 1.0)
+    picks = [(int(vx[k]), int(vy[k])) for k in rng.permutation(len(vy))[:16]] + [(int(mx[k]), int(my[k])) for k in rng.permutation(len(my))[:4]]
+    opaque = 0
+    for x, y in picks:
+        want = frame.wit(0).feature_transmittance(frame.origin, frame.ray_dir(x, y), params.mInitialVisibilityTStepScale)
+        assert int(feat[y, x]["noReflectiveSurface"]) == 1
+        got = float(feat[y, x]["transmittance"])                 # compared as optical depths: the sum is what rounds
+        assert np.log(got) == pytest.approx(np.log(want), rel=5e-6, abs=2e-6), (x, y)
+        opaque += want < 0.01
+    assert density < 0.1 or opaque >= 4            # the dense variant reaches the early out
