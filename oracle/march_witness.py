@@ -447,6 +447,97 @@ class CellSamplingAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:439-515 (Sampl
         pass
 
 
+class ResidualRatioAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:710-794 (ResidualRatioTrackingGVDBAdapter)
+    """Ratio tracking (global majorant), residual ratio tracking (per-brick control density from the brick's min / max / avg) and
+    its analog variant (control = the brick minimum): transmittance estimate = prod over bricks of T_control * T_residual."""
+
+    def __init__(self, analog, global_majorant, rng):
+        self.Tr, self.analog, self.glob, self.rng = F(1), analog or global_majorant, global_majorant, rng
+
+    def start(self):
+        pass
+
+    def main(self, W, dda, vmin_leaf, brick, t):
+        st, b = W.sigma_t, self.bounds
+        mu_min = F(0) if self.glob else b[0] * st
+        mu_max = (W.slot["max_value"] * W.dsf) * st if self.glob else b[1] * st
+        mu_avg = b[2] * st
+        maxDeltaT = min(self.tFar - t, dda.ty - t)
+        currentTMax = min(self.tFar, dda.ty)
+        mu_r_temp = F(mu_max - mu_min)
+        D = W.superVoxelDiagonal
+        if mu_r_temp == 0 or self.analog:
+            mu_c = mu_min
+        else:
+            with np.errstate(over="ignore"):              # 2^(1 / small) overflows to inf; min() then picks mu_avg, as in the shader
+                mu_c = min(mu_avg, max(mu_min, mu_min + mu_r_temp * (np.power(F(2), F(1) / (D * mu_r_temp)) - F(1))))
+        mu_r = max(F(mu_c - mu_min), F(mu_max - mu_c))
+        with np.errstate(divide="ignore"):
+            inv_mu_r = F(1) / mu_r
+        T_c = np.exp(F(-mu_c) * min(self.tFar - t, maxDeltaT))
+        T_r = F(1)
+        if mu_r > 0:
+            while True:
+                t = t - np.log(F(1) - self.rng.next1d()) * inv_mu_r
+                if t >= currentTMax:
+                    break
+                p = (self.ray_o + t * self.ray_d) - vmin_leaf
+                mu = W.density_in_atlas(brick, p, True) * st
+                T_r = T_r * (F(1) - (mu - mu_c) * inv_mu_r)
+        self.Tr = self.Tr * (T_c * T_r)
+        return bool(currentTMax >= self.tFar), currentTMax
+
+    def end(self):
+        pass
+
+
+class DecompositionAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:606-707 (DecompositionTrackingGVDBAdapter)
+    """Free-flight distance by decomposition tracking: an analytic flight through the brick's minimum density raced against delta
+    tracking of the residual; hit = the medium-space parameter of the interaction (== the world parameter), None when the ray leaves."""
+
+    def __init__(self, rng):
+        self.rng, self.hit = rng, None
+
+    def start(self):
+        pass
+
+    def main(self, W, dda, vmin_leaf, brick, t):
+        st, b = W.sigma_t, self.bounds
+        lo, hi = b[0], b[1]
+        currentTMax = min(self.tFar, dda.ty)
+        if lo == 0:
+            t_control = DistanceSamplingAdapter.K_RAY_TMAX
+        else:
+            t_control = t - np.log(F(1) - self.rng.next1d()) / (lo * st)
+        if hi - lo > 0:
+            inv = F(1) / F(hi - lo)
+            while True:
+                t = t - np.log(F(1) - self.rng.next1d()) * inv / st
+                if t >= t_control or t >= currentTMax:
+                    break
+                p = (self.ray_o + t * self.ray_d) - vmin_leaf
+                density = W.density_in_atlas(brick, p, True)
+                if (density - lo) * inv > self.rng.next1d():
+                    self.hit = t
+                    return True, t
+            t = min(t_control, t)
+            if t < currentTMax:
+                self.hit = t
+                return True, t
+            t = currentTMax
+            if t >= self.tFar:
+                self.hit = None
+                return True, t
+            return False, t
+        if t_control < currentTMax:
+            self.hit = t_control
+            return True, t_control
+        return False, currentTMax
+
+    def end(self):
+        self.hit = None
+
+
 class Witness:
     def __init__(self, grid_desc, slot_index):
         self.slot = slot_arrays(grid_desc.slots[slot_index])
@@ -456,6 +547,9 @@ class Witness:
         self.tStepBase = F(v.tStep) * F(v.volumeWorldScaling)
         self.tex = _Texture(self.slot)
         self.mip = slot_index
+        # F/Scene/Scene.cpp:3077-3080: 8 voxels times the length of the medium-to-world scale, from slot 0
+        m2w = np.linalg.inv(np.array(list(grid_desc.slots[0].world_to_medium), dtype=np.float64).reshape(4, 4))
+        self.superVoxelDiagonal = F(8.0 * np.sqrt((m2w[:3, :3] ** 2).sum()))
 
     # VR/VolumeBase.slang:252-263
     def density_in_atlas(self, brick, p, linear):
@@ -558,6 +652,7 @@ class Witness:
                     nodeid[0] = child
                     t = dda.tx - eps
                     vmin_leaf, brick = self._node(0, child)
+                    adapter.bounds = self.slot["nodes"][0][child]["bounds"].astype(F) * self.dsf     # VR/VolumeUtils.slang:251
                     stop, t = adapter.main(self, dda, vmin_leaf, brick, t)
                     if stop:
                         return
@@ -599,6 +694,18 @@ class Witness:
                 a.outTr[i] = -np.log(F(1) - rng.next1d())
         self.track(origin_w, dir_w, DistanceSamplingAdapter.K_RAY_TMAX, a, linear)
         return [float(x) for x in a.hit], [float(x) for x in a.pdf], [float(x) for x in a.outTr]
+
+    def residual_ratio_tracking(self, origin_w, dir_w, tmax, rng, analog=False, global_majorant=False):
+        """MediumTrResidualRatioTrackingGeneric (VR/VolumeUtils.slang:328-339)."""
+        a = ResidualRatioAdapter(analog, global_majorant, rng)
+        self.track(origin_w, dir_w, tmax, a, False)
+        return float(a.Tr)
+
+    def sample_supervoxel(self, origin_w, dir_w, rng):
+        """SampleMediumSuperVoxelGeneric (VR/VolumeUtils.slang:315-326): the free-flight distance of the reference path tracer."""
+        a = DecompositionAdapter(rng)
+        self.track(origin_w, dir_w, DistanceSamplingAdapter.K_RAY_TMAX, a, False)
+        return None if a.hit is None else float(a.hit)
 
     def rejection_sample_point(self, origin_w, dir_w, rng):
         """RejectionSampleRandomPointByDensity (VR/VolumeUtils.slang:572-581): a depth inside the selected cell, or kRayTMax."""

@@ -2377,6 +2377,17 @@ void vro_sample_distances(vro_pass* p, const float o[3], const float d[3], int m
     for (int i = 0; i < 4; i++) { out12[i] = hd[i]; out12[4 + i] = pd[i]; out12[8 + i] = ot[i]; }
     out_state[0] = sg.s[0]; out_state[1] = sg.s[1]; out_state[2] = sg.s[2]; out_state[3] = sg.s[3];
 }
+// SampleMediumSuperVoxelGeneric along one ray: the interaction's distance from the origin (negative: the ray left the volume), and
+// the generator after the call
+float vro_sample_supervoxel(vro_pass* p, const float o[3], const float d[3], int mip, uint32_t spx, uint32_t spy, uint32_t sn, uint32_t out_state[4]) {
+    applyOverrides(*p);
+    Ctx c(*p); SampleGenerator sg = SampleGenerator::create(spx, spy, sn);
+    Ray r = {v3(o), v3(d), 0, kRayTMax};
+    MediumInteraction mi{}; mi.isValid = false;
+    SampleMediumSuperVoxelGeneric(c, r, sg, mi, mip);
+    for (int i = 0; i < 4; i++) out_state[i] = sg.s[i];
+    return mi.isValid ? length(mi.p - r.origin) : -1.f;
+}
 // p-hat of a single-bounce reservoir (depth, lightUV, lightID) of pixel (px, py) under the spatial options: what K1's finish, K2 and K3 evaluate
 float vro_p_hat(vro_pass* p, int px, int py, float depth, float uvx, float uvy, int lightID) {
     applyOverrides(*p);

@@ -71,6 +71,8 @@ def lib():
         L.vro_env_sample.argtypes = [vp, C.c_float, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float), C.POINTER(C.c_float * 3)]
         L.vro_neighbor_offsets.argtypes = [vp, C.c_int, C.c_int, vp]
         L.vro_p_hat.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]; L.vro_p_hat.restype = C.c_float
+        L.vro_sample_supervoxel.restype = C.c_float
+        L.vro_sample_supervoxel.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.vro_sample_distances.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
         L.vro_phase_hg.argtypes = [C.c_float, C.c_float]; L.vro_phase_hg.restype = C.c_float
         L.vro_sample_phase.argtypes = [C.c_float, C.POINTER(C.c_float * 3), C.c_float, C.c_float, C.POINTER(C.c_float * 3)]; L.vro_sample_phase.restype = C.c_float
@@ -212,6 +214,13 @@ class OraclePass:
         out = np.zeros(12, dtype=np.float32); st = np.zeros(4, dtype=np.uint32)
         lib().vro_sample_distances(self._h, C.byref(o), C.byref(d), mip, int(linear), n, seed[0], seed[1], seed[2], out.ctypes.data, st.ctypes.data)
         return out[0:4], out[4:8], out[8:12], st
+
+    def sample_supervoxel(self, origin, direction, mip, seed):
+        """SampleMediumSuperVoxelGeneric along one ray: (distance or None, generator state after)."""
+        o = (C.c_float * 3)(*origin); d = (C.c_float * 3)(*direction)
+        st = np.zeros(4, dtype=np.uint32)
+        t = float(lib().vro_sample_supervoxel(self._h, C.byref(o), C.byref(d), mip, seed[0], seed[1], seed[2], st.ctypes.data))
+        return (None if t < 0 else t), st
 
     def p_hat(self, px, py, depth, light_uv, light_id):
         """evaluate_P_hat of a single-bounce reservoir of pixel (px, py) under the spatial sampling options."""

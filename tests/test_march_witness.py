@@ -92,3 +92,47 @@ def test_oracle_distance_sampling_matches_slang_witness(dim, three_level):
                 assert np.isclose(pd[i], wpd[i], rtol=2e-5, atol=1e-30) and np.isclose(ot[i], wot[i], rtol=2e-5, atol=1e-30), (mip, linear, k, i)
             assert all(hd[i] == 0 and pd[i] == 0 and ot[i] == 0 for i in range(ns, 4))
     assert hits > 40 and exits > 10          # both outcomes are exercised
+
+
+@pytest.mark.parametrize("dim,three_level", [((64, 64, 56), False), ((200, 150, 140), True)])
+def test_oracle_stochastic_trackers_match_slang_witness(dim, three_level):
+    """The random-walk estimators: ratio tracking (global majorant), residual ratio tracking and its analog variant (per-brick
+    control densities from the node bounds) as transmittance estimators, and the decomposition tracker that draws the reference
+    path tracer's free-flight distances — same random-number stream, so the same walk: estimates agree to rounding, the
+    decomposition tracker also in the number of draws it consumed."""
+    from oracle.march_witness import Xoshiro
+    sc = env_scene(dim=dim, density_scale=0.004 if not three_level else 0.0015, num_mips=3)     # optical depths of order 1
+    grid = sc.volume.grid.contents
+    assert float(Witness(grid, 0).superVoxelDiagonal) == pytest.approx(float(grid.volume.superVoxelWorldSpaceDiagonalLength), rel=1e-6)
+    op = vro.OraclePass(VolumetricReSTIRParams())
+    op.setScene(sc, 16, 16, importance=np.zeros(349525, np.float32))
+    n_rays = 12 if three_level else 24
+    nontrivial = 0
+    for method, mip in ((capi.kRatioTracking, 0), (capi.kResidualRatioTracking, 0), (capi.kAnalogResidualRatioTracking, 1), (capi.kResidualRatioTracking, 2)):
+        w = Witness(grid, mip)
+        for k, (o, d, tmax) in enumerate(_rays(sc, n_rays, seed=200 + mip + method)):
+            seed = (k * 5 + 3, k * 11 + 1, k + method)
+            got = op.transmittance(o, d, tmax, method, mip, True, 1.0, seed)
+            want = w.residual_ratio_tracking(o, d, tmax, Xoshiro(*seed), analog=method == capi.kAnalogResidualRatioTracking,
+                                             global_majorant=method == capi.kRatioTracking)
+            assert np.isclose(got, want, rtol=2e-5, atol=1e-7), (method, mip, k, got, want)
+            nontrivial += 0.02 < want < 0.98
+    assert nontrivial > 4 * n_rays * 0.35
+    sc = env_scene(dim=dim, density_scale=0.02 if not three_level else 0.008, num_mips=3)       # dense enough to scatter
+    grid = sc.volume.grid.contents
+    op = vro.OraclePass(VolumetricReSTIRParams())
+    op.setScene(sc, 16, 16, importance=np.zeros(349525, np.float32))
+    hits = exits = 0
+    for mip in (0, 1):
+        w = Witness(grid, mip)
+        for k, (o, d, _) in enumerate(_rays(sc, n_rays, seed=300 + mip)):
+            seed = (k * 13 + 2, k * 3 + 5, k + 40 + mip)
+            t, state = op.sample_supervoxel(o, d, mip, seed)
+            rng = Xoshiro(*seed)
+            wt = w.sample_supervoxel(o, d, rng)
+            assert [int(x) for x in state] == rng.s, (mip, k)
+            if wt is None:
+                assert t is None; exits += 1
+            else:
+                assert t == pytest.approx(wt, rel=5e-6, abs=1e-6), (mip, k); hits += 1     # the hook returns |p - origin|
+    assert hits > n_rays // 2 and exits > 2
