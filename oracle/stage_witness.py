@@ -11,6 +11,10 @@ default option family).
                                 VR/VolumetricReSTIR.cpp:457-470
   temporal reuse (K2)           VR/TemporalReuse.cs.slang:80-377 (linear reprojection, Talbot MIS or none; no velocity grid),
                                 resampleNeighbor VR/ReSTIRHelper.slang:582-597, simpleResampleStepWithMaxM VR/Reservoir.slang:57-87
+  multi-bounce paths            the bounce loop of VR/ComputeInitialSample.slang:29-386 (phase-sampled continuation, one free-flight
+                                sample per bounce on the coarser grid, Russian roulette, per-bounce reservoir streaming), the
+                                extra-bounce records VR/ReSTIRHelper.slang:21-52,66-79 and the vertex loop of evaluate_F_ :205-385
+                                (env-map light, no emission, no vertex reuse)
   final shading (K5)            VR/FinalShading.cs.slang:95-141, finalOptions VR/VolumetricReSTIR.cpp:484-496
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
@@ -387,3 +391,224 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
         taps[i]["runningSum"] = F(taps[i]["runningSum"] * mis)
         _resample_step_max_m(taps[i], max_prev_m, output, rng)
     return output
+
+
+# ---------------------------------------------------------------- multi-bounce paths (MAX_BOUNCES > 1) ----------------------------------------------------------------
+
+def encode_wi_dist(wi, dist):
+    """encodeWiDist: direction xy + distance carrying the sign of direction z."""
+    return np.array([wi[0], wi[1], -dist if wi[2] < 0 else dist], dtype=F)
+
+
+def decode_wi_dist(rec):
+    """decodeWiDist(input, false): (direction, distance)."""
+    x, y, z = F(rec[0]), F(rec[1]), F(rec[2])
+    with np.errstate(invalid="ignore"):
+        wz = np.sqrt(F(1) - (x * x + y * y)).astype(F)
+    if np.isnan(wz):
+        wz = F(0)
+    if z < 0:
+        wz, z = -wz, -z
+    return np.array([x, y, wz], dtype=F), F(z)
+
+
+def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
+    """evaluate_F_ for a reservoir whose sample may be a multi-bounce path: r = the reservoir record, extra = its extra-bounce
+    records (wi_dist), env-map light at the last vertex.  no_reuse (gNoReuse, final shading only): the path was drawn by
+    decomposition tracking, so densities and segment transmittances cancel against its pdf and only the albedo remains per vertex."""
+    bounces = int(r["sampledPixel"]) >> 20
+    depth, light_uv, light_id = F(r["depth"]), np.asarray(r["lightUV"], dtype=F), int(r["lightID"])
+    if not no_reuse and (bounces == 0 or depth == K_RAY_TMAX):
+        return frame.eval_F(d, depth, light_uv, light_id, final)
+    vol, o = frame.grid.volume, frame.origin
+    sig_s, g = np.array(vol.sigma_s[:], dtype=F), vol.PhaseFunctionConstantG
+    background = depth == K_RAY_TMAX
+    p = (o + d * depth).astype(F)
+    if no_reuse:
+        Fv = (F(1) * F(1) * (np.ones(3, F) if background else (sig_s / F(vol.sigma_t)).astype(F))).astype(F)
+    else:
+        density = frame.wit(0).density_world(p)
+        if density == 0:
+            return np.zeros(3, F)
+        Fv = (frame._transmittance(final, "camera", o, d, float(depth)) * density * sig_s).astype(F)
+    if not bool(np.any(Fv > 0)):
+        return Fv
+    if background:
+        return (Fv * lw.env_eval(frame.sc.envMap, d, frame.sc.envMapIntensity)).astype(F)
+    assert (int(r["sampledPixel"]) >> 16) & 0xF == 0 and light_id in (-1, -2)
+    wo = -d
+    for b in range(bounces):
+        wi, dist = decode_wi_dist(extra[b])
+        if dist == K_RAY_TMAX:
+            return np.zeros(3, F)
+        Fv = (Fv * F(lw.phase_hg(float(np.dot(wo, wi)), g))).astype(F)
+        if bool(np.all(Fv == 0)):
+            return np.zeros(3, F)
+        origin = p
+        p = (origin + wi * dist).astype(F)
+        if no_reuse:
+            Fv = (Fv * (F(1) * (sig_s / F(vol.sigma_t)).astype(F))).astype(F)
+        else:
+            scatter_density = max(F(0), frame.wit(0).density_world(p))
+            Fv = (Fv * (scatter_density * sig_s)).astype(F)
+        if bool(np.all(Fv == 0)):
+            return np.zeros(3, F)
+        if not no_reuse:
+            Fv = (Fv * frame._transmittance(final, "camera", origin, wi, float(dist))).astype(F)
+        wo = -wi
+        if bool(np.all(Fv == 0)):
+            return np.zeros(3, F)
+    zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
+    z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
+    wl = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
+    Ld = lw.env_eval(frame.sc.envMap, wl, frame.sc.envMapIntensity) * F(lw.phase_hg(float(np.dot(wo, wl)), g))
+    tr = frame._transmittance(final, "light", p, wl, float(K_RAY_TMAX))
+    return (Fv * (tr * Ld)).astype(F)
+
+
+def _sample_direct_lighting(frame, p, wo, rng, mips):
+    """SampleDirectLighting with only an env-map light: (Ld, light pdf, lightID, lightUV)."""
+    P, g = frame.P, frame.grid.volume.PhaseFunctionConstantG
+    rng.next1d()                                           # light-type selection: env lights only
+    u0 = rng.next1d(); u1 = rng.next1d()
+    wi, pdf, _ = lw.env_sample(mips, u0, u1)
+    pdf = F(F(1) * F(pdf))
+    Le = lw.env_eval(frame.sc.envMap, wi, frame.sc.envMapIntensity)
+    Li = (Le / pdf).astype(F) if pdf > 0 else np.zeros(3, F)
+    light_id, light_uv = (-2 if wi[2] < 0 else -1), np.array([wi[0], wi[1]], dtype=F)
+    if bool(np.any(np.isnan(wi))):
+        return np.zeros(3, F), F(0), light_id, light_uv
+    if P.mInitialLightSamples != 0:
+        vis = F(frame.wit(P.mInitialLightingMipLevel).ray_marching(p, wi, float(K_RAY_TMAX), bool(P.mInitialLightingUseLinearSampler), P.mInitialLightingTStepScale))
+        Li = (Li * vis).astype(F)
+    return (F(lw.phase_hg(float(np.dot(wo, wi)), g)) * Li / F(1)).astype(F), pdf, light_id, light_uv
+
+
+def _initial_path(frame, d, hd, pd, tr, rng, mips, no_reuse=False):
+    """ComputeInitialSample with MAX_BOUNCES > 1: one candidate PATH — a light sample at every vertex, streamed into one reservoir per
+    path.  Returns (combined reservoir, extra-bounce records written so far)."""
+    P, vol = frame.P, frame.grid.volume
+    B = P.mMaxBounces
+    sig_s = np.array(vol.sigma_s[:], dtype=F)
+    albedo = (sig_s / F(vol.sigma_t)).astype(F)
+    linear = bool(P.mInitialVisibilityUseLinearSampler)
+    vis_mip = P.mInitialBaseMipLevel if linear else P.mInitialBaseMipLevel + 8
+    path_pdf, path_phat = F(1), F(1)
+    origin, direction = frame.origin, d
+    combined = _new_reservoir()
+    extra = np.zeros((max(B - 1, 1), 3), F)
+    primary_depth = F(0)
+    for bounce in range(B):
+        out = _new_reservoir(); out["M"] = F(1)
+        p = None
+        if no_reuse:                                       # free flight by decomposition tracking on mip 0, pdf and Tr folded into 1
+            t = frame.wit(0).sample_supervoxel(origin, direction, rng)
+            pdf_dist, Tr = F(1), F(1)
+            if t is None:
+                cur = K_RAY_TMAX
+            else:
+                p = (origin + F(t) * direction).astype(F)
+                cur = F(np.sqrt(np.dot(p - origin, p - origin)))
+        elif bounce >= 1:
+            mip = vis_mip
+            if P.mInitialUseCoarserGridForIndirectBounce:
+                mip = min((8 if vis_mip >= 8 else 0) + vol.numMips - 1, vis_mip + 1)
+            h, q, t = frame.wit(mip).sample_distances(origin, direction, 1, linear, rng)
+            cur, pdf_dist, Tr = F(h[0]), F(q[0]), F(t[0])
+        else:
+            cur, pdf_dist, Tr = hd, pd, tr
+        valid = cur != K_RAY_TMAX
+        if p is None:
+            p = (origin + direction * cur).astype(F)
+        path_pdf = F(path_pdf * pdf_dist)
+        if bounce == 0:
+            out["depth"] = cur if valid else K_RAY_TMAX
+            primary_depth = out["depth"]
+        else:
+            out["depth"] = primary_depth
+            out["sampledPixel"] = bounce << 20
+            extra[bounce - 1] = encode_wi_dist(direction, cur if valid else K_RAY_TMAX)
+        out["p_y"] = path_pdf
+        density = (F(1) if no_reuse else frame.wit(0).density_world(p)) if valid else F(0)
+        hit_empty = False
+        if (not valid and bounce > 0) or (valid and density == 0):
+            out["p_y"] = F(0); out["runningSum"] = F(0); hit_empty = True
+        elif valid:
+            wo = -direction
+            Ld, light_pdf, out["lightID"], out["lightUV"] = _sample_direct_lighting(frame, p, wo, rng, mips)
+            wi, pdf_dir = None, F(1)
+            if B > 1:
+                wi, pdf_dir = lw.sample_phase(vol.PhaseFunctionConstantG, wo, rng.next1d(), rng.next1d())
+                pdf_dir = F(pdf_dir)
+            rng.next1d()                                   # emission-vs-scatter draw; no emission here, so always scatter
+            p_src = F(out["p_y"] * (light_pdf * (F(1) - F(0))))
+            out["runningSum"] = F(0) if p_src == 0 else F(1)
+            out["p_y"] = p_src
+            path_phat = F(F(path_phat * Tr) * density)
+            p_y = F(path_phat * lw.luminance(((sig_s * Ld) * light_pdf).astype(F)))
+            path_phat = F(path_phat * F(lw.luminance(sig_s) * pdf_dir))
+            if no_reuse:
+                p_y = F(p_y / F(vol.sigma_t)); path_phat = F(path_phat / F(vol.sigma_t))
+            if out["runningSum"] > 0:
+                out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
+                out["p_y"] = p_y
+            path_pdf = F(path_pdf * pdf_dir)
+            if bounce < B - 1:
+                origin, direction = p, wi
+                if P.mInitialUseRussianRoulette and bounce >= 2:
+                    if rng.next1d() < albedo[0]:
+                        path_pdf = F(path_pdf * albedo[0])
+                    else:
+                        hit_empty = True; combined["M"] = F(combined["M"] + 1)
+        else:                                              # the camera ray left the volume: the background is the sample
+            Le = lw.env_eval(frame.sc.envMap, direction, frame.sc.envMapIntensity)
+            path_phat = F(path_phat * Tr)
+            p_y = F(path_phat * lw.luminance(Le))
+            out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
+            out["p_y"] = p_y
+            hit_empty = True
+        if B == 1:
+            return out, extra
+        _resample_step(out, combined, rng)
+        if hit_empty:
+            break
+    combined["M"] = F(1)
+    return combined, extra
+
+
+def initial_sampling_pixel_paths(frame, px, py, frame_count, importance_mips):
+    """TraceRays.cs.slang main() with MAX_BOUNCES > 1, or with both reuse passes off (gNoReuse: every candidate is a path drawn by
+    decomposition tracking): (stored reservoir, its extra-bounce records)."""
+    P = frame.P
+    no_reuse = not P.mEnableSpatialReuse and not P.mEnableTemporalReuse
+    total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
+    rng = Xoshiro(px, py, total_rounds * frame_count)
+    d = frame.ray_dir(px, py)
+    final, final_extra = _new_reservoir(), np.zeros((max(P.mMaxBounces - 1, 1), 3), F)
+    linear = bool(P.mInitialVisibilityUseLinearSampler)
+    vis_mip = P.mInitialBaseMipLevel if linear else P.mInitialBaseMipLevel + 8
+    rounds = (P.mInitialM + 3) // 4
+    for r in range(rounds):
+        n = P.mInitialM - 4 * (rounds - 1) if r == rounds - 1 else 4
+        hd, pd, ot = ([0] * 4,) * 3 if no_reuse else frame.wit(vis_mip).sample_distances(frame.origin, d, n, linear, rng)
+        for s in range(n):
+            cand, extra = _initial_path(frame, d, F(hd[s]), F(pd[s]), F(ot[s]), rng, importance_mips, no_reuse)
+            if _resample_step(cand, final, rng):
+                k = int(final["sampledPixel"]) >> 20
+                final_extra[:k] = extra[:k]
+    p_hat = F(lw.luminance(eval_F_path(frame, d, final, final_extra)))
+    if final["runningSum"] > 0:
+        final["runningSum"] = F(final["runningSum"] * (F(0) if final["p_y"] == 0 else F(p_hat / final["p_y"])))
+        final["p_y"] = p_hat
+    return final, final_extra
+
+
+def final_shading_path(frame, px, py, r, extra):
+    """FinalShading.cs.slang for a multi-bounce reservoir."""
+    if not r["runningSum"] > 0:
+        return np.zeros(3, F)
+    no_reuse = not frame.P.mEnableSpatialReuse and not frame.P.mEnableTemporalReuse
+    col = eval_F_path(frame, frame.ray_dir(px, py), r, extra, final=True, no_reuse=no_reuse)
+    W = F(1) if r["p_y"] == 0 else F(F(r["runningSum"]) / F(F(r["p_y"]) * F(r["M"])))
+    out = (col * W).astype(F)
+    return np.zeros(3, F) if bool(np.any(np.isnan(out) | np.isinf(out))) else out

@@ -69,3 +69,89 @@ def test_features_match_the_slang_witness(kw, density):
         assert np.log(got) == pytest.approx(np.log(want), rel=5e-6, abs=2e-6), (x, y)
         opaque += want < 0.01
     assert density < 0.1 or opaque >= 4            # the dense variant reaches the early out
+
+
+@pytest.mark.parametrize("kw,g", [(dict(mMaxBounces=3), 0.0), (dict(mMaxBounces=4, mInitialUseCoarserGridForIndirectBounce=0, mInitialM=3), 0.5)])
+def test_multi_bounce_paths_match_the_slang_witness(kw, g):
+    """MAX_BOUNCES > 1: the bounce loop of ComputeInitialSample (a light sample at every vertex, phase-sampled continuation, one
+    free-flight sample per bounce on the coarser grid, Russian roulette from the third vertex on, per-path reservoir), the
+    extra-bounce records, the vertex loop of evaluate_F_ for the stored path's p-hat, and its final shading."""
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.12, env_size=(128, 64), g=g)
+    params = VolumetricReSTIRParams(mEnableSpatialReuse=0, **kw)
+    B = params.mMaxBounces
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()
+    frame_count = op.frame_count()
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    extra = op.get_buffer(capi.BUF_EXTRA_0).view(np.float32).reshape(h, w, B - 1, 3).copy()
+    op.execute_stage(5, 0, color)
+    imp = op.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
+    mips, off, dim = [], 0, 512
+    while dim >= 1:
+        mips.append(imp[off:off + dim * dim].reshape(dim, dim).copy()); off += dim * dim; dim //= 2
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(6)
+    depth_of = res["sampledPixel"] >> 20
+    picks = []
+    for k, n in ((0, 3), (1, 4), (2, 4)) + (((3, 3),) if B > 3 else ()):
+        ys, xs = np.nonzero((res["runningSum"] > 0) & (depth_of == k) & (res["depth"] < 1e37))
+        assert len(ys) >= n, (k, len(ys))
+        picks += [(int(xs[i]), int(ys[i])) for i in rng.permutation(len(ys))[:n]]
+    for x, y in picks:
+        got = res[y, x]
+        want, want_extra = sw.initial_sampling_pixel_paths(frame, x, y, frame_count, mips)
+        assert int(got["sampledPixel"]) == want["sampledPixel"] and int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        k = int(got["sampledPixel"]) >> 20
+        np.testing.assert_allclose(extra[y, x, :k], want_extra[:k], rtol=1e-5, atol=3e-6)
+        np.testing.assert_allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=3e-6)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        rad = sw.final_shading_path(frame, x, y, got, extra[y, x])
+        np.testing.assert_allclose(color[y, x, :3], rad, rtol=2e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_no_reuse_mode_matches_the_slang_witness(B):
+    """Both reuse passes off (gNoReuse, BASELINE's configuration 1): candidates are paths whose vertices come from decomposition
+    tracking on mip 0, densities and segment transmittances cancel (pdf = Tr = 1, albedo per vertex), and the final shading
+    evaluates F in the same mode."""
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.12, env_size=(128, 64), g=0.3)
+    params = VolumetricReSTIRParams(mEnableTemporalReuse=0, mEnableSpatialReuse=0, mMaxBounces=B, mInitialM=2)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()
+    frame_count = op.frame_count()
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    extra = op.get_buffer(capi.BUF_EXTRA_0).view(np.float32).reshape(h, w, B - 1, 3).copy() if B > 1 else np.zeros((h, w, 1, 3), np.float32)
+    op.execute_stage(5, 0, color)
+    imp = op.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
+    mips, off, dim = [], 0, 512
+    while dim >= 1:
+        mips.append(imp[off:off + dim * dim].reshape(dim, dim).copy()); off += dim * dim; dim //= 2
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(8)
+    ys, xs = np.nonzero((res["runningSum"] > 0) & (res["depth"] < 1e37))
+    by, bx = np.nonzero((res["runningSum"] > 0) & (res["depth"] > 1e37))
+    picks = [(int(xs[i]), int(ys[i])) for i in rng.permutation(len(ys))[:10]] + [(int(bx[i]), int(by[i])) for i in rng.permutation(len(by))[:2]]
+    deep = 0
+    for x, y in picks:
+        got = res[y, x]
+        want, want_extra = sw.initial_sampling_pixel_paths(frame, x, y, frame_count, mips)
+        assert int(got["sampledPixel"]) == want["sampledPixel"] and int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        k = int(got["sampledPixel"]) >> 20
+        deep += k > 0
+        np.testing.assert_allclose(extra[y, x, :k], want_extra[:k], rtol=1e-5, atol=3e-6)
+        np.testing.assert_allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=3e-6)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, got, extra[y, x]), rtol=2e-4, atol=1e-9)
+    assert B == 1 or deep >= 3
