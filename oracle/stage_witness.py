@@ -15,6 +15,10 @@ default option family).
                                 sample per bounce on the coarser grid, Russian roulette, per-bounce reservoir streaming), the
                                 extra-bounce records VR/ReSTIRHelper.slang:21-52,66-79 and the vertex loop of evaluate_F_ :205-385
                                 (env-map light, no emission, no vertex reuse)
+  analytic + emissive lights    sampleSceneLights VR/VolumeUtils.slang:12-149 (type selection, point / directional F/Experimental/Scene/Lights/
+                                LightHelpers.slang:196-244, emissive triangles F/.../EmissivePowerSampler.slang:57-92 +
+                                EmissiveLightSamplerHelpers.slang:56-101, alias draw F/Utils/Sampling/AliasTable.slang:56-70,
+                                computeRayOrigin F/Utils/Helpers.slang:92-105), evaluate_L_in_volume VR/ReSTIRHelper.slang:443-496
   final shading (K5)            VR/FinalShading.cs.slang:95-141, finalOptions VR/VolumetricReSTIR.cpp:484-496
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
@@ -42,6 +46,7 @@ class Frame:
         self.origin = np.array(cam.posW[:], dtype=F)
         self.U, self.V, self.Wv = (np.array(getattr(cam, k)[:], dtype=F) for k in ("cameraU", "cameraV", "cameraW"))
         self._wit = {}
+        self.lights = None              # a Lights instance when the scene has analytic / emissive lights
 
     def wit(self, mip):
         if mip not in self._wit:
@@ -79,8 +84,10 @@ class Frame:
         Fv = (vis * density * np.array(vol.sigma_s[:], dtype=F)).astype(F)
         if not bool(np.any(Fv > 0)):
             return Fv
-        if light_id == SELF_EMISSION or light_id >= 0:
-            raise NotImplementedError("witness covers env-map lights")
+        if light_id == SELF_EMISSION:
+            raise NotImplementedError("witness does not cover volume emission")
+        if light_id >= 0:
+            return (Fv * eval_L_in_volume(self, self.lights, pw, -d, light_id, light_uv, final)).astype(F)
         zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
         z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
         wi = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
@@ -209,23 +216,7 @@ def _initial_candidate(frame, d, hd, pd, tr, rng, mips):
             out["p_y"] = F(0); out["runningSum"] = F(0)
             return out
         albedo = (sig_s / F(vol.sigma_t)).astype(F)
-        # SampleDirectLighting -> sampleSceneLights (env lights only: the selection draw always picks them)
-        rng.next1d()
-        u0 = rng.next1d(); u1 = rng.next1d()
-        wi, pdf, _ = lw.env_sample(mips, u0, u1)
-        pdf = F(F(1) * F(pdf))
-        Le = lw.env_eval(frame.sc.envMap, wi, frame.sc.envMapIntensity)
-        Li = (Le / pdf).astype(F) if pdf > 0 else np.zeros(3, F)
-        out["lightID"] = -2 if wi[2] < 0 else -1
-        out["lightUV"] = np.array([wi[0], wi[1]], dtype=F)
-        light_pdf = pdf
-        if bool(np.any(np.isnan(wi))):
-            light_pdf, Ld = F(0), np.zeros(3, F)
-        else:
-            if P.mInitialLightSamples != 0:
-                vis = F(frame.wit(P.mInitialLightingMipLevel).ray_marching(pw, wi, float(K_RAY_TMAX), bool(P.mInitialLightingUseLinearSampler), P.mInitialLightingTStepScale))
-                Li = (Li * vis).astype(F)
-            Ld = (F(lw.phase_hg(float(np.dot(-d, wi)), vol.PhaseFunctionConstantG)) * Li / F(1)).astype(F)
+        Ld, light_pdf, out["lightID"], out["lightUV"] = _sample_direct_lighting(frame, pw, -d, rng, mips)
         p_src = out["p_y"]
         lum_e = lw.luminance(((F(1) - albedo) * np.zeros(3, F)).astype(F))
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -435,7 +426,7 @@ def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
         return Fv
     if background:
         return (Fv * lw.env_eval(frame.sc.envMap, d, frame.sc.envMapIntensity)).astype(F)
-    assert (int(r["sampledPixel"]) >> 16) & 0xF == 0 and light_id in (-1, -2)
+    assert (int(r["sampledPixel"]) >> 16) & 0xF == 0 and light_id != SELF_EMISSION
     wo = -d
     for b in range(bounces):
         wi, dist = decode_wi_dist(extra[b])
@@ -458,16 +449,13 @@ def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
         wo = -wi
         if bool(np.all(Fv == 0)):
             return np.zeros(3, F)
-    zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
-    z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
-    wl = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
-    Ld = lw.env_eval(frame.sc.envMap, wl, frame.sc.envMapIntensity) * F(lw.phase_hg(float(np.dot(wo, wl)), g))
-    tr = frame._transmittance(final, "light", p, wl, float(K_RAY_TMAX))
-    return (Fv * (tr * Ld)).astype(F)
+    return (Fv * eval_L_in_volume(frame, frame.lights, p, wo, light_id, light_uv, final)).astype(F)
 
 
 def _sample_direct_lighting(frame, p, wo, rng, mips):
     """SampleDirectLighting with only an env-map light: (Ld, light pdf, lightID, lightUV)."""
+    if frame.lights is not None:
+        return sample_direct_lighting(frame, frame.lights, p, wo, rng, mips)
     P, g = frame.P, frame.grid.volume.PhaseFunctionConstantG
     rng.next1d()                                           # light-type selection: env lights only
     u0 = rng.next1d(); u1 = rng.next1d()
@@ -612,3 +600,147 @@ def final_shading_path(frame, px, py, r, extra):
     W = F(1) if r["p_y"] == 0 else F(F(r["runningSum"]) / F(F(r["p_y"]) * F(r["M"])))
     out = (col * W).astype(F)
     return np.zeros(3, F) if bool(np.any(np.isnan(out) | np.isinf(out))) else out
+
+
+# ---------------------------------------------------------------- analytic and emissive lights ----------------------------------------------------------------
+FLT_MIN = F(1.17549435e-38)
+
+
+def compute_ray_origin(pos, normal):
+    """computeRayOrigin: integer offset of the fp32 bit pattern along the normal (fixed offset close to the origin)."""
+    pos, normal = np.asarray(pos, dtype=F), np.asarray(normal, dtype=F)
+    i_off = np.trunc(normal * F(256)).astype(np.int32)
+    bits = pos.view(np.int32) + np.where(pos < 0, -i_off, i_off).astype(np.int32)
+    i_pos = bits.astype(np.int32).view(F)
+    f_off = (normal * F(1.0 / 65536.0)).astype(F)
+    return np.where(np.abs(pos) < F(1.0 / 32.0), pos + f_off, i_pos).astype(F)
+
+
+class Lights:
+    """The scene's light lists as the witness needs them: analytic lights, emissive triangles and their alias table
+    (items = [threshold bits, indexA, indexB], weights, weight sum — built by oracle/alias_oracle.py from AliasTable.cpp)."""
+
+    def __init__(self, scene, emissive_alias=None):
+        self.analytic = list(scene.lights)
+        self.tris = scene.emissiveTriangles
+        self.mult = F(scene.emissiveIntensityMultiplier)
+        if emissive_alias is not None:
+            self.items, self.weights, self.weight_sum = emissive_alias[0], np.asarray(emissive_alias[1], dtype=F), F(emissive_alias[2])
+
+    def sample_triangle(self, p, tri_index, u):
+        """sampleTriangle: dict(valid, dir, distance, posW, normal, Le, pdf, pdfArea, cos) for the shading point p."""
+        t = self.tris[tri_index]
+        su = np.sqrt(F(u[0])).astype(F)
+        b = (F(1) - su, F(u[1]) * su)
+        bary = (F(F(1) - b[0] - b[1]), b[0], b[1])
+        v = [np.array(t.posW[k][:], dtype=F) for k in range(3)]
+        normal = np.array(t.normal[:], dtype=F)
+        pos = compute_ray_origin((v[0] * bary[0] + v[1] * bary[1] + v[2] * bary[2]).astype(F), normal)
+        to_light = (pos - p).astype(F)
+        dist_sqr = max(FLT_MIN, F(np.dot(to_light, to_light)))
+        dist = np.sqrt(dist_sqr).astype(F)
+        direction = (to_light / dist).astype(F)
+        cos = F(np.dot(normal, -direction))
+        out = dict(valid=bool(cos > 0), dir=direction, distance=dist, posW=pos, normal=normal, cos=cos, pdf=F(0), pdfArea=F(0), Le=np.zeros(3, F))
+        if out["valid"]:
+            out["Le"] = np.array(t.Le[:], dtype=F)
+            out["pdf"] = F(dist_sqr / max(FLT_MIN, F(cos * F(t.area))))
+            out["pdfArea"] = F(F(1) / F(t.area))
+        return out
+
+
+def sample_scene_lights(frame, lights, p, rng, mips):
+    """sampleSceneLights: dict(valid, dir, rayDir, rayDistance, Li (pre-divided by pdf), pdfArea, lightID, lightUV)."""
+    P = frame.P
+    sel = [F(1) if P.mUseEnvironmentLights else F(0), F(1) if P.mUseAnalyticLights else F(0), F(1) if P.mUseEmissiveLights else F(0)]
+    total = F(sel[0] + sel[1] + sel[2])
+    invalid = dict(valid=False, pdfArea=F(0), lightID=-1, lightUV=np.zeros(2, F), Li=np.zeros(3, F))
+    if total == 0:
+        return invalid
+    inv = F(1) / total
+    sel = [F(x * inv) for x in sel]
+    u = rng.next1d()
+    if P.mUseEnvironmentLights:
+        if u < sel[0]:
+            u0 = rng.next1d(); u1 = rng.next1d()
+            wi, pdf, _ = lw.env_sample(mips, u0, u1)
+            pdf = F(sel[0] * F(pdf))
+            Le = lw.env_eval(frame.sc.envMap, wi, frame.sc.envMapIntensity)
+            return dict(valid=not bool(np.any(np.isnan(wi))), dir=wi, rayDir=wi, rayDistance=K_RAY_TMAX, pdfArea=pdf,
+                        Li=(Le / pdf).astype(F) if pdf > 0 else np.zeros(3, F), lightID=-2 if wi[2] < 0 else -1, lightUV=np.array([wi[0], wi[1]], dtype=F))
+        u = F(u - sel[0])
+    if P.mUseAnalyticLights:
+        if u < sel[1]:
+            u = F(u / sel[1])
+            count = len(lights.analytic)
+            idx = min(int(np.trunc(F(u * F(count)))), count - 1)
+            direction, distance, Li = analytic_light_sample(lights.analytic[idx], p)
+            pdf = F(F(sel[1] / F(count)) * F(1))
+            return dict(valid=True, dir=direction, rayDir=direction, rayDistance=distance, pdfArea=pdf, Li=(Li / pdf).astype(F), lightID=idx, lightUV=np.zeros(2, F))
+        u = F(u - sel[1])
+    if P.mUseEmissiveLights and u < sel[2]:
+        if lights.tris is None or len(lights.tris) == 0:
+            return invalid
+        x, y = rng.next1d(), rng.next1d()
+        count = len(lights.items)
+        slot = min(count - 1, int(np.trunc(F(x * F(count)))))
+        thr = lights.items[slot, 0:1].copy().view(F)[0]
+        tri = int(lights.items[slot, 1] if y >= thr else lights.items[slot, 2])
+        sel_pdf = F(lights.weights[tri] / lights.weight_sum)
+        uv = np.array([rng.next1d(), rng.next1d()], dtype=F)
+        ls = lights.sample_triangle(p, tri, uv)
+        light_id = tri + len(lights.analytic)
+        if not ls["valid"]:
+            return dict(valid=False, pdfArea=F(0), lightID=light_id, lightUV=uv, Li=np.zeros(3, F))
+        pdf = F(sel[2] * F(ls["pdf"] * sel_pdf))
+        pdf_area = F(sel[2] * F(ls["pdfArea"] * sel_pdf))
+        to_light = (compute_ray_origin(ls["posW"], ls["normal"]) - p).astype(F)
+        ray_dist = np.sqrt(F(np.dot(to_light, to_light))).astype(F)
+        return dict(valid=True, dir=ls["dir"], rayDir=(to_light / ray_dist).astype(F), rayDistance=ray_dist, pdfArea=pdf_area,
+                    Li=((ls["Le"] * lights.mult) / pdf).astype(F) if pdf > 0 else np.zeros(3, F), lightID=light_id, lightUV=uv)
+    return invalid
+
+
+def analytic_light_sample(light, p):
+    """samplePointLight / sampleDirectionalLight: (direction, distance, Li)."""
+    if light["type"] == 1:
+        return (-np.array(light["dirW"], dtype=F)).astype(F), K_RAY_TMAX, np.array(light["intensity"], dtype=F)
+    to_light = (np.array(light["posW"], dtype=F) - p).astype(F)
+    dist_sqr = max(F(np.dot(to_light, to_light)), F(1e-9))
+    dist = np.sqrt(dist_sqr).astype(F)
+    return (to_light / dist).astype(F), dist, (np.array(light["intensity"], dtype=F) / dist_sqr).astype(F)
+
+
+def sample_direct_lighting(frame, lights, p, wo, rng, mips):
+    """SampleDirectLighting under the initial options: (Ld, pdf, lightID, lightUV)."""
+    P, g = frame.P, frame.grid.volume.PhaseFunctionConstantG
+    ls = sample_scene_lights(frame, lights, p, rng, mips)
+    if not ls["valid"]:
+        return np.zeros(3, F), F(0), ls["lightID"], ls["lightUV"]
+    Li = ls["Li"]
+    if P.mInitialLightSamples != 0:
+        vis = F(frame.wit(P.mInitialLightingMipLevel).ray_marching(p, ls["rayDir"], float(ls["rayDistance"]), bool(P.mInitialLightingUseLinearSampler), P.mInitialLightingTStepScale))
+        Li = (Li * vis).astype(F)
+    return (F(lw.phase_hg(float(np.dot(wo, ls["dir"])), g)) * Li / F(1)).astype(F), ls["pdfArea"], ls["lightID"], ls["lightUV"]
+
+
+def eval_L_in_volume(frame, lights, p, wo, light_id, light_uv, final=False):
+    """evaluate_L_in_volume: transmittance to the stored light sample times its radiance times the phase function, float3."""
+    g = frame.grid.volume.PhaseFunctionConstantG
+    if light_id < 0:
+        zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
+        z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
+        ray_dir = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
+        ray_dist = K_RAY_TMAX
+        Ld = lw.env_eval(frame.sc.envMap, ray_dir, frame.sc.envMapIntensity) * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))
+    elif light_id < len(lights.analytic):
+        ray_dir, ray_dist, Li = analytic_light_sample(lights.analytic[light_id], p)
+        Ld = (Li * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))).astype(F)
+    else:
+        ls = lights.sample_triangle(p, light_id - len(lights.analytic), light_uv)
+        if not ls["valid"]:
+            return np.zeros(3, F)
+        ray_dir, ray_dist = ls["dir"], ls["distance"]
+        Ld = ((((ls["Le"] * lights.mult) * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))) * ls["cos"]) / F(ray_dist * ray_dist)).astype(F)
+    tr = frame._transmittance(final, "light", p, ray_dir, float(ray_dist))
+    return (tr * Ld).astype(F)

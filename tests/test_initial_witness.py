@@ -155,3 +155,54 @@ def test_no_reuse_mode_matches_the_slang_witness(B):
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
         np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, got, extra[y, x]), rtol=2e-4, atol=1e-9)
     assert B == 1 or deep >= 3
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_analytic_and_emissive_lights_match_the_slang_witness(B):
+    """All three light types at once (BASELINE's configuration 4 in small: emissive triangles drawn from the power alias table, a
+    point and a directional light, the env map): type selection, the per-type samples and pdfs (area measure for triangles, Dirac
+    lights with pdf 1), the offset shadow-ray origin on the triangle, and evaluate_L_in_volume of the stored (lightID, lightUV)
+    for p-hat and the final shading."""
+    from oracle import alias_oracle
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.1, env_size=(128, 64), g=0.3)
+    lo, hi = sc.volume_bounds_world()
+    sc.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
+    sc.addDirectionalLight((0.3, -1.0, 0.2), (2.0, 1.5, 1.0))
+    tris = sc.addEmissiveShell(300, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
+    params = VolumetricReSTIRParams(mEnableSpatialReuse=0, mMaxBounces=B, mInitialM=4, mUseAnalyticLights=1, mUseEmissiveLights=1)
+    alias = alias_oracle.emissive_alias_table(tris)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h, emissive_alias=alias)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()
+    frame_count = op.frame_count()
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    extra = op.get_buffer(capi.BUF_EXTRA_0).view(np.float32).reshape(h, w, B - 1, 3).copy() if B > 1 else np.zeros((h, w, 1, 3), np.float32)
+    op.execute_stage(5, 0, color)
+    imp = op.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
+    mips, off, dim = [], 0, 512
+    while dim >= 1:
+        mips.append(imp[off:off + dim * dim].reshape(dim, dim).copy()); off += dim * dim; dim //= 2
+    frame = sw.Frame(sc, params, w, h)
+    frame.lights = sw.Lights(sc, alias)
+    rng = np.random.default_rng(9)
+    vol = (res["runningSum"] > 0) & (res["depth"] < 1e37)
+    picks = []
+    for mask, n in ((vol & (res["lightID"] < 0), 4), (vol & (res["lightID"] >= 0) & (res["lightID"] < 2), 5), (vol & (res["lightID"] >= 2), 6)):
+        ys, xs = np.nonzero(mask)
+        assert len(ys) >= n, len(ys)
+        picks += [(int(xs[i]), int(ys[i])) for i in rng.permutation(len(ys))[:n]]
+    for x, y in picks:
+        got = res[y, x]
+        want, want_extra = sw.initial_sampling_pixel_paths(frame, x, y, frame_count, mips) if B > 1 else (sw.initial_sampling_pixel(frame, x, y, frame_count, mips), None)
+        assert int(got["sampledPixel"]) == want["sampledPixel"] and int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        k = int(got["sampledPixel"]) >> 20
+        if k:
+            np.testing.assert_allclose(extra[y, x, :k], want_extra[:k], rtol=1e-5, atol=3e-6)
+        np.testing.assert_allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=3e-6)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, got, extra[y, x]), rtol=2e-4, atol=1e-9)
