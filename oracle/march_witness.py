@@ -570,6 +570,15 @@ class Witness:
         pos = _mul_point(np.asarray(p_world, dtype=F), s["w2m"])
         if bool(np.any(pos < s["bmin"])) or bool(np.any(pos >= s["bmax"])):
             return F(0)
+        return self._value_at(pos) * self.dsf
+
+    def value_world(self, p_world):
+        """getValueAtPoint of this slot at a world-space position without the density wrapper (temperature grid: no bounding-box
+        test, no density scale)."""
+        return self._value_at(_mul_point(np.asarray(p_world, dtype=F), self.slot["w2m"]))
+
+    def _value_at(self, pos):
+        s = self.slot
         lev = s["top_lev"]
         vmin, link = self._node(lev, 0)
         while lev > 0:
@@ -584,7 +593,7 @@ class Witness:
                 return F(0)
             lev -= 1
             vmin, link = self._node(lev, child)
-        return self.tex.linear(link, pos - vmin) * self.dsf
+        return self.tex.linear(link, pos - vmin)
 
     def _node(self, lev, idx):
         n = self.slot["nodes"][lev][idx]

@@ -19,6 +19,9 @@ default option family).
                                 LightHelpers.slang:196-244, emissive triangles F/.../EmissivePowerSampler.slang:57-92 +
                                 EmissiveLightSamplerHelpers.slang:56-101, alias draw F/Utils/Sampling/AliasTable.slang:56-70,
                                 computeRayOrigin F/Utils/Helpers.slang:92-105), evaluate_L_in_volume VR/ReSTIRHelper.slang:443-496
+  volume emission               EmissionWorldSpace / ConvertTempToColor VR/VolumeBase.slang:196-232 (temperature grid = slot 16, 128-texel
+                                black-body table F/Scene/Scene.cpp:2877-2892), the emission-vs-scatter draw and the emissive scatter
+                                vertex of VR/ComputeInitialSample.slang:267-334, encodeEmissivePosition VR/ReSTIRHelper.slang:9-19
   final shading (K5)            VR/FinalShading.cs.slang:95-141, finalOptions VR/VolumetricReSTIR.cpp:484-496
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
@@ -81,11 +84,11 @@ class Frame:
         if density == 0:
             return np.zeros(3, F)
         vis = self._transmittance(final, "camera", o, d, float(depth))
-        Fv = (vis * density * np.array(vol.sigma_s[:], dtype=F)).astype(F)
+        Fv = (vis * density * np.array((vol.sigma_a if light_id == SELF_EMISSION else vol.sigma_s)[:], dtype=F)).astype(F)
         if not bool(np.any(Fv > 0)):
             return Fv
         if light_id == SELF_EMISSION:
-            raise NotImplementedError("witness does not cover volume emission")
+            return (Fv * emission_world(self, pw)).astype(F)
         if light_id >= 0:
             return (Fv * eval_L_in_volume(self, self.lights, pw, -d, light_id, light_uv, final)).astype(F)
         zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
@@ -201,45 +204,7 @@ def _new_reservoir():
 
 def _initial_candidate(frame, d, hd, pd, tr, rng, mips):
     """ComputeInitialSample for one bounce: the candidate at distance hd along the camera ray (pdf pd, transmittance tr)."""
-    P, vol, o = frame.P, frame.grid.volume, frame.origin
-    out = _new_reservoir()
-    out["M"] = F(1)
-    valid = hd != K_RAY_TMAX
-    path_pdf = F(F(1) * pd)
-    out["depth"] = hd if valid else K_RAY_TMAX
-    out["p_y"] = path_pdf
-    sig_s, sig_a = np.array(vol.sigma_s[:], dtype=F), np.array(vol.sigma_a[:], dtype=F)
-    if valid:
-        pw = (o + d * hd).astype(F)
-        density = frame.wit(0).density_world(pw)
-        if density == 0:
-            out["p_y"] = F(0); out["runningSum"] = F(0)
-            return out
-        albedo = (sig_s / F(vol.sigma_t)).astype(F)
-        Ld, light_pdf, out["lightID"], out["lightUV"] = _sample_direct_lighting(frame, pw, -d, rng, mips)
-        p_src = out["p_y"]
-        lum_e = lw.luminance(((F(1) - albedo) * np.zeros(3, F)).astype(F))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            ratio = F(lum_e / (lum_e + lw.luminance((albedo * Ld).astype(F))))
-        if np.isnan(ratio):
-            ratio = F(0)
-        if rng.next1d() < ratio:
-            p_src = F(p_src * ratio); out["lightID"] = SELF_EMISSION
-        else:
-            p_src = F(p_src * (light_pdf * (F(1) - ratio)))
-        out["runningSum"] = F(0) if p_src == 0 else F(1)
-        out["p_y"] = p_src
-        path_phat = F(F(F(1) * tr) * density)
-        p_y = F(path_phat * lw.luminance(((sig_s * Ld) * light_pdf).astype(F)))
-        if out["runningSum"] > 0:
-            out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
-            out["p_y"] = p_y
-    else:
-        Le = lw.env_eval(frame.sc.envMap, d, frame.sc.envMapIntensity)
-        p_y = F(F(F(1) * tr) * lw.luminance(Le))
-        out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
-        out["p_y"] = p_y
-    return out
+    return _initial_path(frame, d, hd, pd, tr, rng, mips)[0]
 
 
 def initial_sampling_pixel(frame, px, py, frame_count, importance_mips):
@@ -426,22 +391,34 @@ def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
         return Fv
     if background:
         return (Fv * lw.env_eval(frame.sc.envMap, d, frame.sc.envMapIntensity)).astype(F)
-    assert (int(r["sampledPixel"]) >> 16) & 0xF == 0 and light_id != SELF_EMISSION
+    emissive_path = (int(r["sampledPixel"]) >> 16) & 0xF == 1
+    if no_reuse and bounces == 0 and light_id == SELF_EMISSION:
+        raise NotImplementedError
+    sig_a = np.array(vol.sigma_a[:], dtype=F)
     wo = -d
     for b in range(bounces):
         wi, dist = decode_wi_dist(extra[b])
-        if dist == K_RAY_TMAX:
+        emissive_vertex = emissive_path and b == bounces - 1
+        if emissive_vertex:                                # the vertex itself is stored, in (lightID, lightUV)
+            vertex = decode_emissive_position(light_id, light_uv)
+            disp = (vertex - p).astype(F)
+            dist = np.sqrt(F(np.dot(disp, disp))).astype(F)
+            wi = (disp / dist).astype(F)
+        elif dist == K_RAY_TMAX:
             return np.zeros(3, F)
         Fv = (Fv * F(lw.phase_hg(float(np.dot(wo, wi)), g))).astype(F)
         if bool(np.all(Fv == 0)):
             return np.zeros(3, F)
         origin = p
-        p = (origin + wi * dist).astype(F)
+        p = vertex if emissive_vertex else (origin + wi * dist).astype(F)
+        sig = sig_a if emissive_vertex else sig_s
         if no_reuse:
-            Fv = (Fv * (F(1) * (sig_s / F(vol.sigma_t)).astype(F))).astype(F)
+            Fv = (Fv * (F(1) * (sig / F(vol.sigma_t)).astype(F))).astype(F)
         else:
             scatter_density = max(F(0), frame.wit(0).density_world(p))
-            Fv = (Fv * (scatter_density * sig_s)).astype(F)
+            Fv = (Fv * (scatter_density * sig)).astype(F)
+        if emissive_vertex:
+            Fv = (Fv * (F(1) / F(dist * dist))).astype(F)
         if bool(np.all(Fv == 0)):
             return np.zeros(3, F)
         if not no_reuse:
@@ -449,6 +426,8 @@ def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
         wo = -wi
         if bool(np.all(Fv == 0)):
             return np.zeros(3, F)
+    if emissive_path:
+        return (Fv * emission_world(frame, p)).astype(F)
     return (Fv * eval_L_in_volume(frame, frame.lights, p, wo, light_id, light_uv, final)).astype(F)
 
 
@@ -528,17 +507,32 @@ def _initial_path(frame, d, hd, pd, tr, rng, mips, no_reuse=False):
             if B > 1:
                 wi, pdf_dir = lw.sample_phase(vol.PhaseFunctionConstantG, wo, rng.next1d(), rng.next1d())
                 pdf_dir = F(pdf_dir)
-            rng.next1d()                                   # emission-vs-scatter draw; no emission here, so always scatter
-            p_src = F(out["p_y"] * (light_pdf * (F(1) - F(0))))
+            Le = emission_world(frame, p) if (vol.hasEmission and density > 0) else np.zeros(3, F)
+            lum_e = lw.luminance(((F(1) - albedo) * Le).astype(F))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ratio = F(lum_e / (lum_e + lw.luminance((albedo * Ld).astype(F))))
+            if np.isnan(ratio):
+                ratio = F(0)
+            if rng.next1d() < ratio:                       # emission vs in-scattering: an RIS step of its own
+                p_src = F(out["p_y"] * ratio); out["lightID"] = SELF_EMISSION
+            else:
+                p_src = F(out["p_y"] * (light_pdf * (F(1) - ratio)))
             out["runningSum"] = F(0) if p_src == 0 else F(1)
             out["p_y"] = p_src
             path_phat = F(F(path_phat * Tr) * density)
-            p_y = F(path_phat * lw.luminance(((sig_s * Ld) * light_pdf).astype(F)))
+            if out["lightID"] == SELF_EMISSION:
+                p_y = F(path_phat * lw.luminance((np.array(vol.sigma_a[:], dtype=F) * Le).astype(F)))
+            else:
+                p_y = F(path_phat * lw.luminance(((sig_s * Ld) * light_pdf).astype(F)))
             path_phat = F(path_phat * F(lw.luminance(sig_s) * pdf_dir))
             if no_reuse:
                 p_y = F(p_y / F(vol.sigma_t)); path_phat = F(path_phat / F(vol.sigma_t))
             if out["runningSum"] > 0:
                 out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
+                if out["lightID"] == SELF_EMISSION and bounce > 0:   # an emissive scatter vertex is stored as a position: area measure
+                    out["lightID"], out["lightUV"] = encode_emissive_position(p)
+                    p_y = F(p_y / F(cur * cur))
+                    out["sampledPixel"] = (1 << 16) | (out["sampledPixel"] & ~0xF0000)
                 out["p_y"] = p_y
             path_pdf = F(path_pdf * pdf_dir)
             if bounce < B - 1:
@@ -744,3 +738,33 @@ def eval_L_in_volume(frame, lights, p, wo, light_id, light_uv, final=False):
         Ld = ((((ls["Le"] * lights.mult) * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))) * ls["cos"]) / F(ray_dist * ray_dist)).astype(F)
     tr = frame._transmittance(final, "light", p, ray_dir, float(ray_dist))
     return (tr * Ld).astype(F)
+
+
+# ---------------------------------------------------------------- volume emission ----------------------------------------------------------------
+
+def emission_world(frame, p):
+    """EmissionWorldSpace: black-body colour of the temperature at p (trilinear point query of the temperature grid, linear lookup
+    in the 128-texel table with border 0), times LeScale."""
+    vol = frame.grid.volume
+    if not vol.hasEmission:
+        return np.zeros(3, F)
+    temp = frame.wit(16).value_world(p)
+    temp = min(F(6400), F(F(temp - F(vol.temperatureCutOff)) * F(vol.temperatureScale)))
+    q = F(F(temp - F(25)) / F(6400))
+    lut = np.ctypeslib.as_array(frame.grid.blackbody_lut, shape=(128, 4))
+    x = F(q * F(128) - F(0.5))
+    x0 = np.floor(x)
+    fx, i0 = F(x - x0), int(x0)
+    tex = lambda i: np.zeros(3, F) if i < 0 or i > 127 else lut[i, :3].astype(F)
+    a, b = tex(i0), tex(i0 + 1)
+    rgb = np.array([F(np.float64(fx) * np.float64(F(b[k] - a[k])) + np.float64(a[k])) for k in range(3)], dtype=F)
+    return (F(vol.LeScale) * rgb).astype(F)
+
+
+def encode_emissive_position(pos):
+    """encodeEmissivePosition: (lightID = bits of z, lightUV = xy)."""
+    return int(np.array([pos[2]], dtype=F).view(np.int32)[0]), np.array([pos[0], pos[1]], dtype=F)
+
+
+def decode_emissive_position(light_id, light_uv):
+    return np.array([light_uv[0], light_uv[1], np.array([light_id], dtype=np.int32).view(F)[0]], dtype=F)

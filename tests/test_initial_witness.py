@@ -206,3 +206,62 @@ def test_analytic_and_emissive_lights_match_the_slang_witness(B):
         assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
         np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, got, extra[y, x]), rtol=2e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_volume_emission_matches_the_slang_witness(B):
+    """A plume with a temperature grid (BASELINE's configuration 3 in small): black-body emission at the scatter point, the
+    emission-vs-scatter draw, self-emission samples (sigma_a * Le) and — with several bounces — emissive scatter vertices stored as
+    positions in (lightID, lightUV) with the path tag, through p-hat and the final shading."""
+    from volumetricrestirrelease_b200 import Scene
+    w, h = 40, 30
+    sc = Scene()
+    sc.addGVDBVolume(sigma_a=(6, 6, 6), sigma_s=(14, 14, 14), g=0.0, dataFile="plume", numMips=4, densityScale=0.1, hasVelocity=True,
+                     hasEmission=True, LeScale=0.3, temperatureCutoff=1.0, temperatureScale=100.0, dim=(64, 96, 64), seed=3, voxelSize=1.0)
+    sc.setEnvMap((128, 64), seed=7)
+    sc.setEnvMapIntensity(0.5)
+    sc.frame_camera(1.0)
+    params = VolumetricReSTIRParams(mEnableSpatialReuse=0, mMaxBounces=B, mInitialM=4)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()
+    frame_count = op.frame_count()
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    extra = op.get_buffer(capi.BUF_EXTRA_0).view(np.float32).reshape(h, w, B - 1, 3).copy() if B > 1 else np.zeros((h, w, 1, 3), np.float32)
+    op.execute_stage(5, 0, color)
+    imp = op.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
+    mips, off, dim = [], 0, 512
+    while dim >= 1:
+        mips.append(imp[off:off + dim * dim].reshape(dim, dim).copy()); off += dim * dim; dim //= 2
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(10)
+    vol = (res["runningSum"] > 0) & (res["depth"] < 1e37)
+    tag = (res["sampledPixel"] >> 16) & 0xF
+    depth_of = res["sampledPixel"] >> 20
+    groups = [(vol & (depth_of == 0) & (res["lightID"] == -3), 5), (vol & (tag == 0) & (res["lightID"] != -3), 5)]
+    if B > 1:
+        groups.append((vol & (tag == 1), 5))
+    picks = []
+    for mask, n in groups:
+        ys, xs = np.nonzero(mask)
+        assert len(ys) >= n, len(ys)
+        picks += [(int(xs[i]), int(ys[i])) for i in rng.permutation(len(ys))[:n]]
+    for x, y in picks:
+        got = res[y, x]
+        want, want_extra = sw.initial_sampling_pixel_paths(frame, x, y, frame_count, mips) if B > 1 else (sw.initial_sampling_pixel(frame, x, y, frame_count, mips), None)
+        assert int(got["sampledPixel"]) == want["sampledPixel"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        k = int(got["sampledPixel"]) >> 20
+        if k:
+            np.testing.assert_allclose(extra[y, x, :k], want_extra[:k], rtol=1e-5, atol=3e-6)
+        if (int(got["sampledPixel"]) >> 16) & 0xF == 1:          # the stored vertex position (z as bits in lightID)
+            np.testing.assert_allclose(sw.decode_emissive_position(int(got["lightID"]), got["lightUV"]),
+                                       sw.decode_emissive_position(want["lightID"], want["lightUV"]), rtol=1e-5, atol=1e-5)
+        else:
+            assert int(got["lightID"]) == want["lightID"]
+            np.testing.assert_allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=3e-6)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=3e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=2e-4, abs=1e-12), (x, y)
+        np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, got, extra[y, x]), rtol=3e-4, atol=1e-9)
