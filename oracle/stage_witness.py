@@ -134,23 +134,51 @@ def _resample_step(tap, state, rng):
     state["runningSum"] = F(state["runningSum"] + w)
     sel = bool(rng.next1d() * state["runningSum"] < w)
     if sel:
-        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel"):
+        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel") + (("src",) if "src" in tap else ()):
             state[k] = tap[k]
     return sel
 
 
-def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0):
+def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0, extra_in=None):
     """SpatialReuse.cs.slang main() for one pixel (Talbot MIS or none, R2 sampler).  res_in: (H, W) structured reservoirs;
-    features: (H, W) structured {noReflectiveSurface, transmittance}.  Returns the output reservoir as a dict."""
+    features: (H, W) structured {noReflectiveSurface, transmittance}.  Returns the output reservoir as a dict.  With extra_in
+    ((H, W, B-1, 3) extra-bounce records: MAX_BOUNCES > 1) the targets are evaluated on whole paths and the result is
+    (reservoir, the extra-bounce records of the pixel the selected sample came from)."""
     P, w, h = frame.P, frame.w, frame.h
     talbot = P.mSpatialMISMethod == 1
     rec = lambda r: dict(runningSum=F(r["runningSum"]), M=F(r["M"]), depth=F(r["depth"]), p_y=F(r["p_y"]),
                          lightUV=np.array(r["lightUV"], dtype=F), lightID=int(r["lightID"]), sampledPixel=int(r["sampledPixel"]))
+    if extra_in is not None:
+        out = _spatial_reuse_pixel(_PathTargets(frame, extra_in), rec, res_in, features, px, py, frame_count, round_id)
+        src = out.pop("src", (px, py))
+        return out, extra_in[src[1], src[0]].copy()
+    return _spatial_reuse_pixel(frame, rec, res_in, features, px, py, frame_count, round_id)
+
+
+class _PathTargets:
+    """p-hat over whole paths: the extra-bounce records travel with the tap's source pixel."""
+
+    def __init__(self, frame, extra):
+        self.frame, self.extra = frame, extra
+        self.P, self.w, self.h, self.ray_dir = frame.P, frame.w, frame.h, frame.ray_dir
+
+    def p_hat_tap(self, d, tap):
+        x, y = tap["src"]
+        return F(lw.luminance(eval_F_path(self.frame, d, tap, self.extra[y, x])))
+
+
+def _spatial_reuse_pixel(frame, rec, res_in, features, px, py, frame_count, round_id):
+    P, w, h = frame.P, frame.w, frame.h
+    talbot = P.mSpatialMISMethod == 1
+    paths = isinstance(frame, _PathTargets)
+    p_hat = (lambda d, tap: frame.p_hat_tap(d, tap)) if paths else (lambda d, tap: frame.p_hat(d, tap["depth"], tap["lightUV"], tap["lightID"]))
     r2_seed = ((P.mSpatialReuseRounds + 1) * frame_count + round_id) % 16
     round_offset = int(bool(P.mEnableTemporalReuse)) + 1
     num_rounds = P.mSpatialReuseRounds + round_offset + 1
     rng = Xoshiro(px, py, num_rounds * frame_count + round_id + round_offset)
     center = rec(res_in[py, px])
+    if paths:
+        center["src"] = (px, py)
     if features[py, px]["transmittance"] == 1.0:          # IsSelfBackground: passed through
         return center
     output = dict(runningSum=F(0), M=F(0), depth=K_RAY_TMAX, p_y=F(0), lightUV=np.zeros(2, F), lightID=0, sampledPixel=0) if talbot else center
@@ -163,9 +191,11 @@ def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0
         if not inside(tx, ty):
             continue
         tap = rec(res_in[ty, tx])
+        if paths:
+            tap["src"] = (tx, ty)
         neighbor_py = tap["p_y"]
         if s > 0 and tap["runningSum"] != 0:            # resampleNeighborSpatialReuse
-            ph = frame.p_hat(d0, tap["depth"], tap["lightUV"], tap["lightID"])
+            ph = p_hat(d0, tap)
             with np.errstate(divide="ignore", invalid="ignore"):
                 weight = F(ph / tap["p_y"])
             if np.isinf(weight) or np.isnan(weight):
@@ -187,7 +217,7 @@ def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0
                 elif s == j:
                     p_qi = F(tap2["p_y"]); p_sum = F(p_sum + F(tap2["p_y"]) * m2)
                 else:
-                    p_y = frame.p_hat(frame.ray_dir(jx, jy), tap["depth"], tap["lightUV"], tap["lightID"])
+                    p_y = p_hat(frame.ray_dir(jx, jy), tap)
                     if np.isinf(p_y) or np.isnan(p_y):
                         p_y = F(0)
                     p_sum = F(p_sum + p_y * m2)
@@ -242,15 +272,24 @@ def _resample_step_max_m(tap, max_m, state, rng):
     state["runningSum"] = F(state["runningSum"] + w)
     sel = bool(rng.next1d() * state["runningSum"] < w)
     if sel:
-        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel"):
+        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel") + (("src",) if "src" in tap else ()):
             state[k] = tap[k]
     return sel
 
 
-def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, frame_count, prev_cam=None):
+def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, frame_count, prev_cam=None, extra_cur=None, extra_prev=None):
     """TemporalReuse.cs.slang main() for one pixel of a frame with history.  prev_cam: (posW, U, V, W, view[16], proj[16]) of the
-    previous frame (default: the current camera, i.e. a static camera).  Returns the reservoir K2 leaves in the current buffer."""
+    previous frame (default: the current camera, i.e. a static camera).  Returns the reservoir K2 leaves in the current buffer; with
+    extra_cur / extra_prev ((H, W, B-1, 3) extra-bounce records of the two frames) the targets are whole paths and the result is
+    (reservoir, extra-bounce records of the selected sample)."""
     P, w, h = frame.P, frame.w, frame.h
+    paths = extra_cur is not None
+
+    def target(direction, tap, depth=None):
+        if not paths:
+            return frame.p_hat(direction, tap["depth"] if depth is None else depth, tap["lightUV"], tap["lightID"])
+        t = dict(tap) if depth is None else dict(tap, depth=depth)
+        return F(lw.luminance(eval_F_path(frame, direction, t, tap["extra"])))
     rec = lambda r: dict(runningSum=F(r["runningSum"]), M=F(r["M"]), depth=F(r["depth"]), p_y=F(r["p_y"]),
                          lightUV=np.array(r["lightUV"], dtype=F), lightID=int(r["lightID"]), sampledPixel=int(r["sampledPixel"]))
     cam = frame.sc.camera.data(w, h)
@@ -261,6 +300,8 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
     total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
     rng = Xoshiro(px, py, total_rounds * frame_count + 1)          # gRoundOffset = numInitialSamplingRounds
     taps = [rec(res_cur[py, px]), None]
+    if paths:
+        taps[0]["extra"] = extra_cur[py, px].copy()
     d = frame.ray_dir(px, py)
     o = frame.origin
     output = _new_reservoir() if talbot else dict(taps[0])
@@ -284,13 +325,15 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
         tf = feat_prev.reshape(-1)[idx] if idx < w * h else None          # out-of-range structured-buffer reads return 0
         tap_bg = tf is not None and tf["transmittance"] == 1.0 and bool(tf["noReflectiveSurface"])
         if is_bg and not tap_bg:
-            return taps[0]                                            # K1's reservoir stays
+            return (taps[0], taps[0].pop("extra")) if paths else taps[0]     # K1's reservoir stays
         scr_i = (int(np.trunc(scr[0])), int(np.trunc(scr[1])))
         reproj = scr_i
         if 0 <= scr_i[0] < w and 0 <= scr_i[1] < h:
             taps[1] = rec(res_prev[scr_i[1], scr_i[0]]); fallback = False
     if fallback:
         reproj = (px, py); taps[1] = rec(res_prev[py, px])
+    if paths:
+        taps[1]["extra"] = extra_prev[reproj[1], reproj[0]].copy()
     max_prev_m = F(F(P.mTemporalReuseMThreshold) * taps[0]["M"])
 
     def prev_dir(x, y):
@@ -315,7 +358,7 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
             if np.isnan(taps[i]["runningSum"]) or np.isinf(taps[i]["runningSum"]):
                 taps[i]["runningSum"] = F(0)
             if i > 0 and taps[i]["runningSum"] != 0:               # resampleNeighbor on the current ray
-                ph = frame.p_hat(d, taps[i]["depth"], taps[i]["lightUV"], taps[i]["lightID"])
+                ph = target(d, taps[i])
                 with np.errstate(divide="ignore", invalid="ignore"):
                     weight = F(ph / taps[i]["p_y"])
                 if np.isinf(weight) or np.isnan(weight):
@@ -336,7 +379,7 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
                     used_depth = center_prev_depth
                     frame.origin = p_pos
                     try:
-                        p_y = frame.p_hat(prev_dir(*reproj), used_depth, taps[i]["lightUV"], taps[i]["lightID"])
+                        p_y = target(prev_dir(*reproj), taps[i], used_depth)
                     finally:
                         frame.origin = saved_origin
                     if np.isinf(p_y) or np.isnan(p_y):
@@ -345,7 +388,10 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
             if p_sum > 0:
                 mis = F(p_qi * k / p_sum)
         taps[i]["runningSum"] = F(taps[i]["runningSum"] * mis)
-        _resample_step_max_m(taps[i], max_prev_m, output, rng)
+        if _resample_step_max_m(taps[i], max_prev_m, output, rng) and paths:
+            output["extra"] = taps[i]["extra"]
+    if paths:
+        return output, output.pop("extra", taps[0]["extra"])
     return output
 
 

@@ -124,3 +124,86 @@ def test_temporal_reuse_matches_the_slang_witness(kw, move):
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
         from_history += float(got["M"]) > float(res_cur[y, x]["M"])
     assert from_history >= 8            # the history really took part
+
+
+def test_spatial_reuse_of_multi_bounce_paths_matches_the_slang_witness():
+    """K3 with MAX_BOUNCES = 3: the targets of the taps are whole paths (vertex loop of evaluate_F_ on the tap's extra-bounce
+    records, re-evaluated from the centre pixel's and every other tap's camera ray), and the selected sample's records travel with it."""
+    w, h, B = 40, 30, 3
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.12, env_size=(128, 64), g=0.3)
+    params = VolumetricReSTIRParams(mMaxBounces=B, mSpatialSampleCount=3)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()
+    frame_count = op.frame_count()
+    for stage in (0, 1, 2):
+        op.execute_stage(stage, 0, color)
+    res_in = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    extra_in = op.get_buffer(capi.BUF_EXTRA_0).view(np.float32).reshape(h, w, B - 1, 3).copy()
+    feat = op.get_buffer(capi.BUF_FEATURES).view(FEAT).reshape(h, w).copy()
+    op.execute_stage(3, 0, color)
+    res_out = op.get_buffer(capi.BUF_RESERVOIR_1).view(RES).reshape(h, w)
+    extra_out = op.get_buffer(capi.BUF_EXTRA_1).view(np.float32).reshape(h, w, B - 1, 3)
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(12)
+    ys, xs = np.nonzero((feat["transmittance"] != 1.0) & ((res_out["sampledPixel"] >> 20) > 0))
+    assert len(ys) >= 8
+    changed = 0
+    for k in rng.permutation(len(ys))[:8]:
+        x, y = int(xs[k]), int(ys[k])
+        got = res_out[y, x]
+        want, want_extra = sw.spatial_reuse_pixel(frame, res_in, feat, x, y, frame_count, extra_in=extra_in)
+        assert int(got["lightID"]) == want["lightID"] and int(got["sampledPixel"]) == want["sampledPixel"], (x, y)
+        assert float(got["M"]) == float(want["M"]) and float(got["depth"]) == float(want["depth"]), (x, y)
+        assert np.array_equal(np.asarray(got["lightUV"], np.float32), want["lightUV"]), (x, y)
+        n = int(got["sampledPixel"]) >> 20
+        assert np.array_equal(extra_out[y, x, :n], want_extra[:n]), (x, y)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=1e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        changed += float(got["depth"]) != float(res_in[y, x]["depth"])
+    assert changed >= 2
+
+
+def test_temporal_reuse_of_multi_bounce_paths_matches_the_slang_witness():
+    """K2 with MAX_BOUNCES = 3 and a camera that moved: the history sample's path is re-evaluated from the current camera ray, the
+    current sample's path from the previous frame's ray (primary depth converted between the two rays), and the records of the
+    selected path end up in the current frame's extra-bounce buffer."""
+    w, h, B = 40, 30, 3
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.12, env_size=(128, 64), g=0.3)
+    params = VolumetricReSTIRParams(mMaxBounces=B)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    cam0 = sc.camera.data(w, h)
+    prev_cam = tuple(np.array(getattr(cam0, k)[:], dtype=np.float32) for k in ("posW", "cameraU", "cameraV", "cameraW", "viewMat", "projMat"))
+    pos = np.array(sc.camera.position); sc.camera.position = tuple(pos + np.array([0.2, -0.1, 0.1]))
+    op.updateCamera()
+    frame_count = op.frame_count()
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    get = lambda b, t: op.get_buffer(b).view(t)
+    res_cur, res_prev = get(capi.BUF_RESERVOIR_0, RES).reshape(h, w).copy(), get(capi.BUF_RESERVOIR_TEMPORAL, RES).reshape(h, w).copy()
+    extra_cur = get(capi.BUF_EXTRA_0, np.float32).reshape(h, w, B - 1, 3).copy()
+    extra_prev = get(capi.BUF_EXTRA_TEMPORAL, np.float32).reshape(h, w, B - 1, 3).copy()
+    feat_cur, feat_prev = get(capi.BUF_FEATURES, FEAT).reshape(h, w).copy(), get(capi.BUF_FEATURES_TEMPORAL, FEAT).reshape(h, w).copy()
+    op.execute_stage(2, 0, color)
+    res_out = get(capi.BUF_RESERVOIR_0, RES).reshape(h, w)
+    extra_out = get(capi.BUF_EXTRA_0, np.float32).reshape(h, w, B - 1, 3)
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(13)
+    ys, xs = np.nonzero((feat_cur["transmittance"] != 1.0) & ((res_out["sampledPixel"] >> 20) > 0))
+    assert len(ys) >= 10
+    from_history = 0
+    for k in rng.permutation(len(ys))[:10]:
+        x, y = int(xs[k]), int(ys[k])
+        got = res_out[y, x]
+        want, want_extra = sw.temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, x, y, frame_count, prev_cam, extra_cur, extra_prev)
+        assert int(got["lightID"]) == want["lightID"] and int(got["sampledPixel"]) == want["sampledPixel"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        n = int(got["sampledPixel"]) >> 20
+        assert np.array_equal(extra_out[y, x, :n], want_extra[:n]), (x, y)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        from_history += not np.array_equal(extra_out[y, x, :n], extra_cur[y, x, :n])
+    assert from_history >= 2
