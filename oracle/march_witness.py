@@ -76,10 +76,10 @@ class _Texture:
     def __init__(self, slot):
         self.s = slot
 
-    def texel(self, brick, ix, iy, iz):
+    def texel(self, brick, ix, iy, iz, ch=0):
         if not (-1 <= ix <= 8 and -1 <= iy <= 8 and -1 <= iz <= 8):
             return F(0)   # only reachable through the checked fetches; inside the apron block by construction otherwise
-        return F(self.s["atlas"][brick * self.s["channels"] * 1000 + ((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1)])
+        return F(self.s["atlas"][(brick * self.s["channels"] + ch) * 1000 + ((iz + 1) * 10 + (iy + 1)) * 10 + (ix + 1)])
 
     def decode(self, raw):
         return F(raw * K_UNORM8) if self.s["format"] == 1 else raw
@@ -87,12 +87,12 @@ class _Texture:
     def point(self, brick, p):
         return self.decode(self.texel(brick, int(np.floor(p[0])), int(np.floor(p[1])), int(np.floor(p[2]))))
 
-    def linear(self, brick, p):
+    def linear(self, brick, p, ch=0):
         q = p - F(0.5)
         f0 = np.floor(q)
         i = [int(f0[0]), int(f0[1]), int(f0[2])]
         fr = q - f0
-        v = [[[self.texel(brick, i[0] + dx, i[1] + dy, i[2] + dz) for dx in (0, 1)] for dy in (0, 1)] for dz in (0, 1)]
+        v = [[[self.texel(brick, i[0] + dx, i[1] + dy, i[2] + dz, ch) for dx in (0, 1)] for dy in (0, 1)] for dz in (0, 1)]
         c = [[_lerp(v[dz][dy][0], v[dz][dy][1], fr[0]) for dy in (0, 1)] for dz in (0, 1)]
         d = [_lerp(c[dz][0], c[dz][1], fr[1]) for dz in (0, 1)]
         return self.decode(_lerp(d[0], d[1], fr[2]))
@@ -539,14 +539,16 @@ class DecompositionAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:606-707 (Deco
 
 
 class Witness:
-    def __init__(self, grid_desc, slot_index):
+    def __init__(self, grid_desc, slot_index, volume_desc=None, mip=None):
+        """volume_desc / mip: for the previous frame's grids, which the shaders bind at slot offsets 19 (density) / 11 (temperature,
+        velocity) under the CURRENT frame's volume description."""
         self.slot = slot_arrays(grid_desc.slots[slot_index])
-        v = grid_desc.volume
+        v = grid_desc.volume if volume_desc is None else volume_desc
         self.sigma_t = F(v.sigma_t)
         self.dsf = F(v.densityScaleFactorByScaling)
         self.tStepBase = F(v.tStep) * F(v.volumeWorldScaling)
         self.tex = _Texture(self.slot)
-        self.mip = slot_index
+        self.mip = slot_index if mip is None else mip
         # F/Scene/Scene.cpp:3077-3080: 8 voxels times the length of the medium-to-world scale, from slot 0
         m2w = np.linalg.inv(np.array(list(grid_desc.slots[0].world_to_medium), dtype=np.float64).reshape(4, 4))
         self.superVoxelDiagonal = F(8.0 * np.sqrt((m2w[:3, :3] ** 2).sum()))
@@ -572,12 +574,12 @@ class Witness:
             return F(0)
         return self._value_at(pos) * self.dsf
 
-    def value_world(self, p_world):
-        """getValueAtPoint of this slot at a world-space position without the density wrapper (temperature grid: no bounding-box
-        test, no density scale)."""
-        return self._value_at(_mul_point(np.asarray(p_world, dtype=F), self.slot["w2m"]))
+    def value_world(self, p_world, ch=0):
+        """getValueAtPoint of this slot at a world-space position without the density wrapper (temperature / velocity grids: no
+        bounding-box test, no density scale)."""
+        return self._value_at(_mul_point(np.asarray(p_world, dtype=F), self.slot["w2m"]), ch)
 
-    def _value_at(self, pos):
+    def _value_at(self, pos, ch=0):
         s = self.slot
         lev = s["top_lev"]
         vmin, link = self._node(lev, 0)
@@ -593,7 +595,7 @@ class Witness:
                 return F(0)
             lev -= 1
             vmin, link = self._node(lev, child)
-        return self.tex.linear(link, pos - vmin)
+        return self.tex.linear(link, pos - vmin, ch)
 
     def _node(self, lev, idx):
         n = self.slot["nodes"][lev][idx]

@@ -50,11 +50,27 @@ class Frame:
         self.U, self.V, self.Wv = (np.array(getattr(cam, k)[:], dtype=F) for k in ("cameraU", "cameraV", "cameraW"))
         self._wit = {}
         self.lights = None              # a Lights instance when the scene has analytic / emissive lights
+        self.prev_grid = None           # the previous frame's grid description of an animated volume (slots 19.. / 27 / 28)
+        self.last_frame = False         # isLastFrame of the evaluation in progress
 
     def wit(self, mip):
+        """The march witness of a slot; while an isLastFrame evaluation with usePrevGridForReproj is in progress, density slots
+        resolve to the previous frame's grids (offset 19) and the temperature grid to slot 27."""
+        if self.last_frame and self.prev_grid is not None and self.P.mUsePrevVolumeForReproj:
+            mip = mip + (11 if mip >= 16 else 19)
         if mip not in self._wit:
-            self._wit[mip] = Witness(self.grid, mip)
+            if mip >= 19:
+                src = mip - 11 if mip >= 27 else mip - 19
+                self._wit[mip] = Witness(self.prev_grid, src, self.grid.volume, mip)
+            else:
+                self._wit[mip] = Witness(self.grid, mip)
         return self._wit[mip]
+
+    def velocity_world(self, p):
+        """VelocityWorld (VR/VolumeBase.slang:183-194): trilinear 3-channel point query of slot 17, rotated to world space."""
+        v = np.array([self.wit(17).value_world(p, ch) for ch in range(3)], dtype=F)
+        M = np.array(self.grid.volume.externalModelToWorld[:], dtype=F).reshape(4, 4)
+        return np.array([v[0] * M[0, j] + v[1] * M[1, j] + v[2] * M[2, j] + F(0) * M[3, j] for j in range(3)], dtype=F)
 
     def ray_dir(self, px, py):
         p = np.array([(F(px) + F(0.5)) / F(self.w), (F(py) + F(0.5)) / F(self.h)], dtype=F)
@@ -312,6 +328,9 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
         if depth == K_RAY_TMAX and P.mTemporalReprojectionMode != 2 and not is_bg:
             depth = frame.wit(8 + P.mTemporalReprojectionMipLevel).rejection_sample_point(o, d, rng)
         pw = (o + d * depth).astype(F)
+        vol = frame.grid.volume
+        if vol.hasVelocity and frame.prev_grid is not None:       # hasAnimation: where was this point one frame ago
+            pw = (pw - (frame.velocity_world(pw) * F(vol.velocityScale)).astype(F)).astype(F)
         view = np.array([pw[0] * p_view[0 + j] + pw[1] * p_view[4 + j] + pw[2] * p_view[8 + j] + F(1) * p_view[12 + j] for j in range(4)], dtype=F)
         clip = np.array([view[0] * p_proj[0 + j] + view[1] * p_proj[4 + j] + view[2] * p_proj[8 + j] + view[3] * p_proj[12 + j] for j in range(4)], dtype=F)
         if depth == K_RAY_TMAX:
@@ -377,11 +396,11 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
                     p_qi = neighbor_py; p_sum = F(p_sum + neighbor_py * cm)
                 else:                                             # i == 0, j == 1: the current sample seen from the previous frame's ray
                     used_depth = center_prev_depth
-                    frame.origin = p_pos
+                    frame.origin, frame.last_frame = p_pos, True
                     try:
                         p_y = target(prev_dir(*reproj), taps[i], used_depth)
                     finally:
-                        frame.origin = saved_origin
+                        frame.origin, frame.last_frame = saved_origin, False
                     if np.isinf(p_y) or np.isnan(p_y):
                         p_y = F(0)
                     p_sum = F(p_sum + p_y * cm)
@@ -792,7 +811,8 @@ def emission_world(frame, p):
     """EmissionWorldSpace: black-body colour of the temperature at p (trilinear point query of the temperature grid, linear lookup
     in the 128-texel table with border 0), times LeScale."""
     vol = frame.grid.volume
-    if not vol.hasEmission:
+    use_prev = frame.last_frame and frame.prev_grid is not None and bool(frame.P.mUsePrevVolumeForReproj)
+    if not (frame.prev_grid.volume.hasEmission if use_prev else vol.hasEmission):
         return np.zeros(3, F)
     temp = frame.wit(16).value_world(p)
     temp = min(F(6400), F(F(temp - F(vol.temperatureCutOff)) * F(vol.temperatureScale)))

@@ -207,3 +207,60 @@ def test_temporal_reuse_of_multi_bounce_paths_matches_the_slang_witness():
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
         from_history += not np.array_equal(extra_out[y, x, :n], extra_cur[y, x, :n])
     assert from_history >= 2
+
+
+@pytest.mark.parametrize("use_prev", [1, 0])
+def test_temporal_reuse_on_an_animated_volume_matches_the_slang_witness(use_prev):
+    """BASELINE's configuration 3 in small: the volume advances between the frames (density, temperature and velocity grids), so K2
+    moves the reprojection point back along the velocity field and — with mUsePrevVolumeForReproj — evaluates the current sample on
+    the previous frame's ray in the previous frame's grids (density slots 19.., temperature slot 27)."""
+    from volumetricrestirrelease_b200 import Scene
+
+    def plume(t):
+        sc = Scene()
+        sc.addGVDBVolume(sigma_a=(6, 6, 6), sigma_s=(14, 14, 14), g=0.0, dataFile="plume", numMips=4, densityScale=0.1, hasVelocity=True,
+                         hasEmission=True, LeScale=0.3, temperatureCutoff=1.0, temperatureScale=100.0, dim=(64, 96, 64), seed=3, voxelSize=1.0,
+                         frameTime=t)
+        sc.setEnvMap((128, 64), seed=7)
+        sc.setEnvMapIntensity(0.5)
+        sc.frame_camera(1.0)
+        return sc
+    w, h = 40, 30
+    sc, nxt = plume(0.0), plume(0.6)
+    params = VolumetricReSTIRParams(mUsePrevVolumeForReproj=use_prev)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    cam0 = sc.camera.data(w, h)
+    prev_cam = tuple(np.array(getattr(cam0, k)[:], dtype=np.float32) for k in ("posW", "cameraU", "cameraV", "cameraW", "viewMat", "projMat"))
+    prev_volume = sc.volume                                     # advanceVolume rebinds sc.volume
+    op.advanceVolume(nxt.volume)
+    pos = np.array(sc.camera.position); sc.camera.position = tuple(pos + np.array([0.6, -0.4, 0.3]))
+    op.updateCamera()
+    frame_count = op.frame_count()
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    get = lambda b, t: op.get_buffer(b).view(t).reshape(h, w).copy()
+    res_cur, res_prev = get(capi.BUF_RESERVOIR_0, RES), get(capi.BUF_RESERVOIR_TEMPORAL, RES)
+    feat_cur, feat_prev = get(capi.BUF_FEATURES, FEAT), get(capi.BUF_FEATURES_TEMPORAL, FEAT)
+    op.execute_stage(2, 0, color)
+    res_out = get(capi.BUF_RESERVOIR_0, RES)
+    frame = sw.Frame(sc, params, w, h)
+    frame.grid, frame.prev_grid = nxt.volume.grid.contents, prev_volume.grid.contents
+    rng = np.random.default_rng(14)
+    vol = feat_cur["transmittance"] != 1.0
+    picks = []
+    for mask, n in ((vol & (res_out["lightID"] == -3), 4), (vol & (res_out["lightID"] != -3) & (res_out["depth"] < 1e37), 6), (vol & (res_cur["depth"] > 1e37), 2)):
+        ys, xs = np.nonzero(mask)
+        assert len(ys) >= n, len(ys)
+        picks += [(int(xs[k]), int(ys[k])) for k in rng.permutation(len(ys))[:n]]
+    from_history = 0
+    for x, y in picks:
+        got = res_out[y, x]
+        want = sw.temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, x, y, frame_count, prev_cam)
+        assert int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        from_history += float(got["M"]) > float(res_cur[y, x]["M"])
+    assert from_history >= 8
