@@ -22,6 +22,8 @@ default option family).
   volume emission               EmissionWorldSpace / ConvertTempToColor VR/VolumeBase.slang:196-232 (temperature grid = slot 16, 128-texel
                                 black-body table F/Scene/Scene.cpp:2877-2892), the emission-vs-scatter draw and the emissive scatter
                                 vertex of VR/ComputeInitialSample.slang:267-334, encodeEmissivePosition VR/ReSTIRHelper.slang:9-19
+  reference path tracer         IntegrateByVolumePathTracing VR/VolumePathTracingFunctions.slang:3-131, directLighting
+                                VR/VolumeUtils.slang:417-447, the gUseReference branch of VR/TraceRays.cs.slang:85-103
   final shading (K5)            VR/FinalShading.cs.slang:95-141, finalOptions VR/VolumetricReSTIR.cpp:484-496
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
@@ -834,3 +836,56 @@ def encode_emissive_position(pos):
 
 def decode_emissive_position(light_id, light_uv):
     return np.array([light_uv[0], light_uv[1], np.array([light_id], dtype=np.int32).view(F)[0]], dtype=F)
+
+
+# ---------------------------------------------------------------- the reference path tracer (mUseReference) ----------------------------------------------------------------
+
+def path_trace_pixel(frame, px, py, frame_count, importance_mips):
+    """TraceRays.cs.slang with gUseReference: gBaselineSamplePerPixel paths by decomposition tracking on mip 0 with next-event
+    estimation at every vertex (residual ratio tracking for the shadow rays), emission collected along the way, Russian roulette
+    from the third vertex on.  Returns the pixel's radiance (float3)."""
+    P, vol = frame.P, frame.grid.volume
+    lights = frame.lights if frame.lights is not None else Lights(frame.sc)
+    total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
+    rng = Xoshiro(px, py, total_rounds * frame_count)
+    g = vol.PhaseFunctionConstantG
+    albedo = (np.array(vol.sigma_s[:], dtype=F) / F(vol.sigma_t)).astype(F)
+    n_light = max(1, P.mInitialLightSamples)
+    avg = np.zeros(3, F)
+    for _ in range(P.mBaselineSamplePerPixel):
+        origin, direction = frame.origin, frame.ray_dir(px, py)
+        beta, L = np.ones(3, F), np.zeros(3, F)
+        bounce, B = 0, P.mMaxBounces
+        while bounce < B:
+            t = frame.wit(0).sample_supervoxel(origin, direction, rng)
+            if t is not None:
+                p = (origin + direction * F(t)).astype(F)
+                L = (L + (emission_world(frame, p) * (F(1) - albedo)) * beta).astype(F)
+                beta = (beta * albedo).astype(F)
+                Ld = np.zeros(3, F)
+                for _s in range(n_light):
+                    ls = sample_scene_lights(frame, lights, p, rng, importance_mips)
+                    if not ls["valid"]:
+                        continue
+                    vis = F(frame.wit(0).residual_ratio_tracking(p, ls["rayDir"], float(ls["rayDistance"]), rng))
+                    Li = (ls["Li"] * vis).astype(F)
+                    Ld = (Ld + (F(lw.phase_hg(float(np.dot(-direction, ls["dir"])), g)) * Li) / F(1)).astype(F)
+                Ld = (Ld / F(n_light)).astype(F)
+                L = (L + beta * Ld).astype(F)
+                wi = None
+                if B > 1:
+                    wi, _pdf = lw.sample_phase(g, -direction, rng.next1d(), rng.next1d())
+                if bounce < B - 1:
+                    origin, direction = p, wi
+                    if P.mInitialUseRussianRoulette and bounce >= 2:
+                        if rng.next1d() < albedo[0]:
+                            beta = (beta / albedo[0]).astype(F)
+                        else:
+                            bounce = B
+            else:
+                if bounce == 0:
+                    L = (L + beta * lw.env_eval(frame.sc.envMap, direction, frame.sc.envMapIntensity)).astype(F)
+                bounce = B
+            bounce += 1
+        avg = (avg + L).astype(F)
+    return (avg / F(P.mBaselineSamplePerPixel)).astype(F)

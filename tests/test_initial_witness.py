@@ -265,3 +265,45 @@ def test_volume_emission_matches_the_slang_witness(B):
         assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=3e-4, abs=1e-12), (x, y)
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=2e-4, abs=1e-12), (x, y)
         np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, got, extra[y, x]), rtol=3e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("B,emission", [(1, False), (4, False), (3, True)])
+def test_reference_path_tracer_matches_the_slang_witness(B, emission):
+    """mUseReference (the ground truth of the unbiasedness tests): paths by decomposition tracking, next-event estimation with
+    residual-ratio-tracked shadow rays at every vertex, emission along the way, Russian roulette — same random-number stream, so the
+    same paths: the radiance of single pixels agrees to rounding."""
+    from volumetricrestirrelease_b200 import Scene
+    w, h = 40, 30
+    if emission:
+        sc = Scene()
+        sc.addGVDBVolume(sigma_a=(6, 6, 6), sigma_s=(14, 14, 14), g=0.2, dataFile="plume", numMips=4, densityScale=0.1, hasVelocity=True,
+                         hasEmission=True, LeScale=0.3, temperatureCutoff=1.0, temperatureScale=100.0, dim=(64, 96, 64), seed=3, voxelSize=1.0)
+        sc.setEnvMap((128, 64), seed=7); sc.setEnvMapIntensity(0.5); sc.frame_camera(1.0)
+    else:
+        sc = env_scene(dim=(64, 64, 56), density_scale=0.1, env_size=(128, 64), g=0.4)
+    lo, hi = sc.volume_bounds_world()
+    sc.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
+    params = VolumetricReSTIRParams(mUseReference=1, mMaxBounces=B, mBaselineSamplePerPixel=2, mUseAnalyticLights=1)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    frame_count = op.frame_count()
+    color = op.execute()
+    imp = op.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
+    mips, off, dim = [], 0, 512
+    while dim >= 1:
+        mips.append(imp[off:off + dim * dim].reshape(dim, dim).copy()); off += dim * dim; dim //= 2
+    frame = sw.Frame(sc, params, w, h)
+    mask_pass = vro.OraclePass(VolumetricReSTIRParams())          # only for K0's mask of the pixels whose ray meets the medium
+    mask_pass.setScene(sc, w, h)
+    mask_pass.execute_stage(0, 0, np.zeros((h, w, 4), np.float32))
+    inside = mask_pass.get_buffer(capi.BUF_FEATURES).view(FEAT).reshape(h, w)["transmittance"] < 0.9
+    rng = np.random.default_rng(15)
+    picks = []
+    for mask, n in ((inside, 12), (~inside, 2)):
+        ys, xs = np.nonzero(mask)
+        picks += [(int(xs[k]), int(ys[k])) for k in rng.permutation(len(ys))[:n]]
+    for x, y in picks:
+        want = sw.path_trace_pixel(frame, x, y, frame_count, mips)
+        np.testing.assert_allclose(color[y, x, :3], want, rtol=3e-4, atol=1e-7, err_msg=str((x, y)))
+        assert color[y, x, 3] == 1.0
