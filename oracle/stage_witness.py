@@ -54,6 +54,13 @@ class Frame:
         self.lights = None              # a Lights instance when the scene has analytic / emissive lights
         self.prev_grid = None           # the previous frame's grid description of an animated volume (slots 19.. / 27 / 28)
         self.last_frame = False         # isLastFrame of the evaluation in progress
+        self.final_rng = None           # the final shading's generator (stochastic trackers only)
+
+    def seed_final(self, px, py, frame_count):
+        """FinalShading.cs.slang:85: the pixel's generator of the last round of the frame."""
+        P = self.P
+        total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
+        self.final_rng = Xoshiro(px, py, total_rounds * frame_count + total_rounds - 1)
 
     def wit(self, mip):
         """The march witness of a slot; while an isLastFrame evaluation with usePrevGridForReproj is in progress, density slots
@@ -84,8 +91,17 @@ class Frame:
         """Ray-marched under the spatial options; exact transmittance of the trilinear mip-0 interpolant (analytic tracking, the
         default of the final shading, VR/VolumetricReSTIR.cpp:484-496) when `final`."""
         P = self.P
-        if final:
-            return F(self.wit(0).analytic(origin, direction, tmax, True))
+        if final:                                           # finalOptions: mip 0, trilinear, the configured tracker and sample count
+            method = P.mFinalVisibilityTrackingMethod if which == "camera" else P.mFinalLightTrackingMethod
+            if method == 1:
+                return F(self.wit(0).analytic(origin, direction, tmax, True))
+            if method == 2:
+                return F(self.wit(0).ray_marching(origin, direction, tmax, True, P.mFinalTStepScale))
+            n = P.mFinalVisibilitySamples if which == "camera" else P.mFinalLightSamples
+            total = F(0)
+            for _ in range(n):                              # ratio (0) / residual ratio (3) / analog residual ratio (4) tracking
+                total = F(total + F(self.wit(0).residual_ratio_tracking(origin, direction, tmax, self.final_rng, method == 4, method == 0)))
+            return F(total / F(n))
         if which == "camera":
             return F(self.wit(P.mSpatialVisibilityMipLevel).ray_marching(origin, direction, tmax, bool(P.mSpatialVisibilityUseLinearSampler), P.mSpatialVisibilityTStepScale))
         return F(self.wit(P.mSpatialLightingMipLevel).ray_marching(origin, direction, tmax, bool(P.mSpatialLightingUseLinearSampler), P.mSpatialLightingTStepScale))
@@ -119,8 +135,11 @@ class Frame:
     def p_hat(self, d, depth, light_uv, light_id):
         return F(lw.luminance(self.eval_F(d, depth, light_uv, light_id)))
 
-    def final_shading(self, px, py, r):
-        """FinalShading.cs.slang:95-141 for one pixel: F of the stored sample under the final options times the RIS weight W."""
+    def final_shading(self, px, py, r, frame_count=None):
+        """FinalShading.cs.slang:95-141 for one pixel: F of the stored sample under the final options times the RIS weight W.
+        frame_count is needed only when a final tracker draws random numbers."""
+        if frame_count is not None:
+            self.seed_final(px, py, frame_count)
         if not r["runningSum"] > 0:
             return np.zeros(3, F)
         col = self.eval_F(self.ray_dir(px, py), F(r["depth"]), np.asarray(r["lightUV"], dtype=F), int(r["lightID"]), final=True)
@@ -652,8 +671,10 @@ def initial_sampling_pixel_paths(frame, px, py, frame_count, importance_mips):
     return final, final_extra
 
 
-def final_shading_path(frame, px, py, r, extra):
+def final_shading_path(frame, px, py, r, extra, frame_count=None):
     """FinalShading.cs.slang for a multi-bounce reservoir."""
+    if frame_count is not None:
+        frame.seed_final(px, py, frame_count)
     if not r["runningSum"] > 0:
         return np.zeros(3, F)
     no_reuse = not frame.P.mEnableSpatialReuse and not frame.P.mEnableTemporalReuse

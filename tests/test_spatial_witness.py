@@ -264,3 +264,34 @@ def test_temporal_reuse_on_an_animated_volume_matches_the_slang_witness(use_prev
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
         from_history += float(got["M"]) > float(res_cur[y, x]["M"])
     assert from_history >= 8
+
+
+@pytest.mark.parametrize("kw", [
+    dict(mFinalVisibilityTrackingMethod=capi.kResidualRatioTracking, mFinalLightTrackingMethod=capi.kRatioTracking, mFinalVisibilitySamples=2, mFinalLightSamples=3),
+    dict(mFinalVisibilityTrackingMethod=capi.kRayMarching, mFinalLightTrackingMethod=capi.kAnalogResidualRatioTracking, mFinalLightSamples=2, mMaxBounces=3)])
+def test_final_shading_with_stochastic_trackers_matches_the_slang_witness(kw):
+    """K5 with random-walk transmittance estimators: the camera segment, (with several bounces) every path segment and the light
+    segment are estimated in that order from the pixel's last-round generator, n samples averaged each."""
+    w, h = 40, 30
+    B = kw.get("mMaxBounces", 1)
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.08, env_size=(128, 64), g=0.2)
+    params = VolumetricReSTIRParams(mEnableSpatialReuse=0, **kw)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    frame_count = op.frame_count()
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    extra = op.get_buffer(capi.BUF_EXTRA_0).view(np.float32).reshape(h, w, B - 1, 3).copy() if B > 1 else np.zeros((h, w, 1, 3), np.float32)
+    op.execute_stage(5, 0, color)
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(16)
+    ys, xs = np.nonzero((res["runningSum"] > 0) & (res["depth"] < 1e37))
+    lit = 0
+    for k in rng.permutation(len(ys))[:12]:
+        x, y = int(xs[k]), int(ys[k])
+        want = sw.final_shading_path(frame, x, y, res[y, x], extra[y, x], frame_count)
+        np.testing.assert_allclose(color[y, x, :3], want, rtol=2e-4, atol=1e-9, err_msg=str((x, y)))
+        lit += bool(want.sum() > 0)
+    assert lit >= 8
