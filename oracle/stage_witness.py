@@ -24,6 +24,9 @@ default option family).
                                 vertex of VR/ComputeInitialSample.slang:267-334, encodeEmissivePosition VR/ReSTIRHelper.slang:9-19
   reference path tracer         IntegrateByVolumePathTracing VR/VolumePathTracingFunctions.slang:3-131, directLighting
                                 VR/VolumeUtils.slang:417-447, the gUseReference branch of VR/TraceRays.cs.slang:85-103
+  vertex reuse (VERTEX_REUSE)   VR/ReSTIRHelper.slang:21-27,222-240,289-296,345-352,392-420, VR/ComputeInitialSample.slang:88-94,116-125,
+                                324-331, VR/Reservoir.slang:46-47: records hold world-space vertices from bounce S on, the path density turns
+                                to area measure at vertex S, p_partial = the suffix of p-hat past that vertex
   final shading (K5)            VR/FinalShading.cs.slang:95-141, finalOptions VR/VolumetricReSTIR.cpp:484-496
   spatial reuse                 VR/SpatialReuse.cs.slang:64-265, resampleNeighborSpatialReuse VR/ReSTIRHelper.slang:563-580,
                                 simpleResampleStep VR/Reservoir.slang:26-55, sample_disk F/Utils/Math/MathHelpers.slang:242-250,
@@ -171,12 +174,12 @@ def _resample_step(tap, state, rng):
     state["runningSum"] = F(state["runningSum"] + w)
     sel = bool(rng.next1d() * state["runningSum"] < w)
     if sel:
-        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel") + (("src",) if "src" in tap else ()):
+        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel") + tuple(x for x in ("src", "p_partial") if x in tap):
             state[k] = tap[k]
     return sel
 
 
-def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0, extra_in=None):
+def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0, extra_in=None, pp_in=None):
     """SpatialReuse.cs.slang main() for one pixel (Talbot MIS or none, R2 sampler).  res_in: (H, W) structured reservoirs;
     features: (H, W) structured {noReflectiveSurface, transmittance}.  Returns the output reservoir as a dict.  With extra_in
     ((H, W, B-1, 3) extra-bounce records: MAX_BOUNCES > 1) the targets are evaluated on whole paths and the result is
@@ -185,11 +188,30 @@ def spatial_reuse_pixel(frame, res_in, features, px, py, frame_count, round_id=0
     talbot = P.mSpatialMISMethod == 1
     rec = lambda r: dict(runningSum=F(r["runningSum"]), M=F(r["M"]), depth=F(r["depth"]), p_y=F(r["p_y"]),
                          lightUV=np.array(r["lightUV"], dtype=F), lightID=int(r["lightID"]), sampledPixel=int(r["sampledPixel"]))
+    if pp_in is not None:                                   # vertex reuse: the p_partial plane travels with the reservoirs
+        plain = res_in
+
+        class _WithPP:
+            def __getitem__(self, idx):
+                return _RecWithPP(plain[idx], pp_in[idx])
+        res_in = _WithPP()
+        rec = lambda r: dict(runningSum=F(r["runningSum"]), M=F(r["M"]), depth=F(r["depth"]), p_y=F(r["p_y"]), lightUV=np.array(r["lightUV"], dtype=F),
+                             lightID=int(r["lightID"]), sampledPixel=int(r["sampledPixel"]), p_partial=F(r["p_partial"]))
     if extra_in is not None:
         out = _spatial_reuse_pixel(_PathTargets(frame, extra_in), rec, res_in, features, px, py, frame_count, round_id)
         src = out.pop("src", (px, py))
         return out, extra_in[src[1], src[0]].copy()
     return _spatial_reuse_pixel(frame, rec, res_in, features, px, py, frame_count, round_id)
+
+
+class _RecWithPP:
+    """A structured reservoir record plus its p_partial."""
+
+    def __init__(self, r, pp):
+        self.r, self.pp = r, pp
+
+    def __getitem__(self, k):
+        return self.pp if k == "p_partial" else self.r[k]
 
 
 class _PathTargets:
@@ -201,7 +223,7 @@ class _PathTargets:
 
     def p_hat_tap(self, d, tap):
         x, y = tap["src"]
-        return F(lw.luminance(eval_F_path(self.frame, d, tap, self.extra[y, x])))
+        return F(lw.luminance(eval_F_path(self.frame, d, tap, self.extra[y, x], spatial_reuse=True)))
 
 
 def _spatial_reuse_pixel(frame, rec, res_in, features, px, py, frame_count, round_id):
@@ -266,7 +288,7 @@ def _spatial_reuse_pixel(frame, rec, res_in, features, px, py, frame_count, roun
 
 
 def _new_reservoir():
-    return dict(runningSum=F(0), M=F(0), depth=K_RAY_TMAX, p_y=F(0), lightUV=np.zeros(2, F), lightID=0, sampledPixel=0)
+    return dict(runningSum=F(0), M=F(0), depth=K_RAY_TMAX, p_y=F(0), lightUV=np.zeros(2, F), lightID=0, sampledPixel=0, p_partial=F(0))
 
 
 def _initial_candidate(frame, d, hd, pd, tr, rng, mips):
@@ -309,12 +331,13 @@ def _resample_step_max_m(tap, max_m, state, rng):
     state["runningSum"] = F(state["runningSum"] + w)
     sel = bool(rng.next1d() * state["runningSum"] < w)
     if sel:
-        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel") + (("src",) if "src" in tap else ()):
+        for k in ("depth", "p_y", "lightUV", "lightID", "sampledPixel") + tuple(x for x in ("src", "p_partial") if x in tap):
             state[k] = tap[k]
     return sel
 
 
-def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, frame_count, prev_cam=None, extra_cur=None, extra_prev=None):
+def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, frame_count, prev_cam=None, extra_cur=None, extra_prev=None,
+                         pp_cur=None, pp_prev=None):
     """TemporalReuse.cs.slang main() for one pixel of a frame with history.  prev_cam: (posW, U, V, W, view[16], proj[16]) of the
     previous frame (default: the current camera, i.e. a static camera).  Returns the reservoir K2 leaves in the current buffer; with
     extra_cur / extra_prev ((H, W, B-1, 3) extra-bounce records of the two frames) the targets are whole paths and the result is
@@ -325,8 +348,8 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
     def target(direction, tap, depth=None):
         if not paths:
             return frame.p_hat(direction, tap["depth"] if depth is None else depth, tap["lightUV"], tap["lightID"])
-        t = dict(tap) if depth is None else dict(tap, depth=depth)
-        return F(lw.luminance(eval_F_path(frame, direction, t, tap["extra"])))
+        t = tap if depth is None else dict(tap, depth=depth)       # resampleNeighbor takes the tap inout (p_partial is rewritten),
+        return F(lw.luminance(eval_F_path(frame, direction, t, tap["extra"])))     # evaluatePHatReadOnly a copy
     rec = lambda r: dict(runningSum=F(r["runningSum"]), M=F(r["M"]), depth=F(r["depth"]), p_y=F(r["p_y"]),
                          lightUV=np.array(r["lightUV"], dtype=F), lightID=int(r["lightID"]), sampledPixel=int(r["sampledPixel"]))
     cam = frame.sc.camera.data(w, h)
@@ -339,6 +362,8 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
     taps = [rec(res_cur[py, px]), None]
     if paths:
         taps[0]["extra"] = extra_cur[py, px].copy()
+    if pp_cur is not None:
+        taps[0]["p_partial"] = F(pp_cur[py, px])
     d = frame.ray_dir(px, py)
     o = frame.origin
     output = _new_reservoir() if talbot else dict(taps[0])
@@ -374,6 +399,8 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
         reproj = (px, py); taps[1] = rec(res_prev[py, px])
     if paths:
         taps[1]["extra"] = extra_prev[reproj[1], reproj[0]].copy()
+    if pp_prev is not None:
+        taps[1]["p_partial"] = F(pp_prev[reproj[1], reproj[0]])
     max_prev_m = F(F(P.mTemporalReuseMThreshold) * taps[0]["M"])
 
     def prev_dir(x, y):
@@ -454,12 +481,20 @@ def decode_wi_dist(rec):
     return np.array([x, y, wz], dtype=F), F(z)
 
 
-def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
+def _reuse_start(P):
+    """options.vertexReuseStartBounce, or None without VERTEX_REUSE (one bounce cannot be compiled with it)."""
+    return P.mVertexReuseStartBounce if (P.mVertexReuse and P.mMaxBounces > 1) else None
+
+
+def eval_F_path(frame, d, r, extra, final=False, no_reuse=False, spatial_reuse=False):
     """evaluate_F_ for a reservoir whose sample may be a multi-bounce path: r = the reservoir record, extra = its extra-bounce
     records (wi_dist), env-map light at the last vertex.  no_reuse (gNoReuse, final shading only): the path was drawn by
-    decomposition tracking, so densities and segment transmittances cancel against its pdf and only the albedo remains per vertex."""
+    decomposition tracking, so densities and segment transmittances cancel against its pdf and only the albedo remains per vertex.
+    With vertex reuse (S = mVertexReuseStartBounce): records from bounce S on are vertices; spatial_reuse multiplies the prefix up to
+    vertex S by r["p_partial"] instead of evaluating the suffix; otherwise r["p_partial"] is UPDATED (r must be a dict) to that suffix."""
     bounces = int(r["sampledPixel"]) >> 20
     depth, light_uv, light_id = F(r["depth"]), np.asarray(r["lightUV"], dtype=F), int(r["lightID"])
+    S = _reuse_start(frame.P)
     if not no_reuse and (bounces == 0 or depth == K_RAY_TMAX):
         return frame.eval_F(d, depth, light_uv, light_id, final)
     vol, o = frame.grid.volume, frame.origin
@@ -482,28 +517,40 @@ def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
         raise NotImplementedError
     sig_a = np.array(vol.sigma_a[:], dtype=F)
     wo = -d
+    prefix = np.ones(3, F)
     for b in range(bounces):
-        wi, dist = decode_wi_dist(extra[b])
         emissive_vertex = emissive_path and b == bounces - 1
-        if emissive_vertex:                                # the vertex itself is stored, in (lightID, lightUV)
-            vertex = decode_emissive_position(light_id, light_uv)
+        vertex = None
+        if S is not None and b + 1 >= S:                   # decodeWiDist(record, reuseAsVertex): a world-space vertex, or a miss
+            if extra[b][0] == K_RAY_TMAX:
+                return np.zeros(3, F)
+            vertex = np.array(extra[b], dtype=F)
+        else:
+            wi, dist = decode_wi_dist(extra[b])
+            if emissive_vertex:                            # the vertex itself is stored, in (lightID, lightUV)
+                vertex = decode_emissive_position(light_id, light_uv)
+            elif dist == K_RAY_TMAX:
+                return np.zeros(3, F)
+        if vertex is not None:
             disp = (vertex - p).astype(F)
             dist = np.sqrt(F(np.dot(disp, disp))).astype(F)
             wi = (disp / dist).astype(F)
-        elif dist == K_RAY_TMAX:
-            return np.zeros(3, F)
         Fv = (Fv * F(lw.phase_hg(float(np.dot(wo, wi)), g))).astype(F)
         if bool(np.all(Fv == 0)):
             return np.zeros(3, F)
+        if S is not None and b == S:
+            if spatial_reuse:
+                return (Fv * F(r["p_partial"])).astype(F)
+            prefix = Fv
         origin = p
-        p = vertex if emissive_vertex else (origin + wi * dist).astype(F)
+        p = vertex if vertex is not None else (origin + wi * dist).astype(F)
         sig = sig_a if emissive_vertex else sig_s
         if no_reuse:
             Fv = (Fv * (F(1) * (sig / F(vol.sigma_t)).astype(F))).astype(F)
         else:
             scatter_density = max(F(0), frame.wit(0).density_world(p))
             Fv = (Fv * (scatter_density * sig)).astype(F)
-        if emissive_vertex:
+        if (S is not None and b + 1 == S) or (emissive_vertex and (S is None or b + 1 < S)):
             Fv = (Fv * (F(1) / F(dist * dist))).astype(F)
         if bool(np.all(Fv == 0)):
             return np.zeros(3, F)
@@ -513,8 +560,18 @@ def eval_F_path(frame, d, r, extra, final=False, no_reuse=False):
         if bool(np.all(Fv == 0)):
             return np.zeros(3, F)
     if emissive_path:
-        return (Fv * emission_world(frame, p)).astype(F)
-    return (Fv * eval_L_in_volume(frame, frame.lights, p, wo, light_id, light_uv, final)).astype(F)
+        Fv = (Fv * emission_world(frame, p)).astype(F)
+    elif bool(np.any(Fv > 0)):
+        at_reuse_vertex = S is not None and bounces == S
+        report = {}
+        Fv = (Fv * eval_L_in_volume(frame, frame.lights, p, wo, light_id, light_uv, final,
+                                    tr_reuse=F(r["p_partial"]) if (at_reuse_vertex and spatial_reuse) else None, report=report)).astype(F)
+        if at_reuse_vertex and not spatial_reuse and "Tr" in report:
+            r["p_partial"] = report["Tr"]
+    if S is not None and bounces > S and not spatial_reuse:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r["p_partial"] = F(lw.luminance((Fv / prefix).astype(F)))
+    return Fv
 
 
 def _sample_direct_lighting(frame, p, wo, rng, mips):
@@ -574,13 +631,19 @@ def _initial_path(frame, d, hd, pd, tr, rng, mips, no_reuse=False):
         if p is None:
             p = (origin + direction * cur).astype(F)
         path_pdf = F(path_pdf * pdf_dist)
+        S = _reuse_start(P)
+        if S is not None and bounce == S and valid:        # area measure at the reuse vertex
+            path_pdf = F(path_pdf / F(cur * cur)); path_phat = F(path_phat / F(cur * cur))
         if bounce == 0:
             out["depth"] = cur if valid else K_RAY_TMAX
             primary_depth = out["depth"]
         else:
             out["depth"] = primary_depth
             out["sampledPixel"] = bounce << 20
-            extra[bounce - 1] = encode_wi_dist(direction, cur if valid else K_RAY_TMAX)
+            if S is None or bounce < S:
+                extra[bounce - 1] = encode_wi_dist(direction, cur if valid else K_RAY_TMAX)
+            else:
+                extra[bounce - 1] = p if valid else np.full(3, K_RAY_TMAX, F)
         out["p_y"] = path_pdf
         density = (F(1) if no_reuse else frame.wit(0).density_world(p)) if valid else F(0)
         hit_empty = False
@@ -616,8 +679,9 @@ def _initial_path(frame, d, hd, pd, tr, rng, mips, no_reuse=False):
             if out["runningSum"] > 0:
                 out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
                 if out["lightID"] == SELF_EMISSION and bounce > 0:   # an emissive scatter vertex is stored as a position: area measure
-                    out["lightID"], out["lightUV"] = encode_emissive_position(p)
-                    p_y = F(p_y / F(cur * cur))
+                    if S is None or bounce < S:
+                        out["lightID"], out["lightUV"] = encode_emissive_position(p)
+                        p_y = F(p_y / F(cur * cur))
                     out["sampledPixel"] = (1 << 16) | (out["sampledPixel"] & ~0xF0000)
                 out["p_y"] = p_y
             path_pdf = F(path_pdf * pdf_dir)
@@ -806,8 +870,9 @@ def sample_direct_lighting(frame, lights, p, wo, rng, mips):
     return (F(lw.phase_hg(float(np.dot(wo, ls["dir"])), g)) * Li / F(1)).astype(F), ls["pdfArea"], ls["lightID"], ls["lightUV"]
 
 
-def eval_L_in_volume(frame, lights, p, wo, light_id, light_uv, final=False):
-    """evaluate_L_in_volume: transmittance to the stored light sample times its radiance times the phase function, float3."""
+def eval_L_in_volume(frame, lights, p, wo, light_id, light_uv, final=False, tr_reuse=None, report=None):
+    """evaluate_L_in_volume: transmittance to the stored light sample times its radiance times the phase function, float3.
+    tr_reuse: lightVisibilityReuse (the stored transmittance replaces the march); report["Tr"] receives the transmittance used."""
     g = frame.grid.volume.PhaseFunctionConstantG
     if light_id < 0:
         zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
@@ -824,7 +889,9 @@ def eval_L_in_volume(frame, lights, p, wo, light_id, light_uv, final=False):
             return np.zeros(3, F)
         ray_dir, ray_dist = ls["dir"], ls["distance"]
         Ld = ((((ls["Le"] * lights.mult) * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))) * ls["cos"]) / F(ray_dist * ray_dist)).astype(F)
-    tr = frame._transmittance(final, "light", p, ray_dir, float(ray_dist))
+    tr = frame._transmittance(final, "light", p, ray_dir, float(ray_dist)) if tr_reuse is None else F(tr_reuse)
+    if report is not None:
+        report["Tr"] = tr
     return (tr * Ld).astype(F)
 
 

@@ -307,3 +307,47 @@ def test_reference_path_tracer_matches_the_slang_witness(B, emission):
         want = sw.path_trace_pixel(frame, x, y, frame_count, mips)
         np.testing.assert_allclose(color[y, x, :3], want, rtol=3e-4, atol=1e-7, err_msg=str((x, y)))
         assert color[y, x, 3] == 1.0
+
+
+@pytest.mark.parametrize("B,S", [(4, 2), (3, 1)])
+def test_vertex_reuse_matches_the_slang_witness(B, S):
+    """VERTEX_REUSE: from bounce S on the extra-bounce records hold world-space vertices, the path density switches to area measure
+    at vertex S, and the p-hat evaluation after K1 leaves the suffix past that vertex in p_partial (the light transmittance when the
+    path ends at vertex S, luminance(F / prefix) when it goes on); the final shading re-evaluates the whole path."""
+    w, h = 40, 30
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.12, env_size=(128, 64), g=0.3)
+    params = VolumetricReSTIRParams(mEnableSpatialReuse=0, mMaxBounces=B, mVertexReuse=1, mVertexReuseStartBounce=S, mInitialM=3)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()
+    frame_count = op.frame_count()
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    extra = op.get_buffer(capi.BUF_EXTRA_0).view(np.float32).reshape(h, w, B - 1, 3).copy()
+    pp = op.get_buffer(capi.BUF_PPARTIAL_0).view(np.float32).reshape(h, w).copy()
+    op.execute_stage(5, 0, color)
+    imp = op.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
+    mips, off, dim = [], 0, 512
+    while dim >= 1:
+        mips.append(imp[off:off + dim * dim].reshape(dim, dim).copy()); off += dim * dim; dim //= 2
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(17)
+    depth_of = res["sampledPixel"] >> 20
+    picks = []
+    for k in range(B):
+        ys, xs = np.nonzero((res["runningSum"] > 0) & (depth_of == k) & (res["depth"] < 1e37))
+        assert len(ys) >= 3, (k, len(ys))
+        picks += [(int(xs[i]), int(ys[i])) for i in rng.permutation(len(ys))[:4]]
+    for x, y in picks:
+        got = res[y, x]
+        want, want_extra = sw.initial_sampling_pixel_paths(frame, x, y, frame_count, mips)
+        assert int(got["sampledPixel"]) == want["sampledPixel"] and int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        k = int(got["sampledPixel"]) >> 20
+        np.testing.assert_allclose(extra[y, x, :k], want_extra[:k], rtol=1e-5, atol=1e-5)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        if k >= S:
+            assert float(pp[y, x]) == pytest.approx(float(want["p_partial"]), rel=2e-4, abs=1e-12), (x, y, k)
+        np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, dict(want), extra[y, x]), rtol=3e-4, atol=1e-9)

@@ -295,3 +295,58 @@ def test_final_shading_with_stochastic_trackers_matches_the_slang_witness(kw):
         np.testing.assert_allclose(color[y, x, :3], want, rtol=2e-4, atol=1e-9, err_msg=str((x, y)))
         lit += bool(want.sum() > 0)
     assert lit >= 8
+
+
+def test_reuse_with_vertex_reuse_matches_the_slang_witness():
+    """K2 and K3 with VERTEX_REUSE (B = 4, S = 2): temporal reuse re-evaluates whole paths and rewrites p_partial of the history
+    sample; spatial reuse evaluates only the prefix up to the reuse vertex on the new camera ray and multiplies by the stored
+    p_partial; the selected sample's p_partial travels with it."""
+    w, h, B, S = 40, 30, 4, 2
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.12, env_size=(128, 64), g=0.3)
+    params = VolumetricReSTIRParams(mMaxBounces=B, mVertexReuse=1, mVertexReuseStartBounce=S, mSpatialSampleCount=3)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    op.execute()
+    cam0 = sc.camera.data(w, h)
+    prev_cam = tuple(np.array(getattr(cam0, k)[:], dtype=np.float32) for k in ("posW", "cameraU", "cameraV", "cameraW", "viewMat", "projMat"))
+    pos = np.array(sc.camera.position); sc.camera.position = tuple(pos + np.array([0.2, -0.1, 0.1]))
+    op.updateCamera()
+    frame_count = op.frame_count()
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = lambda b: op.get_buffer(b).view(RES).reshape(h, w).copy()
+    ext = lambda b: op.get_buffer(b).view(np.float32).reshape(h, w, B - 1, 3).copy()
+    ppl = lambda b: op.get_buffer(b).view(np.float32).reshape(h, w).copy()
+    feat = lambda b: op.get_buffer(b).view(FEAT).reshape(h, w).copy()
+    cur = (res(capi.BUF_RESERVOIR_0), ext(capi.BUF_EXTRA_0), ppl(capi.BUF_PPARTIAL_0))
+    prev = (res(capi.BUF_RESERVOIR_TEMPORAL), ext(capi.BUF_EXTRA_TEMPORAL), ppl(capi.BUF_PPARTIAL_TEMPORAL))
+    feat_cur, feat_prev = feat(capi.BUF_FEATURES), feat(capi.BUF_FEATURES_TEMPORAL)
+    op.execute_stage(2, 0, color)
+    k2 = (res(capi.BUF_RESERVOIR_0), ext(capi.BUF_EXTRA_0), ppl(capi.BUF_PPARTIAL_0))
+    op.execute_stage(3, 0, color)
+    k3 = (res(capi.BUF_RESERVOIR_1), ext(capi.BUF_EXTRA_1), ppl(capi.BUF_PPARTIAL_1))
+    frame = sw.Frame(sc, params, w, h)
+    rng = np.random.default_rng(18)
+
+    def check(got_planes, x, y, want, want_extra, tag):
+        got = got_planes[0][y, x]
+        assert int(got["lightID"]) == want["lightID"] and int(got["sampledPixel"]) == want["sampledPixel"] and float(got["M"]) == float(want["M"]), (tag, x, y)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (tag, x, y)
+        n = int(got["sampledPixel"]) >> 20
+        assert np.array_equal(got_planes[1][y, x, :n], want_extra[:n]), (tag, x, y)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=3e-4, abs=1e-12), (tag, x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=2e-4, abs=1e-12), (tag, x, y)
+        if n >= S:
+            assert float(got_planes[2][y, x]) == pytest.approx(float(want["p_partial"]), rel=3e-4, abs=1e-12), (tag, x, y)
+        return n
+
+    for tag, out in (("temporal", k2), ("spatial", k3)):
+        ys, xs = np.nonzero((feat_cur["transmittance"] != 1.0) & ((out[0]["sampledPixel"] >> 20) >= S))
+        assert len(ys) >= 8, tag
+        for k in rng.permutation(len(ys))[:8]:
+            x, y = int(xs[k]), int(ys[k])
+            if tag == "temporal":
+                want, we = sw.temporal_reuse_pixel(frame, cur[0], prev[0], feat_cur, feat_prev, x, y, frame_count, prev_cam, cur[1], prev[1], cur[2], prev[2])
+            else:
+                want, we = sw.spatial_reuse_pixel(frame, k2[0], feat_cur, x, y, frame_count, extra_in=k2[1], pp_in=k2[2])
+            assert check(out, x, y, want, we, tag) >= S
