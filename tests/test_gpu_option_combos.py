@@ -1,0 +1,70 @@
+"""GPU-vs-oracle staged parity on RANDOM COMBINATIONS of the option surface (tests/test_gpu_options.py varies one option at a
+time): every seed draws each option independently from its table, builds the scene the draw asks for (phase anisotropy, a point
+light, emissive triangles) and runs two frames stage by stage with a moving camera.  Seeds are fixed, so a failure reproduces."""
+import numpy as np
+import pytest
+
+from common import FLIP_BUDGET, capi, check_staged, env_scene, staged
+from volumetricrestirrelease_b200 import VolumetricReSTIRParams
+
+pytestmark = pytest.mark.gpu
+
+W, H = 96, 64
+
+TABLE = {
+    "mMaxBounces": [1, 2, 3, 4],
+    "mInitialM": [1, 3, 4, 6],
+    "mInitialBaseMipLevel": [0, 1, 2],
+    "mInitialVisibilityUseLinearSampler": [0, 0, 1],
+    "mInitialLightingMipLevel": [1, 2],
+    "mInitialLightingTrackingMethod": [capi.kRayMarching, capi.kRayMarching, capi.kAnalyticTracking, capi.kResidualRatioTracking],
+    "mInitialLightSamples": [0, 1, 1],
+    "mInitialUseRussianRoulette": [0, 1],
+    "mInitialUseCoarserGridForIndirectBounce": [0, 1],
+    "mTemporalMISMethod": [capi.kMISNone, capi.kMISTalbot],
+    "mTemporalReuseMThreshold": [1.0, 4.0, 10.0],
+    "mTemporalReprojectionMode": [capi.kReprojectionLinear, capi.kReprojectionLinear, capi.kReprojectionNone, capi.kReprojectionNoBackground],
+    "mSpatialMISMethod": [capi.kMISNone, capi.kMISTalbot],
+    "mSpatialReuseRounds": [1, 2],
+    "mSpatialSampleCount": [2, 4, 5],
+    "mSampleRadius": [4.0, 10.0, 17.0],
+    "mRandomSamplerType": [capi.kR2, capi.kHammersley],
+    "mSpatialVisibilityTrackingMethod": [capi.kRayMarching, capi.kRayMarching, capi.kAnalyticTracking, capi.kRatioTracking],
+    "mSpatialLightingTrackingMethod": [capi.kRayMarching, capi.kRayMarching, capi.kAnalyticTracking, capi.kResidualRatioTracking],
+    "mSpatialVisibilityMipLevel": [1, 2],
+    "mSpatialLightingMipLevel": [1, 2],
+    "mSpatialVisibilityUseLinearSampler": [0, 1, 1],
+    "mSpatialLightingUseLinearSampler": [0, 1, 1],
+    "mSpatialVisibilityTStepScale": [0.5, 1.0, 2.0],
+    "mFinalVisibilityTrackingMethod": [capi.kAnalyticTracking, capi.kAnalyticTracking, capi.kRayMarching, capi.kResidualRatioTracking],
+    "mFinalLightTrackingMethod": [capi.kAnalyticTracking, capi.kAnalyticTracking, capi.kRatioTracking],
+    "mFinalLightSamples": [1, 2],
+    "mVertexReuse": [0, 0, 1],
+    "mVertexReuseStartBounce": [1, 2],
+}
+
+
+def _draw(seed):
+    rng = np.random.default_rng(1000 + seed)
+    kw = {k: v[int(rng.integers(len(v)))] for k, v in TABLE.items()}
+    scene = dict(g=[0.0, 0.5, -0.3][int(rng.integers(3))], point_light=bool(rng.integers(2)), emissive=bool(rng.integers(3) == 0))
+    if kw["mVertexReuseStartBounce"] >= kw["mMaxBounces"]:
+        kw["mVertexReuseStartBounce"] = 1
+    kw["mUseAnalyticLights"], kw["mUseEmissiveLights"] = int(scene["point_light"]), int(scene["emissive"])
+    return kw, scene
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_option_combination_staged(seed):
+    kw, scene = _draw(seed)
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.15, g=scene["g"])
+    lo, hi = sc.volume_bounds_world()
+    if scene["point_light"]:
+        sc.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
+    if scene["emissive"]:
+        sc.addEmissiveShell(300, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
+    p0 = np.array(sc.camera.position)
+    path = [tuple(p0 + np.array((0.7, 0.2, -0.3)) * 12.0 * f) for f in range(2)]
+    print(f"[combo {seed}] {kw} {scene}")
+    out = staged(VolumetricReSTIRParams(**kw), sc, W, H, frames=2, camera_path=path, own_tables=scene["emissive"])
+    check_staged(out, W, H, f"combo{seed}", budget=5 * FLIP_BUDGET)
