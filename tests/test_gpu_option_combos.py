@@ -1,15 +1,15 @@
 """GPU-vs-oracle staged parity on RANDOM COMBINATIONS of the option surface (tests/test_gpu_options.py varies one option at a
-time): every seed draws each option independently from its table, builds the scene the draw asks for (phase anisotropy, a point
-light, emissive triangles) and runs two frames stage by stage with a moving camera.  Seeds are fixed, so a failure reproduces."""
+time): every seed draws each option independently from its table, builds the scene the draw asks for (bunny cloud / emissive plume /
+three-level tree, phase anisotropy, a point light, emissive triangles, full or ragged frame), picks the task-stream path or the
+per-pixel kernels, and runs two frames stage by stage with a moving camera.  Seeds are fixed, so a failure reproduces."""
 import numpy as np
 import pytest
 
 from common import FLIP_BUDGET, capi, check_staged, env_scene, staged
-from volumetricrestirrelease_b200 import VolumetricReSTIRParams
+from volumetricrestirrelease_b200 import Scene, VolumetricReSTIRParams
 
 pytestmark = pytest.mark.gpu
 
-W, H = 96, 64
 
 TABLE = {
     "mMaxBounces": [1, 2, 3, 4],
@@ -51,13 +51,27 @@ def _draw(seed):
     if kw["mVertexReuseStartBounce"] >= kw["mMaxBounces"]:
         kw["mVertexReuseStartBounce"] = 1
     kw["mUseAnalyticLights"], kw["mUseEmissiveLights"] = int(scene["point_light"]), int(scene["emissive"])
+    rng2 = np.random.default_rng(5000 + seed)              # a second stream, so that the option draws above stay what they were
+    scene["kind"] = ["bunny", "bunny", "plume", "three_level"][int(rng2.integers(4))]
+    scene["path"] = ["task streams", "task streams", "per-pixel kernels"][int(rng2.integers(3))]
+    scene["frame"] = [(96, 64), (96, 64), (83, 47)][int(rng2.integers(3))]       # a ragged frame: partial tiles on both axes
     return kw, scene
 
 
 @pytest.mark.parametrize("seed", range(48))
 def test_random_option_combination_staged(seed):
     kw, scene = _draw(seed)
-    sc = env_scene(dim=(64, 64, 56), density_scale=0.15, g=scene["g"])
+    if scene["kind"] == "plume":                            # temperature grid: volume emission and self-emission samples
+        sc = Scene()
+        sc.addGVDBVolume(sigma_a=(6, 6, 6), sigma_s=(14, 14, 14), g=scene["g"], dataFile="plume", numMips=4, densityScale=0.1, hasVelocity=True,
+                         hasEmission=True, LeScale=0.05, temperatureCutoff=1.0, temperatureScale=100.0, dim=(64, 96, 64), seed=3, voxelSize=1.0)
+        sc.setEnvMap((256, 128), seed=7); sc.setEnvMapIntensity(0.5); sc.frame_camera(1.0)
+    elif scene["kind"] == "three_level":                    # a level-2 root above the 128-voxel nodes
+        sc = env_scene(dim=(200, 150, 140), density_scale=0.05, g=scene["g"])
+        assert sc.volume.grid.contents.slots[0].top_lev == 2
+    else:
+        sc = env_scene(dim=(64, 64, 56), density_scale=0.15, g=scene["g"])
+    W, H = scene["frame"]
     lo, hi = sc.volume_bounds_world()
     if scene["point_light"]:
         sc.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
@@ -66,5 +80,6 @@ def test_random_option_combination_staged(seed):
     p0 = np.array(sc.camera.position)
     path = [tuple(p0 + np.array((0.7, 0.2, -0.3)) * 12.0 * f) for f in range(2)]
     print(f"[combo {seed}] {kw} {scene}")
-    out = staged(VolumetricReSTIRParams(**kw), sc, W, H, frames=2, camera_path=path, own_tables=scene["emissive"])
+    out = staged(VolumetricReSTIRParams(**kw), sc, W, H, frames=2, camera_path=path, own_tables=scene["emissive"],
+                 dict_={"mUseWavefront": int(scene["path"] == "task streams")})
     check_staged(out, W, H, f"combo{seed}", budget=5 * FLIP_BUDGET)
