@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--vertex-reuse", type=int, default=0, help="mVertexReuse with this start bounce (0: off); the p_partial plane travels with the halos")
     ap.add_argument("--emissive", type=int, default=0, help="number of emissive triangles around the volume (mUseEmissiveLights)")
     ap.add_argument("--scratch-mb", type=int, default=0, help="mScratchBudgetMB of the sharded pass (small: the generic stages run in row chunks)")
+    ap.add_argument("--combo", type=int, default=-1, help="seed of a random option combination (the table of tests/test_gpu_option_combos.py)")
     a = ap.parse_args()
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -41,6 +42,20 @@ def main():
         lo, hi = scene.volume_bounds_world()
         scene.addEmissiveShell(a.emissive, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
         params.mUseEmissiveLights = 1
+    combo = ""
+    if a.combo >= 0:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+        from test_gpu_option_combos import _draw
+        kw, extra = _draw(a.combo)
+        for k, v in kw.items():
+            setattr(params, k, v)
+        lo, hi = scene.volume_bounds_world()
+        if extra["point_light"]:
+            scene.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
+        if extra["emissive"]:
+            scene.addEmissiveShell(300, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
+        combo = f" combo {a.combo} (bounces {params.mMaxBounces}, rounds {params.mSpatialReuseRounds}, taps {params.mSpatialSampleCount}, radius {params.mSampleRadius}, " \
+                f"vertex reuse {params.mVertexReuse}/{params.mVertexReuseStartBounce}, reprojection {params.mTemporalReprojectionMode}, lights env{'+point' if extra['point_light'] else ''}{'+emissive' if extra['emissive'] else ''})"
     d = {"mParams": params, "mPipelineFrames": a.level}
     if a.scratch_mb:
         d["mScratchBudgetMB"] = a.scratch_mb
@@ -72,7 +87,7 @@ def main():
     dist.all_reduce(t)
     if rank == 0:
         print(f"[check_sharded] world {world} bands {sp.bands} frames {a.frames} pipelining level {a.level} bounces {a.bounces} vertex reuse {a.vertex_reuse} "
-              f"emissive {a.emissive}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
+              f"emissive {a.emissive}{combo}: mismatching pixels = {int(t[0])}, lit fraction {lit:.3f}, "
               f"pipeline {gp.pipeline_stats()}, history all-gathers {sp.history_gathers}")
     dist.destroy_process_group()
     sys.exit(1 if int(t[0]) else 0)
