@@ -83,3 +83,51 @@ def test_random_option_combination_staged(seed):
     out = staged(VolumetricReSTIRParams(**kw), sc, W, H, frames=2, camera_path=path, own_tables=scene["emissive"],
                  dict_={"mUseWavefront": int(scene["path"] == "task streams")})
     check_staged(out, W, H, f"combo{seed}", budget=5 * FLIP_BUDGET)
+
+
+@pytest.mark.parametrize("seed", range(0, 48, 4))
+def test_random_option_combination_whole_frames_are_path_independent(seed):
+    """The same random combinations through the un-staged product call over four frames with an announced moving camera: the
+    pipelined frame (K0/K1 of frame f+1 ahead on their own stream, deferred K5), the serial frame and the per-pixel kernels must
+    produce the same bits on every frame."""
+    import copy
+    import torch
+    from volumetricrestirrelease_b200 import VolumetricReSTIR
+    kw, scene = _draw(seed)
+    sc = env_scene(dim=(64, 64, 56), density_scale=0.15, g=scene["g"])
+    lo, hi = sc.volume_bounds_world()
+    if scene["point_light"]:
+        sc.addPointLight(tuple(0.5 * (lo + hi) + np.array([0.2, 1.1, 0.4]) * (hi - lo)), (9000.0, 7000.0, 5000.0))
+    if scene["emissive"]:
+        sc.addEmissiveShell(300, tuple(0.5 * (lo + hi)), float(np.linalg.norm(hi - lo)) * 0.75, seed=4)
+    w, h, frames = scene["frame"][0] * 2, scene["frame"][1] * 2, 4
+    p0 = np.array(sc.camera.position)
+    path = [tuple(p0 + np.array((0.7, 0.2, -0.3)) * 6.0 * f) for f in range(frames + 1)]
+
+    def run(extra):
+        gp = VolumetricReSTIR.create(dict({"mParams": VolumetricReSTIRParams(**kw)}, **extra))
+        sc.camera.position = path[0]
+        gp.setScene(sc, w, h)
+        color = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        imgs = []
+        for f in range(frames):
+            sc.camera.position = path[f]
+            gp.updateCamera()
+            if extra.get("mPipelineFrames"):
+                nxt = copy.copy(sc.camera)
+                nxt.position = path[f + 1]
+                gp.setNextCamera(nxt)
+            gp.execute(color.data_ptr())
+            gp.wait_output()
+            imgs.append(color.cpu().numpy().view(np.uint32).copy())
+        torch.cuda.synchronize()
+        return imgs, gp.pipeline_stats()
+
+    serial, _ = run({"mPipelineFrames": 0})
+    pipelined, st = run({"mPipelineFrames": 2})
+    per_pixel, _ = run({"mPipelineFrames": 0, "mUseWavefront": 0})
+    assert st["adopted"] in (0, frames - 1) and st["discarded"] == 0      # K1 runs ahead only on its specialised task-stream path
+    for f in range(frames):
+        assert np.array_equal(pipelined[f], serial[f]), f"frame {f}: pipelined != serial"
+        assert np.array_equal(per_pixel[f], serial[f]), f"frame {f}: per-pixel kernels != task streams"
+    assert (serial[-1].view(np.float32)[..., :3].sum(-1) > 0).mean() > 0.05
