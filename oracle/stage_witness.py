@@ -152,8 +152,17 @@ class Frame:
 
 
 def neighbor_offset(P, sample_id, frame_id):
-    """generateNeighborOffset, R2 sequence (fp64 multiplier) + sample_disk, truncated to int2."""
-    if sample_id == 0:
+    """generateNeighborOffset: R2 sequence (fp64 multiplier) or Hammersley points (F/Utils/Helpers.slang:62-75) + sample_disk,
+    truncated to int2."""
+    if P.mRandomSamplerType == 0:                         # kHammersley (0; kR2 = 1): (i / N, bit-reversed i)
+        i = sample_id
+        i = ((i & 0x55555555) << 1) | ((i & 0xAAAAAAAA) >> 1)
+        i = ((i & 0x33333333) << 2) | ((i & 0xCCCCCCCC) >> 2)
+        i = ((i & 0x0F0F0F0F) << 4) | ((i & 0xF0F0F0F0) >> 4)
+        i = ((i & 0x00FF00FF) << 8) | ((i & 0xFF00FF00) >> 8)
+        i = ((i << 16) | (i >> 16)) & 0xFFFFFFFF
+        u = (F(F(sample_id) / F(P.mSpatialSampleCount)), F(F(i) * F(2.3283064365386963e-10)))
+    elif sample_id == 0:
         u = (F(0), F(0))
     else:
         m = float(frame_id * P.mSpatialSampleCount + sample_id)

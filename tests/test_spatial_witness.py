@@ -10,7 +10,8 @@ from oracle import vro
 from volumetricrestirrelease_b200 import VolumetricReSTIRParams, capi
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(mSpatialMISMethod=capi.kMISNone, mSampleRadius=6.0, mSpatialSampleCount=3)])
+@pytest.mark.parametrize("kw", [dict(), dict(mSpatialMISMethod=capi.kMISNone, mSampleRadius=6.0, mSpatialSampleCount=3),
+                                dict(mRandomSamplerType=capi.kHammersley, mSpatialSampleCount=5, mSampleRadius=7.0)])
 def test_spatial_reuse_matches_the_slang_witness(kw):
     w, h = 40, 30
     sc = env_scene(dim=(64, 64, 56), density_scale=0.06, env_size=(128, 64))
@@ -79,7 +80,9 @@ def test_final_shading_matches_the_slang_witness():
         np.testing.assert_allclose(color[by[k], bx[k], :3], frame.final_shading(int(bx[k]), int(by[k]), res[by[k], bx[k]]), rtol=5e-5, atol=1e-9)
 
 
-@pytest.mark.parametrize("kw,move", [(dict(), False), (dict(mTemporalMISMethod=capi.kMISNone, mTemporalReuseMThreshold=2.0), False), (dict(), True)])
+@pytest.mark.parametrize("kw,move", [(dict(), False), (dict(mTemporalMISMethod=capi.kMISNone, mTemporalReuseMThreshold=2.0), False), (dict(), True),
+                                     (dict(mTemporalReprojectionMode=capi.kReprojectionNone), True),
+                                     (dict(mTemporalReprojectionMode=capi.kReprojectionNoBackground), True)])
 def test_temporal_reuse_matches_the_slang_witness(kw, move):
     """K2 on a frame with history: reprojection of the stored depth (or of a density-sampled point for a background sample) through
     the previous frame's view-projection, resampling of the history sample on the current ray, Talbot MIS between the two samples,
