@@ -5,6 +5,12 @@
  * fp32 scalar C++; each function cites the reference file:line it follows.  Abbreviations:
  *   VR/ = Source/RenderPasses/VolumetricReSTIR/    F/ = Source/Falcor/
  *
+ * PIN STATUS: parity unpinned against reference OUTPUT — the reference (Slang SM 6.5 / DXR / Falcor / D3D12 / Windows) cannot run
+ * here and ships no golden vectors for this path; only the RNG core is checked against reference-held code (oracle/_ref, the
+ * vendored xoshiro C) and its seeding KATs.  What stands in for reference output: independent Python restatements written from
+ * the Slang, not from this file (oracle/march_witness.py, light_witness.py, stage_witness.py, alias_oracle.py, mip_oracle.py,
+ * post_oracle.py), which every stage of this oracle is checked against in tests/ (DESIGN.md section 2 lists them).
+ *
  * Build: g++ -O2 -ffp-contract=off -pthread (oracle/Makefile).  No fast-math, no FMA contraction, so every float
  * expression below is evaluated exactly as written, left to right.
  *
