@@ -11,7 +11,8 @@ from oracle import vro
 from volumetricrestirrelease_b200 import VolumetricReSTIRParams, capi
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(mInitialM=6, mInitialLightingMipLevel=1, mInitialBaseMipLevel=2)])
+@pytest.mark.parametrize("kw", [dict(), dict(mInitialM=6, mInitialLightingMipLevel=1, mInitialBaseMipLevel=2),
+                                dict(mInitialVisibilityUseLinearSampler=1, mInitialM=3, mInitialLightingUseLinearSampler=0)])
 def test_initial_sampling_matches_the_slang_witness(kw):
     w, h = 40, 30
     sc = env_scene(dim=(64, 64, 56), density_scale=0.06, env_size=(128, 64))
@@ -71,7 +72,8 @@ def test_features_match_the_slang_witness(kw, density):
     assert density < 0.1 or opaque >= 4            # the dense variant reaches the early out
 
 
-@pytest.mark.parametrize("kw,g", [(dict(mMaxBounces=3), 0.0), (dict(mMaxBounces=4, mInitialUseCoarserGridForIndirectBounce=0, mInitialM=3), 0.5)])
+@pytest.mark.parametrize("kw,g", [(dict(mMaxBounces=3), 0.0), (dict(mMaxBounces=4, mInitialUseCoarserGridForIndirectBounce=0, mInitialM=3), 0.5),
+                                  (dict(mMaxBounces=3, mInitialVisibilityUseLinearSampler=1, mInitialM=2), -0.3)])
 def test_multi_bounce_paths_match_the_slang_witness(kw, g):
     """MAX_BOUNCES > 1: the bounce loop of ComputeInitialSample (a light sample at every vertex, phase-sampled continuation, one
     free-flight sample per bounce on the coarser grid, Russian roulette from the third vertex on, per-path reservoir), the
