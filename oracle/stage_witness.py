@@ -1,20 +1,22 @@
-"""Stage-level witnesses (TEST INFRASTRUCTURE): the target function p-hat and the spatial-reuse pass, written from the reference's
-Slang and composed from the lower-level witnesses (march_witness: transmittance, point query, xoshiro; light_witness: env map,
-phase function) — not from oracle/vr_oracle.cpp or the CUDA kernels.  Single bounce, env-map light, ray-marched transmittances (the
-default option family).
+"""Stage-level witnesses (TEST INFRASTRUCTURE): every stage of the pass — K0 features (march_witness), K1 initial candidates, K2
+temporal reuse, K3 spatial reuse, K5 final shading, the target function p-hat and the reference path tracer — written from the
+reference's Slang and composed from the lower-level witnesses (march_witness: trackers, distance sampling, point query, xoshiro;
+light_witness: env map, phase function; alias_oracle: emissive power table) — not from oracle/vr_oracle.cpp or the CUDA kernels.
+Covered: 1-4 bounces, reuse and no-reuse mode, env-map / point / directional / emissive-triangle lights, volume emission, vertex
+reuse, animated volumes (velocity reprojection, previous-frame grids), every tracker.  Not covered: surface scenes (not built).
+Pure-Python float32, one pixel at a time: tests compare a dozen pixels per case with the oracle's buffers.
 
   camera ray                    F/Scene/Camera/Camera.slang:160-228 (computeRayPinholeScaled(pixel, 1, 0.5))
   evaluate_F_ / evaluate_P_hat  VR/ReSTIRHelper.slang:91-200,426-441 + evaluate_L_in_volume :442-496 (env light)
   option -> mip / sampler       VR/VolumetricReSTIR.cpp:455-500 (gSpatialSamplingOptions)
-  initial candidates (K1)       VR/TraceRays.cs.slang:64-183, VR/ComputeInitialSample.slang:4-395 (one bounce), SampleDirectLighting /
+  initial candidates (K1)       VR/TraceRays.cs.slang:64-183, VR/ComputeInitialSample.slang:4-395, SampleDirectLighting /
                                 sampleSceneLights VR/VolumeUtils.slang:12-66,454-492 (env-map light), gInitialSamplingOptions
                                 VR/VolumetricReSTIR.cpp:457-470
-  temporal reuse (K2)           VR/TemporalReuse.cs.slang:80-377 (linear reprojection, Talbot MIS or none; no velocity grid),
+  temporal reuse (K2)           VR/TemporalReuse.cs.slang:80-377 (reprojection modes, velocity grid, Talbot MIS or none),
                                 resampleNeighbor VR/ReSTIRHelper.slang:582-597, simpleResampleStepWithMaxM VR/Reservoir.slang:57-87
   multi-bounce paths            the bounce loop of VR/ComputeInitialSample.slang:29-386 (phase-sampled continuation, one free-flight
                                 sample per bounce on the coarser grid, Russian roulette, per-bounce reservoir streaming), the
                                 extra-bounce records VR/ReSTIRHelper.slang:21-52,66-79 and the vertex loop of evaluate_F_ :205-385
-                                (env-map light, no emission, no vertex reuse)
   analytic + emissive lights    sampleSceneLights VR/VolumeUtils.slang:12-149 (type selection, point / directional F/Experimental/Scene/Lights/
                                 LightHelpers.slang:196-244, emissive triangles F/.../EmissivePowerSampler.slang:57-92 +
                                 EmissiveLightSamplerHelpers.slang:56-101, alias draw F/Utils/Sampling/AliasTable.slang:56-70,
