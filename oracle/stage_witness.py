@@ -348,13 +348,16 @@ def _resample_step_max_m(tap, max_m, state, rng):
 
 
 def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, frame_count, prev_cam=None, extra_cur=None, extra_prev=None,
-                         pp_cur=None, pp_prev=None):
+                         pp_cur=None, pp_prev=None, info=None):
     """TemporalReuse.cs.slang main() for one pixel of a frame with history.  prev_cam: (posW, U, V, W, view[16], proj[16]) of the
     previous frame (default: the current camera, i.e. a static camera).  Returns the reservoir K2 leaves in the current buffer; with
     extra_cur / extra_prev ((H, W, B-1, 3) extra-bounce records of the two frames) the targets are whole paths and the result is
     (reservoir, extra-bounce records of the selected sample)."""
     P, w, h = frame.P, frame.w, frame.h
     paths = extra_cur is not None
+    if info is None:
+        info = {}
+    info["mvec"] = (F(0), F(0))                             # gMotionVec = (reprojected pixel - pixel) / resolution
 
     def target(direction, tap, depth=None):
         if not paths:
@@ -401,6 +404,7 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
         tf = feat_prev.reshape(-1)[idx] if idx < w * h else None          # out-of-range structured-buffer reads return 0
         tap_bg = tf is not None and tf["transmittance"] == 1.0 and bool(tf["noReflectiveSurface"])
         if is_bg and not tap_bg:
+            info["mvec"] = (F(F(0 - px) / F(w)), F(F(0 - py) / F(h)))    # reprojScreenPos is still (0, 0) at this return
             return (taps[0], taps[0].pop("extra")) if paths else taps[0]     # K1's reservoir stays
         scr_i = (int(np.trunc(scr[0])), int(np.trunc(scr[1])))
         reproj = scr_i
@@ -408,6 +412,7 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
             taps[1] = rec(res_prev[scr_i[1], scr_i[0]]); fallback = False
     if fallback:
         reproj = (px, py); taps[1] = rec(res_prev[py, px])
+    info["mvec"] = (F(F(reproj[0] - px) / F(w)), F(F(reproj[1] - py) / F(h)))
     if paths:
         taps[1]["extra"] = extra_prev[reproj[1], reproj[0]].copy()
     if pp_prev is not None:

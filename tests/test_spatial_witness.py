@@ -92,11 +92,12 @@ def test_temporal_reuse_matches_the_slang_witness(kw, move):
     params = VolumetricReSTIRParams(**kw)
     op = vro.OraclePass(params)
     op.setScene(sc, w, h)
+    op.updateDict({"mOutputMotionVec": 1})
     op.execute()
     cam0 = sc.camera.data(w, h)
     prev_cam = tuple(np.array(getattr(cam0, k)[:], dtype=np.float32) for k in ("posW", "cameraU", "cameraV", "cameraW", "viewMat", "projMat"))
     if move:
-        pos = np.array(sc.camera.position); sc.camera.position = tuple(pos + np.array([0.25, -0.15, 0.1]))
+        pos = np.array(sc.camera.position); sc.camera.position = tuple(pos + np.array([6.0, -4.0, 2.0])); sc.camera.target = tuple(np.array(sc.camera.target) + np.array([6.0, -4.0, 2.0]))   # a pan: every pixel shifts
         op.updateCamera()
     frame_count = op.frame_count()
     color = np.zeros((h, w, 4), np.float32)
@@ -105,7 +106,8 @@ def test_temporal_reuse_matches_the_slang_witness(kw, move):
     res_prev = op.get_buffer(capi.BUF_RESERVOIR_TEMPORAL).view(RES).reshape(h, w).copy()
     feat_cur = op.get_buffer(capi.BUF_FEATURES).view(FEAT).reshape(h, w).copy()
     feat_prev = op.get_buffer(capi.BUF_FEATURES_TEMPORAL).view(FEAT).reshape(h, w).copy()
-    op.execute_stage(2, 0, color)
+    mvec = np.zeros((h, w, 2), np.float32)
+    op.execute_stage(2, 0, color, mvec)
     res_out = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w)
     frame = sw.Frame(sc, params, w, h)
     rng = np.random.default_rng(4)
@@ -116,10 +118,13 @@ def test_temporal_reuse_matches_the_slang_witness(kw, move):
         ys, xs = np.nonzero(mask)
         assert len(ys) >= n
         picks += [(int(xs[k]), int(ys[k])) for k in rng.permutation(len(ys))[:n]]
-    from_history = 0
+    from_history = shifted = 0
     for x, y in picks:
         got = res_out[y, x]
-        want = sw.temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, x, y, frame_count, prev_cam)
+        info = {}
+        want = sw.temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, x, y, frame_count, prev_cam, info=info)
+        assert tuple(mvec[y, x]) == tuple(float(v) for v in info["mvec"]), (x, y)          # the motion vector output
+        shifted += bool(np.any(mvec[y, x] != 0))
         assert int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
         assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
         assert np.allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=1e-7), (x, y)
@@ -127,6 +132,7 @@ def test_temporal_reuse_matches_the_slang_witness(kw, move):
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
         from_history += float(got["M"]) > float(res_cur[y, x]["M"])
     assert from_history >= 8            # the history really took part
+    assert shifted >= 4 if (move and kw.get("mTemporalReprojectionMode", 0) != capi.kReprojectionNone) else shifted == 0
 
 
 def test_spatial_reuse_of_multi_bounce_paths_matches_the_slang_witness():
