@@ -1,6 +1,6 @@
 """GPU: a C++ program that uses only include/VolumetricReSTIR.hpp + include/vrestir.h (the host side a Falcor-style C++ caller
-would write: create, setScene, updateDict, setCamera, execute with host buffers, advance a resident animation frame) renders the
-same frames as the Python mirror — bit for bit, including after an option change and a camera move."""
+would write: create, setScene, updateDict, setCamera, execute with host buffers, getScriptingDictionary) renders the same frames
+as the Python mirror — bit for bit, including after an option change and a camera move — and throws where the reference throws."""
 import ctypes as C
 import os
 import shutil
