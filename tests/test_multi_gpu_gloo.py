@@ -131,3 +131,128 @@ def test_reprojection_row_bound():
             c = np.concatenate([pts, np.ones((len(pts), 1))], axis=1) @ V @ P
             return (-0.5 * c[:, 1] / c[:, 3] + 0.5) * H
         assert np.abs(rows(c0) - rows(c1)).max() <= b
+
+
+# ---- the orchestration of ShardedPass.execute against a model pass -----------------------------------------------------------
+class _ModelPass:
+    """Stands in for the CUDA pass on CPU tensors: every stage is a deterministic row function that READS what the real stage
+    reads (K2: the history around the row; K3: the round's input buffer within the sample radius, with its extra-bounce records and
+    p_partial plane) and writes only its own band — so a missing or misplaced exchange changes the band's result."""
+
+    def __init__(self, H, W, band, params, halo_t):
+        from volumetricrestirrelease_b200 import capi
+        self.capi, self.H, self.W, self.band, self.params, self.halo_t = capi, H, W, band, params, halo_t
+        widths = {capi.BUF_RESERVOIR_0: 32, capi.BUF_RESERVOIR_1: 32, capi.BUF_RESERVOIR_TEMPORAL: 32, capi.BUF_FEATURES: 8, capi.BUF_FEATURES_TEMPORAL: 8,
+                  capi.BUF_EXTRA_0: 12 * (params.mMaxBounces - 1), capi.BUF_EXTRA_1: 12 * (params.mMaxBounces - 1),
+                  capi.BUF_EXTRA_TEMPORAL: 12 * (params.mMaxBounces - 1), capi.BUF_PPARTIAL_0: 4, capi.BUF_PPARTIAL_1: 4, capi.BUF_PPARTIAL_TEMPORAL: 4}
+        self.buf = {b: torch.zeros(H, max(w, 1) * W, dtype=torch.int64) for b, w in widths.items()}
+        self.frame = 0
+        self.final = None
+
+    def frame_count(self):
+        return self.frame
+
+    def spatial_input_buffer(self, r):
+        return self.capi.BUF_RESERVOIR_0 if r % 2 == 0 else self.capi.BUF_RESERVOIR_1
+
+    def _rows(self):
+        return range(self.band[0], self.band[1])
+
+    def _around(self, t, y, h):
+        return int(t[max(0, y - h):min(self.H, y + h + 1)].sum())
+
+    def execute_stage(self, stage, arg=0, *_):
+        c, b, B = self.capi, self.buf, self.params.mMaxBounces
+        vr = bool(self.params.mVertexReuse) and B > 1
+        twin = {c.BUF_RESERVOIR_0: (c.BUF_EXTRA_0, c.BUF_PPARTIAL_0), c.BUF_RESERVOIR_1: (c.BUF_EXTRA_1, c.BUF_PPARTIAL_1),
+                c.BUF_RESERVOIR_TEMPORAL: (c.BUF_EXTRA_TEMPORAL, c.BUF_PPARTIAL_TEMPORAL)}
+
+        def family(res):
+            return [res] + ([twin[res][0]] if B > 1 else []) + ([twin[res][1]] if vr else [])
+        if stage == 0:
+            for y in self._rows():
+                b[c.BUF_FEATURES][y] = 7 * y + self.frame
+        elif stage == 1:
+            for k, t in enumerate(family(c.BUF_RESERVOIR_0)):
+                for y in self._rows():
+                    t = b[family(c.BUF_RESERVOIR_0)[k]]
+                    t[y] = 1000 * (k + 1) + 13 * y + self.frame
+        elif stage == 2 and self.frame > 0:
+            new = {}
+            for cur, prv in zip(family(c.BUF_RESERVOIR_0), family(c.BUF_RESERVOIR_TEMPORAL)):
+                new[cur] = {y: int(b[cur][y, 0]) + self._around(b[prv], y, self.halo_t) + self._around(b[c.BUF_FEATURES_TEMPORAL], y, self.halo_t) for y in self._rows()}
+            for cur, rows in new.items():
+                for y, v in rows.items():
+                    b[cur][y] = v % 1000003
+        elif stage == 3:
+            src = self.spatial_input_buffer(arg)
+            dst = c.BUF_RESERVOIR_1 if src == c.BUF_RESERVOIR_0 else c.BUF_RESERVOIR_0
+            h = int(np.ceil(self.params.mSampleRadius))
+            for s, d in zip(family(src), family(dst)):
+                for y in self._rows():
+                    b[d][y] = (self._around(b[s], y, h) + int(b[c.BUF_FEATURES][y, 0])) % 1000003     # features: the own row only
+            self.final = dst
+        elif stage == 4:
+            src = self.final if self.final is not None else c.BUF_RESERVOIR_0
+            for s, d in zip(family(src), family(c.BUF_RESERVOIR_TEMPORAL)):
+                for y in self._rows():
+                    b[d][y] = b[s][y]
+            for y in self._rows():
+                b[c.BUF_FEATURES_TEMPORAL][y] = b[c.BUF_FEATURES][y]
+        elif stage == 6:
+            self.frame += 1
+
+
+def _orchestration_worker(rank, world, port, H, W, vertex_reuse, out):
+    sys.path.insert(0, ROOT)
+    from volumetricrestirrelease_b200 import VolumetricReSTIRParams, capi
+    from volumetricrestirrelease_b200.multi_gpu import ShardedPass, row_bands
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = VolumetricReSTIRParams(mMaxBounces=3, mVertexReuse=vertex_reuse, mSpatialReuseRounds=2, mSampleRadius=5.0)
+
+    class Model(ShardedPass):
+        def _planes(self, buffer):
+            return [self.p.buf[buffer]]
+
+        def _history_needs_gather(self):
+            return False
+
+    def run(world_, rank_):
+        band = row_bands(H, world_)[rank_]
+        mp_ = _ModelPass(H, W, band, params, halo_t=6)
+        mp_._scene = type("S", (), {"camera": type("C", (), {"data": staticmethod(lambda w, h: None)})()})()
+        sp = Model(mp_, W, H, rank_, world_, torch.device("cpu"), temporal_halo=6)
+        for _ in range(3):
+            if world_ == 1:          # the whole-frame call of the real pass: the same stages, no exchange
+                for st, arg in [(0, 0), (1, 0), (2, 0), (3, 0), (3, 1), (4, 0), (5, 0), (6, 0)]:
+                    mp_.execute_stage(st, arg)
+            else:
+                sp.execute(0)
+        for w in getattr(sp, "_pending_history", []):
+            w.wait()
+        return mp_, band
+
+    sharded, band = run(world, rank)
+    whole, _ = run(1, 0)
+    ok = True
+    for bid in (capi.BUF_RESERVOIR_TEMPORAL, capi.BUF_EXTRA_TEMPORAL, capi.BUF_FEATURES_TEMPORAL) + ((capi.BUF_PPARTIAL_TEMPORAL,) if vertex_reuse else ()):
+        ok &= bool(torch.equal(sharded.buf[bid][band[0]:band[1]], whole.buf[bid][band[0]:band[1]]))
+    if not vertex_reuse:             # the p_partial plane does not travel without vertex reuse
+        other = row_bands(H, world)[1 - rank]
+        ok &= bool((sharded.buf[capi.BUF_PPARTIAL_TEMPORAL][other[0]:other[1]] == 0).all())
+    out[rank] = int(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_execute_exchanges_what_every_stage_reads():
+    """ShardedPass.execute on a model pass (world 2 vs the un-sharded frame): reservoir planes, extra-bounce records and — with
+    vertex reuse — the p_partial plane reach the neighbour before each spatial round, and the history before the next frame's K2."""
+    for vertex_reuse in (0, 1):
+        world, H, W = 2, 48, 3
+        port = _free_port()
+        out = mp.get_context("spawn").Manager().dict()
+        mp.spawn(_orchestration_worker, args=(world, port, H, W, vertex_reuse, out), nprocs=world, join=True)
+        assert dict(out) == {0: 1, 1: 1}, vertex_reuse
