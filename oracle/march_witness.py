@@ -20,6 +20,8 @@ double, one to float).  tests/test_march_witness.py compares the two on random r
 """
 import ctypes as C
 
+import math
+
 import numpy as np
 
 F = np.float32
@@ -469,8 +471,12 @@ class ResidualRatioAdapter:   # VR/VolumeTrackingAdapterGVDB.slang:710-794 (Resi
         if mu_r_temp == 0 or self.analog:
             mu_c = mu_min
         else:
-            with np.errstate(over="ignore"):              # 2^(1 / small) overflows to inf; min() then picks mu_avg, as in the shader
-                mu_c = min(mu_avg, max(mu_min, mu_min + mu_r_temp * (np.power(F(2), F(1) / (D * mu_r_temp)) - F(1))))
+            # pow through float64 and one rounding (what a correctly rounded powf returns): numpy's float32 SIMD pow can be an ulp
+            # off, and an ulp in mu_c decides whether a collision in a saturated voxel (mu == mu_max) multiplies T_r by exactly 0
+            # or by 6e-8 — which in turn decides whether later segments are evaluated at all, i.e. how many numbers are drawn
+            e = float(F(1) / (D * mu_r_temp))
+            p2 = F(math.pow(2.0, e)) if e < 128.0 else F(np.inf)     # 2^(1 / small) overflows to inf; min() then picks mu_avg, as in the shader
+            mu_c = min(mu_avg, max(mu_min, mu_min + mu_r_temp * (p2 - F(1))))
         mu_r = max(F(mu_c - mu_min), F(mu_max - mu_c))
         with np.errstate(divide="ignore"):
             inv_mu_r = F(1) / mu_r

@@ -60,6 +60,7 @@ class Frame:
         self.prev_grid = None           # the previous frame's grid description of an animated volume (slots 19.. / 27 / 28)
         self.last_frame = False         # isLastFrame of the evaluation in progress
         self.final_rng = None           # the final shading's generator (stochastic trackers only)
+        self.stage_rng = None           # the generator of the K1 / K2 / K3 invocation in progress (stochastic trackers in p-hat)
 
     def seed_final(self, px, py, frame_count):
         """FinalShading.cs.slang:85: the pixel's generator of the last round of the frame."""
@@ -92,24 +93,35 @@ class Frame:
         d = ndc[0] * self.U + ndc[1] * self.V + self.Wv
         return (d / np.sqrt(np.dot(d, d))).astype(F)
 
+    def compute_visibility(self, origin, direction, tmax, samples, mip, linear, method, tstep_scale, rng):
+        """computeVisibility (VR/VolumeUtils.slang:549-572): `samples` estimates of the chosen tracker, averaged.  The random-walk
+        trackers (ratio 0 / residual ratio 3 / analog residual ratio 4) always sample trilinearly and draw from `rng`."""
+        total = F(0)
+        for _ in range(samples):
+            if method in (0, 3, 4):
+                v = self.wit(mip).residual_ratio_tracking(origin, direction, tmax, rng, method == 4, method == 0)
+            elif method == 2:
+                v = self.wit(mip).ray_marching(origin, direction, tmax, linear, tstep_scale)
+            else:
+                v = self.wit(mip).analytic(origin, direction, tmax, linear)
+            total = F(total + F(v))
+        return F(total / F(samples))
+
     def _transmittance(self, final, which, origin, direction, tmax):
-        """Ray-marched under the spatial options; exact transmittance of the trilinear mip-0 interpolant (analytic tracking, the
-        default of the final shading, VR/VolumetricReSTIR.cpp:484-496) when `final`."""
+        """The segment transmittance of a p-hat evaluation (spatial options: VR/VolumetricReSTIR.cpp:471-482, one sample) or of the
+        final shading (finalOptions :484-496: mip 0, trilinear, the configured tracker and sample count).  Stochastic trackers draw
+        from the generator of the stage in progress (self.stage_rng / self.final_rng), in shader order."""
         P = self.P
-        if final:                                           # finalOptions: mip 0, trilinear, the configured tracker and sample count
-            method = P.mFinalVisibilityTrackingMethod if which == "camera" else P.mFinalLightTrackingMethod
-            if method == 1:
-                return F(self.wit(0).analytic(origin, direction, tmax, True))
-            if method == 2:
-                return F(self.wit(0).ray_marching(origin, direction, tmax, True, P.mFinalTStepScale))
-            n = P.mFinalVisibilitySamples if which == "camera" else P.mFinalLightSamples
-            total = F(0)
-            for _ in range(n):                              # ratio (0) / residual ratio (3) / analog residual ratio (4) tracking
-                total = F(total + F(self.wit(0).residual_ratio_tracking(origin, direction, tmax, self.final_rng, method == 4, method == 0)))
-            return F(total / F(n))
+        if final:
+            cam = which == "camera"
+            method = P.mFinalVisibilityTrackingMethod if cam else P.mFinalLightTrackingMethod
+            n = 1 if method in (1, 2) else (P.mFinalVisibilitySamples if cam else P.mFinalLightSamples)
+            return self.compute_visibility(origin, direction, tmax, n, 0, True, method, P.mFinalTStepScale, self.final_rng)
         if which == "camera":
-            return F(self.wit(P.mSpatialVisibilityMipLevel).ray_marching(origin, direction, tmax, bool(P.mSpatialVisibilityUseLinearSampler), P.mSpatialVisibilityTStepScale))
-        return F(self.wit(P.mSpatialLightingMipLevel).ray_marching(origin, direction, tmax, bool(P.mSpatialLightingUseLinearSampler), P.mSpatialLightingTStepScale))
+            return self.compute_visibility(origin, direction, tmax, 1, P.mSpatialVisibilityMipLevel, bool(P.mSpatialVisibilityUseLinearSampler),
+                                           P.mSpatialVisibilityTrackingMethod, P.mSpatialVisibilityTStepScale, self.stage_rng)
+        return self.compute_visibility(origin, direction, tmax, 1, P.mSpatialLightingMipLevel, bool(P.mSpatialLightingUseLinearSampler),
+                                       P.mSpatialLightingTrackingMethod, P.mSpatialLightingTStepScale, self.stage_rng)
 
     def eval_F(self, d, depth, light_uv, light_id, final=False):
         """evaluate_F_ of a single-bounce sample (depth along direction d from the camera, env light stored as (uv, id)): float3."""
@@ -246,6 +258,7 @@ def _spatial_reuse_pixel(frame, rec, res_in, features, px, py, frame_count, roun
     round_offset = int(bool(P.mEnableTemporalReuse)) + 1
     num_rounds = P.mSpatialReuseRounds + round_offset + 1
     rng = Xoshiro(px, py, num_rounds * frame_count + round_id + round_offset)
+    getattr(frame, "frame", frame).stage_rng = rng
     center = rec(res_in[py, px])
     if paths:
         center["src"] = (px, py)
@@ -307,13 +320,14 @@ def _initial_candidate(frame, d, hd, pd, tr, rng, mips):
     return _initial_path(frame, d, hd, pd, tr, rng, mips)[0]
 
 
-def initial_sampling_pixel(frame, px, py, frame_count, importance_mips):
+def initial_sampling_pixel(frame, px, py, frame_count, importance_mips, info=None):
     """TraceRays.cs.slang main() for one pixel (one bounce, reuse on, env-map light): M candidates by free-flight sampling along the
     camera ray, each with one importance-sampled env direction and its ray-marched shadow, streamed through a reservoir; then the
     p-hat of the streamed sample under the spatial options replaces the candidate-time target.  Returns the stored reservoir."""
     P = frame.P
     total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
     rng = Xoshiro(px, py, total_rounds * frame_count)
+    frame.stage_rng = rng
     d = frame.ray_dir(px, py)
     final = _new_reservoir()
     linear = bool(P.mInitialVisibilityUseLinearSampler)
@@ -325,7 +339,11 @@ def initial_sampling_pixel(frame, px, py, frame_count, importance_mips):
         for s in range(n):
             cand = _initial_candidate(frame, d, F(hd[s]), F(pd[s]), F(ot[s]), rng, importance_mips)
             _resample_step(cand, final, rng)
+    if info is not None:
+        info["generator_after_candidates"] = list(rng.s)
     p_hat = frame.p_hat(d, final["depth"], final["lightUV"], final["lightID"])
+    if info is not None:
+        info["generator_after_p_hat"] = list(rng.s)
     if final["runningSum"] > 0:
         final["runningSum"] = F(final["runningSum"] * (F(0) if final["p_y"] == 0 else F(p_hat / final["p_y"])))
         final["p_y"] = p_hat
@@ -373,6 +391,7 @@ def temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, px, py, 
     talbot = P.mTemporalMISMethod == 1
     total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
     rng = Xoshiro(px, py, total_rounds * frame_count + 1)          # gRoundOffset = numInitialSamplingRounds
+    frame.stage_rng = rng
     taps = [rec(res_cur[py, px]), None]
     if paths:
         taps[0]["extra"] = extra_cur[py, px].copy()
@@ -605,7 +624,8 @@ def _sample_direct_lighting(frame, p, wo, rng, mips):
     if bool(np.any(np.isnan(wi))):
         return np.zeros(3, F), F(0), light_id, light_uv
     if P.mInitialLightSamples != 0:
-        vis = F(frame.wit(P.mInitialLightingMipLevel).ray_marching(p, wi, float(K_RAY_TMAX), bool(P.mInitialLightingUseLinearSampler), P.mInitialLightingTStepScale))
+        vis = frame.compute_visibility(p, wi, float(K_RAY_TMAX), P.mInitialLightSamples, P.mInitialLightingMipLevel, bool(P.mInitialLightingUseLinearSampler),
+                                       P.mInitialLightingTrackingMethod, P.mInitialLightingTStepScale, rng)
         Li = (Li * vis).astype(F)
     return (F(lw.phase_hg(float(np.dot(wo, wi)), g)) * Li / F(1)).astype(F), pdf, light_id, light_uv
 
@@ -724,13 +744,14 @@ def _initial_path(frame, d, hd, pd, tr, rng, mips, no_reuse=False):
     return combined, extra
 
 
-def initial_sampling_pixel_paths(frame, px, py, frame_count, importance_mips):
+def initial_sampling_pixel_paths(frame, px, py, frame_count, importance_mips, info=None):
     """TraceRays.cs.slang main() with MAX_BOUNCES > 1, or with both reuse passes off (gNoReuse: every candidate is a path drawn by
     decomposition tracking): (stored reservoir, its extra-bounce records)."""
     P = frame.P
     no_reuse = not P.mEnableSpatialReuse and not P.mEnableTemporalReuse
     total_rounds = (P.mSpatialReuseRounds if P.mEnableSpatialReuse else 0) + int(bool(P.mEnableTemporalReuse)) + 1 + 1
     rng = Xoshiro(px, py, total_rounds * frame_count)
+    frame.stage_rng = rng
     d = frame.ray_dir(px, py)
     final, final_extra = _new_reservoir(), np.zeros((max(P.mMaxBounces - 1, 1), 3), F)
     linear = bool(P.mInitialVisibilityUseLinearSampler)
@@ -744,7 +765,11 @@ def initial_sampling_pixel_paths(frame, px, py, frame_count, importance_mips):
             if _resample_step(cand, final, rng):
                 k = int(final["sampledPixel"]) >> 20
                 final_extra[:k] = extra[:k]
+    if info is not None:
+        info["generator_after_candidates"] = list(rng.s)
     p_hat = F(lw.luminance(eval_F_path(frame, d, final, final_extra)))
+    if info is not None:
+        info["generator_after_p_hat"] = list(rng.s)
     if final["runningSum"] > 0:
         final["runningSum"] = F(final["runningSum"] * (F(0) if final["p_y"] == 0 else F(p_hat / final["p_y"])))
         final["p_y"] = p_hat
@@ -881,7 +906,8 @@ def sample_direct_lighting(frame, lights, p, wo, rng, mips):
         return np.zeros(3, F), F(0), ls["lightID"], ls["lightUV"]
     Li = ls["Li"]
     if P.mInitialLightSamples != 0:
-        vis = F(frame.wit(P.mInitialLightingMipLevel).ray_marching(p, ls["rayDir"], float(ls["rayDistance"]), bool(P.mInitialLightingUseLinearSampler), P.mInitialLightingTStepScale))
+        vis = frame.compute_visibility(p, ls["rayDir"], float(ls["rayDistance"]), P.mInitialLightSamples, P.mInitialLightingMipLevel, bool(P.mInitialLightingUseLinearSampler),
+                                       P.mInitialLightingTrackingMethod, P.mInitialLightingTStepScale, rng)
         Li = (Li * vis).astype(F)
     return (F(lw.phase_hg(float(np.dot(wo, ls["dir"])), g)) * Li / F(1)).astype(F), ls["pdfArea"], ls["lightID"], ls["lightUV"]
 

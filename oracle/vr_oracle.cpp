@@ -220,6 +220,7 @@ struct vro_pass {
     std::vector<Reservoir> res[2], resT;
     std::vector<ExtraBounce> ext[2], extT;
     std::vector<Features> feat, featT;
+    std::vector<uint32_t> k1Generator;   // per pixel: the generator after K1's candidate loop and after its p-hat evaluation (2 x 4 words), for the witnesses
     std::vector<float> refColor;  // gOutputColor of the mUseReference path
     int allocW = 0, allocH = 0, allocB = 0;
     int totalRoundId = 0;
@@ -1788,7 +1789,10 @@ void stageInitial(Pass& p, const FrameSetup& fs) {
         }
         ExtraProvider prov{finalExtra};
         Reservoir tapForEval = finalReservoir; tapForEval.extraBounceStartId = 0;
+        uint32_t* gen = p.k1Generator.size() == (size_t)p.W * p.H * 8 ? &p.k1Generator[(size_t)reservoirId * 8] : nullptr;
+        if (gen) for (int i = 0; i < 4; i++) gen[i] = sg.s[i];
         float p_hat = evaluate_P_hat(c, ray, sg, prov, fs.spatial, tapForEval, false, true, false);
+        if (gen) for (int i = 0; i < 4; i++) gen[4 + i] = sg.s[i];
         finalReservoir.p_partial = tapForEval.p_partial;   // TraceRays.cs.slang:176-177 passes finalReservoir itself (inout under VERTEX_REUSE)
         if (finalReservoir.runningSum > 0.f) {
             finalReservoir.runningSum *= finalReservoir.p_y == 0.f ? 0.f : p_hat / finalReservoir.p_y;
@@ -2371,6 +2375,24 @@ float vro_transmittance(vro_pass* p, const float o[3], const float d[3], float t
     Ctx c(*p); SampleGenerator sg = SampleGenerator::create(spx, spy, sn);
     Ray r = {v3(o), v3(d), 0, tmax};
     return computeVisibility(c, r, sg, 1, mip, linear != 0, (uint32_t)method, tss);
+}
+// Records, from the next K1 on, the generator of every pixel after the candidate loop and after the p-hat evaluation (draw-count check)
+int vro_record_k1_generator(vro_pass* p, int on) { if (on) p->k1Generator.assign((size_t)p->W * p->H * 8, 0u); else p->k1Generator.clear(); return VRESTIR_OK; }
+int vro_get_k1_generator(vro_pass* p, int px, int py, uint32_t out8[8]) {
+    if (p->k1Generator.size() != (size_t)p->W * p->H * 8 || px < 0 || py < 0 || px >= p->W || py >= p->H) return fail(VRESTIR_ERR_INVALID_ARGUMENT, "no K1 generator record");
+    for (int i = 0; i < 8; i++) out8[i] = p->k1Generator[((size_t)py * p->W + px) * 8 + i];
+    return VRESTIR_OK;
+}
+// computeVisibility with `samples` estimates; also returns the generator after the call (how many draws the walk consumed)
+float vro_visibility_state(vro_pass* p, const float o[3], const float d[3], float tmax, int method, int mip, int linear, float tss, int samples,
+                           uint32_t spx, uint32_t spy, uint32_t sn, uint32_t out_state[4]) {
+    applyOverrides(*p);
+    Ctx c(*p); SampleGenerator sg = SampleGenerator::create(spx, spy, sn);
+    if (spx == 0xFFFFFFFFu && spy == 0xFFFFFFFFu) for (int i = 0; i < 4; i++) sg.s[i] = out_state[i];   // start from a given generator state
+    Ray r = {v3(o), v3(d), 0, tmax};
+    float v = computeVisibility(c, r, sg, samples, mip, linear != 0, (uint32_t)method, tss);
+    for (int i = 0; i < 4; i++) out_state[i] = sg.s[i];
+    return v;
 }
 // SampleMediumAnalyticGeneric along one ray with the generator of (pixel, sample number): out12 = hit distances | pdfs | transmittances
 // (4 each), out_state = the generator after the call

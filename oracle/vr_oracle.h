@@ -86,6 +86,10 @@ void vro_decode_wi_dist(const float in3[3], float out4[4]);
 void vro_env_eval(vro_pass* p, const float dir[3], float out_rgb[3]);
 int vro_env_sample(vro_pass* p, float u0, float u1, float out_dir[3], float* out_pdf, float out_Le[3]);
 /* spatial neighbour offsets of a round (R2 in double / Hammersley), VR/SpatialReuse.cs.slang:64-81,109 */
+int vro_record_k1_generator(vro_pass* p, int on);
+int vro_get_k1_generator(vro_pass* p, int px, int py, uint32_t out8[8]);
+float vro_visibility_state(vro_pass* p, const float o[3], const float d[3], float tmax, int method, int mip, int linear, float tss, int samples,
+                           uint32_t spx, uint32_t spy, uint32_t sn, uint32_t out_state[4]);
 float vro_sample_supervoxel(vro_pass* p, const float o[3], const float d[3], int mip, uint32_t spx, uint32_t spy, uint32_t sn, uint32_t out_state[4]);
 void vro_sample_distances(vro_pass* p, const float o[3], const float d[3], int mip, int linear, int n, uint32_t spx, uint32_t spy, uint32_t sn, float out12[12], uint32_t out_state[4]);
 float vro_p_hat(vro_pass* p, int px, int py, float depth, float uvx, float uvy, int lightID);

@@ -71,6 +71,11 @@ def lib():
         L.vro_env_sample.argtypes = [vp, C.c_float, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float), C.POINTER(C.c_float * 3)]
         L.vro_neighbor_offsets.argtypes = [vp, C.c_int, C.c_int, vp]
         L.vro_p_hat.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]; L.vro_p_hat.restype = C.c_float
+        L.vro_record_k1_generator.argtypes = [vp, C.c_int]
+        L.vro_get_k1_generator.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.vro_visibility_state.restype = C.c_float
+        L.vro_visibility_state.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                           C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.vro_sample_supervoxel.restype = C.c_float
         L.vro_sample_supervoxel.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.vro_sample_distances.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
@@ -214,6 +219,25 @@ class OraclePass:
         out = np.zeros(12, dtype=np.float32); st = np.zeros(4, dtype=np.uint32)
         lib().vro_sample_distances(self._h, C.byref(o), C.byref(d), mip, int(linear), n, seed[0], seed[1], seed[2], out.ctypes.data, st.ctypes.data)
         return out[0:4], out[4:8], out[8:12], st
+
+    def record_k1_generator(self, on=True):
+        """From the next K1 on, keep every pixel's generator after the candidate loop and after the p-hat evaluation."""
+        check(lib().vro_record_k1_generator(self._h, int(on)))
+
+    def k1_generator(self, px, py):
+        out = np.zeros(8, dtype=np.uint32)
+        check(lib().vro_get_k1_generator(self._h, px, py, out.ctypes.data))
+        return [int(x) for x in out[:4]], [int(x) for x in out[4:]]
+
+    def visibility_state(self, origin, direction, tmax, method, mip, linear, tstep_scale, samples, seed):
+        """computeVisibility with `samples` estimates: (value, generator state after)."""
+        o = (C.c_float * 3)(*origin); d = (C.c_float * 3)(*direction)
+        st = np.zeros(4, dtype=np.uint32)
+        if len(seed) == 4:                                  # a raw generator state instead of (pixel x, pixel y, sample number)
+            st[:] = seed
+            seed = (0xFFFFFFFF, 0xFFFFFFFF, 0)
+        v = float(lib().vro_visibility_state(self._h, C.byref(o), C.byref(d), tmax, method, mip, int(linear), tstep_scale, samples, seed[0], seed[1], seed[2], st.ctypes.data))
+        return v, st
 
     def sample_supervoxel(self, origin, direction, mip, seed):
         """SampleMediumSuperVoxelGeneric along one ray: (distance or None, generator state after)."""

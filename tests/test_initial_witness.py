@@ -12,7 +12,10 @@ from volumetricrestirrelease_b200 import VolumetricReSTIRParams, capi
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(mInitialM=6, mInitialLightingMipLevel=1, mInitialBaseMipLevel=2),
-                                dict(mInitialVisibilityUseLinearSampler=1, mInitialM=3, mInitialLightingUseLinearSampler=0)])
+                                dict(mInitialVisibilityUseLinearSampler=1, mInitialM=3, mInitialLightingUseLinearSampler=0),
+                                dict(mInitialLightingTrackingMethod=capi.kResidualRatioTracking, mInitialLightSamples=2, mInitialM=3,
+                                     mSpatialVisibilityTrackingMethod=capi.kRatioTracking, mSpatialLightingTrackingMethod=capi.kAnalyticTracking),
+                                dict(mInitialLightingTrackingMethod=capi.kAnalyticTracking, mInitialLightingMipLevel=0, mInitialLightSamples=0)])
 def test_initial_sampling_matches_the_slang_witness(kw):
     w, h = 40, 30
     sc = env_scene(dim=(64, 64, 56), density_scale=0.06, env_size=(128, 64))
@@ -22,6 +25,7 @@ def test_initial_sampling_matches_the_slang_witness(kw):
     color = np.zeros((h, w, 4), np.float32)
     op.execute()                                                # frame 0, so that the frame counter is not 0
     frame_count = op.frame_count()
+    op.record_k1_generator()
     op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
     res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w)
     imp = op.get_buffer(capi.BUF_ENV_IMPORTANCE).view(np.float32)
@@ -33,17 +37,27 @@ def test_initial_sampling_matches_the_slang_witness(kw):
     vy, vx = np.nonzero((res["runningSum"] > 0) & (res["depth"] < 1e37))     # the streamed sample scatters in the medium
     by, bx = np.nonzero((res["runningSum"] > 0) & (res["depth"] > 1e37))     # ... or is the background behind it
     picks = [(int(vx[k]), int(vy[k])) for k in rng.permutation(len(vy))[:9]] + [(int(bx[k]), int(by[k])) for k in rng.permutation(len(by))[:3]]
-    checked = volume = 0
+    # A random-walk tracker inside K1 makes the DRAW COUNT depend on the last bit of powf (the control density of residual ratio
+    # tracking): an estimate that is exactly 0 in one implementation and 1e-40 in the other adds or skips one reservoir draw, and
+    # every later draw of that pixel shifts.  Such pixels are recognised by their generator and bounded, not compared.
+    stochastic_k1 = kw.get("mInitialLightingTrackingMethod", capi.kRayMarching) in (capi.kRatioTracking, capi.kResidualRatioTracking, capi.kAnalogResidualRatioTracking)
+    checked = volume = diverged = 0
     for x, y in picks:
         got = res[y, x]
-        want = sw.initial_sampling_pixel(frame, x, y, frame_count, mips)
+        info = {}
+        want = sw.initial_sampling_pixel(frame, x, y, frame_count, mips, info)
+        after_candidates, after_p_hat = op.k1_generator(x, y)
+        if stochastic_k1 and after_candidates != info["generator_after_candidates"]:
+            diverged += 1
+            continue
+        assert after_candidates == info["generator_after_candidates"] and after_p_hat == info["generator_after_p_hat"], (x, y)   # same number of draws
         assert int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
         assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
         np.testing.assert_allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=3e-6)
         assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=1e-4, abs=1e-12), (x, y)
         assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
         checked += 1; volume += float(got["depth"]) < 1e37
-    assert checked == 12 and volume >= 6
+    assert checked + diverged == 12 and diverged <= 1 and volume >= 5
 
 
 @pytest.mark.parametrize("kw,density", [(dict(), 0.06), (dict(mInitialVisibilityTStepScale=2.0), 0.6)])

@@ -11,7 +11,10 @@ from volumetricrestirrelease_b200 import VolumetricReSTIRParams, capi
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(mSpatialMISMethod=capi.kMISNone, mSampleRadius=6.0, mSpatialSampleCount=3),
-                                dict(mRandomSamplerType=capi.kHammersley, mSpatialSampleCount=5, mSampleRadius=7.0)])
+                                dict(mRandomSamplerType=capi.kHammersley, mSpatialSampleCount=5, mSampleRadius=7.0),
+                                dict(mSpatialVisibilityTrackingMethod=capi.kResidualRatioTracking, mSpatialLightingTrackingMethod=capi.kRatioTracking, mSpatialSampleCount=3),
+                                dict(mSpatialVisibilityTrackingMethod=capi.kAnalyticTracking, mSpatialLightingTrackingMethod=capi.kAnalogResidualRatioTracking,
+                                     mSpatialVisibilityUseLinearSampler=0, mSpatialLightingMipLevel=2)])
 def test_spatial_reuse_matches_the_slang_witness(kw):
     w, h = 40, 30
     sc = env_scene(dim=(64, 64, 56), density_scale=0.06, env_size=(128, 64))
@@ -31,19 +34,27 @@ def test_spatial_reuse_matches_the_slang_witness(kw):
     assert frame_count >= 1
     rng = np.random.default_rng(11)
     ys, xs = np.nonzero(feat["transmittance"] != 1.0)
-    checked = changed = 0
-    for k in rng.permutation(len(ys))[:9]:
+    # With a random-walk tracker in p-hat the number of draws a pixel consumes depends on the last bit of powf (an estimate that is
+    # exactly 0 in one implementation and 1e-40 in the other adds or skips a reservoir draw and shifts every later draw of the
+    # pixel): those cases bound the number of diverged pixels instead of demanding every one.
+    stochastic = any(kw.get(k, capi.kRayMarching) in (capi.kRatioTracking, capi.kResidualRatioTracking, capi.kAnalogResidualRatioTracking)
+                     for k in ("mSpatialVisibilityTrackingMethod", "mSpatialLightingTrackingMethod"))
+    checked = changed = diverged = 0
+    for k in rng.permutation(len(ys))[:12 if stochastic else 9]:
         x, y = int(xs[k]), int(ys[k])
         got = res_out[y, x]
         want = sw.spatial_reuse_pixel(frame, res_in, feat, x, y, frame_count)
-        assert int(got["lightID"]) == want["lightID"] and int(got["sampledPixel"]) == want["sampledPixel"], (x, y)
-        assert float(got["M"]) == float(want["M"]) and float(got["depth"]) == float(want["depth"]), (x, y)
-        assert np.array_equal(np.asarray(got["lightUV"], np.float32), want["lightUV"]), (x, y)
-        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=5e-5, abs=1e-12), (x, y)
-        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
+        same = (int(got["lightID"]) == want["lightID"] and int(got["sampledPixel"]) == want["sampledPixel"] and float(got["M"]) == float(want["M"])
+                and float(got["depth"]) == float(want["depth"]) and np.array_equal(np.asarray(got["lightUV"], np.float32), want["lightUV"])
+                and float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=5e-5, abs=1e-12)
+                and float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12))
+        if stochastic and not same:
+            diverged += 1
+            continue
+        assert same, (x, y, got, want)
         checked += 1
         changed += float(got["depth"]) != float(res_in[y, x]["depth"])
-    assert checked == 9 and changed >= 2                     # some pixels ended up with a neighbour's sample
+    assert checked >= 9 and diverged <= 1 and changed >= 2   # some pixels ended up with a neighbour's sample
     # a pixel whose ray misses the medium passes through
     bys, bxs = np.nonzero(feat["transmittance"] == 1.0)
     if len(bys):
@@ -82,7 +93,8 @@ def test_final_shading_matches_the_slang_witness():
 
 @pytest.mark.parametrize("kw,move", [(dict(), False), (dict(mTemporalMISMethod=capi.kMISNone, mTemporalReuseMThreshold=2.0), False), (dict(), True),
                                      (dict(mTemporalReprojectionMode=capi.kReprojectionNone), True),
-                                     (dict(mTemporalReprojectionMode=capi.kReprojectionNoBackground), True)])
+                                     (dict(mTemporalReprojectionMode=capi.kReprojectionNoBackground), True),
+                                     (dict(mSpatialVisibilityTrackingMethod=capi.kRatioTracking, mSpatialLightingTrackingMethod=capi.kResidualRatioTracking), True)])
 def test_temporal_reuse_matches_the_slang_witness(kw, move):
     """K2 on a frame with history: reprojection of the stored depth (or of a density-sampled point for a background sample) through
     the previous frame's view-projection, resampling of the history sample on the current ray, Talbot MIS between the two samples,
@@ -118,21 +130,26 @@ def test_temporal_reuse_matches_the_slang_witness(kw, move):
         ys, xs = np.nonzero(mask)
         assert len(ys) >= n
         picks += [(int(xs[k]), int(ys[k])) for k in rng.permutation(len(ys))[:n]]
-    from_history = shifted = 0
+    from_history = shifted = diverged = 0
+    stochastic = "mSpatialVisibilityTrackingMethod" in kw
     for x, y in picks:
         got = res_out[y, x]
         info = {}
         want = sw.temporal_reuse_pixel(frame, res_cur, res_prev, feat_cur, feat_prev, x, y, frame_count, prev_cam, info=info)
         assert tuple(mvec[y, x]) == tuple(float(v) for v in info["mvec"]), (x, y)          # the motion vector output
         shifted += bool(np.any(mvec[y, x] != 0))
-        assert int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"]), (x, y, got, want)
-        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
-        assert np.allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=1e-7), (x, y)
-        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=1e-4, abs=1e-12), (x, y)
-        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12), (x, y)
+        same = (int(got["lightID"]) == want["lightID"] and float(got["M"]) == float(want["M"])
+                and float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6)
+                and np.allclose(np.asarray(got["lightUV"], np.float32), want["lightUV"], rtol=0, atol=1e-7)
+                and float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=1e-4, abs=1e-12)
+                and float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=5e-5, abs=1e-12))
+        if stochastic and not same:                         # a random walk whose draw count hangs on the last bit of powf (see the spatial test)
+            diverged += 1
+            continue
+        assert same, (x, y, got, want)
         from_history += float(got["M"]) > float(res_cur[y, x]["M"])
-    assert from_history >= 8            # the history really took part
-    assert shifted >= 4 if (move and kw.get("mTemporalReprojectionMode", 0) != capi.kReprojectionNone) else shifted == 0
+    assert from_history >= 8 - diverged and diverged <= 1            # the history really took part
+    assert shifted >= 4 - diverged if (move and kw.get("mTemporalReprojectionMode", 0) != capi.kReprojectionNone) else shifted == 0
 
 
 def test_spatial_reuse_of_multi_bounce_paths_matches_the_slang_witness():
