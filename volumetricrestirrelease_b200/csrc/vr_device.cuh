@@ -787,8 +787,10 @@ struct ResidualRatioTrackingAdapter : AdapterBase {
         float currentTMax = fminf(tFar, dda.ty);
         float mu_r_temp = mu_max - mu_min;
         float D = c_scene.vol.superVoxelWorldSpaceDiagonalLength;
-        float gamma = 2;
-        float mu_c = (mu_r_temp == 0.f || useAnalogResidual) ? mu_min : fminf(mu_avg, fmaxf(mu_min, mu_min + mu_r_temp * (powf(gamma, 1.f / (D * mu_r_temp)) - 1)));
+        // gamma = 2: pow(gamma, x) through double exp2 and one rounding, i.e. correctly rounded like the host's powf.  An ulp in mu_c
+        // decides whether a collision in a saturated voxel (mu == mu_max) multiplies T_r by exactly 0 or by 6e-8, and with it whether
+        // later segments of a p-hat are evaluated and how many numbers the pixel draws - CUDA's powf is within 2 ulp
+        float mu_c = (mu_r_temp == 0.f || useAnalogResidual) ? mu_min : fminf(mu_avg, fmaxf(mu_min, mu_min + mu_r_temp * ((float)exp2((double)(1.f / (D * mu_r_temp))) - 1)));
         float mu_r = fmaxf(mu_c - mu_min, mu_max - mu_c);
         float inv_mu_r = 1.f / mu_r;
         float T_c = expf(-mu_c * fminf(tFar - t, maxDeltaT));
