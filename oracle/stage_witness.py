@@ -46,6 +46,13 @@ K_RAY_TMAX = F(3.402823466e+38)
 SELF_EMISSION = -3
 
 
+def _env(frame, direction):
+    """EnvMapSampler.eval: radiance of the env map along a direction (black without an env map)."""
+    if frame.sc.envMap is None:
+        return np.zeros(3, F)
+    return lw.env_eval(frame.sc.envMap, direction, frame.sc.envMapIntensity)
+
+
 class Frame:
     """Scene + options + camera of one frame, with the per-mip march witnesses cached."""
 
@@ -129,7 +136,7 @@ class Frame:
         o = self.origin
         if depth == K_RAY_TMAX:
             vis = self._transmittance(final, "camera", o, d, float(K_RAY_TMAX))
-            return (vis * lw.env_eval(self.sc.envMap, d, self.sc.envMapIntensity)).astype(F)
+            return (vis * _env(self, d)).astype(F)
         pw = (o + d * F(depth)).astype(F)
         density = self.wit(0).density_world(pw)
         if density == 0:
@@ -145,7 +152,7 @@ class Frame:
         zz = F(1) - light_uv[0] * light_uv[0] - light_uv[1] * light_uv[1]
         z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
         wi = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
-        Ld = lw.env_eval(self.sc.envMap, wi, self.sc.envMapIntensity) * F(lw.phase_hg(float(np.dot(-d, wi)), vol.PhaseFunctionConstantG))
+        Ld = _env(self, wi) * F(lw.phase_hg(float(np.dot(-d, wi)), vol.PhaseFunctionConstantG))
         tr = self._transmittance(final, "light", pw, wi, float(K_RAY_TMAX))
         return (Fv * (tr * Ld)).astype(F)
 
@@ -546,7 +553,7 @@ def eval_F_path(frame, d, r, extra, final=False, no_reuse=False, spatial_reuse=F
     if not bool(np.any(Fv > 0)):
         return Fv
     if background:
-        return (Fv * lw.env_eval(frame.sc.envMap, d, frame.sc.envMapIntensity)).astype(F)
+        return (Fv * _env(frame, d)).astype(F)
     emissive_path = (int(r["sampledPixel"]) >> 16) & 0xF == 1
     if no_reuse and bounces == 0 and light_id == SELF_EMISSION:
         raise NotImplementedError
@@ -618,7 +625,7 @@ def _sample_direct_lighting(frame, p, wo, rng, mips):
     u0 = rng.next1d(); u1 = rng.next1d()
     wi, pdf, _ = lw.env_sample(mips, u0, u1)
     pdf = F(F(1) * F(pdf))
-    Le = lw.env_eval(frame.sc.envMap, wi, frame.sc.envMapIntensity)
+    Le = _env(frame, wi)
     Li = (Le / pdf).astype(F) if pdf > 0 else np.zeros(3, F)
     light_id, light_uv = (-2 if wi[2] < 0 else -1), np.array([wi[0], wi[1]], dtype=F)
     if bool(np.any(np.isnan(wi))):
@@ -729,7 +736,7 @@ def _initial_path(frame, d, hd, pd, tr, rng, mips, no_reuse=False):
                     else:
                         hit_empty = True; combined["M"] = F(combined["M"] + 1)
         else:                                              # the camera ray left the volume: the background is the sample
-            Le = lw.env_eval(frame.sc.envMap, direction, frame.sc.envMapIntensity)
+            Le = _env(frame, direction)
             path_phat = F(path_phat * Tr)
             p_y = F(path_phat * lw.luminance(Le))
             out["runningSum"] = F(0) if out["p_y"] == 0 else F(p_y / out["p_y"])
@@ -852,7 +859,7 @@ def sample_scene_lights(frame, lights, p, rng, mips):
             u0 = rng.next1d(); u1 = rng.next1d()
             wi, pdf, _ = lw.env_sample(mips, u0, u1)
             pdf = F(sel[0] * F(pdf))
-            Le = lw.env_eval(frame.sc.envMap, wi, frame.sc.envMapIntensity)
+            Le = _env(frame, wi)
             return dict(valid=not bool(np.any(np.isnan(wi))), dir=wi, rayDir=wi, rayDistance=K_RAY_TMAX, pdfArea=pdf,
                         Li=(Le / pdf).astype(F) if pdf > 0 else np.zeros(3, F), lightID=-2 if wi[2] < 0 else -1, lightUV=np.array([wi[0], wi[1]], dtype=F))
         u = F(u - sel[0])
@@ -921,7 +928,7 @@ def eval_L_in_volume(frame, lights, p, wo, light_id, light_uv, final=False, tr_r
         z = np.sqrt(zz).astype(F) if zz >= 0 else F(0)
         ray_dir = np.array([light_uv[0], light_uv[1], -z if light_id == -2 else z], dtype=F)
         ray_dist = K_RAY_TMAX
-        Ld = lw.env_eval(frame.sc.envMap, ray_dir, frame.sc.envMapIntensity) * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))
+        Ld = _env(frame, ray_dir) * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))
     elif light_id < len(lights.analytic):
         ray_dir, ray_dist, Li = analytic_light_sample(lights.analytic[light_id], p)
         Ld = (Li * F(lw.phase_hg(float(np.dot(wo, ray_dir)), g))).astype(F)
@@ -1014,7 +1021,7 @@ def path_trace_pixel(frame, px, py, frame_count, importance_mips):
                             bounce = B
             else:
                 if bounce == 0:
-                    L = (L + beta * lw.env_eval(frame.sc.envMap, direction, frame.sc.envMapIntensity)).astype(F)
+                    L = (L + beta * _env(frame, direction)).astype(F)
                 bounce = B
             bounce += 1
         avg = (avg + L).astype(F)

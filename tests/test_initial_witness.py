@@ -367,3 +367,38 @@ def test_vertex_reuse_matches_the_slang_witness(B, S):
         if k >= S:
             assert float(pp[y, x]) == pytest.approx(float(want["p_partial"]), rel=2e-4, abs=1e-12), (x, y, k)
         np.testing.assert_allclose(color[y, x, :3], sw.final_shading_path(frame, x, y, dict(want), extra[y, x]), rtol=3e-4, atol=1e-9)
+
+
+def test_configuration_1_matches_the_slang_witness():
+    """BASELINE's configuration 1 as the reference runs it (64^3 sphere, one directional light, no env map, initial RIS only — so
+    gNoReuse: decomposition-tracked candidates, albedo weights): K1 reservoirs and the frame's radiance."""
+    from common import config1_params, config1_scene
+    w, h = 48, 48
+    sc = config1_scene()
+    params = config1_params(M=4)
+    op = vro.OraclePass(params)
+    op.setScene(sc, w, h)
+    color = np.zeros((h, w, 4), np.float32)
+    op.execute()
+    frame_count = op.frame_count()
+    op.execute_stage(0, 0, color); op.execute_stage(1, 0, color)
+    res = op.get_buffer(capi.BUF_RESERVOIR_0).view(RES).reshape(h, w).copy()
+    op.execute_stage(5, 0, color)
+    frame = sw.Frame(sc, params, w, h)
+    frame.lights = sw.Lights(sc)
+    rng = np.random.default_rng(19)
+    ys, xs = np.nonzero((res["runningSum"] > 0) & (res["depth"] < 1e37))
+    assert len(ys) > 100
+    lit = 0
+    for k in rng.permutation(len(ys))[:14]:
+        x, y = int(xs[k]), int(ys[k])
+        got = res[y, x]
+        want, _ = sw.initial_sampling_pixel_paths(frame, x, y, frame_count, None)
+        assert int(got["lightID"]) == want["lightID"] == 0 and float(got["M"]) == float(want["M"]) == 4.0, (x, y, got, want)
+        assert float(got["depth"]) == pytest.approx(float(want["depth"]), rel=3e-6), (x, y)
+        assert float(got["runningSum"]) == pytest.approx(float(want["runningSum"]), rel=2e-4, abs=1e-12), (x, y)
+        assert float(got["p_y"]) == pytest.approx(float(want["p_y"]), rel=1e-4, abs=1e-12), (x, y)
+        rad = sw.final_shading_path(frame, x, y, got, np.zeros((1, 3), np.float32))
+        np.testing.assert_allclose(color[y, x, :3], rad, rtol=2e-4, atol=1e-9)
+        lit += bool(rad.sum() > 0)
+    assert lit >= 8
